@@ -1,0 +1,213 @@
+/*
+ * neraf_b200.h -- C ABI of the B200-native NeRAF acoustic-field hot path.
+ *
+ * The reference (AmandineBtto/NeRAF) is pure Python/PyTorch and has no FFI of its
+ * own; this header is the boundary a maintainer binds from the nerfstudio plugin
+ * (INTEGRATION.md shows the ctypes stub).  Each entry point names the reference
+ * interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every pointer argument marked "dev" is a CUDA device pointer owned by the
+ *     caller (normally the storage of a torch tensor); the library never allocates
+ *     persistent device memory and never frees caller memory.  Scratch space is the
+ *     caller-provided `workspace` whose size comes from the matching *_sizes call.
+ *   - pointer arrays (`weights`, `biases`, ...) are HOST arrays of device pointers.
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream);
+ *     all work is enqueued on it, nothing synchronises the device.
+ *   - every function returns NERAF_OK (0) or an error code; the text of the last
+ *     error of the calling thread is available through neraf_last_error().
+ *     No C++ exception crosses this boundary.
+ *   - there is NO CPU implementation behind these symbols: without a sm_100
+ *     device they fail with NERAF_ERR_CUDA.
+ */
+#ifndef NERAF_B200_H
+#define NERAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERAF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NERAF_API __attribute__((visibility("default")))
+#else
+#define NERAF_API
+#endif
+
+typedef void* neraf_stream_t; /* cudaStream_t */
+
+enum {
+  NERAF_OK = 0,
+  NERAF_ERR_INVALID = 1,     /* bad argument (shape, alignment, null pointer) */
+  NERAF_ERR_CUDA = 2,        /* CUDA runtime/driver error, text in neraf_last_error() */
+  NERAF_ERR_UNSUPPORTED = 3, /* combination not implemented */
+  NERAF_ERR_WORKSPACE = 4    /* workspace/pack buffer too small */
+};
+
+enum { NERAF_PREC_FP32 = 0, NERAF_PREC_BF16 = 1 };
+enum { NERAF_ACT_NONE = 0, NERAF_ACT_LEAKY = 1, NERAF_ACT_TANH10 = 2 };
+enum { NERAF_CRIT_SC_SLMSE = 0, NERAF_CRIT_SC_SLL1 = 1, NERAF_CRIT_MSE = 2 };
+/* column order of the per-query encodings inside h */
+enum { NERAF_ORDER_TIME_MIC_SRC_ROT = 0, /* NeRAF_model.py:560 (after the grid block) */
+       NERAF_ORDER_MIC_SRC_TIME_ROT = 1  /* NeRAF_model.py:562 (no-grid variant)      */ };
+
+NERAF_API int neraf_version(void);
+NERAF_API const char* neraf_last_error(void);
+/* 1 when the current device is compute capability 10.x, else 0 (no error raised). */
+NERAF_API int neraf_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Acoustic field  (replaces NeRAFAudioModel.get_outputs NeRAF_model.py:531-566 and
+ * NeRAFAudioSoundField.forward NeRAF_field.py:47-65, and their autograd backward)
+ * ---------------------------------------------------------------------------------------------- */
+#define NERAF_MAX_TRUNK 8
+
+typedef struct {
+  int32_t n_grid;                 /* width of the batch-invariant block of h (1024; 0 = none)          */
+  int32_t n_enc;                  /* width of the per-query block of h (163 = 21 + 63 + 63 + 16)       */
+  int32_t n_trunk;                /* number of trunk layers (5)                                        */
+  int32_t trunk[NERAF_MAX_TRUNK]; /* trunk output widths (5096, 2048, 1024, 1024, W)                   */
+  int32_t n_channels;             /* sound_rez C: number of heads                                      */
+  int32_t n_freq;                 /* N_frequencies F: width of every head                              */
+} neraf_field_dims;
+
+/* Bytes of the packed-weight buffer and of the per-call workspace for batches up to max_batch. */
+NERAF_API int neraf_field_sizes(const neraf_field_dims* dims, int precision, int64_t max_batch,
+                      size_t* pack_bytes, size_t* workspace_bytes);
+
+/* Derive the tensor-core operand copies of the fp32 parameters (bf16, padded, plus transposes).
+ * weights[l] : dev fp32 (out,in) row-major, l = 0..n_trunk-1 trunk then n_channels heads
+ *              (state_dict order soundfield.{l}.weight, STFT_linear.{c}.weight; NeRAF_field.py:41-45)
+ * biases[l]  : dev fp32 (out).  Must be re-run whenever the parameters change.  No-op for FP32. */
+NERAF_API int neraf_field_pack(const neraf_field_dims* dims, int precision, const float* const* weights,
+                     const float* const* biases, void* pack, size_t pack_bytes, neraf_stream_t stream);
+
+typedef struct {
+  int64_t batch;                /* B: number of queries (STFT columns)                                  */
+  const int64_t* time_query;    /* dev int64 (B)      batch['time_query']  NeRAF_model.py:533          */
+  const double* mic_pose;       /* dev f64  (B,3)     batch['mic_pose']    :537                          */
+  const double* source_pose;    /* dev f64  (B,3)     batch['source_pose'] :538                          */
+  const double* rot;            /* dev f64  (B,3)     batch['rot']         :539                          */
+  const float* aabb;            /* dev f32  (2,3)     scene_box.aabb       :541                          */
+  float time_denominator;       /* float(max_len - 1) :534                                              */
+  int32_t order;                /* NERAF_ORDER_*                                                        */
+  /* If non-null the encodings above are skipped and this (B, n_enc) fp32 matrix (row stride
+   * enc_ld) is used as the per-query block of h: the dense NeRAFAudioSoundField.forward(h). */
+  const float* enc;
+  int64_t enc_ld;
+} neraf_queries;
+
+/* out: dev fp32 (B, C*F) == (B, C, F) contiguous, log-magnitude STFT columns.
+ * grid_feature: dev fp32 (n_grid) or NULL when n_grid == 0.
+ * keep != 0 stores what neraf_field_backward needs in `workspace` (training);
+ * keep == 0 is the inference path (no transposed copies). */
+NERAF_API int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
+                        const float* grid_feature, const float* const* weights,
+                        const float* const* biases, const void* pack, void* workspace,
+                        size_t workspace_bytes, float* out, int keep, neraf_stream_t stream);
+
+/* Backward of neraf_field_forward(keep=1) on the same workspace.
+ * dout, out : dev fp32 (B, C*F).   dweights[l]/dbiases[l]: dev fp32, parameter shapes, OVERWRITTEN.
+ * dgrid     : dev fp32 (n_grid) or NULL.   denc: dev fp32 (B, n_enc) row stride denc_ld, or NULL. */
+NERAF_API int neraf_field_backward(const neraf_field_dims* dims, int precision, int64_t batch, const float* dout,
+                         const float* out, const float* grid_feature, const float* const* weights,
+                         const void* pack, void* workspace, size_t workspace_bytes,
+                         float* const* dweights, float* const* dbiases, float* dgrid, float* denc,
+                         int64_t denc_ld, neraf_stream_t stream);
+
+/* Encodings only (NeRFEncoding x3 + SHEncoding + normalisation/zeroing, NeRAF_model.py:533-551):
+ * enc_out dev fp32 (B, 163) row stride ld. */
+NERAF_API int neraf_encode_queries(const neraf_queries* q, float* enc_out, int64_t ld, neraf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral loss (replaces STFTLoss.forward NeRAF_evaluator.py:88-108 + weights NeRAF_model.py:593-598)
+ * ---------------------------------------------------------------------------------------------- */
+/* sums: dev f64[4] = { S_num = sum (e^y - e^x)^2, S_den = sum (e^y - 1e-3)^2, S_sq = sum (y-x)^2,
+ *                      S_abs = sum |y-x| } over n elements; OVERWRITTEN (accumulate=0) or added to. */
+NERAF_API int neraf_spectral_loss_sums(const float* pred, const float* gt, int64_t n, double* sums, int accumulate,
+                             neraf_stream_t stream);
+/* losses: dev f32[2] = { w_sc * sqrt(S_num)/sqrt(S_den), w_mag * (S_sq or S_abs)/n_total };
+ * plain-MSE criterion: { 0, w_mag * S_sq/n_total }.  The reference weights are w_sc = 0.1*loss_factor,
+ * w_mag = loss_factor (NeRAF_model.py:597-598).  n_total is the GLOBAL element count (all DP ranks). */
+NERAF_API int neraf_spectral_loss_finalize(const double* sums, int64_t n_total, int criterion, float w_sc, float w_mag,
+                                 float* losses, neraf_stream_t stream);
+/* dpred[i] = upstream[0] * d losses[0]/d pred[i] + upstream[1] * d losses[1]/d pred[i] for the n local
+ * elements (upstream: dev f32[2], or NULL for {1, 1}). */
+NERAF_API int neraf_spectral_loss_backward(const float* pred, const float* gt, int64_t n, int64_t n_total, int criterion,
+                                 const double* sums, const float* upstream, float w_sc, float w_mag,
+                                 float* dpred, neraf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Griffin-Lim (replaces torchaudio GriffinLim as configured at NeRAF_model.py:139, used :229,:753-754,
+ * and the log->magnitude conversion :746-747)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_fft;        /* (N_freq_stft - 1) * 2, power of two in [64, 2048]                         */
+  int32_t win_length;   /* hann(win_length, periodic) centred in n_fft                               */
+  int32_t hop;          /* hop_length                                                                 */
+  int32_t n_frames;     /* T                                                                          */
+  int32_t n_iter;       /* 32                                                                         */
+  float momentum;       /* 0.99 (the 1/(1+m) rescale of torchaudio is applied inside)                 */
+  int32_t input_is_log; /* 1: spec holds log-magnitudes, convert with clip(exp(x) - 1e-3, 0, 1e4)     */
+} neraf_gl_params;
+
+NERAF_API int neraf_griffinlim_sizes(const neraf_gl_params* p, int64_t n_signals, size_t* workspace_bytes);
+
+/* Signals are indexed (item n, channel c), n < n_items, c < n_channels.
+ * spec       : dev fp32, element (n, c, frame t, bin f) at
+ *              spec[n*stride_n + c*stride_c + t*stride_t + f*stride_f]
+ *              (torchaudio layout (N, C, F, T): stride_f = T, stride_t = 1; field layout (N, T, C, F):
+ *              stride_n = T*C*F, stride_t = C*F, stride_c = F, stride_f = 1).
+ * init_phase : dev fp32 interleaved complex with the same logical indexing (strides in complex
+ *              elements), or NULL for an all-ones start (rand_init=False).
+ * wave       : dev fp32 (n_items, n_channels, hop*(n_frames-1)) contiguous. */
+NERAF_API int neraf_griffinlim(const neraf_gl_params* p, int64_t n_items, int32_t n_channels, const float* spec,
+                     int64_t stride_n, int64_t stride_c, int64_t stride_t, int64_t stride_f,
+                     const float* init_phase, int64_t init_stride_n, int64_t init_stride_c,
+                     int64_t init_stride_t, int64_t init_stride_f, void* workspace, size_t workspace_bytes,
+                     float* wave, neraf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator-level entry points (used by the dense module path and by the parity tests)
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 CUDA-core GEMM:  C[m,n] (+)= act( sum_k A[m*a_rs + k*a_cs] * B[n*b_rs + k*b_cs] + bias[n] ) * gate'
+ * gate (optional, (M,N) row stride ldg): multiply by 1 where gate > 0 else 0.1 (LeakyReLU backward). */
+NERAF_API int neraf_gemm_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t a_rs, int64_t a_cs,
+                   const float* B, int64_t b_rs, int64_t b_cs, const float* bias, int act,
+                   const float* gate, int64_t ldg, float* C, int64_t ldc, int accumulate,
+                   neraf_stream_t stream);
+
+/* bf16 tcgen05 GEMM: D[M,N] = A[M,K] * B[N,K]^T, A and B bf16 K-major (row strides lda/ldb, multiples
+ * of 8 elements, 16-byte aligned bases), fp32 accumulation in TMEM, fused epilogue.
+ * Outputs (any subset): out_bf16 (M,N) row stride ld_bf16; out_bf16_t (N,M) row stride ld_t;
+ * out_f32 (M,N) row stride ld_f32 (accumulate_f32: add instead of overwrite). */
+typedef struct {
+  const float* bias;       /* (N) or NULL                                     */
+  int32_t act;             /* NERAF_ACT_*                                     */
+  const void* gate;        /* bf16 (M,N) row stride ldg or NULL               */
+  int64_t ldg;
+  void* out_bf16;
+  int64_t ld_bf16;
+  void* out_bf16_t;
+  int64_t ld_t;
+  float* out_f32;
+  int64_t ld_f32;
+  int32_t accumulate_f32;
+} neraf_gemm_epilogue;
+
+NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
+                    const neraf_gemm_epilogue* epi, neraf_stream_t stream);
+
+/* fp32 (rows, cols) row stride ld_in  ->  bf16 (rows, cols) row stride ld_out (and/or its transpose
+ * (cols, rows) row stride ld_t).  Either output may be NULL. */
+NERAF_API int neraf_convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                       void* out_t, int64_t ld_t, neraf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERAF_B200_H */

@@ -1,0 +1,136 @@
+"""ctypes binding of the C ABI in include/neraf_b200.h.
+
+This is the only place the shared library is opened.  There is deliberately no
+fallback: if ``neraf_b200/lib/libneraf_b200.so`` is missing or no sm_100 device
+is present, every product entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional, Sequence
+
+import torch
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libneraf_b200.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+ACT_NONE, ACT_LEAKY, ACT_TANH10 = 0, 1, 2
+CRIT_SC_SLMSE, CRIT_SC_SLL1, CRIT_MSE = 0, 1, 2
+ORDER_TIME_MIC_SRC_ROT, ORDER_MIC_SRC_TIME_ROT = 0, 1
+MAX_TRUNK = 8
+
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+CRITERIA = {"SC+SLMSE": CRIT_SC_SLMSE, "SC+SLL1": CRIT_SC_SLL1, "MSE": CRIT_MSE}
+
+
+class NerafError(RuntimeError):
+    """Non-zero status from the CUDA library (text from neraf_last_error())."""
+
+
+class FieldDims(C.Structure):
+    _fields_ = [("n_grid", C.c_int32), ("n_enc", C.c_int32), ("n_trunk", C.c_int32),
+                ("trunk", C.c_int32 * MAX_TRUNK), ("n_channels", C.c_int32), ("n_freq", C.c_int32)]
+
+
+class Queries(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("time_query", C.c_void_p), ("mic_pose", C.c_void_p),
+                ("source_pose", C.c_void_p), ("rot", C.c_void_p), ("aabb", C.c_void_p),
+                ("time_denominator", C.c_float), ("order", C.c_int32), ("enc", C.c_void_p), ("enc_ld", C.c_int64)]
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("gate", C.c_void_p), ("ldg", C.c_int64),
+                ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64), ("out_bf16_t", C.c_void_p), ("ld_t", C.c_int64),
+                ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("accumulate_f32", C.c_int32)]
+
+
+class GlParams(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop", C.c_int32), ("n_frames", C.c_int32),
+                ("n_iter", C.c_int32), ("momentum", C.c_float), ("input_is_log", C.c_int32)]
+
+
+_vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol declared in include/neraf_b200.h
+SIGNATURES = {
+    "neraf_version": (C.c_int, []),
+    "neraf_last_error": (C.c_char_p, []),
+    "neraf_device_supported": (C.c_int, []),
+    "neraf_field_sizes": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, C.POINTER(_sz), C.POINTER(_sz)]),
+    "neraf_field_pack": (C.c_int, [C.POINTER(FieldDims), _i32, _pp, _pp, _vp, _sz, _vp]),
+    "neraf_field_forward": (C.c_int, [C.POINTER(FieldDims), _i32, C.POINTER(Queries), _vp, _pp, _pp, _vp, _vp, _sz,
+                                       _vp, _i32, _vp]),
+    "neraf_field_backward": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
+                                        _vp, _vp, _i64, _vp]),
+    "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),
+    "neraf_spectral_loss_sums": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
+    "neraf_spectral_loss_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp]),
+    "neraf_spectral_loss_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp]),
+    "neraf_griffinlim_sizes": (C.c_int, [C.POINTER(GlParams), _i64, C.POINTER(_sz)]),
+    "neraf_griffinlim": (C.c_int, [C.POINTER(GlParams), _i64, _i32, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
+                                    _i64, _vp, _sz, _vp, _vp]),
+    "neraf_gemm_f32": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _i64,
+                                  _i32, _vp]),
+    "neraf_gemm_bf16": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(GemmEpilogue), _vp]),
+    "neraf_convert_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library (opened once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NerafError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(or `make -C neraf_b200/csrc`). neraf_b200 has no CPU fallback.")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise NerafError(f"neraf_b200 error {rc}: {lib().neraf_last_error().decode(errors='replace')}")
+
+
+def require_device(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise NerafError(f"{what} must live on a CUDA device (got {t.device}); neraf_b200 has no CPU path")
+
+
+def stream_ptr(device: Optional[torch.device] = None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def make_dims(n_grid: int, n_enc: int, trunk: Sequence[int], n_channels: int, n_freq: int) -> FieldDims:
+    if len(trunk) > MAX_TRUNK:
+        raise ValueError(f"at most {MAX_TRUNK} trunk layers")
+    d = FieldDims()
+    d.n_grid, d.n_enc, d.n_trunk, d.n_channels, d.n_freq = n_grid, n_enc, len(trunk), n_channels, n_freq
+    for i, w in enumerate(trunk):
+        d.trunk[i] = w
+    return d

@@ -1,0 +1,230 @@
+// Small HBM-bound helpers around the GEMMs of the acoustic field:
+//  * fp32 -> bf16 operand copies (row-major and transposed) for the tcgen05 path,
+//  * the batch-invariant grid-feature block of layer 1 hoisted out of the batch
+//    (NeRAF_model.py:557-560 expands the same 1024 values to every row):
+//    forward mat-vec, its gradient w.r.t. the grid feature and the rank-1 weight gradient,
+//  * bias gradients (column sums), and the gradient through the 10*tanh heads (NeRAF_field.py:57-58).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace neraf {
+
+// ---------------------------------------------------------------------------------------------
+// fp32 (rows, cols) -> bf16 (rows, cols) and/or bf16 (cols, rows)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restrict__ in, int64_t rows, int64_t cols,
+                                                           int64_t ld_in, __nv_bfloat16* __restrict__ out,
+                                                           int64_t ld_out, __nv_bfloat16* __restrict__ out_t,
+                                                           int64_t ld_t) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + i * 8, c = c0 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = __ldg(in + r * ld_in + c);
+      if (out) out[r * ld_out + c] = __float2bfloat16_rn(v);
+    }
+    tile[ty + i * 8][tx] = v;
+  }
+  if (!out_t) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < rows && c < cols) out_t[c * ld_t + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+  }
+}
+
+int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out, void* out_t,
+                 int64_t ld_t, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return NERAF_OK;
+  NERAF_REQUIRE(in && (out || out_t), "convert_bf16: null pointer");
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+  NERAF_REQUIRE(grid.y <= 65535, "convert_bf16: too many rows for one launch (%lld)", (long long)rows);
+  convert_bf16_kernel<<<grid, 256, 0, stream>>>(in, rows, cols, ld_in, (__nv_bfloat16*)out, ld_out,
+                                                (__nv_bfloat16*)out_t, ld_t);
+  NERAF_CHECK_LAUNCH("convert_bf16_kernel");
+  return NERAF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// y[n] = bias[n] + W[n, :K] . g       (one warp per output row, float4 loads when aligned)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_bias_kernel(const float* __restrict__ W, int64_t ldw,
+                                                        const float* __restrict__ bias, const float* __restrict__ g,
+                                                        int64_t N, int64_t K, float* __restrict__ y) {
+  const int64_t n = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (n >= N) return;
+  const float* w = W + n * ldw;
+  float acc = 0.f;
+  for (int64_t k = lane; k < K; k += 32) acc = fmaf(__ldg(w + k), __ldg(g + k), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[n] = acc + (bias ? bias[n] : 0.f);
+}
+
+int grid_bias(const float* W, int64_t ldw, const float* bias, const float* g, int64_t N, int64_t K, float* y,
+              cudaStream_t stream) {
+  if (N <= 0) return NERAF_OK;
+  grid_bias_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, stream>>>(W, ldw, bias, g, N, K, y);
+  NERAF_CHECK_LAUNCH("grid_bias_kernel");
+  return NERAF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[k] = sum_n W[n, k] * s[n]       (block: 32 columns x 32 row lanes, deterministic)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) grid_backward_kernel(const float* __restrict__ W, int64_t ldw,
+                                                             const float* __restrict__ s, int64_t N, int64_t K,
+                                                             float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int kx = threadIdx.x % 32, ny = threadIdx.x / 32;
+  const int64_t k = (int64_t)blockIdx.x * 32 + kx;
+  float acc = 0.f;
+  if (k < K)
+    for (int64_t n = ny; n < N; n += 32) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
+  red[ny][kx] = acc;
+  __syncthreads();
+  if (ny == 0 && k < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][kx];
+    out[k] = t;
+  }
+}
+
+int grid_backward(const float* W, int64_t ldw, const float* s, int64_t N, int64_t K, float* out, cudaStream_t stream) {
+  if (K <= 0) return NERAF_OK;
+  grid_backward_kernel<<<(unsigned)ceil_div(K, 32), 1024, 0, stream>>>(W, ldw, s, N, K, out);
+  NERAF_CHECK_LAUNCH("grid_backward_kernel");
+  return NERAF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW[n, k] = s[n] * g[k]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) outer_product_kernel(const float* __restrict__ s, const float* __restrict__ g,
+                                                            int64_t N, int64_t K, float* __restrict__ dW, int64_t ldw) {
+  const int64_t n = blockIdx.x;
+  const float sn = __ldg(s + n);
+  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) dW[n * ldw + k] = sn * __ldg(g + k);
+}
+
+int outer_product(const float* s, const float* g, int64_t N, int64_t K, float* dW, int64_t ldw, cudaStream_t stream) {
+  if (N <= 0 || K <= 0) return NERAF_OK;
+  outer_product_kernel<<<(unsigned)N, 256, 0, stream>>>(s, g, N, K, dW, ldw);
+  NERAF_CHECK_LAUNCH("outer_product_kernel");
+  return NERAF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column sums (bias gradients)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) colsum_f32_kernel(const float* __restrict__ X, int64_t M, int64_t N, int64_t ld,
+                                                          float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int nx = threadIdx.x % 32, my = threadIdx.x / 32;
+  const int64_t n = (int64_t)blockIdx.x * 32 + nx;
+  float acc = 0.f;
+  if (n < N)
+    for (int64_t m = my; m < M; m += 32) acc += __ldg(X + m * ld + n);
+  red[my][nx] = acc;
+  __syncthreads();
+  if (my == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][nx];
+    out[n] = t;
+  }
+}
+
+int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream) {
+  if (N <= 0) return NERAF_OK;
+  colsum_f32_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, stream>>>(X, M, N, ld, out);
+  NERAF_CHECK_LAUNCH("colsum_f32_kernel");
+  return NERAF_OK;
+}
+
+__global__ void __launch_bounds__(256) rowsum_bf16_kernel(const __nv_bfloat16* __restrict__ Xt, int64_t N, int64_t M,
+                                                          int64_t ld, float* __restrict__ out) {
+  const int64_t n = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (n >= N) return;
+  const __nv_bfloat16* row = Xt + n * ld;
+  float acc = 0.f;
+  const int64_t M8 = (ld % 8 == 0) ? (M / 8) * 8 : 0;       // 16-byte vector part (rows are 16 B aligned when ld % 8 == 0)
+  for (int64_t m = lane * 8; m < M8; m += 256) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + m));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      acc += f.x + f.y;
+    }
+  }
+  for (int64_t m = M8 + lane; m < M; m += 32) acc += __bfloat162float(row[m]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[n] = acc;
+}
+
+int rowsum_bf16(const void* Xt, int64_t N, int64_t M, int64_t ld, float* out, cudaStream_t stream) {
+  if (N <= 0) return NERAF_OK;
+  rowsum_bf16_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, stream>>>((const __nv_bfloat16*)Xt, N, M, ld, out);
+  NERAF_CHECK_LAUNCH("rowsum_bf16_kernel");
+  return NERAF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradient through y = 10*tanh(z):  dz = dout * (10 - y*y/10)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                                            int64_t M, int64_t N, float* __restrict__ dz_f32,
+                                                            int64_t ld_f32, __nv_bfloat16* __restrict__ dz_bf16,
+                                                            int64_t ld_bf16, __nv_bfloat16* __restrict__ dz_bf16_t,
+                                                            int64_t ld_t) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + i * 8, c = c0 + tx;
+    float v = 0.f;
+    if (r < M && c < N) {
+      const float yy = __ldg(y + r * N + c);
+      v = __ldg(dout + r * N + c) * (10.f - yy * yy * 0.1f);
+      if (dz_f32) dz_f32[r * ld_f32 + c] = v;
+      if (dz_bf16) dz_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(v);
+    }
+    tile[ty + i * 8][tx] = v;
+  }
+  if (!dz_bf16_t) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < M && c < N) dz_bf16_t[c * ld_t + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+  }
+}
+
+int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
+                  int64_t ld_bf16, void* dz_bf16_t, int64_t ld_t, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return NERAF_OK;
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
+  NERAF_REQUIRE(grid.y <= 65535, "head_backward: batch too large for one launch (%lld)", (long long)M);
+  head_backward_kernel<<<grid, 256, 0, stream>>>(dout, y, M, N, dz_f32, ld_f32, (__nv_bfloat16*)dz_bf16, ld_bf16,
+                                                 (__nv_bfloat16*)dz_bf16_t, ld_t);
+  NERAF_CHECK_LAUNCH("head_backward_kernel");
+  return NERAF_OK;
+}
+
+}  // namespace neraf
+
+extern "C" int neraf_convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                                  void* out_t, int64_t ld_t, neraf_stream_t stream) {
+  return neraf::convert_bf16(in, rows, cols, ld_in, out, ld_out, out_t, ld_t, (cudaStream_t)stream);
+}

@@ -1,0 +1,489 @@
+// bf16 tensor-core GEMM for the acoustic-field MLP on sm_100a: tcgen05.mma with fp32 accumulators in
+// TMEM, operands streamed by TMA (128-byte swizzle) through an mbarrier ring, fused epilogue.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T        A, B bf16, K-major (row-major with the contraction innermost)
+//
+// Every Linear / dgrad / wgrad of NeRAF_field.py:47-65 is expressed in this one TN form by keeping
+// a transposed bf16 copy of each activation / activation-gradient / weight (written by the epilogue of
+// the producing GEMM, so no separate transpose pass):
+//   forward   X_l  = act(X_{l-1} W_l^T + b_l)         A = X_{l-1} (B,K)      B = W_l   (N,K)
+//   dgrad     dZ_l = (dZ_{l+1} W_{l+1}) * leaky'(X_l) A = dZ_{l+1} (B,N')    B = W_{l+1}^T (N,N')
+//   wgrad     dW_l = dZ_l^T X_{l-1}                   A = dZ_l^T (N,B)       B = X_{l-1}^T (K,B)
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer      (one elected lane; cp.async.bulk.tensor.2d -> smem ring, expect_tx)
+//   warp 1      MMA issuer        (one elected lane; tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16;
+//                                  tcgen05.commit releases smem slots and publishes the accumulator)
+//   warps 2-5   epilogue          (tcgen05.ld 32x32b.x32 -> bias / LeakyReLU / 10*tanh / LeakyReLU' gate ->
+//                                  bf16 row-major, bf16 transposed and/or fp32 stores; smem-staged so that
+//                                  row-major stores are coalesced)
+// TMEM holds two BN-column accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace neraf {
+
+namespace umma {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                 // 64 bf16 = 128 bytes = one swizzle-128B atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+constexpr int STAGE_PITCH = 33;             // floats per staged row (+1: bank-conflict-free transpose)
+constexpr long long WATCHDOG_CYCLES = 4000000000LL;   // ~2 s: a lost mbarrier traps instead of hanging the GPU
+
+struct Params {
+  int M, N, K;
+  const float* bias;
+  int act;
+  const __nv_bfloat16* gate; long long ldg;
+  __nv_bfloat16* out_bf16; long long ld_bf16;
+  __nv_bfloat16* out_bf16_t; long long ld_t;
+  float* out_f32; long long ld_f32;
+  int accumulate_f32;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major, canonical value 1) in [16,30),
+// SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+template <int BN>
+struct Config {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = 4 * 32 * STAGE_PITCH * 4;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using Cfg = Config<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::STAGES * Cfg::A_BYTES;
+  float* stage_buf = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_buf) + Cfg::EPI_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile % num_m, nt = tile / num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
+          tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmA, full_bar + stage, kb * BLOCK_K, mt * BLOCK_M);
+          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, full_bar + stage, kb * BLOCK_K, nt * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tmem_empty + as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance both descriptors by 16 bf16 = 32 B inside the 128 B swizzle row (encoded >> 4)
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar + stage);        // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full + as);             // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    float* sbuf = stage_buf + (warp - EPI_WARP0) * 32 * STAGE_PITCH;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile % num_m, nt = tile / num_m;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tmem_full + as, aphase);
+      tc_fence_after();
+      const int m_base = mt * BLOCK_M + quarter * 32;
+      const int m = m_base + lane;
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = nt * BN + c * 32;
+        if (n0 >= p.N) break;
+        float v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+        const bool full_chunk = n0 + 32 <= p.N;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (full_chunk || n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        }
+        if (p.act != NERAF_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+        if (p.gate && row_ok) {
+          const __nv_bfloat16* g = p.gate + (long long)m * p.ldg + n0;
+          if (full_chunk && (p.ldg % 8 == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 raw = __ldg(reinterpret_cast<const uint4*>(g) + q);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[q * 8 + e * 2] *= f.x > 0.f ? 1.f : kLeakySlope;
+                v[q * 8 + e * 2 + 1] *= f.y > 0.f ? 1.f : kLeakySlope;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] *= __bfloat162float(g[j]) > 0.f ? 1.f : kLeakySlope;
+          }
+        }
+        if (p.out_bf16_t && row_ok) {
+          // lanes hold consecutive m: each store instruction writes 64 contiguous bytes
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full_chunk || n0 + j < p.N) p.out_bf16_t[(long long)(n0 + j) * p.ld_t + m] = __float2bfloat16_rn(v[j]);
+        }
+        if (p.out_bf16 || p.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sbuf[lane * STAGE_PITCH + j] = v[j];
+          __syncwarp();
+          if (p.out_f32) {
+            const int n = n0 + lane;
+            if (n < p.N) {
+#pragma unroll 4
+              for (int r = 0; r < 32; ++r) {
+                const int mm = m_base + r;
+                if (mm >= p.M) break;
+                float* dst = p.out_f32 + (long long)mm * p.ld_f32 + n;
+                const float val = sbuf[r * STAGE_PITCH + lane];
+                *dst = p.accumulate_f32 ? *dst + val : val;
+              }
+            }
+          }
+          if (p.out_bf16) {
+            const int c0 = (lane & 3) * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2);
+              const int mm = m_base + r;
+              if (mm < p.M) {
+                const float* s = sbuf + r * STAGE_PITCH + c0;
+                __nv_bfloat16* dst = p.out_bf16 + (long long)mm * p.ld_bf16 + n0 + c0;
+                if (n0 + c0 + 8 <= p.N) {
+                  uint4 pk;
+                  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(s[2 * e], s[2 * e + 1]);
+                  *reinterpret_cast<uint4*>(dst) = pk;
+                } else {
+                  for (int e = 0; e < 8; ++e)
+                    if (n0 + c0 + e < p.N) dst[e] = __float2bfloat16_rn(s[e]);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int64_t rows, cols, ld; int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.rows;
+    h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)k.box_rows;
+    return h;
+  }
+};
+
+// (rows, cols) bf16 matrix with row stride ld elements; box = box_rows x 64 columns, 128-byte swizzle,
+// out-of-bounds elements read as zero (this is what pads K, M and N tails).
+static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return NERAF_OK; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(NERAF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  CUtensorMap tm;
+  const CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(NERAF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld x %lld ld %lld box %d", (int)r,
+                     (long long)rows, (long long)cols, (long long)ld, box_rows);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache[key] = tm;
+  }
+  *out = tm;
+  return NERAF_OK;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+  using Cfg = Config<BN>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  NERAF_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  const int num_tiles = (int)(ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BN));
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  umma_gemm_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  NERAF_CHECK_LAUNCH("umma_gemm_kernel");
+  return NERAF_OK;
+}
+
+}  // namespace umma
+
+int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
+              const neraf_gemm_epilogue* e, cudaStream_t stream) {
+  using namespace umma;
+  if (M <= 0 || N <= 0) return NERAF_OK;
+  NERAF_REQUIRE(A && B && e && K > 0, "gemm_bf16: null operand or K <= 0");
+  NERAF_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm_bf16: dimension overflow");
+  NERAF_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K,
+                "gemm_bf16: operand row strides must be multiples of 8 elements and >= K (lda %lld ldb %lld K %lld)",
+                (long long)lda, (long long)ldb, (long long)K);
+  NERAF_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, "gemm_bf16: operands must be 16-byte aligned");
+  NERAF_REQUIRE(e->out_bf16 || e->out_bf16_t || e->out_f32, "gemm_bf16: no output requested");
+  if (e->out_bf16)
+    NERAF_REQUIRE(e->ld_bf16 % 8 == 0 && ((uintptr_t)e->out_bf16 % 16) == 0 && e->ld_bf16 >= N,
+                  "gemm_bf16: out_bf16 needs ld %% 8 == 0, ld >= N and 16-byte alignment");
+  if (e->out_bf16_t) NERAF_REQUIRE(e->ld_t >= M, "gemm_bf16: out_bf16_t row stride < M");
+  if (e->out_f32) NERAF_REQUIRE(e->ld_f32 >= N, "gemm_bf16: out_f32 row stride < N");
+  NERAF_REQUIRE(e->act >= 0 && e->act <= 2, "gemm_bf16: unknown activation %d", e->act);
+
+  Params p;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.bias = e->bias; p.act = e->act;
+  p.gate = (const __nv_bfloat16*)e->gate; p.ldg = e->ldg;
+  p.out_bf16 = (__nv_bfloat16*)e->out_bf16; p.ld_bf16 = e->ld_bf16;
+  p.out_bf16_t = (__nv_bfloat16*)e->out_bf16_t; p.ld_t = e->ld_t;
+  p.out_f32 = e->out_f32; p.ld_f32 = e->ld_f32;
+  p.accumulate_f32 = e->accumulate_f32;
+
+  // Tile width: 256 when that still yields at least one full wave of tiles, otherwise narrower tiles
+  // to keep more SMs busy (the MLP's small layers at batch 2048 have few output tiles).
+  const int64_t mt = ceil_div(M, BLOCK_M);
+  const int sms = sm_count();
+  int bn = 256;
+  if (mt * ceil_div(N, 256) < sms) bn = 128;
+  if (bn == 128 && mt * ceil_div(N, 128) < sms / 2) bn = 64;
+
+  CUtensorMap tmA, tmB;
+  NERAF_TRY(get_tensor_map(A, M, K, lda, BLOCK_M, &tmA));
+  NERAF_TRY(get_tensor_map(B, N, K, ldb, bn, &tmB));
+  if (bn == 256) return launch<256>(tmA, tmB, p, stream);
+  if (bn == 128) return launch<128>(tmA, tmB, p, stream);
+  return launch<64>(tmA, tmB, p, stream);
+}
+
+}  // namespace neraf
+
+extern "C" int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
+                               const neraf_gemm_epilogue* epi, neraf_stream_t stream) {
+  return neraf::gemm_bf16(M, N, K, A, lda, B, ldb, epi, (cudaStream_t)stream);
+}

@@ -1,0 +1,176 @@
+"""GPU parity tests of the acoustic field (forward, backward, loss) against the oracle and the golden
+vectors produced by the reference's own classes.
+
+Tolerances (BASELINE.json north_star; scale-relative as argued in SURVEY.md section 7):
+  fp32 path: outputs 1e-5 (max-norm and Frobenius), losses 1e-5, parameter gradients 1e-4
+  bf16 path: outputs 1e-2, losses 1e-2, parameter gradients 3e-2
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neraf_b200 import _lib
+from neraf_b200 import synthetic as syn
+from neraf_b200.field import NeRAFAudioSoundField
+from neraf_b200.loss import spectral_loss
+from oracle import encodings as oenc
+from oracle import field as ofield
+from oracle import loss as oloss
+from tests.util import cuda, rel_fro, rel_max
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": dict(y=1e-5, loss=1e-5, grad=1e-4), "bf16": dict(y=1e-2, loss=1e-2, grad=3e-2)}
+
+
+def _make_field(shape, sd, prec, dev):
+    f = NeRAFAudioSoundField(1187, 512, sound_rez=shape.C, N_frequencies=shape.F, precision=prec)
+    f.load_state_dict(sd)
+    return f.to(dev)
+
+
+def _oracle_step(shape, sd, batch, g):
+    enc = oenc.encode_queries(batch, syn.default_aabb(), shape.T)
+    y, acts = ofield.field_forward_factored(sd, enc, g, torch.float64, keep=True)
+    ld = oloss.loss_dict(y, batch["data"])
+    dy = oloss.loss_grad(y, batch["data"])
+    grads, dgrid = ofield.field_backward(sd, acts, g, y, dy)
+    return y, ld, dy, grads, dgrid
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape,B", [(syn.RAF, 200), (syn.SOUNDSPACES, 136), (syn.RAF, 1)])
+def test_train_step_matches_oracle(prec, shape, B):
+    dev = cuda()
+    sd = syn.make_state_dict(shape, seed=2)
+    batch = syn.make_batch(shape, B, seed=2, outside_frac=0.02)
+    g = syn.make_grid_feature(2)
+    y_ref, ld_ref, dy_ref, grads_ref, dgrid_ref = _oracle_step(shape, sd, batch, g)
+
+    field = _make_field(shape, sd, prec, dev)
+    gd = g.to(dev).requires_grad_(True)
+    y = field.forward_queries(batch["time_query"], batch["mic_pose"], batch["source_pose"], batch["rot"],
+                              syn.default_aabb().to(dev), shape.T, gd)
+    assert y.shape == (B, shape.C, shape.F) and y.dtype == torch.float32
+    sc, mag = spectral_loss(y, batch["data"].to(dev), "SC+SLMSE", 0.1 * 1e-3, 1e-3)
+    (sc + mag).backward()
+    t = TOL[prec]
+    assert rel_fro(y, y_ref) < t["y"] and rel_max(y, y_ref) < t["y"]
+    assert abs(float(sc) - float(ld_ref["audio_sc_loss"])) < t["loss"] * float(ld_ref["audio_sc_loss"])
+    assert abs(float(mag) - float(ld_ref["audio_mag_loss"])) < t["loss"] * float(ld_ref["audio_mag_loss"])
+    assert rel_fro(gd.grad, dgrid_ref) < t["grad"]
+    for name, p in field.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, name
+        assert rel_fro(p.grad, grads_ref[name]) < t["grad"], name
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["RAF", "SoundSpaces"])
+def test_against_reference_golden(golden_dir, prec, name):
+    """Same weights / inputs as oracle/make_golden.py fed to the reference's own NeRAFAudioSoundField + STFTLoss."""
+    dev = cuda()
+    gold = np.load(os.path.join(golden_dir, f"field_{name}.npz"))
+    B, seed, C, F, T = [int(v) for v in gold["meta"]]
+    shape = syn.RAF if name == "RAF" else syn.SOUNDSPACES
+    sd = syn.make_state_dict(shape, seed=seed)
+    batch = syn.make_batch(shape, B, seed=seed)
+    g = syn.make_grid_feature(seed)
+    field = _make_field(shape, sd, prec, dev)
+    gd = g.to(dev).requires_grad_(True)
+    y = field.forward_queries(batch["time_query"], batch["mic_pose"], batch["source_pose"], batch["rot"],
+                              syn.default_aabb().to(dev), T, gd)
+    sc, mag = spectral_loss(y, batch["data"].to(dev), "SC+SLMSE", 0.1 * 1e-3, 1e-3)
+    (sc + mag).backward()
+    t = TOL[prec]
+    assert rel_fro(y, gold["y_f64"]) < t["y"] and rel_max(y, gold["y_f64"]) < t["y"]
+    assert abs(float(sc) / 1e-4 - float(gold["sc_f64"])) < t["loss"] * float(gold["sc_f64"])
+    assert abs(float(mag) / 1e-3 - float(gold["mag_f64"])) < t["loss"] * float(gold["mag_f64"])
+    assert rel_fro(gd.grad, gold["dgrid_f64"]) < t["grad"]
+    for pname, p in field.named_parameters():
+        gn = float(gold[f"gnorm_f64:{pname}"])
+        assert abs(float(p.grad.double().norm()) - gn) < t["grad"] * gn, pname
+        if p.dim() == 2:
+            assert rel_fro(p.grad[:4, -8:], gold[f"gslice_f64:{pname}"]) < 3 * t["grad"], pname
+        else:
+            assert rel_fro(p.grad[:16], gold[f"gslice_f64:{pname}"]) < 3 * t["grad"], pname
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_dense_forward_is_reference_signature(prec):
+    """field.forward(h) on an arbitrary (B, 1187) input, incl. d/dh (NeRAF_field.py:47-65)."""
+    dev = cuda()
+    shape = syn.SOUNDSPACES
+    sd = syn.make_state_dict(shape, seed=4)
+    field = _make_field(shape, sd, prec, dev)
+    g = torch.Generator().manual_seed(4)
+    h = torch.randn(50, 1187, generator=g) * 0.5
+    hd = h.to(dev).requires_grad_(True)
+    y = field(hd)
+    w = torch.randn(50, shape.C, shape.F, generator=g)
+    (y * w.to(dev)).sum().backward()
+    h64 = h.double().requires_grad_(True)
+    y_ref = ofield.field_forward(sd, h64, torch.float64)
+    (y_ref * w.double()).sum().backward()
+    t = TOL[prec]
+    assert rel_fro(y, y_ref) < t["y"]
+    assert rel_fro(hd.grad, h64.grad) < t["grad"]
+
+
+def test_no_grid_variant_uses_other_column_order():
+    dev = cuda()
+    shape = syn.RAF
+    f = NeRAFAudioSoundField(163, 512, sound_rez=1, N_frequencies=513, precision="fp32").to(dev)
+    batch = syn.make_batch(shape, 40, seed=9)
+    y = f.forward_queries(batch["time_query"], batch["mic_pose"], batch["source_pose"], batch["rot"],
+                          syn.default_aabb().to(dev), shape.T, None, order=_lib.ORDER_MIC_SRC_TIME_ROT)
+    h = oenc.assemble_input(batch, syn.default_aabb(), shape.T, None)
+    sd = {k: v.detach().cpu() for k, v in f.state_dict().items()}
+    assert rel_fro(y, ofield.field_forward(sd, h, torch.float64)) < 1e-5
+
+
+def test_inference_path_and_pack_refresh():
+    """no_grad forward (keep=0) equals the training forward; an in-place parameter update invalidates the bf16 pack."""
+    dev = cuda()
+    shape = syn.RAF
+    sd = syn.make_state_dict(shape, seed=6)
+    field = _make_field(shape, sd, "bf16", dev)
+    batch = syn.make_batch(shape, 64, seed=6)
+    g = syn.make_grid_feature(6).to(dev)
+    args = (batch["time_query"], batch["mic_pose"], batch["source_pose"], batch["rot"], syn.default_aabb().to(dev), shape.T, g)
+    y_train = field.forward_queries(*args)
+    with torch.no_grad():
+        y_inf = field.forward_queries(*args)
+        assert torch.equal(y_train.detach(), y_inf)
+        field.STFT_linear[0].bias.add_(1.0)
+        y_new = field.forward_queries(*args)
+    assert float((y_new - y_inf).abs().max()) > 1e-3
+
+
+def test_full_size_batch_properties():
+    """BASELINE size (B=2048): row independence -- any slice of the batch gives the same rows; finite grads."""
+    dev = cuda()
+    shape = syn.RAF
+    sd = syn.make_state_dict(shape, seed=0)
+    field = _make_field(shape, sd, "bf16", dev)
+    batch = syn.make_batch(shape, 2048, seed=0)
+    g = syn.make_grid_feature(0).to(dev).requires_grad_(True)
+    aabb = syn.default_aabb().to(dev)
+    y = field.forward_queries(batch["time_query"], batch["mic_pose"], batch["source_pose"], batch["rot"], aabb, shape.T, g)
+    sl = slice(777, 777 + 130)
+    with torch.no_grad():
+        y_sl = field.forward_queries(batch["time_query"][sl], batch["mic_pose"][sl], batch["source_pose"][sl],
+                                     batch["rot"][sl], aabb, shape.T, g)
+    assert torch.equal(y[sl].detach(), y_sl)
+    sc, mag = spectral_loss(y, batch["data"].to(dev), "SC+SLMSE", 1e-4, 1e-3)
+    (sc + mag).backward()
+    for p in field.parameters():
+        assert torch.isfinite(p.grad).all()
+    assert float(y.abs().max()) <= 10.0
+
+
+def test_cpu_parameters_fail_loudly():
+    f = NeRAFAudioSoundField(1187, 512, 1, 513)
+    with pytest.raises(_lib.NerafError):
+        f(torch.zeros(2, 1187))
