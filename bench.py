@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the acoustic-field hot path (BASELINE.json metric: STFT columns/s train fwd+bwd, RIRs/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA library)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU torch path (oracle port)
+
+One "step" = one pass of the hot path over one synthetic RAF-FurnishedRoom-shaped batch of 2048 STFT
+columns per GPU: query encodings -> acoustic MLP -> spectral loss -> backward (+ gradient all-reduce for
+N > 1).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_COLUMN_TRAIN = {1: 2 * 44769136, 2: 2 * 44770672}       # SURVEY.md section 8d (factored layer 1)
+GL_STREAM_BYTES_PER_RIR = {"RAF": 39.75e6, "SoundSpaces": 66.42e6}  # SURVEY.md section 8d streaming model
+GL_COMPULSORY_BYTES_PER_RIR = {"RAF": 183536, "SoundSpaces": 306976}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own algorithm (oracle port, torch CPU fp32 + autograd) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_factory(shape, batch_size, seed=0):
+    from neraf_b200 import synthetic as syn
+    from oracle import encodings as oenc, field as ofield, loss as oloss
+    sd = {k: v.clone().requires_grad_(True) for k, v in syn.make_state_dict(shape, seed=seed).items()}
+    batch = syn.make_batch(shape, batch_size, seed=seed)
+    g = syn.make_grid_feature(seed).requires_grad_(True)
+    aabb = syn.default_aabb()
+
+    def step():
+        for t in sd.values():
+            t.grad = None
+        g.grad = None
+        h = oenc.assemble_input(batch, aabb, shape.T, g)                # NeRAF_model.py:533-560 (dense, like the reference)
+        y = ofield.field_forward(sd, h, torch.float32)                   # NeRAF_field.py:47-65
+        ld = oloss.loss_dict(y, batch["data"], "SC+SLMSE", 1e-3, dtype=torch.float32)
+        (ld["audio_sc_loss"] + ld["audio_mag_loss"]).backward()
+        return float(ld["audio_mag_loss"].detach())
+    return step
+
+
+def time_cpu_baseline(shape, batch_size, steps, warmup, budget_s=25.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_train_step_factory(shape, batch_size)
+    for _ in range(warmup):
+        step()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    sec = statistics.median(times)
+    return {"value": batch_size / sec, "unit": "columns/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} train steps (fwd+loss+bwd, dense 1187-wide layer 1 as the reference executes it) of "
+                      f"{batch_size} {shape.name}-shaped columns, torch {torch.__version__} CPU fp32, median",
+            "ms_per_step": sec * 1e3, "steps": len(times)}
+
+
+def run_reference(args):
+    from neraf_b200 import synthetic as syn
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape = syn.RAF if args.shape == "RAF" else syn.SOUNDSPACES
+    res = time_cpu_baseline(shape, args.batch, max(args.steps, 1), max(args.warmup, 1), budget_s=120.0)
+    line = {"impl": "reference", "metric": "stft_columns_per_sec_train_fwd_bwd", "value": res["value"],
+            "unit": "columns/s", "n_gpus": args.gpus, "steps": res["steps"], "warmup": max(args.warmup, 1),
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(shape, args),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(shape, args):
+    return {"workload": f"{shape.name} FurnishedRoom-shaped audio-field training step (encode + MLP 1187->5096->2048->"
+                        f"1024->1024->512->{shape.C}x{shape.F} + SC/log-STFT loss + backward), B={args.batch} columns/GPU, "
+                        f"T={shape.T}", "batch_per_gpu": args.batch, "C": shape.C, "F": shape.F, "T": shape.T,
+            "precision": args.precision, "l2": "flushed between timed steps (256 MiB write, outside the events)",
+            "optimizer": "not in the timed region (metric is fwd+bwd; nerfstudio's Adam is outside the path)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=2048, help="STFT columns per GPU per step (NeRAF_config.py:47)")
+    ap.add_argument("--shape", default="RAF", choices=["RAF", "SoundSpaces"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--gl-rirs", type=int, default=2048, help="RIRs per Griffin-Lim launch (0 disables)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from neraf_b200 import _lib
+    from neraf_b200 import synthetic as syn
+    from neraf_b200.distributed import GradientAllReduce
+    from neraf_b200.model import ConstantGridFeature, NeRAFAudioModel, NeRAFAudioModelConfig
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: neraf_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    group = dist.group.WORLD if world > 1 else None
+
+    shape = syn.RAF if args.shape == "RAF" else syn.SOUNDSPACES
+    cfg = NeRAFAudioModelConfig(dataset=shape.name, max_len=shape.T, fs=shape.fs, N_freq_stft=shape.F,
+                                hop_len=shape.hop, win_len=shape.win, precision=args.precision)
+    model = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)),
+                            process_group=group)
+    model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
+    model = model.to(dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    reducer = GradientAllReduce(params, group)
+
+    B = args.batch
+    host_batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=rank).items()}
+    dev_batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
+
+    def step(batch):
+        for p in params:
+            p.grad = None
+        out = model.get_outputs(batch)
+        ld = model.get_loss_dict(out, batch)
+        loss = sum(ld.values())
+        loss.backward()
+        reducer()
+        return loss
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    lib = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batch, n, read_loss):
+        """n steps, each bracketed by CUDA events on the launching stream, L2 flushed in between."""
+        evs = []
+        barrier()
+        l0 = lib.neraf_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            loss = step(batch)
+            if read_loss:
+                loss.item()                              # device -> host read of the step's result
+            e.record()
+            evs.append((s, e))
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = [s.elapsed_time(e) for s, e in evs]
+        return ms, lib.neraf_launch_count() - l0, wall
+
+    for _ in range(args.warmup):
+        step(dev_batch)
+        step(host_batch)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, launches, wall_dev = timed(dev_batch, args.steps, read_loss=False)
+    ms_e2e, _, wall_e2e = timed(host_batch, args.steps, read_loss=True)
+    clocks = sampler.stop()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    total_ms = max_over_ranks(sum(ms_dev))
+    total_ms_e2e = max_over_ranks(sum(ms_e2e))
+    ms_per_step = total_ms / args.steps
+    value = B * world * args.steps / (total_ms * 1e-3)
+    e2e_value = B * world * args.steps / (total_ms_e2e * 1e-3)
+
+    peaks = load_peaks()
+    flops_step = FLOP_PER_COLUMN_TRAIN[shape.C] * B
+    achieved = flops_step / (ms_per_step * 1e-3) / 1e12
+    h2d = sum(v.numel() * v.element_size() for k, v in host_batch.items()
+              if torch.is_tensor(v) and k in ("time_query", "mic_pose", "source_pose", "rot", "data"))
+
+    line = {
+        "metric": "stft_columns_per_sec_train_fwd_bwd", "value": value, "unit": "columns/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": workload_config(shape, args), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": total_ms_e2e / args.steps,
+                "api": "NeRAFAudioModel.get_outputs(host batch) -> get_loss_dict -> backward -> loss.item()"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "kernel": "umma_gemm_kernel (all GEMMs of the step; achieved = 89.54 MFLOP/column x columns / whole-step "
+                               "device time, i.e. the non-GEMM kernels of the step are charged to it)",
+                     "peak_source": f"{peaks['source']} sustained bf16 cuBLAS (MEASURED_PEAKS.json)"},
+        "host_wall_ms_per_step": wall_dev / args.steps * 1e3,
+    }
+
+    # ---- Griffin-Lim: RIRs/s (second half of the BASELINE metric), rank-local poses, no collective
+    if args.gl_rirs > 0:
+        n = args.gl_rirs
+        gen = torch.Generator().manual_seed(100 + rank)
+        log_h = (torch.randn(n, shape.T, shape.C, shape.F, generator=gen) * 1.5 - 3.0).pin_memory()
+        log_d = log_h.to(dev)
+        init = torch.rand(n, shape.C, shape.F, shape.T, dtype=torch.complex64, device=dev)
+        gl = model.istft_transform
+        for _ in range(2):
+            gl.render(log_d, init)
+        barrier()
+        k_gl = 3
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k_gl):
+            gl.render(log_d, init)
+        e.record()
+        barrier()
+        gl_ms = max_over_ranks(s.elapsed_time(e)) / k_gl
+        s.record()
+        for _ in range(k_gl):
+            w = gl.render(log_h.to(dev, non_blocking=True), init)
+            w_host = w.cpu()
+        e.record()
+        barrier()
+        gl_ms_e2e = max_over_ranks(s.elapsed_time(e)) / k_gl
+        rirs = n * world / (gl_ms * 1e-3)
+        stream_gbs = rirs / world * GL_STREAM_BYTES_PER_RIR[shape.name] / 1e9
+        line["griffinlim"] = {
+            "metric": "rirs_per_sec", "value": rirs, "unit": "RIR/s", "rirs_per_launch_per_gpu": n, "ms_per_launch": gl_ms,
+            "e2e": {"value": n * world / (gl_ms_e2e * 1e-3), "unit": "RIR/s",
+                    "h2d_bytes_per_step": log_h.numel() * 4, "d2h_bytes_per_step": w_host.numel() * 4},
+            "roofline": {"bound": "hbm", "achieved": stream_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": stream_gbs / peaks["hbm_gbs"], "traffic": None,
+                         "note": "achieved = streaming-model algorithmic bytes (SURVEY.md 8d: 39.75 MB/RIR RAF) x RIR/s; the "
+                                 "fused kernel keeps the state on chip, its compulsory HBM bytes are "
+                                 f"{GL_COMPULSORY_BYTES_PER_RIR[shape.name]} B/RIR"}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = time_cpu_baseline(shape, B, steps=10, warmup=2)
+        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,8 @@ enum { NERAF_ORDER_TIME_MIC_SRC_ROT = 0, /* NeRAF_model.py:560 (after the grid b
 
 NERAF_API int neraf_version(void);
 NERAF_API const char* neraf_last_error(void);
+/* Cumulative number of CUDA kernels launched by this library in this process (bench.py: gpu_launches). */
+NERAF_API long long neraf_launch_count(void);
 /* 1 when the current device is compute capability 10.x, else 0 (no error raised). */
 NERAF_API int neraf_device_supported(void);
 

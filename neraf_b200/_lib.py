@@ -58,6 +58,7 @@ _pp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "neraf_version": (C.c_int, []),
     "neraf_last_error": (C.c_char_p, []),
+    "neraf_launch_count": (C.c_longlong, []),
     "neraf_device_supported": (C.c_int, []),
     "neraf_field_sizes": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, C.POINTER(_sz), C.POINTER(_sz)]),
     "neraf_field_pack": (C.c_int, [C.POINTER(FieldDims), _i32, _pp, _pp, _vp, _sz, _vp]),

@@ -5,6 +5,8 @@
 
 namespace neraf {
 
+std::atomic<long long> g_launch_count{0};
+
 char* last_error_buffer() {
   static thread_local char buf[1024] = {0};
   return buf;
@@ -37,6 +39,8 @@ extern "C" {
 int neraf_version(void) { return NERAF_ABI_VERSION; }
 
 const char* neraf_last_error(void) { return neraf::last_error_buffer(); }
+
+long long neraf_launch_count(void) { return neraf::g_launch_count.load(std::memory_order_relaxed); }
 
 int neraf_device_supported(void) {
   int dev = 0;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -15,6 +16,8 @@ namespace neraf {
 // Thread-local text of the last error, returned by neraf_last_error().
 char* last_error_buffer();
 int set_error(int code, const char* fmt, ...);
+// Number of kernels this library has launched (process-wide); read through neraf_launch_count().
+extern std::atomic<long long> g_launch_count;
 
 #define NERAF_CHECK_CUDA(expr)                                                                   \
   do {                                                                                           \
@@ -30,6 +33,7 @@ int set_error(int code, const char* fmt, ...);
     if (_e != cudaSuccess)                                                                       \
       return ::neraf::set_error(NERAF_ERR_CUDA, "launch of %s failed: %s (%s:%d)", name,         \
                                 cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+    ::neraf::g_launch_count.fetch_add(1, std::memory_order_relaxed);                             \
   } while (0)
 
 #define NERAF_REQUIRE(cond, ...)                                                                 \

@@ -139,6 +139,8 @@ int encode_queries(const neraf_queries* q, float* out_f32, int64_t ld_f32, void*
 }  // namespace neraf
 
 extern "C" int neraf_encode_queries(const neraf_queries* q, float* enc_out, int64_t ld, neraf_stream_t stream) {
+  NERAF_REQUIRE(q, "neraf_encode_queries: queries is null");
+  if (q->batch == 0) return NERAF_OK;
   NERAF_REQUIRE(enc_out && ld >= 163, "neraf_encode_queries: enc_out null or ld < 163");
   return neraf::encode_queries(q, enc_out, ld, nullptr, 0, nullptr, 0, 163, (cudaStream_t)stream);
 }

@@ -1,0 +1,72 @@
+"""Data parallelism for the acoustic-field train step (one process per GPU, NCCL over NVLink).
+
+The reference refuses ``world_size > 1`` (/root/reference/NeRAF/NeRAF_pipeline.py:154-155); queries
+are independent given replicated weights, so the path shards by rows of the batch dict:
+
+* every rank runs the field forward/backward on its shard (no data-path collective),
+* the spectral-convergence loss is a *global* Frobenius ratio: its four partial sums are all-reduced
+  inside the loss (neraf_b200/loss.py, ``group=``) so loss and gradients equal the single-GPU values on
+  the concatenated batch,
+* parameter gradients are summed across ranks in one coalesced NCCL call.  With the "global" loss the
+  per-rank gradients are already scaled by 1/N_total, so the reduction is a SUM (not a mean).
+
+Inference (rendering) shards poses with no collective at all.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world_size: int) -> Dict[str, torch.Tensor]:
+    """Rows [rank*B/N, (rank+1)*B/N) of every tensor of the batch dict (B must divide evenly)."""
+    out = {}
+    for k, v in batch.items():
+        if not torch.is_tensor(v) or v.dim() == 0:
+            out[k] = v
+            continue
+        B = v.shape[0]
+        if B % world_size:
+            raise ValueError(f"batch of {B} rows does not split evenly over {world_size} ranks")
+        n = B // world_size
+        out[k] = v[rank * n:(rank + 1) * n]
+    return out
+
+
+def shard_range(n_items: int, rank: int, world_size: int):
+    """Contiguous [lo, hi) slice of n_items for this rank (ragged tail goes to the first ranks)."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradientAllReduce:
+    """Sum parameter gradients over the data-parallel group in a single coalesced collective."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                 average: bool = False):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        self.average = average
+
+    def __call__(self) -> None:
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if not grads or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        dev = grads[0].device
+        if dev.type == "cuda":
+            with dist._coalescing_manager(group=self.group, device=dev, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        else:                                   # gloo (CPU tests of the host logic)
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        if self.average:
+            w = dist.get_world_size(self.group)
+            torch._foreach_div_(grads, w)

@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference audio model for the acoustic-field hot path.
+
+``NeRAFAudioModel`` keeps the method surface the nerfstudio pipeline calls
+(/root/reference/NeRAF/NeRAF_pipeline.py:188,191,248-250,279-280,362-364):
+``get_outputs(batch_audio)``, ``get_loss_dict(outputs, batch, metrics_dict)``,
+``get_outputs_for_camera(camera, obb_box, batch_audio)``, ``get_image_metrics_and_images``,
+``get_param_groups`` and the attributes ``field``, ``grid``, ``resnet3d``, ``istft_transform``,
+``max_len``, ``mic_ch`` -- with every tensor operation of the hot path executed by the CUDA library.
+
+nerfstudio is not a dependency: the class derives from ``nn.Module``; INTEGRATION.md shows the
+three-line subclass that plugs it into a real nerfstudio ``Model``.  The scene-grid feature producer
+(ResNet3D, NeRAF_resnet3d.py) is out of scope: any ``nn.Module`` mapping the grid
+to the flat feature vector can be passed as ``resnet3d``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .field import N_ENC, NeRAFAudioSoundField
+from .griffinlim import GriffinLim
+from .loss import spectral_loss
+
+
+@dataclass
+class NeRAFAudioModelConfig:
+    """Same fields and defaults as the reference config (NeRAF_model.py:82-101) + ``precision``."""
+    dataset: str = "SoundSpaces"
+    use_grid: bool = True
+    grid_step: float = 1 / 128
+    N_features: int = 1024
+    use_multiple_viewing_directions: bool = True
+    loss_factor: float = 1e-3
+    max_len: float = 76
+    W_field: int = 512
+    fs: int = 22050
+    criterion: str = "SC+SLMSE"
+    N_freq_stft: int = 257
+    hop_len: int = 128
+    win_len: int = 512
+    precision: str = "bf16"          # "bf16": tcgen05 tensor cores; "fp32": CUDA-core parity path
+
+
+class ConstantGridFeature(nn.Module):
+    """Stand-in for the ResNet3D grid-feature producer: a learnable (N_features,) vector."""
+
+    def __init__(self, n_features: int = 1024, init: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.feature = nn.Parameter(torch.zeros(n_features) if init is None else init.clone().float())
+
+    def forward(self, grid: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.feature
+
+
+class NeRAFAudioModel(nn.Module):
+    def __init__(self, config: NeRAFAudioModelConfig, aabb: torch.Tensor, resnet3d: Optional[nn.Module] = None,
+                 grid: Optional[torch.Tensor] = None, process_group=None):
+        super().__init__()
+        self.config = config
+        self.dataset = config.dataset
+        if self.dataset == "RAF":                       # default_RAF_config, NeRAF_model.py:109-119
+            config.fs = 48000
+            config.max_len = 0.32
+            if config.fs == 48000:
+                config.N_freq_stft, config.hop_len, config.win_len = 513, 256, 512
+            self.max_len = int(config.max_len * config.fs) // config.hop_len
+            self.mic_ch = 1
+        else:
+            self.max_len = int(config.max_len)
+            self.mic_ch = 2
+        self.use_grid = config.use_grid
+        self.loss_factor = config.loss_factor
+        self.criterion_name = config.criterion
+        if self.criterion_name not in _lib.CRITERIA:
+            raise ValueError(f"unknown criterion {self.criterion_name}")
+        self.istft_transform = GriffinLim(n_fft=(config.N_freq_stft - 1) * 2, win_length=config.win_len,
+                                          hop_length=config.hop_len, power=1)
+        self.register_buffer("aabb", aabb.detach().float().reshape(2, 3).clone(), persistent=False)
+        self.process_group = process_group               # DP: global spectral-convergence sums
+        n_grid = config.N_features if self.use_grid else 0
+        if self.use_grid:
+            self.resnet3d = resnet3d if resnet3d is not None else ConstantGridFeature(config.N_features)
+            self.grid = grid                             # plain attribute like the reference (NeRAF_pipeline.py:451-455)
+        self.field = NeRAFAudioSoundField(n_grid + N_ENC, config.W_field, sound_rez=self.mic_ch,
+                                          N_frequencies=config.N_freq_stft, precision=config.precision)
+        self._grid_feature_cache = None
+
+    @property
+    def device(self) -> torch.device:
+        return self.field.soundfield[0].weight.device
+
+    # ---- grid feature -------------------------------------------------------------------------
+    def grid_feature(self) -> Optional[torch.Tensor]:
+        """NeRAF_model.py:554-557: resnet3d(grid[None]).flatten()."""
+        if not self.use_grid:
+            return None
+        g = self.grid.unsqueeze(0).to(self.device) if self.grid is not None else None
+        feat = self.resnet3d(g)
+        if isinstance(feat, (list, tuple)):
+            feat = feat[-1]
+        return feat.flatten()
+
+    # ---- training path --------------------------------------------------------------------------
+    def get_outputs(self, batch_audio: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """NeRAF_model.py:531-566 -> (B, C, F) log-magnitude STFT columns (fp32)."""
+        order = _lib.ORDER_TIME_MIC_SRC_ROT if self.use_grid else _lib.ORDER_MIC_SRC_TIME_ROT
+        return self.field.forward_queries(batch_audio["time_query"], batch_audio["mic_pose"],
+                                          batch_audio["source_pose"], batch_audio["rot"], self.aabb, self.max_len,
+                                          self.grid_feature(), order)
+
+    def get_loss_dict(self, outputs: torch.Tensor, batch: Dict[str, torch.Tensor], metrics_dict=None):
+        """NeRAF_model.py:584-600 (same keys, same weights)."""
+        gt = batch["data"]
+        if self.criterion_name == "MSE":
+            _, mse = spectral_loss(outputs, gt, "MSE", 0.0, self.loss_factor, self.process_group)
+            return {"audio_mse": mse}
+        sc, mag = spectral_loss(outputs, gt, self.criterion_name, 1e-1 * self.loss_factor, 1.0 * self.loss_factor,
+                                self.process_group)
+        return {"audio_sc_loss": sc, "audio_mag_loss": mag}
+
+    def get_param_groups(self):
+        params = list(self.field.parameters())
+        if self.use_grid:
+            params += list(self.resnet3d.parameters())
+        return {"audio_fields": params}
+
+    # ---- eval / render path -----------------------------------------------------------------------
+    @torch.no_grad()
+    def query_rirs(self, mic_pose: torch.Tensor, source_pose: torch.Tensor, rot: torch.Tensor,
+                   grid_feature: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """N poses x all T time bins -> (N, T, C, F) log-STFT (the body of get_outputs_for_camera, batched;
+        the grid feature is computed once for all poses instead of once per RIR, NeRAF_model.py:680-683)."""
+        dev = self.device
+        mic = mic_pose.reshape(-1, 3).to(dev, torch.float64)
+        N, T = mic.shape[0], self.max_len
+        src = source_pose.reshape(-1, 3).to(dev, torch.float64).expand(N, 3)
+        r = rot.reshape(-1, 3).to(dev, torch.float64).expand(N, 3)
+        tq = torch.arange(T, device=dev, dtype=torch.int64).repeat(N)
+        rep = lambda x: x.repeat_interleave(T, dim=0)  # noqa: E731
+        g = self.grid_feature() if grid_feature is None and self.use_grid else grid_feature
+        order = _lib.ORDER_TIME_MIC_SRC_ROT if self.use_grid else _lib.ORDER_MIC_SRC_TIME_ROT
+        y = self.field.forward_queries(tq, rep(mic), rep(src), rep(r), self.aabb, self.max_len, g, order)
+        return y.view(N, T, self.mic_ch, -1)
+
+    @torch.no_grad()
+    def render_rirs(self, mic_pose, source_pose, rot, init_phase: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Loudness-map workload (viz/loudness_maps.ipynb): poses -> waveforms (N, C, hop*(T-1))."""
+        return self.istft_transform.render(self.query_rirs(mic_pose, source_pose, rot), init_phase)
+
+    @torch.no_grad()
+    def get_outputs_for_camera(self, camera=None, obb_box=None, batch_audio: Optional[Dict] = None):
+        """Eval branch of NeRAF_model.py:610-728 (camera=None): one RIR, keys as in the reference."""
+        if camera is not None:
+            raise NotImplementedError("viewer cameras need nerfstudio; pass batch_audio (the ns-eval path)")
+        y = self.query_rirs(batch_audio["mic_pose"], batch_audio["source_pose"], batch_audio["rot"])[0]   # (T, C, F)
+        stft = {}
+        for ch in range(y.shape[1]):
+            stft[f"stft_ch_{ch}"] = torch.flip(y[:, ch, :].transpose(0, 1).unsqueeze(-1).cpu(), [0])
+        gt = batch_audio.get("data")
+        if gt is not None:
+            for ch in range(gt.shape[0]):
+                stft[f"gt_ch_{ch}"] = torch.flip(gt[ch].unsqueeze(-1).cpu(), [0])
+                stft[f"comparison_ch_{ch}"] = torch.cat([stft[f"stft_ch_{ch}"], stft[f"gt_ch_{ch}"]], dim=1)
+        stft["raw_output"] = y
+        return stft
+
+    @torch.no_grad()
+    def get_image_metrics_and_images(self, outputs: Dict, batch: Dict, evaluator=None):
+        """NeRAF_model.py:739-760: Griffin-Lim on prediction AND ground truth (one batched launch), then the
+        CPU acoustic metrics of the supplied evaluator (``evaluator.get_full_metrics`` signature of the reference)."""
+        dev = self.device
+        stft = outputs["raw_output"].permute(1, 2, 0)                       # (C, F, T)
+        data = batch["data"].to(dev)
+        mag_prd = torch.clip(torch.exp(stft) - 1e-3, 0.0, 10000.0)
+        mag_gt = torch.clip(torch.exp(data) - 1e-3, 0.0, 10000.0)
+        waves = self.istft_transform(torch.stack([mag_gt, mag_prd]))         # (2, C, L)
+        wav_istft_gt, wav_istft_prd = waves[0].cpu().numpy(), waves[1].cpu().numpy()
+        out = {"wav_istft_gt": wav_istft_gt, "wav_istft_prd": wav_istft_prd}
+        if evaluator is not None:
+            out["metrics"] = evaluator.get_full_metrics(mag_prd.cpu().numpy(), mag_gt.cpu().numpy(),
+                                                        batch["waveform"].cpu().numpy(), wav_istft_prd, wav_istft_gt,
+                                                        stft.cpu().numpy(), data.cpu().numpy())
+        return out

@@ -24,6 +24,7 @@ def _header_symbols():
     return sorted(set(re.findall(r"NERAF_API\s+[\w\s\*]+?\b(neraf_\w+)\s*\(", text)))
 
 
+
 def test_library_exports_every_declared_symbol(built):
     from neraf_b200 import _lib
     names = _header_symbols()
