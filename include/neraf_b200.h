@@ -204,6 +204,10 @@ typedef struct {
 NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
                     const neraf_gemm_epilogue* epi, neraf_stream_t stream);
 
+/* Pin the tile shape of neraf_gemm_bf16 (tuning / tests): code = cta_group*1000 + tile_n with cta_group in
+ * {1,2}, tile_n in {64,128,256}; 0 restores the built-in cost model. */
+NERAF_API int neraf_gemm_bf16_set_tile(int code);
+
 /* fp32 (rows, cols) row stride ld_in  ->  bf16 (rows, cols) row stride ld_out (and/or its transpose
  * (cols, rows) row stride ld_t).  Either output may be NULL. */
 NERAF_API int neraf_convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,

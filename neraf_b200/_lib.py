@@ -76,6 +76,7 @@ SIGNATURES = {
     "neraf_gemm_f32": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _i64,
                                   _i32, _vp]),
     "neraf_gemm_bf16": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(GemmEpilogue), _vp]),
+    "neraf_gemm_bf16_set_tile": (C.c_int, [C.c_int]),
     "neraf_convert_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
 }
 

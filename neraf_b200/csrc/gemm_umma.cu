@@ -10,16 +10,22 @@
 //   dgrad     dZ_l = (dZ_{l+1} W_{l+1}) * leaky'(X_l) A = dZ_{l+1} (B,N')    B = W_{l+1}^T (N,N')
 //   wgrad     dW_l = dZ_l^T X_{l-1}                   A = dZ_l^T (N,B)       B = X_{l-1}^T (K,B)
 //
-// Kernel anatomy (one CTA per SM, persistent over output tiles, 192 threads):
+// Kernel anatomy (one CTA per SM, persistent over output tiles, 192 threads).  CG = 2 pairs the two SMs of
+// a TPC on one 256 x BN tile (tcgen05 cta_group::2: each CTA stages its 128 rows of A and HALF of the B
+// tile, the leader CTA issues the MMAs for both, each CTA's TMEM receives its 128 accumulator rows): the
+// L2 -> SMEM traffic per FLOP drops by a third, which is what bounds the single-CTA kernel (ncu: tensor
+// pipe 25-30 % busy at 8-10 TB/s of L2 reads).
 //   warp 0      TMA producer      (one elected lane; cp.async.bulk.tensor.2d -> smem ring, expect_tx)
-//   warp 1      MMA issuer        (one elected lane; tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16;
-//                                  tcgen05.commit releases smem slots and publishes the accumulator)
+//   warp 1      MMA issuer        (one elected lane of the leader CTA; tcgen05.mma kind::f16, M=128*CG, N=BN,
+//                                  K=16; tcgen05.commit releases smem slots and publishes the accumulator)
 //   warps 2-5   epilogue          (tcgen05.ld 32x32b.x32 -> bias / LeakyReLU / 10*tanh / LeakyReLU' gate ->
 //                                  bf16 row-major, bf16 transposed and/or fp32 stores; smem-staged so that
 //                                  row-major stores are coalesced)
 // TMEM holds two BN-column accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 
+#include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -83,39 +89,93 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) __trap();
   }
 }
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    // issued by both CTAs of the pair; clearing the peer bit routes the transaction bytes to the leader's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
 }
+// CG == 2: the arrive is multicast to the barrier at the same offset in both CTAs of the pair.
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -146,15 +206,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major.
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int CG>
 struct Config {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int B_ROWS = BN / CG;             // rows of the B tile staged by each CTA
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr int STAGES = (A_BYTES + B_BYTES) >= 48 * 1024 ? 4 : ((A_BYTES + B_BYTES) >= 32 * 1024 ? 6 : 8);
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = 4 * 32 * STAGE_PITCH * 4;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -162,10 +223,10 @@ struct Config {
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using Cfg = Config<BN>;
+  using Cfg = Config<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -178,45 +239,52 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  constexpr int TILE_M = BLOCK_M * CG;               // rows of one work unit (CTA or CTA pair)
+  const int num_m = (p.M + TILE_M - 1) / TILE_M;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4 * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish<CG>(); }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int mt = tile % num_m, nt = tile / num_m;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
-          tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmA, full_bar + stage, kb * BLOCK_K, mt * BLOCK_M);
-          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, full_bar + stage, kb * BLOCK_K, nt * BN);
+          // the leader's barrier collects the bytes landed in BOTH CTAs of the pair
+          if (is_leader) mbar_expect_tx(full_bar + stage, Cfg::STAGE_BYTES * CG);
+          tma_load_2d<CG>(smem_a + stage * Cfg::A_BYTES, &tmA, full_bar + stage, kb * BLOCK_K,
+                          mt * TILE_M + (int)cta_rank * BLOCK_M);
+          tma_load_2d<CG>(smem_b + stage * Cfg::B_BYTES, &tmB, full_bar + stage, kb * BLOCK_K,
+                          nt * BN + (int)cta_rank * Cfg::B_ROWS);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = make_idesc(TILE_M, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tmem_empty + as, aphase ^ 1);
@@ -230,12 +298,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance both descriptors by 16 bf16 = 32 B inside the 128 B swizzle row (encoded >> 4)
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_bf16<CG>(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar + stage);        // frees the smem slot once these MMAs retire
+          umma_commit<CG>(empty_bar + stage);    // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tmem_full + as);             // accumulator complete -> epilogue
+        umma_commit<CG>(tmem_full + as);         // accumulator complete -> epilogue (of both CTAs)
       }
     }
     __syncwarp();
@@ -243,13 +311,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;                // TMEM lane quarter this warp may access
     float* sbuf = stage_buf + (warp - EPI_WARP0) * 32 * STAGE_PITCH;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int mt = tile % num_m, nt = tile / num_m;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tmem_full + as, aphase);
       tc_fence_after();
-      const int m_base = mt * BLOCK_M + quarter * 32;
+      const int m_base = mt * TILE_M + (int)cta_rank * BLOCK_M + quarter * 32;
       const int m = m_base + lane;
       const bool row_ok = m < p.M;
 #pragma unroll 1
@@ -337,15 +405,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + as);
+      if (lane == 0) {                           // the leader's MMA warp owns the accumulator hand-back
+        if (CG == 1 || is_leader) mbar_arrive(tmem_empty + as);
+        else mbar_arrive_remote(tmem_empty + as, 0);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -419,19 +490,42 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   return NERAF_OK;
 }
 
-template <int BN>
+// Tile-shape pin for tuning / tests: cg*1000 + bn (e.g. 2256 = CTA pair, 256-wide tile); 0 = cost model.
+// Initialised from NERAF_UMMA_TILE, changed at run time through neraf_gemm_bf16_set_tile().
+static std::atomic<int> g_tile_override{-1};
+static int tile_override() {
+  int v = g_tile_override.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("NERAF_UMMA_TILE");
+    v = e ? atoi(e) : 0;
+    g_tile_override.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+template <int BN, int CG>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
-  using Cfg = Config<BN>;
+  using Cfg = Config<BN, CG>;
   static bool configured[64] = {false};
   int dev = 0;
   NERAF_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
   }
-  const int num_tiles = (int)(ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BN));
-  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  umma_gemm_kernel<BN><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const int num_tiles = (int)(ceil_div(p.M, BLOCK_M * CG) * ceil_div(p.N, BN));
+  const int units = sm_count() / CG;
+  const int grid = (num_tiles < units ? num_tiles : units) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, CG>, tmA, tmB, p));
   NERAF_CHECK_LAUNCH("umma_gemm_kernel");
   return NERAF_OK;
 }
@@ -465,23 +559,53 @@ int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const
   p.out_f32 = e->out_f32; p.ld_f32 = e->ld_f32;
   p.accumulate_f32 = e->accumulate_f32;
 
-  // Tile width: 256 when that still yields at least one full wave of tiles, otherwise narrower tiles
-  // to keep more SMs busy (the MLP's small layers at batch 2048 have few output tiles).
-  const int64_t mt = ceil_div(M, BLOCK_M);
+  // Tile shape from a small cost model: per work unit (CTA, or CTA pair for cta_group::2) a k-block costs
+  // max(MMA issue, L2->SMEM bytes / per-SM share of the L2 bandwidth); the kernel takes `waves` rounds of tiles
+  // plus a fixed prologue/epilogue.  Constants are calibrated on the ncu captures in profiles/.
   const int sms = sm_count();
-  int bn = 256;
-  if (mt * ceil_div(N, 256) < sms) bn = 128;
-  if (bn == 128 && mt * ceil_div(N, 128) < sms / 2) bn = 64;
+  int best_bn = 256, best_cg = 1;
+  double best_t = 1e30;
+  const int force = tile_override();
+  for (int cg = 1; cg <= 2; ++cg) {
+    for (int bn = 64; bn <= 256; bn *= 2) {
+      if (force && force != cg * 1000 + bn) continue;
+      const double tiles = (double)ceil_div(M, BLOCK_M * cg) * (double)ceil_div(N, bn);
+      const double units = sms / cg;
+      const double waves = ceil(tiles / units);
+      const double kblocks = (double)ceil_div(K, BLOCK_K);
+      const double mma = 4.0 * bn / 2.0;                                   // cycles per k-block per SM (M=128 rows each)
+      const double bytes = (BLOCK_M + (double)bn / cg) * BLOCK_K * 2.0;    // per CTA per k-block
+      const double l2 = bytes / 40.0;                                      // ~40 B/clk/SM when every SM streams from L2
+      const double epi = bn / 32.0 * 450.0;                                // drain of one accumulator stage
+      const double per_tile = kblocks * (mma > l2 ? mma : l2);
+      const double t = waves * (per_tile > epi ? per_tile : epi) + epi + 6000.0;
+      if (t < best_t) { best_t = t; best_bn = bn; best_cg = cg; }
+    }
+  }
 
   CUtensorMap tmA, tmB;
   NERAF_TRY(get_tensor_map(A, M, K, lda, BLOCK_M, &tmA));
-  NERAF_TRY(get_tensor_map(B, N, K, ldb, bn, &tmB));
-  if (bn == 256) return launch<256>(tmA, tmB, p, stream);
-  if (bn == 128) return launch<128>(tmA, tmB, p, stream);
-  return launch<64>(tmA, tmB, p, stream);
+  NERAF_TRY(get_tensor_map(B, N, K, ldb, best_bn / best_cg, &tmB));
+  if (best_cg == 1) {
+    if (best_bn == 256) return launch<256, 1>(tmA, tmB, p, stream);
+    if (best_bn == 128) return launch<128, 1>(tmA, tmB, p, stream);
+    return launch<64, 1>(tmA, tmB, p, stream);
+  }
+  if (best_bn == 256) return launch<256, 2>(tmA, tmB, p, stream);
+  if (best_bn == 128) return launch<128, 2>(tmA, tmB, p, stream);
+  return launch<64, 2>(tmA, tmB, p, stream);
 }
 
 }  // namespace neraf
+
+extern "C" int neraf_gemm_bf16_set_tile(int code) {
+  if (code != 0) {
+    const int cg = code / 1000, bn = code % 1000;
+    NERAF_REQUIRE((cg == 1 || cg == 2) && (bn == 64 || bn == 128 || bn == 256), "set_tile: code must be cg*1000+bn");
+  }
+  neraf::umma::g_tile_override.store(code, std::memory_order_relaxed);
+  return NERAF_OK;
+}
 
 extern "C" int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
                                const neraf_gemm_epilogue* epi, neraf_stream_t stream) {

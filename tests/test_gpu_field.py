@@ -72,7 +72,7 @@ def test_train_step_matches_oracle(prec, shape, B):
     assert rel_fro(gd.grad, dgrid_ref) < _bottom_tol(prec, B)
     for name, p in field.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape, name
-        assert rel_fro(p.grad, grads_ref[name]) < t["grad"], name
+        assert rel_fro(p.grad, grads_ref[name]) < _bottom_tol(prec, B), name
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -97,13 +97,14 @@ def test_against_reference_golden(golden_dir, prec, name):
     assert abs(float(sc) / 1e-4 - float(gold["sc_f64"])) < t["loss"] * float(gold["sc_f64"])
     assert abs(float(mag) / 1e-3 - float(gold["mag_f64"])) < t["loss"] * float(gold["mag_f64"])
     assert rel_fro(gd.grad, gold["dgrid_f64"]) < _bottom_tol(prec, B)
+    gt = _bottom_tol(prec, B)                     # golden batches are small (24 / 16 rows): see _bottom_tol
     for pname, p in field.named_parameters():
         gn = float(gold[f"gnorm_f64:{pname}"])
-        assert abs(float(p.grad.double().norm()) - gn) < t["grad"] * gn, pname
+        assert abs(float(p.grad.double().norm()) - gn) < gt * gn, pname
         if p.dim() == 2:
-            assert rel_fro(p.grad[:4, -8:], gold[f"gslice_f64:{pname}"]) < 3 * t["grad"], pname
+            assert rel_fro(p.grad[:4, -8:], gold[f"gslice_f64:{pname}"]) < 3 * gt, pname
         else:
-            assert rel_fro(p.grad[:16], gold[f"gslice_f64:{pname}"]) < 3 * t["grad"], pname
+            assert rel_fro(p.grad[:16], gold[f"gslice_f64:{pname}"]) < 3 * gt, pname
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])

@@ -116,6 +116,28 @@ def test_gemm_bf16_tcgen05_matches_torch(M, N, K):
         assert torch.all(outs["t"][:, M:] == 7.0), "transposed store wrote past M"
 
 
+@pytest.mark.parametrize("tile", [1064, 1128, 1256, 2064, 2128, 2256])
+@pytest.mark.parametrize("M,N,K", [(2048, 2048, 1024), (300, 520, 200), (5096, 163, 2048), (129, 257, 65)])
+def test_gemm_bf16_every_tile_shape(tile, M, N, K):
+    """Both cta_group variants and all tile widths give the same (correct) result, incl. ragged edges."""
+    dev = cuda()
+    lib = _lib.lib()
+    g = torch.Generator(device="cpu").manual_seed(tile + M)
+    A32 = torch.randn(M, K, generator=g).to(dev)
+    B32 = torch.randn(N, K, generator=g).to(dev) / np.sqrt(K)
+    ldk = (K + 7) // 8 * 8
+    A, B = _bf16_padded(A32, ldk), _bf16_padded(B32, ldk)
+    ref = A[:, :K].double() @ B[:, :K].double().t()
+    _lib.check(lib.neraf_gemm_bf16_set_tile(tile))
+    try:
+        outs = _gemm_bf16(A, B, M, N, K)
+    finally:
+        _lib.check(lib.neraf_gemm_bf16_set_tile(0))
+    assert rel_fro(outs["f32"], ref) < 1e-5
+    assert rel_fro(outs["rm"][:, :N], ref) < 4e-3
+    assert rel_fro(outs["t"][:, :M], ref.t()) < 4e-3
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 def test_gemm_bf16_epilogue(act):
     dev = cuda()

@@ -47,6 +47,9 @@ def run(M, N, K, seed=0):
 
 if __name__ == "__main__":
     print("device", torch.cuda.get_device_name(0), "supported", _lib.lib().neraf_device_supported())
+    if len(sys.argv) > 1:
+        _lib.check(_lib.lib().neraf_gemm_bf16_set_tile(int(sys.argv[1])))
+        print("tile override", sys.argv[1])
     for shape in [(128, 64, 64), (128, 128, 64), (128, 256, 64), (128, 64, 16), (128, 64, 128), (128, 64, 512),
                   (256, 256, 256), (2048, 2048, 512), (100, 72, 40), (2048, 5096, 163 + 5)]:
         run(*shape)
