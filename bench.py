@@ -149,7 +149,8 @@ def workload_config(shape, args):
     return {"workload": f"{shape.name} FurnishedRoom-shaped audio-field training step (encode + MLP 1187->5096->2048->"
                         f"1024->1024->512->{shape.C}x{shape.F} + SC/log-STFT loss + backward), B={args.batch} columns/GPU, "
                         f"T={shape.T}", "batch_per_gpu": args.batch, "C": shape.C, "F": shape.F, "T": shape.T,
-            "precision": args.precision, "l2": "flushed between timed steps (256 MiB write, outside the events)",
+            "precision": args.precision, "launch": "eager" if getattr(args, "no_graph", False) else "one CUDA graph per step (value); eager plugin calls (e2e)",
+            "l2": "flushed between timed steps (256 MiB write, outside the events)",
             "optimizer": "not in the timed region (metric is fwd+bwd; nerfstudio's Adam is outside the path)"}
 
 
@@ -165,6 +166,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gl-rirs", type=int, default=2048, help="RIRs per Griffin-Lim launch (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -175,7 +177,7 @@ def main():
     from neraf_b200 import _lib
     from neraf_b200 import synthetic as syn
     from neraf_b200.distributed import GradientAllReduce
-    from neraf_b200.model import ConstantGridFeature, NeRAFAudioModel, NeRAFAudioModelConfig
+    from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioModel, NeRAFAudioModelConfig
     import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,6 +198,7 @@ def main():
                             process_group=group)
     model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
     model = model.to(dev)
+    model.field.always_repack = True          # training semantics: parameters change every step -> bf16 re-pack in every step
     params = [p for p in model.parameters() if p.requires_grad]
     reducer = GradientAllReduce(params, group)
 
@@ -216,13 +219,27 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     lib = _lib.lib()
 
+    # `value`: the same step captured in one CUDA graph (GraphedTrainStep), inputs resident in HBM.
+    # `e2e`  : the plugin calls a nerfstudio Trainer makes, eager, host batch in pinned memory.
+    graphed = None
+    if not args.no_graph:
+        graphed = GraphedTrainStep(model, dev_batch)
+
+    def step_value(batch):
+        if graphed is None:
+            return step(batch)
+        ld = graphed(batch)
+        reducer()
+        return ld
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batch, n, read_loss):
+    def timed(batch, n, read_loss, fn=None):
         """n steps, each bracketed by CUDA events on the launching stream, L2 flushed in between."""
+        fn = fn or step
         evs = []
         barrier()
         l0 = lib.neraf_launch_count()
@@ -231,7 +248,7 @@ def main():
             flush.fill_(1)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            loss = step(batch)
+            loss = fn(batch)
             if read_loss:
                 loss.item()                              # device -> host read of the step's result
             e.record()
@@ -242,11 +259,16 @@ def main():
         return ms, lib.neraf_launch_count() - l0, wall
 
     for _ in range(args.warmup):
-        step(dev_batch)
+        step_value(dev_batch)
         step(host_batch)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, launches, wall_dev = timed(dev_batch, args.steps, read_loss=False)
+    l_eager0 = lib.neraf_launch_count()
+    step(dev_batch)
+    launches_per_step = lib.neraf_launch_count() - l_eager0     # a graph replay launches the same kernels
+    ms_dev, launches, wall_dev = timed(dev_batch, args.steps, read_loss=False, fn=step_value)
+    if graphed is not None:
+        launches = launches_per_step * args.steps
     ms_e2e, _, wall_e2e = timed(host_batch, args.steps, read_loss=True)
     clocks = sampler.stop()
 

@@ -105,12 +105,16 @@ typedef struct {
 
 /* out: dev fp32 (B, C*F) == (B, C, F) contiguous, log-magnitude STFT columns.
  * grid_feature: dev fp32 (n_grid) or NULL when n_grid == 0.
+ * pack / repack: the bf16 operand copies (neraf_field_sizes bytes).  repack != 0 re-derives them from the
+ *   current fp32 parameters inside this call (on a helper stream, overlapped with the encodings and the earlier
+ *   layers) -- what a training step needs after every optimizer update; repack == 0 trusts the buffer.
  * keep != 0 stores what neraf_field_backward needs in `workspace` (training);
  * keep == 0 is the inference path (no transposed copies). */
 NERAF_API int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
                         const float* grid_feature, const float* const* weights,
-                        const float* const* biases, const void* pack, void* workspace,
-                        size_t workspace_bytes, float* out, int keep, neraf_stream_t stream);
+                        const float* const* biases, void* pack, size_t pack_bytes, int repack,
+                        void* workspace, size_t workspace_bytes, float* out, int keep,
+                        neraf_stream_t stream);
 
 /* Backward of neraf_field_forward(keep=1) on the same workspace.
  * dout, out : dev fp32 (B, C*F).   dweights[l]/dbiases[l]: dev fp32, parameter shapes, OVERWRITTEN.

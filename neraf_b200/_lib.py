@@ -62,8 +62,8 @@ SIGNATURES = {
     "neraf_device_supported": (C.c_int, []),
     "neraf_field_sizes": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, C.POINTER(_sz), C.POINTER(_sz)]),
     "neraf_field_pack": (C.c_int, [C.POINTER(FieldDims), _i32, _pp, _pp, _vp, _sz, _vp]),
-    "neraf_field_forward": (C.c_int, [C.POINTER(FieldDims), _i32, C.POINTER(Queries), _vp, _pp, _pp, _vp, _vp, _sz,
-                                       _vp, _i32, _vp]),
+    "neraf_field_forward": (C.c_int, [C.POINTER(FieldDims), _i32, C.POINTER(Queries), _vp, _pp, _pp, _vp, _sz, _i32,
+                                       _vp, _sz, _vp, _i32, _vp]),
     "neraf_field_backward": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
                                         _vp, _vp, _i64, _vp]),
     "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),

@@ -12,6 +12,9 @@
 //   FP32  CUDA-core GEMMs on the fp32 parameters directly (parity path, 1e-5 gate)
 //   BF16  tcgen05 GEMMs on packed bf16 operand copies; every GEMM is the TN form of gemm_umma.cu, the
 //         transposed copies it needs are written by the producing epilogue.
+#include <cstdlib>
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -102,8 +105,53 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   return NERAF_OK;
 }
 
+// Helper stream for work that is off the critical chain (weight / bias gradients, the grid-feature mat-vec):
+// forked from and joined back into the caller's stream with events, so it is capturable in a CUDA graph.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[NERAF_MAX_TRUNK + 4] = {};
+  cudaEvent_t done = nullptr;
+  bool ok = false;
+};
+
+SideStream* side_stream() {
+  static SideStream per_dev[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& s = per_dev[dev];
+  if (!s.ok) {
+    if (getenv("NERAF_NO_SIDE_STREAM")) return nullptr;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    for (auto& e : s.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    s.ok = true;
+  }
+  return &s;
+}
+
 inline uint8_t* at(void* base, size_t off) { return reinterpret_cast<uint8_t*>(base) + off; }
 inline const uint8_t* at(const void* base, size_t off) { return reinterpret_cast<const uint8_t*>(base) + off; }
+
+// bf16 operand copies of one trunk layer: W (n, k) and W^T (k, n); layer 0 packs only the per-query columns.
+int pack_trunk_layer(const Layout& l, int i, const float* const* weights, void* pack, cudaStream_t stream) {
+  const float* w = weights[i] + (i == 0 ? l.G : 0);
+  const int64_t ld_in = i == 0 ? l.G + l.E : l.k[i];
+  return convert_bf16(w, l.n[i], l.k[i], ld_in, at(pack, l.w[i]), l.ldw[i], at(pack, l.wt[i]), l.ldwt[i], stream);
+}
+
+// heads concatenated along N: W_h (C*F, W), W_h^T (W, C*F) and the fp32 bias vector (C*F)
+int pack_heads(const Layout& l, const float* const* weights, const float* const* biases, void* pack, cudaStream_t stream) {
+  for (int c = 0; c < l.C; ++c) {
+    NERAF_TRY(convert_bf16(weights[l.L + c], l.F, l.W, l.W, at(pack, l.wh) + (size_t)c * l.F * l.ldwh * 2, l.ldwh,
+                           at(pack, l.wht) + (size_t)c * l.F * 2, l.ldwht, stream));
+    NERAF_CHECK_CUDA(cudaMemcpyAsync(at(pack, l.bh) + (size_t)c * l.F * 4, biases[l.L + c], (size_t)l.F * 4,
+                                     cudaMemcpyDeviceToDevice, stream));
+  }
+  return NERAF_OK;
+}
 
 int check_ptr_list(const float* const* list, int n, const char* what) {
   NERAF_REQUIRE(list, "field: %s array is null", what);
@@ -137,24 +185,15 @@ extern "C" int neraf_field_pack(const neraf_field_dims* dims, int precision, con
   NERAF_REQUIRE(pack, "field_pack: pack buffer is null");
   if (pack_bytes < l.pack_bytes)
     return set_error(NERAF_ERR_WORKSPACE, "field_pack: pack buffer %zu < %zu bytes", pack_bytes, l.pack_bytes);
-  for (int i = 0; i < l.L; ++i) {
-    const float* w = weights[i] + (i == 0 ? l.G : 0);
-    const int64_t ld_in = i == 0 ? l.G + l.E : l.k[i];
-    NERAF_TRY(convert_bf16(w, l.n[i], l.k[i], ld_in, at(pack, l.w[i]), l.ldw[i], at(pack, l.wt[i]), l.ldwt[i], stream));
-  }
-  for (int c = 0; c < l.C; ++c) {
-    NERAF_TRY(convert_bf16(weights[l.L + c], l.F, l.W, l.W, at(pack, l.wh) + (size_t)c * l.F * l.ldwh * 2, l.ldwh,
-                           at(pack, l.wht) + (size_t)c * l.F * 2, l.ldwht, stream));
-    NERAF_CHECK_CUDA(cudaMemcpyAsync(at(pack, l.bh) + (size_t)c * l.F * 4, biases[l.L + c], (size_t)l.F * 4,
-                                     cudaMemcpyDeviceToDevice, stream));
-  }
+  for (int i = 0; i < l.L; ++i) NERAF_TRY(pack_trunk_layer(l, i, weights, pack, stream));
+  NERAF_TRY(pack_heads(l, weights, biases, pack, stream));
   return NERAF_OK;
 }
 
 extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
                                    const float* grid_feature, const float* const* weights, const float* const* biases,
-                                   const void* pack, void* ws, size_t ws_bytes, float* out, int keep,
-                                   neraf_stream_t stream_) {
+                                   void* pack, size_t pack_bytes, int repack, void* ws, size_t ws_bytes, float* out,
+                                   int keep, neraf_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NERAF_REQUIRE(q, "field_forward: queries is null");
   Layout l;
@@ -169,16 +208,42 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
     return set_error(NERAF_ERR_WORKSPACE, "field_forward: workspace %zu < %zu bytes for batch %lld", ws_bytes,
                      l.ws_bytes, (long long)B);
   const bool bf = precision == NERAF_PREC_BF16;
-  NERAF_REQUIRE(!bf || pack, "field_forward: pack is null (run neraf_field_pack first)");
+  NERAF_REQUIRE(!bf || pack, "field_forward: pack is null");
   NERAF_REQUIRE(q->enc || l.E == 163, "field_forward: query encodings produce 163 columns, dims->n_enc = %d", l.E);
 
-  // effective layer-1 bias  c1 = b1 + W1[:, :G] g   (once per step, not per query)
+  if (bf && pack_bytes < l.pack_bytes)
+    return set_error(NERAF_ERR_WORKSPACE, "field_forward: pack buffer %zu < %zu bytes", pack_bytes, l.pack_bytes);
+  // Work that does not depend on the queries runs on the helper stream beside the encodings / earlier layers:
+  //  * (repack) re-derive the bf16 operand copies of the CURRENT fp32 parameters, layer by layer,
+  //  * effective layer-1 bias  c1 = b1 + W1[:, :G] g   (once per step, not per query).
+  // ready[i] is recorded when layer i's operands are usable; the GEMM of layer i waits for it.
   const float* c1 = biases[0];
+  float* c1w = reinterpret_cast<float*>(at(ws, l.c1));
+  SideStream* side = bf ? side_stream() : nullptr;
+  cudaStream_t s1 = side ? side->stream : stream;
+  const bool do_pack = bf && repack;
+  if (side && (do_pack || l.G > 0)) {
+    NERAF_CHECK_CUDA(cudaEventRecord(side->done, stream));
+    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->done, 0));
+  }
+  if (do_pack) NERAF_TRY(pack_trunk_layer(l, 0, weights, pack, s1));
   if (l.G > 0) {
-    float* c1w = reinterpret_cast<float*>(at(ws, l.c1));
-    NERAF_TRY(grid_bias(weights[0], l.G + l.E, biases[0], grid_feature, l.n[0], l.G, c1w, stream));
+    NERAF_TRY(grid_bias(weights[0], l.G + l.E, biases[0], grid_feature, l.n[0], l.G, c1w, s1));
     c1 = c1w;
   }
+  if (side && (do_pack || l.G > 0)) NERAF_CHECK_CUDA(cudaEventRecord(side->ev[0], side->stream));
+  if (do_pack) {
+    for (int i = 1; i < l.L; ++i) {
+      NERAF_TRY(pack_trunk_layer(l, i, weights, pack, s1));
+      if (side) NERAF_CHECK_CUDA(cudaEventRecord(side->ev[i], side->stream));
+    }
+    NERAF_TRY(pack_heads(l, weights, biases, pack, s1));
+    if (side) NERAF_CHECK_CUDA(cudaEventRecord(side->ev[l.L], side->stream));
+  }
+  auto wait_ready = [&](int i) -> int {
+    if (side && (do_pack || (i == 0 && l.G > 0))) NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->ev[i], 0));
+    return NERAF_OK;
+  };
 
   if (!bf) {
     // the per-query block of h is kept in the workspace: backward reads it for dW1
@@ -218,6 +283,7 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
   const void* x = enc;
   int64_t ldx = l.ld_enc;
   for (int i = 0; i < l.L; ++i) {
+    NERAF_TRY(wait_ready(i));
     neraf_gemm_epilogue e = {};
     e.bias = i == 0 ? c1 : biases[i];
     e.act = NERAF_ACT_LEAKY;
@@ -226,6 +292,7 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
     NERAF_TRY(gemm_bf16(B, l.n[i], l.k[i], x, ldx, at(pack, l.w[i]), l.ldw[i], &e, stream));
     x = e.out_bf16; ldx = l.ldx[i];
   }
+  NERAF_TRY(wait_ready(l.L));
   neraf_gemm_epilogue e = {};
   e.bias = reinterpret_cast<const float*>(at(pack, l.bh));
   e.act = NERAF_ACT_TANH10;
@@ -297,16 +364,29 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
     return NERAF_OK;
   }
 
-  // ---- bf16 tensor-core path
+  // ---- bf16 tensor-core path.  Critical chain on `stream`: head gradient -> dgrad GEMMs (dZ_L ... dZ_1).
+  // Everything that only CONSUMES a dZ (bias gradients, weight-gradient GEMMs, grid-feature gradients) is forked
+  // onto the helper stream as soon as that dZ exists and joined at the end.
+  SideStream* side = side_stream();
+  cudaStream_t sw = side ? side->stream : stream;
+  int ev = 0;
+  auto fork = [&]() -> int {            // make the helper stream wait for everything enqueued on `stream` so far
+    if (!side) return NERAF_OK;
+    NERAF_CHECK_CUDA(cudaEventRecord(side->ev[ev], stream));
+    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->ev[ev], 0));
+    ++ev;
+    return NERAF_OK;
+  };
   void* dzh = at(ws, l.dzh);
   void* dzht = at(ws, l.dzht);
   NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dzht, l.ldm, stream));
+  NERAF_TRY(fork());
   for (int c = 0; c < l.C; ++c) {
     const uint8_t* dzct = at(dzht, (size_t)c * l.F * l.ldm * 2);
-    NERAF_TRY(rowsum_bf16(dzct, l.F, B, l.ldm, dbiases[l.L + c], stream));
+    NERAF_TRY(rowsum_bf16(dzct, l.F, B, l.ldm, dbiases[l.L + c], sw));
     neraf_gemm_epilogue e = {};
     e.out_f32 = dweights[l.L + c]; e.ld_f32 = l.W;
-    NERAF_TRY(gemm_bf16(l.F, l.W, B, dzct, l.ldm, at(ws, l.xt[last]), l.ldm, &e, stream));
+    NERAF_TRY(gemm_bf16(l.F, l.W, B, dzct, l.ldm, at(ws, l.xt[last]), l.ldm, &e, sw));
   }
   {
     neraf_gemm_epilogue e = {};
@@ -316,30 +396,35 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
     NERAF_TRY(gemm_bf16(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wht), l.ldwht, &e, stream));
   }
   for (int i = last; i >= 0; --i) {
-    NERAF_TRY(rowsum_bf16(at(ws, l.dzt[i]), l.n[i], B, l.ldm, dbiases[i], stream));
-    if (i > 0) {
-      neraf_gemm_epilogue ew = {};
-      ew.out_f32 = dweights[i]; ew.ld_f32 = l.k[i];
-      NERAF_TRY(gemm_bf16(l.n[i], l.k[i], B, at(ws, l.dzt[i]), l.ldm, at(ws, l.xt[i - 1]), l.ldm, &ew, stream));
+    NERAF_TRY(fork());                                                    // dZ_i (both layouts) is on its way
+    if (i > 0) {                                                          // chain first: dZ_{i-1}
       neraf_gemm_epilogue ed = {};
       ed.gate = at(ws, l.x[i - 1]); ed.ldg = l.ldx[i - 1];
       if (i - 1 > 0 || denc) { ed.out_bf16 = at(ws, l.dz[i - 1]); ed.ld_bf16 = l.ldx[i - 1]; }
       ed.out_bf16_t = at(ws, l.dzt[i - 1]); ed.ld_t = l.ldm;
       NERAF_TRY(gemm_bf16(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.wt[i]), l.ldwt[i], &ed, stream));
+    } else if (denc) {
+      neraf_gemm_epilogue ee = {};
+      ee.out_f32 = denc; ee.ld_f32 = denc_ld;
+      NERAF_TRY(gemm_bf16(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.wt[0]), l.ldwt[0], &ee, stream));
+    }
+    NERAF_TRY(rowsum_bf16(at(ws, l.dzt[i]), l.n[i], B, l.ldm, dbiases[i], sw));
+    neraf_gemm_epilogue ew = {};
+    if (i > 0) {
+      ew.out_f32 = dweights[i]; ew.ld_f32 = l.k[i];
+      NERAF_TRY(gemm_bf16(l.n[i], l.k[i], B, at(ws, l.dzt[i]), l.ldm, at(ws, l.xt[i - 1]), l.ldm, &ew, sw));
     } else {
-      neraf_gemm_epilogue ew = {};
       ew.out_f32 = dweights[0] + l.G; ew.ld_f32 = ldw0;
-      NERAF_TRY(gemm_bf16(l.n[0], l.E, B, at(ws, l.dzt[0]), l.ldm, at(ws, l.enc_t), l.ldm, &ew, stream));
+      NERAF_TRY(gemm_bf16(l.n[0], l.E, B, at(ws, l.dzt[0]), l.ldm, at(ws, l.enc_t), l.ldm, &ew, sw));
       if (l.G > 0) {
-        NERAF_TRY(outer_product(dbiases[0], grid_feature, l.n[0], l.G, dweights[0], ldw0, stream));
-        if (dgrid) NERAF_TRY(grid_backward(weights[0], ldw0, dbiases[0], l.n[0], l.G, dgrid, stream));
-      }
-      if (denc) {
-        neraf_gemm_epilogue ee = {};
-        ee.out_f32 = denc; ee.ld_f32 = denc_ld;
-        NERAF_TRY(gemm_bf16(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.wt[0]), l.ldwt[0], &ee, stream));
+        NERAF_TRY(outer_product(dbiases[0], grid_feature, l.n[0], l.G, dweights[0], ldw0, sw));
+        if (dgrid) NERAF_TRY(grid_backward(weights[0], ldw0, dbiases[0], l.n[0], l.G, dgrid, sw));
       }
     }
+  }
+  if (side) {                                                             // join
+    NERAF_CHECK_CUDA(cudaEventRecord(side->done, side->stream));
+    NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
   }
   return NERAF_OK;
 }

@@ -123,6 +123,10 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "}\n" ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
+// Programmatic dependent launch: let the next kernel of the stream start its prologue while this grid drains,
+// and block until the previous grid has completed before touching anything it produced.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -256,10 +260,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish<CG>(); }
+  pdl_launch_dependents();
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -503,6 +509,16 @@ static int tile_override() {
   return v;
 }
 
+// NERAF_PDL=0 disables programmatic dependent launch (debugging).
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NERAF_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <int BN, int CG>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
   using Cfg = Config<BN, CG>;
@@ -521,10 +537,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, CG>, tmA, tmB, p));
   NERAF_CHECK_LAUNCH("umma_gemm_kernel");
   return NERAF_OK;

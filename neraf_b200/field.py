@@ -64,14 +64,15 @@ class _FieldFn(torch.autograd.Function):
             grid_c = grid.detach().float().contiguous().view(-1)
 
         need_grad = any(ctx.needs_input_grad[2:])
-        pack = module._packed(dims, prec, weights, biases)
+        pack, repack = module._packed(dims, prec, weights, biases)
         pack_b, ws_b = C.c_size_t(), C.c_size_t()
         _lib.check(lib.neraf_field_sizes(C.byref(dims), prec, B, C.byref(pack_b), C.byref(ws_b)))
         ws = torch.empty(max(ws_b.value, 16), dtype=torch.uint8, device=dev)
         out = torch.empty(B, module.sound_rez, module.N_frequencies, dtype=torch.float32, device=dev)
         w_arr, b_arr = _lib.ptr_array(weights), _lib.ptr_array(biases)
         _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_c), w_arr, b_arr,
-                                           _lib.ptr(pack), ws.data_ptr(), ws.numel(), out.data_ptr(),
+                                           _lib.ptr(pack), 0 if pack is None else pack.numel(), int(repack),
+                                           ws.data_ptr(), ws.numel(), out.data_ptr(),
                                            1 if need_grad else 0, _lib.stream_ptr(dev)))
         if need_grad:
             ctx.module, ctx.dims, ctx.prec, ctx.B, ctx.n_enc = module, dims, prec, B, n_enc
@@ -122,6 +123,10 @@ class NeRAFAudioSoundField(nn.Module):
         self.soundfield = nn.ModuleList([nn.Linear(widths[i], widths[i + 1]) for i in range(5)])
         self.STFT_linear = nn.ModuleList([nn.Linear(W, N_frequencies) for _ in range(sound_rez)])
         self._pack_cache: Dict = {}
+        # Training changes the parameters every step, so the bf16 operand copies must be re-derived every
+        # forward.  Eagerly this is detected through the parameters' version counters; inside a captured CUDA
+        # graph (no Python on replay) set always_repack so the pack kernels are part of the graph.
+        self.always_repack = False
 
     # ---- helpers -----------------------------------------------------------------------------
     def _param_lists(self):
@@ -132,24 +137,27 @@ class NeRAFAudioSoundField(nn.Module):
         return _lib.make_dims(n_grid, self.in_size - n_grid, [*TRUNK_WIDTHS, self.W], self.sound_rez,
                               self.N_frequencies)
 
-    def _packed(self, dims, prec, weights: List[torch.Tensor], biases: List[torch.Tensor]) -> Optional[torch.Tensor]:
-        """bf16 operand copies of the parameters, rebuilt only when a parameter changed (version counters)."""
+    def _packed(self, dims, prec, weights: List[torch.Tensor], biases: List[torch.Tensor]):
+        """(buffer for the bf16 operand copies, whether neraf_field_forward must re-derive them).
+
+        The copies are stale whenever a parameter changed (version counters; ``always_repack`` forces it for
+        captured graphs); the re-pack itself runs inside neraf_field_forward, overlapped with the encodings.
+        """
         if prec == _lib.PREC_FP32:
-            return None
+            return None, False
         key = (dims.n_grid, prec, weights[0].device)
         sig = tuple((t.data_ptr(), t._version) for t in (*weights, *biases))
         hit = self._pack_cache.get(key)
-        if hit is not None and hit[0] == sig:
-            return hit[1]
-        lib = _lib.lib()
-        pack_b, ws_b = C.c_size_t(), C.c_size_t()
-        _lib.check(lib.neraf_field_sizes(C.byref(dims), prec, 0, C.byref(pack_b), C.byref(ws_b)))
-        pack = hit[1] if hit is not None and hit[1].numel() >= pack_b.value else \
-            torch.empty(pack_b.value, dtype=torch.uint8, device=weights[0].device)
-        _lib.check(lib.neraf_field_pack(C.byref(dims), prec, _lib.ptr_array(weights), _lib.ptr_array(biases),
-                                        pack.data_ptr(), pack.numel(), _lib.stream_ptr(weights[0].device)))
+        if hit is not None and hit[0] == sig and not self.always_repack:
+            return hit[1], False
+        if hit is not None:
+            pack = hit[1]
+        else:
+            pack_b, ws_b = C.c_size_t(), C.c_size_t()
+            _lib.check(_lib.lib().neraf_field_sizes(C.byref(dims), prec, 0, C.byref(pack_b), C.byref(ws_b)))
+            pack = torch.empty(pack_b.value, dtype=torch.uint8, device=weights[0].device)
         self._pack_cache[key] = (sig, pack)
-        return pack
+        return pack, True
 
     def _apply(self, fn, *args, **kwargs):      # .to()/.cuda() invalidate the packed copies
         self._pack_cache = {}

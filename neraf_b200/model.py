@@ -185,3 +185,52 @@ class NeRAFAudioModel(nn.Module):
                                                         batch["waveform"].cpu().numpy(), wav_istft_prd, wav_istft_gt,
                                                         stft.cpu().numpy(), data.cpu().numpy())
         return out
+
+
+class GraphedTrainStep:
+    """One CUDA graph for get_outputs -> get_loss_dict -> backward at a fixed batch size.
+
+    At B=2048 the step is ~40 kernels of 5-60 us: launch latency and host dispatch are first-order, so the
+    whole launch sequence (bf16 re-pack of the current parameters, encodings, GEMMs on two streams, loss,
+    backward) is captured once and replayed.  ``step(batch)`` copies the batch dict (host or device
+    tensors) into static device buffers and replays; parameter gradients land in ``p.grad`` (static
+    tensors owned by the graph), the loss dict is returned as static 0-d tensors.
+    """
+
+    def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3):
+        self.model = model
+        dev = model.device
+        keys = ("time_query", "mic_pose", "source_pose", "rot", "data")
+        self.static = {k: example_batch[k].to(dev).contiguous().clone() for k in keys}
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        prev = model.field.always_repack
+        model.field.always_repack = True
+
+        def run():
+            out = model.get_outputs(self.static)
+            ld = model.get_loss_dict(out, self.static)
+            sum(ld.values()).backward()
+            return ld
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                for p in self.params:
+                    p.grad = None
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = run()
+        model.field.always_repack = prev
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        for k, dst in self.static.items():
+            src = batch[k]
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.losses
