@@ -76,30 +76,37 @@ int grid_bias(const float* W, int64_t ldw, const float* bias, const float* g, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// out[k] = sum_n W[n, k] * s[n]       (block: 32 columns x 32 row lanes, deterministic)
+// out[k] = sum_n W[n, k] * s[n]       (block: 32 columns x 32 row lanes over one slice of n; slices combined
+//                                      with one fp32 atomic per column and slice on a zeroed output)
 // ---------------------------------------------------------------------------------------------
+constexpr int kGridBwdSlices = 16;
+
 __global__ void __launch_bounds__(1024) grid_backward_kernel(const float* __restrict__ W, int64_t ldw,
                                                              const float* __restrict__ s, int64_t N, int64_t K,
                                                              float* __restrict__ out) {
   __shared__ float red[32][33];
   const int kx = threadIdx.x % 32, ny = threadIdx.x / 32;
   const int64_t k = (int64_t)blockIdx.x * 32 + kx;
+  const int64_t per = (N + gridDim.y - 1) / gridDim.y;
+  const int64_t n_lo = (int64_t)blockIdx.y * per, n_hi = n_lo + per < N ? n_lo + per : N;
   float acc = 0.f;
   if (k < K)
-    for (int64_t n = ny; n < N; n += 32) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
+    for (int64_t n = n_lo + ny; n < n_hi; n += 32) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
   red[ny][kx] = acc;
   __syncthreads();
   if (ny == 0 && k < K) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += red[i][kx];
-    out[k] = t;
+    atomicAdd(out + k, t);
   }
 }
 
 int grid_backward(const float* W, int64_t ldw, const float* s, int64_t N, int64_t K, float* out, cudaStream_t stream) {
   if (K <= 0) return NERAF_OK;
-  grid_backward_kernel<<<(unsigned)ceil_div(K, 32), 1024, 0, stream>>>(W, ldw, s, N, K, out);
+  NERAF_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)K * 4, stream));
+  dim3 grid((unsigned)ceil_div(K, 32), kGridBwdSlices);
+  grid_backward_kernel<<<grid, 1024, 0, stream>>>(W, ldw, s, N, K, out);
   NERAF_CHECK_LAUNCH("grid_backward_kernel");
   return NERAF_OK;
 }
@@ -182,11 +189,16 @@ int rowsum_bf16(const void* Xt, int64_t N, int64_t M, int64_t ld, float* out, cu
 // ---------------------------------------------------------------------------------------------
 // Gradient through y = 10*tanh(z):  dz = dout * (10 - y*y/10)
 // ---------------------------------------------------------------------------------------------
+struct HeadColsum {
+  float* ptr[8];          // one bias-gradient vector per head (C <= 8)
+  long long width;        // columns per head; 0 = no column sums
+};
+
 __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                                             int64_t M, int64_t N, float* __restrict__ dz_f32,
                                                             int64_t ld_f32, __nv_bfloat16* __restrict__ dz_bf16,
                                                             int64_t ld_bf16, __nv_bfloat16* __restrict__ dz_bf16_t,
-                                                            int64_t ld_t) {
+                                                            int64_t ld_t, HeadColsum cs) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
@@ -202,22 +214,39 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
     }
     tile[ty + i * 8][tx] = v;
   }
-  if (!dz_bf16_t) return;
+  if (!dz_bf16_t && cs.width == 0) return;
   __syncthreads();
+  if (dz_bf16_t) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t c = c0 + ty + i * 8, r = r0 + tx;
-    if (r < M && c < N) dz_bf16_t[c * ld_t + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    for (int i = 0; i < 4; ++i) {
+      const int64_t c = c0 + ty + i * 8, r = r0 + tx;
+      if (r < M && c < N) dz_bf16_t[c * ld_t + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    }
+  }
+  if (cs.width > 0 && ty == 0 && c0 + tx < N) {            // bias gradient of the heads: column sums of this tile
+    float sum = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) sum += tile[r][tx];
+    const int64_t c = c0 + tx;
+    atomicAdd(cs.ptr[c / cs.width] + (c % cs.width), sum);
   }
 }
 
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
-                  int64_t ld_bf16, void* dz_bf16_t, int64_t ld_t, cudaStream_t stream) {
+                  int64_t ld_bf16, void* dz_bf16_t, int64_t ld_t, float* const* colsum, int64_t head_width,
+                  cudaStream_t stream) {
   if (M <= 0 || N <= 0) return NERAF_OK;
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
   NERAF_REQUIRE(grid.y <= 65535, "head_backward: batch too large for one launch (%lld)", (long long)M);
+  HeadColsum cs = {};
+  if (colsum) {
+    const int64_t heads = ceil_div(N, head_width);
+    NERAF_REQUIRE(heads <= 8, "head_backward: at most 8 heads");
+    for (int64_t c = 0; c < heads; ++c) cs.ptr[c] = colsum[c];
+    cs.width = head_width;
+  }
   head_backward_kernel<<<grid, 256, 0, stream>>>(dout, y, M, N, dz_f32, ld_f32, (__nv_bfloat16*)dz_bf16, ld_bf16,
-                                                 (__nv_bfloat16*)dz_bf16_t, ld_t);
+                                                 (__nv_bfloat16*)dz_bf16_t, ld_t, cs);
   NERAF_CHECK_LAUNCH("head_backward_kernel");
   return NERAF_OK;
 }

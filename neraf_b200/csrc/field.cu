@@ -42,6 +42,7 @@ struct Layout {
   int64_t ldx[NERAF_MAX_TRUNK];
   size_t dzh, dzht;
   int64_t ld_h;
+  size_t counters, counters_bytes;   // dependency counters of the job-list kernel
   size_t ws_bytes;
 };
 
@@ -101,6 +102,8 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   l.ld_h = bf ? round_up(l.CF, 8) : l.CF;
   l.dzh = take(cur, B * l.ld_h * es);
   l.dzht = bf ? take(cur, (size_t)l.CF * l.ldm * 2) : 0;
+  l.counters_bytes = (size_t)NERAF_MEGA_MAX_JOBS * (size_t)(ceil_div(batch > 0 ? batch : 1, 256) + 32) * 4;
+  l.counters = take(cur, l.counters_bytes);
   l.ws_bytes = cur;
   return NERAF_OK;
 }
@@ -130,6 +133,29 @@ SideStream* side_stream() {
     s.ok = true;
   }
   return &s;
+}
+
+bool use_mega() {
+  static int v = -1;
+  if (v < 0) v = getenv("NERAF_NO_MEGA") ? 0 : 1;
+  return v != 0;
+}
+
+// Tile width of a job: the widest tile that still yields enough tiles to spread over the CTA pairs.
+int choose_bn(int64_t M, int64_t N) {
+  const int64_t rb = ceil_div(M, 256);
+  for (int bn = 256; bn > 64; bn /= 2)
+    if (rb * ceil_div(N, bn) >= 48) return bn;
+  return 64;
+}
+
+MegaJob make_job(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, int wait_job,
+                 int wait_all) {
+  MegaJob j = {};
+  j.M = M; j.N = N; j.K = K; j.A = A; j.lda = lda; j.B = B; j.ldb = ldb;
+  j.bn = choose_bn(M, N);
+  j.wait_job = wait_job; j.wait_all = wait_all;
+  return j;
 }
 
 inline uint8_t* at(void* base, size_t off) { return reinterpret_cast<uint8_t*>(base) + off; }
@@ -280,6 +306,42 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
   }
   else NERAF_TRY(encode_queries(q, nullptr, 0, enc, l.ld_enc, enc_t, l.ldm, (int)l.ld_enc, stream));
 
+  if (use_mega()) {
+    // One persistent launch for the whole MLP (two when the operands are being re-packed: layer 1 starts as soon
+    // as its own copies exist, the remaining layers once the helper stream has finished all of them).
+    MegaJob jobs[NERAF_MAX_TRUNK + 1];
+    const void* xin = enc;
+    int64_t ldin = l.ld_enc;
+    for (int i = 0; i <= l.L; ++i) {
+      const bool head = i == l.L;
+      MegaJob& j = jobs[i];
+      j = make_job(B, head ? l.CF : l.n[i], head ? l.W : l.k[i], xin, ldin, head ? at(pack, l.wh) : at(pack, l.w[i]),
+                   head ? l.ldwh : l.ldw[i], i - 1, 0);
+      if (head) {
+        j.epi.bias = reinterpret_cast<const float*>(at(pack, l.bh));
+        j.epi.act = NERAF_ACT_TANH10;
+        j.epi.out_f32 = out; j.epi.ld_f32 = l.CF;
+      } else {
+        j.epi.bias = i == 0 ? c1 : biases[i];
+        j.epi.act = NERAF_ACT_LEAKY;
+        j.epi.out_bf16 = at(ws, l.x[i]); j.epi.ld_bf16 = l.ldx[i];
+        if (keep) { j.epi.out_bf16_t = at(ws, l.xt[i]); j.epi.ld_t = l.ldm; }
+        xin = j.epi.out_bf16; ldin = l.ldx[i];
+      }
+    }
+    NERAF_TRY(wait_ready(0));
+    if (do_pack && side) {
+      NERAF_TRY(mega_run(jobs, 1, at(ws, l.counters), l.counters_bytes, stream));
+      NERAF_TRY(wait_ready(l.L));
+      jobs[1].wait_job = -1;
+      for (int i = 2; i <= l.L; ++i) jobs[i].wait_job = i - 2;
+      NERAF_TRY(mega_run(jobs + 1, l.L, at(ws, l.counters), l.counters_bytes, stream));
+    } else {
+      NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream));
+    }
+    return NERAF_OK;
+  }
+
   const void* x = enc;
   int64_t ldx = l.ld_enc;
   for (int i = 0; i < l.L; ++i) {
@@ -326,7 +388,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
 
   if (!bf) {
     float* dzh = reinterpret_cast<float*>(at(ws, l.dzh));
-    NERAF_TRY(head_backward(dout, out, B, l.CF, dzh, l.CF, nullptr, 0, nullptr, 0, stream));
+    NERAF_TRY(head_backward(dout, out, B, l.CF, dzh, l.CF, nullptr, 0, nullptr, 0, nullptr, 0, stream));
     const float* x_last = reinterpret_cast<const float*>(at(ws, l.x[last]));
     float* dz_last = reinterpret_cast<float*>(at(ws, l.dz[last]));
     for (int c = 0; c < l.C; ++c) {
@@ -364,6 +426,66 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
     return NERAF_OK;
   }
 
+  if (use_mega()) {
+    // ---- bf16 tensor-core path, job-list kernel: the dgrad chain and all weight-gradient GEMMs in ONE launch.
+    // Bias gradients are column sums of the fp32 dZ accumulated by the dgrad epilogues (atomics on zeroed buffers).
+    for (int i = 0; i < l.L + l.C; ++i) {
+      const size_t n = (size_t)(i < l.L ? l.n[i] : l.F);
+      NERAF_CHECK_CUDA(cudaMemsetAsync(dbiases[i], 0, n * 4, stream));
+    }
+    void* dzh = at(ws, l.dzh);
+    void* dzht = at(ws, l.dzht);
+    NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dzht, l.ldm, dbiases + l.L, l.F, stream));
+    MegaJob jobs[NERAF_MEGA_MAX_JOBS];
+    int nj = 0;
+    // dZ_last = (dZ_head W_head) * leaky'(x_last)
+    int producer = nj;
+    {
+      MegaJob& j = jobs[nj++];
+      j = make_job(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wht), l.ldwht, -1, 0);
+      j.epi.gate = at(ws, l.x[last]); j.epi.ldg = l.ldx[last];
+      j.epi.out_bf16 = at(ws, l.dz[last]); j.epi.ld_bf16 = l.ldx[last];
+      j.epi.out_bf16_t = at(ws, l.dzt[last]); j.epi.ld_t = l.ldm;
+      j.colsum = dbiases[last];
+    }
+    for (int c = 0; c < l.C; ++c) {                       // head weight gradients: operands exist already
+      MegaJob& j = jobs[nj++];
+      j = make_job(l.F, l.W, B, at(dzht, (size_t)c * l.F * l.ldm * 2), l.ldm, at(ws, l.xt[last]), l.ldm, -1, 0);
+      j.epi.out_f32 = dweights[l.L + c]; j.epi.ld_f32 = l.W;
+    }
+    for (int i = last; i >= 0; --i) {
+      const int dz_producer = producer;                   // job that writes dZ_i (both layouts)
+      if (i > 0) {                                        // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
+        producer = nj;
+        MegaJob& j = jobs[nj++];
+        j = make_job(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.wt[i]), l.ldwt[i], dz_producer, 0);
+        j.epi.gate = at(ws, l.x[i - 1]); j.epi.ldg = l.ldx[i - 1];
+        if (i - 1 > 0 || denc) { j.epi.out_bf16 = at(ws, l.dz[i - 1]); j.epi.ld_bf16 = l.ldx[i - 1]; }
+        j.epi.out_bf16_t = at(ws, l.dzt[i - 1]); j.epi.ld_t = l.ldm;
+        j.colsum = dbiases[i - 1];
+      }
+      MegaJob& w = jobs[nj++];                            // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
+      if (i > 0) {
+        w = make_job(l.n[i], l.k[i], B, at(ws, l.dzt[i]), l.ldm, at(ws, l.xt[i - 1]), l.ldm, dz_producer, 1);
+        w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
+      } else {
+        w = make_job(l.n[0], l.E, B, at(ws, l.dzt[0]), l.ldm, at(ws, l.enc_t), l.ldm, dz_producer, 1);
+        w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
+        if (denc) {
+          MegaJob& e = jobs[nj++];
+          e = make_job(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.wt[0]), l.ldwt[0], dz_producer, 0);
+          e.epi.out_f32 = denc; e.epi.ld_f32 = denc_ld;
+        }
+      }
+    }
+    NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream));
+    if (l.G > 0) {
+      NERAF_TRY(outer_product(dbiases[0], grid_feature, l.n[0], l.G, dweights[0], ldw0, stream));
+      if (dgrid) NERAF_TRY(grid_backward(weights[0], ldw0, dbiases[0], l.n[0], l.G, dgrid, stream));
+    }
+    return NERAF_OK;
+  }
+
   // ---- bf16 tensor-core path.  Critical chain on `stream`: head gradient -> dgrad GEMMs (dZ_L ... dZ_1).
   // Everything that only CONSUMES a dZ (bias gradients, weight-gradient GEMMs, grid-feature gradients) is forked
   // onto the helper stream as soon as that dZ exists and joined at the end.
@@ -379,7 +501,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
   };
   void* dzh = at(ws, l.dzh);
   void* dzht = at(ws, l.dzht);
-  NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dzht, l.ldm, stream));
+  NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dzht, l.ldm, nullptr, 0, stream));
   NERAF_TRY(fork());
   for (int c = 0; c < l.C; ++c) {
     const uint8_t* dzct = at(dzht, (size_t)c * l.F * l.ldm * 2);

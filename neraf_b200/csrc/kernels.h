@@ -20,6 +20,22 @@ int gemm_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t a_rs, int6
 int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
               const neraf_gemm_epilogue* epi, cudaStream_t stream);
 
+// gemm_mega.cu: a list of dependent bf16 GEMMs (same TN form and epilogue as gemm_bf16) executed by ONE
+// persistent launch with tile-level scheduling and row-block dependency tracking.
+#define NERAF_MEGA_MAX_JOBS 24
+struct MegaJob {
+  int64_t M, N, K;
+  const void* A; int64_t lda;      // (M, K) bf16 K-major
+  const void* B; int64_t ldb;      // (N, K) bf16 K-major
+  int bn;                          // tile width: 64, 128 or 256 (tile height is 256: one CTA pair)
+  int wait_job;                    // index of the job that produces operand A (and/or B), or -1
+  int wait_all;                    // 0: tile (row block rb) needs row block rb of wait_job; 1: needs every row block
+  neraf_gemm_epilogue epi;
+  float* colsum;                   // optional (N): += column sums of the stored values (bias gradient), fp32 atomics
+};
+int mega_counters_bytes(const MegaJob* jobs, int n_jobs, size_t* bytes);
+int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream);
+
 // elementwise.cu
 int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out, void* out_t,
                  int64_t ld_t, cudaStream_t stream);
@@ -35,7 +51,9 @@ int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cud
 // out[n] = sum_m Xt[n*ld + m]  bf16 transposed (N,M)
 int rowsum_bf16(const void* Xt, int64_t N, int64_t M, int64_t ld, float* out, cudaStream_t stream);
 // dz = dout * (10 - y^2/10): gradient through 10*tanh; outputs fp32 (M,N) and/or bf16 (M,N) + bf16^T (N,M)
+// colsum (optional): per-head bias-gradient buffers, column n is added (atomics) to colsum[n / head_width][n % head_width]
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
-                  int64_t ld_bf16, void* dz_bf16_t, int64_t ld_t, cudaStream_t stream);
+                  int64_t ld_bf16, void* dz_bf16_t, int64_t ld_t, float* const* colsum, int64_t head_width,
+                  cudaStream_t stream);
 
 }  // namespace neraf
