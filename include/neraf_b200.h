@@ -208,6 +208,33 @@ typedef struct {
 NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
                     const neraf_gemm_epilogue* epi, neraf_stream_t stream);
 
+/* A LIST of dependent bf16 GEMMs executed by ONE persistent launch (tile-level scheduling over CTA pairs, row-block
+ * dependency counters): the form in which neraf_field_forward/backward run the MLP.  Same TN contract and epilogue as
+ * neraf_gemm_bf16 except: no transposed / accumulating outputs, at most one of out_bf16 / out_f32 per job.
+ *   a_mn / b_mn : operand is stored (K, M) resp. (K, N) row-major and consumed MN-major (weight gradients contract
+ *                 over the batch, the outer dimension of row-major activations) instead of (M, K) / (N, K).
+ *   bn          : tile width 64 / 128 / 256 (>= 128 when b_mn); the tile height is 256 rows (one CTA pair).
+ *   wait_job    : index (< own index) of the job whose outputs this job reads, or -1.  wait_all == 0: tile of row
+ *                 block r (256 rows) starts when row block r of wait_job is complete (both jobs have the same M);
+ *                 wait_all == 1: when every row block of wait_job is complete.
+ *   colsum      : optional dev fp32 (N), must be zeroed by the caller: += column sums of the fp32 results.
+ * counters: dev scratch, >= 4 * sum_j ceil(M_j / 256) bytes. */
+#define NERAF_MAX_GEMM_JOBS 24
+typedef struct {
+  int64_t M, N, K;
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  int32_t a_mn, b_mn;
+  int32_t bn;
+  int32_t wait_job;
+  int32_t wait_all;
+  neraf_gemm_epilogue epi;
+  float* colsum;
+} neraf_gemm_job;
+
+NERAF_API int neraf_gemm_bf16_jobs(const neraf_gemm_job* jobs, int n_jobs, void* counters, size_t counters_bytes,
+                         neraf_stream_t stream);
+
 /* Pin the tile shape of neraf_gemm_bf16 (tuning / tests): code = cta_group*1000 + tile_n with cta_group in
  * {1,2}, tile_n in {64,128,256}; 0 restores the built-in cost model. */
 NERAF_API int neraf_gemm_bf16_set_tile(int code);

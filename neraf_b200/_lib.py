@@ -46,6 +46,12 @@ class GemmEpilogue(C.Structure):
                 ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("accumulate_f32", C.c_int32)]
 
 
+class GemmJob(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("A", C.c_void_p), ("lda", C.c_int64),
+                ("B", C.c_void_p), ("ldb", C.c_int64), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bn", C.c_int32),
+                ("wait_job", C.c_int32), ("wait_all", C.c_int32), ("epi", GemmEpilogue), ("colsum", C.c_void_p)]
+
+
 class GlParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop", C.c_int32), ("n_frames", C.c_int32),
                 ("n_iter", C.c_int32), ("momentum", C.c_float), ("input_is_log", C.c_int32)]
@@ -76,6 +82,7 @@ SIGNATURES = {
     "neraf_gemm_f32": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _i64,
                                   _i32, _vp]),
     "neraf_gemm_bf16": (C.c_int, [_i64, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(GemmEpilogue), _vp]),
+    "neraf_gemm_bf16_jobs": (C.c_int, [C.POINTER(GemmJob), C.c_int, _vp, _sz, _vp]),
     "neraf_gemm_bf16_set_tile": (C.c_int, [C.c_int]),
     "neraf_convert_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
 }

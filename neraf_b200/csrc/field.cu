@@ -43,6 +43,7 @@ struct Layout {
   size_t dzh, dzht;
   int64_t ld_h;
   size_t counters, counters_bytes;   // dependency counters of the job-list kernel
+  size_t dwh;                        // (C*F, W) fp32 joint head weight gradient (only used when C > 1)
   size_t ws_bytes;
 };
 
@@ -104,6 +105,7 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   l.dzht = bf ? take(cur, (size_t)l.CF * l.ldm * 2) : 0;
   l.counters_bytes = (size_t)NERAF_MEGA_MAX_JOBS * (size_t)(ceil_div(batch > 0 ? batch : 1, 256) + 32) * 4;
   l.counters = take(cur, l.counters_bytes);
+  l.dwh = (bf && l.C > 1) ? take(cur, (size_t)l.CF * l.W * 4) : 0;
   l.ws_bytes = cur;
   return NERAF_OK;
 }
@@ -155,6 +157,15 @@ MegaJob make_job(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, co
   j.M = M; j.N = N; j.K = K; j.A = A; j.lda = lda; j.B = B; j.ldb = ldb;
   j.bn = choose_bn(M, N);
   j.wait_job = wait_job; j.wait_all = wait_all;
+  return j;
+}
+
+// dW (N_out, K_in) = dZ^T X with dZ (B, N_out) and X (B, K_in) both row-major: both operands MN-major.
+MegaJob make_wgrad_job(int64_t n_out, int64_t k_in, int64_t batch, const void* dz, int64_t ld_dz, const void* x,
+                       int64_t ld_x, int wait_job) {
+  MegaJob j = make_job(n_out, k_in, batch, dz, ld_dz, x, ld_x, wait_job, 1);
+  j.a_mn = 1; j.b_mn = 1;
+  if (j.bn < 128) j.bn = 128;
   return j;
 }
 
@@ -324,8 +335,7 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
       } else {
         j.epi.bias = i == 0 ? c1 : biases[i];
         j.epi.act = NERAF_ACT_LEAKY;
-        j.epi.out_bf16 = at(ws, l.x[i]); j.epi.ld_bf16 = l.ldx[i];
-        if (keep) { j.epi.out_bf16_t = at(ws, l.xt[i]); j.epi.ld_t = l.ldm; }
+        j.epi.out_bf16 = at(ws, l.x[i]); j.epi.ld_bf16 = l.ldx[i];     // backward consumes it MN-major: no transpose
         xin = j.epi.out_bf16; ldin = l.ldx[i];
       }
     }
@@ -434,8 +444,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
       NERAF_CHECK_CUDA(cudaMemsetAsync(dbiases[i], 0, n * 4, stream));
     }
     void* dzh = at(ws, l.dzh);
-    void* dzht = at(ws, l.dzht);
-    NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dzht, l.ldm, dbiases + l.L, l.F, stream));
+    NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, nullptr, 0, dbiases + l.L, l.F, stream));
     MegaJob jobs[NERAF_MEGA_MAX_JOBS];
     int nj = 0;
     // dZ_last = (dZ_head W_head) * leaky'(x_last)
@@ -445,31 +454,31 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
       j = make_job(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wht), l.ldwht, -1, 0);
       j.epi.gate = at(ws, l.x[last]); j.epi.ldg = l.ldx[last];
       j.epi.out_bf16 = at(ws, l.dz[last]); j.epi.ld_bf16 = l.ldx[last];
-      j.epi.out_bf16_t = at(ws, l.dzt[last]); j.epi.ld_t = l.ldm;
       j.colsum = dbiases[last];
     }
-    for (int c = 0; c < l.C; ++c) {                       // head weight gradients: operands exist already
+    {                                                     // head weight gradients (all heads in one GEMM)
       MegaJob& j = jobs[nj++];
-      j = make_job(l.F, l.W, B, at(dzht, (size_t)c * l.F * l.ldm * 2), l.ldm, at(ws, l.xt[last]), l.ldm, -1, 0);
-      j.epi.out_f32 = dweights[l.L + c]; j.epi.ld_f32 = l.W;
+      j = make_wgrad_job(l.CF, l.W, B, dzh, l.ld_h, at(ws, l.x[last]), l.ldx[last], -1);
+      j.wait_all = 0;
+      j.epi.out_f32 = l.C == 1 ? dweights[l.L] : reinterpret_cast<float*>(at(ws, l.dwh));
+      j.epi.ld_f32 = l.W;
     }
     for (int i = last; i >= 0; --i) {
-      const int dz_producer = producer;                   // job that writes dZ_i (both layouts)
+      const int dz_producer = producer;                   // job that writes dZ_i
       if (i > 0) {                                        // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
         producer = nj;
         MegaJob& j = jobs[nj++];
         j = make_job(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.wt[i]), l.ldwt[i], dz_producer, 0);
         j.epi.gate = at(ws, l.x[i - 1]); j.epi.ldg = l.ldx[i - 1];
-        if (i - 1 > 0 || denc) { j.epi.out_bf16 = at(ws, l.dz[i - 1]); j.epi.ld_bf16 = l.ldx[i - 1]; }
-        j.epi.out_bf16_t = at(ws, l.dzt[i - 1]); j.epi.ld_t = l.ldm;
+        j.epi.out_bf16 = at(ws, l.dz[i - 1]); j.epi.ld_bf16 = l.ldx[i - 1];
         j.colsum = dbiases[i - 1];
       }
       MegaJob& w = jobs[nj++];                            // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
       if (i > 0) {
-        w = make_job(l.n[i], l.k[i], B, at(ws, l.dzt[i]), l.ldm, at(ws, l.xt[i - 1]), l.ldm, dz_producer, 1);
+        w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
         w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
       } else {
-        w = make_job(l.n[0], l.E, B, at(ws, l.dzt[0]), l.ldm, at(ws, l.enc_t), l.ldm, dz_producer, 1);
+        w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
         w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
         if (denc) {
           MegaJob& e = jobs[nj++];
@@ -479,6 +488,10 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
       }
     }
     NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream));
+    if (l.C > 1)
+      for (int c = 0; c < l.C; ++c)
+        NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,
+                                         cudaMemcpyDeviceToDevice, stream));
     if (l.G > 0) {
       NERAF_TRY(outer_product(dbiases[0], grid_feature, l.n[0], l.G, dweights[0], ldw0, stream));
       if (dgrid) NERAF_TRY(grid_backward(weights[0], ldw0, dbiases[0], l.n[0], l.G, dgrid, stream));

@@ -15,10 +15,20 @@
 // smaller index, so the smallest unfinished tile is always runnable.
 //
 // Tile = 256 x bn (bn in {64,128,256}, per job) on a CTA PAIR (tcgen05 cta_group::2, see gemm_umma.cu): each
-// CTA stages its 128 rows of A and bn/2 rows of B per 64-wide k-block through a 6-stage TMA/mbarrier ring, the
+// CTA stages its 128 rows of A and bn/2 rows of B per 64-deep k-block through a 6-stage TMA/mbarrier ring, the
 // leader issues the MMAs, two 256-column TMEM accumulator stages overlap the epilogue with the next tile.
-// Cross-SM visibility: epilogue stores -> __threadfence -> atomicAdd(counter); consumer: ld.acquire spin ->
-// fence.proxy.async -> TMA loads.
+//
+// Operand layouts.  K-major operands (row-major with the contraction innermost) are the forward / dgrad case.
+// The weight gradient dW = dZ^T X contracts over the BATCH, which is the OUTER dimension of the row-major
+// activations: both operands are consumed MN-major (tcgen05 descriptor major bit, TMA boxes of 64 contiguous
+// MN elements x 64 batch rows), so no transposed copy of any activation or gradient is ever written.
+//
+// Epilogue.  TMEM -> registers (lane = row) -> bias / LeakyReLU / 10 tanh / LeakyReLU' gate -> bf16 (or fp32)
+// packed into a 128-byte-swizzled 32-row staging tile per warp -> one TMA store per 64 (32) columns; M/N tails
+// are clipped by the tensor map.  Bias gradients are column sums taken from the fp32 values with a
+// recursive-halving shuffle reduction (31 shuffles per 32 x 32 block) and one atomic per column.
+// Cross-SM visibility: stores complete (bulk wait_group) -> __threadfence -> atomicAdd(counter); consumer:
+// ld.acquire spin -> fence.proxy.async -> TMA loads.
 #include <cstdlib>
 #include <mutex>
 
@@ -33,21 +43,21 @@ constexpr int MEGA_THREADS = 192;
 constexpr int MEGA_STAGES = 6;
 constexpr int MEGA_A_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB
 constexpr int MEGA_B_BYTES = 128 * BLOCK_K * 2;                // up to bn/2 = 128 rows: 16 KB
-constexpr int MEGA_EPI_BYTES = 4 * 32 * STAGE_PITCH * 4;
-constexpr int MEGA_SMEM_BYTES = 1024 + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES) + MEGA_EPI_BYTES + (2 * MEGA_STAGES + 4) * 8 + 16;
+constexpr int MEGA_OUT_BYTES = 32 * 128;                       // per-warp staging tile: 32 rows x 128 B
+constexpr int MEGA_SMEM_BYTES = 1024 + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES) + 4 * MEGA_OUT_BYTES + (2 * MEGA_STAGES + 4) * 8 + 16;
 constexpr int MEGA_TMEM_COLS = 512;
 constexpr int MEGA_ACC_COLS = 256;
+constexpr int MN_BOX_BYTES = 64 * 128;                         // one MN-major box: 64 k-rows x 64 MN elements
 
 struct alignas(64) DeviceJob {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOutB, tmOutF;
   int M, N, K, bn;
   int tile_start, num_m, num_n, cnt_off;
   int wait_job, wait_all, wait_target, wait_nrb, wait_cnt_off;
-  int act, accumulate_f32, pad0;
+  int act, a_mn, b_mn, f32_tma;
   const float* bias;
   const __nv_bfloat16* gate; long long ldg;
-  __nv_bfloat16* out_bf16; long long ld_bf16;
-  __nv_bfloat16* out_bf16_t; long long ld_t;
+  int has_out_bf16, pad0;
   float* out_f32; long long ld_f32;
   float* colsum;
 };
@@ -64,6 +74,7 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target) {
   if (ld_acquire(p) >= target) return;
@@ -75,14 +86,50 @@ __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int t
   }
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// MN-major, 128-byte-swizzled operand: 64 contiguous MN elements per k row (128 B), 8-row groups 1024 B apart
+// (SBO), the next block of 64 MN elements one TMA box (8 KB) further (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(MN_BOX_BYTES >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Column sums of a 32 (rows = lanes) x 32 (registers) block: lane i ends up with sum over lanes of v[i].
+__device__ __forceinline__ float column_sums_32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = upper ? v[i + s] : v[i];
+      const float send = upper ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) {
   constexpr int CG = 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + MEGA_STAGES * MEGA_A_BYTES;
-  float* stage_buf = reinterpret_cast<float*>(smem + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_buf) + MEGA_EPI_BYTES);
+  uint8_t* out_buf = smem + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES);       // 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_buf + 4 * MEGA_OUT_BYTES);
   uint64_t* empty_bar = full_bar + MEGA_STAGES;
   uint64_t* tmem_full = empty_bar + MEGA_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -113,7 +160,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
         const DeviceJob& J = P.jobs[j];
         const int local = tile - J.tile_start;
         const int mt = local / J.num_n, nt = local % J.num_n;          // row-block major: a row block completes early
-        // ---- dependencies: operands written by earlier tiles of this launch (other SMs, generic proxy)
+        // ---- dependencies: operands written by earlier tiles of this launch (other SMs)
         if (J.wait_job >= 0) {
           if (J.wait_all) {
             for (int rb = 0; rb < J.wait_nrb; ++rb) spin_until(P.counters + J.wait_cnt_off + rb, (unsigned)J.wait_target);
@@ -125,13 +172,25 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
         const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
         const int b_rows = J.bn / CG;
         const uint32_t stage_bytes = (uint32_t)(MEGA_A_BYTES + b_rows * BLOCK_K * 2) * CG;
+        const int a_row0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
+        const int b_row0 = nt * J.bn + (int)cta_rank * b_rows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           if (is_leader) mbar_expect_tx(full_bar + stage, stage_bytes);
-          tma_load_2d<CG>(smem_a + stage * MEGA_A_BYTES, &J.tmA, full_bar + stage, kb * BLOCK_K,
-                          mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M);
-          tma_load_2d<CG>(smem_b + stage * MEGA_B_BYTES, &J.tmB, full_bar + stage, kb * BLOCK_K,
-                          nt * J.bn + (int)cta_rank * b_rows);
+          uint8_t* sa = smem_a + stage * MEGA_A_BYTES;
+          uint8_t* sb = smem_b + stage * MEGA_B_BYTES;
+          if (!J.a_mn) {
+            tma_load_2d<CG>(sa, &J.tmA, full_bar + stage, kb * BLOCK_K, a_row0);
+          } else {                                        // matrix is (K rows, MN cols): coordinates {mn, k}
+            tma_load_2d<CG>(sa, &J.tmA, full_bar + stage, a_row0, kb * BLOCK_K);
+            tma_load_2d<CG>(sa + MN_BOX_BYTES, &J.tmA, full_bar + stage, a_row0 + 64, kb * BLOCK_K);
+          }
+          if (!J.b_mn) {
+            tma_load_2d<CG>(sb, &J.tmB, full_bar + stage, kb * BLOCK_K, b_row0);
+          } else {
+            tma_load_2d<CG>(sb, &J.tmB, full_bar + stage, b_row0, kb * BLOCK_K);
+            if (b_rows > 64) tma_load_2d<CG>(sb + MN_BOX_BYTES, &J.tmB, full_bar + stage, b_row0 + 64, kb * BLOCK_K);
+          }
           if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -145,7 +204,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
         while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
         const DeviceJob& J = P.jobs[j];
         const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
-        const uint32_t idesc = make_idesc(BLOCK_M * CG, J.bn);
+        const bool a_mn = J.a_mn != 0, b_mn = J.b_mn != 0;
+        const uint32_t idesc = make_idesc(BLOCK_M * CG, J.bn) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+        // per UMMA_K = 16 step: K-major +32 B inside the swizzle row; MN-major +16 k-rows x 128 B
+        const uint64_t a_step = a_mn ? (2048 >> 4) : (32 >> 4);
+        const uint64_t b_step = b_mn ? (2048 >> 4) : (32 >> 4);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tmem_empty + as, aphase ^ 1);
@@ -154,11 +217,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * MEGA_A_BYTES));
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * MEGA_B_BYTES));
+          const uint32_t sa = smem_u32(smem_a + stage * MEGA_A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * MEGA_B_BYTES);
+          const uint64_t adesc = a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+          const uint64_t bdesc = b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16<CG>(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_bf16<CG>(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
           umma_commit<CG>(empty_bar + stage);
           if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -168,7 +233,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    float* sbuf = stage_buf + (warp - 2) * 32 * STAGE_PITCH;
+    uint8_t* wbuf = out_buf + (warp - 2) * MEGA_OUT_BYTES;       // this warp's 32 x 128 B staging tile
+    float* wbuf_f = reinterpret_cast<float*>(wbuf);
     int it = 0, j = 0;
     for (int tile = unit; tile < P.num_tiles; tile += num_units, ++it) {
       while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
@@ -181,23 +247,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       const float* bias = J.bias;
       const int act = J.act;
       const __nv_bfloat16* gate = J.gate;
-      __nv_bfloat16* out_bf16 = J.out_bf16;
-      __nv_bfloat16* out_bf16_t = J.out_bf16_t;
+      const long long ldg = J.ldg;
+      const bool out_b = J.has_out_bf16 != 0;
       float* out_f32 = J.out_f32;
+      const long long ld_f32 = J.ld_f32;
+      const bool f32_tma = J.f32_tma != 0;
       float* colsum = J.colsum;
-      const long long ldg = J.ldg, ld_bf16 = J.ld_bf16, ld_t = J.ld_t, ld_f32 = J.ld_f32;
-      const bool stage_needed = out_bf16 || out_f32 || colsum;
       mbar_wait(tmem_full + as, aphase);
       tc_fence_after();
       const int m_base = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M + quarter * 32;
       const int m = m_base + lane;
       const bool row_ok = m < M;
+      const int nchunks = bn / 32;
 #pragma unroll 1
-      for (int c = 0; c < bn / 32; ++c) {
+      for (int c = 0; c < nchunks; ++c) {
         const int n0 = nt * bn + c * 32;
         if (n0 >= N) break;
         float v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MEGA_ACC_COLS + c * 32), v);
+        if (c == nchunks - 1 || n0 + 32 >= N) {           // accumulator fully read: hand the TMEM stage back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (is_leader) mbar_arrive(tmem_empty + as);
+            else mbar_arrive_remote(tmem_empty + as, 0);
+          }
+        }
         const bool full_chunk = n0 + 32 <= N;
         if (bias) {
 #pragma unroll
@@ -227,65 +302,82 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
               if (n0 + q < N) v[q] *= __bfloat162float(g[q]) > 0.f ? 1.f : kLeakySlope;
           }
         }
-        if (out_bf16_t && row_ok) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (full_chunk || n0 + q < N) out_bf16_t[(long long)(n0 + q) * ld_t + m] = __float2bfloat16_rn(v[q]);
-        }
-        if (stage_needed) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) sbuf[lane * STAGE_PITCH + q] = row_ok ? v[q] : 0.f;
-          __syncwarp();
-          const int n = n0 + lane;
-          if (colsum && n < N) {                          // bias gradient: column sums of this 32 x 32 block (fp32)
-            float s = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) s += sbuf[r * STAGE_PITCH + lane];
-            atomicAdd(colsum + n, s);
+        // ---- bf16 row-major output: two 32-column chunks share one 64-column (128 B) staging tile / TMA store
+        if (out_b) {
+          const int half = c & 1;
+          if (half == 0) {                                // staging tile is about to be rewritten
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
           }
-          if (out_f32 && n < N) {
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int mm = m_base + r;
-              if (mm >= M) break;
-              float* dst = out_f32 + (long long)mm * ld_f32 + n;
-              const float val = sbuf[r * STAGE_PITCH + lane];
-              *dst = J.accumulate_f32 ? *dst + val : val;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+            const int chunk16 = half * 4 + i;             // 16-byte chunk inside the 128-byte row
+            *reinterpret_cast<uint4*>(wbuf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = pk;
+          }
+          const bool last_half = half == 1 || c == nchunks - 1 || n0 + 32 >= N;
+          if (last_half) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&J.tmOutB, wbuf, n0 - half * 32, m_base);
+              bulk_commit();
             }
           }
-          if (out_bf16) {
-            const int c0 = (lane & 3) * 8;
+        }
+        // ---- fp32 row-major output
+        if (out_f32) {
+          if (f32_tma) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = i * 8 + (lane >> 2);
-              const int mm = m_base + r;
-              if (mm < M) {
-                const float* s = sbuf + r * STAGE_PITCH + c0;
-                __nv_bfloat16* dst = out_bf16 + (long long)mm * ld_bf16 + n0 + c0;
-                if (n0 + c0 + 8 <= N) {
-                  uint4 pk;
-                  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+            for (int i = 0; i < 8; ++i) {
+              const float4 pk = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+              *reinterpret_cast<float4*>(wbuf + lane * 128 + ((i ^ (lane & 7)) << 4)) = pk;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&J.tmOutF, wbuf, n0, m_base);
+              bulk_commit();
+            }
+          } else {
+            // row stride not 16-byte aligned (e.g. (B, 513) outputs): transpose through the staging tile
+            // (XOR-swizzled 32 x 32 floats, conflict-free both ways) so that lanes write consecutive columns
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(s[2 * e], s[2 * e + 1]);
-                  *reinterpret_cast<uint4*>(dst) = pk;
-                } else {
-                  for (int e = 0; e < 8; ++e)
-                    if (n0 + c0 + e < N) dst[e] = __float2bfloat16_rn(s[e]);
-                }
+            for (int q = 0; q < 32; ++q) wbuf_f[lane * 32 + (q ^ lane)] = v[q];
+            __syncwarp();
+            const int n = n0 + lane;
+            if (n < N) {
+#pragma unroll 4
+              for (int r = 0; r < 32; ++r) {
+                const int mm = m_base + r;
+                if (mm >= M) break;
+                out_f32[(long long)mm * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
+        }
+        // ---- bias gradient: column sums of the fp32 values (destroys v)
+        if (colsum) {
+          if (!row_ok) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = 0.f;
+          }
+          const float s = column_sums_32(v, lane);
+          if (n0 + lane < N) atomicAdd(colsum + n0 + lane, s);
         }
       }
-      tc_fence_before();
-      __threadfence();                               // this warp's stores are visible device-wide ...
+      if (lane == 0) bulk_wait_all0();               // this warp's TMA stores have been performed
+      __threadfence();                               // ... and every store of the tile is visible device-wide
       __syncwarp();
-      if (lane == 0) {
-        atomicAdd(P.counters + J.cnt_off + mt, 1u);  // ... before the row block is reported complete (8 arrivals / tile)
-        if (is_leader) mbar_arrive(tmem_empty + as);
-        else mbar_arrive_remote(tmem_empty + as, 0);
-      }
+      if (lane == 0) atomicAdd(P.counters + J.cnt_off + mt, 1u);   // row block progress (8 arrivals per tile)
     }
   }
 
@@ -299,14 +391,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
 
 }  // namespace umma
 
-int get_tensor_map_bf16(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out);
-
-int mega_counters_bytes(const MegaJob* jobs, int n_jobs, size_t* bytes) {
-  size_t total = 0;
-  for (int i = 0; i < n_jobs; ++i) total += (size_t)ceil_div(jobs[i].M, 256);
-  *bytes = total * sizeof(unsigned int);
-  return NERAF_OK;
-}
+int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+                      CUtensorMap* out);
 
 int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream) {
   using namespace umma;
@@ -321,12 +407,18 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     const MegaJob& s = jobs[i];
     NERAF_REQUIRE(s.M > 0 && s.N > 0 && s.K > 0, "mega_run: job %d has an empty dimension", i);
     NERAF_REQUIRE(s.bn == 64 || s.bn == 128 || s.bn == 256, "mega_run: job %d tile width %d", i, s.bn);
-    NERAF_REQUIRE(s.lda % 8 == 0 && s.ldb % 8 == 0 && s.lda >= s.K && s.ldb >= s.K, "mega_run: job %d operand strides", i);
+    NERAF_REQUIRE(!s.b_mn || s.bn >= 128, "mega_run: job %d: an MN-major B operand needs a tile width >= 128", i);
     NERAF_REQUIRE(s.wait_job < i, "mega_run: job %d depends on a later job", i);
-    if (s.epi.out_bf16) NERAF_REQUIRE(s.epi.ld_bf16 % 8 == 0 && ((uintptr_t)s.epi.out_bf16 % 16) == 0, "mega_run: job %d out_bf16 alignment", i);
+    NERAF_REQUIRE(!s.epi.out_bf16_t && !s.epi.accumulate_f32, "mega_run: job %d: transposed / accumulating outputs are not supported", i);
+    NERAF_REQUIRE(!(s.epi.out_bf16 && s.epi.out_f32), "mega_run: job %d: one output per job", i);
+    NERAF_REQUIRE(s.epi.act >= 0 && s.epi.act <= 2, "mega_run: job %d: unknown activation", i);
     DeviceJob& d = P.jobs[i];
-    NERAF_TRY(get_tensor_map_bf16(s.A, s.M, s.K, s.lda, BLOCK_M, &d.tmA));
-    NERAF_TRY(get_tensor_map_bf16(s.B, s.N, s.K, s.ldb, s.bn / 2, &d.tmB));
+    // K-major operand: matrix (MN rows, K cols), box (rows, 64 k).  MN-major: matrix (K rows, MN cols), box (64 k, 64 mn).
+    if (!s.a_mn) NERAF_TRY(get_tensor_map_2d(s.A, 2, s.M, s.K, s.lda, BLOCK_M, BLOCK_K, &d.tmA));
+    else NERAF_TRY(get_tensor_map_2d(s.A, 2, s.K, s.M, s.lda, BLOCK_K, 64, &d.tmA));
+    if (!s.b_mn) NERAF_TRY(get_tensor_map_2d(s.B, 2, s.N, s.K, s.ldb, s.bn / 2, BLOCK_K, &d.tmB));
+    else NERAF_TRY(get_tensor_map_2d(s.B, 2, s.K, s.N, s.ldb, BLOCK_K, 64, &d.tmB));
+    d.a_mn = s.a_mn; d.b_mn = s.b_mn;
     d.M = (int)s.M; d.N = (int)s.N; d.K = (int)s.K; d.bn = s.bn;
     d.num_m = (int)ceil_div(s.M, 256); d.num_n = (int)ceil_div(s.N, s.bn);
     d.tile_start = tile; tile += d.num_m * d.num_n;
@@ -338,11 +430,13 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
       d.wait_cnt_off = cnt_off[s.wait_job];
       if (!s.wait_all) NERAF_REQUIRE(nrb[s.wait_job] == d.num_m, "mega_run: job %d row blocks differ from its producer", i);
     } else { d.wait_target = 0; d.wait_nrb = 0; d.wait_cnt_off = 0; }
-    d.act = s.epi.act; d.accumulate_f32 = s.epi.accumulate_f32; d.bias = s.epi.bias;
+    d.act = s.epi.act; d.bias = s.epi.bias;
     d.gate = (const __nv_bfloat16*)s.epi.gate; d.ldg = s.epi.ldg;
-    d.out_bf16 = (__nv_bfloat16*)s.epi.out_bf16; d.ld_bf16 = s.epi.ld_bf16;
-    d.out_bf16_t = (__nv_bfloat16*)s.epi.out_bf16_t; d.ld_t = s.epi.ld_t;
+    d.has_out_bf16 = s.epi.out_bf16 != nullptr;
+    if (s.epi.out_bf16) NERAF_TRY(get_tensor_map_2d(s.epi.out_bf16, 2, s.M, s.N, s.epi.ld_bf16, 32, 64, &d.tmOutB));
     d.out_f32 = s.epi.out_f32; d.ld_f32 = s.epi.ld_f32;
+    d.f32_tma = s.epi.out_f32 && (s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0);
+    if (d.f32_tma) NERAF_TRY(get_tensor_map_2d(s.epi.out_f32, 4, s.M, s.N, s.epi.ld_f32, 32, 32, &d.tmOutF));
     d.colsum = s.colsum;
   }
   P.num_tiles = tile;
@@ -374,3 +468,8 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
 }
 
 }  // namespace neraf
+
+extern "C" int neraf_gemm_bf16_jobs(const neraf_gemm_job* jobs, int n_jobs, void* counters, size_t counters_bytes,
+                                    neraf_stream_t stream) {
+  return neraf::mega_run(jobs, n_jobs, counters, counters_bytes, (cudaStream_t)stream);
+}

@@ -284,9 +284,10 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; int64_t rows, cols, ld; int box_rows;
+  const void* ptr; int64_t rows, cols, ld; int box_rows, box_cols, elem_bytes;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && elem_bytes == o.elem_bytes;
   }
 };
 struct MapKeyHash {
@@ -295,17 +296,19 @@ struct MapKeyHash {
     h = h * 1000003u ^ (size_t)k.rows;
     h = h * 1000003u ^ (size_t)k.cols;
     h = h * 1000003u ^ (size_t)k.ld;
-    h = h * 1000003u ^ (size_t)k.box_rows;
+    h = h * 1000003u ^ (size_t)(k.box_rows * 4096 + k.box_cols * 8 + k.elem_bytes);
     return h;
   }
 };
 
-// (rows, cols) bf16 matrix with row stride ld elements; box = box_rows x 64 columns, 128-byte swizzle,
-// out-of-bounds elements read as zero (this is what pads K, M and N tails).
-static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+// Row-major (rows, cols) matrix of bf16 (elem_bytes 2) or fp32 (4) with row stride ld elements; box = box_rows x
+// box_cols with box_cols * elem_bytes == 128 (one 128-byte swizzle row).  Loads: out-of-bounds elements read as
+// zero (this is what pads K, M and N tails); stores: out-of-bounds elements are dropped.
+static int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                             int box_cols, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, rows, cols, ld, box_rows};
+  const MapKey key{ptr, rows, cols, ld, box_rows, box_cols, elem_bytes};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -313,17 +316,19 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(NERAF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  NERAF_REQUIRE(box_cols * elem_bytes == 128 && box_rows >= 1 && box_rows <= 256, "tensor map: bad box %d x %d", box_rows, box_cols);
+  NERAF_REQUIRE((ld * elem_bytes) % 16 == 0 && ((uintptr_t)ptr % 16) == 0, "tensor map: base / row stride must be 16-byte aligned");
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estride[2] = {1, 1};
   CUtensorMap tm;
-  const CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(&tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return set_error(NERAF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld x %lld ld %lld box %d", (int)r,
-                     (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return set_error(NERAF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld x %lld ld %lld box %d x %d", (int)r,
+                     (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
   {
     std::lock_guard<std::mutex> lock(mu);
     if (cache.size() > 8192) cache.clear();
@@ -331,6 +336,10 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   }
   *out = tm;
   return NERAF_OK;
+}
+
+static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  return get_tensor_map_2d(ptr, 2, rows, cols, ld, box_rows, BLOCK_K, out);
 }
 
 // Tile-shape pin for tuning / tests: cg*1000 + bn (e.g. 2256 = CTA pair, 256-wide tile); 0 = cost model.
@@ -387,8 +396,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
 
 }  // namespace umma
 
-int get_tensor_map_bf16(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
-  return umma::get_tensor_map(ptr, rows, cols, ld, box_rows, out);
+int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+                      CUtensorMap* out) {
+  return umma::get_tensor_map_2d(ptr, elem_bytes, rows, cols, ld, box_rows, box_cols, out);
 }
 
 int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,

@@ -22,18 +22,8 @@ int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const
 
 // gemm_mega.cu: a list of dependent bf16 GEMMs (same TN form and epilogue as gemm_bf16) executed by ONE
 // persistent launch with tile-level scheduling and row-block dependency tracking.
-#define NERAF_MEGA_MAX_JOBS 24
-struct MegaJob {
-  int64_t M, N, K;
-  const void* A; int64_t lda;      // (M, K) bf16 K-major
-  const void* B; int64_t ldb;      // (N, K) bf16 K-major
-  int bn;                          // tile width: 64, 128 or 256 (tile height is 256: one CTA pair)
-  int wait_job;                    // index of the job that produces operand A (and/or B), or -1
-  int wait_all;                    // 0: tile (row block rb) needs row block rb of wait_job; 1: needs every row block
-  neraf_gemm_epilogue epi;
-  float* colsum;                   // optional (N): += column sums of the stored values (bias gradient), fp32 atomics
-};
-int mega_counters_bytes(const MegaJob* jobs, int n_jobs, size_t* bytes);
+#define NERAF_MEGA_MAX_JOBS NERAF_MAX_GEMM_JOBS
+typedef neraf_gemm_job MegaJob;      // public contract: include/neraf_b200.h
 int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream);
 
 // elementwise.cu

@@ -265,3 +265,118 @@ def test_loss_rejects_cpu_tensors():
     from neraf_b200.loss import spectral_loss
     with pytest.raises(_lib.NerafError):
         spectral_loss(torch.zeros(4), torch.zeros(4))
+
+
+# ------------------------------------------------------------------------------------------------
+# job-list kernel (neraf_gemm_bf16_jobs): one persistent launch, dependent GEMMs, MN-major operands
+# ------------------------------------------------------------------------------------------------
+def _run_jobs(jobs, dev):
+    lib = _lib.lib()
+    arr = (_lib.GemmJob * len(jobs))(*jobs)
+    counters = torch.empty(4096, dtype=torch.int32, device=dev)
+    _lib.check(lib.neraf_gemm_bf16_jobs(arr, len(jobs), counters.data_ptr(), counters.numel() * 4, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+
+
+def _job(M, N, K, A, B, bn, a_mn=0, b_mn=0, wait_job=-1, wait_all=0):
+    j = _lib.GemmJob()
+    j.M, j.N, j.K, j.A, j.lda, j.B, j.ldb = M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
+    j.a_mn, j.b_mn, j.bn, j.wait_job, j.wait_all = a_mn, b_mn, bn, wait_job, wait_all
+    return j
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(2048, 1024, 512), (300, 513, 200), (256, 64, 64), (1000, 5096, 168)])
+def test_gemm_jobs_k_major_outputs(bn, M, N, K):
+    dev = cuda()
+    g = torch.Generator().manual_seed(bn + M)
+    ldk = (K + 7) // 8 * 8
+    A = _bf16_padded(torch.randn(M, K, generator=g).to(dev), ldk)
+    B = _bf16_padded((torch.randn(N, K, generator=g) / np.sqrt(K)).to(dev), ldk)
+    bias = torch.randn(N, generator=g).to(dev)
+    gate = torch.randn(M, (N + 7) // 8 * 8, generator=g).to(dev).to(torch.bfloat16)
+    ref = torch.nn.functional.leaky_relu(A[:, :K].double() @ B[:, :K].double().t() + bias.double(), 0.1)
+    ref = ref * torch.where(gate[:, :N].double() > 0, 1.0, 0.1)
+    # job 0: bf16 output (TMA store) + column sums; job 1: same GEMM, fp32 output with an unaligned row stride
+    out_b = torch.full((M, (N + 7) // 8 * 8), 7.0, dtype=torch.bfloat16, device=dev)
+    colsum = torch.zeros(N, device=dev)
+    out_f = torch.full((M, N + 1), 7.0, device=dev)
+    j0 = _job(M, N, K, A, B, bn)
+    j0.epi.bias, j0.epi.act, j0.epi.gate, j0.epi.ldg = bias.data_ptr(), 1, gate.data_ptr(), gate.stride(0)
+    j0.epi.out_bf16, j0.epi.ld_bf16, j0.colsum = out_b.data_ptr(), out_b.stride(0), colsum.data_ptr()
+    j1 = _job(M, N, K, A, B, bn)
+    j1.epi.bias, j1.epi.act, j1.epi.gate, j1.epi.ldg = bias.data_ptr(), 1, gate.data_ptr(), gate.stride(0)
+    j1.epi.out_f32, j1.epi.ld_f32 = out_f.data_ptr(), out_f.stride(0)
+    # job 2: fp32 output through the aligned (TMA) path
+    out_f2 = torch.full((M, (N + 3) // 4 * 4), 7.0, device=dev)
+    j2 = _job(M, N, K, A, B, bn)
+    j2.epi.out_f32, j2.epi.ld_f32 = out_f2.data_ptr(), out_f2.stride(0)
+    _run_jobs([j0, j1, j2], dev)
+    assert rel_fro(out_f[:, :N], ref) < 2e-5
+    assert torch.all(out_f[:, N] == 7.0)
+    assert rel_fro(out_b[:, :N], ref) < 4e-3
+    if out_b.shape[1] > N:
+        assert torch.all(out_b[:, N:] == 7.0), "TMA store must clip at N"
+    assert rel_fro(colsum, ref.sum(0)) < 1e-4
+    assert rel_fro(out_f2[:, :N], A[:, :K].double() @ B[:, :K].double().t()) < 2e-5
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("n_out,k_in,batch", [(512, 1024, 2048), (513, 512, 300), (5096, 163, 1000), (200, 130, 64)])
+def test_gemm_jobs_mn_major_weight_gradient(bn, n_out, k_in, batch):
+    """dW = dZ^T X with both operands read MN-major straight from their row-major (batch, features) storage."""
+    dev = cuda()
+    g = torch.Generator().manual_seed(n_out + batch)
+    dz = _bf16_padded(torch.randn(batch, n_out, generator=g).to(dev), (n_out + 7) // 8 * 8)
+    x = _bf16_padded(torch.randn(batch, k_in, generator=g).to(dev), (k_in + 7) // 8 * 8)
+    ref = dz[:, :n_out].double().t() @ x[:, :k_in].double()
+    for ld in (k_in, (k_in + 3) // 4 * 4 + 4):          # unaligned (manual store) and 16-byte aligned (TMA store) strides
+        out = torch.full((n_out, ld), 7.0, device=dev)
+        j = _job(n_out, k_in, batch, dz, x, bn, a_mn=1, b_mn=1)
+        j.epi.out_f32, j.epi.ld_f32 = out.data_ptr(), ld
+        _run_jobs([j], dev)
+        assert rel_fro(out[:, :k_in], ref) < 2e-5, ld
+        if ld > k_in:
+            assert torch.all(out[:, k_in:] == 7.0)
+
+
+def test_gemm_jobs_dependency_chain_matches_sequential():
+    """Three chained layers + a weight gradient that needs ALL row blocks of the middle layer, one launch."""
+    dev = cuda()
+    g = torch.Generator().manual_seed(5)
+    Bsz, d0, d1, d2, d3 = 1536, 168, 1024, 512, 264
+    x0 = torch.randn(Bsz, d0, generator=g).to(dev).to(torch.bfloat16)
+    w1 = (torch.randn(d1, d0, generator=g) / np.sqrt(d0)).to(dev).to(torch.bfloat16)
+    w2 = (torch.randn(d2, d1, generator=g) / np.sqrt(d1)).to(dev).to(torch.bfloat16)
+    w3 = (torch.randn(d3, d2, generator=g) / np.sqrt(d2)).to(dev).to(torch.bfloat16)
+    x1 = torch.zeros(Bsz, d1, dtype=torch.bfloat16, device=dev)
+    x2 = torch.zeros(Bsz, d2, dtype=torch.bfloat16, device=dev)
+    y = torch.zeros(Bsz, d3, device=dev)
+    dw = torch.zeros(d2, d1, device=dev)
+    j0 = _job(Bsz, d1, d0, x0, w1, 128); j0.epi.act = 1; j0.epi.out_bf16, j0.epi.ld_bf16 = x1.data_ptr(), d1
+    j1 = _job(Bsz, d2, d1, x1, w2, 64, wait_job=0); j1.epi.act = 1; j1.epi.out_bf16, j1.epi.ld_bf16 = x2.data_ptr(), d2
+    j2 = _job(Bsz, d3, d2, x2, w3, 64, wait_job=1); j2.epi.act = 2; j2.epi.out_f32, j2.epi.ld_f32 = y.data_ptr(), d3
+    j3 = _job(d2, d1, Bsz, x2, x1, 128, a_mn=1, b_mn=1, wait_job=1, wait_all=1); j3.epi.out_f32, j3.epi.ld_f32 = dw.data_ptr(), d1
+    for _ in range(3):                               # repeat: counters must be reset by every launch
+        _run_jobs([j0, j1, j2, j3], dev)
+    lr = torch.nn.functional.leaky_relu
+    r1 = lr(x0.float() @ w1.float().t(), 0.1).to(torch.bfloat16)
+    r2 = lr(r1.float() @ w2.float().t(), 0.1).to(torch.bfloat16)
+    ry = 10 * torch.tanh(r2.float() @ w3.float().t())
+    assert rel_fro(x1, r1) < 3e-3 and rel_fro(x2, r2) < 4e-3
+    assert rel_fro(y, ry) < 1e-2
+    assert rel_fro(dw, x2.double().t() @ x1.double()) < 2e-5
+
+
+def test_gemm_jobs_validation():
+    dev = cuda()
+    A = torch.zeros(64, 64, dtype=torch.bfloat16, device=dev)
+    out = torch.zeros(64, 64, device=dev)
+    j = _job(64, 64, 64, A, A, 64, a_mn=1, b_mn=1)       # MN-major B needs bn >= 128
+    j.epi.out_f32, j.epi.ld_f32 = out.data_ptr(), 64
+    with pytest.raises(_lib.NerafError):
+        _run_jobs([j], dev)
+    j = _job(64, 64, 64, A, A, 64, wait_job=0)          # depends on itself
+    j.epi.out_f32, j.epi.ld_f32 = out.data_ptr(), 64
+    with pytest.raises(_lib.NerafError):
+        _run_jobs([j], dev)
