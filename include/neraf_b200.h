@@ -218,6 +218,8 @@ NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
  *                 block r (256 rows) starts when row block r of wait_job is complete (both jobs have the same M);
  *                 wait_all == 1: when every row block of wait_job is complete.
  *   colsum      : optional dev fp32 (N), must be zeroed by the caller: += column sums of the fp32 results.
+ *   out_bf16    : ld_bf16 is a multiple of 8, so a row has round_up(N, 8) - N pad columns: they may be overwritten
+ *                 with zeros (TMA stores clip with 16-byte granularity); nothing beyond them is touched.
  * counters: dev scratch, >= 4 * sum_j ceil(M_j / 256) bytes. */
 #define NERAF_MAX_GEMM_JOBS 24
 typedef struct {
