@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 1
+#define NERAF_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))
@@ -81,7 +81,8 @@ typedef struct {
 NERAF_API int neraf_field_sizes(const neraf_field_dims* dims, int precision, int64_t max_batch,
                       size_t* pack_bytes, size_t* workspace_bytes);
 
-/* Derive the tensor-core operand copies of the fp32 parameters (bf16, padded, plus transposes).
+/* Derive the tensor-core operand copies of the fp32 parameters (bf16, rows padded to a multiple of 8; one copy per
+ * matrix -- forward reads it K-major, backward MN-major).
  * weights[l] : dev fp32 (out,in) row-major, l = 0..n_trunk-1 trunk then n_channels heads
  *              (state_dict order soundfield.{l}.weight, STFT_linear.{c}.weight; NeRAF_field.py:41-45)
  * biases[l]  : dev fp32 (out).  Must be re-run whenever the parameters change.  No-op for FP32. */
@@ -108,8 +109,8 @@ typedef struct {
  * pack / repack: the bf16 operand copies (neraf_field_sizes bytes).  repack != 0 re-derives them from the
  *   current fp32 parameters inside this call (on a helper stream, overlapped with the encodings and the earlier
  *   layers) -- what a training step needs after every optimizer update; repack == 0 trusts the buffer.
- * keep != 0 stores what neraf_field_backward needs in `workspace` (training);
- * keep == 0 is the inference path (no transposed copies). */
+ * The workspace afterwards holds what neraf_field_backward needs (the bf16 activations of every layer); `keep`
+ * is accepted for ABI stability and ignored (nothing extra is stored for training any more). */
 NERAF_API int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
                         const float* grid_feature, const float* const* weights,
                         const float* const* biases, void* pack, size_t pack_bytes, int repack,
@@ -117,7 +118,9 @@ NERAF_API int neraf_field_forward(const neraf_field_dims* dims, int precision, c
                         neraf_stream_t stream);
 
 /* Backward of neraf_field_forward(keep=1) on the same workspace.
- * dout, out : dev fp32 (B, C*F).   dweights[l]/dbiases[l]: dev fp32, parameter shapes, OVERWRITTEN.
+ * dout, out : dev fp32 (B, C*F).   dweights[l]/dbiases[l]: dev fp32, parameter shapes, OVERWRITTEN (bias gradients
+ *             and dgrid are zeroed then accumulated: laid out back to back -- dbiases[0..], then dgrid -- they are
+ *             zeroed by a single memset).
  * dgrid     : dev fp32 (n_grid) or NULL.   denc: dev fp32 (B, n_enc) row stride denc_ld, or NULL. */
 NERAF_API int neraf_field_backward(const neraf_field_dims* dims, int precision, int64_t batch, const float* dout,
                          const float* out, const float* grid_feature, const float* const* weights,
@@ -141,11 +144,15 @@ NERAF_API int neraf_spectral_loss_sums(const float* pred, const float* gt, int64
  * w_mag = loss_factor (NeRAF_model.py:597-598).  n_total is the GLOBAL element count (all DP ranks). */
 NERAF_API int neraf_spectral_loss_finalize(const double* sums, int64_t n_total, int criterion, float w_sc, float w_mag,
                                  float* losses, neraf_stream_t stream);
-/* dpred[i] = upstream[0] * d losses[0]/d pred[i] + upstream[1] * d losses[1]/d pred[i] for the n local
- * elements (upstream: dev f32[2], or NULL for {1, 1}). */
+/* Single-GPU forward in ONE launch: sums + finalize (n_total == n).  scratch: dev f64[5] (the four sums, readable
+ * by neraf_spectral_loss_backward, + a completion ticket), OVERWRITTEN. */
+NERAF_API int neraf_spectral_loss_forward(const float* pred, const float* gt, int64_t n, int criterion, float w_sc,
+                                float w_mag, double* scratch, float* losses, neraf_stream_t stream);
+/* dpred[i] = upstream_sc[0] * d losses[0]/d pred[i] + upstream_mag[0] * d losses[1]/d pred[i] for the n local
+ * elements (upstream_*: dev f32 scalars -- the autograd gradients of the two loss terms -- or NULL for 1). */
 NERAF_API int neraf_spectral_loss_backward(const float* pred, const float* gt, int64_t n, int64_t n_total, int criterion,
-                                 const double* sums, const float* upstream, float w_sc, float w_mag,
-                                 float* dpred, neraf_stream_t stream);
+                                 const double* sums, const float* upstream_sc, const float* upstream_mag,
+                                 float w_sc, float w_mag, float* dpred, neraf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Griffin-Lim (replaces torchaudio GriffinLim as configured at NeRAF_model.py:139, used :229,:753-754,
@@ -218,8 +225,7 @@ NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
  *                 block r (256 rows) starts when row block r of wait_job is complete (both jobs have the same M);
  *                 wait_all == 1: when every row block of wait_job is complete.
  *   colsum      : optional dev fp32 (N), must be zeroed by the caller: += column sums of the fp32 results.
- *   out_bf16    : ld_bf16 is a multiple of 8, so a row has round_up(N, 8) - N pad columns: they may be overwritten
- *                 with zeros (TMA stores clip with 16-byte granularity); nothing beyond them is touched.
+ *   outputs     : only the M x N results are written (pad columns of a wider row stride are left untouched).
  * counters: dev scratch, >= 4 * sum_j ceil(M_j / 256) bytes. */
 #define NERAF_MAX_GEMM_JOBS 24
 typedef struct {

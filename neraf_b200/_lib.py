@@ -75,7 +75,8 @@ SIGNATURES = {
     "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),
     "neraf_spectral_loss_sums": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
     "neraf_spectral_loss_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp]),
-    "neraf_spectral_loss_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp]),
+    "neraf_spectral_loss_forward": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp]),
+    "neraf_spectral_loss_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _vp]),
     "neraf_griffinlim_sizes": (C.c_int, [C.POINTER(GlParams), _i64, C.POINTER(_sz)]),
     "neraf_griffinlim": (C.c_int, [C.POINTER(GlParams), _i64, _i32, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                     _i64, _vp, _sz, _vp, _vp]),

@@ -51,6 +51,64 @@ int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, voi
 }
 
 // ---------------------------------------------------------------------------------------------
+// bf16 operand copies of SEVERAL fp32 matrices in one launch (the per-step re-pack of the MLP parameters):
+// matrix i is (rows, cols) fp32 with row stride ld_in -> bf16 row stride ld_out (pad columns zero-filled).
+// Work unit = 8 consecutive columns of one row (two 16-byte loads, one 16-byte store when aligned).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_list_kernel(const PackList L) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t u = tid; u < L.total_units; u += nthreads) {
+    int i = 0;
+    while (i + 1 < L.n && u >= L.m[i + 1].unit_start) ++i;
+    const PackMatrix& M = L.m[i];
+    const int64_t local = u - M.unit_start;
+    const int64_t upr = M.ld_out / 8;                       // units per row (ld_out is a multiple of 8)
+    const int64_t r = local / upr, c = (local - r * upr) * 8;
+    const float* src = M.in + r * M.ld_in + c;
+    __nv_bfloat16* dst = M.out + r * M.ld_out + c;
+    uint4 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+    if (M.vec && c + 8 <= M.cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      h[0] = __floats2bfloat162_rn(a.x, a.y); h[1] = __floats2bfloat162_rn(a.z, a.w);
+      h[2] = __floats2bfloat162_rn(b.x, b.y); h[3] = __floats2bfloat162_rn(b.z, b.w);
+    } else {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = c + e < M.cols ? __ldg(src + e) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    }
+    *reinterpret_cast<uint4*>(dst) = pk;
+  }
+  for (int64_t j = tid; j < L.n_copy; j += nthreads) {     // fp32 vector gathered from up to 8 segments (head biases)
+    const int seg = (int)(j / L.copy_width);
+    L.copy_dst[j] = __ldg(L.copy_src[seg] + (j - (int64_t)seg * L.copy_width));
+  }
+}
+
+int pack_list(PackList& L, cudaStream_t stream) {
+  int64_t units = 0;
+  for (int i = 0; i < L.n; ++i) {
+    PackMatrix& M = L.m[i];
+    NERAF_REQUIRE(M.in && M.out && M.ld_out % 8 == 0 && M.ld_out >= M.cols && ((uintptr_t)M.out % 16) == 0,
+                  "pack_list: matrix %d: output must be 16-byte aligned with a row stride that is a multiple of 8", i);
+    M.vec = (M.ld_in % 4 == 0) && (((uintptr_t)M.in % 16) == 0);
+    M.unit_start = units;
+    units += M.rows * (M.ld_out / 8);
+  }
+  L.total_units = units;
+  if (units == 0 && L.n_copy == 0) return NERAF_OK;
+  const int64_t want = ceil_div(units, 256 * 4);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  const unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+  pack_list_kernel<<<grid, 256, 0, stream>>>(L);
+  NERAF_CHECK_LAUNCH("pack_list_kernel");
+  return NERAF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // y[n] = bias[n] + W[n, :K] . g       (one warp per output row, float4 loads when aligned)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grid_bias_kernel(const float* __restrict__ W, int64_t ldw,
@@ -129,6 +187,57 @@ int outer_product(const float* s, const float* g, int64_t N, int64_t K, float* d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Both gradients of the hoisted grid block of layer 1 in ONE launch (they only share their input db1):
+//   blocks [0, n_outer)   dW1[n, :G] = db1[n] * g        (8 rows per block)
+//   the rest              dg[k]     += sum_n W1[n, k] db1[n]   (32 columns x one slice of n per block; dg pre-zeroed)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) grid_grads_kernel(const float* __restrict__ s, const float* __restrict__ g,
+                                                          const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
+                                                          float* __restrict__ dW, float* __restrict__ dg, int n_outer,
+                                                          int n_slices) {
+  __shared__ float red[32][33];
+  int blk = blockIdx.x;
+  if (blk < n_outer) {
+    const int64_t n = (int64_t)blk * 8 + threadIdx.x / 128;
+    if (n >= N) return;
+    const float sn = __ldg(s + n);
+    float* row = dW + n * ldw;
+    for (int64_t k = threadIdx.x % 128; k < K; k += 128) row[k] = sn * __ldg(g + k);
+    return;
+  }
+  blk -= n_outer;
+  const int kx = threadIdx.x % 32, ny = threadIdx.x / 32;
+  const int kblk = blk / n_slices, slice = blk % n_slices;
+  const int64_t k = (int64_t)kblk * 32 + kx;
+  const int64_t per = (N + n_slices - 1) / n_slices;
+  const int64_t n_lo = (int64_t)slice * per, n_hi = n_lo + per < N ? n_lo + per : N;
+  float acc = 0.f;
+  if (k < K)
+    for (int64_t n = n_lo + ny; n < n_hi; n += 32) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
+  red[ny][kx] = acc;
+  __syncthreads();
+  if (ny == 0 && k < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][kx];
+    atomicAdd(dg + k, t);
+  }
+}
+
+int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
+               bool dg_is_zero, cudaStream_t stream) {
+  if (N <= 0 || K <= 0) return NERAF_OK;
+  const int n_outer = dW ? (int)ceil_div(N, 8) : 0;
+  const int n_slices = 16;
+  const int n_bwd = dg ? (int)ceil_div(K, 32) * n_slices : 0;
+  if (n_outer + n_bwd == 0) return NERAF_OK;
+  if (dg && !dg_is_zero) NERAF_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)K * 4, stream));
+  grid_grads_kernel<<<(unsigned)(n_outer + n_bwd), 1024, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, n_outer, n_slices);
+  NERAF_CHECK_LAUNCH("grid_grads_kernel");
+  return NERAF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Column sums (bias gradients)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) colsum_f32_kernel(const float* __restrict__ X, int64_t M, int64_t N, int64_t ld,
@@ -194,49 +303,45 @@ struct HeadColsum {
   long long width;        // columns per head; 0 = no column sums
 };
 
+constexpr int kHeadRows = 128;       // rows per block of head_backward_kernel
+
+// Block = 32 columns x 8 row lanes over kHeadRows rows: coalesced 128-byte row segments, the bias gradient
+// (column sums) is accumulated in registers and leaves the block as one atomic per column.
 __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                                             int64_t M, int64_t N, float* __restrict__ dz_f32,
                                                             int64_t ld_f32, __nv_bfloat16* __restrict__ dz_bf16,
-                                                            int64_t ld_bf16, __nv_bfloat16* __restrict__ dz_bf16_t,
-                                                            int64_t ld_t, HeadColsum cs) {
-  __shared__ float tile[32][33];
+                                                            int64_t ld_bf16, HeadColsum cs) {
+  __shared__ float red[8][32];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t r = r0 + ty + i * 8, c = c0 + tx;
-    float v = 0.f;
-    if (r < M && c < N) {
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * kHeadRows;
+  const int64_t r1 = r0 + kHeadRows < M ? r0 + kHeadRows : M;
+  float sum = 0.f;
+  if (c < N) {
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
       const float yy = __ldg(y + r * N + c);
-      v = __ldg(dout + r * N + c) * (10.f - yy * yy * 0.1f);
+      const float v = __ldg(dout + r * N + c) * (10.f - yy * yy * 0.1f);
       if (dz_f32) dz_f32[r * ld_f32 + c] = v;
       if (dz_bf16) dz_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(v);
+      sum += v;
     }
-    tile[ty + i * 8][tx] = v;
   }
-  if (!dz_bf16_t && cs.width == 0) return;
+  if (cs.width == 0) return;
+  red[ty][tx] = sum;
   __syncthreads();
-  if (dz_bf16_t) {
+  if (ty == 0 && c < N) {
+    float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t c = c0 + ty + i * 8, r = r0 + tx;
-      if (r < M && c < N) dz_bf16_t[c * ld_t + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
-    }
-  }
-  if (cs.width > 0 && ty == 0 && c0 + tx < N) {            // bias gradient of the heads: column sums of this tile
-    float sum = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) sum += tile[r][tx];
-    const int64_t c = c0 + tx;
-    atomicAdd(cs.ptr[c / cs.width] + (c % cs.width), sum);
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(cs.ptr[c / cs.width] + (c % cs.width), t);
   }
 }
 
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
-                  int64_t ld_bf16, void* dz_bf16_t, int64_t ld_t, float* const* colsum, int64_t head_width,
-                  cudaStream_t stream) {
+                  int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return NERAF_OK;
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, kHeadRows));
   NERAF_REQUIRE(grid.y <= 65535, "head_backward: batch too large for one launch (%lld)", (long long)M);
   HeadColsum cs = {};
   if (colsum) {
@@ -245,8 +350,7 @@ int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float
     for (int64_t c = 0; c < heads; ++c) cs.ptr[c] = colsum[c];
     cs.width = head_width;
   }
-  head_backward_kernel<<<grid, 256, 0, stream>>>(dout, y, M, N, dz_f32, ld_f32, (__nv_bfloat16*)dz_bf16, ld_bf16,
-                                                 (__nv_bfloat16*)dz_bf16_t, ld_t, cs);
+  head_backward_kernel<<<grid, 256, 0, stream>>>(dout, y, M, N, dz_f32, ld_f32, (__nv_bfloat16*)dz_bf16, ld_bf16, cs);
   NERAF_CHECK_LAUNCH("head_backward_kernel");
   return NERAF_OK;
 }

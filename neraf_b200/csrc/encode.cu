@@ -39,11 +39,13 @@ __device__ __forceinline__ void put(const EncodeArgs& a, int64_t b, int col, flo
   if (a.out_bf16_t) a.out_bf16_t[(int64_t)col * a.ld_t + b] = __float2bfloat16_rn(v);
 }
 
-// One thread per (query, group); groups: 0 time, 1-3 mic xyz, 4-6 source xyz, 7 rot (+ padding).
-__global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t b = gid >> 3;
-  const int grp = (int)(gid & 7);
+// One thread per (query, group, frequency): 80 threads per query.  Groups: 0 time, 1-3 mic xyz, 4-6 source xyz,
+// 7 rot (spherical harmonics + padding, done by the k == 0 thread).  The k == 0 thread of a group also writes the
+// raw input column (include_input=True appends it last).
+__device__ __forceinline__ void encode_one(const EncodeArgs& a, int64_t gid) {
+  const int64_t b = gid / 80;
+  const int r = (int)(gid - b * 80);
+  const int grp = r / 10, k = r - grp * 10;
   if (b >= a.B) return;
   const int off_time = a.order == NERAF_ORDER_TIME_MIC_SRC_ROT ? 0 : 126;
   const int off_mic = a.order == NERAF_ORDER_TIME_MIC_SRC_ROT ? 21 : 0;
@@ -54,14 +56,11 @@ __global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
     // NeRAF_model.py:533-535 then NeRFEncoding(in_dim=1) entirely in float32.
     const float t = __fdiv_rn((float)a.time_query[b], a.time_den);
     const float scaled = __fmul_rn(0x1.921fb6p+2f, t);            // float32(2*pi) * t
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      const float s = __fmul_rn(scaled, kFreqs[k]);
-      const float c = __fadd_rn(s, 0x1.921fb6p+0f);               // + float32(pi/2)
-      put(a, b, off_time + k, (float)sin((double)s));
-      put(a, b, off_time + 10 + k, (float)sin((double)c));
-    }
-    put(a, b, off_time + 20, t);
+    const float s = __fmul_rn(scaled, kFreqs[k]);
+    const float c = __fadd_rn(s, 0x1.921fb6p+0f);                 // + float32(pi/2)
+    put(a, b, off_time + k, (float)sin((double)s));
+    put(a, b, off_time + 10 + k, (float)sin((double)c));
+    if (k == 0) put(a, b, off_time + 20, t);
   } else if (grp <= 6) {
     const bool is_mic = grp <= 3;
     const int d = is_mic ? grp - 1 : grp - 4;
@@ -77,16 +76,12 @@ __global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
       inside = inside && (pn[i] > 0.0) && (pn[i] < 1.0);
     }
     const double x = inside ? pn[d] : pn[d] * 0.0;                // NeRAF_model.py:543-546 (whole vector)
-    const double scaled = 6.283185307179586 * x;
+    const double s = 6.283185307179586 * x * (double)kFreqs[k];
     const int base = is_mic ? off_mic : off_src;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      const double s = scaled * (double)kFreqs[k];
-      put(a, b, base + d * 10 + k, (float)sin(s));
-      put(a, b, base + 30 + d * 10 + k, (float)sin(s + 1.5707963267948966));
-    }
-    put(a, b, base + 60 + d, (float)x);
-  } else {
+    put(a, b, base + d * 10 + k, (float)sin(s));
+    put(a, b, base + 30 + d * 10 + k, (float)sin(s + 1.5707963267948966));
+    if (k == 0) put(a, b, base + 60 + d, (float)x);
+  } else if (k == 0) {
     // tiny-cuda-nn SphericalHarmonics degree 4 on 2*rot-1; operation order == oracle/encodings.py sh4_tcnn.
     const float x = __fsub_rn(__fmul_rn((float)a.rot[b * 3 + 0], 2.f), 1.f);
     const float y = __fsub_rn(__fmul_rn((float)a.rot[b * 3 + 1], 2.f), 1.f);
@@ -120,19 +115,96 @@ __global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
   }
 }
 
-int encode_queries(const neraf_queries* q, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
-                   void* out_bf16_t, int64_t ld_t, int ncols_padded, cudaStream_t stream) {
+// What precedes layer 1 of a forward pass, in ONE launch (block ranges):
+//   [0, enc_blocks)                      the query encodings above
+//   [enc_blocks, +gb_blocks)             c1[n] = b1[n] + W1[n, :G] . g   (batch-invariant grid block of layer 1, one warp per row)
+//   [.., +pk_blocks)                     bf16 operand copy of the per-query columns W1[:, G:] (only when re-packing)
+struct PrepArgs {
+  EncodeArgs enc;
+  int enc_blocks, gb_blocks, pk_blocks;
+  const float* W1; int64_t ldw; const float* b1; const float* g; int64_t n1, G; float* c1;
+  int64_t E; __nv_bfloat16* w1_out; int64_t w1_ld;
+};
+
+__global__ void __launch_bounds__(256) field_prep_kernel(const PrepArgs p) {
+  int blk = blockIdx.x;
+  if (blk < p.enc_blocks) {
+    encode_one(p.enc, (int64_t)blk * 256 + threadIdx.x);
+    return;
+  }
+  blk -= p.enc_blocks;
+  if (blk < p.gb_blocks) {
+    const int64_t n = (int64_t)blk * 8 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (n >= p.n1) return;
+    const float* w = p.W1 + n * p.ldw;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int64_t k = lane;
+    for (; k + 96 < p.G; k += 128) {                              // 4 independent loads in flight per lane
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(__ldg(w + k + 32 * u), __ldg(p.g + k + 32 * u), acc[u]);
+    }
+    for (; k < p.G; k += 32) acc[0] = fmaf(__ldg(w + k), __ldg(p.g + k), acc[0]);
+    float t = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) p.c1[n] = t + (p.b1 ? p.b1[n] : 0.f);
+    return;
+  }
+  blk -= p.gb_blocks;
+  {                                                               // W1[:, G:G+E] -> bf16 (n1, w1_ld): 8 rows per block
+    const int64_t n = (int64_t)blk * 8 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (n >= p.n1) return;
+    const float* w = p.W1 + n * p.ldw + p.G;
+    __nv_bfloat16* o = p.w1_out + n * p.w1_ld;
+    for (int64_t k = lane; k < p.w1_ld; k += 32) o[k] = __float2bfloat16_rn(k < p.E ? __ldg(w + k) : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
+  encode_one(a, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+static int check_queries(const neraf_queries* q) {
   NERAF_REQUIRE(q && q->batch >= 0, "encode: bad query struct");
   if (q->batch == 0) return NERAF_OK;
   NERAF_REQUIRE(q->time_query && q->mic_pose && q->source_pose && q->rot && q->aabb,
                 "encode: null query pointer");
   NERAF_REQUIRE(q->time_denominator != 0.f, "encode: time_denominator must be max_len - 1 != 0");
+  return NERAF_OK;
+}
+
+int encode_queries(const neraf_queries* q, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
+                   void* out_bf16_t, int64_t ld_t, int ncols_padded, cudaStream_t stream) {
+  NERAF_TRY(check_queries(q));
+  if (q->batch == 0) return NERAF_OK;
   EncodeArgs a{q->batch, q->time_query, q->mic_pose, q->source_pose, q->rot, q->aabb, q->time_denominator,
                q->order, out_f32, ld_f32, (__nv_bfloat16*)out_bf16, ld_bf16, (__nv_bfloat16*)out_bf16_t, ld_t,
                ncols_padded};
-  const int64_t threads = q->batch * 8;
-  encode_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, stream>>>(a);
+  encode_kernel<<<(unsigned)ceil_div(q->batch * 80, 256), 256, 0, stream>>>(a);
   NERAF_CHECK_LAUNCH("encode_kernel");
+  return NERAF_OK;
+}
+
+int field_prep(const neraf_queries* q, float* enc_f32, int64_t ld_f32, void* enc_bf16, int64_t ld_bf16, int ncols_padded,
+               const float* W1, int64_t ldw, const float* b1, const float* g, int64_t n1, int64_t G, float* c1,
+               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream) {
+  PrepArgs p = {};
+  if (q) {
+    NERAF_TRY(check_queries(q));
+    p.enc = EncodeArgs{q->batch, q->time_query, q->mic_pose, q->source_pose, q->rot, q->aabb, q->time_denominator,
+                       q->order, enc_f32, ld_f32, (__nv_bfloat16*)enc_bf16, ld_bf16, nullptr, 0, ncols_padded};
+    p.enc_blocks = (int)ceil_div(q->batch * 80, 256);
+  }
+  p.W1 = W1; p.ldw = ldw; p.b1 = b1; p.g = g; p.n1 = n1; p.G = G; p.c1 = c1;
+  p.gb_blocks = (G > 0 && c1) ? (int)ceil_div(n1, 8) : 0;
+  p.E = E; p.w1_out = (__nv_bfloat16*)w1_out; p.w1_ld = w1_ld;
+  p.pk_blocks = w1_out ? (int)ceil_div(n1, 8) : 0;
+  const int blocks = p.enc_blocks + p.gb_blocks + p.pk_blocks;
+  if (blocks == 0) return NERAF_OK;
+  field_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  NERAF_CHECK_LAUNCH("field_prep_kernel");
   return NERAF_OK;
 }
 

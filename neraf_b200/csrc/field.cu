@@ -10,8 +10,12 @@
 //
 // Two precisions share the sequence:
 //   FP32  CUDA-core GEMMs on the fp32 parameters directly (parity path, 1e-5 gate)
-//   BF16  tcgen05 GEMMs on packed bf16 operand copies; every GEMM is the TN form of gemm_umma.cu, the
-//         transposed copies it needs are written by the producing epilogue.
+//   BF16  the job-list tcgen05 kernel (gemm_mega.cu) on bf16 operand copies of the parameters.  One copy per
+//         weight matrix, (out, in) row-major: forward reads it K-major, dgrad reads the SAME copy MN-major, and the
+//         weight gradients read the row-major activations / gradients MN-major, so nothing is ever transposed.
+//
+// Launches per bf16 train step: prep (encodings + c1 + layer-1 operand copy) | pack of the other layers on a helper
+// stream | layer 1 | layers 2..heads | ... loss ... | memset + head gradient | whole backward | grid-block gradients.
 #include <cstdlib>
 #include <mutex>
 
@@ -29,18 +33,17 @@ struct Layout {
   int n[NERAF_MAX_TRUNK];   // trunk widths
   int k[NERAF_MAX_TRUNK];   // trunk input widths (k[0] = E: the per-query block only)
   // ---- pack (bf16) offsets in bytes
-  size_t w[NERAF_MAX_TRUNK], wt[NERAF_MAX_TRUNK];
-  int64_t ldw[NERAF_MAX_TRUNK], ldwt[NERAF_MAX_TRUNK];
-  size_t wh, wht, bh;
-  int64_t ldwh, ldwht;
+  size_t w[NERAF_MAX_TRUNK];
+  int64_t ldw[NERAF_MAX_TRUNK];
+  size_t wh, bh;
+  int64_t ldwh;
   size_t pack_bytes;
   // ---- workspace offsets in bytes
-  int64_t ldm;           // row stride of every transposed (feature, batch) buffer
-  size_t c1, enc, enc_t;
+  size_t c1, enc;
   int64_t ld_enc;
-  size_t x[NERAF_MAX_TRUNK], xt[NERAF_MAX_TRUNK], dz[NERAF_MAX_TRUNK], dzt[NERAF_MAX_TRUNK];
+  size_t x[NERAF_MAX_TRUNK], dz[NERAF_MAX_TRUNK];
   int64_t ldx[NERAF_MAX_TRUNK];
-  size_t dzh, dzht;
+  size_t dzh;
   int64_t ld_h;
   size_t counters, counters_bytes;   // dependency counters of the job-list kernel
   size_t dwh;                        // (C*F, W) fp32 joint head weight gradient (only used when C > 1)
@@ -57,6 +60,7 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   NERAF_REQUIRE(d, "field: dims is null");
   NERAF_REQUIRE(d->n_trunk >= 1 && d->n_trunk <= NERAF_MAX_TRUNK, "field: n_trunk %d out of range", d->n_trunk);
   NERAF_REQUIRE(d->n_enc > 0 && d->n_grid >= 0 && d->n_channels >= 1 && d->n_freq >= 1, "field: bad dims");
+  NERAF_REQUIRE(d->n_channels <= 8, "field: at most 8 heads");
   NERAF_REQUIRE(precision == NERAF_PREC_FP32 || precision == NERAF_PREC_BF16, "field: unknown precision %d", precision);
   NERAF_REQUIRE(batch >= 0 && batch < (1ll << 30), "field: batch %lld out of range", (long long)batch);
   Layout& l = *lo;
@@ -74,35 +78,26 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   if (bf) {
     for (int i = 0; i < l.L; ++i) {
       l.ldw[i] = round_up(l.k[i], 8);
-      l.ldwt[i] = round_up(l.n[i], 8);
       l.w[i] = take(cur, (size_t)l.n[i] * l.ldw[i] * 2);
-      l.wt[i] = take(cur, (size_t)l.k[i] * l.ldwt[i] * 2);
     }
     l.ldwh = round_up(l.W, 8);
-    l.ldwht = round_up(l.CF, 8);
     l.wh = take(cur, (size_t)l.CF * l.ldwh * 2);
-    l.wht = take(cur, (size_t)l.W * l.ldwht * 2);
     l.bh = take(cur, (size_t)l.CF * 4);
   }
   l.pack_bytes = cur;
 
   cur = 0;
   const size_t B = (size_t)batch;
-  l.ldm = round_up(batch > 0 ? batch : 1, 64);
   l.c1 = take(cur, (size_t)l.n[0] * 4);
   l.ld_enc = bf ? round_up(l.E, 8) : l.E;
   l.enc = take(cur, B * l.ld_enc * es);
-  l.enc_t = bf ? take(cur, (size_t)l.E * l.ldm * 2) : 0;
   for (int i = 0; i < l.L; ++i) {
     l.ldx[i] = bf ? round_up(l.n[i], 8) : l.n[i];
     l.x[i] = take(cur, B * l.ldx[i] * es);
-    l.xt[i] = bf ? take(cur, (size_t)l.n[i] * l.ldm * 2) : 0;
     l.dz[i] = take(cur, B * l.ldx[i] * es);
-    l.dzt[i] = bf ? take(cur, (size_t)l.n[i] * l.ldm * 2) : 0;
   }
   l.ld_h = bf ? round_up(l.CF, 8) : l.CF;
   l.dzh = take(cur, B * l.ld_h * es);
-  l.dzht = bf ? take(cur, (size_t)l.CF * l.ldm * 2) : 0;
   l.counters_bytes = (size_t)NERAF_MEGA_MAX_JOBS * (size_t)(ceil_div(batch > 0 ? batch : 1, 256) + 32) * 4;
   l.counters = take(cur, l.counters_bytes);
   l.dwh = (bf && l.C > 1) ? take(cur, (size_t)l.CF * l.W * 4) : 0;
@@ -110,12 +105,11 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   return NERAF_OK;
 }
 
-// Helper stream for work that is off the critical chain (weight / bias gradients, the grid-feature mat-vec):
-// forked from and joined back into the caller's stream with events, so it is capturable in a CUDA graph.
+// Helper stream for the per-step re-pack of layers 2.. (off the critical chain encodings -> layer 1): forked from and
+// joined back into the caller's stream with events, so it is capturable in a CUDA graph.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[NERAF_MAX_TRUNK + 4] = {};
-  cudaEvent_t done = nullptr;
+  cudaEvent_t fork = nullptr, done = nullptr;
   bool ok = false;
 };
 
@@ -129,65 +123,81 @@ SideStream* side_stream() {
   if (!s.ok) {
     if (getenv("NERAF_NO_SIDE_STREAM")) return nullptr;
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    for (auto& e : s.ev)
-      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     s.ok = true;
   }
   return &s;
 }
 
-bool use_mega() {
-  static int v = -1;
-  if (v < 0) v = getenv("NERAF_NO_MEGA") ? 0 : 1;
-  return v != 0;
-}
-
 // Tile width of a job: the widest tile that still yields enough tiles to spread over the CTA pairs.
-int choose_bn(int64_t M, int64_t N) {
+int choose_bn(int64_t M, int64_t N, int min_bn) {
   const int64_t rb = ceil_div(M, 256);
-  for (int bn = 256; bn > 64; bn /= 2)
+  for (int bn = 256; bn > min_bn; bn /= 2)
     if (rb * ceil_div(N, bn) >= 48) return bn;
-  return 64;
+  return min_bn;
 }
 
 MegaJob make_job(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, int wait_job,
                  int wait_all) {
   MegaJob j = {};
   j.M = M; j.N = N; j.K = K; j.A = A; j.lda = lda; j.B = B; j.ldb = ldb;
-  j.bn = choose_bn(M, N);
+  j.bn = choose_bn(M, N, 64);
   j.wait_job = wait_job; j.wait_all = wait_all;
   return j;
 }
 
-// dW (N_out, K_in) = dZ^T X with dZ (B, N_out) and X (B, K_in) both row-major: both operands MN-major.
+// dX (B, k_in) = dZ (B, n_out) W with W (n_out, k_in) row-major: the B operand is consumed MN-major.
+MegaJob make_dgrad_job(int64_t batch, int64_t k_in, int64_t n_out, const void* dz, int64_t ld_dz, const void* w,
+                       int64_t ld_w, int wait_job) {
+  MegaJob j = make_job(batch, k_in, n_out, dz, ld_dz, w, ld_w, wait_job, 0);
+  j.b_mn = 1;
+  j.bn = choose_bn(batch, k_in, 128);
+  return j;
+}
+
+// dW (n_out, k_in) = dZ^T X with dZ (B, n_out) and X (B, k_in) both row-major: both operands MN-major.
 MegaJob make_wgrad_job(int64_t n_out, int64_t k_in, int64_t batch, const void* dz, int64_t ld_dz, const void* x,
                        int64_t ld_x, int wait_job) {
   MegaJob j = make_job(n_out, k_in, batch, dz, ld_dz, x, ld_x, wait_job, 1);
   j.a_mn = 1; j.b_mn = 1;
-  if (j.bn < 128) j.bn = 128;
+  j.bn = choose_bn(n_out, k_in, 128);
   return j;
 }
 
 inline uint8_t* at(void* base, size_t off) { return reinterpret_cast<uint8_t*>(base) + off; }
 inline const uint8_t* at(const void* base, size_t off) { return reinterpret_cast<const uint8_t*>(base) + off; }
 
-// bf16 operand copies of one trunk layer: W (n, k) and W^T (k, n); layer 0 packs only the per-query columns.
-int pack_trunk_layer(const Layout& l, int i, const float* const* weights, void* pack, cudaStream_t stream) {
-  const float* w = weights[i] + (i == 0 ? l.G : 0);
-  const int64_t ld_in = i == 0 ? l.G + l.E : l.k[i];
-  return convert_bf16(w, l.n[i], l.k[i], ld_in, at(pack, l.w[i]), l.ldw[i], at(pack, l.wt[i]), l.ldwt[i], stream);
-}
-
-// heads concatenated along N: W_h (C*F, W), W_h^T (W, C*F) and the fp32 bias vector (C*F)
-int pack_heads(const Layout& l, const float* const* weights, const float* const* biases, void* pack, cudaStream_t stream) {
-  for (int c = 0; c < l.C; ++c) {
-    NERAF_TRY(convert_bf16(weights[l.L + c], l.F, l.W, l.W, at(pack, l.wh) + (size_t)c * l.F * l.ldwh * 2, l.ldwh,
-                           at(pack, l.wht) + (size_t)c * l.F * 2, l.ldwht, stream));
-    NERAF_CHECK_CUDA(cudaMemcpyAsync(at(pack, l.bh) + (size_t)c * l.F * 4, biases[l.L + c], (size_t)l.F * 4,
-                                     cudaMemcpyDeviceToDevice, stream));
+// bf16 operand copies of trunk layers [first, L) and of the heads (+ their concatenated fp32 bias vector), one launch.
+int pack_layers(const Layout& l, int first, const float* const* weights, const float* const* biases, void* pack,
+                cudaStream_t stream) {
+  PackList pl = {};
+  for (int i = first; i < l.L; ++i) {
+    PackMatrix& m = pl.m[pl.n++];
+    m.in = weights[i] + (i == 0 ? l.G : 0);
+    m.rows = l.n[i]; m.cols = l.k[i]; m.ld_in = i == 0 ? l.G + l.E : l.k[i];
+    m.out = reinterpret_cast<__nv_bfloat16*>(at(pack, l.w[i])); m.ld_out = l.ldw[i];
+    if (pl.n == 7) {                                   // keep one slot for the heads
+      NERAF_TRY(pack_list(pl, stream));
+      pl = PackList{};
+    }
   }
-  return NERAF_OK;
+  // heads are concatenated along N: every head is (F, W) with the same row stride, so they form one (C*F, W) matrix
+  // in the pack; in the parameters they are C separate tensors -> one list entry per head would exceed 8 for C = 8,
+  // so heads go in a list of their own when needed.
+  if (pl.n + l.C > 8) {
+    NERAF_TRY(pack_list(pl, stream));
+    pl = PackList{};
+  }
+  for (int c = 0; c < l.C; ++c) {
+    PackMatrix& m = pl.m[pl.n++];
+    m.in = weights[l.L + c]; m.rows = l.F; m.cols = l.W; m.ld_in = l.W;
+    m.out = reinterpret_cast<__nv_bfloat16*>(at(pack, l.wh)) + (size_t)c * l.F * l.ldwh; m.ld_out = l.ldwh;
+    pl.copy_src[c] = biases[l.L + c];
+  }
+  pl.copy_dst = reinterpret_cast<float*>(at(pack, l.bh));
+  pl.copy_width = l.F; pl.n_copy = l.CF;
+  return pack_list(pl, stream);
 }
 
 int check_ptr_list(const float* const* list, int n, const char* what) {
@@ -222,15 +232,14 @@ extern "C" int neraf_field_pack(const neraf_field_dims* dims, int precision, con
   NERAF_REQUIRE(pack, "field_pack: pack buffer is null");
   if (pack_bytes < l.pack_bytes)
     return set_error(NERAF_ERR_WORKSPACE, "field_pack: pack buffer %zu < %zu bytes", pack_bytes, l.pack_bytes);
-  for (int i = 0; i < l.L; ++i) NERAF_TRY(pack_trunk_layer(l, i, weights, pack, stream));
-  NERAF_TRY(pack_heads(l, weights, biases, pack, stream));
-  return NERAF_OK;
+  return pack_layers(l, 0, weights, biases, pack, stream);
 }
 
 extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
                                    const float* grid_feature, const float* const* weights, const float* const* biases,
                                    void* pack, size_t pack_bytes, int repack, void* ws, size_t ws_bytes, float* out,
                                    int keep, neraf_stream_t stream_) {
+  (void)keep;                                        // nothing extra is stored for backward any more
   cudaStream_t stream = (cudaStream_t)stream_;
   NERAF_REQUIRE(q, "field_forward: queries is null");
   Layout l;
@@ -247,57 +256,29 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
   const bool bf = precision == NERAF_PREC_BF16;
   NERAF_REQUIRE(!bf || pack, "field_forward: pack is null");
   NERAF_REQUIRE(q->enc || l.E == 163, "field_forward: query encodings produce 163 columns, dims->n_enc = %d", l.E);
-
+  NERAF_REQUIRE(!q->enc || q->enc_ld >= l.E, "field_forward: enc_ld < n_enc");
   if (bf && pack_bytes < l.pack_bytes)
     return set_error(NERAF_ERR_WORKSPACE, "field_forward: pack buffer %zu < %zu bytes", pack_bytes, l.pack_bytes);
-  // Work that does not depend on the queries runs on the helper stream beside the encodings / earlier layers:
-  //  * (repack) re-derive the bf16 operand copies of the CURRENT fp32 parameters, layer by layer,
-  //  * effective layer-1 bias  c1 = b1 + W1[:, :G] g   (once per step, not per query).
-  // ready[i] is recorded when layer i's operands are usable; the GEMM of layer i waits for it.
-  const float* c1 = biases[0];
+
+  // effective layer-1 bias  c1 = b1 + W1[:, :G] g   (once per step, not per query)
   float* c1w = reinterpret_cast<float*>(at(ws, l.c1));
-  SideStream* side = bf ? side_stream() : nullptr;
-  cudaStream_t s1 = side ? side->stream : stream;
-  const bool do_pack = bf && repack;
-  if (side && (do_pack || l.G > 0)) {
-    NERAF_CHECK_CUDA(cudaEventRecord(side->done, stream));
-    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->done, 0));
-  }
-  if (do_pack) NERAF_TRY(pack_trunk_layer(l, 0, weights, pack, s1));
-  if (l.G > 0) {
-    NERAF_TRY(grid_bias(weights[0], l.G + l.E, biases[0], grid_feature, l.n[0], l.G, c1w, s1));
-    c1 = c1w;
-  }
-  if (side && (do_pack || l.G > 0)) NERAF_CHECK_CUDA(cudaEventRecord(side->ev[0], side->stream));
-  if (do_pack) {
-    for (int i = 1; i < l.L; ++i) {
-      NERAF_TRY(pack_trunk_layer(l, i, weights, pack, s1));
-      if (side) NERAF_CHECK_CUDA(cudaEventRecord(side->ev[i], side->stream));
-    }
-    NERAF_TRY(pack_heads(l, weights, biases, pack, s1));
-    if (side) NERAF_CHECK_CUDA(cudaEventRecord(side->ev[l.L], side->stream));
-  }
-  auto wait_ready = [&](int i) -> int {
-    if (side && (do_pack || (i == 0 && l.G > 0))) NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->ev[i], 0));
-    return NERAF_OK;
-  };
+  const float* c1 = l.G > 0 ? c1w : biases[0];
+  const int64_t ldw0 = l.G + l.E;
 
   if (!bf) {
     // the per-query block of h is kept in the workspace: backward reads it for dW1
     float* enc = reinterpret_cast<float*>(at(ws, l.enc));
-    if (q->enc) {
-      NERAF_REQUIRE(q->enc_ld >= l.E, "field_forward: enc_ld < n_enc");
+    if (q->enc)
       NERAF_CHECK_CUDA(cudaMemcpy2DAsync(enc, (size_t)l.E * 4, q->enc, (size_t)q->enc_ld * 4, (size_t)l.E * 4, (size_t)B,
                                          cudaMemcpyDeviceToDevice, stream));
-    } else {
-      NERAF_TRY(encode_queries(q, enc, l.E, nullptr, 0, nullptr, 0, l.E, stream));
-    }
+    NERAF_TRY(field_prep(q->enc ? nullptr : q, enc, l.E, nullptr, 0, l.E, weights[0], ldw0, biases[0], grid_feature, l.n[0],
+                         l.G, c1w, l.E, nullptr, 0, stream));
     const float* x = enc;
     int64_t ldx = l.E;
     for (int i = 0; i < l.L; ++i) {
       float* y = reinterpret_cast<float*>(at(ws, l.x[i]));
       const float* w = weights[i] + (i == 0 ? l.G : 0);
-      const int64_t ldw = i == 0 ? l.G + l.E : l.k[i];
+      const int64_t ldw = i == 0 ? ldw0 : l.k[i];
       NERAF_TRY(gemm_f32(B, l.n[i], l.k[i], x, ldx, 1, w, ldw, 1, i == 0 ? c1 : biases[i], NERAF_ACT_LEAKY, nullptr, 0, y,
                          l.n[i], 0, stream));
       x = y; ldx = l.n[i];
@@ -309,67 +290,51 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
   }
 
   // ---- bf16 tensor-core path
+  const bool do_pack = repack != 0;
+  SideStream* side = do_pack ? side_stream() : nullptr;
+  if (side) {                                        // layers 2.. are re-packed beside the encodings and layer 1
+    NERAF_CHECK_CUDA(cudaEventRecord(side->fork, stream));
+    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    NERAF_TRY(pack_layers(l, 1, weights, biases, pack, side->stream));
+    NERAF_CHECK_CUDA(cudaEventRecord(side->done, side->stream));
+  } else if (do_pack) {
+    NERAF_TRY(pack_layers(l, 1, weights, biases, pack, stream));
+  }
   void* enc = at(ws, l.enc);
-  void* enc_t = keep ? at(ws, l.enc_t) : nullptr;
-  if (q->enc) {
-    NERAF_REQUIRE(q->enc_ld >= l.E, "field_forward: enc_ld < n_enc");
-    NERAF_TRY(convert_bf16(q->enc, B, l.E, q->enc_ld, enc, l.ld_enc, enc_t, l.ldm, stream));
-  }
-  else NERAF_TRY(encode_queries(q, nullptr, 0, enc, l.ld_enc, enc_t, l.ldm, (int)l.ld_enc, stream));
+  if (q->enc) NERAF_TRY(convert_bf16(q->enc, B, l.E, q->enc_ld, enc, l.ld_enc, nullptr, 0, stream));
+  NERAF_TRY(field_prep(q->enc ? nullptr : q, nullptr, 0, enc, l.ld_enc, (int)l.ld_enc, weights[0], ldw0, biases[0],
+                       grid_feature, l.n[0], l.G, c1w, l.E, do_pack ? at(pack, l.w[0]) : nullptr, l.ldw[0], stream));
 
-  if (use_mega()) {
-    // One persistent launch for the whole MLP (two when the operands are being re-packed: layer 1 starts as soon
-    // as its own copies exist, the remaining layers once the helper stream has finished all of them).
-    MegaJob jobs[NERAF_MAX_TRUNK + 1];
-    const void* xin = enc;
-    int64_t ldin = l.ld_enc;
-    for (int i = 0; i <= l.L; ++i) {
-      const bool head = i == l.L;
-      MegaJob& j = jobs[i];
-      j = make_job(B, head ? l.CF : l.n[i], head ? l.W : l.k[i], xin, ldin, head ? at(pack, l.wh) : at(pack, l.w[i]),
-                   head ? l.ldwh : l.ldw[i], i - 1, 0);
-      if (head) {
-        j.epi.bias = reinterpret_cast<const float*>(at(pack, l.bh));
-        j.epi.act = NERAF_ACT_TANH10;
-        j.epi.out_f32 = out; j.epi.ld_f32 = l.CF;
-      } else {
-        j.epi.bias = i == 0 ? c1 : biases[i];
-        j.epi.act = NERAF_ACT_LEAKY;
-        j.epi.out_bf16 = at(ws, l.x[i]); j.epi.ld_bf16 = l.ldx[i];     // backward consumes it MN-major: no transpose
-        xin = j.epi.out_bf16; ldin = l.ldx[i];
-      }
-    }
-    NERAF_TRY(wait_ready(0));
-    if (do_pack && side) {
-      NERAF_TRY(mega_run(jobs, 1, at(ws, l.counters), l.counters_bytes, stream));
-      NERAF_TRY(wait_ready(l.L));
-      jobs[1].wait_job = -1;
-      for (int i = 2; i <= l.L; ++i) jobs[i].wait_job = i - 2;
-      NERAF_TRY(mega_run(jobs + 1, l.L, at(ws, l.counters), l.counters_bytes, stream));
+  // One persistent launch for the whole MLP (two when the operands are being re-packed on the helper stream:
+  // layer 1 starts as soon as its own copy exists, the remaining layers once the helper stream has finished).
+  MegaJob jobs[NERAF_MAX_TRUNK + 1];
+  const void* xin = enc;
+  int64_t ldin = l.ld_enc;
+  for (int i = 0; i <= l.L; ++i) {
+    const bool head = i == l.L;
+    MegaJob& j = jobs[i];
+    j = make_job(B, head ? l.CF : l.n[i], head ? l.W : l.k[i], xin, ldin, head ? at(pack, l.wh) : at(pack, l.w[i]),
+                 head ? l.ldwh : l.ldw[i], i - 1, 0);
+    if (head) {
+      j.epi.bias = reinterpret_cast<const float*>(at(pack, l.bh));
+      j.epi.act = NERAF_ACT_TANH10;
+      j.epi.out_f32 = out; j.epi.ld_f32 = l.CF;
     } else {
-      NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream));
+      j.epi.bias = i == 0 ? c1 : biases[i];
+      j.epi.act = NERAF_ACT_LEAKY;
+      j.epi.out_bf16 = at(ws, l.x[i]); j.epi.ld_bf16 = l.ldx[i];
+      xin = j.epi.out_bf16; ldin = l.ldx[i];
     }
-    return NERAF_OK;
   }
-
-  const void* x = enc;
-  int64_t ldx = l.ld_enc;
-  for (int i = 0; i < l.L; ++i) {
-    NERAF_TRY(wait_ready(i));
-    neraf_gemm_epilogue e = {};
-    e.bias = i == 0 ? c1 : biases[i];
-    e.act = NERAF_ACT_LEAKY;
-    e.out_bf16 = at(ws, l.x[i]); e.ld_bf16 = l.ldx[i];
-    if (keep) { e.out_bf16_t = at(ws, l.xt[i]); e.ld_t = l.ldm; }
-    NERAF_TRY(gemm_bf16(B, l.n[i], l.k[i], x, ldx, at(pack, l.w[i]), l.ldw[i], &e, stream));
-    x = e.out_bf16; ldx = l.ldx[i];
+  if (side) {
+    NERAF_TRY(mega_run(jobs, 1, at(ws, l.counters), l.counters_bytes, stream));
+    NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
+    jobs[1].wait_job = -1;
+    for (int i = 2; i <= l.L; ++i) jobs[i].wait_job = i - 2;
+    NERAF_TRY(mega_run(jobs + 1, l.L, at(ws, l.counters), l.counters_bytes, stream));
+  } else {
+    NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream));
   }
-  NERAF_TRY(wait_ready(l.L));
-  neraf_gemm_epilogue e = {};
-  e.bias = reinterpret_cast<const float*>(at(pack, l.bh));
-  e.act = NERAF_ACT_TANH10;
-  e.out_f32 = out; e.ld_f32 = l.CF;
-  NERAF_TRY(gemm_bf16(B, l.CF, l.W, x, ldx, at(pack, l.wh), l.ldwh, &e, stream));
   return NERAF_OK;
 }
 
@@ -398,7 +363,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
 
   if (!bf) {
     float* dzh = reinterpret_cast<float*>(at(ws, l.dzh));
-    NERAF_TRY(head_backward(dout, out, B, l.CF, dzh, l.CF, nullptr, 0, nullptr, 0, nullptr, 0, stream));
+    NERAF_TRY(head_backward(dout, out, B, l.CF, dzh, l.CF, nullptr, 0, nullptr, 0, stream));
     const float* x_last = reinterpret_cast<const float*>(at(ws, l.x[last]));
     float* dz_last = reinterpret_cast<float*>(at(ws, l.dz[last]));
     for (int c = 0; c < l.C; ++c) {
@@ -424,10 +389,8 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
         const float* enc = reinterpret_cast<const float*>(at(ws, l.enc));
         NERAF_TRY(gemm_f32(l.n[0], l.E, B, dz, 1, l.n[0], enc, 1, l.E, nullptr, NERAF_ACT_NONE, nullptr, 0,
                            dweights[0] + l.G, ldw0, 0, stream));
-        if (l.G > 0) {
-          NERAF_TRY(outer_product(dbiases[0], grid_feature, l.n[0], l.G, dweights[0], ldw0, stream));
-          if (dgrid) NERAF_TRY(grid_backward(weights[0], ldw0, dbiases[0], l.n[0], l.G, dgrid, stream));
-        }
+        if (l.G > 0)
+          NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, false, stream));
         if (denc)
           NERAF_TRY(gemm_f32(B, l.E, l.n[0], dz, l.n[0], 1, weights[0] + l.G, 1, ldw0, nullptr, NERAF_ACT_NONE, nullptr, 0,
                              denc, denc_ld, 0, stream));
@@ -436,130 +399,75 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
     return NERAF_OK;
   }
 
-  if (use_mega()) {
-    // ---- bf16 tensor-core path, job-list kernel: the dgrad chain and all weight-gradient GEMMs in ONE launch.
-    // Bias gradients are column sums of the fp32 dZ accumulated by the dgrad epilogues (atomics on zeroed buffers).
-    for (int i = 0; i < l.L + l.C; ++i) {
-      const size_t n = (size_t)(i < l.L ? l.n[i] : l.F);
-      NERAF_CHECK_CUDA(cudaMemsetAsync(dbiases[i], 0, n * 4, stream));
-    }
-    void* dzh = at(ws, l.dzh);
-    NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, nullptr, 0, dbiases + l.L, l.F, stream));
-    MegaJob jobs[NERAF_MEGA_MAX_JOBS];
-    int nj = 0;
-    // dZ_last = (dZ_head W_head) * leaky'(x_last)
-    int producer = nj;
-    {
-      MegaJob& j = jobs[nj++];
-      j = make_job(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wht), l.ldwht, -1, 0);
-      j.epi.gate = at(ws, l.x[last]); j.epi.ldg = l.ldx[last];
-      j.epi.out_bf16 = at(ws, l.dz[last]); j.epi.ld_bf16 = l.ldx[last];
-      j.colsum = dbiases[last];
-    }
-    {                                                     // head weight gradients (all heads in one GEMM)
-      MegaJob& j = jobs[nj++];
-      j = make_wgrad_job(l.CF, l.W, B, dzh, l.ld_h, at(ws, l.x[last]), l.ldx[last], -1);
-      j.wait_all = 0;
-      j.epi.out_f32 = l.C == 1 ? dweights[l.L] : reinterpret_cast<float*>(at(ws, l.dwh));
-      j.epi.ld_f32 = l.W;
-    }
-    for (int i = last; i >= 0; --i) {
-      const int dz_producer = producer;                   // job that writes dZ_i
-      if (i > 0) {                                        // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
-        producer = nj;
-        MegaJob& j = jobs[nj++];
-        j = make_job(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.wt[i]), l.ldwt[i], dz_producer, 0);
-        j.epi.gate = at(ws, l.x[i - 1]); j.epi.ldg = l.ldx[i - 1];
-        j.epi.out_bf16 = at(ws, l.dz[i - 1]); j.epi.ld_bf16 = l.ldx[i - 1];
-        j.colsum = dbiases[i - 1];
-      }
-      MegaJob& w = jobs[nj++];                            // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
-      if (i > 0) {
-        w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
-        w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
-      } else {
-        w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
-        w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
-        if (denc) {
-          MegaJob& e = jobs[nj++];
-          e = make_job(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.wt[0]), l.ldwt[0], dz_producer, 0);
-          e.epi.out_f32 = denc; e.epi.ld_f32 = denc_ld;
-        }
-      }
-    }
-    NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream));
-    if (l.C > 1)
-      for (int c = 0; c < l.C; ++c)
-        NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,
-                                         cudaMemcpyDeviceToDevice, stream));
-    if (l.G > 0) {
-      NERAF_TRY(outer_product(dbiases[0], grid_feature, l.n[0], l.G, dweights[0], ldw0, stream));
-      if (dgrid) NERAF_TRY(grid_backward(weights[0], ldw0, dbiases[0], l.n[0], l.G, dgrid, stream));
-    }
-    return NERAF_OK;
-  }
-
-  // ---- bf16 tensor-core path.  Critical chain on `stream`: head gradient -> dgrad GEMMs (dZ_L ... dZ_1).
-  // Everything that only CONSUMES a dZ (bias gradients, weight-gradient GEMMs, grid-feature gradients) is forked
-  // onto the helper stream as soon as that dZ exists and joined at the end.
-  SideStream* side = side_stream();
-  cudaStream_t sw = side ? side->stream : stream;
-  int ev = 0;
-  auto fork = [&]() -> int {            // make the helper stream wait for everything enqueued on `stream` so far
-    if (!side) return NERAF_OK;
-    NERAF_CHECK_CUDA(cudaEventRecord(side->ev[ev], stream));
-    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->ev[ev], 0));
-    ++ev;
-    return NERAF_OK;
-  };
-  void* dzh = at(ws, l.dzh);
-  void* dzht = at(ws, l.dzht);
-  NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dzht, l.ldm, nullptr, 0, stream));
-  NERAF_TRY(fork());
-  for (int c = 0; c < l.C; ++c) {
-    const uint8_t* dzct = at(dzht, (size_t)c * l.F * l.ldm * 2);
-    NERAF_TRY(rowsum_bf16(dzct, l.F, B, l.ldm, dbiases[l.L + c], sw));
-    neraf_gemm_epilogue e = {};
-    e.out_f32 = dweights[l.L + c]; e.ld_f32 = l.W;
-    NERAF_TRY(gemm_bf16(l.F, l.W, B, dzct, l.ldm, at(ws, l.xt[last]), l.ldm, &e, sw));
-  }
+  // ---- bf16 tensor-core path: the dgrad chain and all weight-gradient GEMMs in ONE launch.
+  // Bias gradients are column sums of the fp32 dZ accumulated by the epilogues (atomics on zeroed buffers): the
+  // buffers (and dgrid, accumulated by grid_grads) are zeroed with as few memsets as their addresses allow -- one
+  // when the caller laid them out back to back (neraf_b200/field.py does).
+  bool dgrid_zeroed = false;
   {
-    neraf_gemm_epilogue e = {};
-    e.gate = at(ws, l.x[last]); e.ldg = l.ldx[last];
-    e.out_bf16 = at(ws, l.dz[last]); e.ld_bf16 = l.ldx[last];
-    e.out_bf16_t = at(ws, l.dzt[last]); e.ld_t = l.ldm;
-    NERAF_TRY(gemm_bf16(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wht), l.ldwht, &e, stream));
+    const int nb = l.L + l.C;
+    int i = 0;
+    while (i < nb) {
+      float* start = dbiases[i];
+      float* end = start + (i < l.L ? l.n[i] : l.F);
+      int j = i + 1;
+      while (j < nb && dbiases[j] == end) { end += j < l.L ? l.n[j] : l.F; ++j; }
+      if (j == nb && dgrid && l.G > 0 && dgrid == end) { end += l.G; dgrid_zeroed = true; }
+      NERAF_CHECK_CUDA(cudaMemsetAsync(start, 0, (size_t)(end - start) * 4, stream));
+      i = j;
+    }
+  }
+  void* dzh = at(ws, l.dzh);
+  NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream));
+  bool heads_contiguous = true;                      // the C head gradients form one (C*F, W) matrix?
+  for (int c = 1; c < l.C; ++c) heads_contiguous = heads_contiguous && dweights[l.L + c] == dweights[l.L] + (size_t)c * l.F * l.W;
+  MegaJob jobs[NERAF_MEGA_MAX_JOBS];
+  int nj = 0;
+  int producer = nj;
+  {                                                    // dZ_last = (dZ_head W_head) * leaky'(x_last)
+    MegaJob& j = jobs[nj++];
+    j = make_dgrad_job(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wh), l.ldwh, -1);
+    j.epi.gate = at(ws, l.x[last]); j.epi.ldg = l.ldx[last];
+    j.epi.out_bf16 = at(ws, l.dz[last]); j.epi.ld_bf16 = l.ldx[last];
+    j.colsum = dbiases[last];
+  }
+  {                                                    // head weight gradients (all heads in one GEMM)
+    MegaJob& j = jobs[nj++];
+    j = make_wgrad_job(l.CF, l.W, B, dzh, l.ld_h, at(ws, l.x[last]), l.ldx[last], -1);
+    j.wait_all = 0;
+    j.epi.out_f32 = heads_contiguous ? dweights[l.L] : reinterpret_cast<float*>(at(ws, l.dwh));
+    j.epi.ld_f32 = l.W;
   }
   for (int i = last; i >= 0; --i) {
-    NERAF_TRY(fork());                                                    // dZ_i (both layouts) is on its way
-    if (i > 0) {                                                          // chain first: dZ_{i-1}
-      neraf_gemm_epilogue ed = {};
-      ed.gate = at(ws, l.x[i - 1]); ed.ldg = l.ldx[i - 1];
-      if (i - 1 > 0 || denc) { ed.out_bf16 = at(ws, l.dz[i - 1]); ed.ld_bf16 = l.ldx[i - 1]; }
-      ed.out_bf16_t = at(ws, l.dzt[i - 1]); ed.ld_t = l.ldm;
-      NERAF_TRY(gemm_bf16(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.wt[i]), l.ldwt[i], &ed, stream));
-    } else if (denc) {
-      neraf_gemm_epilogue ee = {};
-      ee.out_f32 = denc; ee.ld_f32 = denc_ld;
-      NERAF_TRY(gemm_bf16(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.wt[0]), l.ldwt[0], &ee, stream));
+    const int dz_producer = producer;                  // job that writes dZ_i
+    if (i > 0) {                                       // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
+      producer = nj;
+      MegaJob& j = jobs[nj++];
+      j = make_dgrad_job(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.w[i]), l.ldw[i], dz_producer);
+      j.epi.gate = at(ws, l.x[i - 1]); j.epi.ldg = l.ldx[i - 1];
+      j.epi.out_bf16 = at(ws, l.dz[i - 1]); j.epi.ld_bf16 = l.ldx[i - 1];
+      j.colsum = dbiases[i - 1];
     }
-    NERAF_TRY(rowsum_bf16(at(ws, l.dzt[i]), l.n[i], B, l.ldm, dbiases[i], sw));
-    neraf_gemm_epilogue ew = {};
+    MegaJob& w = jobs[nj++];                           // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
     if (i > 0) {
-      ew.out_f32 = dweights[i]; ew.ld_f32 = l.k[i];
-      NERAF_TRY(gemm_bf16(l.n[i], l.k[i], B, at(ws, l.dzt[i]), l.ldm, at(ws, l.xt[i - 1]), l.ldm, &ew, sw));
+      w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
+      w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
     } else {
-      ew.out_f32 = dweights[0] + l.G; ew.ld_f32 = ldw0;
-      NERAF_TRY(gemm_bf16(l.n[0], l.E, B, at(ws, l.dzt[0]), l.ldm, at(ws, l.enc_t), l.ldm, &ew, sw));
-      if (l.G > 0) {
-        NERAF_TRY(outer_product(dbiases[0], grid_feature, l.n[0], l.G, dweights[0], ldw0, sw));
-        if (dgrid) NERAF_TRY(grid_backward(weights[0], ldw0, dbiases[0], l.n[0], l.G, dgrid, sw));
+      w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
+      w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
+      if (denc) {
+        MegaJob& e = jobs[nj++];
+        e = make_dgrad_job(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.w[0]), l.ldw[0], dz_producer);
+        e.epi.out_f32 = denc; e.epi.ld_f32 = denc_ld;
       }
     }
   }
-  if (side) {                                                             // join
-    NERAF_CHECK_CUDA(cudaEventRecord(side->done, side->stream));
-    NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
-  }
+  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream));
+  if (!heads_contiguous)
+    for (int c = 0; c < l.C; ++c)
+      NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,
+                                       cudaMemcpyDeviceToDevice, stream));
+  if (l.G > 0)
+    NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, dgrid_zeroed, stream));
   return NERAF_OK;
 }

@@ -15,20 +15,25 @@
 // smaller index, so the smallest unfinished tile is always runnable.
 //
 // Tile = 256 x bn (bn in {64,128,256}, per job) on a CTA PAIR (tcgen05 cta_group::2, see gemm_umma.cu): each
-// CTA stages its 128 rows of A and bn/2 rows of B per 64-deep k-block through a 6-stage TMA/mbarrier ring, the
+// CTA stages its 128 rows of A and bn/2 rows of B per 64-deep k-block through a 5-stage TMA/mbarrier ring, the
 // leader issues the MMAs, two 256-column TMEM accumulator stages overlap the epilogue with the next tile.
+// 10 warps per CTA: TMA producer, MMA issuer, 8 epilogue warps (two per TMEM lane quarter, each takes half of the
+// tile's 32-column chunks: at the reference batch a unit gets about one tile per layer, so the epilogue sits on
+// the critical path of the layer chain and its latency is what matters).
 //
 // Operand layouts.  K-major operands (row-major with the contraction innermost) are the forward / dgrad case.
 // The weight gradient dW = dZ^T X contracts over the BATCH, which is the OUTER dimension of the row-major
 // activations: both operands are consumed MN-major (tcgen05 descriptor major bit, TMA boxes of 64 contiguous
 // MN elements x 64 batch rows), so no transposed copy of any activation or gradient is ever written.
 //
-// Epilogue.  TMEM -> registers (lane = row) -> bias / LeakyReLU / 10 tanh / LeakyReLU' gate -> bf16 (or fp32)
-// packed into a 128-byte-swizzled 32-row staging tile per warp -> one TMA store per 64 (32) columns; M/N tails
-// are clipped by the tensor map.  Bias gradients are column sums taken from the fp32 values with a
+// Epilogue.  Per 32 x 32 chunk: tcgen05.ld (lane = row) with the NEXT chunk's bias / gate loads issued behind it
+// -> bias (one coalesced load per chunk, shuffle broadcast) / LeakyReLU / 10 tanh / LeakyReLU' gate, activation
+// switch hoisted out of the element loop -> the lane's 32 consecutive columns (64 B of bf16 / 128 B of fp32, whole
+// sectors) go straight from registers to global memory as 16-byte stores: no staging and no store-completion wait
+// on the critical path of the layer chain (a TMA-store epilogue measured ~1300 cycles per chunk, profiles/r01b).  Bias gradients are column sums taken from the fp32 values with a
 // recursive-halving shuffle reduction (31 shuffles per 32 x 32 block) and one atomic per column.
-// Cross-SM visibility: stores complete (bulk wait_group) -> __threadfence -> atomicAdd(counter); consumer:
-// ld.acquire spin -> fence.proxy.async -> TMA loads.
+// Cross-SM visibility: stores -> __threadfence -> red.release(counter); consumer: ld.acquire spin ->
+// fence.proxy.async -> TMA loads.
 #include <cstdlib>
 #include <mutex>
 
@@ -39,25 +44,28 @@
 namespace neraf {
 namespace umma {
 
-constexpr int MEGA_THREADS = 192;
+constexpr int MEGA_EPI_WARPS = 8;                              // two per TMEM lane quarter (column halves)
+constexpr int MEGA_THREADS = 64 + 32 * MEGA_EPI_WARPS;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int MEGA_STAGES = 6;
 constexpr int MEGA_A_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB
 constexpr int MEGA_B_BYTES = 128 * BLOCK_K * 2;                // up to bn/2 = 128 rows: 16 KB
-constexpr int MEGA_OUT_BYTES = 32 * 128;                       // per-warp staging tile: 32 rows x 128 B
-constexpr int MEGA_SMEM_BYTES = 1024 + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES) + 4 * MEGA_OUT_BYTES + (2 * MEGA_STAGES + 4) * 8 + 16;
+constexpr int MEGA_OUT_BYTES = 32 * 128;                       // per-warp 32x32 fp32 transpose tile (unaligned fp32 outputs only)
+constexpr int MEGA_SMEM_BYTES = 1024 + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES) + MEGA_EPI_WARPS * MEGA_OUT_BYTES + (2 * MEGA_STAGES + 4) * 8 + 16;
 constexpr int MEGA_TMEM_COLS = 512;
 constexpr int MEGA_ACC_COLS = 256;
 constexpr int MN_BOX_BYTES = 64 * 128;                         // one MN-major box: 64 k-rows x 64 MN elements
+constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct alignas(64) DeviceJob {
-  CUtensorMap tmA, tmB, tmOutB, tmOutF;
+  CUtensorMap tmA, tmB;
   int M, N, K, bn;
   int tile_start, num_m, num_n, cnt_off;
   int wait_job, wait_all, wait_target, wait_nrb, wait_cnt_off;
-  int act, a_mn, b_mn, f32_tma;
+  int act, a_mn, b_mn;
+  int out_mode;                    // 0 none, 1 bf16, 2 fp32 (16-byte aligned rows), 3 fp32 (unaligned rows, via smem transpose)
+  __nv_bfloat16* out_bf16; long long ld_bf16;
   const float* bias;
   const __nv_bfloat16* gate; long long ldg;
-  int has_out_bf16, pad0;
   float* out_f32; long long ld_f32;
   float* colsum;
 };
@@ -73,6 +81,9 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -81,19 +92,10 @@ __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int t
   const long long t0 = clock64();
   unsigned int spins = 0;
   while (ld_acquire(p) < target) {
-    __nanosleep(64);
+    __nanosleep(32);
     if ((++spins & 255u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) __trap();
   }
 }
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // MN-major, 128-byte-swizzled operand: 64 contiguous MN elements per k row (128 B), 8-row groups 1024 B apart
 // (SBO), the next block of 64 MN elements one TMA box (8 KB) further (LBO).
@@ -116,11 +118,29 @@ __device__ __forceinline__ float column_sums_32(float (&v)[32], int lane) {
     for (int i = 0; i < s; ++i) {
       const float keep = upper ? v[i + s] : v[i];
       const float send = upper ? v[i] : v[i + s];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = keep + __shfl_xor_sync(FULL_MASK, send, s);
     }
   }
   return v[0];
 }
+
+// tcgen05.ld of one 32 x 32 fp32 block WITHOUT the wait (the caller overlaps independent loads with it).
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float gate_factor(float x) { return x > 0.f ? 1.f : kLeakySlope; }
 
 __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) {
   constexpr int CG = 2;
@@ -129,7 +149,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + MEGA_STAGES * MEGA_A_BYTES;
   uint8_t* out_buf = smem + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES);       // 1024-byte aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_buf + 4 * MEGA_OUT_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_buf + MEGA_EPI_WARPS * MEGA_OUT_BYTES);
   uint64_t* empty_bar = full_bar + MEGA_STAGES;
   uint64_t* tmem_full = empty_bar + MEGA_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -142,7 +162,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MEGA_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4 * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, MEGA_EPI_WARPS * CG); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc<CG>(tmem_slot, MEGA_TMEM_COLS); tmem_relinquish<CG>(); }
@@ -152,6 +172,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int j = 0;
@@ -160,43 +181,67 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
         const DeviceJob& J = P.jobs[j];
         const int local = tile - J.tile_start;
         const int mt = local / J.num_n, nt = local % J.num_n;          // row-block major: a row block completes early
-        // ---- dependencies: operands written by earlier tiles of this launch (other SMs)
+        const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
+        const int b_rows = J.bn / CG;
+        const uint32_t stage_bytes = (uint32_t)(MEGA_A_BYTES + b_rows * BLOCK_K * 2) * CG;
+        const int a_row0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
+        const int b_row0 = nt * J.bn + (int)cta_rank * b_rows;
+        auto load_a = [&](int st, int kb) {
+          uint8_t* sa = smem_a + st * MEGA_A_BYTES;
+          if (!J.a_mn) {
+            tma_load_2d<CG>(sa, &J.tmA, full_bar + st, kb * BLOCK_K, a_row0);
+          } else {                                        // matrix is (K rows, MN cols): coordinates {mn, k}
+            tma_load_2d<CG>(sa, &J.tmA, full_bar + st, a_row0, kb * BLOCK_K);
+            tma_load_2d<CG>(sa + MN_BOX_BYTES, &J.tmA, full_bar + st, a_row0 + 64, kb * BLOCK_K);
+          }
+        };
+        auto load_b = [&](int st, int kb) {
+          uint8_t* sb = smem_b + st * MEGA_B_BYTES;
+          if (!J.b_mn) {
+            tma_load_2d<CG>(sb, &J.tmB, full_bar + st, kb * BLOCK_K, b_row0);
+          } else {
+            tma_load_2d<CG>(sb, &J.tmB, full_bar + st, b_row0, kb * BLOCK_K);
+            if (b_rows > 64) tma_load_2d<CG>(sb + MN_BOX_BYTES, &J.tmB, full_bar + st, b_row0 + 64, kb * BLOCK_K);
+          }
+        };
+        int kb0 = 0;
         if (J.wait_job >= 0) {
+          // Operands written by earlier tiles of this launch (other SMs).  Only the operands that ARE produced in the
+          // launch have to wait: a K-major B of a dependent job is a weight matrix, so its first ring-full of
+          // k-blocks is fetched while the dependency is still being resolved.
+          const bool b_early = !J.b_mn && !J.a_mn;
+          const int pre = b_early ? (num_kb < MEGA_STAGES ? num_kb : MEGA_STAGES) : 0;
+          int st = stage; uint32_t ph = phase;
+          for (int kb = 0; kb < pre; ++kb) {
+            mbar_wait(empty_bar + st, ph ^ 1);
+            if (is_leader) mbar_expect_tx(full_bar + st, stage_bytes);
+            load_b(st, kb);
+            if (++st == MEGA_STAGES) { st = 0; ph ^= 1; }
+          }
           if (J.wait_all) {
             for (int rb = 0; rb < J.wait_nrb; ++rb) spin_until(P.counters + J.wait_cnt_off + rb, (unsigned)J.wait_target);
           } else {
             spin_until(P.counters + J.wait_cnt_off + mt, (unsigned)J.wait_target);
           }
           fence_proxy_async_all();
+          for (int kb = 0; kb < pre; ++kb) {
+            load_a(stage, kb);
+            if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
+          }
+          kb0 = pre;
         }
-        const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
-        const int b_rows = J.bn / CG;
-        const uint32_t stage_bytes = (uint32_t)(MEGA_A_BYTES + b_rows * BLOCK_K * 2) * CG;
-        const int a_row0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
-        const int b_row0 = nt * J.bn + (int)cta_rank * b_rows;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           if (is_leader) mbar_expect_tx(full_bar + stage, stage_bytes);
-          uint8_t* sa = smem_a + stage * MEGA_A_BYTES;
-          uint8_t* sb = smem_b + stage * MEGA_B_BYTES;
-          if (!J.a_mn) {
-            tma_load_2d<CG>(sa, &J.tmA, full_bar + stage, kb * BLOCK_K, a_row0);
-          } else {                                        // matrix is (K rows, MN cols): coordinates {mn, k}
-            tma_load_2d<CG>(sa, &J.tmA, full_bar + stage, a_row0, kb * BLOCK_K);
-            tma_load_2d<CG>(sa + MN_BOX_BYTES, &J.tmA, full_bar + stage, a_row0 + 64, kb * BLOCK_K);
-          }
-          if (!J.b_mn) {
-            tma_load_2d<CG>(sb, &J.tmB, full_bar + stage, kb * BLOCK_K, b_row0);
-          } else {
-            tma_load_2d<CG>(sb, &J.tmB, full_bar + stage, b_row0, kb * BLOCK_K);
-            if (b_rows > 64) tma_load_2d<CG>(sb + MN_BOX_BYTES, &J.tmB, full_bar + stage, b_row0 + 64, kb * BLOCK_K);
-          }
+          load_a(stage, kb);
+          load_b(stage, kb);
           if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
     if (lane == 0 && is_leader) {
       int stage = 0; uint32_t phase = 0;
       int it = 0, j = 0;
@@ -232,8 +277,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
     }
     __syncwarp();
   } else {
-    const int quarter = warp & 3;
-    uint8_t* wbuf = out_buf + (warp - 2) * MEGA_OUT_BYTES;       // this warp's 32 x 128 B staging tile
+    // ------------------------------------------------------------------ epilogue: 8 warps, warp (quarter, half)
+    const int quarter = warp & 3;                                 // TMEM lanes this warp may read
+    const int half = (warp - 2) >> 2;                             // which half of the tile's 32-column chunks
+    uint8_t* wbuf = out_buf + (warp - 2) * MEGA_OUT_BYTES;
     float* wbuf_f = reinterpret_cast<float*>(wbuf);
     int it = 0, j = 0;
     for (int tile = unit; tile < P.num_tiles; tile += num_units, ++it) {
@@ -243,29 +290,58 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       const int mt = local / J.num_n, nt = local % J.num_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int M = J.M, N = J.N, bn = J.bn;
+      const int M = J.M, N = J.N;
       const float* bias = J.bias;
       const int act = J.act;
       const __nv_bfloat16* gate = J.gate;
       const long long ldg = J.ldg;
-      const bool out_b = J.has_out_bf16 != 0;
-      float* out_f32 = J.out_f32;
-      const long long ld_f32 = J.ld_f32;
-      const bool f32_tma = J.f32_tma != 0;
+      const int out_mode = J.out_mode;
       float* colsum = J.colsum;
-      mbar_wait(tmem_full + as, aphase);
-      tc_fence_after();
       const int m_base = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M + quarter * 32;
       const int m = m_base + lane;
       const bool row_ok = m < M;
-      const int nchunks = bn / 32;
+      const int per = J.bn / 64;                                  // chunks per warp: 1, 2 or 4
+      const int c_first = half * per;
+      const int n_first = nt * J.bn + c_first * 32;
+      int nvalid = (N - n_first + 31) / 32;                       // my chunks that start inside N
+      nvalid = nvalid < 0 ? 0 : (nvalid > per ? per : nvalid);
+      const bool gate_vec_ok = gate != nullptr && (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(gate) & 15) == 0);
+
+      // operands of the first chunk that do not depend on the accumulator: fetched before it is ready
+      float b_cur = 0.f, b_next = 0.f;
+      uint4 g_cur[4], g_next[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { g_cur[q] = make_uint4(0, 0, 0, 0); g_next[q] = g_cur[q]; }
+      auto fetch = [&](int n0, float& b, uint4 (&g)[4]) {
+        if (bias != nullptr && n0 + lane < N) b = __ldg(bias + n0 + lane); else b = 0.f;
+        if (gate_vec_ok && row_ok && n0 + 32 <= N) {
+          const uint4* gp = reinterpret_cast<const uint4*>(gate + (long long)m * ldg + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g[q] = __ldg(gp + q);
+        }
+      };
+      if (nvalid > 0) fetch(n_first, b_cur, g_cur);
+
+      mbar_wait(tmem_full + as, aphase);
+      tc_fence_after();
+      if (nvalid == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(tmem_empty + as);
+          else mbar_arrive_remote(tmem_empty + as, 0);
+        }
+      }
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        const int n0 = nt * bn + c * 32;
-        if (n0 >= N) break;
+      for (int k = 0; k < nvalid; ++k) {
+        const int c = c_first + k;
+        const int n0 = nt * J.bn + c * 32;
+        const bool full_chunk = n0 + 32 <= N;
         float v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MEGA_ACC_COLS + c * 32), v);
-        if (c == nchunks - 1 || n0 + 32 >= N) {           // accumulator fully read: hand the TMEM stage back early
+        tmem_ld_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MEGA_ACC_COLS + c * 32), v);
+        if (k + 1 < nvalid) fetch(n0 + 32, b_next, g_next);      // next chunk's bias / gate behind the TMEM load
+        tmem_ld_wait();
+        if (k == nvalid - 1) {                                    // accumulator fully read: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -273,99 +349,88 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
             else mbar_arrive_remote(tmem_empty + as, 0);
           }
         }
-        const bool full_chunk = n0 + 32 <= N;
-        if (bias) {
+        if (bias != nullptr) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] += (full_chunk || n0 + q < N) ? __ldg(bias + n0 + q) : 0.f;
+          for (int q = 0; q < 32; ++q) v[q] += __shfl_sync(FULL_MASK, b_cur, q);
         }
-        if (act != NERAF_ACT_NONE) {
+        if (act == NERAF_ACT_LEAKY) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = apply_act(v[q], act);
+          for (int q = 0; q < 32; ++q) v[q] = v[q] > 0.f ? v[q] : kLeakySlope * v[q];
+        } else if (act == NERAF_ACT_TANH10) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = 10.f * tanhf(v[q]);
         }
-        if (gate && row_ok) {
-          const __nv_bfloat16* g = gate + (long long)m * ldg + n0;
-          if (full_chunk && (ldg % 8 == 0)) {
+        if (gate != nullptr && row_ok) {
+          if (gate_vec_ok && full_chunk) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 raw = __ldg(reinterpret_cast<const uint4*>(g) + q);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&g_cur[q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(h[e]);
-                v[q * 8 + e * 2] *= f.x > 0.f ? 1.f : kLeakySlope;
-                v[q * 8 + e * 2 + 1] *= f.y > 0.f ? 1.f : kLeakySlope;
+                v[q * 8 + e * 2] *= gate_factor(f.x);
+                v[q * 8 + e * 2 + 1] *= gate_factor(f.y);
               }
             }
           } else {
+            const __nv_bfloat16* g = gate + (long long)m * ldg + n0;
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              if (n0 + q < N) v[q] *= __bfloat162float(g[q]) > 0.f ? 1.f : kLeakySlope;
+              if (n0 + q < N) v[q] *= gate_factor(__bfloat162float(g[q]));
           }
         }
-        // ---- bf16 row-major output: two 32-column chunks share one 64-column (128 B) staging tile / TMA store
-        if (out_b) {
-          const int half = c & 1;
-          if (half == 0) {                                // staging tile is about to be rewritten
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-          }
+        if (out_mode == 1) {
+          // bf16 row-major, straight from registers: the lane owns 32 consecutive columns of its row = 64 contiguous
+          // bytes (two full sectors), written as 4 x 16 B.  No staging, no store-completion wait on the critical path.
+          if (row_ok) {
+            __nv_bfloat16* dst = J.out_bf16 + (long long)m * J.ld_bf16 + n0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+            for (int i = 0; i < 4; ++i) {
+              if (full_chunk || n0 + i * 8 + 8 <= N) {
+                uint4 pk;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
-            const int chunk16 = half * 4 + i;             // 16-byte chunk inside the 128-byte row
-            *reinterpret_cast<uint4*>(wbuf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = pk;
-          }
-          const bool last_half = half == 1 || c == nchunks - 1 || n0 + 32 >= N;
-          if (last_half) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&J.tmOutB, wbuf, n0 - half * 32, m_base);
-              bulk_commit();
-            }
-          }
-        }
-        // ---- fp32 row-major output
-        if (out_f32) {
-          if (f32_tma) {
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
+                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(dst + i * 8) = pk;
+              } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 pk = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-              *reinterpret_cast<float4*>(wbuf + lane * 128 + ((i ^ (lane & 7)) << 4)) = pk;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&J.tmOutF, wbuf, n0, m_base);
-              bulk_commit();
-            }
-          } else {
-            // row stride not 16-byte aligned (e.g. (B, 513) outputs): transpose through the staging tile
-            // (XOR-swizzled 32 x 32 floats, conflict-free both ways) so that lanes write consecutive columns
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 32; ++q) wbuf_f[lane * 32 + (q ^ lane)] = v[q];
-            __syncwarp();
-            const int n = n0 + lane;
-            if (n < N) {
-#pragma unroll 4
-              for (int r = 0; r < 32; ++r) {
-                const int mm = m_base + r;
-                if (mm >= M) break;
-                out_f32[(long long)mm * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
+                for (int e = 0; e < 8; ++e)
+                  if (n0 + i * 8 + e < N) dst[i * 8 + e] = __float2bfloat16_rn(v[i * 8 + e]);
               }
             }
-            __syncwarp();
           }
+        } else if (out_mode == 2) {
+          if (row_ok) {
+            float* dst = J.out_f32 + (long long)m * J.ld_f32 + n0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (full_chunk || n0 + i * 4 + 4 <= N) {
+                *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n0 + i * 4 + e < N) dst[i * 4 + e] = v[i * 4 + e];
+              }
+            }
+          }
+        } else if (out_mode == 3) {
+          // row stride not 16-byte aligned (e.g. (B, 513) outputs): transpose through the staging tile
+          // (XOR-swizzled 32 x 32 floats, conflict-free both ways) so that lanes write consecutive columns
+          float* out_f32 = J.out_f32;
+          const long long ld_f32 = J.ld_f32;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) wbuf_f[lane * 32 + (q ^ lane)] = v[q];
+          __syncwarp();
+          const int n = n0 + lane;
+          if (n < N) {
+            const int rows = M - m_base < 32 ? M - m_base : 32;
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) out_f32[(long long)(m_base + r) * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
+          }
+          __syncwarp();
         }
         // ---- bias gradient: column sums of the fp32 values (destroys v)
-        if (colsum) {
+        if (colsum != nullptr) {
           if (!row_ok) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] = 0.f;
@@ -373,11 +438,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           const float s = column_sums_32(v, lane);
           if (n0 + lane < N) atomicAdd(colsum + n0 + lane, s);
         }
+        b_cur = b_next;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g_cur[q] = g_next[q];
       }
-      if (lane == 0) bulk_wait_all0();               // this warp's TMA stores have been performed
-      __threadfence();                               // ... and every store of the tile is visible device-wide
+      __threadfence();                               // every store of the warp is visible device-wide ...
       __syncwarp();
-      if (lane == 0) atomicAdd(P.counters + J.cnt_off + mt, 1u);   // row block progress (8 arrivals per tile)
+      if (lane == 0) red_release_add(P.counters + J.cnt_off + mt, 1u);   // ... before the row block's progress is (16 arrivals per tile)
     }
   }
 
@@ -425,18 +492,24 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     d.cnt_off = cnt; cnt_off[i] = cnt; nrb[i] = d.num_m; num_n[i] = d.num_n; cnt += d.num_m;
     d.wait_job = s.wait_job; d.wait_all = s.wait_all;
     if (s.wait_job >= 0) {
-      d.wait_target = num_n[s.wait_job] * 8;            // 4 epilogue warps x 2 CTAs report every tile
+      d.wait_target = num_n[s.wait_job] * MEGA_EPI_WARPS * 2;   // every epilogue warp of both CTAs reports every tile
       d.wait_nrb = nrb[s.wait_job];
       d.wait_cnt_off = cnt_off[s.wait_job];
       if (!s.wait_all) NERAF_REQUIRE(nrb[s.wait_job] == d.num_m, "mega_run: job %d row blocks differ from its producer", i);
     } else { d.wait_target = 0; d.wait_nrb = 0; d.wait_cnt_off = 0; }
     d.act = s.epi.act; d.bias = s.epi.bias;
     d.gate = (const __nv_bfloat16*)s.epi.gate; d.ldg = s.epi.ldg;
-    d.has_out_bf16 = s.epi.out_bf16 != nullptr;
-    if (s.epi.out_bf16) NERAF_TRY(get_tensor_map_2d(s.epi.out_bf16, 2, s.M, s.N, s.epi.ld_bf16, 32, 64, &d.tmOutB));
     d.out_f32 = s.epi.out_f32; d.ld_f32 = s.epi.ld_f32;
-    d.f32_tma = s.epi.out_f32 && (s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0);
-    if (d.f32_tma) NERAF_TRY(get_tensor_map_2d(s.epi.out_f32, 4, s.M, s.N, s.epi.ld_f32, 32, 32, &d.tmOutF));
+    d.out_bf16 = (__nv_bfloat16*)s.epi.out_bf16; d.ld_bf16 = s.epi.ld_bf16;
+    d.out_mode = 0;
+    if (s.epi.out_bf16) {
+      NERAF_REQUIRE(s.epi.ld_bf16 % 8 == 0 && ((uintptr_t)s.epi.out_bf16 % 16) == 0 && s.epi.ld_bf16 >= s.N,
+                    "mega_run: job %d: out_bf16 needs ld %% 8 == 0, ld >= N and 16-byte alignment", i);
+      d.out_mode = 1;
+    } else if (s.epi.out_f32) {
+      NERAF_REQUIRE(s.epi.ld_f32 >= s.N, "mega_run: job %d: out_f32 row stride < N", i);
+      d.out_mode = ((s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0)) ? 2 : 3;
+    }
     d.colsum = s.colsum;
   }
   P.num_tiles = tile;

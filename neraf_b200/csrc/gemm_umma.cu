@@ -302,7 +302,7 @@ struct MapKeyHash {
 };
 
 // Row-major (rows, cols) matrix of bf16 (elem_bytes 2) or fp32 (4) with row stride ld elements; box = box_rows x
-// box_cols with box_cols * elem_bytes == 128 (one 128-byte swizzle row).  Loads: out-of-bounds elements read as
+// box_cols with box_cols * elem_bytes == 128 (one 128-byte swizzle row) or == 64 (64-byte swizzle).  Loads: out-of-bounds elements read as
 // zero (this is what pads K, M and N tails); stores: out-of-bounds elements are dropped.
 static int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                              int box_cols, CUtensorMap* out) {
@@ -316,7 +316,8 @@ static int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int6
   }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(NERAF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  NERAF_REQUIRE(box_cols * elem_bytes == 128 && box_rows >= 1 && box_rows <= 256, "tensor map: bad box %d x %d", box_rows, box_cols);
+  const int inner_bytes = box_cols * elem_bytes;
+  NERAF_REQUIRE((inner_bytes == 128 || inner_bytes == 64) && box_rows >= 1 && box_rows <= 256, "tensor map: bad box %d x %d", box_rows, box_cols);
   NERAF_REQUIRE((ld * elem_bytes) % 16 == 0 && ((uintptr_t)ptr % 16) == 0, "tensor map: base / row stride must be 16-byte aligned");
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
@@ -325,7 +326,8 @@ static int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int6
   CUtensorMap tm;
   const CUresult r = fn(&tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(NERAF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld x %lld ld %lld box %d x %d", (int)r,
                      (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);

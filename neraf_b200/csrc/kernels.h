@@ -1,5 +1,6 @@
 // Internal (non-ABI) launch helpers shared between translation units.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -10,6 +11,13 @@ namespace neraf {
 // encode.cu
 int encode_queries(const neraf_queries* q, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
                    void* out_bf16_t, int64_t ld_t, int ncols_padded, cudaStream_t stream);
+
+// What precedes layer 1 of a forward pass in one launch: query encodings (q may be null: skipped), the effective
+// layer-1 bias c1 = b1 + W1[:, :G] g (skipped when G == 0 or c1 is null) and the bf16 copy of W1[:, G:G+E]
+// (skipped when w1_out is null).
+int field_prep(const neraf_queries* q, float* enc_f32, int64_t ld_f32, void* enc_bf16, int64_t ld_bf16, int ncols_padded,
+               const float* W1, int64_t ldw, const float* b1, const float* g, int64_t n1, int64_t G, float* c1,
+               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream);
 
 // gemm_simt.cu
 int gemm_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
@@ -29,6 +37,22 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
 // elementwise.cu
 int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out, void* out_t,
                  int64_t ld_t, cudaStream_t stream);
+// bf16 operand copies of up to 8 fp32 matrices + one gathered fp32 vector, one launch (elementwise.cu)
+struct PackMatrix {
+  const float* in; int64_t rows, cols, ld_in;
+  __nv_bfloat16* out; int64_t ld_out;
+  int64_t unit_start; int vec;                 // filled by pack_list
+};
+struct PackList {
+  int n;
+  PackMatrix m[8];
+  int64_t total_units;
+  const float* copy_src[8]; float* copy_dst; int64_t copy_width, n_copy;   // copy_dst[j] = copy_src[j / width][j % width]
+};
+int pack_list(PackList& L, cudaStream_t stream);
+// dW[n*ldw + k] = s[n] * g[k] (dW may be null) and dg[k] = sum_n W[n*ldw + k] * s[n] (dg may be null) in one launch
+int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
+               bool dg_is_zero, cudaStream_t stream);
 // y[n] = bias[n] + sum_k W[n*ldw + k] * g[k]   (the batch-invariant part of layer 1)
 int grid_bias(const float* W, int64_t ldw, const float* bias, const float* g, int64_t N, int64_t K, float* y,
               cudaStream_t stream);
@@ -40,10 +64,9 @@ int outer_product(const float* s, const float* g, int64_t N, int64_t K, float* d
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
 // out[n] = sum_m Xt[n*ld + m]  bf16 transposed (N,M)
 int rowsum_bf16(const void* Xt, int64_t N, int64_t M, int64_t ld, float* out, cudaStream_t stream);
-// dz = dout * (10 - y^2/10): gradient through 10*tanh; outputs fp32 (M,N) and/or bf16 (M,N) + bf16^T (N,M)
+// dz = dout * (10 - y^2/10): gradient through 10*tanh; outputs fp32 (M,N) and/or bf16 (M,N) row-major.
 // colsum (optional): per-head bias-gradient buffers, column n is added (atomics) to colsum[n / head_width][n % head_width]
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
-                  int64_t ld_bf16, void* dz_bf16_t, int64_t ld_t, float* const* colsum, int64_t head_width,
-                  cudaStream_t stream);
+                  int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream);
 
 }  // namespace neraf

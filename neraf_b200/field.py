@@ -89,11 +89,16 @@ class _FieldFn(torch.autograd.Function):
         weights = list(params[:n_layers])
         dev = out.device
         dout_c = dout.contiguous().float()
-        dws = [torch.empty_like(w) for w in weights]
-        dbs = [torch.empty_like(b) for b in params[n_layers:]]
-        dgrid = None
-        if ctx.grid_c is not None and ctx.needs_input_grad[3]:
-            dgrid = torch.empty_like(ctx.grid_c)
+        # one flat gradient buffer: weights first (their sizes keep every view 16-byte aligned), then the bias
+        # gradients and dgrid back to back so that the library zeroes them with a single memset
+        biases = params[n_layers:]
+        want_dgrid = ctx.grid_c is not None and ctx.needs_input_grad[3]
+        sizes = [w.numel() for w in weights] + [b.numel() for b in biases] + ([ctx.grid_c.numel()] if want_dgrid else [])
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        views = torch.split(flat, sizes)
+        dws = [v.view_as(w) for v, w in zip(views[:n_layers], weights)]
+        dbs = [v.view_as(b) for v, b in zip(views[n_layers:2 * n_layers], biases)]
+        dgrid = views[2 * n_layers] if want_dgrid else None
         denc = None
         if ctx.enc_given and ctx.needs_input_grad[2]:
             denc = torch.empty(ctx.B, ctx.n_enc, dtype=torch.float32, device=dev)

@@ -33,17 +33,20 @@ class _SpectralLossFn(torch.autograd.Function):
         n = p.numel()
         if n == 0:
             raise ValueError("spectral loss of an empty batch is undefined")
-        sums = torch.empty(4, dtype=torch.float64, device=dev)
-        stream = _lib.stream_ptr(dev)
-        _lib.check(lib.neraf_spectral_loss_sums(p.data_ptr(), g.data_ptr(), n, sums.data_ptr(), 0, stream))
-        n_total = n
-        if group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-            n_total = n * dist.get_world_size(group)      # equal shards (the DP sampler guarantees it)
+        sums = torch.empty(5, dtype=torch.float64, device=dev)     # 4 sums + the fused kernel's completion ticket
         losses = torch.empty(2, dtype=torch.float32, device=dev)
-        _lib.check(lib.neraf_spectral_loss_finalize(sums.data_ptr(), n_total, criterion, w_sc, w_mag,
-                                                    losses.data_ptr(), stream))
+        stream = _lib.stream_ptr(dev)
+        n_total = n
+        if group is None:                                          # one launch: reduction + finalize
+            _lib.check(lib.neraf_spectral_loss_forward(p.data_ptr(), g.data_ptr(), n, criterion, w_sc, w_mag,
+                                                       sums.data_ptr(), losses.data_ptr(), stream))
+        else:
+            import torch.distributed as dist
+            _lib.check(lib.neraf_spectral_loss_sums(p.data_ptr(), g.data_ptr(), n, sums.data_ptr(), 0, stream))
+            dist.all_reduce(sums[:4], op=dist.ReduceOp.SUM, group=group)
+            n_total = n * dist.get_world_size(group)      # equal shards (the DP sampler guarantees it)
+            _lib.check(lib.neraf_spectral_loss_finalize(sums.data_ptr(), n_total, criterion, w_sc, w_mag,
+                                                        losses.data_ptr(), stream))
         ctx.save_for_backward(p, g, sums)
         ctx.meta = (criterion, w_sc, w_mag, n_total)
         return losses[0], losses[1]
@@ -54,10 +57,11 @@ class _SpectralLossFn(torch.autograd.Function):
         p, g, sums = ctx.saved_tensors
         criterion, w_sc, w_mag, n_total = ctx.meta
         dev = p.device
-        upstream = torch.stack([g_sc.reshape(()), g_mag.reshape(())]).float().contiguous()
+        g_sc = g_sc if g_sc.dtype == torch.float32 else g_sc.float()      # 0-d upstream gradients, read on the device
+        g_mag = g_mag if g_mag.dtype == torch.float32 else g_mag.float()
         dpred = torch.empty_like(p)
         _lib.check(lib.neraf_spectral_loss_backward(p.data_ptr(), g.data_ptr(), p.numel(), n_total, criterion,
-                                                    sums.data_ptr(), upstream.data_ptr(), w_sc, w_mag,
+                                                    sums.data_ptr(), g_sc.data_ptr(), g_mag.data_ptr(), w_sc, w_mag,
                                                     dpred.data_ptr(), _lib.stream_ptr(dev)))
         return dpred, None, None, None, None, None
 

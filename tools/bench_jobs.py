@@ -108,13 +108,34 @@ def main():
             j.epi.out_f32, j.epi.ld_f32 = dw[i].data_ptr(), dw[i].stride(0)
         return j
 
+    if os.environ.get("NCU_SEQ"):
+        # fixed launch sequence for `ncu --metrics gpu__time_duration.sum,...`: each entry launched 3 times
+        t_a, t_b = bf(256, 64), bf(256, 64)
+        t_o = torch.empty(256, 256, dtype=torch.bfloat16, device=dev)
+        def tiny(n, k):
+            a, b = bf(256, k), bf(n, k)
+            j = job(256, n, k, a, b, 64 if n < 128 else (128 if n < 256 else 256))
+            j.epi.out_bf16, j.epi.ld_bf16 = t_o.data_ptr(), 256
+            return j, (a, b)
+        seq = [("tiny256x64x64", [tiny(64, 64)[0]]), ("tiny256x256x64", [tiny(256, 64)[0]]), ("tiny256x256x4096", [tiny(256, 4096)[0]]),
+               ("fwd6", [fwd_job(5)]), ("fwd1", [fwd_job(0)]), ("fwd2", [fwd_job(1)]), ("fwd3", [fwd_job(2)]), ("fwd4", [fwd_job(3)]),
+               ("fwd5", [fwd_job(4)]), ("dgrad1", [dgrad_job(1)]), ("wgrad3", [wgrad_job(3, wait=-1, wait_all=0)]),
+               ("wgrad2", [wgrad_job(2, wait=-1, wait_all=0)]),
+               ("fwd_all", [fwd_job(i, None, i - 1) for i in range(6)])]
+        keep = []
+        for name, jobs in seq:
+            for _ in range(3):
+                run(jobs)
+            torch.cuda.synchronize()
+            print(name)
+        return
     print(f"BATCH {B}: single-job launches (us; warm L2 / flushed L2), GFLOP, TFLOP/s warm")
     def report(name, mk, M, N, K, bns):
         gf = 2.0 * M * N * K / 1e9
         cells = []
         for bn in bns:
             tw, tc = timeit([mk(bn)], False), timeit([mk(bn)], True)
-            cells.append(f"bn{bn}: {tw:7.1f}/{tc:7.1f} ({gf / tw * 1e-3:5.0f} TF)")
+            cells.append(f"bn{bn}: {tw:7.1f}/{tc:7.1f} ({gf / tw * 1e3:5.0f} TF)")
         print(f"{name:8s} M{M:5d} N{N:5d} K{K:5d} {gf:6.1f} GF  " + "  ".join(cells))
 
     for i in range(6):
