@@ -53,7 +53,7 @@ def test_size_queries_and_validation_without_gpu(built):
     assert lib.neraf_field_sizes(C.byref(dims), _lib.PREC_BF16, 2048, C.byref(pack), C.byref(ws)) == 0
     n_w = 163 * 5096 + 5096 * 2048 + 2048 * 1024 + 1024 * 1024 + 1024 * 512 + 512 * 513
     assert 2 * n_w <= pack.value < 2 * n_w * 1.05                  # one bf16 copy per weight matrix (+ padding)
-    assert ws.value > 2048 * 9704 * 2 * 4
+    assert ws.value > 2048 * 9704 * 2 * 2                          # bf16 activations + their gradients, no transposes
     assert lib.neraf_field_sizes(C.byref(dims), _lib.PREC_FP32, 2048, C.byref(pack), C.byref(ws)) == 0
     assert pack.value == 0
     assert lib.neraf_field_sizes(C.byref(dims), 7, 2048, C.byref(pack), C.byref(ws)) == 1
