@@ -210,6 +210,13 @@ typedef struct {
   float* out_f32;
   int64_t ld_f32;
   int32_t accumulate_f32;
+  /* job-list kernel only (neraf_gemm_bf16_jobs); must be NULL for neraf_gemm_bf16:
+   * mask_out  : with act == NERAF_ACT_LEAKY, also store the sign pattern of the pre-activation: bit (n % 32) of the
+   *             uint32 word mask_out[(n / 32) * ld_mask + m] is set when element (m, n) is > 0;
+   * gate_mask : LeakyReLU' gate read from such a mask instead of `gate` (same indexing). */
+  void* mask_out;
+  const void* gate_mask;
+  int64_t ld_mask;
 } neraf_gemm_epilogue;
 
 NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -225,7 +232,11 @@ NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
  *                 block r (256 rows) starts when row block r of wait_job is complete (both jobs have the same M);
  *                 wait_all == 1: when every row block of wait_job is complete.
  *   colsum      : optional dev fp32 (N), must be zeroed by the caller: += column sums of the fp32 results.
- *   outputs     : only the M x N results are written (pad columns of a wider row stride are left untouched).
+ *   bias        : must not be produced by a job of the same launch (it is prefetched before dependencies resolve);
+ *                 A, B, gate and gate_mask may be.
+ *   out_bf16    : ld_bf16 is a multiple of 8, so a row has round_up(N, 8) - N pad columns: they may be overwritten
+ *                 with zeros (TMA stores clip with 16-byte granularity); nothing beyond them is touched.
+ *   out_f32     : only the M x N results are written.
  * counters: dev scratch, >= 4 * sum_j ceil(M_j / 256) bytes. */
 #define NERAF_MAX_GEMM_JOBS 24
 typedef struct {

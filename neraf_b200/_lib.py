@@ -43,7 +43,8 @@ class Queries(C.Structure):
 class GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("gate", C.c_void_p), ("ldg", C.c_int64),
                 ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64), ("out_bf16_t", C.c_void_p), ("ld_t", C.c_int64),
-                ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("accumulate_f32", C.c_int32)]
+                ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("accumulate_f32", C.c_int32),
+                ("mask_out", C.c_void_p), ("gate_mask", C.c_void_p), ("ld_mask", C.c_int64)]
 
 
 class GemmJob(C.Structure):

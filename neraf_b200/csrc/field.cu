@@ -43,6 +43,8 @@ struct Layout {
   int64_t ld_enc;
   size_t x[NERAF_MAX_TRUNK], dz[NERAF_MAX_TRUNK];
   int64_t ldx[NERAF_MAX_TRUNK];
+  size_t mask[NERAF_MAX_TRUNK];      // sign bit masks of the pre-activations: (ceil(n/32), ld_mask) uint32, bf16 path
+  int64_t ld_mask;
   size_t dzh;
   int64_t ld_h;
   size_t counters, counters_bytes;   // dependency counters of the job-list kernel
@@ -91,10 +93,12 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   l.c1 = take(cur, (size_t)l.n[0] * 4);
   l.ld_enc = bf ? round_up(l.E, 8) : l.E;
   l.enc = take(cur, B * l.ld_enc * es);
+  l.ld_mask = round_up(batch > 0 ? batch : 1, 64);
   for (int i = 0; i < l.L; ++i) {
     l.ldx[i] = bf ? round_up(l.n[i], 8) : l.n[i];
     l.x[i] = take(cur, B * l.ldx[i] * es);
     l.dz[i] = take(cur, B * l.ldx[i] * es);
+    l.mask[i] = bf ? take(cur, (size_t)ceil_div(l.n[i], 32) * l.ld_mask * 4) : 0;
   }
   l.ld_h = bf ? round_up(l.CF, 8) : l.CF;
   l.dzh = take(cur, B * l.ld_h * es);
@@ -323,6 +327,7 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
       j.epi.bias = i == 0 ? c1 : biases[i];
       j.epi.act = NERAF_ACT_LEAKY;
       j.epi.out_bf16 = at(ws, l.x[i]); j.epi.ld_bf16 = l.ldx[i];
+      j.epi.mask_out = at(ws, l.mask[i]); j.epi.ld_mask = l.ld_mask;       // LeakyReLU' gate of the backward pass
       xin = j.epi.out_bf16; ldin = l.ldx[i];
     }
   }
@@ -427,7 +432,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
   {                                                    // dZ_last = (dZ_head W_head) * leaky'(x_last)
     MegaJob& j = jobs[nj++];
     j = make_dgrad_job(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wh), l.ldwh, -1);
-    j.epi.gate = at(ws, l.x[last]); j.epi.ldg = l.ldx[last];
+    j.epi.gate_mask = at(ws, l.mask[last]); j.epi.ld_mask = l.ld_mask;
     j.epi.out_bf16 = at(ws, l.dz[last]); j.epi.ld_bf16 = l.ldx[last];
     j.colsum = dbiases[last];
   }
@@ -444,7 +449,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
       producer = nj;
       MegaJob& j = jobs[nj++];
       j = make_dgrad_job(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.w[i]), l.ldw[i], dz_producer);
-      j.epi.gate = at(ws, l.x[i - 1]); j.epi.ldg = l.ldx[i - 1];
+      j.epi.gate_mask = at(ws, l.mask[i - 1]); j.epi.ld_mask = l.ld_mask;
       j.epi.out_bf16 = at(ws, l.dz[i - 1]); j.epi.ld_bf16 = l.ldx[i - 1];
       j.colsum = dbiases[i - 1];
     }

@@ -28,14 +28,18 @@
 //
 // Epilogue.  Per 32 x 32 chunk: tcgen05.ld (lane = row) with the NEXT chunk's bias / gate loads issued behind it
 // -> bias (one coalesced load per chunk, shuffle broadcast) / LeakyReLU / 10 tanh / LeakyReLU' gate, activation
-// switch hoisted out of the element loop -> the lane's 32 consecutive columns (64 B of bf16 / 128 B of fp32, whole
-// sectors) go straight from registers to global memory as 16-byte stores: no staging and no store-completion wait
-// on the critical path of the layer chain (a TMA-store epilogue measured ~1300 cycles per chunk, profiles/r01b).  Bias gradients are column sums taken from the fp32 values with a
+// switch hoisted out of the element loop -> 2 KB staging halves (64-byte swizzle) -> TMA stores.  The per-tile
+// timeline (tools/mega_trace.py) shows what bounds it: TMEM -> registers runs at ~64 B/clk per SM (560 cycles per
+// round of 8 warp-chunks), so everything else per round must stay below that: bias comes in as 8 uniform 16-byte
+// loads (32 shuffles cost 600 cycles per round), the LeakyReLU' gate as ONE coalesced word of a transposed sign
+// bit mask written by the forward epilogue (reading the bf16 activations row-wise costs 1000+ LSU cycles per
+// round, as do row-wise register stores of the outputs: 32 distinct lines per instruction).  Bias gradients are column sums taken from the fp32 values with a
 // recursive-halving shuffle reduction (31 shuffles per 32 x 32 block) and one atomic per column.
-// Cross-SM visibility: stores -> __threadfence -> red.release(counter); consumer: ld.acquire spin ->
-// fence.proxy.async -> TMA loads.
+// Cross-SM visibility: TMA stores complete (bulk wait_group) -> __threadfence -> red.release(counter); consumer:
+// ld.acquire spin -> fence.proxy.async -> TMA loads.
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -57,22 +61,28 @@ constexpr int MN_BOX_BYTES = 64 * 128;                         // one MN-major b
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct alignas(64) DeviceJob {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut;
   int M, N, K, bn;
   int tile_start, num_m, num_n, cnt_off;
   int wait_job, wait_all, wait_target, wait_nrb, wait_cnt_off;
   int act, a_mn, b_mn;
-  int out_mode;                    // 0 none, 1 bf16, 2 fp32 (16-byte aligned rows), 3 fp32 (unaligned rows, via smem transpose)
-  __nv_bfloat16* out_bf16; long long ld_bf16;
+  int out_mode;                    // 0 none, 1 bf16 (TMA), 2 fp32 (TMA), 3 fp32 (rows not 16-byte tileable: smem transpose)
+  int bias_vec;                    // bias may be read with 16-byte loads
+  unsigned int* mask_out; const unsigned int* gate_mask; long long ld_mask;
   const float* bias;
   const __nv_bfloat16* gate; long long ldg;
   float* out_f32; long long ld_f32;
   float* colsum;
 };
 
+// Optional per-tile timeline (NERAF_MEGA_TRACE=<file>): 8 globaltimer stamps per tile, see tools/mega_trace.py.
+enum { TR_DEP = 0, TR_LOADED, TR_MMA_START, TR_MMA_FIRST, TR_MMA_DONE, TR_EPI_START, TR_EPI_STORED, TR_EPI_DONE,
+       TR_CK_START, TR_CK_LD, TR_CK_MATH, TR_CK_STORE, TR_CK_LOOP, TR_CK_FENCE, TR_PAD0, TR_PAD1, TR_SLOTS };   // TR_CK_*: clock64 of the tracer warp
+
 struct MegaParams {
   int num_jobs, num_tiles;
   unsigned int* counters;
+  unsigned long long* trace;       // null unless tracing
   DeviceJob jobs[NERAF_MEGA_MAX_JOBS];
 };
 
@@ -83,6 +93,16 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
 }
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stamp(unsigned long long* trace, int tile, int slot) {
+  if (trace == nullptr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  trace[(size_t)tile * TR_SLOTS + slot] = t;
+}
+__device__ __forceinline__ void stamp_clock(unsigned long long* trace, int tile, int slot) {
+  if (trace == nullptr) return;
+  trace[(size_t)tile * TR_SLOTS + slot] = (unsigned long long)clock64();
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -96,6 +116,16 @@ __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int t
     if ((++spins & 255u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) __trap();
   }
 }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // MN-major, 128-byte-swizzled operand: 64 contiguous MN elements per k row (128 B), 8-row groups 1024 B apart
 // (SBO), the next block of 64 MN elements one TMA box (8 KB) further (LBO).
@@ -224,6 +254,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
             spin_until(P.counters + J.wait_cnt_off + mt, (unsigned)J.wait_target);
           }
           fence_proxy_async_all();
+          if (is_leader) stamp(P.trace, tile, TR_DEP);
           for (int kb = 0; kb < pre; ++kb) {
             load_a(stage, kb);
             if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
@@ -237,6 +268,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           load_b(stage, kb);
           if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (is_leader) stamp(P.trace, tile, TR_LOADED);
       }
     }
     __syncwarp();
@@ -259,9 +291,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
         mbar_wait(tmem_empty + as, aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * MEGA_ACC_COLS);
+        stamp(P.trace, tile, TR_MMA_START);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
+          if (kb == 0) stamp(P.trace, tile, TR_MMA_FIRST);
           const uint32_t sa = smem_u32(smem_a + stage * MEGA_A_BYTES);
           const uint32_t sb = smem_u32(smem_b + stage * MEGA_B_BYTES);
           const uint64_t adesc = a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
@@ -273,6 +307,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit<CG>(tmem_full + as);
+        stamp(P.trace, tile, TR_MMA_DONE);
       }
     }
     __syncwarp();
@@ -305,25 +340,34 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       const int n_first = nt * J.bn + c_first * 32;
       int nvalid = (N - n_first + 31) / 32;                       // my chunks that start inside N
       nvalid = nvalid < 0 ? 0 : (nvalid > per ? per : nvalid);
+      const unsigned int* gate_mask = J.gate_mask;
+      unsigned int* mask_out = J.mask_out;
+      const long long ld_mask = J.ld_mask;
       const bool gate_vec_ok = gate != nullptr && (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(gate) & 15) == 0);
 
-      // operands of the first chunk that do not depend on the accumulator: fetched before it is ready
-      float b_cur = 0.f, b_next = 0.f;
-      uint4 g_cur[4], g_next[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { g_cur[q] = make_uint4(0, 0, 0, 0); g_next[q] = g_cur[q]; }
-      auto fetch = [&](int n0, float& b, uint4 (&g)[4]) {
-        if (bias != nullptr && n0 + lane < N) b = __ldg(bias + n0 + lane); else b = 0.f;
-        if (gate_vec_ok && row_ok && n0 + 32 <= N) {
-          const uint4* gp = reinterpret_cast<const uint4*>(gate + (long long)m * ldg + n0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g[q] = __ldg(gp + q);
-        }
+      // Per-chunk side operands, one coalesced load per chunk (at most 4 chunks per warp -> 8 registers):
+      //  * bias (lane q holds column q, broadcast by shuffles later): never produced inside the launch, so it is
+      //    fetched BEFORE waiting for the accumulator;
+      //  * the LeakyReLU' gate word of the lane's row in the transposed bit mask: may have been written by an earlier
+      //    job of this launch, so it is read (L2-coherent) only once the accumulator is complete -- the MMAs consumed
+      //    operands the TMA producer loaded after it had acquired the dependency counter.
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+      unsigned int w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      auto pre_bias = [&](int jj, float& bj) {
+        const int n0 = n_first + 32 * jj;
+        if (jj < nvalid && bias != nullptr && n0 + lane < N) bj = __ldg(bias + n0 + lane);
       };
-      if (nvalid > 0) fetch(n_first, b_cur, g_cur);
+      auto pre_gate = [&](int jj, unsigned int& wj) {
+        const int n0 = n_first + 32 * jj;
+        if (jj < nvalid && gate_mask != nullptr && row_ok) wj = __ldcg(gate_mask + (long long)(n0 >> 5) * ld_mask + m);
+      };
+      pre_bias(0, b0); pre_bias(1, b1); pre_bias(2, b2); pre_bias(3, b3);
 
       mbar_wait(tmem_full + as, aphase);
       tc_fence_after();
+      pre_gate(0, w0); pre_gate(1, w1); pre_gate(2, w2); pre_gate(3, w3);
+      const bool tracer = is_leader && warp == 2 && lane == 0;
+      if (tracer) { stamp(P.trace, tile, TR_EPI_START); stamp_clock(P.trace, tile, TR_CK_START); }
       if (nvalid == 0) {
         tc_fence_before();
         __syncwarp();
@@ -332,15 +376,25 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           else mbar_arrive_remote(tmem_empty + as, 0);
         }
       }
+      int sbuf = 0;                                               // staging half (2 KB) the next TMA store uses
+      const uint32_t t_addr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MEGA_ACC_COLS + c_first * 32);
 #pragma unroll 1
       for (int k = 0; k < nvalid; ++k) {
         const int c = c_first + k;
         const int n0 = nt * J.bn + c * 32;
         const bool full_chunk = n0 + 32 <= N;
         float v[32];
-        tmem_ld_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MEGA_ACC_COLS + c * 32), v);
-        if (k + 1 < nvalid) fetch(n0 + 32, b_next, g_next);      // next chunk's bias / gate behind the TMEM load
+        tmem_ld_issue(t_addr0 + (uint32_t)(k * 32), v);
+        const float bk = k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3));
+        const unsigned int gm = k == 0 ? w0 : (k == 1 ? w1 : (k == 2 ? w2 : w3));
+        uint4 g_cur[4];
+        if (gate != nullptr && gate_vec_ok && row_ok && full_chunk) {      // generic bf16 gate (not used by the field)
+          const uint4* gp = reinterpret_cast<const uint4*>(gate + (long long)m * ldg + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g_cur[q] = __ldcg(gp + q);
+        }
         tmem_ld_wait();
+        if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_LD);
         if (k == nvalid - 1) {                                    // accumulator fully read: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
@@ -351,16 +405,30 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
         }
         if (bias != nullptr) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] += __shfl_sync(FULL_MASK, b_cur, q);
+          for (int q = 0; q < 32; ++q) v[q] += __shfl_sync(FULL_MASK, bk, q);
         }
         if (act == NERAF_ACT_LEAKY) {
+          if (mask_out != nullptr) {                              // remember the sign pattern for the backward gate
+            unsigned int bits = 0;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = v[q] > 0.f ? v[q] : kLeakySlope * v[q];
+            for (int q = 0; q < 32; ++q) {
+              const bool pos = v[q] > 0.f;
+              bits |= pos ? (1u << q) : 0u;
+              v[q] = pos ? v[q] : kLeakySlope * v[q];
+            }
+            if (row_ok) mask_out[(long long)(n0 >> 5) * ld_mask + m] = bits;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = v[q] > 0.f ? v[q] : kLeakySlope * v[q];
+          }
         } else if (act == NERAF_ACT_TANH10) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = 10.f * tanhf(v[q]);
         }
-        if (gate != nullptr && row_ok) {
+        if (gate_mask != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = (gm >> q) & 1u ? v[q] : kLeakySlope * v[q];
+        } else if (gate != nullptr && row_ok) {
           if (gate_vec_ok && full_chunk) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -376,45 +444,54 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
             const __nv_bfloat16* g = gate + (long long)m * ldg + n0;
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              if (n0 + q < N) v[q] *= gate_factor(__bfloat162float(g[q]));
+              if (n0 + q < N) v[q] *= gate_factor(__bfloat162float(__ldcg(g + q)));
           }
         }
+        if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_MATH);
         if (out_mode == 1) {
-          // bf16 row-major, straight from registers: the lane owns 32 consecutive columns of its row = 64 contiguous
-          // bytes (two full sectors), written as 4 x 16 B.  No staging, no store-completion wait on the critical path.
-          if (row_ok) {
-            __nv_bfloat16* dst = J.out_bf16 + (long long)m * J.ld_bf16 + n0;
+          // bf16 row-major: 32 x 32 tile = 32 rows of 64 bytes (64-byte swizzle), two 2 KB staging halves alternate
+          uint8_t* sb = wbuf + sbuf * 2048;
+          if (lane == 0) bulk_wait_read1();                       // the store issued two tiles ago has left this half
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(sb + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&J.tmOut, sb, n0, m_base);
+            bulk_commit();
+          }
+          sbuf ^= 1;
+        } else if (out_mode == 2) {
+          // fp32 row-major: two 32 x 16 halves (64-byte rows, 64-byte swizzle), one TMA store each
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            if (n0 + hf * 16 >= N) break;
+            uint8_t* sb = wbuf + sbuf * 2048;
+            if (lane == 0) bulk_wait_read1();
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if (full_chunk || n0 + i * 8 + 8 <= N) {
-                uint4 pk;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(dst + i * 8) = pk;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (n0 + i * 8 + e < N) dst[i * 8 + e] = __float2bfloat16_rn(v[i * 8 + e]);
-              }
+              const int q0 = hf * 16 + i * 4;
+              *reinterpret_cast<float4*>(sb + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
+                  make_float4(v[q0], v[q0 + 1], v[q0 + 2], v[q0 + 3]);
             }
-          }
-        } else if (out_mode == 2) {
-          if (row_ok) {
-            float* dst = J.out_f32 + (long long)m * J.ld_f32 + n0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (full_chunk || n0 + i * 4 + 4 <= N) {
-                *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (n0 + i * 4 + e < N) dst[i * 4 + e] = v[i * 4 + e];
-              }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&J.tmOut, sb, n0 + hf * 16, m_base);
+              bulk_commit();
             }
+            sbuf ^= 1;
           }
         } else if (out_mode == 3) {
-          // row stride not 16-byte aligned (e.g. (B, 513) outputs): transpose through the staging tile
+          // rows that TMA cannot tile (e.g. (B, 513) fp32 outputs): transpose through the staging tile
           // (XOR-swizzled 32 x 32 floats, conflict-free both ways) so that lanes write consecutive columns
           float* out_f32 = J.out_f32;
           const long long ld_f32 = J.ld_f32;
@@ -429,6 +506,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           }
           __syncwarp();
         }
+        if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_STORE);
         // ---- bias gradient: column sums of the fp32 values (destroys v)
         if (colsum != nullptr) {
           if (!row_ok) {
@@ -438,12 +516,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           const float s = column_sums_32(v, lane);
           if (n0 + lane < N) atomicAdd(colsum + n0 + lane, s);
         }
-        b_cur = b_next;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) g_cur[q] = g_next[q];
       }
-      __threadfence();                               // every store of the warp is visible device-wide ...
+      if (tracer) { stamp_clock(P.trace, tile, TR_CK_LOOP); stamp(P.trace, tile, TR_EPI_STORED); }
+      // Publish the tile: lane 0 waits until its TMA stores have been performed, the warp's plain stores (bit mask,
+      // unaligned fp32 rows, column-sum atomics) are ordered before lane 0 by the warp barrier, and the counter
+      // update itself is a gpu-scope release (one fence instead of a full membar in every lane).
+      if (lane == 0 && out_mode != 0 && out_mode != 3) { bulk_wait_all0(); fence_proxy_async_all(); }
       __syncwarp();
+      if (tracer) { stamp_clock(P.trace, tile, TR_CK_FENCE); stamp(P.trace, tile, TR_EPI_DONE); }
       if (lane == 0) red_release_add(P.counters + J.cnt_off + mt, 1u);   // ... before the row block's progress is (16 arrivals per tile)
     }
   }
@@ -500,22 +580,38 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     d.act = s.epi.act; d.bias = s.epi.bias;
     d.gate = (const __nv_bfloat16*)s.epi.gate; d.ldg = s.epi.ldg;
     d.out_f32 = s.epi.out_f32; d.ld_f32 = s.epi.ld_f32;
-    d.out_bf16 = (__nv_bfloat16*)s.epi.out_bf16; d.ld_bf16 = s.epi.ld_bf16;
     d.out_mode = 0;
     if (s.epi.out_bf16) {
       NERAF_REQUIRE(s.epi.ld_bf16 % 8 == 0 && ((uintptr_t)s.epi.out_bf16 % 16) == 0 && s.epi.ld_bf16 >= s.N,
                     "mega_run: job %d: out_bf16 needs ld %% 8 == 0, ld >= N and 16-byte alignment", i);
       d.out_mode = 1;
+      NERAF_TRY(get_tensor_map_2d(s.epi.out_bf16, 2, s.M, s.N, s.epi.ld_bf16, 32, 32, &d.tmOut));
     } else if (s.epi.out_f32) {
       NERAF_REQUIRE(s.epi.ld_f32 >= s.N, "mega_run: job %d: out_f32 row stride < N", i);
-      d.out_mode = ((s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0)) ? 2 : 3;
+      // TMA stores clip with 16-byte granularity: only rows that end on a 16-byte boundary take the TMA path
+      const bool tma_ok = (s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0) && (s.N % 4 == 0);
+      d.out_mode = tma_ok ? 2 : 3;
+      if (tma_ok) NERAF_TRY(get_tensor_map_2d(s.epi.out_f32, 4, s.M, s.N, s.epi.ld_f32, 32, 16, &d.tmOut));
     }
+    d.bias_vec = s.epi.bias && ((uintptr_t)s.epi.bias % 16) == 0;
+    d.mask_out = (unsigned int*)s.epi.mask_out; d.gate_mask = (const unsigned int*)s.epi.gate_mask; d.ld_mask = s.epi.ld_mask;
+    NERAF_REQUIRE(!(s.epi.mask_out || s.epi.gate_mask) || s.epi.ld_mask >= s.M, "mega_run: job %d: ld_mask < M", i);
+    NERAF_REQUIRE(!s.epi.mask_out || s.epi.act == NERAF_ACT_LEAKY, "mega_run: job %d: mask_out needs the LeakyReLU epilogue", i);
+    NERAF_REQUIRE(!(s.epi.gate && s.epi.gate_mask), "mega_run: job %d: gate and gate_mask are exclusive", i);
     d.colsum = s.colsum;
   }
   P.num_tiles = tile;
   NERAF_REQUIRE(counters && counters_bytes >= (size_t)cnt * sizeof(unsigned int), "mega_run: counter buffer too small");
   P.counters = reinterpret_cast<unsigned int*>(counters);
   NERAF_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)cnt * sizeof(unsigned int), stream));
+  // Debug timeline: NERAF_MEGA_TRACE=<file> makes every launch synchronous and appends its per-tile stamps.
+  static const char* trace_path = getenv("NERAF_MEGA_TRACE");
+  P.trace = nullptr;
+  const size_t trace_bytes = (size_t)tile * TR_SLOTS * sizeof(unsigned long long);
+  if (trace_path) {
+    NERAF_CHECK_CUDA(cudaMalloc(&P.trace, trace_bytes));
+    NERAF_CHECK_CUDA(cudaMemsetAsync(P.trace, 0, trace_bytes, stream));
+  }
 
   static bool configured[64] = {false};
   int dev = 0;
@@ -537,6 +633,24 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   cfg.attrs = attr; cfg.numAttrs = 1;
   NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_mega_kernel, P));
   NERAF_CHECK_LAUNCH("umma_mega_kernel");
+  if (trace_path) {
+    std::vector<unsigned long long> host((size_t)tile * TR_SLOTS);
+    NERAF_CHECK_CUDA(cudaStreamSynchronize(stream));
+    NERAF_CHECK_CUDA(cudaMemcpy(host.data(), P.trace, trace_bytes, cudaMemcpyDeviceToHost));
+    NERAF_CHECK_CUDA(cudaFree(P.trace));
+    if (FILE* f = fopen(trace_path, "ab")) {
+      // record: magic, n_jobs, n_tiles, units, then per job {tile_start, M, N, K, bn, a_mn, b_mn, wait_job}, then the stamps
+      const int hdr[4] = {0x4d454741, n_jobs, tile, units};
+      fwrite(hdr, sizeof(int), 4, f);
+      for (int i = 0; i < n_jobs; ++i) {
+        const DeviceJob& d = P.jobs[i];
+        const int rec[8] = {d.tile_start, d.M, d.N, d.K, d.bn, d.a_mn, d.b_mn, d.wait_job};
+        fwrite(rec, sizeof(int), 8, f);
+      }
+      fwrite(host.data(), sizeof(unsigned long long), host.size(), f);
+      fclose(f);
+    }
+  }
   return NERAF_OK;
 }
 

@@ -316,7 +316,11 @@ def test_gemm_jobs_k_major_outputs(bn, M, N, K):
     assert rel_fro(out_f[:, :N], ref) < 2e-5
     assert torch.all(out_f[:, N] == 7.0)
     assert rel_fro(out_b[:, :N], ref) < 4e-3
-    assert torch.all(out_b[:, N:] == 7.0), "stores must stop at N (pad columns untouched)"
+    # bf16 rows go out through TMA stores, which clip with 16-byte granularity: pad columns sharing the last valid
+    # column's 16-byte group may receive zeros, nothing beyond round_up(N, 8) is touched.  fp32 rows are exact.
+    assert torch.all(out_b[:, n8:] == 7.0), "TMA store must clip at round_up(N, 8)"
+    pad = out_b[:, N:n8]
+    assert torch.all((pad == 7.0) | (pad == 0.0))
     assert torch.all(out_f2[:, N:] == 7.0)
     assert rel_fro(colsum, ref.sum(0)) < 1e-4
     assert rel_fro(out_f2[:, :N], A[:, :K].double() @ B[:, :K].double().t()) < 2e-5
@@ -339,6 +343,44 @@ def test_gemm_jobs_mn_major_weight_gradient(bn, n_out, k_in, batch):
         assert rel_fro(out[:, :k_in], ref) < 2e-5, ld
         if ld > k_in:
             assert torch.all(out[:, k_in:] == 7.0)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 1024, 256, 128), (300, 513, 200, 64), (1000, 5096, 168, 256)])
+def test_gemm_jobs_sign_mask_gate(M, N, K, bn):
+    """Forward job stores the transposed sign bit mask; a second job gated by the mask == gated by the activations."""
+    dev = cuda()
+    g = torch.Generator().manual_seed(M + N)
+    ldk = (K + 7) // 8 * 8
+    n8 = (N + 7) // 8 * 8
+    A = _bf16_padded(torch.randn(M, K, generator=g).to(dev), ldk)
+    B = _bf16_padded((torch.randn(N, K, generator=g) / np.sqrt(K)).to(dev), ldk)
+    bias = torch.randn(N, generator=g).to(dev) * 0.1
+    ld_mask = (M + 63) // 64 * 64
+    mask = torch.zeros((N + 31) // 32, ld_mask, dtype=torch.int32, device=dev)
+    x = torch.zeros(M, n8, dtype=torch.bfloat16, device=dev)
+    j0 = _job(M, N, K, A, B, bn)
+    j0.epi.bias, j0.epi.act = bias.data_ptr(), 1
+    j0.epi.out_bf16, j0.epi.ld_bf16 = x.data_ptr(), n8
+    j0.epi.mask_out, j0.epi.ld_mask = mask.data_ptr(), ld_mask
+    out_m = torch.zeros(M, N + 1, device=dev)
+    out_g = torch.zeros(M, N + 1, device=dev)
+    j1 = _job(M, N, K, A, B, bn, wait_job=0)
+    j1.epi.gate_mask, j1.epi.ld_mask = mask.data_ptr(), ld_mask
+    j1.epi.out_f32, j1.epi.ld_f32 = out_m.data_ptr(), N + 1
+    j2 = _job(M, N, K, A, B, bn, wait_job=0)
+    j2.epi.gate, j2.epi.ldg = x.data_ptr(), n8
+    j2.epi.out_f32, j2.epi.ld_f32 = out_g.data_ptr(), N + 1
+    _run_jobs([j0, j1, j2], dev)
+    z = A[:, :K].double() @ B[:, :K].double().t() + bias.double()
+    bits = (mask[:, :M].t().unsqueeze(-1) >> torch.arange(32, device=dev)) & 1        # (M, words, 32)
+    pos = bits.reshape(M, -1)[:, :N].bool()
+    sure = z.abs() > 1e-4                                   # away from zero the fp32 accumulator has the sign of z
+    assert torch.all(pos[sure] == (z[sure] > 0))
+    # the bf16 activation has the sign of its fp32 source, so both gates agree wherever x did not round to zero
+    agree = (out_m[:, :N] == out_g[:, :N]) | (x[:, :N] == 0)
+    assert torch.all(agree)
+    ref = (A[:, :K].double() @ B[:, :K].double().t()) * torch.where(pos, 1.0, 0.1)
+    assert rel_fro(out_m[:, :N], ref) < 2e-5
 
 
 def test_gemm_jobs_dependency_chain_matches_sequential():

@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-NCU_SEQ=1 timeout 600 ncu --cache-control none --metrics gpu__time_duration.sum,sm__cycles_elapsed.max --clock-control none -k regex:mega --csv --log-file gpurun_out/seq_warm.csv python tools/bench_jobs.py > gpurun_out/seq.log 2>&1; echo "rc=$?"
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+NCU_SEQ=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:mega -s 14 -c 1 -f -o gpurun_out/fwd1 python tools/bench_jobs.py > gpurun_out/seq.log 2>&1; echo "rc=$?"

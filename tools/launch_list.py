@@ -1,0 +1,16 @@
+"""Prints one train step of an ncu launch list (gpurun_out/launches.csv): kernels in order with their device time."""
+import csv
+import sys
+
+path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/launches.csv"
+rows = list(csv.DictReader([l for l in open(path) if not l.startswith("==")]))
+idx = [i for i, r in enumerate(rows) if "field_prep" in r["Kernel Name"] or "encode_kernel" in r["Kernel Name"]]
+a, b = idx[-2], idx[-1]
+while a > 0 and "pack_list" in rows[a - 1]["Kernel Name"]:
+    a -= 1; b -= 1
+tot = 0.0
+for r in rows[a:b]:
+    v = float(r["Metric Value"].replace(",", "")) / 1e3
+    tot += v
+    print(f"{v:8.1f} us  grid {r['Grid Size']:>14} blk {r['Block Size']:>12}  {r['Kernel Name'][:90]}")
+print(f"total {tot:.1f} us over {b - a} launches")
