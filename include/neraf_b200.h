@@ -212,7 +212,7 @@ typedef struct {
   int32_t accumulate_f32;
   /* job-list kernel only (neraf_gemm_bf16_jobs); must be NULL for neraf_gemm_bf16:
    * mask_out  : with act == NERAF_ACT_LEAKY, also store the sign pattern of the pre-activation: bit (n % 32) of the
-   *             uint32 word mask_out[(n / 32) * ld_mask + m] is set when element (m, n) is > 0;
+   *             uint32 word mask_out[(n / 32) * ld_mask + m] is set when element (m, n) is >= +0 (sign bit clear);
    * gate_mask : LeakyReLU' gate read from such a mask instead of `gate` (same indexing). */
   void* mask_out;
   const void* gate_mask;

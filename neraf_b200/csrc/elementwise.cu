@@ -303,7 +303,7 @@ struct HeadColsum {
   long long width;        // columns per head; 0 = no column sums
 };
 
-constexpr int kHeadRows = 128;       // rows per block of head_backward_kernel
+constexpr int kHeadRows = 32;        // rows per block of head_backward_kernel (4 per thread, all loads in flight at once)
 
 // Block = 32 columns x 8 row lanes over kHeadRows rows: coalesced 128-byte row segments, the bias gradient
 // (column sums) is accumulated in registers and leaves the block as one atomic per column.
@@ -318,12 +318,21 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
   const int64_t r1 = r0 + kHeadRows < M ? r0 + kHeadRows : M;
   float sum = 0.f;
   if (c < N) {
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const float yy = __ldg(y + r * N + c);
-      const float v = __ldg(dout + r * N + c) * (10.f - yy * yy * 0.1f);
-      if (dz_f32) dz_f32[r * ld_f32 + c] = v;
-      if (dz_bf16) dz_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(v);
+    float yy[kHeadRows / 8], dd[kHeadRows / 8];
+#pragma unroll
+    for (int i = 0; i < kHeadRows / 8; ++i) {
+      const int64_t r = r0 + ty + 8 * i;
+      yy[i] = r < r1 ? __ldg(y + r * N + c) : 0.f;
+      dd[i] = r < r1 ? __ldg(dout + r * N + c) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kHeadRows / 8; ++i) {
+      const int64_t r = r0 + ty + 8 * i;
+      const float v = dd[i] * (10.f - yy[i] * yy[i] * 0.1f);
+      if (r < r1) {
+        if (dz_f32) dz_f32[r * ld_f32 + c] = v;
+        if (dz_bf16) dz_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(v);
+      }
       sum += v;
     }
   }

@@ -16,6 +16,7 @@
 //
 // Launches per bf16 train step: prep (encodings + c1 + layer-1 operand copy) | pack of the other layers on a helper
 // stream | layer 1 | layers 2..heads | ... loss ... | memset + head gradient | whole backward | grid-block gradients.
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -134,19 +135,30 @@ SideStream* side_stream() {
   return &s;
 }
 
-// Tile width of a job: the widest tile that still yields enough tiles to spread over the CTA pairs.
-int choose_bn(int64_t M, int64_t N, int min_bn) {
-  const int64_t rb = ceil_div(M, 256);
-  for (int bn = 256; bn > min_bn; bn /= 2)
-    if (rb * ceil_div(N, bn) >= 48) return bn;
-  return min_bn;
+// Tile width of a job from a small cost model calibrated on the per-tile timeline (tools/mega_trace.py): a CTA pair
+// spends max(MMA, epilogue) per tile -- k-blocks stream from L2 at ~0.36 us for bn <= 128 and ~0.41 us for bn = 256,
+// the epilogue costs ~0.9 us per 32-column chunk of a warp plus ~0.9 us to publish the tile -- and the job takes
+// ceil(tiles / pairs) rounds of that (the epilogue of the last round is exposed).
+int choose_bn(int64_t M, int64_t N, int64_t K, int min_bn) {
+  const double pairs = sm_count() / 2;
+  const double kb = (double)ceil_div(K, 64);
+  int best = min_bn;
+  double best_t = 1e30;
+  for (int bn = min_bn; bn <= 256; bn *= 2) {
+    const double tiles = (double)ceil_div(M, 256) * (double)ceil_div(N, bn);
+    const double mma = kb * (bn == 256 ? 0.41 : 0.36);
+    const double epi = 0.9 * (bn / 64) + 0.9;
+    const double t = (ceil(tiles / pairs) - 1.0) * (mma > epi ? mma : epi) + mma + epi;   // last round: nothing overlaps
+    if (t < best_t * 0.97) { best_t = t; best = bn; }        // ties go to the narrower tile (shorter epilogue tail)
+  }
+  return best;
 }
 
 MegaJob make_job(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, int wait_job,
                  int wait_all) {
   MegaJob j = {};
   j.M = M; j.N = N; j.K = K; j.A = A; j.lda = lda; j.B = B; j.ldb = ldb;
-  j.bn = choose_bn(M, N, 64);
+  j.bn = choose_bn(M, N, K, 64);
   j.wait_job = wait_job; j.wait_all = wait_all;
   return j;
 }
@@ -156,7 +168,7 @@ MegaJob make_dgrad_job(int64_t batch, int64_t k_in, int64_t n_out, const void* d
                        int64_t ld_w, int wait_job) {
   MegaJob j = make_job(batch, k_in, n_out, dz, ld_dz, w, ld_w, wait_job, 0);
   j.b_mn = 1;
-  j.bn = choose_bn(batch, k_in, 128);
+  j.bn = choose_bn(batch, k_in, n_out, 128);
   return j;
 }
 
@@ -165,7 +177,7 @@ MegaJob make_wgrad_job(int64_t n_out, int64_t k_in, int64_t batch, const void* d
                        int64_t ld_x, int wait_job) {
   MegaJob j = make_job(n_out, k_in, batch, dz, ld_dz, x, ld_x, wait_job, 1);
   j.a_mn = 1; j.b_mn = 1;
-  j.bn = choose_bn(n_out, k_in, 128);
+  j.bn = choose_bn(n_out, k_in, batch, 128);
   return j;
 }
 

@@ -408,18 +408,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           for (int q = 0; q < 32; ++q) v[q] += __shfl_sync(FULL_MASK, bk, q);
         }
         if (act == NERAF_ACT_LEAKY) {
+          // predicate-free (max(v, 0.1 v)): the compare + predicated-multiply form serialises on two predicates
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], kLeakySlope * v[q]);
           if (mask_out != nullptr) {                              // remember the sign pattern for the backward gate
-            unsigned int bits = 0;
+            unsigned int neg0 = 0, neg1 = 0;                      // LeakyReLU keeps the sign: bit set <=> x < 0
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const bool pos = v[q] > 0.f;
-              bits |= pos ? (1u << q) : 0u;
-              v[q] = pos ? v[q] : kLeakySlope * v[q];
+            for (int q = 0; q < 32; q += 2) {
+              neg0 |= (__float_as_uint(v[q]) >> 31) << q;
+              neg1 |= (__float_as_uint(v[q + 1]) >> 31) << (q + 1);
             }
-            if (row_ok) mask_out[(long long)(n0 >> 5) * ld_mask + m] = bits;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] = v[q] > 0.f ? v[q] : kLeakySlope * v[q];
+            if (row_ok) mask_out[(long long)(n0 >> 5) * ld_mask + m] = ~(neg0 | neg1);
           }
         } else if (act == NERAF_ACT_TANH10) {
 #pragma unroll

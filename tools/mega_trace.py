@@ -53,3 +53,16 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def unit_timeline(path, li, unit):
+    """Per-tile stamps (us) of one unit in launch li: where its time goes between consecutive tiles."""
+    jobs, units, t, ck = read(path)[li]
+    t = np.where(t == 0, np.nan, t)
+    t = (t - np.nanmin(t)) / 1e3
+    starts = [j[0] for j in jobs]
+    print(f"launch {li} unit {unit}:  tile job |  dep  loaded | mma_start mma_first mma_done | epi_start epi_stored epi_done")
+    for tile in range(unit, t.shape[0], units):
+        j = max(i for i, s in enumerate(starts) if s <= tile)
+        r = t[tile]
+        print(f"  {tile:5d} {j:3d} | {r[0]:6.1f} {r[1]:6.1f} | {r[2]:6.1f} {r[3]:6.1f} {r[4]:6.1f} | {r[5]:6.1f} {r[6]:6.1f} {r[7]:6.1f}")
