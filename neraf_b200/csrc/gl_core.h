@@ -4,9 +4,11 @@
 //
 // A warp owns one STFT frame at a time.  The n_fft-point real transform is done as an H = n_fft/2
 // point complex FFT (Stockham autosort, radix-8 passes with a radix-4/2 tail) on a per-warp
-// shared-memory buffer (split re/im, index-padded by i + i/32 so that the strided stores of the
-// early passes are bank-conflict free) plus the usual even/odd post-/pre-processing.  Twiddles
-// come from one table tw[m] = exp(-2 pi i m / n_fft), m < n_fft.
+// shared-memory buffer (split re/im, bank-swizzled so that the strided stores of the early passes are
+// conflict free) plus the usual even/odd post-/pre-processing.  Twiddles: the even/odd split uses one
+// table tw[m] = exp(-2 pi i m / n_fft), m < n_fft; every FFT pass has its own small table laid out
+// [r - 1][k] so that consecutive lanes read consecutive entries (indexing the big table with k*r*step
+// made every twiddle load an 8-16 way bank conflict: 43 % of all shared-memory wavefronts, ncu).
 //
 // Every pass is split in a "load+butterfly" half that only reads the buffer and a "store" half that
 // only writes it; the caller separates the halves with a warp barrier (the values live in registers
@@ -37,9 +39,14 @@ GL_HD C2 rot90(C2 a) {
   return INV ? C2{-a.y, a.x} : C2{a.y, -a.x};
 }
 
-GL_HD int padi(int i) { return i + (i >> 5); }
+// Bank swizzle of the per-warp FFT buffers (4-byte elements, split re/im): low index bits are XOR-ed with higher
+// ones so that the three access patterns of the Stockham passes are conflict free --
+//   contiguous (loads, last-pass stores), stride 8 (first-pass stores: i = 8 lane + r) and
+//   8-element groups 64 apart (second-pass stores: i = 64 g + 8 r + m) --
+// without padding (a bijection on [0, H)).  Index-padding (i + i/32) left the second pattern 2-4 way conflicted.
+GL_HD int padi(int i) { return i ^ ((i >> 5) & 7) ^ (((i >> 6) & 3) << 3); }
 
-constexpr int padded_size(int h) { return h + (h >> 5) + 1; }
+constexpr int padded_size(int h) { return h; }
 
 // ------------------------------------------------------------------------------------------------
 // Small DFTs, natural-order output.  Forward: exp(-2 pi i nk/R); INV: conjugate kernel, unnormalised.
@@ -99,11 +106,11 @@ struct PassShape {
 
 // One Stockham pass, first half: gather R inputs per butterfly, apply the inter-stage twiddles and
 // the radix-R DFT; results stay in `v` (registers).  Ns = product of the radices of earlier passes.
+// twp: this pass's twiddle table, twp[(r - 1) * Ns + k] = exp(-2 pi i k r / (Ns R)) (unused when Ns == 1).
 template <int R, int H, bool INV>
-GL_HD void pass_load(int lane, int Ns, const float* re, const float* im, const C2* tw, C2 (*v)[R]) {
+GL_HD void pass_load(int lane, int Ns, const float* re, const float* im, const C2* twp, C2 (*v)[R]) {
   constexpr int NB = PassShape<R, H>::BUTTERFLIES;
   constexpr int PL = PassShape<R, H>::PER_LANE;
-  const int tw_step = (2 * H) / (Ns * R);      // table has n_fft = 2H entries per turn
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -118,7 +125,7 @@ GL_HD void pass_load(int lane, int Ns, const float* re, const float* im, const C
         const int idx = padi(j + r * NB);
         C2 x{re[idx], im[idx]};
         if (r > 0 && Ns > 1) {
-          C2 w = tw[k * r * tw_step];
+          C2 w = twp[(r - 1) * Ns + k];
           if (INV) w.y = -w.y;
           x = cmul(x, w);
         }
@@ -162,6 +169,36 @@ struct Schedule {
   static constexpr int N8 = LOG2 / 3;
   static constexpr int TAIL = LOG2 % 3 == 0 ? 1 : (LOG2 % 3 == 1 ? 2 : 4);
 };
+
+// Per-pass twiddle tables, concatenated in pass order (passes with Ns == 1 have none).
+template <int H>
+struct PassTables {
+  static constexpr int N8 = Schedule<H>::N8, TAIL = Schedule<H>::TAIL;
+  // offset of the table of radix-8 pass p (p >= 1): 7 * (8 + 64 + ... + 8^(p-1))
+  static constexpr int offset8(int p) { return p <= 1 ? 0 : offset8(p - 1) + 7 * ipow8(p - 1); }
+  static constexpr int ipow8(int p) { return p == 0 ? 1 : 8 * ipow8(p - 1); }
+  static constexpr int TAIL_OFFSET = offset8(N8);
+  static constexpr int TOTAL = TAIL_OFFSET + (TAIL > 1 ? (TAIL - 1) * ipow8(N8) : 0);
+};
+
+// Entry e of the concatenated tables as (numerator, denominator): exp(-2 pi i num / den).
+template <int H>
+GL_HD void pass_table_angle(int e, int* num, int* den) {
+  int Ns = 8, off = 0;
+  for (int p = 1; p < Schedule<H>::N8; ++p) {
+    if (e < off + 7 * Ns) {
+      const int r = (e - off) / Ns + 1, k = (e - off) % Ns;
+      *num = k * r; *den = Ns * 8;
+      return;
+    }
+    off += 7 * Ns;
+    Ns *= 8;
+  }
+  // tail pass (radix 4 or 2) after N8 radix-8 passes: Ns = 8^N8
+  const int NsT = PassTables<H>::ipow8(Schedule<H>::N8);
+  const int r = (e - off) / NsT + 1, k = (e - off) % NsT;
+  *num = k * r; *den = NsT * Schedule<H>::TAIL;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Frame load: z[j] = x[2j] + i x[2j+1] with x[n] = D[reflect(t*hop + n - H)] * win[n]

@@ -43,16 +43,17 @@ __device__ __forceinline__ void run_pass(int lane, int Ns, float* re, float* im,
   __syncwarp();
 }
 
+// twp: the concatenated per-pass twiddle tables (gl_core.h PassTables)
 template <int H, bool INV>
-__device__ __forceinline__ void fft_warp(int lane, float* re, float* im, const C2* tw) {
+__device__ __forceinline__ void fft_warp(int lane, float* re, float* im, const C2* twp) {
   int Ns = 1;
 #pragma unroll
   for (int i = 0; i < Schedule<H>::N8; ++i) {
-    run_pass<8, H, INV>(lane, Ns, re, im, tw);
+    run_pass<8, H, INV>(lane, Ns, re, im, twp + PassTables<H>::offset8(i));
     Ns *= 8;
   }
-  if (Schedule<H>::TAIL == 4) run_pass<4, H, INV>(lane, Ns, re, im, tw);
-  if (Schedule<H>::TAIL == 2) run_pass<2, H, INV>(lane, Ns, re, im, tw);
+  if (Schedule<H>::TAIL == 4) run_pass<4, H, INV>(lane, Ns, re, im, twp + PassTables<H>::TAIL_OFFSET);
+  if (Schedule<H>::TAIL == 2) run_pass<2, H, INV>(lane, Ns, re, im, twp + PassTables<H>::TAIL_OFFSET);
 }
 
 template <int H>
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
   float* ACC = D + Lp;
   float* win = ACC + Lp;
   C2* tw = reinterpret_cast<C2*>(win + N);
-  float* fftbuf = reinterpret_cast<float*>(tw + N);
+  C2* twp = tw + N;
+  float* fftbuf = reinterpret_cast<float*>(twp + PassTables<H>::TOTAL);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid / 32, lane = tid % 32, nwarps = nthreads / 32;
@@ -80,6 +82,13 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
     sincospi(2.0 * (double)n / (double)N, &s, &c);
     tw[n] = C2{(float)c, (float)(-s)};
   }
+  for (int e = tid; e < PassTables<H>::TOTAL; e += nthreads) {
+    int num, den;
+    pass_table_angle<H>(e, &num, &den);
+    double s, c;
+    sincospi(2.0 * (double)num / (double)den, &s, &c);
+    twp[e] = C2{(float)c, (float)(-s)};
+  }
   const float scale = 1.f / (float)N;
 
   for (long long sig = blockIdx.x; sig < a.n_signals; sig += gridDim.x) {
@@ -91,6 +100,8 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
       for (int color = 0; color < a.n_colors; ++color) {
         for (int t = color + a.n_colors * warp; t < a.T; t += a.n_colors * nwarps) {
           const float* mag_row = mag_sig + (long long)t * a.F;
+          // the magnitude row is consumed after the forward FFT: pull its lines (L2 -> L1) now
+          if (lane * 32 < a.F) asm volatile("prefetch.global.L1 [%0];" ::"l"(mag_row + lane * 32));
           if (it == 0) {
             const float* init_row = a.init ? a.init + 2 * ((sig / a.n_channels) * a.init_sn + (sig % a.n_channels) * a.init_sc +
                                                            (long long)t * a.init_st)
@@ -100,11 +111,11 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
           } else {
             load_frame<H>(lane, t, a.hop, a.L, D, win, re, im);
             __syncwarp();
-            fft_warp<H, false>(lane, re, im, tw);
+            fft_warp<H, false>(lane, re, im, twp);
             spectrum_step<H>(lane, tw, mag_row, re, im);
             __syncwarp();
           }
-          fft_warp<H, true>(lane, re, im, tw);
+          fft_warp<H, true>(lane, re, im, twp);
           ola_frame<H>(lane, t, a.hop, a.L, win, re, im, scale, ACC);
           __syncwarp();
         }
@@ -164,6 +175,18 @@ __global__ void __launch_bounds__(256) gl_env_kernel(float* __restrict__ inv_env
   inv_env[n] = e > 1e-11 ? (float)(1.0 / e) : 0.f;
 }
 
+static size_t pass_tables_total(int H) {
+  switch (H) {
+    case 32: return PassTables<32>::TOTAL;
+    case 64: return PassTables<64>::TOTAL;
+    case 128: return PassTables<128>::TOTAL;
+    case 256: return PassTables<256>::TOTAL;
+    case 512: return PassTables<512>::TOTAL;
+    case 1024: return PassTables<1024>::TOTAL;
+  }
+  return 0;
+}
+
 struct Plan {
   int H, L, n_colors, nwarps;
   size_t smem_bytes;
@@ -188,7 +211,7 @@ static int make_plan(const neraf_gl_params* p, long long S, Plan* pl) {
   const size_t Lp = (size_t)((pl->L + 3) & ~3);
   pl->nwarps = 0;
   for (int nw = 16; nw >= 2; nw /= 2) {
-    const size_t bytes = (2 * Lp + N) * 4 + (size_t)N * 8 + (size_t)nw * 2 * padded_size(pl->H) * 4;
+    const size_t bytes = (2 * Lp + N) * 4 + ((size_t)N + pass_tables_total(pl->H)) * 8 + (size_t)nw * 2 * padded_size(pl->H) * 4;
     if (bytes <= 227 * 1024) { pl->nwarps = nw; pl->smem_bytes = bytes; break; }
   }
   if (pl->nwarps == 0)

@@ -25,12 +25,29 @@ static void run_pass(int Ns, float* re, float* im, const C2* tw) {
   for (int lane = 0; lane < 32; ++lane) pass_store<R, H>(lane, Ns, re, im, regs[lane]);
 }
 
+// per-pass twiddle tables exactly as the kernel builds them (gl_core.h PassTables / pass_table_angle)
+template <int H>
+static const C2* pass_tables() {
+  static std::vector<C2> t;
+  if (t.empty()) {
+    t.resize(PassTables<H>::TOTAL + 1);
+    for (int e = 0; e < PassTables<H>::TOTAL; ++e) {
+      int num, den;
+      pass_table_angle<H>(e, &num, &den);
+      const double a = -2.0 * M_PI * num / den;
+      t[e] = C2{(float)std::cos(a), (float)std::sin(a)};
+    }
+  }
+  return t.data();
+}
+
 template <int H, bool INV>
-static void fft_host(float* re, float* im, const C2* tw) {
+static void fft_host(float* re, float* im, const C2*) {
+  const C2* twp = pass_tables<H>();
   int Ns = 1;
-  for (int i = 0; i < Schedule<H>::N8; ++i) { run_pass<8, H, INV>(Ns, re, im, tw); Ns *= 8; }
-  if (Schedule<H>::TAIL == 4) run_pass<4, H, INV>(Ns, re, im, tw);
-  if (Schedule<H>::TAIL == 2) run_pass<2, H, INV>(Ns, re, im, tw);
+  for (int i = 0; i < Schedule<H>::N8; ++i) { run_pass<8, H, INV>(Ns, re, im, twp + PassTables<H>::offset8(i)); Ns *= 8; }
+  if (Schedule<H>::TAIL == 4) run_pass<4, H, INV>(Ns, re, im, twp + PassTables<H>::TAIL_OFFSET);
+  if (Schedule<H>::TAIL == 2) run_pass<2, H, INV>(Ns, re, im, twp + PassTables<H>::TAIL_OFFSET);
 }
 
 static std::vector<C2> make_tw(int n_fft) {
