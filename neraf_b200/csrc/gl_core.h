@@ -258,10 +258,36 @@ GL_HD void write_inverse_pair(int k, C2 yk, C2 ykk, const C2* tw, float* re, flo
   im[pkk] = -e.y + o.x;
 }
 
+// The magnitudes a lane needs in spectrum_step (bins k = lane + 32 i and H - k), fetched into registers ahead of the
+// forward FFT so that their global-memory latency hides behind it.
 template <int H>
-GL_HD void spectrum_step(int lane, const C2* tw, const float* mag_row, float* re, float* im) {
+struct MagRegs {
+  static constexpr int NK = (H / 2) / 32 + 1;
+  float k[NK], kk[NK];
+};
+
+template <int H>
+GL_HD void load_mag(int lane, const float* mag_row, MagRegs<H>& m) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < MagRegs<H>::NK; ++i) {
+    const int k = lane + 32 * i;
+    const bool ok = k <= H / 2;
+    m.k[i] = ok ? mag_row[k] : 0.f;
+    m.kk[i] = ok ? mag_row[H - k] : 0.f;
+  }
+}
+
+template <int H>
+GL_HD void spectrum_step(int lane, const C2* tw, const MagRegs<H>& m, float* re, float* im) {
   // k = 0 (DC / Nyquist pair) is done by the lane that owns index 0.
-  for (int k = lane; k <= H / 2; k += 32) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < MagRegs<H>::NK; ++i) {
+    const int k = lane + 32 * i;
+    if (k > H / 2) continue;
     if (k == 0) {
       const float zr = re[0], zi = im[0];
       const float x0 = zr + zi, xh = zr - zi;
@@ -270,7 +296,7 @@ GL_HD void spectrum_step(int lane, const C2* tw, const float* mag_row, float* re
 #else
       const float a0 = x0 / (std::fabs(x0) + 1e-16f), ah = xh / (std::fabs(xh) + 1e-16f);
 #endif
-      const float y0 = mag_row[0] * a0, yh = mag_row[H] * ah;
+      const float y0 = m.k[i] * a0, yh = m.kk[i] * ah;
       re[0] = y0 + yh;
       im[0] = y0 - yh;
     } else {
@@ -285,7 +311,7 @@ GL_HD void spectrum_step(int lane, const C2* tw, const float* mag_row, float* re
       const C2 xk = cadd(xe, tt);
       const C2 xkk = cconj(csub(xe, tt));
       const C2 ak = unit_phase(xk), akk = unit_phase(xkk);
-      const float mk = mag_row[k], mkk = mag_row[kk];
+      const float mk = m.k[i], mkk = m.kk[i];
       write_inverse_pair<H>(k, C2{mk * ak.x, mk * ak.y}, C2{mkk * akk.x, mkk * akk.y}, tw, re, im);
     }
   }

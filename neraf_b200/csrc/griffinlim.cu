@@ -100,8 +100,6 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
       for (int color = 0; color < a.n_colors; ++color) {
         for (int t = color + a.n_colors * warp; t < a.T; t += a.n_colors * nwarps) {
           const float* mag_row = mag_sig + (long long)t * a.F;
-          // the magnitude row is consumed after the forward FFT: pull its lines (L2 -> L1) now
-          if (lane * 32 < a.F) asm volatile("prefetch.global.L1 [%0];" ::"l"(mag_row + lane * 32));
           if (it == 0) {
             const float* init_row = a.init ? a.init + 2 * ((sig / a.n_channels) * a.init_sn + (sig % a.n_channels) * a.init_sc +
                                                            (long long)t * a.init_st)
@@ -109,10 +107,12 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
             init_step<H>(lane, tw, mag_row, init_row, a.init_sf, re, im);
             __syncwarp();
           } else {
+            MagRegs<H> mag;                       // consumed after the forward FFT: its latency hides behind it
+            load_mag<H>(lane, mag_row, mag);
             load_frame<H>(lane, t, a.hop, a.L, D, win, re, im);
             __syncwarp();
             fft_warp<H, false>(lane, re, im, twp);
-            spectrum_step<H>(lane, tw, mag_row, re, im);
+            spectrum_step<H>(lane, tw, mag, re, im);
             __syncwarp();
           }
           fft_warp<H, true>(lane, re, im, twp);

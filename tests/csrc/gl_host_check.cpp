@@ -116,7 +116,11 @@ static int run_gl(int win_length, int hop, int T, int n_iter, float momentum, bo
       } else {
         for (int lane = 0; lane < 32; ++lane) load_frame<H>(lane, t, hop, L, D.data(), win.data(), re.data(), im.data());
         fft_host<H, false>(re.data(), im.data(), tw.data());
-        for (int lane = 0; lane < 32; ++lane) spectrum_step<H>(lane, tw.data(), &mag[(size_t)t * F], re.data(), im.data());
+        for (int lane = 0; lane < 32; ++lane) {
+          MagRegs<H> m;
+          load_mag<H>(lane, &mag[(size_t)t * F], m);
+          spectrum_step<H>(lane, tw.data(), m, re.data(), im.data());
+        }
       }
       fft_host<H, true>(re.data(), im.data(), tw.data());
       for (int lane = 0; lane < 32; ++lane) ola_frame<H>(lane, t, hop, L, win.data(), re.data(), im.data(), scale, ACC.data());
