@@ -121,17 +121,56 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
         }
         __syncthreads();
       }
-      // whole-waveform pass: window-envelope normalisation (torch.istft) + momentum combination
+      // whole-waveform pass: window-envelope normalisation (torch.istft) + momentum combination.  Every thread issues
+      // ALL its global loads (envelope, previous waveform) before it touches them: one exposed L2 latency per
+      // iteration instead of one per unrolled group (ncu: 16 % of all stall samples sat on these loads).
       const bool last = it == a.n_iter;
-      for (int n = tid; n < a.L; n += nthreads) {
-        const float b = ACC[n] * __ldg(a.inv_env + n);
-        ACC[n] = 0.f;
-        if (last) {
-          a.wave[sig * (long long)a.L + n] = b;
-        } else {
-          const float p = it > 0 ? prev[n] : 0.f;
-          D[n] = b - a.m * p;
-          prev[n] = b;
+      float* wave = a.wave + sig * (long long)a.L;
+      if ((a.L & 3) == 0) {
+        constexpr int UNR = 4;
+        const int L4 = a.L >> 2;
+        const float4* env4 = reinterpret_cast<const float4*>(a.inv_env);
+        float4* prev4 = reinterpret_cast<float4*>(prev);
+        float4* acc4 = reinterpret_cast<float4*>(ACC);
+        float4* d4 = reinterpret_cast<float4*>(D);
+        for (int base = tid; base < L4; base += nthreads * UNR) {
+          float4 e[UNR], p[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int i = base + u * nthreads;
+            if (i < L4) {
+              e[u] = __ldg(env4 + i);
+              if (!last && it > 0) p[u] = prev4[i];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int i = base + u * nthreads;
+            if (i < L4) {
+              const float4 acc = acc4[i];
+              const float4 b = make_float4(acc.x * e[u].x, acc.y * e[u].y, acc.z * e[u].z, acc.w * e[u].w);
+              acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (last) {
+                reinterpret_cast<float4*>(wave)[i] = b;
+              } else {
+                const float4 q = it > 0 ? p[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                d4[i] = make_float4(b.x - a.m * q.x, b.y - a.m * q.y, b.z - a.m * q.z, b.w - a.m * q.w);
+                prev4[i] = b;
+              }
+            }
+          }
+        }
+      } else {
+        for (int n = tid; n < a.L; n += nthreads) {
+          const float b = ACC[n] * __ldg(a.inv_env + n);
+          ACC[n] = 0.f;
+          if (last) {
+            wave[n] = b;
+          } else {
+            const float p = it > 0 ? prev[n] : 0.f;
+            D[n] = b - a.m * p;
+            prev[n] = b;
+          }
         }
       }
       __syncthreads();
