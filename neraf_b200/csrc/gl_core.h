@@ -210,17 +210,21 @@ GL_HD int reflect_index(int idx, int L) {
   return idx;
 }
 
+// [j_lo, j_hi): complex samples j = n/2 that touch the window support [left, left + win_length) (zero elsewhere).
 template <int H>
-GL_HD void load_frame(int lane, int t, int hop, int L, const float* D, const float* win, float* re, float* im) {
+GL_HD void load_frame(int lane, int t, int hop, int L, int j_lo, int j_hi, const float* D, const float* win, float* re,
+                      float* im) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 4
 #endif
   for (int j = lane; j < H; j += 32) {
-    const int n0 = 2 * j;
-    const float w0 = win[n0], w1 = win[n0 + 1];
-    const int base = t * hop + n0 - H;
-    const float x0 = (w0 != 0.f) ? D[reflect_index(base, L)] * w0 : 0.f;
-    const float x1 = (w1 != 0.f) ? D[reflect_index(base + 1, L)] * w1 : 0.f;
+    float x0 = 0.f, x1 = 0.f;
+    if (j >= j_lo && j < j_hi) {
+      const int n0 = 2 * j;
+      const int base = t * hop + n0 - H;
+      x0 = D[reflect_index(base, L)] * win[n0];
+      x1 = D[reflect_index(base + 1, L)] * win[n0 + 1];
+    }
     const int p = padi(j);
     re[p] = x0;
     im[p] = x1;
@@ -235,11 +239,15 @@ GL_HD void load_frame(int lane, int t, int hop, int L, const float* D, const flo
 // and the buffer is overwritten with Z' such that IFFT_H(Z') = y[2n] + i y[2n+1], y = n_fft * irfft(Y).
 // Pairs (k, H-k) are handled by one lane, so the pass is in place.
 // ------------------------------------------------------------------------------------------------
+// x / (|x| + 1e-16) (torchaudio functional.py:345).  Evaluated as x * rsqrt(max(|x|^2, 1e-32)): identical to rounding
+// for |x| >> 1e-16, 0 for x == 0 like the reference, and differs only for 0 < |x| < ~1e-15 where the reference shrinks
+// the unit phasor (never reached by STFTs of fp32 audio).  One MUFU.RSQ instead of an IEEE sqrt + division.
 GL_HD C2 unit_phase(C2 x) {
+  const float s = x.x * x.x + x.y * x.y;
 #if defined(__CUDA_ARCH__)
-  const float inv = 1.f / (sqrtf(x.x * x.x + x.y * x.y) + 1e-16f);
+  const float inv = rsqrtf(fmaxf(s, 1e-32f));
 #else
-  const float inv = 1.f / (std::sqrt(x.x * x.x + x.y * x.y) + 1e-16f);
+  const float inv = 1.f / std::sqrt(s > 1e-32f ? s : 1e-32f);
 #endif
   return C2{x.x * inv, x.y * inv};
 }
@@ -346,18 +354,18 @@ GL_HD void init_step(int lane, const C2* tw, const float* mag_row, const float* 
 // happens once per iteration on the whole waveform).
 // ------------------------------------------------------------------------------------------------
 template <int H>
-GL_HD void ola_frame(int lane, int t, int hop, int L, const float* win, const float* re, const float* im, float scale,
-                     float* ACC) {
+GL_HD void ola_frame(int lane, int t, int hop, int L, int j_lo, int j_hi, const float* win, const float* re, const float* im,
+                     float scale, float* ACC) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 4
 #endif
-  for (int j = lane; j < H; j += 32) {
+  for (int j = j_lo + lane; j < j_hi; j += 32) {               // outside the window support nothing is added
     const int n0 = 2 * j;
     const int p = padi(j);
     const int idx = t * hop + n0 - H;
     const float w0 = win[n0], w1 = win[n0 + 1];
-    if (w0 != 0.f && idx >= 0 && idx < L) ACC[idx] += re[p] * (w0 * scale);
-    if (w1 != 0.f && idx + 1 >= 0 && idx + 1 < L) ACC[idx + 1] += im[p] * (w1 * scale);
+    if (idx >= 0 && idx < L) ACC[idx] += re[p] * (w0 * scale);
+    if (idx + 1 >= 0 && idx + 1 < L) ACC[idx + 1] += im[p] * (w1 * scale);
   }
 }
 

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
     twp[e] = C2{(float)c, (float)(-s)};
   }
   const float scale = 1.f / (float)N;
+  const int j_lo = left / 2, j_hi = (left + a.win_length + 1) / 2;      // complex samples inside the window support
 
   for (long long sig = blockIdx.x; sig < a.n_signals; sig += gridDim.x) {
     for (int n = tid; n < a.L; n += nthreads) ACC[n] = 0.f;
@@ -109,14 +110,14 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
           } else {
             MagRegs<H> mag;                       // consumed after the forward FFT: its latency hides behind it
             load_mag<H>(lane, mag_row, mag);
-            load_frame<H>(lane, t, a.hop, a.L, D, win, re, im);
+            load_frame<H>(lane, t, a.hop, a.L, j_lo, j_hi, D, win, re, im);
             __syncwarp();
             fft_warp<H, false>(lane, re, im, twp);
             spectrum_step<H>(lane, tw, mag, re, im);
             __syncwarp();
           }
           fft_warp<H, true>(lane, re, im, twp);
-          ola_frame<H>(lane, t, a.hop, a.L, win, re, im, scale, ACC);
+          ola_frame<H>(lane, t, a.hop, a.L, j_lo, j_hi, win, re, im, scale, ACC);
           __syncwarp();
         }
         __syncthreads();

@@ -114,7 +114,7 @@ static int run_gl(int win_length, int hop, int T, int n_iter, float momentum, bo
         for (int lane = 0; lane < 32; ++lane)
           init_step<H>(lane, tw.data(), &mag[(size_t)t * F], has_init ? &init[(size_t)t * F * 2] : nullptr, 1, re.data(), im.data());
       } else {
-        for (int lane = 0; lane < 32; ++lane) load_frame<H>(lane, t, hop, L, D.data(), win.data(), re.data(), im.data());
+        for (int lane = 0; lane < 32; ++lane) load_frame<H>(lane, t, hop, L, left / 2, (left + win_length + 1) / 2, D.data(), win.data(), re.data(), im.data());
         fft_host<H, false>(re.data(), im.data(), tw.data());
         for (int lane = 0; lane < 32; ++lane) {
           MagRegs<H> m;
@@ -123,7 +123,7 @@ static int run_gl(int win_length, int hop, int T, int n_iter, float momentum, bo
         }
       }
       fft_host<H, true>(re.data(), im.data(), tw.data());
-      for (int lane = 0; lane < 32; ++lane) ola_frame<H>(lane, t, hop, L, win.data(), re.data(), im.data(), scale, ACC.data());
+      for (int lane = 0; lane < 32; ++lane) ola_frame<H>(lane, t, hop, L, left / 2, (left + win_length + 1) / 2, win.data(), re.data(), im.data(), scale, ACC.data());
     }
     for (int n = 0; n < L; ++n) {
       const float b = ACC[n] * inv_env[n];
