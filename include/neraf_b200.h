@@ -211,8 +211,9 @@ typedef struct {
   int64_t ld_f32;
   int32_t accumulate_f32;
   /* job-list kernel only (neraf_gemm_bf16_jobs); must be NULL for neraf_gemm_bf16:
-   * mask_out  : with act == NERAF_ACT_LEAKY, also store the sign pattern of the pre-activation: bit (n % 32) of the
-   *             uint32 word mask_out[(n / 32) * ld_mask + m] is set when element (m, n) is >= +0 (sign bit clear);
+   * mask_out  : with act == NERAF_ACT_LEAKY and out_bf16, also store the sign bits of the 32 stored activations
+   *             (m, 32 w .. 32 w + 31) in the uint32 word mask_out[w * ld_mask + m]: bit i <- column 32 w + 2 i,
+   *             bit 16 + i <- column 32 w + 2 i + 1, set when the activation is negative;
    * gate_mask : LeakyReLU' gate read from such a mask instead of `gate` (same indexing). */
   void* mask_out;
   const void* gate_mask;
@@ -244,6 +245,8 @@ typedef struct {
   const void* A; int64_t lda;
   const void* B; int64_t ldb;
   int32_t a_mn, b_mn;
+  int32_t b_static;   /* 1: B is not written by any job of this launch (weights, data of an earlier launch): it may be
+                         fetched before this job's dependency is resolved */
   int32_t bn;
   int32_t wait_job;
   int32_t wait_all;

@@ -49,7 +49,8 @@ class GemmEpilogue(C.Structure):
 
 class GemmJob(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("A", C.c_void_p), ("lda", C.c_int64),
-                ("B", C.c_void_p), ("ldb", C.c_int64), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bn", C.c_int32),
+                ("B", C.c_void_p), ("ldb", C.c_int64), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("b_static", C.c_int32),
+                ("bn", C.c_int32),
                 ("wait_job", C.c_int32), ("wait_all", C.c_int32), ("epi", GemmEpilogue), ("colsum", C.c_void_p)]
 
 

@@ -160,6 +160,7 @@ MegaJob make_job(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, co
   j.M = M; j.N = N; j.K = K; j.A = A; j.lda = lda; j.B = B; j.ldb = ldb;
   j.bn = choose_bn(M, N, K, 64);
   j.wait_job = wait_job; j.wait_all = wait_all;
+  j.b_static = 1;      // every B operand of the field is a weight matrix or an activation of the forward launch
   return j;
 }
 

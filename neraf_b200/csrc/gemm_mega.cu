@@ -54,18 +54,19 @@ constexpr int MEGA_STAGES = 6;
 constexpr int MEGA_A_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB
 constexpr int MEGA_B_BYTES = 128 * BLOCK_K * 2;                // up to bn/2 = 128 rows: 16 KB
 constexpr int MEGA_OUT_BYTES = 32 * 128;                       // per-warp 32x32 fp32 transpose tile (unaligned fp32 outputs only)
-constexpr int MEGA_SMEM_BYTES = 1024 + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES) + MEGA_EPI_WARPS * MEGA_OUT_BYTES + (2 * MEGA_STAGES + 4) * 8 + 16;
+constexpr int MEGA_BIAS_BYTES = 256;                            // per-warp bias slice of the current chunk pair
+constexpr int MEGA_SMEM_BYTES = MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES) + MEGA_EPI_WARPS * (MEGA_OUT_BYTES + MEGA_BIAS_BYTES) + (2 * MEGA_STAGES + 4) * 8 + 16;
 constexpr int MEGA_TMEM_COLS = 512;
 constexpr int MEGA_ACC_COLS = 256;
 constexpr int MN_BOX_BYTES = 64 * 128;                         // one MN-major box: 64 k-rows x 64 MN elements
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct alignas(64) DeviceJob {
-  CUtensorMap tmA, tmB, tmOut;
+  CUtensorMap tmA, tmB, tmOut, tmOut1;   // tmOut1: single-chunk (32-column) bf16 stores
   int M, N, K, bn;
   int tile_start, num_m, num_n, cnt_off;
   int wait_job, wait_all, wait_target, wait_nrb, wait_cnt_off;
-  int act, a_mn, b_mn;
+  int act, a_mn, b_mn, b_static;
   int out_mode;                    // 0 none, 1 bf16 (TMA), 2 fp32 (TMA), 3 fp32 (rows not 16-byte tileable: smem transpose)
   int bias_vec;                    // bias may be read with 16-byte loads
   unsigned int* mask_out; const unsigned int* gate_mask; long long ld_mask;
@@ -174,12 +175,15 @@ __device__ __forceinline__ float gate_factor(float x) { return x > 0.f ? 1.f : k
 
 __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) {
   constexpr int CG = 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // the kernel has no static shared memory, so the dynamic window starts 1024-byte aligned (checked below: the
+  // 128-byte swizzle of TMA / UMMA needs it, and there is no room for an alignment slack)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + MEGA_STAGES * MEGA_A_BYTES;
   uint8_t* out_buf = smem + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES);       // 1024-byte aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_buf + MEGA_EPI_WARPS * MEGA_OUT_BYTES);
+  float* bias_buf = reinterpret_cast<float*>(out_buf + MEGA_EPI_WARPS * MEGA_OUT_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_buf + MEGA_EPI_WARPS * (MEGA_OUT_BYTES + MEGA_BIAS_BYTES));
   uint64_t* empty_bar = full_bar + MEGA_STAGES;
   uint64_t* tmem_full = empty_bar + MEGA_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -203,64 +207,94 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int j = 0;
-      for (int tile = unit; tile < P.num_tiles; tile += num_units) {
-        while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
-        const DeviceJob& J = P.jobs[j];
-        const int local = tile - J.tile_start;
-        const int mt = local / J.num_n, nt = local % J.num_n;          // row-block major: a row block completes early
-        const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
-        const int b_rows = J.bn / CG;
-        const uint32_t stage_bytes = (uint32_t)(MEGA_A_BYTES + b_rows * BLOCK_K * 2) * CG;
-        const int a_row0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
-        const int b_row0 = nt * J.bn + (int)cta_rank * b_rows;
-        auto load_a = [&](int st, int kb) {
-          uint8_t* sa = smem_a + st * MEGA_A_BYTES;
-          if (!J.a_mn) {
-            tma_load_2d<CG>(sa, &J.tmA, full_bar + st, kb * BLOCK_K, a_row0);
-          } else {                                        // matrix is (K rows, MN cols): coordinates {mn, k}
-            tma_load_2d<CG>(sa, &J.tmA, full_bar + st, a_row0, kb * BLOCK_K);
-            tma_load_2d<CG>(sa + MN_BOX_BYTES, &J.tmA, full_bar + st, a_row0 + 64, kb * BLOCK_K);
-          }
-        };
-        auto load_b = [&](int st, int kb) {
-          uint8_t* sb = smem_b + st * MEGA_B_BYTES;
-          if (!J.b_mn) {
-            tma_load_2d<CG>(sb, &J.tmB, full_bar + st, kb * BLOCK_K, b_row0);
-          } else {
-            tma_load_2d<CG>(sb, &J.tmB, full_bar + st, b_row0, kb * BLOCK_K);
-            if (b_rows > 64) tma_load_2d<CG>(sb + MN_BOX_BYTES, &J.tmB, full_bar + st, b_row0 + 64, kb * BLOCK_K);
-          }
-        };
-        int kb0 = 0;
-        if (J.wait_job >= 0) {
-          // Operands written by earlier tiles of this launch (other SMs).  Only the operands that ARE produced in the
-          // launch have to wait: a K-major B of a dependent job is a weight matrix, so its first ring-full of
-          // k-blocks is fetched while the dependency is still being resolved.
-          const bool b_early = !J.b_mn && !J.a_mn;
-          const int pre = b_early ? (num_kb < MEGA_STAGES ? num_kb : MEGA_STAGES) : 0;
-          int st = stage; uint32_t ph = phase;
-          for (int kb = 0; kb < pre; ++kb) {
-            mbar_wait(empty_bar + st, ph ^ 1);
-            if (is_leader) mbar_expect_tx(full_bar + st, stage_bytes);
-            load_b(st, kb);
-            if (++st == MEGA_STAGES) { st = 0; ph ^= 1; }
-          }
+    // Lane 0 issues every TMA; the other lanes only help to poll dependency counters (a "wait for every row block"
+    // dependency checks up to 32 counters per round trip instead of one after the other: 8 sequential L2 round trips
+    // cost ~3 us in front of every weight-gradient tile) -- and a job seen complete once is never polled again.
+    int stage = 0; uint32_t phase = 0;
+    int j = 0;
+    uint32_t done_jobs = 0;                                      // bit i: every row block of job i is known complete
+    for (int tile = unit; tile < P.num_tiles; tile += num_units) {
+      while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
+      const DeviceJob& J = P.jobs[j];
+      const int local = tile - J.tile_start;
+      const int mt = local / J.num_n, nt = local % J.num_n;          // row-block major: a row block completes early
+      const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
+      const int b_rows = J.bn / CG;
+      const uint32_t stage_bytes = (uint32_t)(MEGA_A_BYTES + b_rows * BLOCK_K * 2) * CG;
+      const int a_row0 = mt * (BLOCK_M * CG) + (int)cta_rank * BLOCK_M;
+      const int b_row0 = nt * J.bn + (int)cta_rank * b_rows;
+      auto load_a = [&](int st, int kb) {
+        uint8_t* sa = smem_a + st * MEGA_A_BYTES;
+        if (!J.a_mn) {
+          tma_load_2d<CG>(sa, &J.tmA, full_bar + st, kb * BLOCK_K, a_row0);
+        } else {                                        // matrix is (K rows, MN cols): coordinates {mn, k}
+          tma_load_2d<CG>(sa, &J.tmA, full_bar + st, a_row0, kb * BLOCK_K);
+          tma_load_2d<CG>(sa + MN_BOX_BYTES, &J.tmA, full_bar + st, a_row0 + 64, kb * BLOCK_K);
+        }
+      };
+      auto load_b = [&](int st, int kb) {
+        uint8_t* sb = smem_b + st * MEGA_B_BYTES;
+        if (!J.b_mn) {
+          tma_load_2d<CG>(sb, &J.tmB, full_bar + st, kb * BLOCK_K, b_row0);
+        } else {
+          tma_load_2d<CG>(sb, &J.tmB, full_bar + st, b_row0, kb * BLOCK_K);
+          if (b_rows > 64) tma_load_2d<CG>(sb + MN_BOX_BYTES, &J.tmB, full_bar + st, b_row0 + 64, kb * BLOCK_K);
+        }
+      };
+      int kb0 = 0;
+      const bool must_wait = J.wait_job >= 0 && !((done_jobs >> J.wait_job) & 1u);
+      if (must_wait) {
+        // Operands written by earlier tiles of this launch (other SMs).  The whole warp polls (wait_all: one counter
+        // per lane).  While the dependency is unresolved, ring slots that become free are filled with the B operand
+        // when it is flagged static (weights, data of an earlier launch): only A has to wait.
+        auto ready = [&]() -> bool {
+          bool ok = true;
           if (J.wait_all) {
-            for (int rb = 0; rb < J.wait_nrb; ++rb) spin_until(P.counters + J.wait_cnt_off + rb, (unsigned)J.wait_target);
-          } else {
-            spin_until(P.counters + J.wait_cnt_off + mt, (unsigned)J.wait_target);
+            for (int rb0 = 0; rb0 < J.wait_nrb; rb0 += 32) {
+              const int rb = rb0 + lane;
+              if (rb < J.wait_nrb) ok = ok && ld_acquire(P.counters + J.wait_cnt_off + rb) >= (unsigned)J.wait_target;
+            }
+          } else if (lane == 0) {
+            ok = ld_acquire(P.counters + J.wait_cnt_off + mt) >= (unsigned)J.wait_target;
           }
+          return __all_sync(FULL_MASK, ok);
+        };
+        const int pre_max = J.b_static ? (num_kb < MEGA_STAGES ? num_kb : MEGA_STAGES) : 0;
+        int pre = 0;
+        int st = stage; uint32_t ph = phase;
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (!ready()) {
+          bool issued = false;
+          if (pre < pre_max) {
+            if (lane == 0 && mbar_try_wait(empty_bar + st, ph ^ 1)) {
+              if (is_leader) mbar_expect_tx(full_bar + st, stage_bytes);
+              load_b(st, pre);
+              issued = true;
+            }
+            issued = __shfl_sync(FULL_MASK, issued, 0);
+            if (issued) {
+              ++pre;
+              if (++st == MEGA_STAGES) { st = 0; ph ^= 1; }
+            }
+          }
+          if (!issued) __nanosleep(32);
+          if ((++spins & 255u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) __trap();
+        }
+        if (J.wait_all) done_jobs |= 1u << J.wait_job;
+        if (lane == 0) {
           fence_proxy_async_all();
           if (is_leader) stamp(P.trace, tile, TR_DEP);
           for (int kb = 0; kb < pre; ++kb) {
             load_a(stage, kb);
             if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
           }
-          kb0 = pre;
+        } else {
+          stage = st; phase = ph;
         }
+        kb0 = pre;
+      }
+      if (lane == 0) {
         for (int kb = kb0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           if (is_leader) mbar_expect_tx(full_bar + stage, stage_bytes);
@@ -269,9 +303,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
         }
         if (is_leader) stamp(P.trace, tile, TR_LOADED);
+      } else {
+        for (int kb = kb0; kb < num_kb; ++kb)
+          if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
     if (lane == 0 && is_leader) {
@@ -317,6 +354,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
     const int half = (warp - 2) >> 2;                             // which half of the tile's 32-column chunks
     uint8_t* wbuf = out_buf + (warp - 2) * MEGA_OUT_BYTES;
     float* wbuf_f = reinterpret_cast<float*>(wbuf);
+    float* bias_s = bias_buf + (warp - 2) * (MEGA_BIAS_BYTES / 4);
     int it = 0, j = 0;
     for (int tile = unit; tile < P.num_tiles; tile += num_units, ++it) {
       while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
@@ -345,9 +383,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       const long long ld_mask = J.ld_mask;
       const bool gate_vec_ok = gate != nullptr && (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(gate) & 15) == 0);
 
-      // Per-chunk side operands, one coalesced load per chunk (at most 4 chunks per warp -> 8 registers):
-      //  * bias (lane q holds column q, broadcast by shuffles later): never produced inside the launch, so it is
-      //    fetched BEFORE waiting for the accumulator;
+      // Side operands, one coalesced load per chunk (at most 4 chunks per warp -> 8 registers):
+      //  * bias (lane q holds column q): never produced inside the launch, so it is fetched BEFORE waiting for the
+      //    accumulator; it reaches the other lanes through a 256-byte per-warp shared-memory slice read back as
+      //    broadcast 16-byte loads (32 shuffles per chunk cost ~500 cycles per round of 8 warps: tools/micro/epi_bench);
       //  * the LeakyReLU' gate word of the lane's row in the transposed bit mask: may have been written by an earlier
       //    job of this launch, so it is read (L2-coherent) only once the accumulator is complete -- the MMAs consumed
       //    operands the TMA producer loaded after it had acquired the dependency counter.
@@ -376,26 +415,31 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           else mbar_arrive_remote(tmem_empty + as, 0);
         }
       }
-      int sbuf = 0;                                               // staging half (2 KB) the next TMA store uses
       const uint32_t t_addr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MEGA_ACC_COLS + c_first * 32);
+      // Two chunks (64 columns) per iteration: both TMEM loads in flight before one wait, one proxy fence and one
+      // TMA store (128-byte rows) per pair -- the per-chunk fixed costs measured by tools/micro/epi_bench (LDTM 216,
+      // fence 170, TMA store 156 cycles per round of 8 warps) are what the 32-column version was made of.
 #pragma unroll 1
-      for (int k = 0; k < nvalid; ++k) {
-        const int c = c_first + k;
-        const int n0 = nt * J.bn + c * 32;
-        const bool full_chunk = n0 + 32 <= N;
-        float v[32];
-        tmem_ld_issue(t_addr0 + (uint32_t)(k * 32), v);
-        const float bk = k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3));
-        const unsigned int gm = k == 0 ? w0 : (k == 1 ? w1 : (k == 2 ? w2 : w3));
-        uint4 g_cur[4];
-        if (gate != nullptr && gate_vec_ok && row_ok && full_chunk) {      // generic bf16 gate (not used by the field)
-          const uint4* gp = reinterpret_cast<const uint4*>(gate + (long long)m * ldg + n0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g_cur[q] = __ldcg(gp + q);
+      for (int k = 0; k < nvalid; k += 2) {
+        const int nch = k + 1 < nvalid ? 2 : 1;
+        const int n0 = nt * J.bn + (c_first + k) * 32;
+        float v[64];
+        {
+          float (&va)[32] = *reinterpret_cast<float (*)[32]>(&v[0]);
+          float (&vb)[32] = *reinterpret_cast<float (*)[32]>(&v[32]);
+          tmem_ld_issue(t_addr0 + (uint32_t)(k * 32), va);
+          if (nch == 2) tmem_ld_issue(t_addr0 + (uint32_t)(k * 32 + 32), vb);
         }
+        // this pair's bias slice -> shared memory (while the TMEM loads are in flight)
+        if (bias != nullptr) {
+          bias_s[lane] = k == 0 ? b0 : b2;
+          bias_s[32 + lane] = k == 0 ? b1 : b3;
+          __syncwarp();
+        }
+        const unsigned int gm0 = k == 0 ? w0 : w2, gm1 = k == 0 ? w1 : w3;
         tmem_ld_wait();
         if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_LD);
-        if (k == nvalid - 1) {                                    // accumulator fully read: hand the TMEM stage back early
+        if (k + 2 >= nvalid) {                                    // accumulator fully read: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -403,117 +447,148 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
             else mbar_arrive_remote(tmem_empty + as, 0);
           }
         }
-        if (bias != nullptr) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] += __shfl_sync(FULL_MASK, bk, q);
-        }
-        if (act == NERAF_ACT_LEAKY) {
-          // predicate-free (max(v, 0.1 v)): the compare + predicated-multiply form serialises on two predicates
+        for (int h = 0; h < 2; ++h) {
+          if (h < nch) {
+            float* vh = v + 32 * h;
+            const int n0h = n0 + 32 * h;
+            const bool full_chunk = n0h + 32 <= N;
+            if (bias != nullptr) {
+              const float4* bs = reinterpret_cast<const float4*>(bias_s + 32 * h);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], kLeakySlope * v[q]);
-          if (mask_out != nullptr) {                              // remember the sign pattern for the backward gate
-            unsigned int neg0 = 0, neg1 = 0;                      // LeakyReLU keeps the sign: bit set <=> x < 0
-#pragma unroll
-            for (int q = 0; q < 32; q += 2) {
-              neg0 |= (__float_as_uint(v[q]) >> 31) << q;
-              neg1 |= (__float_as_uint(v[q + 1]) >> 31) << (q + 1);
-            }
-            if (row_ok) mask_out[(long long)(n0 >> 5) * ld_mask + m] = ~(neg0 | neg1);
-          }
-        } else if (act == NERAF_ACT_TANH10) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = 10.f * tanhf(v[q]);
-        }
-        if (gate_mask != nullptr) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = (gm >> q) & 1u ? v[q] : kLeakySlope * v[q];
-        } else if (gate != nullptr && row_ok) {
-          if (gate_vec_ok && full_chunk) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&g_cur[q]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
-                v[q * 8 + e * 2] *= gate_factor(f.x);
-                v[q * 8 + e * 2 + 1] *= gate_factor(f.y);
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = bs[q];
+                vh[4 * q] += t.x; vh[4 * q + 1] += t.y; vh[4 * q + 2] += t.z; vh[4 * q + 3] += t.w;
               }
             }
-          } else {
-            const __nv_bfloat16* g = gate + (long long)m * ldg + n0;
+            if (act == NERAF_ACT_LEAKY) {
+              // LeakyReLU on the FMA pipe only: 0.55 v + 0.45 |v|  (= v for v > 0, 0.1 v for v < 0, a few ulp of fp32
+              // off, invisible after the bf16 rounding).  max(v, 0.1 v) needs FMNMX, compare + predicated multiply
+              // needs FSETP: both run on the half-rate ALU pipe, which is what bounds this epilogue.
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (n0 + q < N) v[q] *= gate_factor(__bfloat162float(__ldcg(g + q)));
+              for (int q = 0; q < 32; ++q) vh[q] = fmaf(0.55f, vh[q], 0.45f * fabsf(vh[q]));
+            } else if (act == NERAF_ACT_TANH10) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) vh[q] = 10.f * tanhf(vh[q]);
+            }
+            if (gate_mask != nullptr) {
+              const unsigned int gm = h == 0 ? gm0 : gm1;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) vh[q] = (gm >> ((q & 1) * 16 + (q >> 1))) & 1u ? kLeakySlope * vh[q] : vh[q];
+            } else if (gate != nullptr && row_ok) {               // generic bf16 gate (not used by the field)
+              const __nv_bfloat16* g = gate + (long long)m * ldg + n0h;
+              if (gate_vec_ok && full_chunk) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(g) + q);
+                  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(hh[e]);
+                    vh[q * 8 + e * 2] *= gate_factor(f.x);
+                    vh[q * 8 + e * 2 + 1] *= gate_factor(f.y);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                  if (n0h + q < N) vh[q] *= gate_factor(__bfloat162float(__ldcg(g + q)));
+              }
+            }
           }
         }
         if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_MATH);
         if (out_mode == 1) {
-          // bf16 row-major: 32 x 32 tile = 32 rows of 64 bytes (64-byte swizzle), two 2 KB staging halves alternate
-          uint8_t* sb = wbuf + sbuf * 2048;
-          if (lane == 0) bulk_wait_read1();                       // the store issued two tiles ago has left this half
+          // bf16 row-major through the 4 KB staging tile: a pair is 32 rows of 128 bytes (128-byte swizzle, one TMA
+          // store), a single chunk 32 rows of 64 bytes (64-byte swizzle)
+          if (lane == 0) bulk_wait_read0();                       // the previous store has left the staging tile
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+          for (int h = 0; h < 2; ++h) {
+            if (h < nch) {
+              unsigned int neg = 0;                               // sign bits: bit i <- element 2i, bit 16+i <- element 2i+1
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(sb + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = pk;
+              for (int i = 0; i < 4; ++i) {
+                uint4 pk;
+                __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[32 * h + i * 8 + 2 * e], v[32 * h + i * 8 + 2 * e + 1]);
+                const int off = nch == 2 ? lane * 128 + (((h * 4 + i) ^ (lane & 7)) << 4)
+                                         : lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
+                *reinterpret_cast<uint4*>(wbuf + off) = pk;
+                if (mask_out != nullptr) {
+                  neg = (neg >> 1) | (pk.x & 0x80008000u);
+                  neg = (neg >> 1) | (pk.y & 0x80008000u);
+                  neg = (neg >> 1) | (pk.z & 0x80008000u);
+                  neg = (neg >> 1) | (pk.w & 0x80008000u);
+                }
+              }
+              // LeakyReLU keeps the sign and so does the bf16 rounding: the stored activations' sign bits ARE the
+              // backward gate (bit set <=> x < 0), one coalesced word per lane in the transposed mask
+              if (mask_out != nullptr && row_ok) mask_out[(long long)((n0 + 32 * h) >> 5) * ld_mask + m] = neg;
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&J.tmOut, sb, n0, m_base);
+            tma_store_2d(nch == 2 ? &J.tmOut : &J.tmOut1, wbuf, n0, m_base);
             bulk_commit();
           }
-          sbuf ^= 1;
         } else if (out_mode == 2) {
-          // fp32 row-major: two 32 x 16 halves (64-byte rows, 64-byte swizzle), one TMA store each
+          // fp32 row-major: one 32 x 32 tile (128-byte rows, 128-byte swizzle) per chunk
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            if (n0 + hf * 16 >= N) break;
-            uint8_t* sb = wbuf + sbuf * 2048;
-            if (lane == 0) bulk_wait_read1();
-            __syncwarp();
+          for (int h = 0; h < 2; ++h) {
+            if (h < nch) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int q0 = hf * 16 + i * 4;
-              *reinterpret_cast<float4*>(sb + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
-                  make_float4(v[q0], v[q0 + 1], v[q0 + 2], v[q0 + 3]);
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(wbuf + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                    make_float4(v[32 * h + i * 4], v[32 * h + i * 4 + 1], v[32 * h + i * 4 + 2], v[32 * h + i * 4 + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&J.tmOut, wbuf, n0 + 32 * h, m_base);
+                bulk_commit();
+              }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&J.tmOut, sb, n0 + hf * 16, m_base);
-              bulk_commit();
-            }
-            sbuf ^= 1;
           }
         } else if (out_mode == 3) {
           // rows that TMA cannot tile (e.g. (B, 513) fp32 outputs): transpose through the staging tile
           // (XOR-swizzled 32 x 32 floats, conflict-free both ways) so that lanes write consecutive columns
           float* out_f32 = J.out_f32;
           const long long ld_f32 = J.ld_f32;
+          const int rows = M - m_base < 32 ? M - m_base : 32;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) wbuf_f[lane * 32 + (q ^ lane)] = v[q];
-          __syncwarp();
-          const int n = n0 + lane;
-          if (n < N) {
-            const int rows = M - m_base < 32 ? M - m_base : 32;
+          for (int h = 0; h < 2; ++h) {
+            if (h < nch) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) wbuf_f[lane * 32 + (q ^ lane)] = v[32 * h + q];
+              __syncwarp();
+              const int n = n0 + 32 * h + lane;
+              if (n < N) {
 #pragma unroll 4
-            for (int r = 0; r < rows; ++r) out_f32[(long long)(m_base + r) * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
+                for (int r = 0; r < rows; ++r) out_f32[(long long)(m_base + r) * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
+              }
+              __syncwarp();
+            }
           }
-          __syncwarp();
         }
         if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_STORE);
         // ---- bias gradient: column sums of the fp32 values (destroys v)
         if (colsum != nullptr) {
-          if (!row_ok) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] = 0.f;
+          for (int h = 0; h < 2; ++h) {
+            if (h < nch) {
+              float (&vh)[32] = *reinterpret_cast<float (*)[32]>(&v[32 * h]);
+              if (!row_ok) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) vh[q] = 0.f;
+              }
+              const float ssum = column_sums_32(vh, lane);
+              if (n0 + 32 * h + lane < N) atomicAdd(colsum + n0 + 32 * h + lane, ssum);
+            }
           }
-          const float s = column_sums_32(v, lane);
-          if (n0 + lane < N) atomicAdd(colsum + n0 + lane, s);
         }
       }
       if (tracer) { stamp_clock(P.trace, tile, TR_CK_LOOP); stamp(P.trace, tile, TR_EPI_STORED); }
@@ -564,7 +639,7 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     else NERAF_TRY(get_tensor_map_2d(s.A, 2, s.K, s.M, s.lda, BLOCK_K, 64, &d.tmA));
     if (!s.b_mn) NERAF_TRY(get_tensor_map_2d(s.B, 2, s.N, s.K, s.ldb, s.bn / 2, BLOCK_K, &d.tmB));
     else NERAF_TRY(get_tensor_map_2d(s.B, 2, s.K, s.N, s.ldb, BLOCK_K, 64, &d.tmB));
-    d.a_mn = s.a_mn; d.b_mn = s.b_mn;
+    d.a_mn = s.a_mn; d.b_mn = s.b_mn; d.b_static = s.b_static;
     d.M = (int)s.M; d.N = (int)s.N; d.K = (int)s.K; d.bn = s.bn;
     d.num_m = (int)ceil_div(s.M, 256); d.num_n = (int)ceil_div(s.N, s.bn);
     d.tile_start = tile; tile += d.num_m * d.num_n;
@@ -584,18 +659,20 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
       NERAF_REQUIRE(s.epi.ld_bf16 % 8 == 0 && ((uintptr_t)s.epi.out_bf16 % 16) == 0 && s.epi.ld_bf16 >= s.N,
                     "mega_run: job %d: out_bf16 needs ld %% 8 == 0, ld >= N and 16-byte alignment", i);
       d.out_mode = 1;
-      NERAF_TRY(get_tensor_map_2d(s.epi.out_bf16, 2, s.M, s.N, s.epi.ld_bf16, 32, 32, &d.tmOut));
+      NERAF_TRY(get_tensor_map_2d(s.epi.out_bf16, 2, s.M, s.N, s.epi.ld_bf16, 32, 64, &d.tmOut));
+      NERAF_TRY(get_tensor_map_2d(s.epi.out_bf16, 2, s.M, s.N, s.epi.ld_bf16, 32, 32, &d.tmOut1));
     } else if (s.epi.out_f32) {
       NERAF_REQUIRE(s.epi.ld_f32 >= s.N, "mega_run: job %d: out_f32 row stride < N", i);
       // TMA stores clip with 16-byte granularity: only rows that end on a 16-byte boundary take the TMA path
       const bool tma_ok = (s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0) && (s.N % 4 == 0);
       d.out_mode = tma_ok ? 2 : 3;
-      if (tma_ok) NERAF_TRY(get_tensor_map_2d(s.epi.out_f32, 4, s.M, s.N, s.epi.ld_f32, 32, 16, &d.tmOut));
+      if (tma_ok) NERAF_TRY(get_tensor_map_2d(s.epi.out_f32, 4, s.M, s.N, s.epi.ld_f32, 32, 32, &d.tmOut));
     }
     d.bias_vec = s.epi.bias && ((uintptr_t)s.epi.bias % 16) == 0;
     d.mask_out = (unsigned int*)s.epi.mask_out; d.gate_mask = (const unsigned int*)s.epi.gate_mask; d.ld_mask = s.epi.ld_mask;
     NERAF_REQUIRE(!(s.epi.mask_out || s.epi.gate_mask) || s.epi.ld_mask >= s.M, "mega_run: job %d: ld_mask < M", i);
-    NERAF_REQUIRE(!s.epi.mask_out || s.epi.act == NERAF_ACT_LEAKY, "mega_run: job %d: mask_out needs the LeakyReLU epilogue", i);
+    NERAF_REQUIRE(!s.epi.mask_out || (s.epi.act == NERAF_ACT_LEAKY && s.epi.out_bf16),
+                  "mega_run: job %d: mask_out needs the LeakyReLU epilogue and a bf16 output", i);
     NERAF_REQUIRE(!(s.epi.gate && s.epi.gate_mask), "mega_run: job %d: gate and gate_mask are exclusive", i);
     d.colsum = s.colsum;
   }

@@ -372,8 +372,10 @@ def test_gemm_jobs_sign_mask_gate(M, N, K, bn):
     j2.epi.out_f32, j2.epi.ld_f32 = out_g.data_ptr(), N + 1
     _run_jobs([j0, j1, j2], dev)
     z = A[:, :K].double() @ B[:, :K].double().t() + bias.double()
-    bits = (mask[:, :M].t().unsqueeze(-1) >> torch.arange(32, device=dev)) & 1        # (M, words, 32)
-    pos = bits.reshape(M, -1)[:, :N].bool()
+    cols = torch.arange(32, device=dev)
+    shifts = (cols & 1) * 16 + (cols >> 1)                  # bit i <- column 2i, bit 16 + i <- column 2i + 1
+    bits = (mask[:, :M].t().unsqueeze(-1) >> shifts) & 1                               # (M, words, 32), 1 = negative
+    pos = ~bits.reshape(M, -1)[:, :N].bool()
     sure = z.abs() > 1e-4                                   # away from zero the fp32 accumulator has the sign of z
     assert torch.all(pos[sure] == (z[sure] > 0))
     # the bf16 activation has the sign of its fp32 source, so both gates agree wherever x did not round to zero
