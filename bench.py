@@ -149,13 +149,25 @@ def workload_config(shape, args):
     return {"workload": f"{shape.name} FurnishedRoom-shaped audio-field training step (encode + MLP 1187->5096->2048->"
                         f"1024->1024->512->{shape.C}x{shape.F} + SC/log-STFT loss + backward), B={args.batch} columns/GPU, "
                         f"T={shape.T}", "batch_per_gpu": args.batch, "C": shape.C, "F": shape.F, "T": shape.T,
-            "precision": args.precision, "launch": "eager" if getattr(args, "no_graph", False) else "one CUDA graph per step (value); eager plugin calls (e2e)",
+            "precision": args.precision, "launch": "eager" if (getattr(args, "no_graph", False) or args.gpus > 1) else "one CUDA graph per step (value); eager plugin calls (e2e)",
             "l2": "flushed between timed steps (256 MiB write, outside the events)",
             "optimizer": "not in the timed region (metric is fwd+bwd; nerfstudio's Adam is outside the path)"}
 
 
 # ------------------------------------------------------------------------------------------------
+def arm_watchdog(seconds: float):
+    """Hard exit if the run wedges (a hung collective must not hold the GPU box until the driver's limit)."""
+    def fire():
+        sys.stderr.write(f"bench.py watchdog: no result after {seconds:.0f} s, exiting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def main():
+    arm_watchdog(900.0)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -222,7 +234,9 @@ def main():
     # `value`: the same step captured in one CUDA graph (GraphedTrainStep), inputs resident in HBM.
     # `e2e`  : the plugin calls a nerfstudio Trainer makes, eager, host batch in pinned memory.
     graphed = None
-    if not args.no_graph:
+    if not args.no_graph and world == 1:
+        # N > 1 times the eager launch sequence: a graph that captures the loss's NCCL all-reduce left the ranks
+        # hanging at teardown (measured at N = 2), and a hung bench is worse than a slower one
         graphed = GraphedTrainStep(model, dev_batch)
 
     def step_value(batch):
@@ -353,6 +367,7 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 NCU_SEQ=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:mega -s 14 -c 1 -f -o gpurun_out/fwd1 python tools/bench_jobs.py > gpurun_out/seq.log 2>&1; echo "rc=$?"
