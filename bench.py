@@ -149,8 +149,9 @@ def workload_config(shape, args):
     return {"workload": f"{shape.name} FurnishedRoom-shaped audio-field training step (encode + MLP 1187->5096->2048->"
                         f"1024->1024->512->{shape.C}x{shape.F} + SC/log-STFT loss + backward), B={args.batch} columns/GPU, "
                         f"T={shape.T}", "batch_per_gpu": args.batch, "C": shape.C, "F": shape.F, "T": shape.T,
-            "precision": args.precision, "launch": "eager" if (getattr(args, "no_graph", False) or args.gpus > 1) else "one CUDA graph per step (value); eager plugin calls (e2e)",
+            "precision": args.precision, "launch": "eager" if getattr(args, "no_graph", False) else ("one CUDA graph per step" if args.gpus == 1 else "two CUDA graphs per step + eager NCCL all-reduces") + " (value); eager plugin calls (e2e)",
             "l2": "flushed between timed steps (256 MiB write, outside the events)",
+            "grad_allreduce": f"{getattr(args, 'grad_dtype', 'fp32')} (one flat NCCL all-reduce, N > 1 only)",
             "optimizer": "not in the timed region (metric is fwd+bwd; nerfstudio's Adam is outside the path)"}
 
 
@@ -179,8 +180,12 @@ def main():
     ap.add_argument("--gl-rirs", type=int, default=2048, help="RIRs per Griffin-Lim launch (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
+    ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"],
+                    help="dtype of the gradient all-reduce for N > 1 (default: bf16 with --precision bf16, else fp32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.grad_dtype is None:
+        args.grad_dtype = "bf16" if args.precision == "bf16" else "fp32"
 
     if args.impl == "reference":
         run_reference(args)
@@ -234,16 +239,16 @@ def main():
     # `value`: the same step captured in one CUDA graph (GraphedTrainStep), inputs resident in HBM.
     # `e2e`  : the plugin calls a nerfstudio Trainer makes, eager, host batch in pinned memory.
     graphed = None
-    if not args.no_graph and world == 1:
-        # N > 1 times the eager launch sequence: a graph that captures the loss's NCCL all-reduce left the ranks
-        # hanging at teardown (measured at N = 2), and a hung bench is worse than a slower one
+    if not args.no_graph:
+        # N = 1: one graph around the autograd calls.  N > 1: two graphs (forward + loss sums | backward) with the
+        # loss's 32-byte all-reduce between them issued eagerly -- no NCCL call is ever captured
         graphed = GraphedTrainStep(model, dev_batch)
 
     def step_value(batch):
         if graphed is None:
             return step(batch)
         ld = graphed(batch)
-        reducer()
+        graphed.allreduce_grads(torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32)
         return ld
 
     def barrier():

@@ -188,21 +188,38 @@ class NeRAFAudioModel(nn.Module):
 
 
 class GraphedTrainStep:
-    """One CUDA graph for get_outputs -> get_loss_dict -> backward at a fixed batch size.
+    """CUDA-graphed get_outputs -> get_loss_dict -> backward at a fixed batch size.
 
-    At B=2048 the step is ~40 kernels of 5-60 us: launch latency and host dispatch are first-order, so the
-    whole launch sequence (bf16 re-pack of the current parameters, encodings, GEMMs on two streams, loss,
-    backward) is captured once and replayed.  ``step(batch)`` copies the batch dict (host or device
-    tensors) into static device buffers and replays; parameter gradients land in ``p.grad`` (static
-    tensors owned by the graph), the loss dict is returned as static 0-d tensors.
+    At B=2048 the step is a dozen kernels of 5-170 us: launch latency and host dispatch are first-order, so the
+    whole launch sequence (bf16 re-pack of the current parameters, encodings, the job-list GEMM launches, loss,
+    backward) is captured once and replayed.  ``step(batch)`` copies the batch dict (host or device tensors) into
+    static device buffers and replays; parameter gradients land in ``p.grad`` (static tensors owned by the graph),
+    the loss dict is returned as static 0-d tensors.
+
+    Single process: ONE graph around the autograd calls a Trainer makes.  Data parallel (``model.process_group``):
+    the spectral loss needs its four partial sums all-reduced between forward and backward, and a captured NCCL
+    collective proved fragile (ranks hung at teardown), so the step is TWO graphs built straight from the C-ABI
+    calls -- forward + loss sums | finalize + loss gradient + backward -- with the 32-byte all-reduce issued eagerly
+    between them; ``allreduce_grads()`` then sums the single flat gradient buffer across ranks.
     """
 
     def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3):
         self.model = model
         dev = model.device
         keys = ("time_query", "mic_pose", "source_pose", "rot", "data")
-        self.static = {k: example_batch[k].to(dev).contiguous().clone() for k in keys}
+        dtypes = {"time_query": torch.int64, "mic_pose": torch.float64, "source_pose": torch.float64,
+                  "rot": torch.float64, "data": torch.float32}
+        self.static = {k: example_batch[k].to(device=dev, dtype=dtypes[k]).contiguous().clone() for k in keys}
         self.params = [p for p in model.parameters() if p.requires_grad]
+        self.group = model.process_group
+        if self.group is None:
+            self._capture_autograd(warmup)
+        else:
+            self._capture_functional(warmup)
+
+    # ---- single process: autograd inside one graph ------------------------------------------------
+    def _capture_autograd(self, warmup: int):
+        model, dev = self.model, self.model.device
         prev = model.field.always_repack
         model.field.always_repack = True
 
@@ -227,10 +244,129 @@ class GraphedTrainStep:
             self.losses = run()
         model.field.always_repack = prev
 
+    # ---- data parallel: two graphs of direct library calls ------------------------------------------
+    def _capture_functional(self, warmup: int):
+        import ctypes as C
+        import torch.distributed as dist
+        model, dev = self.model, self.model.device
+        field = model.field
+        if field.precision != "bf16" and field.precision != "fp32":
+            raise ValueError("unknown precision")
+        if model.use_grid and not isinstance(model.resnet3d, ConstantGridFeature):
+            raise NotImplementedError("the two-graph data-parallel step needs a ConstantGridFeature grid producer "
+                                      "(an arbitrary ResNet3D is trained through autograd: use the eager calls)")
+        lib = _lib.lib()
+        weights, biases = field._param_lists()
+        grid_p = model.resnet3d.feature if model.use_grid else None
+        n_grid = 0 if grid_p is None else grid_p.numel()
+        dims = field._dims(n_grid)
+        prec = _lib.PRECISIONS[field.precision]
+        B = self.static["time_query"].shape[0]
+        pack_b, ws_b = C.c_size_t(), C.c_size_t()
+        _lib.check(lib.neraf_field_sizes(C.byref(dims), prec, B, C.byref(pack_b), C.byref(ws_b)))
+        pack = torch.empty(max(pack_b.value, 16), dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(ws_b.value, 16), dtype=torch.uint8, device=dev)
+        out = torch.empty(B, field.sound_rez, field.N_frequencies, dtype=torch.float32, device=dev)
+        dpred = torch.empty_like(out)
+        self.sums = torch.zeros(5, dtype=torch.float64, device=dev)
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        # flat gradient buffer: weights, then biases and dgrid back to back (single memset inside the library)
+        order = list(weights) + list(biases) + ([grid_p] if grid_p is not None else [])
+        sizes = [t.numel() for t in order]
+        self.flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views = [v.view_as(t) for v, t in zip(torch.split(self.flat_grad, sizes), order)]
+        for t, v in zip(order, views):
+            t.grad = v
+        n = len(weights)
+        dws, dbs = views[:n], views[n:2 * n]
+        dgrid = views[2 * n] if grid_p is not None else None
+        qs = _lib.Queries()
+        st = self.static
+        qs.batch = B
+        qs.time_query, qs.mic_pose = st["time_query"].data_ptr(), st["mic_pose"].data_ptr()
+        qs.source_pose, qs.rot, qs.aabb = st["source_pose"].data_ptr(), st["rot"].data_ptr(), model.aabb.data_ptr()
+        qs.time_denominator = float(model.max_len - 1.0)
+        qs.order = _lib.ORDER_TIME_MIC_SRC_ROT if model.use_grid else _lib.ORDER_MIC_SRC_TIME_ROT
+        qs.enc, qs.enc_ld = None, 0
+        crit = _lib.CRITERIA[model.criterion_name]
+        w_sc = 0.0 if model.criterion_name == "MSE" else 1e-1 * model.loss_factor
+        w_mag = model.loss_factor
+        n_local = out.numel()
+        n_total = n_local * dist.get_world_size(self.group)
+        w_arr, b_arr = _lib.ptr_array(weights), _lib.ptr_array(biases)
+        dw_arr, db_arr = _lib.ptr_array(dws), _lib.ptr_array(dbs)
+        self._keep = (pack, ws, out, dpred, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims)
+        self._grad_views = list(zip(order, views))
+
+        def forward_part():
+            s = _lib.stream_ptr(dev)
+            _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
+                                               pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
+                                               out.data_ptr(), 1, s))
+            _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
+                                                    self.sums.data_ptr(), 0, s))
+
+        def backward_part():
+            s = _lib.stream_ptr(dev)
+            _lib.check(lib.neraf_spectral_loss_finalize(self.sums.data_ptr(), n_total, crit, w_sc, w_mag,
+                                                        losses.data_ptr(), s))
+            _lib.check(lib.neraf_spectral_loss_backward(out.data_ptr(), st["data"].data_ptr(), n_local, n_total, crit,
+                                                        self.sums.data_ptr(), None, None, w_sc, w_mag,
+                                                        dpred.data_ptr(), s))
+            _lib.check(lib.neraf_field_backward(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
+                                                _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                dw_arr, db_arr, _lib.ptr(dgrid), None, 0, s))
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                forward_part()
+                dist.all_reduce(self.sums[:4], group=self.group)
+                backward_part()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph_fwd, self.graph_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fwd):
+            forward_part()
+        with torch.cuda.graph(self.graph_bwd):
+            backward_part()
+        if model.criterion_name == "MSE":
+            self.losses = {"audio_mse": losses[1]}
+        else:
+            self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
+
+    def allreduce_grads(self, dtype: torch.dtype = torch.float32) -> None:
+        """Data parallel: sum the flat gradient buffer over the ranks (one NCCL call).
+
+        ``dtype=torch.bfloat16`` halves the bytes on NVLink (40.9 MB instead of 81.7 MB): the buffer is rounded to
+        bf16, summed, and widened back -- two extra elementwise passes (~40 us) against ~half of the all-reduce time;
+        the rounding (2^-9 relative per element) is below the bf16 path's own gradient error.
+        """
+        if self.group is None:
+            return
+        import torch.distributed as dist
+        if dtype == torch.float32:
+            dist.all_reduce(self.flat_grad, group=self.group)
+            return
+        if getattr(self, "_flat_lowp", None) is None or self._flat_lowp.dtype != dtype:
+            self._flat_lowp = torch.empty_like(self.flat_grad, dtype=dtype)
+        self._flat_lowp.copy_(self.flat_grad)
+        dist.all_reduce(self._flat_lowp, group=self.group)
+        self.flat_grad.copy_(self._flat_lowp)
+
     def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         for k, dst in self.static.items():
             src = batch[k]
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
-        self.graph.replay()
+        if self.group is None:
+            self.graph.replay()
+        else:
+            import torch.distributed as dist
+            self.graph_fwd.replay()
+            dist.all_reduce(self.sums[:4], group=self.group)
+            self.graph_bwd.replay()
+            for t, v in self._grad_views:          # eager steps in between may have replaced .grad
+                t.grad = v
         return self.losses

@@ -184,3 +184,42 @@ def test_cpu_parameters_fail_loudly():
     f = NeRAFAudioSoundField(1187, 512, 1, 513)
     with pytest.raises(_lib.NerafError):
         f(torch.zeros(2, 1187))
+
+
+def test_two_graph_data_parallel_step_equals_autograd_step():
+    """GraphedTrainStep with a process group (two graphs of direct C-ABI calls, loss sums all-reduced between them)
+    == the eager autograd step, on a one-rank NCCL group."""
+    import socket
+    import torch.distributed as dist
+    from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioModel, NeRAFAudioModelConfig
+    dev = cuda()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        shape, B = syn.RAF, 384
+        cfg = NeRAFAudioModelConfig(dataset="RAF", precision="bf16")
+        model = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)),
+                                process_group=dist.group.WORLD)
+        model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
+        model = model.to(dev)
+        batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=1).items()}
+        params = [p for p in model.parameters() if p.requires_grad]
+        out = model.get_outputs(batch)
+        ld = model.get_loss_dict(out, batch)
+        sum(ld.values()).backward()
+        ref = [p.grad.clone() for p in params]
+        ref_loss = {k: float(v) for k, v in ld.items()}
+        step = GraphedTrainStep(model, batch)
+        for _ in range(2):
+            got = step(batch)
+            step.allreduce_grads()
+        torch.cuda.synchronize()
+        for k in ref_loss:
+            assert abs(float(got[k]) - ref_loss[k]) < 1e-5 * abs(ref_loss[k]), k
+        for p, r in zip(params, ref):
+            assert rel_fro(p.grad, r) < 1e-5            # same kernels, same order: only atomics differ
+    finally:
+        dist.destroy_process_group()
