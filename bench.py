@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="STFT columns per GPU per step (NeRAF_config.py:47)")
     ap.add_argument("--shape", default="RAF", choices=["RAF", "SoundSpaces"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--gl-rirs", type=int, default=2048, help="RIRs per Griffin-Lim launch (0 disables)")
+    ap.add_argument("--gl-rirs", type=int, default=2072, help="RIRs per Griffin-Lim launch (0 disables); 2072 = 14 per SM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
     ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"],
@@ -366,9 +366,45 @@ def main():
                                  "fused kernel keeps the state on chip, its compulsory HBM bytes are "
                                  f"{GL_COMPULSORY_BYTES_PER_RIR[shape.name]} B/RIR"}}
 
+        # ---- batched RIR rendering (BASELINE config 4, loudness-map workload): poses -> field query over all T time
+        # bins -> log->magnitude -> Griffin-Lim, one grid feature for all poses; rank-local poses, no collective
+        n_pose = 1024
+        gp = torch.Generator().manual_seed(200 + rank)
+        aabb = syn.default_aabb()
+        lo, hi = aabb[0] + 1.0, aabb[1] - 1.0
+        mic = (lo + (hi - lo) * torch.rand(n_pose, 3, generator=gp)).double().pin_memory()
+        src = ((lo + hi) / 2).double().reshape(1, 3)
+        rot = torch.tensor([[1.0, 0.5, 0.5]], dtype=torch.float64)
+        init_r = init[:n_pose] if n >= n_pose else torch.rand(n_pose, shape.C, shape.F, shape.T, dtype=torch.complex64, device=dev)
+        model.field.always_repack = False
+        for _ in range(2):
+            model.render_rirs(mic, src, rot, init_r)
+        barrier()
+        s.record()
+        for _ in range(k_gl):
+            wr = model.render_rirs(mic, src, rot, init_r).cpu()
+        e.record()
+        barrier()
+        r_ms = max_over_ranks(s.elapsed_time(e)) / k_gl
+        model.field.always_repack = True
+        line["render"] = {"metric": "rendered_rirs_per_sec", "value": n_pose * world / (r_ms * 1e-3), "unit": "RIR/s",
+                          "poses_per_call_per_gpu": n_pose, "queries_per_call_per_gpu": n_pose * shape.T, "ms_per_call": r_ms,
+                          "api": "NeRAFAudioModel.render_rirs(host poses) -> waveforms on the host (field forward over T bins "
+                                 "+ Griffin-Lim)", "d2h_bytes_per_call": wr.numel() * 4}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = time_cpu_baseline(shape, B, steps=10, warmup=2)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if args.gl_rirs > 0:
+            from oracle import griffinlim as ogl
+            n_cpu = 16
+            _, mag_c, init_c = syn.make_rirs(shape, n_cpu, seed=0)
+            t0 = time.perf_counter()
+            ogl.griffinlim(mag_c, init_c, shape.n_fft, shape.hop, shape.win)
+            dt = time.perf_counter() - t0
+            line["griffinlim"]["cpu_baseline"] = {"value": n_cpu / dt, "unit": "RIR/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                                  "sample": f"{n_cpu} {shape.name}-shaped RIRs, 32 iterations, oracle restatement of "
+                                                            f"torchaudio GriffinLim on torch {torch.__version__} CPU"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
