@@ -344,15 +344,12 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
       xin = j.epi.out_bf16; ldin = l.ldx[i];
     }
   }
-  if (side) {
-    NERAF_TRY(mega_run(jobs, 1, at(ws, l.counters), l.counters_bytes, stream));
-    NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
-    jobs[1].wait_job = -1;
-    for (int i = 2; i <= l.L; ++i) jobs[i].wait_job = i - 2;
-    NERAF_TRY(mega_run(jobs + 1, l.L, at(ws, l.counters), l.counters_bytes, stream));
-  } else {
-    NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream));
-  }
+  // ONE persistent launch for the whole MLP: row blocks of layer 2 start while layer 1 is still finishing others.
+  // (An earlier version launched layer 1 on its own so that it could start before the helper stream had re-packed
+  // the other layers; the second launch's fixed cost and the lost layer-1 / layer-2 overlap cost more than the
+  // few microseconds of waiting for the pack.)
+  if (side) NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
+  NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream));
   return NERAF_OK;
 }
 

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/trace.bin
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --no-cpu-baseline --steps 50 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+timeout 300 python bench.py --no-cpu-baseline --steps 50 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
