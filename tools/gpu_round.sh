@@ -1,11 +1,18 @@
 #!/bin/bash
-# One gpurun call: parity tests, bench line, ncu launch list.  Outputs under gpurun_out/.
+# One gpurun call for the record: parity tests, smoke, bench line, reference arm, ncu launch list, ncu --set full of the
+# job-list kernel.  Outputs under gpurun_out/ (copy what should be judged into profiles/).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
-tail -5 gpurun_out/smoke.log
+tail -4 gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --gl-rirs 256 > gpurun_out/bench_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; echo "ref rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --gl-rirs 148 > gpurun_out/bench_ncu.log 2>&1; echo "ncu list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:mega -s 6 -c 2 -f -o gpurun_out/mega python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --gl-rirs 0 > gpurun_out/ncu_mega.log 2>&1; echo "ncu full rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'], 'e2e_graphed', (d.get('e2e_graphed') or {}).get('value'), 'frac', d['roofline']['frac'], 'GL', d['griffinlim']['value'], d['griffinlim']['roofline']['frac'], 'render', d['render']['value'], 'cpu', d['cpu_baseline']['value'], d['clocks'])
+PY

@@ -4,10 +4,9 @@ import sys
 
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/launches.csv"
 rows = list(csv.DictReader([l for l in open(path) if not l.startswith("==")]))
-idx = [i for i, r in enumerate(rows) if "field_prep" in r["Kernel Name"] or "encode_kernel" in r["Kernel Name"]]
+# a training step starts with the re-pack of the parameters (render / inference calls do not re-pack)
+idx = [i for i, r in enumerate(rows) if "pack_list" in r["Kernel Name"]]
 a, b = idx[-2], idx[-1]
-while a > 0 and "pack_list" in rows[a - 1]["Kernel Name"]:
-    a -= 1; b -= 1
 tot = 0.0
 for r in rows[a:b]:
     v = float(r["Metric Value"].replace(",", "")) / 1e3
