@@ -109,8 +109,8 @@ typedef struct {
  * pack / repack: the bf16 operand copies (neraf_field_sizes bytes).  repack != 0 re-derives them from the
  *   current fp32 parameters inside this call (on a helper stream, overlapped with the encodings and the earlier
  *   layers) -- what a training step needs after every optimizer update; repack == 0 trusts the buffer.
- * The workspace afterwards holds what neraf_field_backward needs (the bf16 activations of every layer); `keep`
- * is accepted for ABI stability and ignored (nothing extra is stored for training any more). */
+ * keep != 0 (training): the workspace afterwards holds what neraf_field_backward needs (the bf16 activations of every
+ * layer and the sign bit masks of the LeakyReLU gates); keep == 0 (inference) skips the masks. */
 NERAF_API int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
                         const float* grid_feature, const float* const* weights,
                         const float* const* biases, void* pack, size_t pack_bytes, int repack,

@@ -1,8 +1,8 @@
 // Small HBM-bound helpers around the GEMMs of the acoustic field:
 //  * fp32 -> bf16 operand copies (row-major and transposed) for the tcgen05 path,
-//  * the batch-invariant grid-feature block of layer 1 hoisted out of the batch
-//    (NeRAF_model.py:557-560 expands the same 1024 values to every row):
-//    forward mat-vec, its gradient w.r.t. the grid feature and the rank-1 weight gradient,
+//  * the gradients of the batch-invariant grid-feature block of layer 1 hoisted out of the batch
+//    (NeRAF_model.py:557-560 expands the same 1024 values to every row): the rank-1 weight
+//    gradient and the gradient w.r.t. the grid feature (the forward mat-vec lives in encode.cu's prep kernel),
 //  * bias gradients (column sums), and the gradient through the 10*tanh heads (NeRAF_field.py:57-58).
 #include "common.cuh"
 #include "kernels.h"
@@ -109,84 +109,6 @@ int pack_list(PackList& L, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// y[n] = bias[n] + W[n, :K] . g       (one warp per output row, float4 loads when aligned)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grid_bias_kernel(const float* __restrict__ W, int64_t ldw,
-                                                        const float* __restrict__ bias, const float* __restrict__ g,
-                                                        int64_t N, int64_t K, float* __restrict__ y) {
-  const int64_t n = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
-  const int lane = threadIdx.x % 32;
-  if (n >= N) return;
-  const float* w = W + n * ldw;
-  float acc = 0.f;
-  for (int64_t k = lane; k < K; k += 32) acc = fmaf(__ldg(w + k), __ldg(g + k), acc);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) y[n] = acc + (bias ? bias[n] : 0.f);
-}
-
-int grid_bias(const float* W, int64_t ldw, const float* bias, const float* g, int64_t N, int64_t K, float* y,
-              cudaStream_t stream) {
-  if (N <= 0) return NERAF_OK;
-  grid_bias_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, stream>>>(W, ldw, bias, g, N, K, y);
-  NERAF_CHECK_LAUNCH("grid_bias_kernel");
-  return NERAF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// out[k] = sum_n W[n, k] * s[n]       (block: 32 columns x 32 row lanes over one slice of n; slices combined
-//                                      with one fp32 atomic per column and slice on a zeroed output)
-// ---------------------------------------------------------------------------------------------
-constexpr int kGridBwdSlices = 16;
-
-__global__ void __launch_bounds__(1024) grid_backward_kernel(const float* __restrict__ W, int64_t ldw,
-                                                             const float* __restrict__ s, int64_t N, int64_t K,
-                                                             float* __restrict__ out) {
-  __shared__ float red[32][33];
-  const int kx = threadIdx.x % 32, ny = threadIdx.x / 32;
-  const int64_t k = (int64_t)blockIdx.x * 32 + kx;
-  const int64_t per = (N + gridDim.y - 1) / gridDim.y;
-  const int64_t n_lo = (int64_t)blockIdx.y * per, n_hi = n_lo + per < N ? n_lo + per : N;
-  float acc = 0.f;
-  if (k < K)
-    for (int64_t n = n_lo + ny; n < n_hi; n += 32) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
-  red[ny][kx] = acc;
-  __syncthreads();
-  if (ny == 0 && k < K) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) t += red[i][kx];
-    atomicAdd(out + k, t);
-  }
-}
-
-int grid_backward(const float* W, int64_t ldw, const float* s, int64_t N, int64_t K, float* out, cudaStream_t stream) {
-  if (K <= 0) return NERAF_OK;
-  NERAF_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)K * 4, stream));
-  dim3 grid((unsigned)ceil_div(K, 32), kGridBwdSlices);
-  grid_backward_kernel<<<grid, 1024, 0, stream>>>(W, ldw, s, N, K, out);
-  NERAF_CHECK_LAUNCH("grid_backward_kernel");
-  return NERAF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// dW[n, k] = s[n] * g[k]
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) outer_product_kernel(const float* __restrict__ s, const float* __restrict__ g,
-                                                            int64_t N, int64_t K, float* __restrict__ dW, int64_t ldw) {
-  const int64_t n = blockIdx.x;
-  const float sn = __ldg(s + n);
-  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) dW[n * ldw + k] = sn * __ldg(g + k);
-}
-
-int outer_product(const float* s, const float* g, int64_t N, int64_t K, float* dW, int64_t ldw, cudaStream_t stream) {
-  if (N <= 0 || K <= 0) return NERAF_OK;
-  outer_product_kernel<<<(unsigned)N, 256, 0, stream>>>(s, g, N, K, dW, ldw);
-  NERAF_CHECK_LAUNCH("outer_product_kernel");
-  return NERAF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Both gradients of the hoisted grid block of layer 1 in ONE launch (they only share their input db1):
 //   blocks [0, n_outer)   dW1[n, :G] = db1[n] * g        (8 rows per block)
 //   the rest              dg[k]     += sum_n W1[n, k] db1[n]   (32 columns x one slice of n per block; dg pre-zeroed)
@@ -262,36 +184,6 @@ int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cud
   if (N <= 0) return NERAF_OK;
   colsum_f32_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, stream>>>(X, M, N, ld, out);
   NERAF_CHECK_LAUNCH("colsum_f32_kernel");
-  return NERAF_OK;
-}
-
-__global__ void __launch_bounds__(256) rowsum_bf16_kernel(const __nv_bfloat16* __restrict__ Xt, int64_t N, int64_t M,
-                                                          int64_t ld, float* __restrict__ out) {
-  const int64_t n = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
-  const int lane = threadIdx.x % 32;
-  if (n >= N) return;
-  const __nv_bfloat16* row = Xt + n * ld;
-  float acc = 0.f;
-  const int64_t M8 = (ld % 8 == 0) ? (M / 8) * 8 : 0;       // 16-byte vector part (rows are 16 B aligned when ld % 8 == 0)
-  for (int64_t m = lane * 8; m < M8; m += 256) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + m));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      acc += f.x + f.y;
-    }
-  }
-  for (int64_t m = M8 + lane; m < M; m += 32) acc += __bfloat162float(row[m]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) out[n] = acc;
-}
-
-int rowsum_bf16(const void* Xt, int64_t N, int64_t M, int64_t ld, float* out, cudaStream_t stream) {
-  if (N <= 0) return NERAF_OK;
-  rowsum_bf16_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, stream>>>((const __nv_bfloat16*)Xt, N, M, ld, out);
-  NERAF_CHECK_LAUNCH("rowsum_bf16_kernel");
   return NERAF_OK;
 }
 

@@ -256,7 +256,6 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
                                    const float* grid_feature, const float* const* weights, const float* const* biases,
                                    void* pack, size_t pack_bytes, int repack, void* ws, size_t ws_bytes, float* out,
                                    int keep, neraf_stream_t stream_) {
-  (void)keep;                                        // nothing extra is stored for backward any more
   cudaStream_t stream = (cudaStream_t)stream_;
   NERAF_REQUIRE(q, "field_forward: queries is null");
   Layout l;
@@ -340,7 +339,7 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
       j.epi.bias = i == 0 ? c1 : biases[i];
       j.epi.act = NERAF_ACT_LEAKY;
       j.epi.out_bf16 = at(ws, l.x[i]); j.epi.ld_bf16 = l.ldx[i];
-      j.epi.mask_out = at(ws, l.mask[i]); j.epi.ld_mask = l.ld_mask;       // LeakyReLU' gate of the backward pass
+      if (keep) { j.epi.mask_out = at(ws, l.mask[i]); j.epi.ld_mask = l.ld_mask; }   // LeakyReLU' gate of the backward pass
       xin = j.epi.out_bf16; ldin = l.ldx[i];
     }
   }

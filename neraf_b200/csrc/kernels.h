@@ -53,17 +53,8 @@ int pack_list(PackList& L, cudaStream_t stream);
 // dW[n*ldw + k] = s[n] * g[k] (dW may be null) and dg[k] = sum_n W[n*ldw + k] * s[n] (dg may be null) in one launch
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
                bool dg_is_zero, cudaStream_t stream);
-// y[n] = bias[n] + sum_k W[n*ldw + k] * g[k]   (the batch-invariant part of layer 1)
-int grid_bias(const float* W, int64_t ldw, const float* bias, const float* g, int64_t N, int64_t K, float* y,
-              cudaStream_t stream);
-// out[k] = sum_n W[n*ldw + k] * s[n]           (d loss / d grid feature)
-int grid_backward(const float* W, int64_t ldw, const float* s, int64_t N, int64_t K, float* out, cudaStream_t stream);
-// dW[n*ldw + k] = s[n] * g[k], k < K           (rank-1 weight gradient of the grid block)
-int outer_product(const float* s, const float* g, int64_t N, int64_t K, float* dW, int64_t ldw, cudaStream_t stream);
 // out[n] = sum_m X[m*ld + n]   fp32 row-major (M,N)
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
-// out[n] = sum_m Xt[n*ld + m]  bf16 transposed (N,M)
-int rowsum_bf16(const void* Xt, int64_t N, int64_t M, int64_t ld, float* out, cudaStream_t stream);
 // dz = dout * (10 - y^2/10): gradient through 10*tanh; outputs fp32 (M,N) and/or bf16 (M,N) row-major.
 // colsum (optional): per-head bias-gradient buffers, column n is added (atomics) to colsum[n / head_width][n % head_width]
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,

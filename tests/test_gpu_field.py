@@ -50,7 +50,7 @@ def _oracle_step(shape, sd, batch, g):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("shape,B", [(syn.RAF, 200), (syn.SOUNDSPACES, 136), (syn.RAF, 1)])
+@pytest.mark.parametrize("shape,B", [(syn.RAF, 200), (syn.SOUNDSPACES, 136), (syn.RAF, 1), (syn.RAF, 257), (syn.SOUNDSPACES, 513)])
 def test_train_step_matches_oracle(prec, shape, B):
     dev = cuda()
     sd = syn.make_state_dict(shape, seed=2)
@@ -223,3 +223,17 @@ def test_two_graph_data_parallel_step_equals_autograd_step():
             assert rel_fro(p.grad, r) < 1e-5            # same kernels, same order: only atomics differ
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_empty_batch(prec):
+    """B = 0: an empty (0, C, F) result, no launch, no error (the reference returns an empty tensor as well)."""
+    dev = cuda()
+    shape = syn.RAF
+    field = _make_field(shape, syn.make_state_dict(shape, seed=0), prec, dev)
+    z3 = torch.zeros(0, 3, dtype=torch.float64)
+    y = field.forward_queries(torch.zeros(0, dtype=torch.int64), z3, z3, z3, syn.default_aabb().to(dev), shape.T,
+                              syn.make_grid_feature(0).to(dev))
+    assert y.shape == (0, shape.C, shape.F)
+    h = field(torch.zeros(0, 1187, device=dev))
+    assert h.shape == (0, shape.C, shape.F)

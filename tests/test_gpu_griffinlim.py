@@ -131,3 +131,10 @@ def test_rejects_bad_arguments():
         gl(torch.rand(1, 100, 10, device=dev))               # wrong number of bins
     with pytest.raises(_lib.NerafError):
         gl(torch.rand(1, 257, 10))                           # CPU tensor: no fallback
+
+
+def test_no_signals_is_a_no_op():
+    dev = torch.device("cuda:0")
+    gl = GriffinLim(n_fft=1024, win_length=512, hop_length=256, power=1)
+    out = gl(torch.zeros(0, 1, 513, 60, device=dev))
+    assert out.shape == (0, 1, 256 * 59)
