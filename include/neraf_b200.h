@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 2
+#define NERAF_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))
@@ -128,6 +128,35 @@ NERAF_API int neraf_field_backward(const neraf_field_dims* dims, int precision, 
                          float* const* dweights, float* const* dbiases, float* dgrid, float* denc,
                          int64_t denc_ld, neraf_stream_t stream);
 
+/* Data-parallel backward with the gradient all-reduce FUSED into the weight-gradient GEMMs (the reference refuses
+ * world_size > 1, NeRAF_pipeline.py:154-155).
+ *   mc != NULL : the weight-gradient tiles are not stored but added into every rank's copy of a symmetric gradient
+ *                buffer through its multicast alias (NVLS multimem.red in the epilogue; bf16 path only).  Every
+ *                dweights[l] must lie inside [local_base, local_base + bytes); the caller zeroes that buffer on EVERY
+ *                rank before ANY rank starts this call (e.g. memset, then the loss's all-reduce), and makes the ranks
+ *                meet again afterwards (e.g. the bias all-reduce) before reading the sums.  dbiases / dgrid / denc
+ *                stay local sums, to be all-reduced by the caller.
+ *   defer_grid_grads != 0 : skip the two gradients of the hoisted grid block (dW1[:, :n_grid] = db1 (x) g and dgrid =
+ *                W1[:, :n_grid]^T db1).  Both are LINEAR in db1 and g is replicated, so under data parallelism they are
+ *                formed once from the all-reduced db1 by neraf_field_grid_grads -- 20.9 MB less to all-reduce. */
+typedef struct {
+  const void* local_base;   /* this device's address of the symmetric buffer                         */
+  void* multicast_base;     /* multicast address of the same buffer (cuMulticast* / torch symm_mem) */
+  size_t bytes;
+} neraf_multicast;
+
+NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t batch, const float* dout,
+                            const float* out, const float* grid_feature, const float* const* weights,
+                            const void* pack, void* workspace, size_t workspace_bytes,
+                            float* const* dweights, float* const* dbiases, float* dgrid, float* denc,
+                            int64_t denc_ld, const neraf_multicast* mc, int defer_grid_grads,
+                            neraf_stream_t stream);
+
+/* dweight0[n, k] = dbias0[n] * grid_feature[k] (k < n_grid; row stride n_grid + n_enc; may be NULL) and
+ * dgrid[k] = sum_n weight0[n, k] * dbias0[n] (may be NULL): the deferred part of neraf_field_backward_dp. */
+NERAF_API int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
+                           const float* dbias0, float* dweight0, float* dgrid, neraf_stream_t stream);
+
 /* Encodings only (NeRFEncoding x3 + SHEncoding + normalisation/zeroing, NeRAF_model.py:533-551):
  * enc_out dev fp32 (B, 163) row stride ld. */
 NERAF_API int neraf_encode_queries(const neraf_queries* q, float* enc_out, int64_t ld, neraf_stream_t stream);
@@ -218,6 +247,11 @@ typedef struct {
   void* mask_out;
   const void* gate_mask;
   int64_t ld_mask;
+  /* job-list kernel only: multicast (NVLS) alias of out_f32 -- same layout, address from cuMulticast* / torch
+   * symmetric memory.  When set, the results are not stored but ADDED into every GPU's copy of the buffer by the
+   * NVSwitch (multimem.red.add.f32): a gradient all-reduce fused into the weight-gradient GEMM.  The buffers must be
+   * zero on every rank before any rank's launch starts. */
+  void* out_f32_multicast;
 } neraf_gemm_epilogue;
 
 NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -250,6 +284,7 @@ typedef struct {
   int32_t bn;
   int32_t wait_job;
   int32_t wait_all;
+  int32_t merge_next;   /* 1: interleave this job's tiles with those of the NEXT job (which must not wait for this one) */
   neraf_gemm_epilogue epi;
   float* colsum;
 } neraf_gemm_job;

@@ -44,14 +44,19 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("gate", C.c_void_p), ("ldg", C.c_int64),
                 ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64), ("out_bf16_t", C.c_void_p), ("ld_t", C.c_int64),
                 ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("accumulate_f32", C.c_int32),
-                ("mask_out", C.c_void_p), ("gate_mask", C.c_void_p), ("ld_mask", C.c_int64)]
+                ("mask_out", C.c_void_p), ("gate_mask", C.c_void_p), ("ld_mask", C.c_int64),
+                ("out_f32_multicast", C.c_void_p)]
 
 
 class GemmJob(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("A", C.c_void_p), ("lda", C.c_int64),
                 ("B", C.c_void_p), ("ldb", C.c_int64), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("b_static", C.c_int32),
                 ("bn", C.c_int32),
-                ("wait_job", C.c_int32), ("wait_all", C.c_int32), ("epi", GemmEpilogue), ("colsum", C.c_void_p)]
+                ("wait_job", C.c_int32), ("wait_all", C.c_int32), ("merge_next", C.c_int32), ("epi", GemmEpilogue), ("colsum", C.c_void_p)]
+
+
+class Multicast(C.Structure):
+    _fields_ = [("local_base", C.c_void_p), ("multicast_base", C.c_void_p), ("bytes", C.c_size_t)]
 
 
 class GlParams(C.Structure):
@@ -74,6 +79,9 @@ SIGNATURES = {
                                        _vp, _sz, _vp, _i32, _vp]),
     "neraf_field_backward": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
                                         _vp, _vp, _i64, _vp]),
+    "neraf_field_backward_dp": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
+                                           _vp, _vp, _i64, C.POINTER(Multicast), _i32, _vp]),
+    "neraf_field_grid_grads": (C.c_int, [C.POINTER(FieldDims), _vp, _vp, _vp, _vp, _vp, _vp]),
     "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),
     "neraf_spectral_loss_sums": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
     "neraf_spectral_loss_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp]),

@@ -352,12 +352,11 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
   return NERAF_OK;
 }
 
-extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision, int64_t B, const float* dout,
-                                    const float* out, const float* grid_feature, const float* const* weights,
-                                    const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
-                                    float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
-                                    neraf_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int field_backward_impl(const neraf_field_dims* dims, int precision, int64_t B, const float* dout,
+                               const float* out, const float* grid_feature, const float* const* weights,
+                               const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
+                               float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
+                               const neraf_multicast* mc, int defer_grid_grads, cudaStream_t stream) {
   Layout l;
   NERAF_TRY(make_layout(dims, precision, B, &l));
   if (B == 0) return NERAF_OK;
@@ -375,6 +374,8 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
   const int last = l.L - 1;
   const int64_t ldw0 = l.G + l.E;
 
+  if (!bf && (mc || defer_grid_grads))
+    return set_error(NERAF_ERR_UNSUPPORTED, "field_backward_dp: the fused all-reduce exists for the bf16 path only");
   if (!bf) {
     float* dzh = reinterpret_cast<float*>(at(ws, l.dzh));
     NERAF_TRY(head_backward(dout, out, B, l.CF, dzh, l.CF, nullptr, 0, nullptr, 0, stream));
@@ -426,7 +427,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
       float* end = start + (i < l.L ? l.n[i] : l.F);
       int j = i + 1;
       while (j < nb && dbiases[j] == end) { end += j < l.L ? l.n[j] : l.F; ++j; }
-      if (j == nb && dgrid && l.G > 0 && dgrid == end) { end += l.G; dgrid_zeroed = true; }
+      if (j == nb && dgrid && l.G > 0 && dgrid == end && !defer_grid_grads) { end += l.G; dgrid_zeroed = true; }
       NERAF_CHECK_CUDA(cudaMemsetAsync(start, 0, (size_t)(end - start) * 4, stream));
       i = j;
     }
@@ -435,6 +436,18 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
   NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream));
   bool heads_contiguous = true;                      // the C head gradients form one (C*F, W) matrix?
   for (int c = 1; c < l.C; ++c) heads_contiguous = heads_contiguous && dweights[l.L + c] == dweights[l.L] + (size_t)c * l.F * l.W;
+  // Fused all-reduce (data parallel): weight gradients are not stored but added into every rank's copy of the
+  // caller's symmetric gradient buffer through its multicast alias (NVLS multimem.red in the GEMM epilogue).
+  auto mc_alias = [&](float* p, void** out_mc) -> int {
+    *out_mc = nullptr;
+    if (!mc) return NERAF_OK;
+    const uintptr_t lo = (uintptr_t)mc->local_base, a = (uintptr_t)p;
+    NERAF_REQUIRE(mc->multicast_base && a >= lo && a < lo + mc->bytes,
+                  "field_backward_dp: a weight gradient lies outside the symmetric buffer");
+    *out_mc = reinterpret_cast<uint8_t*>(mc->multicast_base) + (a - lo);
+    return NERAF_OK;
+  };
+  NERAF_REQUIRE(!mc || heads_contiguous, "field_backward_dp: head gradients must be contiguous");
   MegaJob jobs[NERAF_MEGA_MAX_JOBS];
   int nj = 0;
   int producer = nj;
@@ -451,6 +464,7 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
     j.wait_all = 0;
     j.epi.out_f32 = heads_contiguous ? dweights[l.L] : reinterpret_cast<float*>(at(ws, l.dwh));
     j.epi.ld_f32 = l.W;
+    NERAF_TRY(mc_alias(j.epi.out_f32, &j.epi.out_f32_multicast));
   }
   for (int i = last; i >= 0; --i) {
     const int dz_producer = producer;                  // job that writes dZ_i
@@ -461,14 +475,20 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
       j.epi.gate_mask = at(ws, l.mask[i - 1]); j.epi.ld_mask = l.ld_mask;
       j.epi.out_bf16 = at(ws, l.dz[i - 1]); j.epi.ld_bf16 = l.ldx[i - 1];
       j.colsum = dbiases[i - 1];
+      // Fused all-reduce: the tiles of dW_i push their results over NVLink, the tiles of this dgrad job do not, and
+      // both only need dZ_i -- interleaved, the link drains behind the dgrad tiles instead of throttling every CTA
+      // pair at once (the largest pair, dgrad 2->1 / dW_2, is 70 % of the bytes and sits at the end of the backward).
+      if (mc) j.merge_next = 1;
     }
     MegaJob& w = jobs[nj++];                           // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
     if (i > 0) {
       w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
       w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
+      NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
     } else {
       w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
       w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
+      NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
       if (denc) {
         MegaJob& e = jobs[nj++];
         e = make_dgrad_job(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.w[0]), l.ldw[0], dz_producer);
@@ -481,7 +501,34 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
     for (int c = 0; c < l.C; ++c)
       NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,
                                        cudaMemcpyDeviceToDevice, stream));
-  if (l.G > 0)
+  if (l.G > 0 && !defer_grid_grads)
     NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, dgrid_zeroed, stream));
   return NERAF_OK;
+}
+
+extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision, int64_t B, const float* dout,
+                                    const float* out, const float* grid_feature, const float* const* weights,
+                                    const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
+                                    float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
+                                    neraf_stream_t stream) {
+  return field_backward_impl(dims, precision, B, dout, out, grid_feature, weights, pack, ws, ws_bytes, dweights, dbiases,
+                             dgrid, denc, denc_ld, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t B, const float* dout,
+                                       const float* out, const float* grid_feature, const float* const* weights,
+                                       const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
+                                       float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
+                                       const neraf_multicast* mc, int defer_grid_grads, neraf_stream_t stream) {
+  return field_backward_impl(dims, precision, B, dout, out, grid_feature, weights, pack, ws, ws_bytes, dweights, dbiases,
+                             dgrid, denc, denc_ld, mc, defer_grid_grads, (cudaStream_t)stream);
+}
+
+extern "C" int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
+                                      const float* dbias0, float* dweight0, float* dgrid, neraf_stream_t stream) {
+  NERAF_REQUIRE(dims && dims->n_trunk >= 1, "field_grid_grads: dims is null");
+  if (dims->n_grid <= 0) return NERAF_OK;
+  NERAF_REQUIRE(grid_feature && weight0 && dbias0 && (dweight0 || dgrid), "field_grid_grads: null pointer");
+  return grid_grads(dbias0, grid_feature, weight0, (int64_t)dims->n_grid + dims->n_enc, dims->trunk[0], dims->n_grid, dweight0,
+                    dgrid, false, (cudaStream_t)stream);
 }

@@ -65,9 +65,12 @@ struct alignas(64) DeviceJob {
   CUtensorMap tmA, tmB, tmOut, tmOut1;   // tmOut1: single-chunk (32-column) bf16 stores
   int M, N, K, bn;
   int tile_start, num_m, num_n, cnt_off;
+  int merged, merge_na, merge_total;   // merged == 2: second job of an interleaved pair (first = previous job, na tiles)
   int wait_job, wait_all, wait_target, wait_nrb, wait_cnt_off;
   int act, a_mn, b_mn, b_static;
-  int out_mode;                    // 0 none, 1 bf16 (TMA), 2 fp32 (TMA), 3 fp32 (rows not 16-byte tileable: smem transpose)
+  int out_mode;                    // 0 none, 1 bf16 (TMA), 2 fp32 (TMA), 3 fp32 (rows not 16-byte tileable: smem transpose),
+                                   // 4 fp32 reduced into every GPU's copy through the NVSwitch (multimem.red on out_mc)
+  float* out_mc;
   int bias_vec;                    // bias may be read with 16-byte loads
   unsigned int* mask_out; const unsigned int* gate_mask; long long ld_mask;
   const float* bias;
@@ -171,6 +174,27 @@ __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, float (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Tile index -> (job, tile of that job).  Jobs own contiguous index ranges, except an interleaved pair (A, B): both
+// start at the same index and their tiles alternate in proportion na : nb over the merged range, so that e.g. the
+// weight-gradient tiles whose epilogues push gradients over NVLink are mixed with tiles that do not.
+__device__ __forceinline__ const DeviceJob& locate_tile(const MegaParams& P, int tile, int& j, int& local) {
+  while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
+  const DeviceJob& J = P.jobs[j];
+  if (J.merged != 2) {
+    local = tile - J.tile_start;
+    return J;
+  }
+  const long long m = tile - J.tile_start;
+  const int a_before = (int)((m * J.merge_na) / J.merge_total);
+  const int a_after = (int)(((m + 1) * J.merge_na) / J.merge_total);
+  if (a_after > a_before) {
+    local = a_before;
+    return P.jobs[j - 1];
+  }
+  local = (int)m - a_before;
+  return J;
+}
+
 __device__ __forceinline__ float gate_factor(float x) { return x > 0.f ? 1.f : kLeakySlope; }
 
 __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) {
@@ -214,9 +238,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
     int j = 0;
     uint32_t done_jobs = 0;                                      // bit i: every row block of job i is known complete
     for (int tile = unit; tile < P.num_tiles; tile += num_units) {
-      while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
-      const DeviceJob& J = P.jobs[j];
-      const int local = tile - J.tile_start;
+      int local;
+      const DeviceJob& J = locate_tile(P, tile, j, local);
       const int mt = local / J.num_n, nt = local % J.num_n;          // row-block major: a row block completes early
       const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
       const int b_rows = J.bn / CG;
@@ -315,8 +338,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       int stage = 0; uint32_t phase = 0;
       int it = 0, j = 0;
       for (int tile = unit; tile < P.num_tiles; tile += num_units, ++it) {
-        while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
-        const DeviceJob& J = P.jobs[j];
+        int local;
+        const DeviceJob& J = locate_tile(P, tile, j, local);
         const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
         const bool a_mn = J.a_mn != 0, b_mn = J.b_mn != 0;
         const uint32_t idesc = make_idesc(BLOCK_M * CG, J.bn) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
@@ -355,11 +378,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
     uint8_t* wbuf = out_buf + (warp - 2) * MEGA_OUT_BYTES;
     float* wbuf_f = reinterpret_cast<float*>(wbuf);
     float* bias_s = bias_buf + (warp - 2) * (MEGA_BIAS_BYTES / 4);
+    bool used_multicast = false;
     int it = 0, j = 0;
     for (int tile = unit; tile < P.num_tiles; tile += num_units, ++it) {
-      while (j + 1 < P.num_jobs && tile >= P.jobs[j + 1].tile_start) ++j;
-      const DeviceJob& J = P.jobs[j];
-      const int local = tile - J.tile_start;
+      int local;
+      const DeviceJob& J = locate_tile(P, tile, j, local);
       const int mt = local / J.num_n, nt = local % J.num_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -574,6 +597,49 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
             }
           }
         }
+        else if (out_mode == 4) {
+          // Fused all-reduce: the tile is ADDED into every rank's copy of the gradient by the NVSwitch
+          // (multimem.red on the multicast alias of the output; NVLS).  Same shared-memory transpose as above so
+          // that one instruction covers 128 contiguous bytes of a row.
+          float* out_mc = J.out_mc;
+          const long long ld_f32 = J.ld_f32;
+          const int rows = M - m_base < 32 ? M - m_base : 32;
+          const bool mc_vec = (ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_mc) & 15) == 0);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h < nch) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) wbuf_f[lane * 32 + (q ^ lane)] = v[32 * h + q];
+              __syncwarp();
+              const int nbase = n0 + 32 * h;
+              if (mc_vec && nbase + 32 <= N) {
+                // 16 bytes per lane: one instruction covers 4 rows x 128 contiguous bytes
+                const int c4 = 4 * (lane & 7);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int r = i * 4 + (lane >> 3);
+                  if (r < rows) {
+                    const float* src = wbuf_f + r * 32;
+                    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                     out_mc + (long long)(m_base + r) * ld_f32 + nbase + c4),
+                                 "f"(src[(c4 + 0) ^ r]), "f"(src[(c4 + 1) ^ r]), "f"(src[(c4 + 2) ^ r]), "f"(src[(c4 + 3) ^ r])
+                                 : "memory");
+                  }
+                }
+              } else {
+                const int n = nbase + lane;
+                if (n < N) {
+#pragma unroll 4
+                  for (int r = 0; r < rows; ++r)
+                    asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(out_mc + (long long)(m_base + r) * ld_f32 + n),
+                                 "f"(wbuf_f[r * 32 + (lane ^ r)])
+                                 : "memory");
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
         if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_STORE);
         // ---- bias gradient: column sums of the fp32 values (destroys v)
         if (colsum != nullptr) {
@@ -595,11 +661,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       // Publish the tile: lane 0 waits until its TMA stores have been performed, the warp's plain stores (bit mask,
       // unaligned fp32 rows, column-sum atomics) are ordered before lane 0 by the warp barrier, and the counter
       // update itself is a gpu-scope release (one fence instead of a full membar in every lane).
-      if (lane == 0 && out_mode != 0 && out_mode != 3) { bulk_wait_all0(); fence_proxy_async_all(); }
+      if (lane == 0 && (out_mode == 1 || out_mode == 2)) { bulk_wait_all0(); fence_proxy_async_all(); }
+      if (out_mode == 4) used_multicast = true;      // fenced once, at the end of the kernel
       __syncwarp();
       if (tracer) { stamp_clock(P.trace, tile, TR_CK_FENCE); stamp(P.trace, tile, TR_EPI_DONE); }
       if (lane == 0) red_release_add(P.counters + J.cnt_off + mt, 1u);   // ... before the row block's progress is (16 arrivals per tile)
     }
+    // multimem.red reductions are fire-and-forget while the kernel runs (the NVLink queue drains behind the remaining
+    // tiles); one system-scope fence per warp makes them performed before the kernel can end
+    if (used_multicast) __threadfence_system();
   }
 
   tc_fence_before();
@@ -642,7 +712,17 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     d.a_mn = s.a_mn; d.b_mn = s.b_mn; d.b_static = s.b_static;
     d.M = (int)s.M; d.N = (int)s.N; d.K = (int)s.K; d.bn = s.bn;
     d.num_m = (int)ceil_div(s.M, 256); d.num_n = (int)ceil_div(s.N, s.bn);
-    d.tile_start = tile; tile += d.num_m * d.num_n;
+    d.merged = 0; d.merge_na = 0; d.merge_total = 0;
+    if (i > 0 && jobs[i - 1].merge_next) {             // second job of an interleaved pair: shares the range of the first
+      NERAF_REQUIRE(s.wait_job != i - 1 && !s.merge_next, "mega_run: job %d cannot be interleaved with the job it waits for", i);
+      DeviceJob& a = P.jobs[i - 1];
+      const int na = a.num_m * a.num_n, nb = d.num_m * d.num_n;
+      a.merged = 1;
+      d.merged = 2; d.merge_na = na; d.merge_total = na + nb;
+      d.tile_start = a.tile_start; tile = a.tile_start + na + nb;
+    } else {
+      d.tile_start = tile; tile += d.num_m * d.num_n;
+    }
     d.cnt_off = cnt; cnt_off[i] = cnt; nrb[i] = d.num_m; num_n[i] = d.num_n; cnt += d.num_m;
     d.wait_job = s.wait_job; d.wait_all = s.wait_all;
     if (s.wait_job >= 0) {
@@ -666,6 +746,8 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
       // TMA stores clip with 16-byte granularity: only rows that end on a 16-byte boundary take the TMA path
       const bool tma_ok = (s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0) && (s.N % 4 == 0);
       d.out_mode = tma_ok ? 2 : 3;
+      d.out_mc = (float*)s.epi.out_f32_multicast;
+      if (d.out_mc) d.out_mode = 4;
       if (tma_ok) NERAF_TRY(get_tensor_map_2d(s.epi.out_f32, 4, s.M, s.N, s.epi.ld_f32, 32, 32, &d.tmOut));
     }
     d.bias_vec = s.epi.bias && ((uintptr_t)s.epi.bias % 16) == 0;

@@ -228,8 +228,15 @@ class GraphedTrainStep:
     between them; ``allreduce_grads()`` then sums the single flat gradient buffer across ranks.
     """
 
-    def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3):
+    def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3,
+                 fused_allreduce: bool = False):
         self.model = model
+        # Data parallel, experimental: NVLS multimem.red in the weight-gradient epilogues (the all-reduce fused into the
+        # GEMMs over torch symmetric memory).  Numerically identical to backward + NCCL (tools/check_dp_nvls.py) and as
+        # fast at 2 GPUs, but multimem.red delivers every rank's addend to every rank (inbound traffic grows with the
+        # world size) and the pushes throttle the epilogues, so it is off by default: see DESIGN.md section 8.
+        self.fused_allreduce = fused_allreduce
+        self.nvls = False
         dev = model.device
         keys = ("time_query", "mic_pose", "source_pose", "rot", "data")
         dtypes = {"time_query": torch.int64, "mic_pose": torch.float64, "source_pose": torch.float64,
@@ -298,7 +305,23 @@ class GraphedTrainStep:
         # flat gradient buffer: weights, then biases and dgrid back to back (single memset inside the library)
         order = list(weights) + list(biases) + ([grid_p] if grid_p is not None else [])
         sizes = [t.numel() for t in order]
-        self.flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # Fused all-reduce: the flat buffer lives in symmetric memory and the weight-gradient GEMMs add their tiles
+        # into every rank's copy through its multicast alias.  Without NVLS (no multicast pointer) the buffer is plain
+        # memory and allreduce_grads() falls back to one NCCL all-reduce.
+        self.flat_grad, mc_ptr = None, 0
+        if self.fused_allreduce and field.precision == "bf16" and dist.get_world_size(self.group) > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.flat_grad = symm_mem.empty(sum(sizes), dtype=torch.float32, device=dev)
+                self._symm = symm_mem.rendezvous(self.flat_grad, self.group.group_name)
+                mc_ptr = int(self._symm.multicast_ptr or 0)
+            except Exception:                      # symmetric memory unavailable: plain buffer + NCCL
+                self.flat_grad, mc_ptr = None, 0
+        if self.flat_grad is None or mc_ptr == 0:
+            self.flat_grad, mc_ptr = torch.zeros(sum(sizes), dtype=torch.float32, device=dev), 0
+        self.nvls = mc_ptr != 0
+        self.flat_grad.zero_()
+        n_weight_elems = sum(t.numel() for t in weights)
         views = [v.view_as(t) for v, t in zip(torch.split(self.flat_grad, sizes), order)]
         for t, v in zip(order, views):
             t.grad = v
@@ -323,13 +346,28 @@ class GraphedTrainStep:
         self._keep = (pack, ws, out, dpred, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims)
         self._grad_views = list(zip(order, views))
 
+        mc = _lib.Multicast()
+        mc.local_base, mc.multicast_base, mc.bytes = self.flat_grad.data_ptr(), mc_ptr, self.flat_grad.numel() * 4
+        weight_region = self.flat_grad[:n_weight_elems]
+        self._bias_region = self.flat_grad[n_weight_elems:n_weight_elems + sum(b.numel() for b in biases)]
+        zero_stream = torch.cuda.Stream(device=dev) if self.nvls else None
+
         def forward_part():
+            if self.nvls:
+                # every rank's copy of the weight gradients must be zero before ANY rank's backward adds into it: the
+                # memset runs beside the forward, the loss's all-reduce between the two graphs is the rendezvous
+                cur = torch.cuda.current_stream(dev)
+                zero_stream.wait_stream(cur)
+                with torch.cuda.stream(zero_stream):
+                    weight_region.zero_()
             s = _lib.stream_ptr(dev)
             _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
                                                pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
                                                out.data_ptr(), 1, s))
             _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
                                                     self.sums.data_ptr(), 0, s))
+            if self.nvls:
+                torch.cuda.current_stream(dev).wait_stream(zero_stream)
 
         def backward_part():
             s = _lib.stream_ptr(dev)
@@ -338,9 +376,21 @@ class GraphedTrainStep:
             _lib.check(lib.neraf_spectral_loss_backward(out.data_ptr(), st["data"].data_ptr(), n_local, n_total, crit,
                                                         self.sums.data_ptr(), None, None, w_sc, w_mag,
                                                         dpred.data_ptr(), s))
-            _lib.check(lib.neraf_field_backward(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
-                                                _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                dw_arr, db_arr, _lib.ptr(dgrid), None, 0, s))
+            if self.nvls:
+                _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
+                                                       _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                       dw_arr, db_arr, _lib.ptr(dgrid), None, 0, C.byref(mc), 1, s))
+            else:
+                _lib.check(lib.neraf_field_backward(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
+                                                    _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    dw_arr, db_arr, _lib.ptr(dgrid), None, 0, s))
+
+        def grid_part():          # after the bias all-reduce: the grid-block gradients from the REDUCED db1
+            if self.nvls and grid_p is not None:
+                _lib.check(lib.neraf_field_grid_grads(C.byref(dims), grid_p.data_ptr(), weights[0].data_ptr(),
+                                                      dbs[0].data_ptr(), dws[0].data_ptr(), _lib.ptr(dgrid),
+                                                      _lib.stream_ptr(dev)))
+        self._grid_part = grid_part
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -349,6 +399,9 @@ class GraphedTrainStep:
                 forward_part()
                 dist.all_reduce(self.sums[:4], group=self.group)
                 backward_part()
+                if self.nvls:
+                    dist.all_reduce(self._bias_region, group=self.group)
+                    grid_part()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph_fwd, self.graph_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -371,6 +424,13 @@ class GraphedTrainStep:
         if self.group is None:
             return
         import torch.distributed as dist
+        if self.nvls:
+            # the weight gradients were summed by the NVSwitch inside the backward GEMMs; what is left is the 40 KB of
+            # bias gradients (this collective is also where the ranks meet after their reductions were issued) and
+            # the grid-block gradients, linear in the now-reduced db1
+            dist.all_reduce(self._bias_region, group=self.group)
+            self._grid_part()
+            return
         if dtype == torch.float32:
             dist.all_reduce(self.flat_grad, group=self.group)
             return

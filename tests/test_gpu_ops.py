@@ -413,6 +413,30 @@ def test_gemm_jobs_dependency_chain_matches_sequential():
     assert rel_fro(dw, x2.double().t() @ x1.double()) < 2e-5
 
 
+def test_gemm_jobs_interleaved_pair():
+    """merge_next: the tiles of two independent jobs alternate in the tile list; results are those of the plain list."""
+    dev = cuda()
+    g = torch.Generator().manual_seed(11)
+    M, K = 1024, 256
+    A = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
+    B1 = (torch.randn(1000, K, generator=g) / 16).to(dev).to(torch.bfloat16)
+    B2 = (torch.randn(328, K, generator=g) / 16).to(dev).to(torch.bfloat16)
+    x0 = torch.zeros(M, 512, dtype=torch.bfloat16, device=dev)
+    W0 = (torch.randn(512, K, generator=g) / 16).to(dev).to(torch.bfloat16)
+    o1, o2 = torch.zeros(M, 1000, device=dev), torch.zeros(M, 328, device=dev)
+    j0 = _job(M, 512, K, A, W0, 128); j0.epi.out_bf16, j0.epi.ld_bf16 = x0.data_ptr(), 512
+    j1 = _job(M, 1000, K, A, B1, 128, wait_job=0); j1.epi.out_f32, j1.epi.ld_f32 = o1.data_ptr(), 1000
+    j1.merge_next = 1
+    j2 = _job(M, 328, K, A, B2, 64, wait_job=0, wait_all=1); j2.epi.out_f32, j2.epi.ld_f32 = o2.data_ptr(), 328
+    _run_jobs([j0, j1, j2], dev)
+    assert rel_fro(o1, A.double() @ B1.double().t()) < 2e-5
+    assert rel_fro(o2, A.double() @ B2.double().t()) < 2e-5
+    assert rel_fro(x0, A.double() @ W0.double().t()) < 4e-3
+    j2.wait_job = 1                                   # the second job of a pair must not wait for the first
+    with pytest.raises(_lib.NerafError):
+        _run_jobs([j0, j1, j2], dev)
+
+
 def test_gemm_jobs_validation():
     dev = cuda()
     A = torch.zeros(64, 64, dtype=torch.bfloat16, device=dev)

@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/probe_symm.py 2>&1 | grep -v "^\*\|OMP_NUM" | tail -12
