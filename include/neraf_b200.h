@@ -138,7 +138,11 @@ NERAF_API int neraf_field_backward(const neraf_field_dims* dims, int precision, 
  *                stay local sums, to be all-reduced by the caller.
  *   defer_grid_grads != 0 : skip the two gradients of the hoisted grid block (dW1[:, :n_grid] = db1 (x) g and dgrid =
  *                W1[:, :n_grid]^T db1).  Both are LINEAR in db1 and g is replicated, so under data parallelism they are
- *                formed once from the all-reduced db1 by neraf_field_grid_grads -- 20.9 MB less to all-reduce. */
+ *                formed once from the all-reduced db1 by neraf_field_grid_grads -- 20.9 MB less to all-reduce.
+ *   dw0_compact != NULL (needs defer_grid_grads): the per-query block of dW1 is written to this (trunk[0], n_enc)
+ *                fp32 buffer with row stride round_up(n_enc, 4) instead of into the strided dweights[0][:, n_grid:], so
+ *                that everything that must be all-reduced can sit in one contiguous buffer WITHOUT the grid block;
+ *                neraf_field_grid_grads copies it back.  (With n_grid == 0 nothing is deferred: pass NULL.) */
 typedef struct {
   const void* local_base;   /* this device's address of the symmetric buffer                         */
   void* multicast_base;     /* multicast address of the same buffer (cuMulticast* / torch symm_mem) */
@@ -149,13 +153,15 @@ NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precisio
                             const float* out, const float* grid_feature, const float* const* weights,
                             const void* pack, void* workspace, size_t workspace_bytes,
                             float* const* dweights, float* const* dbiases, float* dgrid, float* denc,
-                            int64_t denc_ld, const neraf_multicast* mc, int defer_grid_grads,
-                            neraf_stream_t stream);
+                            int64_t denc_ld, const neraf_multicast* mc, float* dw0_compact,
+                            int defer_grid_grads, neraf_stream_t stream);
 
-/* dweight0[n, k] = dbias0[n] * grid_feature[k] (k < n_grid; row stride n_grid + n_enc; may be NULL) and
+/* dweight0[n, k] = dbias0[n] * grid_feature[k] (k < n_grid; row stride n_grid + n_enc; may be NULL),
+ * dweight0[n, n_grid + e] = dw0_compact[n, e] (when dw0_compact != NULL) and
  * dgrid[k] = sum_n weight0[n, k] * dbias0[n] (may be NULL): the deferred part of neraf_field_backward_dp. */
 NERAF_API int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
-                           const float* dbias0, float* dweight0, float* dgrid, neraf_stream_t stream);
+                           const float* dbias0, const float* dw0_compact, float* dweight0, float* dgrid,
+                           neraf_stream_t stream);
 
 /* Encodings only (NeRFEncoding x3 + SHEncoding + normalisation/zeroing, NeRAF_model.py:533-551):
  * enc_out dev fp32 (B, 163) row stride ld. */

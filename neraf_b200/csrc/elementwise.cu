@@ -113,10 +113,13 @@ int pack_list(PackList& L, cudaStream_t stream) {
 //   blocks [0, n_outer)   dW1[n, :G] = db1[n] * g        (8 rows per block)
 //   the rest              dg[k]     += sum_n W1[n, k] db1[n]   (32 columns x one slice of n per block; dg pre-zeroed)
 // ---------------------------------------------------------------------------------------------
+// compact (optional): the per-query block of dW1, (N, E) with row stride ld_c, copied into dW[:, K:K+E] by the same
+// rows (data parallel: that block was all-reduced in a compact buffer, see neraf_field_backward_dp).
 __global__ void __launch_bounds__(1024) grid_grads_kernel(const float* __restrict__ s, const float* __restrict__ g,
                                                           const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
                                                           float* __restrict__ dW, float* __restrict__ dg, int n_outer,
-                                                          int n_slices) {
+                                                          int n_slices, const float* __restrict__ compact, int64_t E,
+                                                          int64_t ld_c) {
   __shared__ float red[32][33];
   int blk = blockIdx.x;
   if (blk < n_outer) {
@@ -125,6 +128,8 @@ __global__ void __launch_bounds__(1024) grid_grads_kernel(const float* __restric
     const float sn = __ldg(s + n);
     float* row = dW + n * ldw;
     for (int64_t k = threadIdx.x % 128; k < K; k += 128) row[k] = sn * __ldg(g + k);
+    if (compact)
+      for (int64_t e = threadIdx.x % 128; e < E; e += 128) row[K + e] = __ldg(compact + n * ld_c + e);
     return;
   }
   blk -= n_outer;
@@ -147,14 +152,15 @@ __global__ void __launch_bounds__(1024) grid_grads_kernel(const float* __restric
 }
 
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
-               bool dg_is_zero, cudaStream_t stream) {
+               bool dg_is_zero, cudaStream_t stream, const float* compact, int64_t E, int64_t ld_c) {
   if (N <= 0 || K <= 0) return NERAF_OK;
   const int n_outer = dW ? (int)ceil_div(N, 8) : 0;
   const int n_slices = 16;
   const int n_bwd = dg ? (int)ceil_div(K, 32) * n_slices : 0;
   if (n_outer + n_bwd == 0) return NERAF_OK;
   if (dg && !dg_is_zero) NERAF_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)K * 4, stream));
-  grid_grads_kernel<<<(unsigned)(n_outer + n_bwd), 1024, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, n_outer, n_slices);
+  grid_grads_kernel<<<(unsigned)(n_outer + n_bwd), 1024, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, n_outer, n_slices,
+                                                                      dW ? compact : nullptr, E, ld_c);
   NERAF_CHECK_LAUNCH("grid_grads_kernel");
   return NERAF_OK;
 }

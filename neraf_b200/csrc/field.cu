@@ -356,7 +356,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
                                const float* out, const float* grid_feature, const float* const* weights,
                                const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
                                float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
-                               const neraf_multicast* mc, int defer_grid_grads, cudaStream_t stream) {
+                               const neraf_multicast* mc, float* dw0_compact, int defer_grid_grads, cudaStream_t stream) {
   Layout l;
   NERAF_TRY(make_layout(dims, precision, B, &l));
   if (B == 0) return NERAF_OK;
@@ -374,6 +374,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   const int last = l.L - 1;
   const int64_t ldw0 = l.G + l.E;
 
+  NERAF_REQUIRE(!dw0_compact || defer_grid_grads, "field_backward_dp: dw0_compact needs defer_grid_grads");
   if (!bf && (mc || defer_grid_grads))
     return set_error(NERAF_ERR_UNSUPPORTED, "field_backward_dp: the fused all-reduce exists for the bf16 path only");
   if (!bf) {
@@ -488,6 +489,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     } else {
       w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
       w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
+      if (dw0_compact) { w.epi.out_f32 = dw0_compact; w.epi.ld_f32 = round_up(l.E, 4); }   // (n_1, E) with 16-byte rows
       NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
       if (denc) {
         MegaJob& e = jobs[nj++];
@@ -512,23 +514,25 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
                                     float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
                                     neraf_stream_t stream) {
   return field_backward_impl(dims, precision, B, dout, out, grid_feature, weights, pack, ws, ws_bytes, dweights, dbiases,
-                             dgrid, denc, denc_ld, nullptr, 0, (cudaStream_t)stream);
+                             dgrid, denc, denc_ld, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t B, const float* dout,
                                        const float* out, const float* grid_feature, const float* const* weights,
                                        const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
                                        float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
-                                       const neraf_multicast* mc, int defer_grid_grads, neraf_stream_t stream) {
+                                       const neraf_multicast* mc, float* dw0_compact, int defer_grid_grads,
+                                       neraf_stream_t stream) {
   return field_backward_impl(dims, precision, B, dout, out, grid_feature, weights, pack, ws, ws_bytes, dweights, dbiases,
-                             dgrid, denc, denc_ld, mc, defer_grid_grads, (cudaStream_t)stream);
+                             dgrid, denc, denc_ld, mc, dw0_compact, defer_grid_grads, (cudaStream_t)stream);
 }
 
 extern "C" int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
-                                      const float* dbias0, float* dweight0, float* dgrid, neraf_stream_t stream) {
+                                      const float* dbias0, const float* dw0_compact, float* dweight0, float* dgrid,
+                                      neraf_stream_t stream) {
   NERAF_REQUIRE(dims && dims->n_trunk >= 1, "field_grid_grads: dims is null");
   if (dims->n_grid <= 0) return NERAF_OK;
   NERAF_REQUIRE(grid_feature && weight0 && dbias0 && (dweight0 || dgrid), "field_grid_grads: null pointer");
   return grid_grads(dbias0, grid_feature, weight0, (int64_t)dims->n_grid + dims->n_enc, dims->trunk[0], dims->n_grid, dweight0,
-                    dgrid, false, (cudaStream_t)stream);
+                    dgrid, false, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 4));
 }

@@ -51,8 +51,9 @@ struct PackList {
 };
 int pack_list(PackList& L, cudaStream_t stream);
 // dW[n*ldw + k] = s[n] * g[k] (dW may be null) and dg[k] = sum_n W[n*ldw + k] * s[n] (dg may be null) in one launch
+// compact (optional): (N, E) block with row stride ld_c copied into dW[:, K:K+E]
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
-               bool dg_is_zero, cudaStream_t stream);
+               bool dg_is_zero, cudaStream_t stream, const float* compact = nullptr, int64_t E = 0, int64_t ld_c = 0);
 // out[n] = sum_m X[m*ld + n]   fp32 row-major (M,N)
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
 // dz = dout * (10 - y^2/10): gradient through 10*tanh; outputs fp32 (M,N) and/or bf16 (M,N) row-major.

@@ -302,12 +302,19 @@ class GraphedTrainStep:
         dpred = torch.empty_like(out)
         self.sums = torch.zeros(5, dtype=torch.float64, device=dev)
         losses = torch.zeros(2, dtype=torch.float32, device=dev)
-        # flat gradient buffer: weights, then biases and dgrid back to back (single memset inside the library)
-        order = list(weights) + list(biases) + ([grid_p] if grid_p is not None else [])
-        sizes = [t.numel() for t in order]
-        # Fused all-reduce: the flat buffer lives in symmetric memory and the weight-gradient GEMMs add their tiles
-        # into every rank's copy through its multicast alias.  Without NVLS (no multicast pointer) the buffer is plain
-        # memory and allreduce_grads() falls back to one NCCL all-reduce.
+        # Gradient buffers.  Everything that must be summed over the ranks sits in ONE flat buffer: the weight
+        # gradients, the bias gradients -- and, with a grid feature, only the per-query block of dW1 as a compact
+        # (n1, 164) matrix: the grid block dW1[:, :1024] = db1 (x) g and dg = W1[:, :1024]^T db1 are linear in db1 with g
+        # replicated, so they are formed AFTER the exchange from the reduced db1 (neraf_field_grid_grads), which keeps
+        # 20.9 MB out of the all-reduce.
+        defer = grid_p is not None
+        n1 = weights[0].shape[0]
+        ldc = (field.in_size - n_grid + 3) // 4 * 4
+        red_w = list(weights[1:]) if defer else list(weights)
+        sizes = [t.numel() for t in red_w] + ([n1 * ldc] if defer else []) + [b.numel() for b in biases]
+        n_weight_elems = sum(sizes) - sum(b.numel() for b in biases)
+        # Fused all-reduce (experimental): the flat buffer lives in symmetric memory and the weight-gradient GEMMs add
+        # their tiles into every rank's copy through its multicast alias.  Otherwise plain memory + one NCCL all-reduce.
         self.flat_grad, mc_ptr = None, 0
         if self.fused_allreduce and field.precision == "bf16" and dist.get_world_size(self.group) > 1:
             try:
@@ -321,13 +328,18 @@ class GraphedTrainStep:
             self.flat_grad, mc_ptr = torch.zeros(sum(sizes), dtype=torch.float32, device=dev), 0
         self.nvls = mc_ptr != 0
         self.flat_grad.zero_()
-        n_weight_elems = sum(t.numel() for t in weights)
-        views = [v.view_as(t) for v, t in zip(torch.split(self.flat_grad, sizes), order)]
+        parts = list(torch.split(self.flat_grad, sizes))
+        nw = len(red_w)
+        dws = [v.view_as(t) for v, t in zip(parts[:nw], red_w)]
+        compact = parts[nw] if defer else None
+        dbs = [v.view_as(t) for v, t in zip(parts[nw + (1 if defer else 0):], biases)]
+        dgrid = torch.zeros_like(grid_p) if defer else None
+        if defer:
+            dws = [torch.zeros_like(weights[0])] + dws
+        order = list(weights) + list(biases) + ([grid_p] if defer else [])
+        views = dws + dbs + ([dgrid] if defer else [])
         for t, v in zip(order, views):
             t.grad = v
-        n = len(weights)
-        dws, dbs = views[:n], views[n:2 * n]
-        dgrid = views[2 * n] if grid_p is not None else None
         qs = _lib.Queries()
         st = self.static
         qs.batch = B
@@ -349,7 +361,7 @@ class GraphedTrainStep:
         mc = _lib.Multicast()
         mc.local_base, mc.multicast_base, mc.bytes = self.flat_grad.data_ptr(), mc_ptr, self.flat_grad.numel() * 4
         weight_region = self.flat_grad[:n_weight_elems]
-        self._bias_region = self.flat_grad[n_weight_elems:n_weight_elems + sum(b.numel() for b in biases)]
+        self._bias_region = self.flat_grad[n_weight_elems:]
         zero_stream = torch.cuda.Stream(device=dev) if self.nvls else None
 
         def forward_part():
@@ -376,20 +388,17 @@ class GraphedTrainStep:
             _lib.check(lib.neraf_spectral_loss_backward(out.data_ptr(), st["data"].data_ptr(), n_local, n_total, crit,
                                                         self.sums.data_ptr(), None, None, w_sc, w_mag,
                                                         dpred.data_ptr(), s))
-            if self.nvls:
-                _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
-                                                       _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                       dw_arr, db_arr, _lib.ptr(dgrid), None, 0, C.byref(mc), 1, s))
-            else:
-                _lib.check(lib.neraf_field_backward(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
-                                                    _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                    dw_arr, db_arr, _lib.ptr(dgrid), None, 0, s))
+            _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
+                                                   _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                   dw_arr, db_arr, _lib.ptr(dgrid), None, 0,
+                                                   C.byref(mc) if self.nvls else None, _lib.ptr(compact),
+                                                   1 if defer else 0, s))
 
-        def grid_part():          # after the bias all-reduce: the grid-block gradients from the REDUCED db1
-            if self.nvls and grid_p is not None:
+        def grid_part():          # after the exchange: the grid-block gradients from the REDUCED db1, dW1 block copied back
+            if defer:
                 _lib.check(lib.neraf_field_grid_grads(C.byref(dims), grid_p.data_ptr(), weights[0].data_ptr(),
-                                                      dbs[0].data_ptr(), dws[0].data_ptr(), _lib.ptr(dgrid),
-                                                      _lib.stream_ptr(dev)))
+                                                      dbs[0].data_ptr(), compact.data_ptr(), dws[0].data_ptr(),
+                                                      dgrid.data_ptr(), _lib.stream_ptr(dev)))
         self._grid_part = grid_part
 
         side = torch.cuda.Stream(device=dev)
@@ -399,9 +408,8 @@ class GraphedTrainStep:
                 forward_part()
                 dist.all_reduce(self.sums[:4], group=self.group)
                 backward_part()
-                if self.nvls:
-                    dist.all_reduce(self._bias_region, group=self.group)
-                    grid_part()
+                dist.all_reduce(self._bias_region if self.nvls else self.flat_grad, group=self.group)
+                grid_part()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph_fwd, self.graph_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -415,9 +423,10 @@ class GraphedTrainStep:
             self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
 
     def allreduce_grads(self, dtype: torch.dtype = torch.float32) -> None:
-        """Data parallel: sum the flat gradient buffer over the ranks (one NCCL call).
+        """Data parallel: sum the flat gradient buffer over the ranks (one NCCL call), then form the grid-block gradients
+        from the reduced layer-1 bias gradient.
 
-        ``dtype=torch.bfloat16`` halves the bytes on NVLink (40.9 MB instead of 81.7 MB): the buffer is rounded to
+        ``dtype=torch.bfloat16`` halves the bytes on NVLink (30.4 MB instead of 60.8 MB): the buffer is rounded to
         bf16, summed, and widened back -- two extra elementwise passes (~40 us) against ~half of the all-reduce time;
         the rounding (2^-9 relative per element) is below the bf16 path's own gradient error.
         """
@@ -433,12 +442,13 @@ class GraphedTrainStep:
             return
         if dtype == torch.float32:
             dist.all_reduce(self.flat_grad, group=self.group)
-            return
-        if getattr(self, "_flat_lowp", None) is None or self._flat_lowp.dtype != dtype:
-            self._flat_lowp = torch.empty_like(self.flat_grad, dtype=dtype)
-        self._flat_lowp.copy_(self.flat_grad)
-        dist.all_reduce(self._flat_lowp, group=self.group)
-        self.flat_grad.copy_(self._flat_lowp)
+        else:
+            if getattr(self, "_flat_lowp", None) is None or self._flat_lowp.dtype != dtype:
+                self._flat_lowp = torch.empty_like(self.flat_grad, dtype=dtype)
+            self._flat_lowp.copy_(self.flat_grad)
+            dist.all_reduce(self._flat_lowp, group=self.group)
+            self.flat_grad.copy_(self._flat_lowp)
+        self._grid_part()
 
     def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         for k, dst in self.static.items():
