@@ -242,13 +242,14 @@ def main():
     if not args.no_graph:
         # N = 1: one graph around the autograd calls.  N > 1: two graphs (forward + loss sums | backward) with the
         # loss's 32-byte all-reduce between them issued eagerly -- no NCCL call is ever captured
-        graphed = GraphedTrainStep(model, dev_batch)
+        graphed = GraphedTrainStep(model, dev_batch,
+                                   grad_dtype=torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32)
 
     def step_value(batch):
         if graphed is None:
             return step(batch)
         ld = graphed(batch)
-        graphed.allreduce_grads(torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32)
+        graphed.allreduce_grads()
         return ld
 
     def barrier():

@@ -128,33 +128,46 @@ NERAF_API int neraf_field_backward(const neraf_field_dims* dims, int precision, 
                          float* const* dweights, float* const* dbiases, float* dgrid, float* denc,
                          int64_t denc_ld, neraf_stream_t stream);
 
-/* Data-parallel backward with the gradient all-reduce FUSED into the weight-gradient GEMMs (the reference refuses
- * world_size > 1, NeRAF_pipeline.py:154-155).
- *   mc != NULL : the weight-gradient tiles are not stored but added into every rank's copy of a symmetric gradient
- *                buffer through its multicast alias (NVLS multimem.red in the epilogue; bf16 path only).  Every
- *                dweights[l] must lie inside [local_base, local_base + bytes); the caller zeroes that buffer on EVERY
- *                rank before ANY rank starts this call (e.g. memset, then the loss's all-reduce), and makes the ranks
- *                meet again afterwards (e.g. the bias all-reduce) before reading the sums.  dbiases / dgrid / denc
- *                stay local sums, to be all-reduced by the caller.
- *   defer_grid_grads != 0 : skip the two gradients of the hoisted grid block (dW1[:, :n_grid] = db1 (x) g and dgrid =
+/* Data-parallel backward (the reference refuses world_size > 1, NeRAF_pipeline.py:154-155):
+ * neraf_field_backward plus the hooks a gradient exchange needs.  All options are independent; opt == NULL or all
+ * zero is neraf_field_backward.
+ *   defer_grid_grads : skip the two gradients of the hoisted grid block (dW1[:, :n_grid] = db1 (x) g and dgrid =
  *                W1[:, :n_grid]^T db1).  Both are LINEAR in db1 and g is replicated, so under data parallelism they are
  *                formed once from the all-reduced db1 by neraf_field_grid_grads -- 20.9 MB less to all-reduce.
- *   dw0_compact != NULL (needs defer_grid_grads): the per-query block of dW1 is written to this (trunk[0], n_enc)
- *                fp32 buffer with row stride round_up(n_enc, 4) instead of into the strided dweights[0][:, n_grid:], so
- *                that everything that must be all-reduced can sit in one contiguous buffer WITHOUT the grid block;
- *                neraf_field_grid_grads copies it back.  (With n_grid == 0 nothing is deferred: pass NULL.) */
+ *   dw0_compact (needs defer_grid_grads): the per-query block of dW1 is written to this (trunk[0], n_enc) fp32 buffer
+ *                with row stride round_up(n_enc, 4) instead of into the strided dweights[0][:, n_grid:], so that
+ *                everything that must be all-reduced can sit in one contiguous buffer WITHOUT the grid block;
+ *                neraf_field_grid_grads copies it back.
+ *   phase      : 0 = the whole backward.  1 = everything except the last dgrad (the gradient of layer 1's output) and
+ *                the per-query block of dW1 -- after it, every gradient except dW1 / db1 is final and can be
+ *                all-reduced; 2 = exactly the rest, to be launched while that all-reduce runs.
+ *   max_ctas   : upper bound on the grid of the job-list launch (0 = one CTA per SM): a concurrent collective kernel
+ *                needs SMs of its own, and the persistent kernel requires all its CTAs to be co-resident.
+ *   mc         : (experimental) the weight-gradient tiles are not stored but added into every rank's copy of a
+ *                symmetric gradient buffer through its multicast alias (NVLS multimem.red in the epilogue; bf16 path
+ *                only).  Every dweights[l] / dw0_compact must lie inside [local_base, local_base + bytes); the caller
+ *                zeroes that buffer on EVERY rank before ANY rank starts this call (e.g. memset, then the loss's
+ *                all-reduce), and makes the ranks meet again afterwards (e.g. the bias all-reduce) before reading the
+ *                sums.  dbiases / dgrid / denc stay local sums, to be all-reduced by the caller. */
 typedef struct {
   const void* local_base;   /* this device's address of the symmetric buffer                         */
   void* multicast_base;     /* multicast address of the same buffer (cuMulticast* / torch symm_mem) */
   size_t bytes;
 } neraf_multicast;
 
+typedef struct {
+  const neraf_multicast* mc;
+  float* dw0_compact;
+  int32_t defer_grid_grads;
+  int32_t phase;
+  int32_t max_ctas;
+} neraf_dp_options;
+
 NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t batch, const float* dout,
                             const float* out, const float* grid_feature, const float* const* weights,
                             const void* pack, void* workspace, size_t workspace_bytes,
                             float* const* dweights, float* const* dbiases, float* dgrid, float* denc,
-                            int64_t denc_ld, const neraf_multicast* mc, float* dw0_compact,
-                            int defer_grid_grads, neraf_stream_t stream);
+                            int64_t denc_ld, const neraf_dp_options* opt, neraf_stream_t stream);
 
 /* dweight0[n, k] = dbias0[n] * grid_feature[k] (k < n_grid; row stride n_grid + n_enc; may be NULL),
  * dweight0[n, n_grid + e] = dw0_compact[n, e] (when dw0_compact != NULL) and

@@ -59,6 +59,11 @@ class Multicast(C.Structure):
     _fields_ = [("local_base", C.c_void_p), ("multicast_base", C.c_void_p), ("bytes", C.c_size_t)]
 
 
+class DpOptions(C.Structure):
+    _fields_ = [("mc", C.POINTER(Multicast)), ("dw0_compact", C.c_void_p), ("defer_grid_grads", C.c_int32),
+                ("phase", C.c_int32), ("max_ctas", C.c_int32)]
+
+
 class GlParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop", C.c_int32), ("n_frames", C.c_int32),
                 ("n_iter", C.c_int32), ("momentum", C.c_float), ("input_is_log", C.c_int32)]
@@ -80,7 +85,7 @@ SIGNATURES = {
     "neraf_field_backward": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
                                         _vp, _vp, _i64, _vp]),
     "neraf_field_backward_dp": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
-                                           _vp, _vp, _i64, C.POINTER(Multicast), _vp, _i32, _vp]),
+                                           _vp, _vp, _i64, C.POINTER(DpOptions), _vp]),
     "neraf_field_grid_grads": (C.c_int, [C.POINTER(FieldDims), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),
     "neraf_spectral_loss_sums": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),

@@ -356,7 +356,13 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
                                const float* out, const float* grid_feature, const float* const* weights,
                                const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
                                float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
-                               const neraf_multicast* mc, float* dw0_compact, int defer_grid_grads, cudaStream_t stream) {
+                               const neraf_dp_options* opt, cudaStream_t stream) {
+  const neraf_multicast* mc = opt ? opt->mc : nullptr;
+  float* dw0_compact = opt ? opt->dw0_compact : nullptr;
+  const int defer_grid_grads = opt ? opt->defer_grid_grads : 0;
+  int phase = opt ? opt->phase : 0;
+  const int max_ctas = opt ? opt->max_ctas : 0;
+  NERAF_REQUIRE(phase >= 0 && phase <= 2, "field_backward_dp: phase must be 0, 1 or 2");
   Layout l;
   NERAF_TRY(make_layout(dims, precision, B, &l));
   if (B == 0) return NERAF_OK;
@@ -373,9 +379,13 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   NERAF_REQUIRE(!bf || pack, "field_backward: pack is null");
   const int last = l.L - 1;
   const int64_t ldw0 = l.G + l.E;
+  if (l.L < 2) {                                     // nothing to split with a single trunk layer
+    if (phase == 2) return NERAF_OK;
+    phase = 0;
+  }
 
   NERAF_REQUIRE(!dw0_compact || defer_grid_grads, "field_backward_dp: dw0_compact needs defer_grid_grads");
-  if (!bf && (mc || defer_grid_grads))
+  if (!bf && (mc || defer_grid_grads || phase))
     return set_error(NERAF_ERR_UNSUPPORTED, "field_backward_dp: the fused all-reduce exists for the bf16 path only");
   if (!bf) {
     float* dzh = reinterpret_cast<float*>(at(ws, l.dzh));
@@ -420,7 +430,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   // buffers (and dgrid, accumulated by grid_grads) are zeroed with as few memsets as their addresses allow -- one
   // when the caller laid them out back to back (neraf_b200/field.py does).
   bool dgrid_zeroed = false;
-  {
+  if (phase != 2) {
     const int nb = l.L + l.C;
     int i = 0;
     while (i < nb) {
@@ -434,7 +444,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     }
   }
   void* dzh = at(ws, l.dzh);
-  NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream));
+  if (phase != 2) NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream));
   bool heads_contiguous = true;                      // the C head gradients form one (C*F, W) matrix?
   for (int c = 1; c < l.C; ++c) heads_contiguous = heads_contiguous && dweights[l.L + c] == dweights[l.L] + (size_t)c * l.F * l.W;
   // Fused all-reduce (data parallel): weight gradients are not stored but added into every rank's copy of the
@@ -451,15 +461,17 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   NERAF_REQUIRE(!mc || heads_contiguous, "field_backward_dp: head gradients must be contiguous");
   MegaJob jobs[NERAF_MEGA_MAX_JOBS];
   int nj = 0;
+  // phase 1 stops before the last dgrad (dZ of layer 1) and the per-query block of dW1; phase 2 is exactly those:
+  // the caller all-reduces what phase 1 finished while phase 2 computes (neraf_dp_options).
   int producer = nj;
-  {                                                    // dZ_last = (dZ_head W_head) * leaky'(x_last)
+  if (phase != 2) {                                    // dZ_last = (dZ_head W_head) * leaky'(x_last)
     MegaJob& j = jobs[nj++];
     j = make_dgrad_job(B, l.W, l.CF, dzh, l.ld_h, at(pack, l.wh), l.ldwh, -1);
     j.epi.gate_mask = at(ws, l.mask[last]); j.epi.ld_mask = l.ld_mask;
     j.epi.out_bf16 = at(ws, l.dz[last]); j.epi.ld_bf16 = l.ldx[last];
     j.colsum = dbiases[last];
   }
-  {                                                    // head weight gradients (all heads in one GEMM)
+  if (phase != 2) {                                    // head weight gradients (all heads in one GEMM)
     MegaJob& j = jobs[nj++];
     j = make_wgrad_job(l.CF, l.W, B, dzh, l.ld_h, at(ws, l.x[last]), l.ldx[last], -1);
     j.wait_all = 0;
@@ -468,8 +480,10 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     NERAF_TRY(mc_alias(j.epi.out_f32, &j.epi.out_f32_multicast));
   }
   for (int i = last; i >= 0; --i) {
-    const int dz_producer = producer;                  // job that writes dZ_i
-    if (i > 0) {                                       // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
+    if (phase == 2 && i > 1) continue;
+    if (phase == 1 && i == 0) break;
+    const int dz_producer = (phase == 2 && i == 1) ? -1 : producer;   // job that writes dZ_i (phase 2: an earlier launch)
+    if (i > 0 && !(phase == 1 && i == 1)) {            // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
       producer = nj;
       MegaJob& j = jobs[nj++];
       j = make_dgrad_job(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.w[i]), l.ldw[i], dz_producer);
@@ -479,8 +493,9 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       // Fused all-reduce: the tiles of dW_i push their results over NVLink, the tiles of this dgrad job do not, and
       // both only need dZ_i -- interleaved, the link drains behind the dgrad tiles instead of throttling every CTA
       // pair at once (the largest pair, dgrad 2->1 / dW_2, is 70 % of the bytes and sits at the end of the backward).
-      if (mc) j.merge_next = 1;
+      if (mc && phase == 0) j.merge_next = 1;
     }
+    if (phase == 2 && i == 1) continue;                // dW_1 belongs to phase 1
     MegaJob& w = jobs[nj++];                           // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
     if (i > 0) {
       w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
@@ -498,12 +513,12 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       }
     }
   }
-  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream));
-  if (!heads_contiguous)
+  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas));
+  if (!heads_contiguous && phase != 2)
     for (int c = 0; c < l.C; ++c)
       NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,
                                        cudaMemcpyDeviceToDevice, stream));
-  if (l.G > 0 && !defer_grid_grads)
+  if (l.G > 0 && !defer_grid_grads && phase != 1)
     NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, dgrid_zeroed, stream));
   return NERAF_OK;
 }
@@ -514,17 +529,16 @@ extern "C" int neraf_field_backward(const neraf_field_dims* dims, int precision,
                                     float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
                                     neraf_stream_t stream) {
   return field_backward_impl(dims, precision, B, dout, out, grid_feature, weights, pack, ws, ws_bytes, dweights, dbiases,
-                             dgrid, denc, denc_ld, nullptr, nullptr, 0, (cudaStream_t)stream);
+                             dgrid, denc, denc_ld, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t B, const float* dout,
                                        const float* out, const float* grid_feature, const float* const* weights,
                                        const void* pack, void* ws, size_t ws_bytes, float* const* dweights,
                                        float* const* dbiases, float* dgrid, float* denc, int64_t denc_ld,
-                                       const neraf_multicast* mc, float* dw0_compact, int defer_grid_grads,
-                                       neraf_stream_t stream) {
+                                       const neraf_dp_options* opt, neraf_stream_t stream) {
   return field_backward_impl(dims, precision, B, dout, out, grid_feature, weights, pack, ws, ws_bytes, dweights, dbiases,
-                             dgrid, denc, denc_ld, mc, dw0_compact, defer_grid_grads, (cudaStream_t)stream);
+                             dgrid, denc, denc_ld, opt, (cudaStream_t)stream);
 }
 
 extern "C" int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,

@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
 int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
                       CUtensorMap* out);
 
-int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream) {
+int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas) {
   using namespace umma;
   NERAF_REQUIRE(jobs && n_jobs > 0 && n_jobs <= NERAF_MEGA_MAX_JOBS, "mega_run: 1..%d jobs", NERAF_MEGA_MAX_JOBS);
   static MegaParams P;          // large: build in static storage (single-threaded driver, see header conventions)
@@ -778,7 +778,8 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
     configured[dev] = true;
   }
-  const int units = sm_count() / 2;
+  int units = sm_count() / 2;
+  if (max_ctas >= 2 && max_ctas / 2 < units) units = max_ctas / 2;   // leave SMs to a concurrent kernel (collectives)
   const int grid = (tile < units ? tile : units) * 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -816,5 +817,5 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
 
 extern "C" int neraf_gemm_bf16_jobs(const neraf_gemm_job* jobs, int n_jobs, void* counters, size_t counters_bytes,
                                     neraf_stream_t stream) {
-  return neraf::mega_run(jobs, n_jobs, counters, counters_bytes, (cudaStream_t)stream);
+  return neraf::mega_run(jobs, n_jobs, counters, counters_bytes, (cudaStream_t)stream, 0);
 }

@@ -32,7 +32,8 @@ int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const
 // persistent launch with tile-level scheduling and row-block dependency tracking.
 #define NERAF_MEGA_MAX_JOBS NERAF_MAX_GEMM_JOBS
 typedef neraf_gemm_job MegaJob;      // public contract: include/neraf_b200.h
-int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream);
+// max_ctas: 0 = one CTA per SM; otherwise an upper bound on the grid (a concurrent kernel gets the other SMs)
+int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas = 0);
 
 // elementwise.cu
 int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out, void* out_t,

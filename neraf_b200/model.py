@@ -229,8 +229,18 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3,
-                 fused_allreduce: bool = False):
+                 fused_allreduce: bool = False, overlap_allreduce: bool = False,
+                 grad_dtype: torch.dtype = torch.float32):
         self.model = model
+        # Data parallel, optional: the backward is split in two graphs; everything the first one finishes (all weight
+        # gradients but dW1's: 57.5 of the 60.8 MB) is all-reduced on a communication stream WHILE the second computes
+        # the last dgrad and dW1 on fewer CTAs (the collective kernel needs SMs of its own: ``comm_ctas``; set
+        # NCCL_MAX_CTAS accordingly).  Measured at 2 GPUs (tools/time_dp_segments.py) it LOSES to the serial exchange
+        # (700 vs 612 us fp32, 639 vs 579 us bf16): capped to 16 CTAs NCCL is slower, and the two kernels contend for
+        # L2 / HBM.  Off by default.
+        self.overlap_allreduce = overlap_allreduce
+        self.grad_dtype = grad_dtype
+        self.comm_ctas = 20
         # Data parallel, experimental: NVLS multimem.red in the weight-gradient epilogues (the all-reduce fused into the
         # GEMMs over torch symmetric memory).  Numerically identical to backward + NCCL (tools/check_dp_nvls.py) and as
         # fast at 2 GPUs, but multimem.red delivers every rank's addend to every rank (inbound traffic grows with the
@@ -364,6 +374,23 @@ class GraphedTrainStep:
         self._bias_region = self.flat_grad[n_weight_elems:]
         zero_stream = torch.cuda.Stream(device=dev) if self.nvls else None
 
+        self.overlap = bool(self.overlap_allreduce and not self.nvls and field.precision == "bf16" and len(weights) > 2)
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        opt1, opt2 = _lib.DpOptions(), _lib.DpOptions()
+        for o in (opt1, opt2):
+            o.mc = C.pointer(mc) if self.nvls else None
+            o.dw0_compact = _lib.ptr(compact)
+            o.defer_grid_grads = 1 if defer else 0
+        opt1.phase, opt1.max_ctas = (1 if self.overlap else 0), 0
+        opt2.phase, opt2.max_ctas = 2, max(2, (sm_count - self.comm_ctas) // 2 * 2)
+        # regions of the flat buffer: what the first backward graph finishes | what the second one does
+        n_early = sum(t.numel() for t in (weights[1:] if defer else weights[1:]))
+        self._early_region = self.flat_grad[:n_early] if defer else None
+        self._late_region = self.flat_grad[n_early:] if defer else None
+        if not defer:
+            self.overlap = False
+        self._comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
+
         def forward_part():
             if self.nvls:
                 # every rank's copy of the weight gradients must be zero before ANY rank's backward adds into it: the
@@ -390,9 +417,13 @@ class GraphedTrainStep:
                                                         dpred.data_ptr(), s))
             _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
                                                    _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                   dw_arr, db_arr, _lib.ptr(dgrid), None, 0,
-                                                   C.byref(mc) if self.nvls else None, _lib.ptr(compact),
-                                                   1 if defer else 0, s))
+                                                   dw_arr, db_arr, _lib.ptr(dgrid), None, 0, C.byref(opt1), s))
+
+        def backward_part2():
+            _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
+                                                   _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                   dw_arr, db_arr, _lib.ptr(dgrid), None, 0, C.byref(opt2),
+                                                   _lib.stream_ptr(dev)))
 
         def grid_part():          # after the exchange: the grid-block gradients from the REDUCED db1, dW1 block copied back
             if defer:
@@ -408,6 +439,8 @@ class GraphedTrainStep:
                 forward_part()
                 dist.all_reduce(self.sums[:4], group=self.group)
                 backward_part()
+                if self.overlap:
+                    backward_part2()
                 dist.all_reduce(self._bias_region if self.nvls else self.flat_grad, group=self.group)
                 grid_part()
         torch.cuda.current_stream(dev).wait_stream(side)
@@ -417,37 +450,53 @@ class GraphedTrainStep:
             forward_part()
         with torch.cuda.graph(self.graph_bwd):
             backward_part()
+        if self.overlap:
+            self.graph_bwd2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_bwd2):
+                backward_part2()
         if model.criterion_name == "MSE":
             self.losses = {"audio_mse": losses[1]}
         else:
             self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
 
-    def allreduce_grads(self, dtype: torch.dtype = torch.float32) -> None:
-        """Data parallel: sum the flat gradient buffer over the ranks (one NCCL call), then form the grid-block gradients
-        from the reduced layer-1 bias gradient.
+    def _reduce(self, region: torch.Tensor, dtype: torch.dtype) -> None:
+        """Sum ``region`` of the flat gradient buffer over the ranks (NCCL), optionally through a bf16 copy."""
+        import torch.distributed as dist
+        if dtype == torch.float32:
+            dist.all_reduce(region, group=self.group)
+            return
+        key = (region.data_ptr(), dtype)
+        cache = self.__dict__.setdefault("_lowp", {})
+        if key not in cache:
+            cache[key] = torch.empty_like(region, dtype=dtype)
+        low = cache[key]
+        low.copy_(region)
+        dist.all_reduce(low, group=self.group)
+        region.copy_(low)
 
-        ``dtype=torch.bfloat16`` halves the bytes on NVLink (30.4 MB instead of 60.8 MB): the buffer is rounded to
-        bf16, summed, and widened back -- two extra elementwise passes (~40 us) against ~half of the all-reduce time;
-        the rounding (2^-9 relative per element) is below the bf16 path's own gradient error.
+    def allreduce_grads(self, dtype: Optional[torch.dtype] = None) -> None:
+        """Data parallel: finish the gradient exchange of the last step, then form the grid-block gradients from the
+        reduced layer-1 bias gradient.
+
+        Without overlap: one NCCL all-reduce of the flat buffer.  With overlap (default): the bulk was reduced on the
+        communication stream while the second backward graph ran; what is left is the 3.4 MB that graph produced.
+        ``dtype=torch.bfloat16`` halves the bytes on NVLink (30.4 MB instead of 60.8 MB): the buffer is rounded to bf16,
+        summed, and widened back; the rounding (2^-9 relative per element) is below the bf16 path's own gradient error.
         """
         if self.group is None:
             return
         import torch.distributed as dist
+        dtype = self.grad_dtype if dtype is None else dtype
         if self.nvls:
             # the weight gradients were summed by the NVSwitch inside the backward GEMMs; what is left is the 40 KB of
             # bias gradients (this collective is also where the ranks meet after their reductions were issued) and
             # the grid-block gradients, linear in the now-reduced db1
             dist.all_reduce(self._bias_region, group=self.group)
-            self._grid_part()
-            return
-        if dtype == torch.float32:
-            dist.all_reduce(self.flat_grad, group=self.group)
+        elif self.overlap:
+            torch.cuda.current_stream(self.model.device).wait_stream(self._comm_stream)
+            self._reduce(self._late_region, torch.float32)
         else:
-            if getattr(self, "_flat_lowp", None) is None or self._flat_lowp.dtype != dtype:
-                self._flat_lowp = torch.empty_like(self.flat_grad, dtype=dtype)
-            self._flat_lowp.copy_(self.flat_grad)
-            dist.all_reduce(self._flat_lowp, group=self.group)
-            self.flat_grad.copy_(self._flat_lowp)
+            self._reduce(self.flat_grad, dtype)
         self._grid_part()
 
     def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -462,6 +511,12 @@ class GraphedTrainStep:
             self.graph_fwd.replay()
             dist.all_reduce(self.sums[:4], group=self.group)
             self.graph_bwd.replay()
+            if self.overlap:
+                cur = torch.cuda.current_stream(self.model.device)
+                self._comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self._comm_stream):
+                    self._reduce(self._early_region, self.grad_dtype)      # runs beside the second backward graph
+                self.graph_bwd2.replay()
             for t, v in self._grad_views:          # eager steps in between may have replaced .grad
                 t.grad = v
         return self.losses

@@ -14,6 +14,7 @@ from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioMo
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
+os.environ.setdefault("NCCL_MAX_CTAS", "16")
 dist.init_process_group("nccl", device_id=dev)
 shape, B = syn.RAF, 512
 

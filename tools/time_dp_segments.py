@@ -1,4 +1,4 @@
-"""2+ GPU (torchrun): per-segment device time of the two-graph data-parallel step, NCCL vs fused NVLS all-reduce."""
+"""2+ GPU (torchrun): device time per data-parallel train step (two/three-graph step) for the gradient-exchange variants."""
 import os
 import sys
 
@@ -12,36 +12,43 @@ from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioMo
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
+os.environ.setdefault("NCCL_MAX_CTAS", "16")
 dist.init_process_group("nccl", device_id=dev)
 shape, B = syn.RAF, 2048
 batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=10 + rank).items()}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name, fused in (("nccl", False), ("nvls", True)):
+ref = None
+variants = [("serial fp32", dict(overlap_allreduce=False, grad_dtype=torch.float32)),
+            ("serial bf16", dict(overlap_allreduce=False, grad_dtype=torch.bfloat16)),
+            ("overlap fp32", dict(overlap_allreduce=True, grad_dtype=torch.float32)),
+            ("overlap bf16", dict(overlap_allreduce=True, grad_dtype=torch.bfloat16)),
+            ("nvls fused", dict(fused_allreduce=True))]
+for name, kw in variants:
     cfg = NeRAFAudioModelConfig(dataset="RAF", precision="bf16")
     model = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)),
                             process_group=dist.group.WORLD)
     model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
     model = model.to(dev)
-    step = GraphedTrainStep(model, batch, fused_allreduce=fused)
-    seg = {k: 0.0 for k in ("fwd", "sums_ar", "bwd", "grad_ar")}
-    n = 40
+    step = GraphedTrainStep(model, batch, **kw)
+    n, tot = 40, 0.0
     for it in range(n + 5):
         flush.fill_(1)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        ev[0].record()
-        step.graph_fwd.replay()
-        ev[1].record()
-        dist.all_reduce(step.sums[:4], group=step.group)
-        ev[2].record()
-        step.graph_bwd.replay()
-        ev[3].record()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(batch)
         step.allreduce_grads()
-        ev[4].record()
+        e.record()
         torch.cuda.synchronize()
         if it >= 5:
-            for i, k in enumerate(seg):
-                seg[k] += ev[i].elapsed_time(ev[i + 1]) * 1e3 / n
+            tot += s.elapsed_time(e) * 1e3 / n
+    g = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).double()
+    if ref is None:
+        ref = g
+    err = float((g - ref).norm() / ref.norm())
+    t = torch.tensor([tot], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(name, "nvls" if step.nvls else "plain", {k: round(v, 1) for k, v in seg.items()}, "total us", round(sum(seg.values()), 1), flush=True)
+        print(f"{name:14s} {float(t):8.1f} us/step   overlap={getattr(step, 'overlap', False)} nvls={step.nvls}   "
+              f"grads vs serial fp32: {err:.2e}", flush=True)
     dist.barrier()
 dist.destroy_process_group()
