@@ -14,6 +14,7 @@ to the flat feature vector can be passed as ``resnet3d``.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -240,7 +241,7 @@ class GraphedTrainStep:
         # L2 / HBM.  Off by default.
         self.overlap_allreduce = overlap_allreduce
         self.grad_dtype = grad_dtype
-        self.comm_ctas = 20
+        self.comm_ctas = int(os.environ.get("NERAF_COMM_CTAS", "20"))
         # Data parallel, experimental: NVLS multimem.red in the weight-gradient epilogues (the all-reduce fused into the
         # GEMMs over torch symmetric memory).  Numerically identical to backward + NCCL (tools/check_dp_nvls.py) and as
         # fast at 2 GPUs, but multimem.red delivers every rank's addend to every rank (inbound traffic grows with the

@@ -21,8 +21,9 @@ ref = None
 variants = [("serial fp32", dict(overlap_allreduce=False, grad_dtype=torch.float32)),
             ("serial bf16", dict(overlap_allreduce=False, grad_dtype=torch.bfloat16)),
             ("overlap fp32", dict(overlap_allreduce=True, grad_dtype=torch.float32)),
-            ("overlap bf16", dict(overlap_allreduce=True, grad_dtype=torch.bfloat16)),
-            ("nvls fused", dict(fused_allreduce=True))]
+            ("overlap bf16", dict(overlap_allreduce=True, grad_dtype=torch.bfloat16))]
+if os.environ.get("WITH_NVLS"):
+    variants.append(("nvls fused", dict(fused_allreduce=True)))
 for name, kw in variants:
     cfg = NeRAFAudioModelConfig(dataset="RAF", precision="bf16")
     model = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)),
