@@ -98,28 +98,32 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
     const float* mag_sig = a.mag_t + sig * (long long)a.T * a.F;
     float* prev = a.prev + sig * (long long)a.L;
     for (int it = 0; it <= a.n_iter; ++it) {
-      for (int color = 0; color < a.n_colors; ++color) {
-        for (int t = color + a.n_colors * warp; t < a.T; t += a.n_colors * nwarps) {
-          const float* mag_row = mag_sig + (long long)t * a.F;
-          if (it == 0) {
-            const float* init_row = a.init ? a.init + 2 * ((sig / a.n_channels) * a.init_sn + (sig % a.n_channels) * a.init_sc +
-                                                           (long long)t * a.init_st)
-                                           : nullptr;
-            init_step<H>(lane, tw, mag_row, init_row, a.init_sf, re, im);
-            __syncwarp();
-          } else {
-            MagRegs<H> mag;                       // consumed after the forward FFT: its latency hides behind it
-            load_mag<H>(lane, mag_row, mag);
-            load_frame<H>(lane, t, a.hop, a.L, j_lo, j_hi, D, win, re, im);
-            __syncwarp();
-            fft_warp<H, false>(lane, re, im, twp);
-            spectrum_step<H>(lane, tw, mag, re, im);
-            __syncwarp();
-          }
-          fft_warp<H, true>(lane, re, im, twp);
-          ola_frame<H>(lane, t, a.hop, a.L, j_lo, j_hi, win, re, im, scale, ACC);
+      // One frame per warp at a time; frames that overlap in time must not overlap-add concurrently: frame t has
+      // colour t % n_colors, same-coloured frames are >= n_colors hops apart, one barrier per colour.  (Walking a block
+      // of consecutive frames per warp instead saves one of SoundSpaces' 8 rounds and measured no faster.)
+      auto frame = [&](int t) {
+        const float* mag_row = mag_sig + (long long)t * a.F;
+        if (it == 0) {
+          const float* init_row = a.init ? a.init + 2 * ((sig / a.n_channels) * a.init_sn + (sig % a.n_channels) * a.init_sc +
+                                                         (long long)t * a.init_st)
+                                         : nullptr;
+          init_step<H>(lane, tw, mag_row, init_row, a.init_sf, re, im);
+          __syncwarp();
+        } else {
+          MagRegs<H> mag;                       // consumed after the forward FFT: its latency hides behind it
+          load_mag<H>(lane, mag_row, mag);
+          load_frame<H>(lane, t, a.hop, a.L, j_lo, j_hi, D, win, re, im);
+          __syncwarp();
+          fft_warp<H, false>(lane, re, im, twp);
+          spectrum_step<H>(lane, tw, mag, re, im);
           __syncwarp();
         }
+        fft_warp<H, true>(lane, re, im, twp);
+        ola_frame<H>(lane, t, a.hop, a.L, j_lo, j_hi, win, re, im, scale, ACC);
+        __syncwarp();
+      };
+      for (int color = 0; color < a.n_colors; ++color) {
+        for (int t = color + a.n_colors * warp; t < a.T; t += a.n_colors * nwarps) frame(t);
         __syncthreads();
       }
       // whole-waveform pass: window-envelope normalisation (torch.istft) + momentum combination.  Every thread issues
@@ -246,7 +250,12 @@ static int make_plan(const neraf_gl_params* p, long long S, Plan* pl) {
   pl->H = N / 2;
   pl->L = p->hop * (p->n_frames - 1);
   NERAF_REQUIRE(pl->L > N / 2, "griffinlim: signal too short for reflect padding (L=%d, n_fft=%d)", pl->L, N);
-  pl->n_colors = (int)ceil_div(p->win_length, p->hop);
+  {
+    // samples one frame overlap-adds: the window support rounded outwards to whole complex pairs (kernel: j_lo, j_hi)
+    const int left = (N - p->win_length) / 2;
+    const int span = 2 * ((left + p->win_length + 1) / 2 - left / 2);
+    pl->n_colors = (int)ceil_div(span, p->hop);
+  }
   const int F = N / 2 + 1;
   const size_t Lp = (size_t)((pl->L + 3) & ~3);
   pl->nwarps = 0;

@@ -248,6 +248,8 @@ class GraphedTrainStep:
         # world size) and the pushes throttle the epilogues, so it is off by default: see DESIGN.md section 8.
         self.fused_allreduce = fused_allreduce
         self.nvls = False
+        self._staging = None
+        self._staged_for = None
         dev = model.device
         keys = ("time_query", "mic_pose", "source_pose", "rot", "data")
         dtypes = {"time_query": torch.int64, "mic_pose": torch.float64, "source_pose": torch.float64,
@@ -500,11 +502,38 @@ class GraphedTrainStep:
             self._reduce(self.flat_grad, dtype)
         self._grid_part()
 
+    def prefetch(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Start copying the NEXT step's batch (pinned host tensors) into staging buffers on a copy stream, so that the
+        PCIe transfer (4.2 MB of target columns at B=2048: ~80 us) runs under the current step's kernels; the next
+        ``step(batch)`` with the same dict then only copies staging -> static buffers on the device (~4 us).  What a
+        prefetching data loader does for the reference's ``batch.to(device)`` (NeRAF_model.py:531-540)."""
+        dev = self.model.device
+        if self._staging is None:
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged_ev = torch.cuda.Event()
+            self._consumed_ev = torch.cuda.Event()
+            self._consumed_ev.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._consumed_ev)        # the previous staging -> static copy has read the buffers
+        with torch.cuda.stream(self._copy_stream):
+            for k, dst in self._staging.items():
+                dst.copy_(batch[k], non_blocking=True)
+            self._staged_ev.record(self._copy_stream)
+        self._staged_for = batch
+
     def __call__(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        for k, dst in self.static.items():
-            src = batch[k]
-            if src is not dst:
-                dst.copy_(src, non_blocking=True)
+        if self._staged_for is not None and batch is self._staged_for:
+            cur = torch.cuda.current_stream(self.model.device)
+            cur.wait_event(self._staged_ev)
+            for k, dst in self.static.items():
+                dst.copy_(self._staging[k], non_blocking=True)
+            self._consumed_ev.record(cur)
+            self._staged_for = None
+        else:
+            for k, dst in self.static.items():
+                src = batch[k]
+                if src is not dst:
+                    dst.copy_(src, non_blocking=True)
         if self.group is None:
             self.graph.replay()
         else:

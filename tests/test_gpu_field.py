@@ -186,9 +186,52 @@ def test_cpu_parameters_fail_loudly():
         f(torch.zeros(2, 1187))
 
 
+def test_graphed_step_and_prefetch_equal_autograd_step():
+    """One-graph GraphedTrainStep (N = 1) fed pinned host batches -- directly and through prefetch() -- reproduces the
+    eager plugin calls, batch after batch."""
+    from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioModel, NeRAFAudioModelConfig
+    dev = cuda()
+    shape, B = syn.RAF, 320
+    cfg = NeRAFAudioModelConfig(dataset="RAF", precision="bf16")
+    model = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)))
+    model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
+    model = model.to(dev)
+    model.field.always_repack = True
+    params = [p for p in model.parameters() if p.requires_grad]
+    host = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=s).items()}
+            for s in (1, 2, 3)]
+
+    def eager(batch):
+        for p in params:
+            p.grad = None
+        ld = model.get_loss_dict(model.get_outputs(batch), batch)
+        sum(ld.values()).backward()
+        return {k: float(v) for k, v in ld.items()}, [p.grad.clone() for p in params]
+
+    refs = [eager(b) for b in host]
+    step = GraphedTrainStep(model, host[0])
+
+    def check(got, i):
+        torch.cuda.synchronize()
+        for k, v in refs[i][0].items():
+            assert abs(float(got[k]) - v) < 1e-5 * abs(v), (k, i)
+        for p, r in zip(params, refs[i][1]):
+            assert rel_fro(p.grad, r) < 1e-5, i
+
+    for i in (1, 0, 2):
+        check(step(host[i]), i)
+    step.prefetch(host[1])
+    for i in (1, 2, 0):                        # consume the staged batch, stage the next one under the step
+        got = step(host[i])
+        step.prefetch(host[(i + 1) % 3])
+        check(got, i)
+    check(step(host[2]), 2)                    # a batch that was NOT the staged one is copied directly
+    check(step(host[1]), 1)                    # ... and the batch still staged is consumed afterwards
+
+
 def test_two_graph_data_parallel_step_equals_autograd_step():
-    """GraphedTrainStep with a process group (two graphs of direct C-ABI calls, loss sums all-reduced between them)
-    == the eager autograd step, on a one-rank NCCL group."""
+    """GraphedTrainStep with a process group (graphs of direct C-ABI calls, loss sums all-reduced between them, every
+    gradient-exchange variant of neraf_field_backward_dp) == the eager autograd step, on a one-rank NCCL group."""
     import socket
     import torch.distributed as dist
     from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioModel, NeRAFAudioModelConfig
@@ -212,15 +255,19 @@ def test_two_graph_data_parallel_step_equals_autograd_step():
         sum(ld.values()).backward()
         ref = [p.grad.clone() for p in params]
         ref_loss = {k: float(v) for k, v in ld.items()}
-        step = GraphedTrainStep(model, batch)
-        for _ in range(2):
-            got = step(batch)
-            step.allreduce_grads()
-        torch.cuda.synchronize()
-        for k in ref_loss:
-            assert abs(float(got[k]) - ref_loss[k]) < 1e-5 * abs(ref_loss[k]), k
-        for p, r in zip(params, ref):
-            assert rel_fro(p.grad, r) < 1e-5            # same kernels, same order: only atomics differ
+        # serial exchange (compact dW1 block, deferred grid-block gradients), two-phase backward with the bulk of the
+        # exchange on a communication stream, bf16 exchange: all must reproduce the autograd step
+        for kw, tol in ((dict(), 1e-5), (dict(overlap_allreduce=True), 1e-5),
+                        (dict(grad_dtype=torch.bfloat16), 4e-3), (dict(fused_allreduce=True), 1e-5)):
+            step = GraphedTrainStep(model, batch, **kw)
+            for _ in range(2):
+                got = step(batch)
+                step.allreduce_grads()
+            torch.cuda.synchronize()
+            for k in ref_loss:
+                assert abs(float(got[k]) - ref_loss[k]) < 1e-5 * abs(ref_loss[k]), (k, kw)
+            for p, r in zip(params, ref):
+                assert rel_fro(p.grad, r) < tol, kw          # same kernels: only atomics order / bf16 rounding differ
     finally:
         dist.destroy_process_group()
 

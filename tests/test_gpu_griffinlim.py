@@ -62,7 +62,9 @@ def test_acoustic_metrics_within_one_percent(shape):
 
 
 @pytest.mark.parametrize("n_fft,win,hop,T", [(512, 256, 128, 9), (256, 256, 64, 33), (2048, 1024, 512, 12),
-                                             (64, 64, 16, 40), (128, 100, 50, 17)])
+                                             (64, 64, 16, 40), (128, 100, 50, 17),
+                                             # many frames per warp; an odd window offset (support rounded to pairs)
+                                             (256, 256, 64, 110), (128, 101, 25, 120)])
 def test_other_stft_geometries(n_fft, win, hop, T):
     dev = cuda()
     g = torch.Generator().manual_seed(n_fft + T)
