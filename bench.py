@@ -285,7 +285,9 @@ def main():
     sampler.start()
     l_eager0 = lib.neraf_launch_count()
     step(dev_batch)
-    launches_per_step = lib.neraf_launch_count() - l_eager0     # a graph replay launches the same kernels
+    launches_per_step = lib.neraf_launch_count() - l_eager0
+    if graphed is not None:          # the graph replays the kernels of its last eager warm-up step
+        launches_per_step = graphed.launches_per_step
     ms_dev, launches, wall_dev = timed(dev_batch, args.steps, read_loss=False, fn=step_value)
     if graphed is not None:
         launches = launches_per_step * args.steps

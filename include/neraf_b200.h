@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 3
+#define NERAF_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))
@@ -155,12 +155,24 @@ typedef struct {
   size_t bytes;
 } neraf_multicast;
 
+/* The spectral loss's gradient formed inside the backward instead of being read from `dout` (which may then be NULL):
+ * dout[i] = neraf_spectral_loss_backward(out, gt, ..., sums, upstream = 1)[i], evaluated on the fly by the kernel that
+ * applies the heads' 10*tanh derivative -- one launch and a 2 x 4 B/element round trip less per step. */
+typedef struct {
+  const float* gt;          /* (B, C, F) target log-magnitudes, same layout as out          */
+  int64_t n_total;          /* elements over ALL ranks (the mean's denominator)             */
+  int32_t criterion;        /* NERAF_CRIT_*                                                  */
+  const double* sums;       /* device f64[>=4]: the (all-reduced) partial sums of the loss   */
+  float w_sc, w_mag;        /* loss weights (NeRAF_model.py:597-598)                         */
+} neraf_loss_grad;
+
 typedef struct {
   const neraf_multicast* mc;
   float* dw0_compact;
   int32_t defer_grid_grads;
   int32_t phase;
   int32_t max_ctas;
+  const neraf_loss_grad* loss;   /* NULL: read the upstream gradient from dout */
 } neraf_dp_options;
 
 NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t batch, const float* dout,

@@ -59,9 +59,14 @@ class Multicast(C.Structure):
     _fields_ = [("local_base", C.c_void_p), ("multicast_base", C.c_void_p), ("bytes", C.c_size_t)]
 
 
+class LossGrad(C.Structure):        # neraf_loss_grad
+    _fields_ = [("gt", C.c_void_p), ("n_total", C.c_int64), ("criterion", C.c_int32), ("sums", C.c_void_p),
+                ("w_sc", C.c_float), ("w_mag", C.c_float)]
+
+
 class DpOptions(C.Structure):
     _fields_ = [("mc", C.POINTER(Multicast)), ("dw0_compact", C.c_void_p), ("defer_grid_grads", C.c_int32),
-                ("phase", C.c_int32), ("max_ctas", C.c_int32)]
+                ("phase", C.c_int32), ("max_ctas", C.c_int32), ("loss", C.POINTER(LossGrad))]
 
 
 class GlParams(C.Structure):

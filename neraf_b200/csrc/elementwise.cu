@@ -205,10 +205,13 @@ constexpr int kHeadRows = 32;        // rows per block of head_backward_kernel (
 
 // Block = 32 columns x 8 row lanes over kHeadRows rows: coalesced 128-byte row segments, the bias gradient
 // (column sums) is accumulated in registers and leaves the block as one atomic per column.
+// LOSS: `dout` holds the targets and the upstream gradient is the spectral loss's, evaluated here with exactly the
+// arithmetic of loss_backward_kernel (loss.cu) -- fused, the step saves one launch and the dpred round trip.
+template <bool LOSS>
 __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                                                             int64_t M, int64_t N, float* __restrict__ dz_f32,
                                                             int64_t ld_f32, __nv_bfloat16* __restrict__ dz_bf16,
-                                                            int64_t ld_bf16, HeadColsum cs) {
+                                                            int64_t ld_bf16, HeadColsum cs, neraf_loss_grad lg) {
   __shared__ float red[8][32];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
@@ -222,6 +225,22 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
       const int64_t r = r0 + ty + 8 * i;
       yy[i] = r < r1 ? __ldg(y + r * N + c) : 0.f;
       dd[i] = r < r1 ? __ldg(dout + r * N + c) : 0.f;
+    }
+    if (LOSS) {
+      float a = 0.f;
+      if (lg.criterion != NERAF_CRIT_MSE) a = (float)((double)lg.w_sc / (sqrt(lg.sums[0]) * sqrt(lg.sums[1])));
+      const float b = (float)((double)lg.w_mag / (double)lg.n_total);
+      const bool l1 = lg.criterion == NERAF_CRIT_SC_SLL1;
+#pragma unroll
+      for (int i = 0; i < kHeadRows / 8; ++i) {
+        const float x = yy[i], t = dd[i], d = x - t;
+        float g = l1 ? b * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * b * d;
+        if (lg.criterion != NERAF_CRIT_MSE) {
+          const float ex = expf(x), et = expf(t);
+          g += a * (ex - et) * ex;
+        }
+        dd[i] = g;
+      }
     }
 #pragma unroll
     for (int i = 0; i < kHeadRows / 8; ++i) {
@@ -246,7 +265,8 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
 }
 
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
-                  int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream) {
+                  int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream,
+                  const neraf_loss_grad* loss) {
   if (M <= 0 || N <= 0) return NERAF_OK;
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, kHeadRows));
   NERAF_REQUIRE(grid.y <= 65535, "head_backward: batch too large for one launch (%lld)", (long long)M);
@@ -257,7 +277,15 @@ int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float
     for (int64_t c = 0; c < heads; ++c) cs.ptr[c] = colsum[c];
     cs.width = head_width;
   }
-  head_backward_kernel<<<grid, 256, 0, stream>>>(dout, y, M, N, dz_f32, ld_f32, (__nv_bfloat16*)dz_bf16, ld_bf16, cs);
+  if (loss) {
+    NERAF_REQUIRE(loss->gt && loss->sums && loss->n_total > 0 && loss->criterion >= 0 && loss->criterion <= 2,
+                  "head_backward: bad neraf_loss_grad");
+    head_backward_kernel<true><<<grid, 256, 0, stream>>>(loss->gt, y, M, N, dz_f32, ld_f32, (__nv_bfloat16*)dz_bf16,
+                                                         ld_bf16, cs, *loss);
+  } else {
+    head_backward_kernel<false><<<grid, 256, 0, stream>>>(dout, y, M, N, dz_f32, ld_f32, (__nv_bfloat16*)dz_bf16,
+                                                          ld_bf16, cs, neraf_loss_grad{});
+  }
   NERAF_CHECK_LAUNCH("head_backward_kernel");
   return NERAF_OK;
 }

@@ -362,6 +362,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   const int defer_grid_grads = opt ? opt->defer_grid_grads : 0;
   int phase = opt ? opt->phase : 0;
   const int max_ctas = opt ? opt->max_ctas : 0;
+  const neraf_loss_grad* loss = opt ? opt->loss : nullptr;
   NERAF_REQUIRE(phase >= 0 && phase <= 2, "field_backward_dp: phase must be 0, 1 or 2");
   Layout l;
   NERAF_TRY(make_layout(dims, precision, B, &l));
@@ -369,7 +370,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   NERAF_TRY(check_ptr_list(weights, l.L + l.C, "weights"));
   NERAF_TRY(check_ptr_list(dweights, l.L + l.C, "dweights"));
   NERAF_TRY(check_ptr_list(dbiases, l.L + l.C, "dbiases"));
-  NERAF_REQUIRE(dout && out && ws, "field_backward: dout/out/workspace is null");
+  NERAF_REQUIRE((dout || loss) && out && ws, "field_backward: dout/out/workspace is null");
   NERAF_REQUIRE(l.G == 0 || grid_feature, "field_backward: grid_feature is null but n_grid = %d", l.G);
   NERAF_REQUIRE(!denc || denc_ld >= l.E, "field_backward: denc_ld < n_enc");
   if (ws_bytes < l.ws_bytes)
@@ -389,7 +390,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     return set_error(NERAF_ERR_UNSUPPORTED, "field_backward_dp: the fused all-reduce exists for the bf16 path only");
   if (!bf) {
     float* dzh = reinterpret_cast<float*>(at(ws, l.dzh));
-    NERAF_TRY(head_backward(dout, out, B, l.CF, dzh, l.CF, nullptr, 0, nullptr, 0, stream));
+    NERAF_TRY(head_backward(dout, out, B, l.CF, dzh, l.CF, nullptr, 0, nullptr, 0, stream, loss));
     const float* x_last = reinterpret_cast<const float*>(at(ws, l.x[last]));
     float* dz_last = reinterpret_cast<float*>(at(ws, l.dz[last]));
     for (int c = 0; c < l.C; ++c) {
@@ -444,7 +445,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     }
   }
   void* dzh = at(ws, l.dzh);
-  if (phase != 2) NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream));
+  if (phase != 2) NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream, loss));
   bool heads_contiguous = true;                      // the C head gradients form one (C*F, W) matrix?
   for (int c = 1; c < l.C; ++c) heads_contiguous = heads_contiguous && dweights[l.L + c] == dweights[l.L] + (size_t)c * l.F * l.W;
   // Fused all-reduce (data parallel): weight gradients are not stored but added into every rank's copy of the

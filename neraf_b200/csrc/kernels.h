@@ -59,7 +59,9 @@ int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int6
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
 // dz = dout * (10 - y^2/10): gradient through 10*tanh; outputs fp32 (M,N) and/or bf16 (M,N) row-major.
 // colsum (optional): per-head bias-gradient buffers, column n is added (atomics) to colsum[n / head_width][n % head_width]
+// loss (optional): dout is not read but evaluated from (y, loss->gt, loss->sums) as neraf_spectral_loss_backward does.
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
-                  int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream);
+                  int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream,
+                  const neraf_loss_grad* loss = nullptr);
 
 }  // namespace neraf

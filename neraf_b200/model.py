@@ -222,17 +222,20 @@ class GraphedTrainStep:
     static device buffers and replays; parameter gradients land in ``p.grad`` (static tensors owned by the graph),
     the loss dict is returned as static 0-d tensors.
 
-    Single process: ONE graph around the autograd calls a Trainer makes.  Data parallel (``model.process_group``):
-    the spectral loss needs its four partial sums all-reduced between forward and backward, and a captured NCCL
-    collective proved fragile (ranks hung at teardown), so the step is TWO graphs built straight from the C-ABI
-    calls -- forward + loss sums | finalize + loss gradient + backward -- with the 32-byte all-reduce issued eagerly
-    between them; ``allreduce_grads()`` then sums the single flat gradient buffer across ranks.
+    The graphs are built straight from the C-ABI calls (no autograd nodes, no tiny scalar kernels): forward + fused
+    loss | backward with the loss gradient formed inside the heads' backward kernel (``neraf_loss_grad``).  Single
+    process: ONE graph.  Data parallel (``model.process_group``): the spectral loss needs its four partial sums
+    all-reduced between forward and backward, and a captured NCCL collective proved fragile (ranks hung at teardown),
+    so the step is TWO graphs with the 32-byte all-reduce issued eagerly between them; ``allreduce_grads()`` then sums
+    the single flat gradient buffer across ranks.  With a trainable grid-feature producer (a real ResNet3D) and a
+    single process the autograd calls a Trainer makes are captured instead.
     """
 
     def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3,
                  fused_allreduce: bool = False, overlap_allreduce: bool = False,
-                 grad_dtype: torch.dtype = torch.float32):
+                 grad_dtype: torch.dtype = torch.float32, functional: Optional[bool] = None):
         self.model = model
+        self.launches_per_step = 0        # library kernels per step (counted over the last eager warm-up step)
         # Data parallel, optional: the backward is split in two graphs; everything the first one finishes (all weight
         # gradients but dW1's: 57.5 of the 60.8 MB) is all-reduced on a communication stream WHILE the second computes
         # the last dgrad and dW1 on fewer CTAs (the collective kernel needs SMs of its own: ``comm_ctas``; set
@@ -257,8 +260,13 @@ class GraphedTrainStep:
         self.static = {k: example_batch[k].to(device=dev, dtype=dtypes[k]).contiguous().clone() for k in keys}
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.group = model.process_group
-        if self.group is None:
-            self._capture_autograd(warmup)
+        functional_ok = (not model.use_grid) or isinstance(model.resnet3d, ConstantGridFeature)
+        if functional is None:
+            functional = functional_ok
+        if not functional and self.group is not None:
+            raise ValueError("the data-parallel step is built from direct library calls (functional=True)")
+        if not functional:
+            self._capture_autograd(warmup)      # a trainable ResNet3D producer: gradients flow on through autograd
         else:
             self._capture_functional(warmup)
 
@@ -280,7 +288,9 @@ class GraphedTrainStep:
             for _ in range(warmup):
                 for p in self.params:
                     p.grad = None
+                l0 = _lib.lib().neraf_launch_count()
                 run()
+                self.launches_per_step = _lib.lib().neraf_launch_count() - l0
         torch.cuda.current_stream(dev).wait_stream(side)
         for p in self.params:
             p.grad = None
@@ -289,11 +299,12 @@ class GraphedTrainStep:
             self.losses = run()
         model.field.always_repack = prev
 
-    # ---- data parallel: two graphs of direct library calls ------------------------------------------
+    # ---- graphs of direct library calls: one (single process) or two around the loss all-reduce (data parallel) ----
     def _capture_functional(self, warmup: int):
         import ctypes as C
         import torch.distributed as dist
         model, dev = self.model, self.model.device
+        world = 1 if self.group is None else dist.get_world_size(self.group)
         field = model.field
         if field.precision != "bf16" and field.precision != "fp32":
             raise ValueError("unknown precision")
@@ -312,7 +323,6 @@ class GraphedTrainStep:
         pack = torch.empty(max(pack_b.value, 16), dtype=torch.uint8, device=dev)
         ws = torch.empty(max(ws_b.value, 16), dtype=torch.uint8, device=dev)
         out = torch.empty(B, field.sound_rez, field.N_frequencies, dtype=torch.float32, device=dev)
-        dpred = torch.empty_like(out)
         self.sums = torch.zeros(5, dtype=torch.float64, device=dev)
         losses = torch.zeros(2, dtype=torch.float32, device=dev)
         # Gradient buffers.  Everything that must be summed over the ranks sits in ONE flat buffer: the weight
@@ -320,7 +330,7 @@ class GraphedTrainStep:
         # (n1, 164) matrix: the grid block dW1[:, :1024] = db1 (x) g and dg = W1[:, :1024]^T db1 are linear in db1 with g
         # replicated, so they are formed AFTER the exchange from the reduced db1 (neraf_field_grid_grads), which keeps
         # 20.9 MB out of the all-reduce.
-        defer = grid_p is not None
+        defer = grid_p is not None and self.group is not None
         n1 = weights[0].shape[0]
         ldc = (field.in_size - n_grid + 3) // 4 * 4
         red_w = list(weights[1:]) if defer else list(weights)
@@ -329,7 +339,7 @@ class GraphedTrainStep:
         # Fused all-reduce (experimental): the flat buffer lives in symmetric memory and the weight-gradient GEMMs add
         # their tiles into every rank's copy through its multicast alias.  Otherwise plain memory + one NCCL all-reduce.
         self.flat_grad, mc_ptr = None, 0
-        if self.fused_allreduce and field.precision == "bf16" and dist.get_world_size(self.group) > 1:
+        if self.fused_allreduce and field.precision == "bf16" and world > 1:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 self.flat_grad = symm_mem.empty(sum(sizes), dtype=torch.float32, device=dev)
@@ -346,11 +356,11 @@ class GraphedTrainStep:
         dws = [v.view_as(t) for v, t in zip(parts[:nw], red_w)]
         compact = parts[nw] if defer else None
         dbs = [v.view_as(t) for v, t in zip(parts[nw + (1 if defer else 0):], biases)]
-        dgrid = torch.zeros_like(grid_p) if defer else None
+        dgrid = torch.zeros_like(grid_p) if grid_p is not None else None
         if defer:
             dws = [torch.zeros_like(weights[0])] + dws
-        order = list(weights) + list(biases) + ([grid_p] if defer else [])
-        views = dws + dbs + ([dgrid] if defer else [])
+        order = list(weights) + list(biases) + ([grid_p] if grid_p is not None else [])
+        views = dws + dbs + ([dgrid] if grid_p is not None else [])
         for t, v in zip(order, views):
             t.grad = v
         qs = _lib.Queries()
@@ -365,10 +375,14 @@ class GraphedTrainStep:
         w_sc = 0.0 if model.criterion_name == "MSE" else 1e-1 * model.loss_factor
         w_mag = model.loss_factor
         n_local = out.numel()
-        n_total = n_local * dist.get_world_size(self.group)
+        n_total = n_local * world
+        # the loss gradient is formed inside the backward's head kernel from (out, target, reduced sums)
+        lg = _lib.LossGrad()
+        lg.gt, lg.n_total, lg.criterion, lg.sums = st["data"].data_ptr(), n_total, crit, self.sums.data_ptr()
+        lg.w_sc, lg.w_mag = w_sc, w_mag
         w_arr, b_arr = _lib.ptr_array(weights), _lib.ptr_array(biases)
         dw_arr, db_arr = _lib.ptr_array(dws), _lib.ptr_array(dbs)
-        self._keep = (pack, ws, out, dpred, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims)
+        self._keep = (pack, ws, out, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims, lg)
         self._grad_views = list(zip(order, views))
 
         mc = _lib.Multicast()
@@ -377,13 +391,15 @@ class GraphedTrainStep:
         self._bias_region = self.flat_grad[n_weight_elems:]
         zero_stream = torch.cuda.Stream(device=dev) if self.nvls else None
 
-        self.overlap = bool(self.overlap_allreduce and not self.nvls and field.precision == "bf16" and len(weights) > 2)
+        self.overlap = bool(self.overlap_allreduce and not self.nvls and field.precision == "bf16" and len(weights) > 2
+                            and defer)
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
         opt1, opt2 = _lib.DpOptions(), _lib.DpOptions()
         for o in (opt1, opt2):
             o.mc = C.pointer(mc) if self.nvls else None
             o.dw0_compact = _lib.ptr(compact)
             o.defer_grid_grads = 1 if defer else 0
+            o.loss = C.pointer(lg)
         opt1.phase, opt1.max_ctas = (1 if self.overlap else 0), 0
         opt2.phase, opt2.max_ctas = 2, max(2, (sm_count - self.comm_ctas) // 2 * 2)
         # regions of the flat buffer: what the first backward graph finishes | what the second one does
@@ -406,24 +422,26 @@ class GraphedTrainStep:
             _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
                                                pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
                                                out.data_ptr(), 1, s))
-            _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
-                                                    self.sums.data_ptr(), 0, s))
+            if self.group is None:         # sums + both losses in one kernel
+                _lib.check(lib.neraf_spectral_loss_forward(out.data_ptr(), st["data"].data_ptr(), n_local, crit, w_sc,
+                                                           w_mag, self.sums.data_ptr(), losses.data_ptr(), s))
+            else:
+                _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
+                                                        self.sums.data_ptr(), 0, s))
             if self.nvls:
                 torch.cuda.current_stream(dev).wait_stream(zero_stream)
 
         def backward_part():
             s = _lib.stream_ptr(dev)
-            _lib.check(lib.neraf_spectral_loss_finalize(self.sums.data_ptr(), n_total, crit, w_sc, w_mag,
-                                                        losses.data_ptr(), s))
-            _lib.check(lib.neraf_spectral_loss_backward(out.data_ptr(), st["data"].data_ptr(), n_local, n_total, crit,
-                                                        self.sums.data_ptr(), None, None, w_sc, w_mag,
-                                                        dpred.data_ptr(), s))
-            _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
+            if self.group is not None:
+                _lib.check(lib.neraf_spectral_loss_finalize(self.sums.data_ptr(), n_total, crit, w_sc, w_mag,
+                                                            losses.data_ptr(), s))
+            _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, None, out.data_ptr(),
                                                    _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
                                                    dw_arr, db_arr, _lib.ptr(dgrid), None, 0, C.byref(opt1), s))
 
         def backward_part2():
-            _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, dpred.data_ptr(), out.data_ptr(),
+            _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, None, out.data_ptr(),
                                                    _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
                                                    dw_arr, db_arr, _lib.ptr(dgrid), None, 0, C.byref(opt2),
                                                    _lib.stream_ptr(dev)))
@@ -435,15 +453,35 @@ class GraphedTrainStep:
                                                       dgrid.data_ptr(), _lib.stream_ptr(dev)))
         self._grid_part = grid_part
 
+        if model.criterion_name == "MSE":
+            self.losses = {"audio_mse": losses[1]}
+        else:
+            self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        if self.group is None:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    l0 = lib.neraf_launch_count()
+                    forward_part()
+                    backward_part()
+                    self.launches_per_step = lib.neraf_launch_count() - l0
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                forward_part()
+                backward_part()
+            return
         with torch.cuda.stream(side):
             for _ in range(warmup):
+                l0 = lib.neraf_launch_count()
                 forward_part()
                 dist.all_reduce(self.sums[:4], group=self.group)
                 backward_part()
                 if self.overlap:
                     backward_part2()
+                self.launches_per_step = lib.neraf_launch_count() - l0
                 dist.all_reduce(self._bias_region if self.nvls else self.flat_grad, group=self.group)
                 grid_part()
         torch.cuda.current_stream(dev).wait_stream(side)
@@ -457,10 +495,6 @@ class GraphedTrainStep:
             self.graph_bwd2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_bwd2):
                 backward_part2()
-        if model.criterion_name == "MSE":
-            self.losses = {"audio_mse": losses[1]}
-        else:
-            self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
 
     def _reduce(self, region: torch.Tensor, dtype: torch.dtype) -> None:
         """Sum ``region`` of the flat gradient buffer over the ranks (NCCL), optionally through a bf16 copy."""
@@ -536,6 +570,8 @@ class GraphedTrainStep:
                     dst.copy_(src, non_blocking=True)
         if self.group is None:
             self.graph.replay()
+            for t, v in getattr(self, "_grad_views", ()):          # eager steps in between may have replaced .grad
+                t.grad = v
         else:
             import torch.distributed as dist
             self.graph_fwd.replay()

@@ -186,13 +186,14 @@ def test_cpu_parameters_fail_loudly():
         f(torch.zeros(2, 1187))
 
 
-def test_graphed_step_and_prefetch_equal_autograd_step():
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_graphed_step_and_prefetch_equal_autograd_step(prec):
     """One-graph GraphedTrainStep (N = 1) fed pinned host batches -- directly and through prefetch() -- reproduces the
     eager plugin calls, batch after batch."""
     from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioModel, NeRAFAudioModelConfig
     dev = cuda()
     shape, B = syn.RAF, 320
-    cfg = NeRAFAudioModelConfig(dataset="RAF", precision="bf16")
+    cfg = NeRAFAudioModelConfig(dataset="RAF", precision=prec)
     model = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)))
     model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
     model = model.to(dev)
@@ -209,14 +210,24 @@ def test_graphed_step_and_prefetch_equal_autograd_step():
         return {k: float(v) for k, v in ld.items()}, [p.grad.clone() for p in params]
 
     refs = [eager(b) for b in host]
-    step = GraphedTrainStep(model, host[0])
+    step = GraphedTrainStep(model, host[0], functional=False)      # the autograd calls, captured
+    assert step.launches_per_step > 0
+    for i in (2, 0):
+        got = step(host[i])
+        torch.cuda.synchronize()
+        for k, v in refs[i][0].items():
+            assert abs(float(got[k]) - v) < 1e-5 * abs(v), (k, i)
+        for p, r in zip(params, refs[i][1]):
+            assert rel_fro(p.grad, r) < 1e-4, i        # same kernels; the bias sums' atomics re-order
+    step = GraphedTrainStep(model, host[0])                        # direct library calls, fused loss gradient
+    assert 0 < step.launches_per_step
 
     def check(got, i):
         torch.cuda.synchronize()
         for k, v in refs[i][0].items():
             assert abs(float(got[k]) - v) < 1e-5 * abs(v), (k, i)
         for p, r in zip(params, refs[i][1]):
-            assert rel_fro(p.grad, r) < 1e-5, i
+            assert rel_fro(p.grad, r) < 1e-4, i        # same kernels; the bias sums' atomics re-order
 
     for i in (1, 0, 2):
         check(step(host[i]), i)
