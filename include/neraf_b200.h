@@ -245,6 +245,49 @@ NERAF_API int neraf_griffinlim(const neraf_gl_params* p, int64_t n_items, int32_
                      float* wave, neraf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Acoustic metrics of rendered impulse responses, batched (replaces the per-RIR numpy of NeRAF_helper.py:
+ * compute_t60 :48-64 / measure_rt60_advance :66-77 (pyroomacoustics measure_rt60), measure_clarity :104-107,
+ * measure_edt :124-146, called from NeRAF_evaluator.py:131-190 after a device -> host copy of every waveform)
+ *
+ * wave : dev fp32 (n_signals, n_samples), e.g. the output of neraf_griffinlim viewed as (N*C, L).
+ * t60  : dev f64 (n_signals) or NULL.  t60_highpass_hz == 0: measure_rt60(h, fs, t60_decay_db) (SoundSpaces: 30);
+ *        > 0: the response is first high-passed (torchaudio highpass_biquad, Q 0.707, clamped to [-1, 1]) into the
+ *        workspace (n_signals * n_samples floats) -- RAF: 200 Hz, decay 10.  A failed fit reads -1 (compute_t60's except).
+ * edt  : dev f64 (n_signals) or NULL: measure_edt(h, fs, decay_db = 10); NaN when the curve never drops 10 dB.
+ * c50  : dev f64 (n_signals) or NULL: measure_clarity(h, 50 ms, fs).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_samples;
+  double fs;
+  float t60_decay_db;
+  double t60_highpass_hz;
+} neraf_metric_params;
+
+NERAF_API int neraf_acoustic_metrics(const neraf_metric_params* p, const float* wave, int64_t n_signals,
+                           void* workspace, size_t workspace_bytes, double* t60, double* edt, double* c50,
+                           neraf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Audio data feed (replaces the per-sample host work of NeRAFDataset / SoundSpacesDataset.get_data,
+ * NeRAF_dataset.py:89-132 and :272-296, and the DataLoader collate in NeRAF_datamanager.py:80-119)
+ *
+ * cache        : dev fp32 (n_rirs * n_frames, column_floats): row rir * n_frames + t is the target column
+ *                log(|STFT[rir][:, :, t]| + 1e-3) flattened (C, F); columns past the end of a recording are filled
+ *                the reference's way (log(min + 1e-3)) when the cache is built, so dataset index == cache row
+ *                (get_id_tmp, NeRAF_dataset.py:86-87).
+ * *_table      : dev f64 (n_rirs, 3) poses per RIR (dataparser outputs).
+ * sample_idx   : dev i64 (batch) dataset indices in [0, n_rirs * n_frames).
+ * Outputs (dev, the batch dict of NeRAF_dataset.py:129-130): data fp32 (batch, column_floats); time_query i64 (batch);
+ * audio_idx i64 (batch) or NULL; mic_pose / source_pose / rot f64 (batch, 3).
+ * status       : dev i32 or NULL: set to 1 when an index was out of range (that sample then reads row 0).
+ * ---------------------------------------------------------------------------------------------- */
+NERAF_API int neraf_gather_batch(const float* cache, int64_t n_rirs, int32_t n_frames, int32_t column_floats,
+                       const double* mic_table, const double* source_table, const double* rot_table,
+                       const int64_t* sample_idx, int64_t batch, float* data, int64_t* time_query,
+                       int64_t* audio_idx, double* mic_pose, double* source_pose, double* rot,
+                       int32_t* status, neraf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Operator-level entry points (used by the dense module path and by the parity tests)
  * ---------------------------------------------------------------------------------------------- */
 /* fp32 CUDA-core GEMM:  C[m,n] (+)= act( sum_k A[m*a_rs + k*a_cs] * B[n*b_rs + k*b_cs] + bias[n] ) * gate'

@@ -69,6 +69,10 @@ class DpOptions(C.Structure):
                 ("phase", C.c_int32), ("max_ctas", C.c_int32), ("loss", C.POINTER(LossGrad))]
 
 
+class MetricParams(C.Structure):     # neraf_metric_params
+    _fields_ = [("n_samples", C.c_int32), ("fs", C.c_double), ("t60_decay_db", C.c_float), ("t60_highpass_hz", C.c_double)]
+
+
 class GlParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop", C.c_int32), ("n_frames", C.c_int32),
                 ("n_iter", C.c_int32), ("momentum", C.c_float), ("input_is_log", C.c_int32)]
@@ -95,6 +99,8 @@ SIGNATURES = {
     "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),
     "neraf_spectral_loss_sums": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
     "neraf_spectral_loss_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp]),
+    "neraf_acoustic_metrics": (C.c_int, [C.POINTER(MetricParams), _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "neraf_gather_batch": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "neraf_spectral_loss_forward": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp]),
     "neraf_spectral_loss_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _vp]),
     "neraf_griffinlim_sizes": (C.c_int, [C.POINTER(GlParams), _i64, C.POINTER(_sz)]),

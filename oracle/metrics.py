@@ -21,7 +21,9 @@ def measure_clarity(signal: np.ndarray, time: float = 50, fs: int = 44100) -> fl
 
 
 def _schroeder_db(h: np.ndarray) -> np.ndarray:
-    power = np.asarray(h, dtype=np.float64) ** 2
+    """dtype-preserving like pyroomacoustics (``h = np.array(h); power = h ** 2``): a float32 response gives a float32
+    running sum from the tail and a float32 curve."""
+    power = np.array(h) ** 2
     energy = np.cumsum(power[::-1])[::-1]
     i_nz = np.max(np.where(energy > 0)[0])
     energy = energy[:i_nz]
@@ -44,18 +46,17 @@ def measure_edt(h: np.ndarray, fs: float = 44100, decay_db: float = 10) -> float
 
 
 def measure_rt60(h: np.ndarray, fs: float = 1, decay_db: float = 60) -> float:
-    """pyroomacoustics.experimental.measure_rt60 restated (Schroeder integration, -5 dB .. -5-decay_db)."""
+    """pyroomacoustics.experimental.measure_rt60 restated (Schroeder integration, -5 dB .. -5-decay_db).  Raises
+    ValueError (numpy's, on an empty ``np.where``) when the curve has no such span, like the original."""
+    fs = float(fs)
     e_db = _schroeder_db(h)
     min_energy_db = -np.min(e_db)
     if min_energy_db - 5 < decay_db:
         decay_db = min_energy_db
     i_5db = np.min(np.where(e_db < -5)[0])
-    e_5db = e_db[i_5db]
     t_5db = i_5db / fs
-    below = np.where(e_db < -5 - decay_db)[0]
-    i_decay = np.min(below) if len(below) else len(e_db)
+    i_decay = np.min(np.where(e_db < -5 - decay_db)[0])
     t_decay = i_decay / fs
-    del e_5db
     return float((60 / decay_db) * (t_decay - t_5db))
 
 
@@ -81,10 +82,18 @@ def highpass_biquad(x: np.ndarray, fs: float, cutoff: float = 200.0, q: float = 
 
 
 def t60_soundspaces(h: np.ndarray, fs: float) -> float:
-    """NeRAF_helper.py:58-59."""
-    return measure_rt60(h, fs=fs, decay_db=30)
+    """NeRAF_helper.py:48-64 (``compute_t60``, advanced=False): a failed fit reads -1."""
+    try:
+        return measure_rt60(h, fs=fs, decay_db=30)
+    except (ValueError, IndexError):
+        return -1.0
 
 
 def t60_raf(h: np.ndarray, fs: float) -> float:
-    """NeRAF_helper.py:67-77 (``measure_rt60_advance``)."""
-    return measure_rt60(highpass_biquad(h, fs, 200.0), fs, decay_db=10)
+    """NeRAF_helper.py:48-77 (``compute_t60`` advanced=True -> ``measure_rt60_advance``).  The filtered signal is
+    float32, as torchaudio returns it for a float32 waveform."""
+    try:
+        y = highpass_biquad(h, fs, 200.0)
+        return measure_rt60(y.astype(np.asarray(h).dtype), fs, decay_db=10)
+    except (ValueError, IndexError):
+        return -1.0

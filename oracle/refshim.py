@@ -60,3 +60,40 @@ def load():
     from NeRAF.NeRAF_evaluator import STFTLoss
     import NeRAF.NeRAF_helper as helper
     return NeRAFAudioSoundField, STFTLoss, helper
+
+
+def load_datasets():
+    """Returns the reference's real (RAFDataset, SoundSpacesDataset) classes (NeRAF_dataset.py).
+
+    NeRAF_dataparser.py:16,21 needs nerfstudio's dataparser base classes (only subclassed, never called by the
+    datasets) and NeRAF_dataset.py:21 imports librosa (used by the RAF wav loader only): stand-ins for both, so the
+    SoundSpaces ``get_data`` path -- np.load of a magnitude file, one column, log, poses -- runs unmodified.
+    """
+    install()
+    import dataclasses
+
+    class _Cfg:
+        pass
+
+    @dataclasses.dataclass
+    class _Outputs:
+        pass
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    for name in ("nerfstudio", "nerfstudio.data", "nerfstudio.data.dataparsers"):
+        mod(name).__path__ = []          # make them packages
+    mod("nerfstudio.data.dataparsers.base_dataparser", DataParser=_Cfg, DataParserConfig=_Cfg, DataparserOutputs=_Outputs)
+    mod("nerfstudio.data.scene_box", SceneBox=_Cfg)
+    if "librosa" not in sys.modules:
+        try:
+            import librosa  # noqa: F401
+        except ImportError:
+            mod("librosa")
+    from NeRAF.NeRAF_dataset import RAFDataset, SoundSpacesDataset
+    return RAFDataset, SoundSpacesDataset
