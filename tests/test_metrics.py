@@ -105,3 +105,28 @@ def test_reference_signatures_and_shapes():
     m = M.acoustic_metrics(h.view(2, 4, -1), shape.fs)
     assert m["t60"].shape == (2, 4) and m["edt"].dtype == torch.float64
     assert M.acoustic_metrics(h[:0], shape.fs)["c50"].shape == (0,)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["RAF", "SoundSpaces"])
+def test_evaluators_match_the_reference_evaluators(golden_dir, name):
+    """Golden: the reference's RAFEvaluator / SoundSpacesEvaluator.get_full_metrics run per RIR
+    (oracle/make_golden_evaluator.py); here per RIR through the same signature and for all RIRs in one batch."""
+    from neraf_b200.evaluator import RAFEvaluator, SoundSpacesEvaluator
+    cuda()
+    z = np.load(os.path.join(golden_dir, f"evaluator_{name}.npz"))
+    shape = syn.RAF if name == "RAF" else syn.SOUNDSPACES
+    ev = (RAFEvaluator if name == "RAF" else SoundSpacesEvaluator)(fs=shape.fs)
+    keys, rows = [str(k) for k in z["keys"]], z["rows"]
+    batch = ev.get_full_metrics_batch(z["gt_ff"], z["prd"], z["log_gt"])
+    tol = {"audio_T60": 0.15, "audio_T60_mean_error": 0.15, "audio_total_invalids_T60": 0.0,
+           "audio_stft_error": 1e-3, "audio_EDT": 12.0 / shape.fs, "audio_C50": 1e-3}
+    for i in range(rows.shape[0]):
+        one = ev.get_full_metrics(None, None, z["gt_ff"][i], z["prd"][i], z["prd"][i], None, z["log_gt"][i])
+        assert list(one) == keys == list(batch[i])
+        for k, ref in zip(keys, rows[i]):
+            for got in (one[k], batch[i][k]):
+                if np.isnan(ref):
+                    assert np.isnan(got), (k, i)
+                else:
+                    assert abs(got - ref) <= tol[k] + 1e-12, (k, i, got, ref)

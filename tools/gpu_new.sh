@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_datafeed.py tests/test_metrics.py -m gpu -q -x 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_metrics.py -m gpu -q -x 2>&1 | tail -25
