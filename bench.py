@@ -22,6 +22,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 FLOP_PER_COLUMN_TRAIN = {1: 2 * 44769136, 2: 2 * 44770672}       # SURVEY.md section 8d (factored layer 1)
@@ -310,6 +311,30 @@ def main():
             step_graphed_prefetch(host_batch)
         ms_e2e_p, _, _ = timed(host_batch, args.steps, read_loss=True, fn=step_graphed_prefetch)
     ms_e2e = ms_e2e_p if ms_e2e_p is not None else ms_e2e_eager
+    ms_e2e_feed = None
+    if graphed is not None:
+        # ... and with the GPU-resident data feed (neraf_b200.datafeed): the batch is gathered on the device from a
+        # cache of target columns straight into the graph's static buffers; nothing crosses PCIe but the loss
+        from neraf_b200.datafeed import ResidentAudioFeed
+        n_cache = 2048
+        gf = torch.Generator().manual_seed(77 + rank)
+        cache = (torch.randn(n_cache, shape.T, shape.C, shape.F, generator=gf) - 3.0).to(dev)
+        pose = lambda: syn.make_batch(shape, n_cache, seed=5 + rank)          # noqa: E731
+        pb = pose()
+        feed = ResidentAudioFeed(cache, pb["mic_pose"], pb["source_pose"], pb["rot"], shape.T, B, seed=1, rank=rank,
+                                 world_size=world, drop_last=True)
+        counter = [0]
+
+        def step_graphed_feed(_):
+            feed.next_train(counter[0], out=graphed.static)
+            counter[0] += 1
+            ld = step_value(graphed.static)
+            return sum(ld.values())
+        for _ in range(3):
+            step_graphed_feed(None)
+        ms_e2e_feed, _, _ = timed(None, args.steps, read_loss=True, fn=step_graphed_feed)
+        feed.check()
+        del cache
     clocks = sampler.stop()
 
     def max_over_ranks(x):
@@ -351,6 +376,10 @@ def main():
         "e2e_graphed_no_prefetch": None if ms_e2e_g is None else e2e_entry(
             ms_e2e_g, "GraphedTrainStep(pinned host batch) -> loss.item(): the batch is copied into the graph's static "
                       "buffers on the compute stream, then the graph replays"),
+        "e2e_resident_feed": None if ms_e2e_feed is None else dict(e2e_entry(
+            ms_e2e_feed, "ResidentAudioFeed.next_train(out=static buffers) -> GraphedTrainStep -> loss.item(): batches "
+                         "gathered on the device from a resident cache of target columns (neraf_gather_batch), the "
+                         "epoch permutation uploaded once per epoch"), h2d_bytes_per_step=8 * B),
         "e2e_eager": e2e_entry(
             ms_e2e_eager, "NeRAFAudioModel.get_outputs(pinned host batch) -> get_loss_dict -> backward -> loss.item(): the "
                           "plugin calls a nerfstudio Trainer makes, one C-ABI call per autograd node"),
@@ -428,7 +457,42 @@ def main():
                           "api": "NeRAFAudioModel.render_rirs(host poses) -> waveforms on the host (field forward over T bins "
                                  "+ Griffin-Lim)", "d2h_bytes_per_call": wr.numel() * 4}
 
+        # ---- acoustic metrics of the rendered RIRs (T60 / EDT / C50), one launch for the whole batch
+        from neraf_b200.metrics import acoustic_metrics
+        wd = gl.render(log_d, init)                                    # (n, C, L) on the device
+        advanced = shape.C == 1
+        for _ in range(2):
+            acoustic_metrics(wd, shape.fs, advanced)
+        barrier()
+        s.record()
+        for _ in range(k_gl):
+            mt = acoustic_metrics(wd, shape.fs, advanced)
+            host_m = {k: v.cpu() for k, v in mt.items()}
+        e.record()
+        barrier()
+        m_ms = max_over_ranks(s.elapsed_time(e)) / k_gl
+        line["acoustic_metrics"] = {"metric": "rirs_measured_per_sec", "value": n * world / (m_ms * 1e-3), "unit": "RIR/s",
+                                    "rirs_per_call_per_gpu": n, "ms_per_call": m_ms,
+                                    "api": "neraf_b200.metrics.acoustic_metrics(device waveforms) -> T60, EDT, C50 on the host",
+                                    "d2h_bytes_per_call": sum(v.numel() * 8 for v in host_m.values())}
+        del wd
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if args.gl_rirs > 0:
+            from oracle import metrics as omet
+            n_cpu = 32
+            rir_c, _, _ = syn.make_rirs(shape, n_cpu, seed=0)
+            hs = rir_c.reshape(-1, rir_c.shape[-1]).numpy().astype(np.float32)
+            t0 = time.perf_counter()
+            for h1 in hs:
+                (omet.t60_raf if shape.C == 1 else omet.t60_soundspaces)(h1, shape.fs)
+                omet.measure_edt(h1, shape.fs)
+                omet.measure_clarity(h1, fs=shape.fs)
+            dt = time.perf_counter() - t0
+            line["acoustic_metrics"]["cpu_baseline"] = {
+                "value": n_cpu / dt, "unit": "RIR/s", "cores": 1, "kind": "port",
+                "sample": f"{n_cpu} {shape.name}-shaped RIRs, oracle restatement of NeRAF_helper.py compute_t60 / "
+                          "measure_edt / measure_clarity (numpy, one RIR at a time like the reference)"}
         res = time_cpu_baseline(shape, B, steps=10, warmup=2)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if args.gl_rirs > 0:

@@ -110,7 +110,11 @@ class ResidentAudioFeed:
     def _next_indices(self) -> torch.Tensor:
         epoch, lo, hi = self.sampler.next_range()
         if epoch != self._epoch:
-            self._epoch, self._perm = epoch, self.sampler.permutation(epoch).to(self.device)
+            # the epoch's permutation is drawn ON the device (Philox, seeded like the host sampler: every rank gets the
+            # same order) -- a host randperm of 10^5..10^7 indices plus its upload stalls the step for milliseconds
+            g = torch.Generator(device=self.device)
+            g.manual_seed(self.sampler.seed * 1_000_003 + epoch)
+            self._epoch, self._perm = epoch, torch.randperm(len(self), generator=g, device=self.device)
         return self._perm[lo:hi]
 
     # -- gather ----------------------------------------------------------------------------------

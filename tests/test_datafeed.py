@@ -136,6 +136,22 @@ def test_gather_at_training_size_against_the_oracle_and_into_static_buffers():
 
 
 @pytest.mark.gpu
+def test_two_rank_feeds_split_the_global_batch():
+    """Data parallel: with one seed, rank r's batch is rows [r*B, (r+1)*B) of what a single feed with batch 2*B draws."""
+    dev = cuda()
+    n, T = 40, 12
+    cache = torch.randn(n, T, 2, 9, device=dev)
+    poses = [torch.rand(n, 3, dtype=torch.float64) for _ in range(3)]
+    one = ResidentAudioFeed(cache, *poses, T, 64, seed=9)
+    halves = [ResidentAudioFeed(cache, *poses, T, 32, seed=9, rank=r, world_size=2) for r in (0, 1)]
+    for step in range(2 * (n * T // 64 + 1)):                     # across an epoch boundary, with a partial last batch
+        whole = one.next_train(step)[1]
+        parts = [f.next_train(step)[1] for f in halves]
+        for k in KEYS:
+            assert torch.equal(torch.cat([p[k] for p in parts]), whole[k]), (k, step)
+
+
+@pytest.mark.gpu
 def test_gather_edge_cases():
     dev = cuda()
     feed = ResidentAudioFeed(torch.arange(2 * 3 * 1 * 5, dtype=torch.float32, device=dev).reshape(2, 3, 1, 5),
