@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(512, 1) griffinlim_kernel(GlArgs a) {
     for (int it = 0; it <= a.n_iter; ++it) {
       // One frame per warp at a time; frames that overlap in time must not overlap-add concurrently: frame t has
       // colour t % n_colors, same-coloured frames are >= n_colors hops apart, one barrier per colour.  (Walking a block
-      // of consecutive frames per warp instead saves one of SoundSpaces' 8 rounds and measured no faster.)
+      // of consecutive frames per warp instead saves one of SoundSpaces' 8 rounds and measured no faster; two frames
+      // per warp for the 512-point transform halves the rounds but spills at 128 registers and ran 1.9x slower: the
+      // kernel is throughput-bound on the shared-memory pipe, not on rounds.)
       auto frame = [&](int t) {
         const float* mag_row = mag_sig + (long long)t * a.F;
         if (it == 0) {
