@@ -70,6 +70,25 @@ def test_size_queries_and_validation_without_gpu(built):
     assert lib.neraf_griffinlim_sizes(C.byref(p), 16, C.byref(ws)) == 1
 
 
+def test_feed_and_metrics_argument_validation_without_gpu(built):
+    """The widened entry points reject bad arguments before any launch (no device needed)."""
+    from neraf_b200 import _lib
+    lib = _lib.lib()
+    z = None
+    # empty batch / no signals: a no-op, whatever the pointers
+    assert lib.neraf_gather_batch(z, 4, 60, 513, z, z, z, z, 0, z, z, z, z, z, z, z, z) == 0
+    assert lib.neraf_gather_batch(z, 4, 60, 513, z, z, z, z, 8, z, z, z, z, z, z, z, z) == 1
+    assert b"gather_batch" in lib.neraf_last_error()
+    assert lib.neraf_gather_batch(z, 4, 0, 513, z, z, z, z, 0, z, z, z, z, z, z, z, z) == 1
+    mp = _lib.MetricParams()
+    mp.n_samples, mp.fs, mp.t60_decay_db, mp.t60_highpass_hz = 15104, 48000.0, 10.0, 200.0
+    assert lib.neraf_acoustic_metrics(C.byref(mp), z, 0, z, 0, z, z, z, z) == 0
+    assert lib.neraf_acoustic_metrics(C.byref(mp), z, 4, z, 0, z, z, z, z) == 1
+    mp.n_samples = 1
+    assert lib.neraf_acoustic_metrics(C.byref(mp), z, 0, z, 0, z, z, z, z) == 1
+    assert b"acoustic_metrics" in lib.neraf_last_error()
+
+
 def test_product_modules_fail_loudly_without_gpu(built):
     from neraf_b200 import _lib
     from neraf_b200.field import NeRAFAudioSoundField
