@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 4
+#define NERAF_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))
@@ -135,9 +135,15 @@ NERAF_API int neraf_field_backward(const neraf_field_dims* dims, int precision, 
  *                W1[:, :n_grid]^T db1).  Both are LINEAR in db1 and g is replicated, so under data parallelism they are
  *                formed once from the all-reduced db1 by neraf_field_grid_grads -- 20.9 MB less to all-reduce.
  *   dw0_compact (needs defer_grid_grads): the per-query block of dW1 is written to this (trunk[0], n_enc) fp32 buffer
- *                with row stride round_up(n_enc, 4) instead of into the strided dweights[0][:, n_grid:], so that
+ *                with row stride round_up(n_enc, 8) instead of into the strided dweights[0][:, n_grid:], so that
  *                everything that must be all-reduced can sit in one contiguous buffer WITHOUT the grid block;
  *                neraf_field_grid_grads copies it back.
+ *   dweights_bf16 (needs defer_grid_grads; not with mc): n_trunk + n_channels bf16 matrices; the weight-gradient GEMMs
+ *                store their results THERE, rounded to bf16 (TMA stores from the epilogue), instead of fp32 into
+ *                dweights / dw0_compact -- for a bf16 gradient exchange there is then no fp32 -> bf16 pass over the
+ *                gradients at all.  Entry 0 is the compact (trunk[0], round_up(n_enc, 8)) block, entry l >= 1 has the
+ *                shape of dweights[l] (all row lengths are multiples of 8); head entries must be contiguous.  Bases
+ *                16-byte aligned.  Bias gradients (and dgrid / denc) stay fp32.
  *   phase      : 0 = the whole backward.  1 = everything except the last dgrad (the gradient of layer 1's output) and
  *                the per-query block of dW1 -- after it, every gradient except dW1 / db1 is final and can be
  *                all-reduced; 2 = exactly the rest, to be launched while that all-reduce runs.
@@ -173,6 +179,7 @@ typedef struct {
   int32_t phase;
   int32_t max_ctas;
   const neraf_loss_grad* loss;   /* NULL: read the upstream gradient from dout */
+  void* const* dweights_bf16;    /* NULL: fp32 weight gradients in dweights / dw0_compact */
 } neraf_dp_options;
 
 NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t batch, const float* dout,

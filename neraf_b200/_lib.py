@@ -66,7 +66,8 @@ class LossGrad(C.Structure):        # neraf_loss_grad
 
 class DpOptions(C.Structure):
     _fields_ = [("mc", C.POINTER(Multicast)), ("dw0_compact", C.c_void_p), ("defer_grid_grads", C.c_int32),
-                ("phase", C.c_int32), ("max_ctas", C.c_int32), ("loss", C.POINTER(LossGrad))]
+                ("phase", C.c_int32), ("max_ctas", C.c_int32), ("loss", C.POINTER(LossGrad)),
+                ("dweights_bf16", C.POINTER(C.c_void_p))]
 
 
 class MetricParams(C.Structure):     # neraf_metric_params

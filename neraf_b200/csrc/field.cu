@@ -363,6 +363,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   int phase = opt ? opt->phase : 0;
   const int max_ctas = opt ? opt->max_ctas : 0;
   const neraf_loss_grad* loss = opt ? opt->loss : nullptr;
+  void* const* dw16 = opt ? opt->dweights_bf16 : nullptr;
   NERAF_REQUIRE(phase >= 0 && phase <= 2, "field_backward_dp: phase must be 0, 1 or 2");
   Layout l;
   NERAF_TRY(make_layout(dims, precision, B, &l));
@@ -386,6 +387,18 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   }
 
   NERAF_REQUIRE(!dw0_compact || defer_grid_grads, "field_backward_dp: dw0_compact needs defer_grid_grads");
+  NERAF_REQUIRE(!dw16 || (defer_grid_grads && !mc && precision == NERAF_PREC_BF16),
+                "field_backward_dp: dweights_bf16 needs the bf16 path with defer_grid_grads and no multicast");
+  if (dw16) {
+    for (int i = 0; i < l.L + l.C; ++i)
+      NERAF_REQUIRE(dw16[i] && ((uintptr_t)dw16[i] & 15) == 0, "field_backward_dp: dweights_bf16[%d] is null or misaligned", i);
+    for (int c = 1; c < l.C; ++c)
+      NERAF_REQUIRE((uint8_t*)dw16[l.L + c] == (uint8_t*)dw16[l.L] + (size_t)c * l.F * l.W * 2,
+                    "field_backward_dp: bf16 head gradients must be contiguous");
+    for (int i = 1; i < l.L; ++i)
+      NERAF_REQUIRE(l.k[i] % 8 == 0, "field_backward_dp: dweights_bf16 needs layer widths that are multiples of 8");
+    NERAF_REQUIRE(l.W % 8 == 0, "field_backward_dp: dweights_bf16 needs a feature width that is a multiple of 8");
+  }
   if (!bf && (mc || defer_grid_grads || phase))
     return set_error(NERAF_ERR_UNSUPPORTED, "field_backward_dp: the fused all-reduce exists for the bf16 path only");
   if (!bf) {
@@ -476,9 +489,13 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     MegaJob& j = jobs[nj++];
     j = make_wgrad_job(l.CF, l.W, B, dzh, l.ld_h, at(ws, l.x[last]), l.ldx[last], -1);
     j.wait_all = 0;
-    j.epi.out_f32 = heads_contiguous ? dweights[l.L] : reinterpret_cast<float*>(at(ws, l.dwh));
-    j.epi.ld_f32 = l.W;
-    NERAF_TRY(mc_alias(j.epi.out_f32, &j.epi.out_f32_multicast));
+    if (dw16) {
+      j.epi.out_bf16 = dw16[l.L]; j.epi.ld_bf16 = l.W;
+    } else {
+      j.epi.out_f32 = heads_contiguous ? dweights[l.L] : reinterpret_cast<float*>(at(ws, l.dwh));
+      j.epi.ld_f32 = l.W;
+      NERAF_TRY(mc_alias(j.epi.out_f32, &j.epi.out_f32_multicast));
+    }
   }
   for (int i = last; i >= 0; --i) {
     if (phase == 2 && i > 1) continue;
@@ -500,12 +517,17 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     MegaJob& w = jobs[nj++];                           // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
     if (i > 0) {
       w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
-      w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
-      NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
+      if (dw16) {
+        w.epi.out_bf16 = dw16[i]; w.epi.ld_bf16 = l.k[i];
+      } else {
+        w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
+        NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
+      }
     } else {
       w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
       w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
-      if (dw0_compact) { w.epi.out_f32 = dw0_compact; w.epi.ld_f32 = round_up(l.E, 4); }   // (n_1, E) with 16-byte rows
+      if (dw0_compact) { w.epi.out_f32 = dw0_compact; w.epi.ld_f32 = round_up(l.E, 8); }   // (n_1, E) with 32-byte rows
+      if (dw16) { w.epi.out_f32 = nullptr; w.epi.out_bf16 = dw16[0]; w.epi.ld_bf16 = round_up(l.E, 8); }
       NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
       if (denc) {
         MegaJob& e = jobs[nj++];
@@ -515,7 +537,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     }
   }
   NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas));
-  if (!heads_contiguous && phase != 2)
+  if (!heads_contiguous && phase != 2 && !dw16)
     for (int c = 0; c < l.C; ++c)
       NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,
                                        cudaMemcpyDeviceToDevice, stream));
@@ -549,5 +571,5 @@ extern "C" int neraf_field_grid_grads(const neraf_field_dims* dims, const float*
   if (dims->n_grid <= 0) return NERAF_OK;
   NERAF_REQUIRE(grid_feature && weight0 && dbias0 && (dweight0 || dgrid), "field_grid_grads: null pointer");
   return grid_grads(dbias0, grid_feature, weight0, (int64_t)dims->n_grid + dims->n_enc, dims->trunk[0], dims->n_grid, dweight0,
-                    dgrid, false, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 4));
+                    dgrid, false, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 8));
 }

@@ -332,7 +332,7 @@ class GraphedTrainStep:
         # 20.9 MB out of the all-reduce.
         defer = grid_p is not None and self.group is not None
         n1 = weights[0].shape[0]
-        ldc = (field.in_size - n_grid + 3) // 4 * 4
+        ldc = (field.in_size - n_grid + 7) // 8 * 8
         red_w = list(weights[1:]) if defer else list(weights)
         sizes = [t.numel() for t in red_w] + ([n1 * ldc] if defer else []) + [b.numel() for b in biases]
         n_weight_elems = sum(sizes) - sum(b.numel() for b in biases)
@@ -385,6 +385,18 @@ class GraphedTrainStep:
         self._keep = (pack, ws, out, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims, lg)
         self._grad_views = list(zip(order, views))
 
+        # bf16 exchange: the weight-gradient GEMMs store bf16 straight into the buffer that is all-reduced (same element
+        # layout as the fp32 flat buffer), so the only conversion passes left are the 40 KB of bias gradients before
+        # and the widening of the reduced sums after the collective
+        self._flat_low, dw16_arr = None, None
+        if (self.grad_dtype == torch.bfloat16 and defer and field.precision == "bf16" and not self.nvls
+                and not self.overlap_allreduce and all(t.shape[1] % 8 == 0 for t in weights[1:])):
+            self._flat_low = torch.zeros(sum(sizes), dtype=torch.bfloat16, device=dev)
+            parts16 = list(torch.split(self._flat_low, sizes))
+            dw16 = [parts16[nw]] + parts16[:nw]                   # entry 0: the compact dW1 block
+            dw16_arr = _lib.ptr_array(dw16)
+            self._n_weight_elems = n_weight_elems
+        self._keep_dw16 = dw16_arr
         mc = _lib.Multicast()
         mc.local_base, mc.multicast_base, mc.bytes = self.flat_grad.data_ptr(), mc_ptr, self.flat_grad.numel() * 4
         weight_region = self.flat_grad[:n_weight_elems]
@@ -400,6 +412,7 @@ class GraphedTrainStep:
             o.dw0_compact = _lib.ptr(compact)
             o.defer_grid_grads = 1 if defer else 0
             o.loss = C.pointer(lg)
+            o.dweights_bf16 = dw16_arr
         opt1.phase, opt1.max_ctas = (1 if self.overlap else 0), 0
         opt2.phase, opt2.max_ctas = 2, max(2, (sm_count - self.comm_ctas) // 2 * 2)
         # regions of the flat buffer: what the first backward graph finishes | what the second one does
@@ -499,6 +512,12 @@ class GraphedTrainStep:
     def _reduce(self, region: torch.Tensor, dtype: torch.dtype) -> None:
         """Sum ``region`` of the flat gradient buffer over the ranks (NCCL), optionally through a bf16 copy."""
         import torch.distributed as dist
+        if self._flat_low is not None:              # the backward wrote bf16 weight gradients: that IS the exchange format
+            n_w = self._n_weight_elems              # biases (fp32 atomics) join them
+            self._flat_low[n_w:].copy_(self.flat_grad[n_w:])
+            dist.all_reduce(self._flat_low, group=self.group)
+            self.flat_grad.copy_(self._flat_low)
+            return
         if dtype == torch.float32:
             dist.all_reduce(region, group=self.group)
             return
