@@ -296,16 +296,16 @@ def main():
     ms_e2e_g = ms_e2e_p = None
     if graphed is not None:          # same host batch through the repo's graphed step (H2D into static buffers + replay)
         def step_graphed_host(batch):
-            ld = step_value(batch)
-            return sum(ld.values())
+            step_value(batch)
+            return graphed.total_loss
         ms_e2e_g, _, _ = timed(host_batch, args.steps, read_loss=True, fn=step_graphed_host)
 
         # ... and with the data loader's prefetch: every step consumes the batch staged by the previous step and
         # starts the host -> device copy of the next one (one copy per step, inside the timed region, on a copy stream)
         def step_graphed_prefetch(batch):
-            ld = step_value(batch)
+            step_value(batch)
             graphed.prefetch(batch)
-            return sum(ld.values())
+            return graphed.total_loss
         graphed.prefetch(host_batch)
         for _ in range(3):
             step_graphed_prefetch(host_batch)
@@ -328,8 +328,8 @@ def main():
         def step_graphed_feed(_):
             feed.next_train(counter[0], out=graphed.static)
             counter[0] += 1
-            ld = step_value(graphed.static)
-            return sum(ld.values())
+            step_value(graphed.static)
+            return graphed.total_loss
         for _ in range(3):
             step_graphed_feed(None)
         ms_e2e_feed, _, _ = timed(None, args.steps, read_loss=True, fn=step_graphed_feed)
@@ -450,8 +450,9 @@ def main():
             model.render_rirs(mic, src, rot, init_r)
         barrier()
         s.record()
+        wr = torch.empty(n_pose, shape.C, shape.hop * (shape.T - 1), dtype=torch.float32).pin_memory()
         for _ in range(k_gl):
-            wr = model.render_rirs(mic, src, rot, init_r).cpu()
+            wr.copy_(model.render_rirs(mic, src, rot, init_r), non_blocking=True)      # waveforms into pinned host memory
         e.record()
         barrier()
         r_ms = max_over_ranks(s.elapsed_time(e)) / k_gl

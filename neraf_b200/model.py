@@ -220,7 +220,7 @@ class GraphedTrainStep:
     whole launch sequence (bf16 re-pack of the current parameters, encodings, the job-list GEMM launches, loss,
     backward) is captured once and replayed.  ``step(batch)`` copies the batch dict (host or device tensors) into
     static device buffers and replays; parameter gradients land in ``p.grad`` (static tensors owned by the graph),
-    the loss dict is returned as static 0-d tensors.
+    the loss dict is returned as static 0-d tensors (``total_loss``: their sum, also formed inside the graph).
 
     The graphs are built straight from the C-ABI calls (no autograd nodes, no tiny scalar kernels): forward + fused
     loss | backward with the loss gradient formed inside the heads' backward kernel (``neraf_loss_grad``).  Single
@@ -257,7 +257,25 @@ class GraphedTrainStep:
         keys = ("time_query", "mic_pose", "source_pose", "rot", "data")
         dtypes = {"time_query": torch.int64, "mic_pose": torch.float64, "source_pose": torch.float64,
                   "rot": torch.float64, "data": torch.float32}
-        self.static = {k: example_batch[k].to(device=dev, dtype=dtypes[k]).contiguous().clone() for k in keys}
+        # the static input tensors are views of ONE byte buffer (256-byte aligned offsets): a staged batch moves in
+        # with a single device copy
+        shapes = {k: tuple(example_batch[k].shape) for k in keys}
+        offs, cur = {}, 0
+        for k in keys:
+            offs[k] = cur
+            cur += (example_batch[k].numel() * torch.empty((), dtype=dtypes[k]).element_size() + 255) // 256 * 256
+        self._static_bytes = torch.zeros(max(cur, 256), dtype=torch.uint8, device=dev)
+
+        def views(buf):
+            out = {}
+            for k in keys:
+                n = example_batch[k].numel() * torch.empty((), dtype=dtypes[k]).element_size()
+                out[k] = buf[offs[k]:offs[k] + n].view(dtypes[k]).view(shapes[k])
+            return out
+        self._views = views
+        self.static = views(self._static_bytes)
+        for k in keys:
+            self.static[k].copy_(example_batch[k].to(device=dev, dtype=dtypes[k]))
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.group = model.process_group
         functional_ok = (not model.use_grid) or isinstance(model.resnet3d, ConstantGridFeature)
@@ -279,7 +297,9 @@ class GraphedTrainStep:
         def run():
             out = model.get_outputs(self.static)
             ld = model.get_loss_dict(out, self.static)
-            sum(ld.values()).backward()
+            total = sum(ld.values())
+            total.backward()
+            self.total_loss = total.detach()
             return ld
 
         side = torch.cuda.Stream(device=dev)
@@ -470,6 +490,16 @@ class GraphedTrainStep:
             self.losses = {"audio_mse": losses[1]}
         else:
             self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
+        # what a Trainer reads back every step (the sum of the loss dict), formed inside the graph
+        self.total_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        plain_backward = backward_part
+
+        def backward_part():
+            plain_backward()
+            if model.criterion_name == "MSE":
+                self.total_loss.copy_(losses[1])
+            else:
+                torch.add(losses[0], losses[1], out=self.total_loss)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         if self.group is None:
@@ -562,7 +592,8 @@ class GraphedTrainStep:
         prefetching data loader does for the reference's ``batch.to(device)`` (NeRAF_model.py:531-540)."""
         dev = self.model.device
         if self._staging is None:
-            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._staging_bytes = torch.empty_like(self._static_bytes)
+            self._staging = self._views(self._staging_bytes)
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._staged_ev = torch.cuda.Event()
             self._consumed_ev = torch.cuda.Event()
@@ -578,8 +609,7 @@ class GraphedTrainStep:
         if self._staged_for is not None and batch is self._staged_for:
             cur = torch.cuda.current_stream(self.model.device)
             cur.wait_event(self._staged_ev)
-            for k, dst in self.static.items():
-                dst.copy_(self._staging[k], non_blocking=True)
+            self._static_bytes.copy_(self._staging_bytes, non_blocking=True)
             self._consumed_ev.record(cur)
             self._staged_for = None
         else:

@@ -226,6 +226,7 @@ def test_graphed_step_and_prefetch_equal_autograd_step(prec):
         torch.cuda.synchronize()
         for k, v in refs[i][0].items():
             assert abs(float(got[k]) - v) < 1e-5 * abs(v), (k, i)
+        assert float(step.total_loss) == pytest.approx(sum(refs[i][0].values()), rel=1e-5)
         for p, r in zip(params, refs[i][1]):
             assert rel_fro(p.grad, r) < 1e-4, i        # same kernels; the bias sums' atomics re-order
 
