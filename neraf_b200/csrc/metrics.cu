@@ -7,7 +7,8 @@
 // reversed float32 power is a running float32 sum from the tail, and the decay times are "first index where the
 // curve is below a threshold" -- so each thread walks its response from the tail exactly like numpy does (bit-equal
 // running sums) and the batch supplies the parallelism: 2 000-16 000 responses per render.  A warp touches 32 rows at
-// a time and re-uses every 128-byte line for 32 steps, so the walks run out of L1.
+// a time and re-uses every 128-byte line for 32 steps, so the walks run out of L1 (transposing the batch so that a warp
+// reads ONE line per step was measured 1.5x slower: every step then waits for L2).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -24,15 +25,21 @@ struct MetricArgs {
 // Returns through the references: EDT index (first n with -10 - e_db > 0) and the rt60 pair (i_5db, i_decay, decay).
 struct Decay { int i_edt, i_5, i_dec; float decay; bool ok; };
 
-__device__ __forceinline__ Decay decay_walk(const float* __restrict__ h, int L, float decay_db, bool want_edt) {
+// c50 (optional): the first walk also accumulates measure_clarity's two energy sums (fp64), split at sample t50.
+__device__ __forceinline__ Decay decay_walk(const float* __restrict__ h, int L, float decay_db, bool want_edt,
+                                            double* c50 = nullptr, int t50 = 0) {
   Decay d; d.i_edt = -1; d.i_5 = -1; d.i_dec = -1; d.decay = decay_db; d.ok = false;
   float e = 0.f;
   int i_nz = -1;
+  double early = 0.0, late = 0.0;
   for (int n = L - 1; n >= 0; --n) {                 // np.cumsum(power[::-1])[::-1]: running float32 sum from the tail
     const float v = h[n];
-    e = __fadd_rn(e, __fmul_rn(v, v));
+    const float p = __fmul_rn(v, v);
+    e = __fadd_rn(e, p);
     if (i_nz < 0 && e > 0.f) i_nz = n;                // np.max(np.where(energy > 0))
+    if (c50) { if (n < t50) early += (double)p; else late += (double)p; }
   }
+  if (c50) *c50 = 10.0 * log10(early / late);         // measure_clarity: 10 log10(sum h^2[:t] / sum h^2[t:])
   if (i_nz <= 0) return d;                            // all-zero response, or nothing left after energy[:i_nz]
   const float l0 = __fmul_rn(10.f, log10f(e));        // energy_db[0] before the shift
   float thr_dec = 0.f;
@@ -55,24 +62,16 @@ __device__ __forceinline__ Decay decay_walk(const float* __restrict__ h, int L, 
   return d;
 }
 
-__global__ void __launch_bounds__(128) acoustic_metrics_kernel(MetricArgs a) {
+__global__ void __launch_bounds__(32) acoustic_metrics_kernel(MetricArgs a) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.S) return;
   const float* h = a.wave + s * (long long)a.L;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
 
-  // C50 (measure_clarity): 10 log10(sum h^2[:t] / sum h^2[t:]), t = int(0.05 fs + 1)
-  if (a.c50) {
-    double early = 0.0, late = 0.0;
-    for (int n = 0; n < a.L; ++n) {
-      const float v = h[n];
-      const double p = (double)__fmul_rn(v, v);
-      if (n < a.t50) early += p; else late += p;
-    }
-    a.c50[s] = 10.0 * log10(early / late);
-  }
-
-  Decay raw = decay_walk(h, a.L, a.highpass ? 10.f : a.decay_db, a.edt != nullptr);
+  // raw response: EDT, (SoundSpaces) T60, and C50 (t = int(0.05 fs + 1)) ride on the same two walks
+  double c50 = 0.0;
+  Decay raw = decay_walk(h, a.L, a.highpass ? 10.f : a.decay_db, a.edt != nullptr, a.c50 ? &c50 : nullptr, a.t50);
+  if (a.c50) a.c50[s] = c50;
   if (a.edt) a.edt[s] = (raw.ok && raw.i_edt >= 0) ? (60.0 / 10.0) * ((double)raw.i_edt / a.fs) : nan;
 
   if (a.t60) {
@@ -80,11 +79,13 @@ __global__ void __launch_bounds__(128) acoustic_metrics_kernel(MetricArgs a) {
     if (a.highpass) {
       // torchaudio.functional.highpass_biquad (RBJ high-pass, direct form I, clamp to [-1, 1]) in float64
       float* y = a.filtered + s * (long long)a.L;
+      // y[n] = (b0 x[n] + b1 x[n-1] + b2 x[n-2] - a2 y[n-2]) - a1 y[n-1]: everything but the last product is off the
+      // loop-carried chain, which is ONE fp64 FMA per sample
       double x1 = 0.0, x2 = 0.0, y1 = 0.0, y2 = 0.0;
       for (int n = 0; n < a.L; ++n) {
         const double xn = (double)h[n];
-        const double yn = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.b0, xn), __dmul_rn(a.b1, x1)), __dmul_rn(a.b2, x2)),
-                                              __dmul_rn(a.a1, y1)), __dmul_rn(a.a2, y2));
+        const double u = fma(a.b0, xn, fma(a.b1, x1, fma(a.b2, x2, -a.a2 * y2)));
+        const double yn = fma(-a.a1, y1, u);
         x2 = x1; x1 = xn; y2 = y1; y1 = yn;
         y[n] = (float)fmin(fmax(yn, -1.0), 1.0);
       }
@@ -123,7 +124,7 @@ extern "C" int neraf_acoustic_metrics(const neraf_metric_params* p, const float*
     a.b0 = (1.0 + cw) / 2.0 / a0; a.b1 = (-1.0 - cw) / a0; a.b2 = a.b0;
     a.a1 = -2.0 * cw / a0; a.a2 = (1.0 - alpha) / a0;
   }
-  acoustic_metrics_kernel<<<(unsigned)ceil_div(n_signals, 128), 128, 0, (cudaStream_t)stream>>>(a);
+  acoustic_metrics_kernel<<<(unsigned)ceil_div(n_signals, 32), 32, 0, (cudaStream_t)stream>>>(a);      // one warp per block: spread over the SMs
   NERAF_CHECK_LAUNCH("acoustic_metrics_kernel");
   return NERAF_OK;
 }
