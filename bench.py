@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--shape", default="RAF", choices=["RAF", "SoundSpaces"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gl-rirs", type=int, default=2072, help="RIRs per Griffin-Lim launch (0 disables); 2072 = 14 per SM")
+    ap.add_argument("--large-batch", type=int, default=16384, help="extra large-batch point of the sweep (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
     ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"],
@@ -396,6 +397,21 @@ def main():
                      "peak_source": f"{peaks['source']} sustained bf16 cuBLAS (MEASURED_PEAKS.json)"},
         "host_wall_ms_per_step": wall_dev / args.steps * 1e3,
     }
+
+    # ---- the same step at 8x the reference batch (BASELINE config 5's sweep, one point): what the kernels reach once
+    # a layer is more than one tile per CTA pair.  Not the headline: `value` stays at the reference batch.
+    if world == 1 and graphed is not None and args.large_batch > 0 and args.large_batch != B:
+        BL = args.large_batch
+        big = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, BL, seed=3).items()}
+        g_big = GraphedTrainStep(model, big)
+        for _ in range(3):
+            g_big(big)
+        ms_big, _, _ = timed(big, 20, read_loss=False, fn=g_big)
+        ms_b = sum(ms_big) / len(ms_big)
+        ach = FLOP_PER_COLUMN_TRAIN[shape.C] * BL / (ms_b * 1e-3) / 1e12
+        line["large_batch"] = {"batch_per_gpu": BL, "value": BL / (ms_b * 1e-3), "unit": "columns/s", "ms_per_step": ms_b,
+                               "roofline_frac": ach / peaks["bf16_tflops_sustained"], "achieved_tflops": ach, "steps": 20}
+        del g_big, big
 
     # ---- Griffin-Lim: RIRs/s (second half of the BASELINE metric), rank-local poses, no collective
     if args.gl_rirs > 0:

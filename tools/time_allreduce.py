@@ -16,6 +16,18 @@ for dtype in (torch.float32, torch.bfloat16):
     sym.fill_(1)
     symm_mem.rendezvous(sym, gname)
     variants = {"nccl": lambda: dist.all_reduce(plain)}
+    # NCCL user-buffer registration: the tensor comes from ncclMemAlloc (torch.cuda.MemPool over the backend's allocator)
+    # and the pool is registered with the communicator -> zero-copy / NVLS all-reduce that needs few SMs
+    try:
+        backend = dist.group.WORLD._get_backend(dev)
+        pool = torch.cuda.MemPool(backend.mem_allocator)
+        with torch.cuda.use_mem_pool(pool):
+            reg = torch.ones(n, dtype=dtype, device=dev)
+        backend.register_mem_pool(pool)
+        variants["nccl registered"] = lambda: dist.all_reduce(reg)
+    except Exception as ex:
+        if rank == 0:
+            print("registered pool unavailable:", repr(ex)[:200], flush=True)
     for opname in ("multimem_all_reduce_", "two_shot_all_reduce_", "one_shot_all_reduce"):
         op = getattr(torch.ops.symm_mem, opname, None)
         if op is not None:
