@@ -67,7 +67,10 @@ class _FieldFn(torch.autograd.Function):
         pack, repack = module._packed(dims, prec, weights, biases)
         pack_b, ws_b = C.c_size_t(), C.c_size_t()
         _lib.check(lib.neraf_field_sizes(C.byref(dims), prec, B, C.byref(pack_b), C.byref(ws_b)))
-        ws = torch.empty(max(ws_b.value, 16), dtype=torch.uint8, device=dev)
+        # training keeps the workspace (saved activations) until backward; inference re-uses one grow-only buffer per
+        # stream, so rendering thousands of RIRs never goes back to the allocator for its 0.3-2 GB of scratch
+        ws = torch.empty(max(ws_b.value, 16), dtype=torch.uint8, device=dev) if need_grad \
+            else module._inference_workspace(max(ws_b.value, 16), dev)
         out = torch.empty(B, module.sound_rez, module.N_frequencies, dtype=torch.float32, device=dev)
         w_arr, b_arr = _lib.ptr_array(weights), _lib.ptr_array(biases)
         _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_c), w_arr, b_arr,
@@ -128,6 +131,7 @@ class NeRAFAudioSoundField(nn.Module):
         self.soundfield = nn.ModuleList([nn.Linear(widths[i], widths[i + 1]) for i in range(5)])
         self.STFT_linear = nn.ModuleList([nn.Linear(W, N_frequencies) for _ in range(sound_rez)])
         self._pack_cache: Dict = {}
+        self._ws_cache: Dict = {}
         # Training changes the parameters every step, so the bf16 operand copies must be re-derived every
         # forward.  Eagerly this is detected through the parameters' version counters; inside a captured CUDA
         # graph (no Python on replay) set always_repack so the pack kernels are part of the graph.
@@ -141,6 +145,14 @@ class NeRAFAudioSoundField(nn.Module):
     def _dims(self, n_grid: int) -> _lib.FieldDims:
         return _lib.make_dims(n_grid, self.in_size - n_grid, [*TRUNK_WIDTHS, self.W], self.sound_rez,
                               self.N_frequencies)
+
+    def _inference_workspace(self, nbytes: int, dev: torch.device) -> torch.Tensor:
+        key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws_cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws_cache[key] = ws
+        return ws
 
     def _packed(self, dims, prec, weights: List[torch.Tensor], biases: List[torch.Tensor]):
         """(buffer for the bf16 operand copies, whether neraf_field_forward must re-derive them).

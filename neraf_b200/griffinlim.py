@@ -21,13 +21,27 @@ import torch.nn as nn
 from . import _lib
 
 
+_WS_CACHE = {}
+
+
+def _workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    """Grow-only scratch per (device, stream): the kernel's staged magnitudes and previous-waveform lines (tens to
+    hundreds of MB per batch) are not handed back to the allocator between renders."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = ws
+    return ws
+
+
 def _run(params: _lib.GlParams, n_items: int, n_channels: int, spec: torch.Tensor, strides,
          init: Optional[torch.Tensor], init_strides, out: torch.Tensor) -> None:
     lib = _lib.lib()
     dev = spec.device
     ws_b = C.c_size_t()
     _lib.check(lib.neraf_griffinlim_sizes(C.byref(params), n_items * n_channels, C.byref(ws_b)))
-    ws = torch.empty(max(ws_b.value, 16), dtype=torch.uint8, device=dev)
+    ws = _workspace(max(ws_b.value, 16), dev)
     _lib.check(lib.neraf_griffinlim(C.byref(params), n_items, n_channels, spec.data_ptr(), *strides,
                                     None if init is None else init.data_ptr(), *init_strides,
                                     ws.data_ptr(), ws.numel(), out.data_ptr(), _lib.stream_ptr(dev)))

@@ -169,7 +169,15 @@ class NeRAFAudioModel(nn.Module):
         rep = lambda x: x.repeat_interleave(T, dim=0)  # noqa: E731
         g = self.grid_feature() if grid_feature is None and self.use_grid else grid_feature
         order = _lib.ORDER_TIME_MIC_SRC_ROT if self.use_grid else _lib.ORDER_MIC_SRC_TIME_ROT
-        y = self.field.forward_queries(tq, rep(mic), rep(src), rep(r), self.aabb, self.max_len, g, order)
+        # at most ~16k queries per launch: the activations of one launch (9704 bf16 values per query) stay a few
+        # hundred MB of re-used scratch instead of growing with the number of poses
+        per = max(1, 16384 // T)
+        ys = []
+        for lo in range(0, max(N, 1), per):
+            hi = min(lo + per, N)
+            ys.append(self.field.forward_queries(tq[lo * T:hi * T], rep(mic[lo:hi]), rep(src[lo:hi]), rep(r[lo:hi]),
+                                                 self.aabb, self.max_len, g, order))
+        y = ys[0] if len(ys) == 1 else torch.cat(ys)
         return y.view(N, T, self.mic_ch, -1)
 
     @torch.no_grad()
