@@ -462,11 +462,11 @@ def main():
         rot = torch.tensor([[1.0, 0.5, 0.5]], dtype=torch.float64)
         init_r = init[:n_pose] if n >= n_pose else torch.rand(n_pose, shape.C, shape.F, shape.T, dtype=torch.complex64, device=dev)
         model.field.always_repack = False
+        wr = torch.empty(n_pose, shape.C, shape.hop * (shape.T - 1), dtype=torch.float32).pin_memory()
         for _ in range(2):
-            model.render_rirs(mic, src, rot, init_r)
+            wr.copy_(model.render_rirs(mic, src, rot, init_r), non_blocking=True)
         barrier()
         s.record()
-        wr = torch.empty(n_pose, shape.C, shape.hop * (shape.T - 1), dtype=torch.float32).pin_memory()
         for _ in range(k_gl):
             wr.copy_(model.render_rirs(mic, src, rot, init_r), non_blocking=True)      # waveforms into pinned host memory
         e.record()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 5
+#define NERAF_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))
@@ -161,6 +161,15 @@ typedef struct {
   size_t bytes;
 } neraf_multicast;
 
+/* neraf_field_forward with the spectral loss's partial sums formed by the epilogue that stores the prediction (bf16
+ * path; the fp32 path runs neraf_spectral_loss_sums behind the forward): gt is the (B, C, F) target, sums f64[>=5] is
+ * zeroed by the call and holds the four sums of neraf_spectral_loss_sums afterwards.  With neraf_loss_grad.losses in
+ * the backward, a training step needs no loss launch at all. */
+NERAF_API int neraf_field_forward_loss_sums(const neraf_field_dims* dims, int precision, const neraf_queries* queries,
+                                  const float* grid_feature, const float* const* weights, const float* const* biases,
+                                  void* pack, size_t pack_bytes, int repack, void* workspace, size_t workspace_bytes,
+                                  float* out, int keep, const float* gt, double* sums, neraf_stream_t stream);
+
 /* The spectral loss's gradient formed inside the backward instead of being read from `dout` (which may then be NULL):
  * dout[i] = neraf_spectral_loss_backward(out, gt, ..., sums, upstream = 1)[i], evaluated on the fly by the kernel that
  * applies the heads' 10*tanh derivative -- one launch and a 2 x 4 B/element round trip less per step. */
@@ -170,6 +179,8 @@ typedef struct {
   int32_t criterion;        /* NERAF_CRIT_*                                                  */
   const double* sums;       /* device f64[>=4]: the (all-reduced) partial sums of the loss   */
   float w_sc, w_mag;        /* loss weights (NeRAF_model.py:597-598)                         */
+  float* losses;            /* optional dev f32[2]: the two weighted losses (what                */
+                            /* neraf_spectral_loss_finalize writes), formed by the same launch  */
 } neraf_loss_grad;
 
 typedef struct {
@@ -333,6 +344,12 @@ typedef struct {
    * NVSwitch (multimem.red.add.f32): a gradient all-reduce fused into the weight-gradient GEMM.  The buffers must be
    * zero on every rank before any rank's launch starts. */
   void* out_f32_multicast;
+  /* job-list kernel only, with out_f32: the spectral loss's four partial sums over the stored values x against the
+   * targets y = loss_gt[m * ld_gt + n] are ADDED to loss_sums[0..3] (f64, as neraf_spectral_loss_sums defines them:
+   * sum (e^y - e^x)^2, sum (e^y - 1e-3)^2, sum (y - x)^2, sum |y - x|) by the epilogue that stores x. */
+  const float* loss_gt;
+  int64_t ld_gt;
+  double* loss_sums;
 } neraf_gemm_epilogue;
 
 NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,

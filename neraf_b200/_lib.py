@@ -45,7 +45,8 @@ class GemmEpilogue(C.Structure):
                 ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64), ("out_bf16_t", C.c_void_p), ("ld_t", C.c_int64),
                 ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("accumulate_f32", C.c_int32),
                 ("mask_out", C.c_void_p), ("gate_mask", C.c_void_p), ("ld_mask", C.c_int64),
-                ("out_f32_multicast", C.c_void_p)]
+                ("out_f32_multicast", C.c_void_p), ("loss_gt", C.c_void_p), ("ld_gt", C.c_int64),
+                ("loss_sums", C.c_void_p)]
 
 
 class GemmJob(C.Structure):
@@ -61,7 +62,7 @@ class Multicast(C.Structure):
 
 class LossGrad(C.Structure):        # neraf_loss_grad
     _fields_ = [("gt", C.c_void_p), ("n_total", C.c_int64), ("criterion", C.c_int32), ("sums", C.c_void_p),
-                ("w_sc", C.c_float), ("w_mag", C.c_float)]
+                ("w_sc", C.c_float), ("w_mag", C.c_float), ("losses", C.c_void_p)]
 
 
 class DpOptions(C.Structure):
@@ -92,6 +93,8 @@ SIGNATURES = {
     "neraf_field_pack": (C.c_int, [C.POINTER(FieldDims), _i32, _pp, _pp, _vp, _sz, _vp]),
     "neraf_field_forward": (C.c_int, [C.POINTER(FieldDims), _i32, C.POINTER(Queries), _vp, _pp, _pp, _vp, _sz, _i32,
                                        _vp, _sz, _vp, _i32, _vp]),
+    "neraf_field_forward_loss_sums": (C.c_int, [C.POINTER(FieldDims), _i32, C.POINTER(Queries), _vp, _pp, _pp, _vp, _sz,
+                                                 _i32, _vp, _sz, _vp, _i32, _vp, _vp, _vp]),
     "neraf_field_backward": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
                                         _vp, _vp, _i64, _vp]),
     "neraf_field_backward_dp": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,

@@ -6,6 +6,7 @@
 //  * bias gradients (column sums), and the gradient through the 10*tanh heads (NeRAF_field.py:57-58).
 #include "common.cuh"
 #include "kernels.h"
+#include "loss_math.cuh"
 
 namespace neraf {
 
@@ -214,6 +215,8 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
                                                             int64_t ld_bf16, HeadColsum cs, neraf_loss_grad lg) {
   __shared__ float red[8][32];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  if (LOSS && lg.losses && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)      // the loss values themselves
+    finalize(lg.sums, lg.n_total, lg.criterion, lg.w_sc, lg.w_mag, lg.losses);
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
   const int64_t r0 = (int64_t)blockIdx.y * kHeadRows;
   const int64_t r1 = r0 + kHeadRows < M ? r0 + kHeadRows : M;

@@ -252,16 +252,20 @@ extern "C" int neraf_field_pack(const neraf_field_dims* dims, int precision, con
   return pack_layers(l, 0, weights, biases, pack, stream);
 }
 
-extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
-                                   const float* grid_feature, const float* const* weights, const float* const* biases,
-                                   void* pack, size_t pack_bytes, int repack, void* ws, size_t ws_bytes, float* out,
-                                   int keep, neraf_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// loss_gt / loss_sums (optional, together): the spectral loss's partial sums of `out` against the targets, formed by
+// the heads' epilogue (bf16) or by loss_sums_kernel behind the GEMMs (fp32); loss_sums[0..4] is cleared first.
+static int field_forward_impl(const neraf_field_dims* dims, int precision, const neraf_queries* q,
+                              const float* grid_feature, const float* const* weights, const float* const* biases,
+                              void* pack, size_t pack_bytes, int repack, void* ws, size_t ws_bytes, float* out,
+                              int keep, const float* loss_gt, double* loss_sums, cudaStream_t stream) {
   NERAF_REQUIRE(q, "field_forward: queries is null");
   Layout l;
   NERAF_TRY(make_layout(dims, precision, q->batch, &l));
   const int64_t B = q->batch;
-  if (B == 0) return NERAF_OK;
+  if (B == 0) {
+    if (loss_sums) NERAF_CHECK_CUDA(cudaMemsetAsync(loss_sums, 0, 5 * sizeof(double), stream));
+    return NERAF_OK;
+  }
   NERAF_TRY(check_ptr_list(weights, l.L + l.C, "weights"));
   NERAF_TRY(check_ptr_list(biases, l.L + l.C, "biases"));
   NERAF_REQUIRE(out && ws, "field_forward: out/workspace is null");
@@ -302,6 +306,10 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
     for (int c = 0; c < l.C; ++c)
       NERAF_TRY(gemm_f32(B, l.F, l.W, x, ldx, 1, weights[l.L + c], l.W, 1, biases[l.L + c], NERAF_ACT_TANH10, nullptr, 0,
                          out + (size_t)c * l.F, l.CF, 0, stream));
+    if (loss_sums) {
+      NERAF_CHECK_CUDA(cudaMemsetAsync(loss_sums + 4, 0, sizeof(double), stream));
+      NERAF_TRY(neraf_spectral_loss_sums(out, loss_gt, B * l.CF, loss_sums, 0, stream));
+    }
     return NERAF_OK;
   }
 
@@ -319,7 +327,8 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
   void* enc = at(ws, l.enc);
   if (q->enc) NERAF_TRY(convert_bf16(q->enc, B, l.E, q->enc_ld, enc, l.ld_enc, nullptr, 0, stream));
   NERAF_TRY(field_prep(q->enc ? nullptr : q, nullptr, 0, enc, l.ld_enc, (int)l.ld_enc, weights[0], ldw0, biases[0],
-                       grid_feature, l.n[0], l.G, c1w, l.E, do_pack ? at(pack, l.w[0]) : nullptr, l.ldw[0], stream));
+                       grid_feature, l.n[0], l.G, c1w, l.E, do_pack ? at(pack, l.w[0]) : nullptr, l.ldw[0], stream,
+                       loss_sums));
 
   // One persistent launch for the whole MLP (two when the operands are being re-packed on the helper stream:
   // layer 1 starts as soon as its own copy exists, the remaining layers once the helper stream has finished).
@@ -335,6 +344,7 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
       j.epi.bias = reinterpret_cast<const float*>(at(pack, l.bh));
       j.epi.act = NERAF_ACT_TANH10;
       j.epi.out_f32 = out; j.epi.ld_f32 = l.CF;
+      j.epi.loss_gt = loss_gt; j.epi.ld_gt = l.CF; j.epi.loss_sums = loss_sums;
     } else {
       j.epi.bias = i == 0 ? c1 : biases[i];
       j.epi.act = NERAF_ACT_LEAKY;
@@ -350,6 +360,24 @@ extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, 
   if (side) NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
   NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream));
   return NERAF_OK;
+}
+
+extern "C" int neraf_field_forward(const neraf_field_dims* dims, int precision, const neraf_queries* q,
+                                   const float* grid_feature, const float* const* weights, const float* const* biases,
+                                   void* pack, size_t pack_bytes, int repack, void* ws, size_t ws_bytes, float* out,
+                                   int keep, neraf_stream_t stream) {
+  return field_forward_impl(dims, precision, q, grid_feature, weights, biases, pack, pack_bytes, repack, ws, ws_bytes, out,
+                            keep, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int neraf_field_forward_loss_sums(const neraf_field_dims* dims, int precision, const neraf_queries* q,
+                                             const float* grid_feature, const float* const* weights,
+                                             const float* const* biases, void* pack, size_t pack_bytes, int repack,
+                                             void* ws, size_t ws_bytes, float* out, int keep, const float* gt,
+                                             double* sums, neraf_stream_t stream) {
+  NERAF_REQUIRE(sums && (gt || (q && q->batch == 0)), "field_forward_loss_sums: gt / sums is null");
+  return field_forward_impl(dims, precision, q, grid_feature, weights, biases, pack, pack_bytes, repack, ws, ws_bytes, out,
+                            keep, gt, sums, (cudaStream_t)stream);
 }
 
 static int field_backward_impl(const neraf_field_dims* dims, int precision, int64_t B, const float* dout,

@@ -77,6 +77,7 @@ struct alignas(64) DeviceJob {
   const __nv_bfloat16* gate; long long ldg;
   float* out_f32; long long ld_f32;
   float* colsum;
+  const float* loss_gt; long long ld_gt; double* loss_sums;   // out_mode 3 only: spectral-loss partial sums (fused)
 };
 
 // Optional per-tile timeline (NERAF_MEGA_TRACE=<file>): 8 globaltimer stamps per tile, see tools/mega_trace.py.
@@ -582,6 +583,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           float* out_f32 = J.out_f32;
           const long long ld_f32 = J.ld_f32;
           const int rows = M - m_base < 32 ? M - m_base : 32;
+          const float* loss_gt = J.loss_gt;
+          double s_num = 0.0, s_den = 0.0, s_sq = 0.0, s_abs = 0.0;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h < nch) {
@@ -590,10 +593,43 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
               __syncwarp();
               const int n = n0 + 32 * h + lane;
               if (n < N) {
+                if (loss_gt == nullptr) {
 #pragma unroll 4
-                for (int r = 0; r < rows; ++r) out_f32[(long long)(m_base + r) * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
+                  for (int r = 0; r < rows; ++r) out_f32[(long long)(m_base + r) * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
+                } else {
+                  // the prediction leaves through here exactly once: form the spectral loss's terms against the
+                  // target on the way (same arithmetic as loss_sums_kernel, lanes = consecutive columns)
+                  const long long ld_gt = J.ld_gt;
+#pragma unroll 4
+                  for (int r = 0; r < rows; ++r) {
+                    const float x = wbuf_f[r * 32 + (lane ^ r)];
+                    out_f32[(long long)(m_base + r) * ld_f32 + n] = x;
+                    const float y = __ldg(loss_gt + (long long)(m_base + r) * ld_gt + n);
+                    const float ex = expf(x), ey = expf(y);
+                    const float dm = ey - ex, ym = ey - 1e-3f, d = y - x;
+                    s_num += (double)(dm * dm);
+                    s_den += (double)(ym * ym);
+                    s_sq += (double)(d * d);
+                    s_abs += (double)fabsf(d);
+                  }
+                }
               }
               __syncwarp();
+            }
+          }
+          if (loss_gt != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s_num += __shfl_xor_sync(FULL_MASK, s_num, o);
+              s_den += __shfl_xor_sync(FULL_MASK, s_den, o);
+              s_sq += __shfl_xor_sync(FULL_MASK, s_sq, o);
+              s_abs += __shfl_xor_sync(FULL_MASK, s_abs, o);
+            }
+            if (lane == 0) {
+              atomicAdd(J.loss_sums + 0, s_num);
+              atomicAdd(J.loss_sums + 1, s_den);
+              atomicAdd(J.loss_sums + 2, s_sq);
+              atomicAdd(J.loss_sums + 3, s_abs);
             }
           }
         }
@@ -745,9 +781,11 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
       NERAF_REQUIRE(s.epi.ld_f32 >= s.N, "mega_run: job %d: out_f32 row stride < N", i);
       // TMA stores clip with 16-byte granularity: only rows that end on a 16-byte boundary take the TMA path
       const bool tma_ok = (s.epi.ld_f32 % 4 == 0) && ((uintptr_t)s.epi.out_f32 % 16 == 0) && (s.N % 4 == 0);
-      d.out_mode = tma_ok ? 2 : 3;
+      d.out_mode = (tma_ok && !s.epi.loss_gt) ? 2 : 3;
       d.out_mc = (float*)s.epi.out_f32_multicast;
       if (d.out_mc) d.out_mode = 4;
+      NERAF_REQUIRE(!s.epi.loss_gt || (s.epi.loss_sums && !d.out_mc && s.epi.ld_gt >= s.N),
+                    "mega_run: job %d: loss_gt needs loss_sums, ld_gt >= N and no multicast output", i);
       if (tma_ok) NERAF_TRY(get_tensor_map_2d(s.epi.out_f32, 4, s.M, s.N, s.epi.ld_f32, 32, 32, &d.tmOut));
     }
     d.bias_vec = s.epi.bias && ((uintptr_t)s.epi.bias % 16) == 0;
@@ -757,6 +795,8 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
                   "mega_run: job %d: mask_out needs the LeakyReLU epilogue and a bf16 output", i);
     NERAF_REQUIRE(!(s.epi.gate && s.epi.gate_mask), "mega_run: job %d: gate and gate_mask are exclusive", i);
     d.colsum = s.colsum;
+    d.loss_gt = s.epi.out_f32 ? s.epi.loss_gt : nullptr; d.ld_gt = s.epi.ld_gt; d.loss_sums = s.epi.loss_sums;
+    NERAF_REQUIRE(!s.epi.loss_gt || s.epi.out_f32, "mega_run: job %d: loss_gt needs an fp32 output", i);
   }
   P.num_tiles = tile;
   NERAF_REQUIRE(counters && counters_bytes >= (size_t)cnt * sizeof(unsigned int), "mega_run: counter buffer too small");

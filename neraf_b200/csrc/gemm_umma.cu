@@ -420,7 +420,7 @@ int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const
   if (e->out_bf16_t) NERAF_REQUIRE(e->ld_t >= M, "gemm_bf16: out_bf16_t row stride < M");
   if (e->out_f32) NERAF_REQUIRE(e->ld_f32 >= N, "gemm_bf16: out_f32 row stride < N");
   NERAF_REQUIRE(e->act >= 0 && e->act <= 2, "gemm_bf16: unknown activation %d", e->act);
-  NERAF_REQUIRE(!e->mask_out && !e->gate_mask && !e->out_f32_multicast,
+  NERAF_REQUIRE(!e->mask_out && !e->gate_mask && !e->out_f32_multicast && !e->loss_gt,
                 "gemm_bf16: bit-mask gates and multicast outputs are features of neraf_gemm_bf16_jobs");
 
   Params p;

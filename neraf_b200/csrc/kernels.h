@@ -17,7 +17,7 @@ int encode_queries(const neraf_queries* q, float* out_f32, int64_t ld_f32, void*
 // (skipped when w1_out is null).
 int field_prep(const neraf_queries* q, float* enc_f32, int64_t ld_f32, void* enc_bf16, int64_t ld_bf16, int ncols_padded,
                const float* W1, int64_t ldw, const float* b1, const float* g, int64_t n1, int64_t G, float* c1,
-               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream);
+               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream, double* zero5 = nullptr);
 
 // gemm_simt.cu
 int gemm_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,

@@ -12,6 +12,7 @@
 //   3. one elementwise kernel for d loss / d pred.
 // HBM-bound: 8 B/element forward, 12 B/element backward.
 #include "common.cuh"
+#include "loss_math.cuh"
 
 namespace neraf {
 
@@ -32,18 +33,6 @@ __device__ __forceinline__ void accumulate(float x, float y, double& s_num, doub
   s_den += (double)(ym * ym);
   s_sq += (double)(d * d);
   s_abs += (double)fabsf(d);
-}
-
-__device__ __forceinline__ void finalize(const double* sums, int64_t n_total, int criterion, float w_sc, float w_mag,
-                                         float* losses) {
-  const double n = (double)n_total;
-  if (criterion == NERAF_CRIT_MSE) {
-    losses[0] = 0.f;
-    losses[1] = (float)(w_mag * (sums[2] / n));
-  } else {
-    losses[0] = (float)(w_sc * (sqrt(sums[0]) / sqrt(sums[1])));          // NeRAF_evaluator.py:26 (no epsilon)
-    losses[1] = (float)(w_mag * ((criterion == NERAF_CRIT_SC_SLMSE ? sums[2] : sums[3]) / n));
-  }
 }
 
 // FUSED != 0: the last block to finish (ticket in sums[4], reinterpreted as an integer) also forms the two losses,

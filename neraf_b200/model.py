@@ -408,6 +408,7 @@ class GraphedTrainStep:
         lg = _lib.LossGrad()
         lg.gt, lg.n_total, lg.criterion, lg.sums = st["data"].data_ptr(), n_total, crit, self.sums.data_ptr()
         lg.w_sc, lg.w_mag = w_sc, w_mag
+        lg.losses = losses.data_ptr()          # ... and so are the two loss values: no loss launch in the step
         w_arr, b_arr = _lib.ptr_array(weights), _lib.ptr_array(biases)
         dw_arr, db_arr = _lib.ptr_array(dws), _lib.ptr_array(dbs)
         self._keep = (pack, ws, out, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims, lg)
@@ -460,23 +461,16 @@ class GraphedTrainStep:
                 with torch.cuda.stream(zero_stream):
                     weight_region.zero_()
             s = _lib.stream_ptr(dev)
-            _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
-                                               pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
-                                               out.data_ptr(), 1, s))
-            if self.group is None:         # sums + both losses in one kernel
-                _lib.check(lib.neraf_spectral_loss_forward(out.data_ptr(), st["data"].data_ptr(), n_local, crit, w_sc,
-                                                           w_mag, self.sums.data_ptr(), losses.data_ptr(), s))
-            else:
-                _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
-                                                        self.sums.data_ptr(), 0, s))
+            # forward with the spectral loss's partial sums formed by the epilogue that stores the prediction
+            _lib.check(lib.neraf_field_forward_loss_sums(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
+                                                         pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
+                                                         out.data_ptr(), 1, st["data"].data_ptr(),
+                                                         self.sums.data_ptr(), s))
             if self.nvls:
                 torch.cuda.current_stream(dev).wait_stream(zero_stream)
 
         def backward_part():
             s = _lib.stream_ptr(dev)
-            if self.group is not None:
-                _lib.check(lib.neraf_spectral_loss_finalize(self.sums.data_ptr(), n_total, crit, w_sc, w_mag,
-                                                            losses.data_ptr(), s))
             _lib.check(lib.neraf_field_backward_dp(C.byref(dims), prec, B, None, out.data_ptr(),
                                                    _lib.ptr(grid_p), w_arr, pack.data_ptr(), ws.data_ptr(), ws.numel(),
                                                    dw_arr, db_arr, _lib.ptr(dgrid), None, 0, C.byref(opt1), s))

@@ -232,6 +232,13 @@ def test_graphed_step_and_prefetch_equal_autograd_step(prec):
 
     for i in (1, 0, 2):
         check(step(host[i]), i)
+    # the partial sums formed by the heads' epilogue == the loss kernel's on the same prediction
+    pred = step._keep[2]
+    ref_sums = torch.zeros(5, dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().neraf_spectral_loss_sums(pred.data_ptr(), step.static["data"].data_ptr(), pred.numel(),
+                                                   ref_sums.data_ptr(), 0, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.allclose(step.sums[:4], ref_sums[:4], rtol=1e-9, atol=0.0)
     step.prefetch(host[1])
     for i in (1, 2, 0):                        # consume the staged batch, stage the next one under the step
         got = step(host[i])
