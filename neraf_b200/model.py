@@ -241,8 +241,14 @@ class GraphedTrainStep:
 
     def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3,
                  fused_allreduce: bool = False, overlap_allreduce: bool = False,
-                 grad_dtype: torch.dtype = torch.float32, functional: Optional[bool] = None):
+                 grad_dtype: torch.dtype = torch.float32, functional: Optional[bool] = None,
+                 fuse_loss_sums: bool = False):
         self.model = model
+        # True: the loss's partial sums come out of the heads' forward epilogue (neraf_field_forward_loss_sums) -- one
+        # launch and a re-read of the prediction less, but the extra exp / target loads sit in the epilogue of the LAST
+        # link of the forward's dependency chain: measured 4.5 us per step slower at B=2048 (tools/ab_step.py: 378.0
+        # vs 373.5 us), so the default is the separate loss_sums launch behind the forward (same numbers).
+        self.fuse_loss_sums = fuse_loss_sums
         self.launches_per_step = 0        # library kernels per step (counted over the last eager warm-up step)
         # Data parallel, optional: the backward is split in two graphs; everything the first one finishes (all weight
         # gradients but dW1's: 57.5 of the 60.8 MB) is all-reduced on a communication stream WHILE the second computes
@@ -461,11 +467,18 @@ class GraphedTrainStep:
                 with torch.cuda.stream(zero_stream):
                     weight_region.zero_()
             s = _lib.stream_ptr(dev)
-            # forward with the spectral loss's partial sums formed by the epilogue that stores the prediction
-            _lib.check(lib.neraf_field_forward_loss_sums(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
-                                                         pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
-                                                         out.data_ptr(), 1, st["data"].data_ptr(),
-                                                         self.sums.data_ptr(), s))
+            if self.fuse_loss_sums:
+                # forward with the spectral loss's partial sums formed by the epilogue that stores the prediction
+                _lib.check(lib.neraf_field_forward_loss_sums(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr,
+                                                             b_arr, pack.data_ptr(), pack.numel(), 1, ws.data_ptr(),
+                                                             ws.numel(), out.data_ptr(), 1, st["data"].data_ptr(),
+                                                             self.sums.data_ptr(), s))
+            else:
+                _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
+                                                   pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
+                                                   out.data_ptr(), 1, s))
+                _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
+                                                        self.sums.data_ptr(), 0, s))
             if self.nvls:
                 torch.cuda.current_stream(dev).wait_stream(zero_stream)
 

@@ -232,7 +232,11 @@ def test_graphed_step_and_prefetch_equal_autograd_step(prec):
 
     for i in (1, 0, 2):
         check(step(host[i]), i)
-    # the partial sums formed by the heads' epilogue == the loss kernel's on the same prediction
+    # the partial sums formed by the heads' epilogue (optional variant) == the loss kernel's on the same prediction
+    step = GraphedTrainStep(model, host[0], fuse_loss_sums=True)
+    assert step.launches_per_step > 0
+    for i in (0, 2):
+        check(step(host[i]), i)
     pred = step._keep[2]
     ref_sums = torch.zeros(5, dtype=torch.float64, device=dev)
     _lib.check(_lib.lib().neraf_spectral_loss_sums(pred.data_ptr(), step.static["data"].data_ptr(), pred.numel(),
