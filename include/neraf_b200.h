@@ -181,6 +181,7 @@ typedef struct {
   float w_sc, w_mag;        /* loss weights (NeRAF_model.py:597-598)                         */
   float* losses;            /* optional dev f32[2]: the two weighted losses (what                */
                             /* neraf_spectral_loss_finalize writes), formed by the same launch  */
+  float* total;             /* optional dev f32[1] (with losses): their sum, what a Trainer reads */
 } neraf_loss_grad;
 
 typedef struct {

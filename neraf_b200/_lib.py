@@ -62,7 +62,7 @@ class Multicast(C.Structure):
 
 class LossGrad(C.Structure):        # neraf_loss_grad
     _fields_ = [("gt", C.c_void_p), ("n_total", C.c_int64), ("criterion", C.c_int32), ("sums", C.c_void_p),
-                ("w_sc", C.c_float), ("w_mag", C.c_float), ("losses", C.c_void_p)]
+                ("w_sc", C.c_float), ("w_mag", C.c_float), ("losses", C.c_void_p), ("total", C.c_void_p)]
 
 
 class DpOptions(C.Structure):

@@ -5,6 +5,8 @@
 //    gradient and the gradient w.r.t. the grid feature (the forward mat-vec lives in encode.cu's prep kernel),
 //  * bias gradients (column sums), and the gradient through the 10*tanh heads (NeRAF_field.py:57-58).
 #include "common.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 #include "loss_math.cuh"
 
@@ -116,15 +118,19 @@ int pack_list(PackList& L, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // compact (optional): the per-query block of dW1, (N, E) with row stride ld_c, copied into dW[:, K:K+E] by the same
 // rows (data parallel: that block was all-reduced in a compact buffer, see neraf_field_backward_dp).
-__global__ void __launch_bounds__(1024) grid_grads_kernel(const float* __restrict__ s, const float* __restrict__ g,
-                                                          const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
-                                                          float* __restrict__ dW, float* __restrict__ dg, int n_outer,
-                                                          int n_slices, const float* __restrict__ compact, int64_t E,
-                                                          int64_t ld_c) {
-  __shared__ float red[32][33];
+// TPB threads per block: TPB / 128 outer rows and TPB / 32 n-lanes per block.
+template <int TPB>
+__global__ void __launch_bounds__(TPB) grid_grads_kernel(const float* __restrict__ s, const float* __restrict__ g,
+                                                         const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
+                                                         float* __restrict__ dW, float* __restrict__ dg, int n_outer,
+                                                         int n_slices, const float* __restrict__ compact, int64_t E,
+                                                         int64_t ld_c) {
+  constexpr int NY = TPB / 32;                     // n-lanes of the dg part
+  constexpr int RPB = TPB / 128;                   // rows per block of the outer part
+  __shared__ float red[NY][33];
   int blk = blockIdx.x;
   if (blk < n_outer) {
-    const int64_t n = (int64_t)blk * 8 + threadIdx.x / 128;
+    const int64_t n = (int64_t)blk * RPB + threadIdx.x / 128;
     if (n >= N) return;
     const float sn = __ldg(s + n);
     float* row = dW + n * ldw;
@@ -141,13 +147,13 @@ __global__ void __launch_bounds__(1024) grid_grads_kernel(const float* __restric
   const int64_t n_lo = (int64_t)slice * per, n_hi = n_lo + per < N ? n_lo + per : N;
   float acc = 0.f;
   if (k < K)
-    for (int64_t n = n_lo + ny; n < n_hi; n += 32) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
+    for (int64_t n = n_lo + ny; n < n_hi; n += NY) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
   red[ny][kx] = acc;
   __syncthreads();
   if (ny == 0 && k < K) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t += red[i][kx];
+    for (int i = 0; i < NY; ++i) t += red[i][kx];
     atomicAdd(dg + k, t);
   }
 }
@@ -155,13 +161,15 @@ __global__ void __launch_bounds__(1024) grid_grads_kernel(const float* __restric
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
                bool dg_is_zero, cudaStream_t stream, const float* compact, int64_t E, int64_t ld_c) {
   if (N <= 0 || K <= 0) return NERAF_OK;
-  const int n_outer = dW ? (int)ceil_div(N, 8) : 0;
-  const int n_slices = 16;
+  // 256-thread blocks (2 outer rows / 8 n-lanes each) and 32 slices of n: measured 1.7 us faster per step than
+  // 1024-thread blocks with 16 slices (tools/ab_step.py) -- more, shorter blocks fill the last wave better
+  const int n_outer = dW ? (int)ceil_div(N, 2) : 0;
+  const int n_slices = 32;
   const int n_bwd = dg ? (int)ceil_div(K, 32) * n_slices : 0;
   if (n_outer + n_bwd == 0) return NERAF_OK;
   if (dg && !dg_is_zero) NERAF_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)K * 4, stream));
-  grid_grads_kernel<<<(unsigned)(n_outer + n_bwd), 1024, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, n_outer, n_slices,
-                                                                      dW ? compact : nullptr, E, ld_c);
+  grid_grads_kernel<256><<<(unsigned)(n_outer + n_bwd), 256, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, n_outer, n_slices,
+                                                                        dW ? compact : nullptr, E, ld_c);
   NERAF_CHECK_LAUNCH("grid_grads_kernel");
   return NERAF_OK;
 }
@@ -215,8 +223,10 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
                                                             int64_t ld_bf16, HeadColsum cs, neraf_loss_grad lg) {
   __shared__ float red[8][32];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  if (LOSS && lg.losses && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)      // the loss values themselves
+  if (LOSS && lg.losses && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {    // the loss values themselves
     finalize(lg.sums, lg.n_total, lg.criterion, lg.w_sc, lg.w_mag, lg.losses);
+    if (lg.total) lg.total[0] = lg.losses[0] + lg.losses[1];
+  }
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
   const int64_t r0 = (int64_t)blockIdx.y * kHeadRows;
   const int64_t r1 = r0 + kHeadRows < M ? r0 + kHeadRows : M;

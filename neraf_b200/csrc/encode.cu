@@ -125,11 +125,15 @@ struct PrepArgs {
   const float* W1; int64_t ldw; const float* b1; const float* g; int64_t n1, G; float* c1;
   int64_t E; __nv_bfloat16* w1_out; int64_t w1_ld;
   double* zero5;          // optional: five doubles cleared by block 0 (the loss sums a later launch of the step adds to)
+  unsigned int* zero_u32; int64_t n_zero_u32;     // optional: words cleared by block 0 (the job-list kernel's counters)
 };
 
 __global__ void __launch_bounds__(256) field_prep_kernel(const PrepArgs p) {
   int blk = blockIdx.x;
-  if (blk == 0 && threadIdx.x < 5 && p.zero5) p.zero5[threadIdx.x] = 0.0;
+  if (blk == 0) {
+    if (threadIdx.x < 5 && p.zero5) p.zero5[threadIdx.x] = 0.0;
+    for (int64_t i = threadIdx.x; i < p.n_zero_u32; i += 256) p.zero_u32[i] = 0u;
+  }
   if (blk < p.enc_blocks) {
     encode_one(p.enc, (int64_t)blk * 256 + threadIdx.x);
     return;
@@ -191,9 +195,11 @@ int encode_queries(const neraf_queries* q, float* out_f32, int64_t ld_f32, void*
 
 int field_prep(const neraf_queries* q, float* enc_f32, int64_t ld_f32, void* enc_bf16, int64_t ld_bf16, int ncols_padded,
                const float* W1, int64_t ldw, const float* b1, const float* g, int64_t n1, int64_t G, float* c1,
-               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream, double* zero5) {
+               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream, double* zero5, unsigned int* zero_u32,
+               int64_t n_zero_u32) {
   PrepArgs p = {};
   p.zero5 = zero5;
+  p.zero_u32 = zero_u32; p.n_zero_u32 = zero_u32 ? n_zero_u32 : 0;
   if (q) {
     NERAF_TRY(check_queries(q));
     p.enc = EncodeArgs{q->batch, q->time_query, q->mic_pose, q->source_pose, q->rot, q->aabb, q->time_denominator,
@@ -207,6 +213,7 @@ int field_prep(const neraf_queries* q, float* enc_f32, int64_t ld_f32, void* enc
   const int blocks = p.enc_blocks + p.gb_blocks + p.pk_blocks;
   if (blocks == 0) {
     if (zero5) NERAF_CHECK_CUDA(cudaMemsetAsync(zero5, 0, 5 * sizeof(double), stream));
+    if (p.n_zero_u32 > 0) NERAF_CHECK_CUDA(cudaMemsetAsync(zero_u32, 0, (size_t)p.n_zero_u32 * 4, stream));
     return NERAF_OK;
   }
   field_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);

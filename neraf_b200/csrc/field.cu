@@ -328,7 +328,7 @@ static int field_forward_impl(const neraf_field_dims* dims, int precision, const
   if (q->enc) NERAF_TRY(convert_bf16(q->enc, B, l.E, q->enc_ld, enc, l.ld_enc, nullptr, 0, stream));
   NERAF_TRY(field_prep(q->enc ? nullptr : q, nullptr, 0, enc, l.ld_enc, (int)l.ld_enc, weights[0], ldw0, biases[0],
                        grid_feature, l.n[0], l.G, c1w, l.E, do_pack ? at(pack, l.w[0]) : nullptr, l.ldw[0], stream,
-                       loss_sums));
+                       loss_sums, reinterpret_cast<unsigned int*>(at(ws, l.counters)), (int64_t)(l.counters_bytes / 4)));
 
   // One persistent launch for the whole MLP (two when the operands are being re-packed on the helper stream:
   // layer 1 starts as soon as its own copy exists, the remaining layers once the helper stream has finished).
@@ -358,7 +358,9 @@ static int field_forward_impl(const neraf_field_dims* dims, int precision, const
   // the other layers; the second launch's fixed cost and the lost layer-1 / layer-2 overlap cost more than the
   // few microseconds of waiting for the pack.)
   if (side) NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
-  NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream));
+  // the counters were cleared by field_prep_kernel above, and every job-list launch clears them again before it exits:
+  // neither this launch nor the backward's needs a memset node
+  NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream, 0, true));
   return NERAF_OK;
 }
 
@@ -564,7 +566,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       }
     }
   }
-  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas));
+  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas, true));   // left clean by the forward's launch
   if (!heads_contiguous && phase != 2 && !dw16)
     for (int c = 0; c < l.C; ++c)
       NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,

@@ -86,6 +86,8 @@ enum { TR_DEP = 0, TR_LOADED, TR_MMA_START, TR_MMA_FIRST, TR_MMA_DONE, TR_EPI_ST
 
 struct MegaParams {
   int num_jobs, num_tiles;
+  int num_counters;                // counters[0 .. num_counters) are dependency counters, counters[num_counters] a ticket:
+                                   // the last CTA to finish clears them all, so the NEXT launch finds them zero
   unsigned int* counters;
   unsigned long long* trace;       // null unless tracing
   DeviceJob jobs[NERAF_MEGA_MAX_JOBS];
@@ -714,6 +716,16 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, MEGA_TMEM_COLS);
   }
+  // Leave the counters as they were found: a CTA takes its ticket after its last poll, so whoever draws the last ticket
+  // knows nobody reads the counters any more and clears them (and the ticket) for the next launch on this buffer.
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(P.counters + P.num_counters, 1u);
+    if (t == gridDim.x - 1) {
+      for (int i = 0; i <= P.num_counters; ++i) P.counters[i] = 0u;
+      __threadfence();
+    }
+  }
 }
 
 }  // namespace umma
@@ -721,7 +733,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
 int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
                       CUtensorMap* out);
 
-int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas) {
+int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas,
+             bool counters_clean) {
   using namespace umma;
   NERAF_REQUIRE(jobs && n_jobs > 0 && n_jobs <= NERAF_MEGA_MAX_JOBS, "mega_run: 1..%d jobs", NERAF_MEGA_MAX_JOBS);
   static MegaParams P;          // large: build in static storage (single-threaded driver, see header conventions)
@@ -799,9 +812,12 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     NERAF_REQUIRE(!s.epi.loss_gt || s.epi.out_f32, "mega_run: job %d: loss_gt needs an fp32 output", i);
   }
   P.num_tiles = tile;
-  NERAF_REQUIRE(counters && counters_bytes >= (size_t)cnt * sizeof(unsigned int), "mega_run: counter buffer too small");
+  NERAF_REQUIRE(counters && counters_bytes >= (size_t)(cnt + 1) * sizeof(unsigned int), "mega_run: counter buffer too small");
   P.counters = reinterpret_cast<unsigned int*>(counters);
-  NERAF_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)cnt * sizeof(unsigned int), stream));
+  P.num_counters = cnt;
+  // every launch leaves its counters zero (kernel epilogue); a caller that knows the buffer was cleared before, or last
+  // used by this kernel, skips the memset node
+  if (!counters_clean) NERAF_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)(cnt + 1) * sizeof(unsigned int), stream));
   // Debug timeline: NERAF_MEGA_TRACE=<file> makes every launch synchronous and appends its per-tile stamps.
   static const char* trace_path = getenv("NERAF_MEGA_TRACE");
   P.trace = nullptr;

@@ -17,7 +17,8 @@ int encode_queries(const neraf_queries* q, float* out_f32, int64_t ld_f32, void*
 // (skipped when w1_out is null).
 int field_prep(const neraf_queries* q, float* enc_f32, int64_t ld_f32, void* enc_bf16, int64_t ld_bf16, int ncols_padded,
                const float* W1, int64_t ldw, const float* b1, const float* g, int64_t n1, int64_t G, float* c1,
-               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream, double* zero5 = nullptr);
+               int64_t E, void* w1_out, int64_t w1_ld, cudaStream_t stream, double* zero5 = nullptr,
+               unsigned int* zero_u32 = nullptr, int64_t n_zero_u32 = 0);
 
 // gemm_simt.cu
 int gemm_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
@@ -33,7 +34,10 @@ int gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const
 #define NERAF_MEGA_MAX_JOBS NERAF_MAX_GEMM_JOBS
 typedef neraf_gemm_job MegaJob;      // public contract: include/neraf_b200.h
 // max_ctas: 0 = one CTA per SM; otherwise an upper bound on the grid (a concurrent kernel gets the other SMs)
-int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas = 0);
+// counters_clean: the caller guarantees the counter buffer is zero (cleared explicitly, or last used by this kernel,
+// which clears what it used before it exits): no memset node is issued
+int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas = 0,
+             bool counters_clean = false);
 
 // elementwise.cu
 int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out, void* out_t,

@@ -414,7 +414,9 @@ class GraphedTrainStep:
         lg = _lib.LossGrad()
         lg.gt, lg.n_total, lg.criterion, lg.sums = st["data"].data_ptr(), n_total, crit, self.sums.data_ptr()
         lg.w_sc, lg.w_mag = w_sc, w_mag
-        lg.losses = losses.data_ptr()          # ... and so are the two loss values: no loss launch in the step
+        lg.losses = losses.data_ptr()          # ... and so are the two loss values and their sum
+        self.total_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        lg.total = self.total_loss.data_ptr()
         w_arr, b_arr = _lib.ptr_array(weights), _lib.ptr_array(biases)
         dw_arr, db_arr = _lib.ptr_array(dws), _lib.ptr_array(dbs)
         self._keep = (pack, ws, out, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims, lg)
@@ -505,16 +507,6 @@ class GraphedTrainStep:
             self.losses = {"audio_mse": losses[1]}
         else:
             self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
-        # what a Trainer reads back every step (the sum of the loss dict), formed inside the graph
-        self.total_loss = torch.zeros((), dtype=torch.float32, device=dev)
-        plain_backward = backward_part
-
-        def backward_part():
-            plain_backward()
-            if model.criterion_name == "MSE":
-                self.total_loss.copy_(losses[1])
-            else:
-                torch.add(losses[0], losses[1], out=self.total_loss)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         if self.group is None:
