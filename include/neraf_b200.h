@@ -164,7 +164,9 @@ typedef struct {
 /* neraf_field_forward with the spectral loss's partial sums formed by the epilogue that stores the prediction (bf16
  * path; the fp32 path runs neraf_spectral_loss_sums behind the forward): gt is the (B, C, F) target, sums f64[>=5] is
  * zeroed by the call and holds the four sums of neraf_spectral_loss_sums afterwards.  With neraf_loss_grad.losses in
- * the backward, a training step needs no loss launch at all. */
+ * the backward, a training step needs no loss launch at all.  gt == NULL: the call only clears sums (inside the launch
+ * that precedes the GEMMs), for a following neraf_spectral_loss_sums(..., accumulate = 1) -- the variant that measured
+ * faster at the reference batch, see neraf_b200/model.py. */
 NERAF_API int neraf_field_forward_loss_sums(const neraf_field_dims* dims, int precision, const neraf_queries* queries,
                                   const float* grid_feature, const float* const* weights, const float* const* biases,
                                   void* pack, size_t pack_bytes, int repack, void* workspace, size_t workspace_bytes,

@@ -307,8 +307,8 @@ static int field_forward_impl(const neraf_field_dims* dims, int precision, const
       NERAF_TRY(gemm_f32(B, l.F, l.W, x, ldx, 1, weights[l.L + c], l.W, 1, biases[l.L + c], NERAF_ACT_TANH10, nullptr, 0,
                          out + (size_t)c * l.F, l.CF, 0, stream));
     if (loss_sums) {
-      NERAF_CHECK_CUDA(cudaMemsetAsync(loss_sums + 4, 0, sizeof(double), stream));
-      NERAF_TRY(neraf_spectral_loss_sums(out, loss_gt, B * l.CF, loss_sums, 0, stream));
+      NERAF_CHECK_CUDA(cudaMemsetAsync(loss_sums, 0, 5 * sizeof(double), stream));
+      if (loss_gt) NERAF_TRY(neraf_spectral_loss_sums(out, loss_gt, B * l.CF, loss_sums, 1, stream));
     }
     return NERAF_OK;
   }
@@ -377,7 +377,7 @@ extern "C" int neraf_field_forward_loss_sums(const neraf_field_dims* dims, int p
                                              const float* const* biases, void* pack, size_t pack_bytes, int repack,
                                              void* ws, size_t ws_bytes, float* out, int keep, const float* gt,
                                              double* sums, neraf_stream_t stream) {
-  NERAF_REQUIRE(sums && (gt || (q && q->batch == 0)), "field_forward_loss_sums: gt / sums is null");
+  NERAF_REQUIRE(sums, "field_forward_loss_sums: sums is null");
   return field_forward_impl(dims, precision, q, grid_feature, weights, biases, pack, pack_bytes, repack, ws, ws_bytes, out,
                             keep, gt, sums, (cudaStream_t)stream);
 }

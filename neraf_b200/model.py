@@ -370,6 +370,10 @@ class GraphedTrainStep:
         red_w = list(weights[1:]) if defer else list(weights)
         sizes = [t.numel() for t in red_w] + ([n1 * ldc] if defer else []) + [b.numel() for b in biases]
         n_weight_elems = sum(sizes) - sum(b.numel() for b in biases)
+        # single process: dg sits right behind the bias gradients, so the library clears both with ONE memset node
+        tail_grid = grid_p is not None and not defer
+        if tail_grid:
+            sizes = sizes + [grid_p.numel()]
         # Fused all-reduce (experimental): the flat buffer lives in symmetric memory and the weight-gradient GEMMs add
         # their tiles into every rank's copy through its multicast alias.  Otherwise plain memory + one NCCL all-reduce.
         self.flat_grad, mc_ptr = None, 0
@@ -390,7 +394,12 @@ class GraphedTrainStep:
         dws = [v.view_as(t) for v, t in zip(parts[:nw], red_w)]
         compact = parts[nw] if defer else None
         dbs = [v.view_as(t) for v, t in zip(parts[nw + (1 if defer else 0):], biases)]
-        dgrid = torch.zeros_like(grid_p) if grid_p is not None else None
+        n_b = len(biases)
+        first_b = nw + (1 if defer else 0)
+        dbs = dbs[:n_b]
+        dgrid = None
+        if grid_p is not None:
+            dgrid = parts[first_b + n_b].view_as(grid_p) if tail_grid else torch.zeros_like(grid_p)
         if defer:
             dws = [torch.zeros_like(weights[0])] + dws
         order = list(weights) + list(biases) + ([grid_p] if grid_p is not None else [])
@@ -476,11 +485,13 @@ class GraphedTrainStep:
                                                              ws.numel(), out.data_ptr(), 1, st["data"].data_ptr(),
                                                              self.sums.data_ptr(), s))
             else:
-                _lib.check(lib.neraf_field_forward(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr, b_arr,
-                                                   pack.data_ptr(), pack.numel(), 1, ws.data_ptr(), ws.numel(),
-                                                   out.data_ptr(), 1, s))
+                # gt = NULL: the forward only clears the sums (no memset node), the loss kernel then accumulates
+                _lib.check(lib.neraf_field_forward_loss_sums(C.byref(dims), prec, C.byref(qs), _lib.ptr(grid_p), w_arr,
+                                                             b_arr, pack.data_ptr(), pack.numel(), 1, ws.data_ptr(),
+                                                             ws.numel(), out.data_ptr(), 1, None,
+                                                             self.sums.data_ptr(), s))
                 _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
-                                                        self.sums.data_ptr(), 0, s))
+                                                        self.sums.data_ptr(), 1, s))
             if self.nvls:
                 torch.cuda.current_stream(dev).wait_stream(zero_stream)
 
