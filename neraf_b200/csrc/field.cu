@@ -149,7 +149,10 @@ int choose_bn(int64_t M, int64_t N, int64_t K, int min_bn) {
     const double mma = kb * (bn == 256 ? 0.41 : 0.36);
     const double epi = 0.9 * (bn / 64) + 0.9;
     const double t = (ceil(tiles / pairs) - 1.0) * (mma > epi ? mma : epi) + mma + epi;   // last round: nothing overlaps
-    if (t < best_t * 0.97) { best_t = t; best = bn; }        // ties go to the narrower tile (shorter epilogue tail)
+    // ties go to the narrower tile (shorter epilogue tail) -- except for epilogue-bound jobs (layer 1 forward: 3
+    // k-blocks), where the wider tile means fewer rounds and fewer publishes: 256 instead of 128 columns measured
+    // 4.5 us per step faster at B=2048 (tools/ab_step.py)
+    if (t < best_t * (mma < epi ? 1.02 : 0.97)) { best_t = t; best = bn; }
   }
   return best;
 }
@@ -178,7 +181,11 @@ MegaJob make_wgrad_job(int64_t n_out, int64_t k_in, int64_t batch, const void* d
                        int64_t ld_x, int wait_job) {
   MegaJob j = make_job(n_out, k_in, batch, dz, ld_dz, x, ld_x, wait_job, 1);
   j.a_mn = 1; j.b_mn = 1;
-  j.bn = choose_bn(n_out, k_in, batch, 128);
+  // A weight-gradient job is never on the dgrad chain, it fills the pairs the chain leaves idle -- and every pair it
+  // occupies starts its next chain tile later.  Rows of >= 2048 columns take the widest tile (half as many tiles, less
+  // operand traffic): dW3 (1024 x 2048) at 256 instead of 128 columns measured 6.5 us per step faster at B=2048, while
+  // 256 columns for the 1024-wide rows (dW4, dW5) measured slower or equal (tools/ab_step.py).
+  j.bn = k_in >= 2048 ? 256 : choose_bn(n_out, k_in, batch, 128);
   return j;
 }
 
