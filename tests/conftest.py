@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def built():
+    """The in-tree library and the CPU harnesses (tests/csrc) are built once per session (nvcc cross-compiles)."""
+    import __graft_entry__ as ge
+    ge.build()
+    return True
+

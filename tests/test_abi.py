@@ -12,13 +12,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="session")
-def built():
-    import __graft_entry__ as ge
-    ge.build()
-    return True
-
-
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "neraf_b200.h")).read()
     return sorted(set(re.findall(r"NERAF_API\s+[\w\s\*]+?\b(neraf_\w+)\s*\(", text)))

@@ -50,7 +50,6 @@ def test_metrics_fail_loudly_without_a_device():
         acoustic_metrics(torch.zeros(2, 100), 48000.0)
 
 
-# ------------------------------------------------------------------------------------------------ GPU
 def _oracle_all(h, fs, advanced):
     t60 = np.array([(omet.t60_raf if advanced else omet.t60_soundspaces)(x, fs) for x in h])
     edt = []
@@ -64,13 +63,7 @@ def _oracle_all(h, fs, advanced):
     return t60, np.array(edt), c50
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("shape,advanced", [(syn.RAF, True), (syn.SOUNDSPACES, False), (syn.RAF, False)])
-def test_batched_metrics_match_the_oracle(shape, advanced):
-    from neraf_b200.metrics import acoustic_metrics
-    dev = cuda()
-    h = _rirs(shape, 48, 2)
-    got = {k: v.cpu().numpy() for k, v in acoustic_metrics(torch.from_numpy(h).to(dev), shape.fs, advanced).items()}
+def _check_against_oracle(got, h, shape, advanced):
     t60, edt, c50 = _oracle_all(h, shape.fs, advanced)
     one_sample = 1.0 / shape.fs
     # decay times are sample indices over fs: identical up to one sample where log10f's last bit decides a crossing
@@ -86,6 +79,31 @@ def test_batched_metrics_match_the_oracle(shape, advanced):
     fin = np.isfinite(c50)
     assert np.array_equal(np.isfinite(got["c50"]), fin)
     assert np.max(np.abs(got["c50"][fin] - c50[fin])) < 1e-4
+
+
+@pytest.mark.parametrize("shape,advanced", [(syn.RAF, True), (syn.SOUNDSPACES, False)])
+def test_metrics_core_on_host_matches_the_oracle(built, shape, advanced):
+    """Drives neraf_b200/csrc/metrics_core.h (the code the GPU kernel executes per response) on the CPU."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "metrics_host_check")
+    h = _rirs(shape, 24, 2)
+    hz, decay = (200.0, 10.0) if advanced else (0.0, 30.0)
+    out = subprocess.run([exe, str(h.shape[0]), str(h.shape[1]), repr(float(shape.fs)), str(hz), str(decay)],
+                         input=np.ascontiguousarray(h).tobytes(), capture_output=True)
+    assert out.returncode == 0
+    m = np.frombuffer(out.stdout, dtype=np.float64).reshape(-1, 3)
+    _check_against_oracle({"t60": m[:, 0], "edt": m[:, 1], "c50": m[:, 2]}, h, shape, advanced)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,advanced", [(syn.RAF, True), (syn.SOUNDSPACES, False), (syn.RAF, False)])
+def test_batched_metrics_match_the_oracle(shape, advanced):
+    from neraf_b200.metrics import acoustic_metrics
+    dev = cuda()
+    h = _rirs(shape, 48, 2)
+    got = {k: v.cpu().numpy() for k, v in acoustic_metrics(torch.from_numpy(h).to(dev), shape.fs, advanced).items()}
+    _check_against_oracle(got, h, shape, advanced)
 
 
 @pytest.mark.gpu
