@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 6
+#define NERAF_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))
@@ -401,6 +401,76 @@ NERAF_API int neraf_gemm_bf16_set_tile(int code);
  * (cols, rows) row stride ld_t).  Either output may be NULL. */
 NERAF_API int neraf_convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                        void* out_t, int64_t ld_t, neraf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grid-feature producer: the operators of the reference's ResNet3D (NeRAF_resnet3d.py:116-201, called at
+ * NeRAF_model.py:554-556 every training step and :680-683 per rendered RIR) that are not GEMMs.  A convolution is
+ * neraf_grid_im2col + neraf_gemm_bf16_jobs (bf16) / neraf_gemm_f32 (fp32); its data gradient is a GEMM +
+ * neraf_grid_col2im, its weight gradient one GEMM that contracts over the voxels.  neraf_b200/gridnet.py assembles
+ * them into ResNet3D_helper with the reference's parameter names.
+ *
+ * Activations are matrices (V, C): row v = (d * H + h) * W + w is a voxel, its C channels are contiguous (channels
+ * last), row stride ld >= C elements; dtype NERAF_DT_F32 or NERAF_DT_BF16.  Every function processes one grid
+ * (the reference's batch is 1).
+ * ---------------------------------------------------------------------------------------------- */
+enum { NERAF_DT_F32 = 0, NERAF_DT_BF16 = 1 };
+
+typedef struct {
+  int32_t in_d, in_h, in_w; /* input extent in voxels                                     */
+  int32_t channels;         /* channels of the tensor the window slides over               */
+  int32_t k, stride, pad;   /* cubic window; output extent (in + 2 pad - k) / stride + 1   */
+} neraf_window3d;
+
+/* col[v_out, ((kd k + kh) k + kw) C + c] = in[v_in(v_out, kd, kh, kw), c] (zero outside the grid); columns
+ * [k^3 C, ld_col) are zero-filled.  The input element (v, c) is read at in[v * voxel_stride + c * channel_stride]:
+ * (ld, 1) for an activation matrix, (1, V) for the reference's channels-first grid (1, C, D, H, W). */
+NERAF_API int neraf_grid_im2col(const neraf_window3d* w, const void* in, int32_t in_dtype, int64_t voxel_stride,
+                      int64_t channel_stride, void* col, int32_t col_dtype, int64_t ld_col, neraf_stream_t stream);
+/* dx[v_in, c] = sum of dcol[v_out, kidx C + c] over the window positions that read v_in (gather, deterministic). */
+NERAF_API int neraf_grid_col2im(const neraf_window3d* w, const void* dcol, int32_t dtype, int64_t ld_col, void* dx,
+                      int64_t ld_dx, neraf_stream_t stream);
+/* nn.Conv3d weight (c_out, c_in, k, k, k) fp32 -> GEMM operand out[co, kidx c_in + ci], row stride ld_out (pad
+ * columns zero), and the weight gradient back: dw[co, ci, kidx] = dw_mat[co * ld + kidx c_in + ci]. */
+NERAF_API int neraf_grid_pack_weight(const float* weight, int64_t c_out, int64_t c_in, int64_t k3, void* out,
+                           int32_t out_dtype, int64_t ld_out, neraf_stream_t stream);
+NERAF_API int neraf_grid_unpack_wgrad(const float* dw_mat, int64_t ld, int64_t c_out, int64_t c_in, int64_t k3,
+                            float* dweight, neraf_stream_t stream);
+
+/* nn.BatchNorm3d.  sums: dev f64 (2, C), cleared by the call: sum x, sum x^2 over the V rows. */
+NERAF_API int neraf_grid_bn_stats(const void* x, int32_t dtype, int64_t V, int64_t C, int64_t ld, double* sums,
+                        neraf_stream_t stream);
+/* training != 0: mean / invstd (dev fp32 (C)) from the batch sums (biased variance), running estimates updated with
+ * the unbiased variance when momentum > 0 (running_* may be NULL otherwise); training == 0: from the running
+ * estimates (sums ignored).  invstd may be NULL (global average pooling = stats + this call's mean). */
+NERAF_API int neraf_grid_bn_finalize(const double* sums, int64_t V, int64_t C, float eps, float momentum, int32_t training,
+                           float* running_mean, float* running_var, float* mean, float* invstd,
+                           neraf_stream_t stream);
+/* y = [relu]( gamma (x - mean) invstd + beta [+ residual] ); residual may be NULL. */
+NERAF_API int neraf_grid_bn_apply(const void* x, int32_t dtype, int64_t V, int64_t C, int64_t ld_x, const float* mean,
+                        const float* invstd, const float* gamma, const float* beta, const void* residual,
+                        int64_t ld_res, int32_t relu, void* y, int64_t ld_y, neraf_stream_t stream);
+/* Backward in two passes (all matrices (V, C) with the same row stride ld).
+ * reduce: g = (dy [+ dy2]) * [y > 0] (dy2, y optional) is stored to g_out and sums (dev f64 (2, C), cleared by the
+ *         call) receive sum g and sum g xhat;
+ * apply : dx = gamma invstd (g - (sum g + xhat sum g xhat) / V) (training) or gamma invstd g (running statistics);
+ *         dgamma = sum g xhat, dbeta = sum g (dev fp32 (C), either may be NULL).  dx may alias g. */
+NERAF_API int neraf_grid_bn_backward_reduce(const void* dy, const void* dy2, const void* y, const void* x, int32_t dtype,
+                                  int64_t V, int64_t C, int64_t ld, const float* mean, const float* invstd,
+                                  void* g_out, double* sums, neraf_stream_t stream);
+NERAF_API int neraf_grid_bn_backward_apply(const void* g, const void* x, int32_t dtype, int64_t V, int64_t C, int64_t ld,
+                                 const float* mean, const float* invstd, const float* gamma, const double* sums,
+                                 int32_t training, void* dx, float* dgamma, float* dbeta, neraf_stream_t stream);
+
+/* nn.MaxPool3d(k, stride, pad) (NeRAF_resnet3d.py:122): y (V_out, C), argmax dev i32 (V_out, C) = the winning input
+ * voxel (first maximum in scan order, as torch's CPU kernel); backward gathers dy (+ dy2, optional: the pooled tensor
+ * has two consumers, same row stride) through argmax into dx (V_in, C). */
+NERAF_API int neraf_grid_maxpool(const neraf_window3d* w, const void* x, int32_t dtype, int64_t ld_x, void* y, int64_t ld_y,
+                       int32_t* argmax, neraf_stream_t stream);
+NERAF_API int neraf_grid_maxpool_backward(const neraf_window3d* w, const void* dy, const void* dy2, int32_t dtype, int64_t ld_dy,
+                                const int32_t* argmax, void* dx, int64_t ld_dx, neraf_stream_t stream);
+/* out[r, c] = v[c] * scale for r < V: gradient of the global average pooling (NeRAF_resnet3d.py:141-157). */
+NERAF_API int neraf_grid_broadcast_rows(const float* v, float scale, int64_t V, int64_t C, void* out, int32_t dtype,
+                              int64_t ld, neraf_stream_t stream);
 
 #ifdef __cplusplus
 }

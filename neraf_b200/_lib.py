@@ -75,6 +75,11 @@ class MetricParams(C.Structure):     # neraf_metric_params
     _fields_ = [("n_samples", C.c_int32), ("fs", C.c_double), ("t60_decay_db", C.c_float), ("t60_highpass_hz", C.c_double)]
 
 
+class Window3d(C.Structure):         # neraf_window3d
+    _fields_ = [("in_d", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("channels", C.c_int32),
+                ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32)]
+
+
 class GlParams(C.Structure):
     _fields_ = [("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop", C.c_int32), ("n_frames", C.c_int32),
                 ("n_iter", C.c_int32), ("momentum", C.c_float), ("input_is_log", C.c_int32)]
@@ -82,6 +87,24 @@ class GlParams(C.Structure):
 
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 _pp = C.POINTER(C.c_void_p)
+
+_pw = C.POINTER(Window3d)
+# the grid-feature producer's operators; tests/test_gridnet.py binds a host build of the same code with the same lists
+GRID_SIGNATURES = {
+    "neraf_grid_im2col": (C.c_int, [_pw, _vp, _i32, _i64, _i64, _vp, _i32, _i64, _vp]),
+    "neraf_grid_col2im": (C.c_int, [_pw, _vp, _i32, _i64, _vp, _i64, _vp]),
+    "neraf_grid_pack_weight": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _vp]),
+    "neraf_grid_unpack_wgrad": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "neraf_grid_bn_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),
+    "neraf_grid_bn_finalize": (C.c_int, [_vp, _i64, _i64, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "neraf_grid_bn_apply": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "neraf_grid_bn_backward_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "neraf_grid_bn_backward_apply": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                                                _vp]),
+    "neraf_grid_maxpool": (C.c_int, [_pw, _vp, _i32, _i64, _vp, _i64, _vp, _vp]),
+    "neraf_grid_maxpool_backward": (C.c_int, [_pw, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp]),
+    "neraf_grid_broadcast_rows": (C.c_int, [_vp, _f32, _i64, _i64, _vp, _i32, _i64, _vp]),
+}
 
 # name -> (restype, argtypes); must list every symbol declared in include/neraf_b200.h
 SIGNATURES = {
@@ -116,6 +139,7 @@ SIGNATURES = {
     "neraf_gemm_bf16_jobs": (C.c_int, [C.POINTER(GemmJob), C.c_int, _vp, _sz, _vp]),
     "neraf_gemm_bf16_set_tile": (C.c_int, [C.c_int]),
     "neraf_convert_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+    **GRID_SIGNATURES,
 }
 
 _lib = None

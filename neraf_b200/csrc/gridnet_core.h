@@ -1,0 +1,314 @@
+// Per-element code of the grid-feature producer's data-movement and normalisation kernels (gridnet.cu), written so
+// that the SAME functions compile for the device and for the host: tests/csrc/gridnet_host.cpp loops them over the
+// whole index space on the CPU and the not-gpu tests compare the result -- and the whole ResNet3D assembled from
+// them by neraf_b200/gridnet.py -- with the reference's NeRAF_resnet3d.py run by torch.
+//
+// Layout: an activation is a matrix (V, C): row v = (d * H + h) * W + w is a voxel, the C channels of a voxel are
+// contiguous ("channels last"), row stride ld >= C.  Elements are fp32 or bf16 (bf16_t: the same 16 bits as
+// __nv_bfloat16, round-to-nearest-even).  A convolution is im2col (gather) + GEMM; column j of the gathered matrix
+// is ((kd * k + kh) * k + kw) * C + c, so a voxel's channel vector is copied as a unit.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define GN_HD __host__ __device__ __forceinline__
+#else
+#define GN_HD inline
+#endif
+
+namespace neraf {
+namespace gridnet {
+
+struct bf16_t { uint16_t bits; };
+
+GN_HD float bits_to_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+GN_HD uint32_t float_to_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+GN_HD float to_float(float v) { return v; }
+GN_HD float to_float(bf16_t v) { return bits_to_float((uint32_t)v.bits << 16); }
+GN_HD void from_float(float v, float* out) { *out = v; }
+GN_HD void from_float(float v, bf16_t* out) {                 // round to nearest even, NaN stays NaN
+  uint32_t u = float_to_bits(v);
+  if ((u & 0x7fffffffu) > 0x7f800000u) { out->bits = 0x7fc0; return; }
+  u += 0x7fffu + ((u >> 16) & 1u);
+  out->bits = (uint16_t)(u >> 16);
+}
+
+// Cubic-window geometry shared by the convolutions and the max pooling (NeRAF_resnet3d.py:119,122,88-89,83).
+struct Window {
+  int in_d, in_h, in_w;      // input extent
+  int C;                     // channels
+  int k, stride, pad;
+  int out_d, out_h, out_w;   // (in + 2 pad - k) / stride + 1
+};
+
+GN_HD int out_extent(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+
+GN_HD Window make_window(int in_d, int in_h, int in_w, int C, int k, int stride, int pad) {
+  Window w;
+  w.in_d = in_d; w.in_h = in_h; w.in_w = in_w; w.C = C; w.k = k; w.stride = stride; w.pad = pad;
+  w.out_d = out_extent(in_d, k, stride, pad);
+  w.out_h = out_extent(in_h, k, stride, pad);
+  w.out_w = out_extent(in_w, k, stride, pad);
+  return w;
+}
+
+GN_HD long long in_voxels(const Window& w) { return (long long)w.in_d * w.in_h * w.in_w; }
+GN_HD long long out_voxels(const Window& w) { return (long long)w.out_d * w.out_h * w.out_w; }
+
+// ---- im2col: element (v_out, j) of the gathered matrix, j in [0, ld): pad columns (j >= k^3 C) read as zero ----------
+// The input is addressed as in[v * voxel_stride + c * channel_stride]: (V, C) row-major activations use (ld, 1), the
+// reference's channels-first grid (1, C, D, H, W) uses (1, V).
+template <class Tin, class Tout>
+GN_HD void im2col_element(const Window& w, const Tin* in, long long voxel_stride, long long channel_stride, Tout* col,
+                          long long ld, long long idx) {
+  const long long v = idx / ld;
+  const int j = (int)(idx - v * ld);
+  float val = 0.f;
+  const int K = w.k * w.k * w.k * w.C;
+  if (j < K) {
+    const int kidx = j / w.C, c = j - kidx * w.C;
+    const int kw = kidx % w.k, kh = (kidx / w.k) % w.k, kd = kidx / (w.k * w.k);
+    const int ow = (int)(v % w.out_w), oh = (int)((v / w.out_w) % w.out_h), od = (int)(v / ((long long)w.out_w * w.out_h));
+    const int id = od * w.stride - w.pad + kd, ih = oh * w.stride - w.pad + kh, iw = ow * w.stride - w.pad + kw;
+    if (id >= 0 && id < w.in_d && ih >= 0 && ih < w.in_h && iw >= 0 && iw < w.in_w) {
+      const long long vin = ((long long)id * w.in_h + ih) * w.in_w + iw;
+      val = to_float(in[vin * voxel_stride + c * channel_stride]);
+    }
+  }
+  from_float(val, col + idx);
+}
+
+// ---- col2im (the data gradient of a convolution, gather form): dx[v_in, c] = sum over the window positions that
+// read voxel v_in of dcol[v_out, kidx * C + c].  fp32 accumulation, fixed order (kd, kh, kw ascending): deterministic.
+template <class T>
+GN_HD void col2im_element(const Window& w, const T* dcol, long long ld_col, T* dx, long long ld_dx, long long idx) {
+  const long long v = idx / w.C;
+  const int c = (int)(idx - v * w.C);
+  const int iw = (int)(v % w.in_w), ih = (int)((v / w.in_w) % w.in_h), id = (int)(v / ((long long)w.in_w * w.in_h));
+  float acc = 0.f;
+  for (int kd = 0; kd < w.k; ++kd) {
+    const int td = id + w.pad - kd;
+    if (td < 0 || td % w.stride) continue;
+    const int od = td / w.stride;
+    if (od >= w.out_d) continue;
+    for (int kh = 0; kh < w.k; ++kh) {
+      const int th = ih + w.pad - kh;
+      if (th < 0 || th % w.stride) continue;
+      const int oh = th / w.stride;
+      if (oh >= w.out_h) continue;
+      for (int kw = 0; kw < w.k; ++kw) {
+        const int tw = iw + w.pad - kw;
+        if (tw < 0 || tw % w.stride) continue;
+        const int ow = tw / w.stride;
+        if (ow >= w.out_w) continue;
+        const long long vout = ((long long)od * w.out_h + oh) * w.out_w + ow;
+        const int kidx = (kd * w.k + kh) * w.k + kw;
+        acc += to_float(dcol[vout * ld_col + (long long)kidx * w.C + c]);
+      }
+    }
+  }
+  from_float(acc, dx + v * ld_dx + c);
+}
+
+// ---- max pooling (nn.MaxPool3d(3, 2, 1), NeRAF_resnet3d.py:122): first maximum in (d, h, w) scan order, like
+// torch's CPU kernel (max_pool3d_with_indices: `val > maxval`), so that gradients of tied maxima -- frequent after a
+// ReLU -- take the same route as in the reference.  argmax holds the input voxel index.
+template <class T>
+GN_HD void maxpool_element(const Window& w, const T* x, long long ld_x, T* y, long long ld_y, int32_t* argmax,
+                           long long idx) {
+  const long long v = idx / w.C;
+  const int c = (int)(idx - v * w.C);
+  const int ow = (int)(v % w.out_w), oh = (int)((v / w.out_w) % w.out_h), od = (int)(v / ((long long)w.out_w * w.out_h));
+  float best = 0.f;
+  long long arg = -1;
+  for (int kd = 0; kd < w.k; ++kd) {
+    const int id = od * w.stride - w.pad + kd;
+    if (id < 0 || id >= w.in_d) continue;
+    for (int kh = 0; kh < w.k; ++kh) {
+      const int ih = oh * w.stride - w.pad + kh;
+      if (ih < 0 || ih >= w.in_h) continue;
+      for (int kw = 0; kw < w.k; ++kw) {
+        const int iw = ow * w.stride - w.pad + kw;
+        if (iw < 0 || iw >= w.in_w) continue;
+        const long long vin = ((long long)id * w.in_h + ih) * w.in_w + iw;
+        const float val = to_float(x[vin * ld_x + c]);
+        if (arg < 0 || val > best || val != val) { best = val; arg = vin; }
+      }
+    }
+  }
+  from_float(best, y + v * ld_y + c);
+  argmax[v * w.C + c] = (int32_t)arg;
+}
+
+// gradient of the pooling, gather form: every input voxel sums the gradients of the windows it won; dy2 (optional) is
+// a second gradient of the pooled tensor (its two consumers: the first block's convolution and its shortcut)
+template <class T>
+GN_HD void maxpool_backward_element(const Window& w, const T* dy, const T* dy2, long long ld_dy, const int32_t* argmax,
+                                    T* dx, long long ld_dx, long long idx) {
+  const long long v = idx / w.C;
+  const int c = (int)(idx - v * w.C);
+  const int iw = (int)(v % w.in_w), ih = (int)((v / w.in_w) % w.in_h), id = (int)(v / ((long long)w.in_w * w.in_h));
+  float acc = 0.f;
+  for (int kd = 0; kd < w.k; ++kd) {
+    const int td = id + w.pad - kd;
+    if (td < 0 || td % w.stride) continue;
+    const int od = td / w.stride;
+    if (od >= w.out_d) continue;
+    for (int kh = 0; kh < w.k; ++kh) {
+      const int th = ih + w.pad - kh;
+      if (th < 0 || th % w.stride) continue;
+      const int oh = th / w.stride;
+      if (oh >= w.out_h) continue;
+      for (int kw = 0; kw < w.k; ++kw) {
+        const int tw = iw + w.pad - kw;
+        if (tw < 0 || tw % w.stride) continue;
+        const int ow = tw / w.stride;
+        if (ow >= w.out_w) continue;
+        const long long vout = ((long long)od * w.out_h + oh) * w.out_w + ow;
+        if (argmax[vout * w.C + c] == (int32_t)v) {
+          acc += to_float(dy[vout * ld_dy + c]);
+          if (dy2) acc += to_float(dy2[vout * ld_dy + c]);
+        }
+      }
+    }
+  }
+  from_float(acc, dx + v * ld_dx + c);
+}
+
+// ---- convolution weights: the parameter (c_out, c_in, k, k, k) <-> the GEMM operand (c_out, k^3 c_in), element
+// (co, j) with j in [0, ld) (pad columns zero) ---------------------------------------------------------------------
+template <class Tout>
+GN_HD void pack_weight_element(const float* w, long long c_in, long long k3, Tout* out, long long ld, long long idx) {
+  const long long co = idx / ld, j = idx - co * ld;
+  float val = 0.f;
+  if (j < k3 * c_in) {
+    const long long kidx = j / c_in, ci = j - kidx * c_in;
+    val = w[(co * c_in + ci) * k3 + kidx];
+  }
+  from_float(val, out + idx);
+}
+// the weight gradient back in the parameter's layout: element idx of dw (c_out, c_in, k^3)
+GN_HD void unpack_wgrad_element(const float* dw_mat, long long ld, long long c_in, long long k3, float* dw, long long idx) {
+  const long long kidx = idx % k3, ci = (idx / k3) % c_in, co = idx / (k3 * c_in);
+  dw[idx] = dw_mat[co * ld + kidx * c_in + ci];
+}
+
+// ---- batch normalisation (nn.BatchNorm3d, NeRAF_resnet3d.py:120 and the blocks) ------------------------------------
+// column sums over rows [r0, r1) stepping by `step`: fp32 inside a strip of <= 64 visited rows, fp64 across strips
+template <class T>
+GN_HD void column_sums_partial(const T* x, long long ld, long long c, long long r0, long long r1, long long step,
+                               double* s, double* ss) {
+  double S = 0.0, SS = 0.0;
+  long long r = r0;
+  while (r < r1) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 64 && r < r1; ++i, r += step) {
+      const float v = to_float(x[r * ld + c]);
+      a += v; b = fmaf(v, v, b);
+    }
+    S += (double)a; SS += (double)b;
+  }
+  *s = S; *ss = SS;
+}
+
+// One channel of the statistics: training -> batch mean / biased variance (what normalises, torch batch_norm) and the
+// running estimates updated with the UNBIASED variance and `momentum` (nn.BatchNorm3d default 0.1; momentum 0 leaves
+// them alone); evaluation -> the running estimates themselves.
+GN_HD void bn_finalize_channel(const double* sums, long long V, long long C, float eps, float momentum, int training,
+                               float* running_mean, float* running_var, float* mean, float* invstd, long long c) {
+  if (training) {
+    const double m = sums[c] / (double)V;
+    double var = sums[C + c] / (double)V - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    if (invstd) invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (momentum > 0.f && running_mean && running_var) {
+      const double unbiased = V > 1 ? var * (double)V / (double)(V - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean[c] = running_mean[c];
+    if (invstd) invstd[c] = 1.f / sqrtf(running_var[c] + eps);
+  }
+}
+
+// y = [relu]( gamma (x - mean) invstd + beta [+ residual] )  -- the tail of every conv unit (NeRAF_resnet3d.py:98-113)
+template <class T>
+GN_HD void bn_apply_element(const T* x, long long ld_x, long long C, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, const T* residual, long long ld_res, int relu, T* y,
+                            long long ld_y, long long idx) {
+  const long long r = idx / C, c = idx - r * C;
+  float v = (to_float(x[r * ld_x + c]) - mean[c]) * invstd[c] * gamma[c] + beta[c];
+  if (residual) v += to_float(residual[r * ld_res + c]);
+  if (relu && !(v > 0.f)) v = 0.f;
+  from_float(v, y + r * ld_y + c);
+}
+
+// Backward, first pass over rows [r0, r1) of column c: the gradient that reaches the normalisation is
+// g = (dy [+ dy2]) * [y > 0] (dy2: the second consumer of this unit's output -- the next block's shortcut; y: the
+// unit's output when it ends in a ReLU, else null).  g is stored (the shortcut branch of a residual unit receives
+// exactly g) and the two sums of the batch-norm gradient are formed: sum g, sum g xhat.
+template <class T>
+GN_HD void bn_backward_partial(const T* dy, const T* dy2, const T* y, const T* x, long long ld, const float* mean,
+                               const float* invstd, T* g_out, long long c, long long r0, long long r1, long long step,
+                               double* s_g, double* s_gx) {
+  const float m = mean[c], is = invstd[c];
+  double S = 0.0, SX = 0.0;
+  long long r = r0;
+  while (r < r1) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 64 && r < r1; ++i, r += step) {
+      float g = to_float(dy[r * ld + c]);
+      if (dy2) g += to_float(dy2[r * ld + c]);
+      if (y && !(to_float(y[r * ld + c]) > 0.f)) g = 0.f;
+      T stored;
+      from_float(g, &stored);
+      g_out[r * ld + c] = stored;
+      g = to_float(stored);                       // the sums see what the second pass will read
+      const float xh = (to_float(x[r * ld + c]) - m) * is;
+      a += g; b = fmaf(g, xh, b);
+    }
+    S += (double)a; SX += (double)b;
+  }
+  *s_g = S; *s_gx = SX;
+}
+
+// Second pass: dx = gamma invstd (g - (sum g + xhat sum g xhat) / V) with batch statistics, gamma invstd g with the
+// running ones (they are constants then).
+template <class T>
+GN_HD void bn_backward_element(const T* g, const T* x, long long ld, long long C, const float* mean, const float* invstd,
+                               const float* gamma, const double* sums, long long V, int training, T* dx, long long idx) {
+  const long long r = idx / C, c = idx - r * C;
+  float v = to_float(g[r * ld + c]);
+  if (training) {
+    const float xh = (to_float(x[r * ld + c]) - mean[c]) * invstd[c];
+    v -= (float)((sums[c] + (double)xh * sums[C + c]) / (double)V);
+  }
+  from_float(v * gamma[c] * invstd[c], dx + r * ld + c);
+}
+
+// out[r, c] = v[c] * scale: the gradient of the global average pooling (nn.AvgPool3d over the whole extent,
+// NeRAF_resnet3d.py:141-157) spread back over the voxels
+template <class T>
+GN_HD void broadcast_rows_element(const float* v, float scale, long long C, T* out, long long ld, long long idx) {
+  const long long r = idx / C, c = idx - r * C;
+  from_float(v[c] * scale, out + r * ld + c);
+}
+
+}  // namespace gridnet
+}  // namespace neraf

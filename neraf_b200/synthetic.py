@@ -109,3 +109,63 @@ def make_rirs(shape: Shape, n: int, seed: int = 0):
     re = torch.rand(n, shape.C, shape.F, shape.T, generator=g)
     im = torch.rand(n, shape.C, shape.F, shape.T, generator=g)
     return rir, mag, torch.complex(re, im)
+
+
+# ---- grid-feature producer (NeRAF_resnet3d.py) ----------------------------------------------------------------------
+RESNET_LAYERS = {"resnet18": ("basic", [2, 2, 2, 2]), "resnet34": ("basic", [3, 4, 6, 3]),
+                 "resnet50": ("bottleneck", [3, 4, 6, 3])}
+
+
+def make_grid(n: int, seed: int = 0, channels: int = 7) -> torch.Tensor:
+    """A (1, 7, n, n, n) fp32 grid shaped like NeRAF_model.py:269-277 after a few query_grid_one_batch calls: colour and
+    density in the first four channels of ~30 % of the voxels (zero elsewhere), voxel-centre coordinates in the last
+    three."""
+    g = torch.Generator().manual_seed(seed + 2000)
+    grid = torch.zeros(channels, n, n, n)
+    filled = (torch.rand(n, n, n, generator=g) < 0.3).float()
+    grid[:channels - 3] = torch.rand(channels - 3, n, n, n, generator=g) * filled
+    c = (torch.arange(n, dtype=torch.float32) + 0.5) / n
+    grid[channels - 3:] = torch.stack(torch.meshgrid(c, c, c, indexing="ij"), 0)
+    return grid[None]
+
+
+def make_gridnet_state_dict(backbone: str = "resnet50", in_channels: int = 7, N_features: int = 1024, seed: int = 0,
+                            prefix: str = "backbone_net.") -> Dict[str, torch.Tensor]:
+    """A state_dict in the reference's naming (NeRAF_resnet3d.py:116-176, 265-278): xavier-normal convolution weights
+    like the reference's init (:162-163); batch-norm scale / shift drawn around (1, 0) and non-trivial running
+    statistics so that every term of the normalisation is exercised."""
+    g = torch.Generator().manual_seed(seed + 3000)
+    kind, layers = RESNET_LAYERS[backbone]
+    expansion = 4 if kind == "bottleneck" else 1
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, c_in, c_out, k):
+        std = math.sqrt(2.0 / ((c_in + c_out) * k ** 3))
+        sd[prefix + name + ".weight"] = torch.randn(c_out, c_in, k, k, k, generator=g) * std
+
+    def bn(name, c):
+        sd[prefix + name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        sd[prefix + name + ".bias"] = 0.1 * torch.randn(c, generator=g)
+        sd[prefix + name + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+        sd[prefix + name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[prefix + name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    conv("conv1", in_channels, 64, 5)
+    bn("bn1", 64)
+    in_planes = 64
+    n_stages = 4 if N_features == 2048 else 3
+    for s in range(n_stages):
+        planes, stride = 64 * 2 ** s, (1 if s == 0 else 2)
+        for b in range(layers[s]):
+            p = f"layer{s + 1}.{b}."
+            if kind == "bottleneck":
+                conv(p + "conv1", in_planes, planes, 1); bn(p + "bn1", planes)
+                conv(p + "conv2", planes, planes, 3); bn(p + "bn2", planes)
+                conv(p + "conv3", planes, planes * 4, 1); bn(p + "bn3", planes * 4)
+            else:
+                conv(p + "conv1", in_planes, planes, 3); bn(p + "bn1", planes)
+                conv(p + "conv2", planes, planes, 3); bn(p + "bn2", planes)
+            if b == 0 and (stride != 1 or in_planes != planes * expansion):
+                conv(p + "downsample.0", in_planes, planes * expansion, 1); bn(p + "downsample.1", planes * expansion)
+            in_planes = planes * expansion
+    return sd

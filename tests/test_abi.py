@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     exported = sorted(set(re.findall(r" T (neraf_\w+)", out)))
     assert exported == names
     lib = _lib.lib()
-    assert lib.neraf_version() == 6
+    assert lib.neraf_version() == 7
 
 
 def test_library_is_sm100a_with_tcgen05_and_tma(built):

@@ -1,0 +1,335 @@
+"""Grid-feature producer, CPU tests.
+
+* the oracle (oracle/gridnet.py) against the golden vectors produced by the reference's real ResNet3D_helper;
+* the per-element code of the CUDA kernels (csrc/gridnet_core.h, built for the host) against torch's own operators,
+  on non-cubic extents so that an axis mix-up cannot hide;
+* neraf_b200/gridnet.py's assembly of the whole network, run on those host-built operators, against the oracle.
+
+Tolerances.  Evaluation mode (running statistics: every layer is well conditioned) -- fp32: feature 1e-6, every
+gradient tensor 1e-3 with a median of 1e-5 (a ReLU gate that flips in fp32 moves one tensor by ~1e-4); bf16: feature
+1e-2 (north_star's bf16 bound), gradients 5e-2 median.  Training mode normalises with statistics of the batch of ONE
+grid: the gradient through batch-norm + global average pooling is the small remainder of a cancellation, so torch's
+own fp32 gradient is already 1.5e-2 away from its float64 value on this problem and its bf16-autocast gradient is
+noise (measured in DESIGN.md section 9).  There the bound is relative to torch's own error at the same precision,
+computed in the test.
+"""
+import json
+import os
+import statistics
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from neraf_b200 import _lib, synthetic as syn
+from neraf_b200.gridnet import ResNet3D_helper, Window3d
+from oracle import gridnet as og
+from tests.util import rel_fro
+
+N, GRID_STEP = 64, 1 / 64
+
+
+@pytest.fixture(scope="module")
+def host_ops(built):
+    from tests.gridnet_host import HostOps
+    return HostOps()
+
+
+@pytest.fixture(scope="module")
+def problem():
+    sd = syn.make_gridnet_state_dict("resnet50")
+    x = syn.make_grid(N)
+    dout = torch.randn(1, 1024, 1, 1, 1, generator=torch.Generator().manual_seed(5))
+    return sd, x, dout
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "gridnet_resnet50.npz"))
+
+
+def _projection(t, name):
+    seed = sum((i + 1) * ord(ch) for i, ch in enumerate(name)) % (2 ** 31)
+    g = torch.Generator().manual_seed(seed)
+    return float((t.double() * torch.randn(t.shape, generator=g).double()).sum())
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs reference
+def test_oracle_matches_the_reference_golden(problem, golden):
+    sd, x, dout = problem
+    assert np.array_equal(golden["dout"], dout.reshape(-1).numpy())
+    stats = {}
+    with torch.no_grad():
+        f_train = og.forward(sd, x, GRID_STEP, 1024, True, new_stats=stats)
+    assert rel_fro(f_train.reshape(-1), golden["feature_train"]) < 1e-6
+    for k in golden.files:
+        if k.startswith("stats/"):
+            assert rel_fro(stats[k[6:]], golden[k]) < 1e-6, k
+    f_eval, grads, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=False, dtype=torch.float32)
+    assert rel_fro(f_eval.reshape(-1), golden["feature_eval"]) < 1e-6
+    norms = json.loads(str(golden["grad_eval_norms"]))
+    projs = json.loads(str(golden["grad_eval_projections"]))
+    assert set(norms) == set(grads)
+    for k, g in grads.items():
+        assert abs(float(g.double().norm()) - norms[k]) <= 1e-4 * norms[k], k
+        assert abs(_projection(g, k) - projs[k]) <= 1e-4 * norms[k], k
+    for k in golden.files:
+        if k.startswith("grad_eval/"):
+            assert rel_fro(grads[k[10:]], golden[k]) < 1e-5, k
+
+
+def test_state_dict_is_the_reference_checkpoint_contract(golden):
+    want = json.loads(str(golden["state_keys"]))
+    net = ResNet3D_helper(in_channels=7, backbone="resnet50", pretrained=False, grid_step=GRID_STEP, N_features=1024)
+    got = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert got == want
+    assert list(got) == list(want), "same order: optimizers index parameters by position"
+    assert net.backbone_net.avgpool_size == og.avgpool_window(GRID_STEP, 1024) == 4
+    for step, n_feat, size in ((1 / 128, 1024, 8), (1 / 128, 2048, 4), (1 / 256, 1024, 16), (None, 1024, 8)):
+        assert ResNet3D_helper(7, "resnet18", False, step, n_feat).backbone_net.avgpool_size == size
+
+
+# ------------------------------------------------------------------------------------------------ operators on the host
+def _act(t5):                      # (1, C, D, H, W) -> channels-last matrix (V, C)
+    c = t5.shape[1]
+    return t5[0].permute(1, 2, 3, 0).reshape(-1, c).contiguous()
+
+
+def _unact(m, dims):               # (V, C) -> (1, C, D, H, W)
+    return m.reshape(*dims, m.shape[1]).permute(3, 0, 1, 2)[None].contiguous()
+
+
+@pytest.mark.parametrize("dims,c_in,c_out,k,stride,pad,from_grid", [
+    ((9, 6, 7), 7, 16, 5, 2, 2, True),          # the stem, read from the channels-first grid
+    ((6, 5, 7), 8, 24, 3, 1, 1, False),
+    ((7, 6, 5), 16, 8, 3, 2, 1, False),
+    ((6, 4, 5), 8, 16, 1, 2, 0, False),         # the shortcut convolution
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_convolution_as_gather_and_gemm(host_ops, dims, c_in, c_out, k, stride, pad, from_grid, dtype):
+    g = torch.Generator().manual_seed(k * 100 + stride)
+    x = torch.randn(1, c_in, *dims, generator=g)
+    wt = torch.randn(c_out, c_in, k, k, k, generator=g) / np.sqrt(c_in * k ** 3)
+    if dtype == torch.bfloat16 and not from_grid:
+        x = x.bfloat16().float()
+    xr = x.double().requires_grad_(True)
+    wr = (wt.bfloat16().double() if dtype == torch.bfloat16 else wt.double()).requires_grad_(True)
+    y_ref = F.conv3d(xr, wr, stride=stride, padding=pad)
+    dy = torch.randn(y_ref.shape, generator=g)
+    if dtype == torch.bfloat16:
+        dy = dy.bfloat16().float()
+    y_ref.backward(dy.double())
+
+    w = Window3d(dims[0], dims[1], dims[2], c_in, k, stride, pad)
+    od = w.out_dims
+    assert tuple(y_ref.shape[2:]) == od
+    v_out, kc = od[0] * od[1] * od[2], k ** 3 * c_in
+    ld = (kc + 7) // 8 * 8
+    col = torch.full((v_out, ld), 9.0, dtype=dtype)
+    if from_grid:
+        host_ops.im2col(w, x.contiguous(), 1, dims[0] * dims[1] * dims[2], col)
+    else:
+        host_ops.im2col(w, _act(x).to(dtype), c_in, 1, col)
+    assert torch.all(col[:, kc:] == 0), "pad columns are zero-filled"
+    wmat = torch.full((c_out, ld), 9.0, dtype=dtype)
+    host_ops.pack_weight(wt, wmat)
+    assert torch.all(wmat[:, kc:] == 0)
+    y = torch.empty(v_out, c_out, dtype=torch.float32)
+    host_ops.gemm_nt(col, wmat, v_out, c_out, kc, y)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_fro(_unact(y, od), y_ref) < tol
+    # weight gradient: contraction over the voxels, then back to the parameter's layout
+    dym = _act(dy).to(dtype)
+    dw_mat = torch.zeros(c_out, ld)
+    host_ops.gemm_tn(dym, col, c_out, kc, v_out, dw_mat)
+    dw = torch.empty_like(wt)
+    host_ops.unpack_wgrad(dw_mat, dw)
+    assert rel_fro(dw, wr.grad) < tol
+    # data gradient: GEMM + gather
+    dcol = torch.zeros(v_out, ld, dtype=dtype)
+    host_ops.gemm_nn(dym, wmat, v_out, kc, c_out, dcol)
+    dx = torch.full((dims[0] * dims[1] * dims[2], c_in), 9.0, dtype=dtype)
+    host_ops.col2im(w, dcol, dx)
+    assert rel_fro(_unact(dx.float(), dims), xr.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool_with_ties_routes_gradients_like_torch(host_ops, dtype):
+    g = torch.Generator().manual_seed(3)
+    dims, c = (7, 6, 9), 8
+    x = torch.relu(torch.randn(1, c, *dims, generator=g))            # ~half the entries tie at zero, as after a ReLU
+    x = torch.round(x * 4) / 4                                       # and positive values tie too
+    xr = x.clone().requires_grad_(True)
+    y_ref = F.max_pool3d(xr, 3, 2, 1)
+    dy = torch.round(torch.randn(y_ref.shape, generator=g) * 8) / 8
+    dy2 = torch.round(torch.randn(y_ref.shape, generator=g) * 8) / 8
+    y_ref.backward(dy + dy2)
+    w = Window3d(dims[0], dims[1], dims[2], c, 3, 2, 1)
+    od = w.out_dims
+    v_out = od[0] * od[1] * od[2]
+    y = torch.empty(v_out, c, dtype=dtype)
+    arg = torch.empty(v_out, c, dtype=torch.int32)
+    host_ops.maxpool(w, _act(x).to(dtype), y, arg)
+    assert torch.equal(_unact(y.float(), od), y_ref.detach())
+    dx = torch.empty(dims[0] * dims[1] * dims[2], c, dtype=dtype)
+    host_ops.maxpool_backward(w, _act(dy).to(dtype), _act(dy2).to(dtype), arg, dx)
+    assert torch.equal(_unact(dx.float(), dims), xr.grad)
+    host_ops.maxpool_backward(w, _act(dy).to(dtype), None, arg, dx)
+    xr.grad = None
+    F.max_pool3d(xr, 3, 2, 1).backward(dy)
+    assert torch.equal(_unact(dx.float(), dims), xr.grad)
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("relu,with_res", [(True, True), (True, False), (False, False)])
+def test_batchnorm_unit_forward_and_backward(host_ops, training, relu, with_res):
+    g = torch.Generator().manual_seed(11)
+    V, c = 333, 24
+    x = torch.randn(V, c, generator=g) * 2 + 0.5
+    res = torch.randn(V, c, generator=g) if with_res else None
+    gamma, beta = 1 + 0.2 * torch.randn(c, generator=g), 0.2 * torch.randn(c, generator=g)
+    rm, rv = 0.1 * torch.randn(c, generator=g), 0.5 + torch.rand(c, generator=g)
+    dy, dy2 = torch.randn(V, c, generator=g), torch.randn(V, c, generator=g)
+    # torch, float64
+    xr, gr, br = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    y_ref = F.batch_norm(xr.t()[None], rm_ref, rv_ref, gr, br, training, 0.1, 1e-5)[0].t()
+    if with_res:
+        resr = res.double().requires_grad_(True)
+        y_ref = y_ref + resr
+    if relu:
+        y_ref = F.relu(y_ref)
+    y_ref.backward((dy + dy2).double())
+    # host operators
+    sums = torch.empty(2, c, dtype=torch.float64)
+    mean, invstd = torch.empty(c), torch.empty(c)
+    rm_h, rv_h = rm.clone(), rv.clone()
+    if training:
+        host_ops.bn_stats(x, sums)
+        assert rel_fro(sums[0], x.double().sum(0)) < 1e-6 and rel_fro(sums[1], (x.double() ** 2).sum(0)) < 1e-6
+    host_ops.bn_finalize(sums if training else None, V, c, 1e-5, 0.1 if training else 0.0, training, rm_h, rv_h, mean, invstd)
+    assert rel_fro(rm_h, rm_ref) < 1e-6 and rel_fro(rv_h, rv_ref) < 1e-6
+    y = torch.empty(V, c)
+    host_ops.bn_apply(x, mean, invstd, gamma, beta, res, relu, y)
+    assert rel_fro(y, y_ref) < 1e-6
+    gbuf, dx = torch.empty(V, c), torch.empty(V, c)
+    dgamma, dbeta = torch.empty(c), torch.empty(c)
+    host_ops.bn_backward_reduce(dy, dy2, y if relu else None, x, mean, invstd, gbuf, sums)
+    host_ops.bn_backward_apply(gbuf, x, mean, invstd, gamma, sums, training, dx, dgamma, dbeta)
+    assert rel_fro(dx, xr.grad) < 1e-5
+    assert rel_fro(dgamma, gr.grad) < 1e-5 and rel_fro(dbeta, br.grad) < 1e-5
+    if with_res:
+        assert rel_fro(gbuf, resr.grad) < 1e-6          # the shortcut receives exactly g
+    # in-place form (dx aliases g), as the assembly uses it for units without a shortcut
+    host_ops.bn_backward_apply(gbuf, x, mean, invstd, gamma, sums, training, gbuf, None, None)
+    assert torch.equal(gbuf, dx)
+
+
+def test_global_average_pool_and_its_gradient(host_ops):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(64, 40, generator=g).bfloat16()
+    sums, feat = torch.empty(2, 40, dtype=torch.float64), torch.empty(40)
+    host_ops.bn_stats(x, sums)
+    host_ops.bn_finalize(sums, 64, 40, 0.0, 0.0, True, None, None, feat, None)
+    assert rel_fro(feat, x.double().mean(0)) < 1e-6
+    d = torch.empty(64, 40, dtype=torch.bfloat16)
+    v = torch.randn(40, generator=g)
+    host_ops.broadcast_rows(v, 1 / 64, d)
+    assert torch.equal(d, (v / 64).bfloat16()[None].expand(64, 40))
+
+
+# ------------------------------------------------------------------------------------------------ the whole network
+def _run(host_ops, sd, x, dout, precision, training, backbone="resnet50", n_features=1024, grid_step=GRID_STEP):
+    net = ResNet3D_helper(in_channels=7, backbone=backbone, grid_step=grid_step, N_features=n_features, precision=precision)
+    net.load_state_dict(sd, strict=True)
+    net.backbone_net.ops = host_ops
+    net.train(training)
+    out = net(x)
+    out.backward(dout)
+    return net, out.detach()
+
+
+def test_network_eval_mode_fp32_matches_oracle_and_golden(host_ops, problem, golden):
+    sd, x, dout = problem
+    ref, grads, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=False)
+    net, out = _run(host_ops, sd, x, dout, "fp32", False)
+    assert out.shape == (1, 1024, 1, 1, 1) and out.dtype == torch.float32
+    assert rel_fro(out, ref) < 1e-6
+    assert rel_fro(out.reshape(-1), golden["feature_eval"]) < 1e-6
+    errs = {k: rel_fro(p.grad, grads[k]) for k, p in net.named_parameters()}
+    assert max(errs.values()) < 1e-3, max(errs.items(), key=lambda kv: kv[1])
+    assert statistics.median(errs.values()) < 1e-5
+    for k in golden.files:
+        if k.startswith("grad_eval/"):
+            assert rel_fro(dict(net.named_parameters())[k[10:]].grad, golden[k]) < 1e-3, k
+    after = net.state_dict()
+    assert all(torch.equal(after[k], sd[k]) for k in sd), "evaluation mode leaves the running statistics alone"
+
+
+def test_network_training_mode_fp32(host_ops, problem, golden):
+    sd, x, dout = problem
+    ref, grads, stats = og.forward_backward(sd, x, dout, GRID_STEP, training=True)
+    _, grads32, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=True, dtype=torch.float32)
+    net, out = _run(host_ops, sd, x, dout, "fp32", True)
+    assert rel_fro(out, ref) < 2e-5
+    assert rel_fro(out.reshape(-1), golden["feature_train"]) < 2e-5
+    after = net.state_dict()
+    for k, v in stats.items():
+        assert rel_fro(after[k], v) < 1e-5, k
+    for k in golden.files:
+        if k.startswith("stats/"):
+            assert rel_fro(after[k[6:]], golden[k]) < 1e-5, k
+    assert int(after["backbone_net.layer3.5.bn3.num_batches_tracked"]) == int(golden["num_batches_tracked"]) == 1
+    ours = statistics.median(rel_fro(p.grad, grads[k]) for k, p in net.named_parameters())
+    torch32 = statistics.median(rel_fro(grads32[k], grads[k]) for k in grads)
+    assert torch32 > 1e-3, "the premise of this bound: torch's own fp32 gradient is far from float64 here"
+    assert ours < 3 * torch32
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_network_bf16(host_ops, problem, training):
+    sd, x, dout = problem
+    ref, grads, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=training)
+    net, out = _run(host_ops, sd, x, dout, "bf16", training)
+    err = rel_fro(out, ref)
+    if not training:
+        assert err < 1e-2
+        assert statistics.median(rel_fro(p.grad, grads[k]) for k, p in net.named_parameters()) < 5e-2
+    else:
+        assert err < 5e-2          # torch's own bf16 autocast: 2.3e-2 on this problem
+    assert all(p.grad is not None and p.grad.dtype == torch.float32 and torch.isfinite(p.grad).all()
+               for p in net.parameters())
+
+
+def test_basic_block_backbone_and_2048_features(host_ops):
+    sd = syn.make_gridnet_state_dict("resnet18", N_features=2048, seed=4)
+    x = syn.make_grid(64, seed=1)                # 64 -> 32 -> 16 -> 16 -> 8 -> 4 -> 2, pooling window 2
+    dout = torch.randn(1, 512, 1, 1, 1, generator=torch.Generator().manual_seed(6))
+    ref, grads, _ = og.forward_backward(sd, x, dout, GRID_STEP, n_features=2048, training=False)
+    net, out = _run(host_ops, sd, x, dout, "fp32", False, backbone="resnet18", n_features=2048)
+    assert out.shape == ref.shape == (1, 512, 1, 1, 1)
+    assert rel_fro(out, ref) < 1e-6
+    errs = [rel_fro(p.grad, grads[k]) for k, p in net.named_parameters()]
+    assert max(errs) < 1e-3 and statistics.median(errs) < 1e-5
+
+
+def test_calling_conventions_and_errors(host_ops, problem):
+    sd, x, dout = problem
+    net = ResNet3D_helper(in_channels=7, backbone="resnet50", grid_step=GRID_STEP, N_features=1024)
+    net.load_state_dict(sd)
+    with pytest.raises(_lib.NerafError):                     # the product path has no CPU implementation
+        net(x)
+    net.backbone_net.ops = host_ops
+    with pytest.raises(ValueError):
+        net(x[0])
+    with pytest.raises(ValueError):
+        net(x[:, :5])
+    with pytest.raises(_lib.NerafError):                     # 32^3 leaves 2^3 voxels, the pooling window is 4^3
+        net(syn.make_grid(32))
+    with pytest.raises(ValueError):
+        ResNet3D_helper(precision="fp16")
+    net.eval()
+    with torch.no_grad():
+        f = net(x)
+    assert not f.requires_grad and f.shape == (1, 1024, 1, 1, 1)
