@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--gl-rirs", type=int, default=2072, help="RIRs per Griffin-Lim launch (0 disables); 2072 = 14 per SM")
     ap.add_argument("--large-batch", type=int, default=16384, help="extra large-batch point of the sweep (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid-net", type=int, default=0,
+                    help="also time the grid-feature producer (ResNet3D-50 fwd+bwd, SURVEY 8f row 1) on an N^3 grid, e.g. 128; "
+                         "off by default: its launch code has not run on a B200 yet (DESIGN.md section 9)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
     ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"],
                     help="dtype of the gradient all-reduce for N > 1 (default: bf16 with --precision bf16, else fp32)")
@@ -497,6 +500,39 @@ def main():
                                     "api": "neraf_b200.metrics.acoustic_metrics(device waveforms) -> T60, EDT, C50 on the host",
                                     "d2h_bytes_per_call": sum(v.numel() * 8 for v in host_m.values())}
         del wd
+
+    # ---- grid-feature producer (opt-in): one training-mode forward + backward of ResNet3D-50 on a (1, 7, N, N, N) grid
+    if args.grid_net > 0:
+        try:
+            from neraf_b200.gridnet import ResNet3D_helper, conv_flops
+            n_g = args.grid_net
+            net = ResNet3D_helper(in_channels=7, backbone="resnet50", grid_step=1.0 / n_g, N_features=1024,
+                                  precision=args.precision)
+            net.load_state_dict(syn.make_gridnet_state_dict("resnet50"))
+            net = net.to(dev).train()
+            grid = syn.make_grid(n_g).to(dev)
+            dfeat = torch.randn(1, 1024, 1, 1, 1, device=dev)
+            for _ in range(2):
+                net(grid).backward(dfeat)
+            barrier()
+            l0 = lib.neraf_launch_count()
+            k_gn = 5
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(k_gn):
+                net(grid).backward(dfeat)
+            e.record()
+            barrier()
+            gn_ms = max_over_ranks(s.elapsed_time(e)) / k_gn
+            fl = conv_flops(net.backbone_net, n_g)
+            line["grid_feature"] = {"metric": "grid_net_steps_per_sec", "value": world / (gn_ms * 1e-3), "unit": "step/s",
+                                    "grid": [1, 7, n_g, n_g, n_g], "ms_per_step": gn_ms,
+                                    "gflop_per_step": fl / 1e9, "achieved_tflops": fl / (gn_ms * 1e-3) / 1e12,
+                                    "launches_per_step": (lib.neraf_launch_count() - l0) // k_gn,
+                                    "api": "gridnet.ResNet3D_helper(grid).backward(): training-mode batch norm, all parameter gradients"}
+            del net, grid
+        except Exception as exc:                                   # noqa: BLE001 -- an opt-in extra must not lose the line
+            line["grid_feature"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.gl_rirs > 0:

@@ -34,6 +34,14 @@ __global__ void __launch_bounds__(kThreads) col2im_kernel(Window w, const T* dco
                                                           long long n) {
   GN_LOOP(n) col2im_element(w, dcol, ld_col, dx, ld_dx, idx);
 }
+__global__ void __launch_bounds__(kThreads) im2col_vec8_kernel(Window w, const bf16_t* in, long long vs, bf16_t* col,
+                                                               long long ld, long long n) {
+  GN_LOOP(n) im2col_vec8_element(w, in, vs, col, ld, idx);
+}
+__global__ void __launch_bounds__(kThreads) col2im_vec8_kernel(Window w, const bf16_t* dcol, long long ld_col, bf16_t* dx,
+                                                               long long ld_dx, long long n) {
+  GN_LOOP(n) col2im_vec8_element(w, dcol, ld_col, dx, ld_dx, idx);
+}
 template <class T>
 __global__ void __launch_bounds__(kThreads) maxpool_kernel(Window w, const T* x, long long ld_x, T* y, long long ld_y,
                                                            int32_t* argmax, long long n) {
@@ -178,6 +186,12 @@ extern "C" int neraf_grid_im2col(const neraf_window3d* wd, const void* in, int32
   NERAF_REQUIRE(voxel_stride >= 1 && channel_stride >= 1, "im2col: bad input strides");
   const long long n = out_voxels(w) * ld_col;
   cudaStream_t s = (cudaStream_t)stream;
+  if (gather_can_vec8(w, in_dtype == NERAF_DT_BF16 && col_dtype == NERAF_DT_BF16, voxel_stride, channel_stride, ld_col, in,
+                      col)) {
+    im2col_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>(w, (const bf16_t*)in, voxel_stride, (bf16_t*)col, ld_col, n / 8);
+    NERAF_CHECK_LAUNCH("im2col_vec8_kernel");
+    return NERAF_OK;
+  }
   const unsigned g = grid_for(n);
   if (in_dtype == NERAF_DT_F32 && col_dtype == NERAF_DT_F32)
     im2col_kernel<<<g, kThreads, 0, s>>>(w, (const float*)in, voxel_stride, channel_stride, (float*)col, ld_col, n);
@@ -200,6 +214,11 @@ extern "C" int neraf_grid_col2im(const neraf_window3d* wd, const void* dcol, int
   NERAF_REQUIRE(ld_col >= (int64_t)w.k * w.k * w.k * w.C && ld_dx >= w.C, "col2im: row stride too small");
   const long long n = in_voxels(w) * w.C;
   cudaStream_t s = (cudaStream_t)stream;
+  if (gather_can_vec8(w, dtype == NERAF_DT_BF16, ld_dx, 1, ld_col, dcol, dx)) {
+    col2im_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>(w, (const bf16_t*)dcol, ld_col, (bf16_t*)dx, ld_dx, n / 8);
+    NERAF_CHECK_LAUNCH("col2im_vec8_kernel");
+    return NERAF_OK;
+  }
   if (dtype == NERAF_DT_F32)
     col2im_kernel<<<grid_for(n), kThreads, 0, s>>>(w, (const float*)dcol, ld_col, (float*)dx, ld_dx, n);
   else

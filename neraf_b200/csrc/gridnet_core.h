@@ -124,6 +124,84 @@ GN_HD void col2im_element(const Window& w, const T* dcol, long long ld_col, T* d
   from_float(acc, dx + v * ld_dx + c);
 }
 
+// ---- 16-byte forms of the two gathers for bf16 activations whose channel count is a multiple of 8: eight channels of
+// one voxel move as one 128-bit word (the scalar forms issue 2-byte accesses; these are the HBM-bound passes that move
+// the most bytes: 0.46 GB for the stem's gathered matrix of a 128^3 grid) -------------------------------------------
+struct alignas(16) vec8_t { uint32_t w[4]; };
+
+GN_HD bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// usable when input and output are bf16, rows are whole 16-byte words and the channels are contiguous
+GN_HD bool gather_can_vec8(const Window& w, bool all_bf16, long long in_row_stride, long long channel_stride,
+                           long long ld_col, const void* a, const void* b) {
+  return all_bf16 && channel_stride == 1 && w.C % 8 == 0 && in_row_stride % 8 == 0 && ld_col % 8 == 0 && aligned16(a) &&
+         aligned16(b);
+}
+
+// unit idx = (v_out, j8): columns [8 j8, 8 j8 + 8) of row v_out
+GN_HD void im2col_vec8_element(const Window& w, const bf16_t* in, long long voxel_stride, bf16_t* col, long long ld,
+                               long long idx) {
+  const long long ld8 = ld / 8;
+  const long long v = idx / ld8;
+  const int j = (int)(idx - v * ld8) * 8;
+  vec8_t val = {{0u, 0u, 0u, 0u}};
+  const int K = w.k * w.k * w.k * w.C;
+  if (j < K) {
+    const int kidx = j / w.C, c = j - kidx * w.C;
+    const int kw = kidx % w.k, kh = (kidx / w.k) % w.k, kd = kidx / (w.k * w.k);
+    const int ow = (int)(v % w.out_w), oh = (int)((v / w.out_w) % w.out_h), od = (int)(v / ((long long)w.out_w * w.out_h));
+    const int id = od * w.stride - w.pad + kd, ih = oh * w.stride - w.pad + kh, iw = ow * w.stride - w.pad + kw;
+    if (id >= 0 && id < w.in_d && ih >= 0 && ih < w.in_h && iw >= 0 && iw < w.in_w) {
+      const long long vin = ((long long)id * w.in_h + ih) * w.in_w + iw;
+      val = *reinterpret_cast<const vec8_t*>(in + vin * voxel_stride + c);
+    }
+  }
+  *reinterpret_cast<vec8_t*>(col + v * ld + j) = val;
+}
+
+// unit idx = (v_in, c8): channels [8 c8, 8 c8 + 8) of input voxel v_in; same summation order as col2im_element
+GN_HD void col2im_vec8_element(const Window& w, const bf16_t* dcol, long long ld_col, bf16_t* dx, long long ld_dx,
+                               long long idx) {
+  const int C8 = w.C / 8;
+  const long long v = idx / C8;
+  const int c = (int)(idx - v * C8) * 8;
+  const int iw = (int)(v % w.in_w), ih = (int)((v / w.in_w) % w.in_h), id = (int)(v / ((long long)w.in_w * w.in_h));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int kd = 0; kd < w.k; ++kd) {
+    const int td = id + w.pad - kd;
+    if (td < 0 || td % w.stride) continue;
+    const int od = td / w.stride;
+    if (od >= w.out_d) continue;
+    for (int kh = 0; kh < w.k; ++kh) {
+      const int th = ih + w.pad - kh;
+      if (th < 0 || th % w.stride) continue;
+      const int oh = th / w.stride;
+      if (oh >= w.out_h) continue;
+      for (int kw = 0; kw < w.k; ++kw) {
+        const int tw = iw + w.pad - kw;
+        if (tw < 0 || tw % w.stride) continue;
+        const int ow = tw / w.stride;
+        if (ow >= w.out_w) continue;
+        const long long vout = ((long long)od * w.out_h + oh) * w.out_w + ow;
+        const int kidx = (kd * w.k + kh) * w.k + kw;
+        const vec8_t q = *reinterpret_cast<const vec8_t*>(dcol + vout * ld_col + (long long)kidx * w.C + c);
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += bits_to_float(q.w[i] << 16);
+          acc[2 * i + 1] += bits_to_float(q.w[i] & 0xffff0000u);
+        }
+      }
+    }
+  }
+  vec8_t out;
+  for (int i = 0; i < 4; ++i) {
+    bf16_t lo, hi;
+    from_float(acc[2 * i], &lo);
+    from_float(acc[2 * i + 1], &hi);
+    out.w[i] = (uint32_t)lo.bits | ((uint32_t)hi.bits << 16);
+  }
+  *reinterpret_cast<vec8_t*>(dx + v * ld_dx + c) = out;
+}
+
 // ---- max pooling (nn.MaxPool3d(3, 2, 1), NeRAF_resnet3d.py:122): first maximum in (d, h, w) scan order, like
 // torch's CPU kernel (max_pool3d_with_indices: `val > maxval`), so that gradients of tied maxima -- frequent after a
 // ReLU -- take the same route as in the reference.  argmax holds the input voxel index.

@@ -493,6 +493,27 @@ class ResNet3D(nn.Module):
         return run.grads
 
 
+def conv_flops(net: ResNet3D, n: int) -> float:
+    """Algorithmic FLOPs of one training step (forward + data gradient + weight gradient of every convolution; the stem
+    has no data gradient) on an n^3 grid -- the contraction work, 2 FLOP per multiply-add."""
+    def out(e, conv):
+        return (e + 2 * conv.pad - conv.k) // conv.stride + 1
+
+    e = out(n, net.conv1)
+    total = 2.0 * e ** 3 * net.conv1.k ** 3 * net.conv1.c_in * net.conv1.c_out * 2           # forward + wgrad
+    e = (e + 2 - 3) // 2 + 1                                                                  # max pooling
+    for stage in net._stages():
+        for block in stage:
+            e_in = e
+            for conv, _ in block.units():
+                e = out(e, conv)
+                total += 2.0 * e ** 3 * conv.k ** 3 * conv.c_in * conv.c_out * 3
+            if block.downsample is not None:
+                ds = block.downsample[0]
+                total += 2.0 * out(e_in, ds) ** 3 * ds.c_in * ds.c_out * 3
+    return total
+
+
 # NeRAF_resnet3d.py:204-262
 def resnet18(in_channels=3, pretrained=False, grid_step=None, N_features=None, **kwargs):
     return ResNet3D(in_channels, BasicBlock, [2, 2, 2, 2], grid_step=grid_step, N_features=N_features, **kwargs)

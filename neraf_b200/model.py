@@ -8,9 +8,10 @@
 ``max_len``, ``mic_ch`` -- with every tensor operation of the hot path executed by the CUDA library.
 
 nerfstudio is not a dependency: the class derives from ``nn.Module``; INTEGRATION.md shows the
-three-line subclass that plugs it into a real nerfstudio ``Model``.  The scene-grid feature producer
-(ResNet3D, NeRAF_resnet3d.py) is out of scope: any ``nn.Module`` mapping the grid
-to the flat feature vector can be passed as ``resnet3d``.
+three-line subclass that plugs it into a real nerfstudio ``Model``.  The scene-grid feature producer is either the
+reference's ResNet3D-50 on the library (``config.grid_net = "resnet50"`` builds ``gridnet.ResNet3D_helper`` exactly
+as NeRAF_model.py:185 does), a learnable constant vector (``"constant"``, the default until the producer's launch code
+has run on a B200 -- DESIGN.md section 9), or any ``nn.Module`` passed as ``resnet3d``.
 """
 from __future__ import annotations
 
@@ -44,6 +45,7 @@ class NeRAFAudioModelConfig:
     hop_len: int = 128
     win_len: int = 512
     precision: str = "bf16"          # "bf16": tcgen05 tensor cores; "fp32": CUDA-core parity path
+    grid_net: str = "constant"       # "resnet50": the reference's ResNet3D_helper (gridnet.py); "constant": a vector
 
 
 class ConstantGridFeature(nn.Module):
@@ -84,7 +86,17 @@ class NeRAFAudioModel(nn.Module):
         self.process_group = process_group               # DP: global spectral-convergence sums
         n_grid = config.N_features if self.use_grid else 0
         if self.use_grid:
-            self.resnet3d = resnet3d if resnet3d is not None else ConstantGridFeature(config.N_features)
+            if resnet3d is not None:
+                self.resnet3d = resnet3d
+            elif config.grid_net == "constant":
+                self.resnet3d = ConstantGridFeature(config.N_features)
+            elif config.grid_net == "resnet50":          # NeRAF_model.py:185
+                from .gridnet import ResNet3D_helper
+                self.resnet3d = ResNet3D_helper(in_channels=7, backbone="resnet50", pretrained=False,
+                                                grid_step=config.grid_step, N_features=config.N_features,
+                                                precision=config.precision)
+            else:
+                raise ValueError(f"unknown grid_net {config.grid_net!r}")
             self.grid = grid                             # plain attribute like the reference (NeRAF_pipeline.py:451-455)
         self.field = NeRAFAudioSoundField(n_grid + N_ENC, config.W_field, sound_rez=self.mic_ch,
                                           N_frequencies=config.N_freq_stft, precision=config.precision)

@@ -24,6 +24,10 @@ HOST_API int gridhost_im2col(const neraf_window3d* wd, const void* in, int32_t i
                              int32_t col_dtype, int64_t ld, void*) {
   const Window w = window_of(wd);
   const long long n = out_voxels(w) * ld;
+  if (gather_can_vec8(w, in_dtype == NERAF_DT_BF16 && col_dtype == NERAF_DT_BF16, vs, cs, ld, in, col)) {   // as gridnet.cu
+    for (long long i = 0; i < n / 8; ++i) im2col_vec8_element(w, (const bf16_t*)in, vs, (bf16_t*)col, ld, i);
+    return 0;
+  }
   for (long long i = 0; i < n; ++i) {
     if (in_dtype == NERAF_DT_F32 && col_dtype == NERAF_DT_F32) im2col_element(w, (const float*)in, vs, cs, (float*)col, ld, i);
     else if (in_dtype == NERAF_DT_F32) im2col_element(w, (const float*)in, vs, cs, (bf16_t*)col, ld, i);
@@ -37,6 +41,10 @@ HOST_API int gridhost_col2im(const neraf_window3d* wd, const void* dcol, int32_t
                              int64_t ld_dx, void*) {
   const Window w = window_of(wd);
   const long long n = in_voxels(w) * w.C;
+  if (gather_can_vec8(w, dtype == NERAF_DT_BF16, ld_dx, 1, ld_col, dcol, dx)) {                               // as gridnet.cu
+    for (long long i = 0; i < n / 8; ++i) col2im_vec8_element(w, (const bf16_t*)dcol, ld_col, (bf16_t*)dx, ld_dx, i);
+    return 0;
+  }
   for (long long i = 0; i < n; ++i) {
     if (dtype == NERAF_DT_F32) col2im_element(w, (const float*)dcol, ld_col, (float*)dx, ld_dx, i);
     else col2im_element(w, (const bf16_t*)dcol, ld_col, (bf16_t*)dx, ld_dx, i);

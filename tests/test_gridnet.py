@@ -333,3 +333,48 @@ def test_calling_conventions_and_errors(host_ops, problem):
     with torch.no_grad():
         f = net(x)
     assert not f.requires_grad and f.shape == (1, 1024, 1, 1, 1)
+
+
+def test_model_builds_the_reference_grid_net(host_ops):
+    """NeRAF_model.py:185,554-557: the model owns a ResNet3D_helper and feeds it grid[None]; its parameters join the
+    "audio_fields" group (:734)."""
+    from neraf_b200.model import NeRAFAudioModel, NeRAFAudioModelConfig
+    cfg = NeRAFAudioModelConfig(dataset="RAF", grid_step=GRID_STEP, grid_net="resnet50", precision="fp32")
+    model = NeRAFAudioModel(cfg, syn.default_aabb(), grid=syn.make_grid(N)[0])
+    assert isinstance(model.resnet3d, ResNet3D_helper) and model.resnet3d.backbone_net.precision == "fp32"
+    sd = syn.make_gridnet_state_dict("resnet50")
+    model.resnet3d.load_state_dict(sd)
+    model.resnet3d.backbone_net.ops = host_ops
+    model.resnet3d.eval()
+    feat = model.grid_feature()
+    with torch.no_grad():
+        ref = og.forward({k: v.double() if v.dtype.is_floating_point else v for k, v in sd.items()},
+                         syn.make_grid(N).double(), GRID_STEP, training=False)
+    assert feat.shape == (1024,) and rel_fro(feat, ref.reshape(-1)) < 1e-6
+    group = model.get_param_groups()["audio_fields"]
+    assert all(any(p is q for q in group) for p in model.resnet3d.parameters())
+    with pytest.raises(ValueError):
+        NeRAFAudioModel(NeRAFAudioModelConfig(grid_net="vgg"), syn.default_aabb())
+
+
+def test_16_byte_gathers_equal_the_scalar_forms(host_ops):
+    """bf16 activations with a multiple of 8 channels take the 128-bit kernels (gather_can_vec8); a buffer that starts
+    2 bytes off a 16-byte boundary forces the scalar kernels.  Same bits either way."""
+    g = torch.Generator().manual_seed(9)
+    dims, c = (6, 5, 7), 16
+    w = Window3d(dims[0], dims[1], dims[2], c, 3, 2, 1)
+    od = w.out_dims
+    v_in, v_out, kc = dims[0] * dims[1] * dims[2], od[0] * od[1] * od[2], 27 * c
+    x = torch.randn(v_in, c, generator=g).bfloat16()
+    col_v = torch.empty(v_out, kc, dtype=torch.bfloat16)
+    host_ops.im2col(w, x, c, 1, col_v)
+    off = torch.empty(v_out * kc + 1, dtype=torch.bfloat16)[1:].view(v_out, kc)
+    assert off.data_ptr() % 16 != 0 and col_v.data_ptr() % 16 == 0
+    host_ops.im2col(w, x, c, 1, off)
+    assert torch.equal(off, col_v)
+    dcol = torch.randn(v_out, kc, generator=g).bfloat16()
+    dx_v = torch.empty(v_in, c, dtype=torch.bfloat16)
+    host_ops.col2im(w, dcol, dx_v)
+    dx_s = torch.empty(v_in * c + 1, dtype=torch.bfloat16)[1:].view(v_in, c)
+    host_ops.col2im(w, dcol, dx_s)
+    assert torch.equal(dx_s, dx_v)
