@@ -181,9 +181,9 @@ def main():
     ap.add_argument("--gl-rirs", type=int, default=2072, help="RIRs per Griffin-Lim launch (0 disables); 2072 = 14 per SM")
     ap.add_argument("--large-batch", type=int, default=16384, help="extra large-batch point of the sweep (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grid-net", type=int, default=0,
-                    help="also time the grid-feature producer (ResNet3D-50 fwd+bwd, SURVEY 8f row 1) on an N^3 grid, e.g. 128; "
-                         "off by default: its launch code has not run on a B200 yet (DESIGN.md section 9)")
+    ap.add_argument("--grid-net", type=int, default=128,
+                    help="also time the grid-feature producer (ResNet3D-50 training-mode fwd+bwd, SURVEY 8f row 1) on an "
+                         "N^3 grid (the reference's grid is 128^3); 0 disables")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
     ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"],
                     help="dtype of the gradient all-reduce for N > 1 (default: bf16 with --precision bf16, else fp32)")
@@ -501,7 +501,7 @@ def main():
                                     "d2h_bytes_per_call": sum(v.numel() * 8 for v in host_m.values())}
         del wd
 
-    # ---- grid-feature producer (opt-in): one training-mode forward + backward of ResNet3D-50 on a (1, 7, N, N, N) grid
+    # ---- grid-feature producer: one training-mode forward + backward of ResNet3D-50 on a (1, 7, N, N, N) grid
     if args.grid_net > 0:
         try:
             from neraf_b200.gridnet import ResNet3D_helper, conv_flops
@@ -531,7 +531,7 @@ def main():
                                     "launches_per_step": (lib.neraf_launch_count() - l0) // k_gn,
                                     "api": "gridnet.ResNet3D_helper(grid).backward(): training-mode batch norm, all parameter gradients"}
             del net, grid
-        except Exception as exc:                                   # noqa: BLE001 -- an opt-in extra must not lose the line
+        except Exception as exc:                                   # noqa: BLE001 -- an extra row must not lose the line
             line["grid_feature"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -552,6 +552,17 @@ def main():
                           "measure_edt / measure_clarity (numpy, one RIR at a time like the reference)"}
         res = time_cpu_baseline(shape, B, steps=10, warmup=2)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if args.grid_net > 0 and "error" not in line.get("grid_feature", {"error": 1}):
+            from oracle import gridnet as ogn
+            n_c = min(64, args.grid_net)               # bounded sample: a 64^3 grid is 1/8 of the 128^3 work
+            sd_c, x_c = syn.make_gridnet_state_dict("resnet50"), syn.make_grid(n_c)
+            t0 = time.perf_counter()
+            ogn.forward_backward(sd_c, x_c, torch.ones(1, 1024, 1, 1, 1), 1.0 / n_c, dtype=torch.float32)
+            dt = time.perf_counter() - t0
+            line["grid_feature"]["cpu_baseline"] = {
+                "value": 1.0 / dt, "unit": "step/s", "cores": os.cpu_count() or 1, "kind": "port", "grid": [1, 7, n_c, n_c, n_c],
+                "sample": f"one training-mode fwd+bwd of the oracle (torch {torch.__version__} CPU fp32 conv3d / batch_norm) on a "
+                          f"{n_c}^3 grid -- {(args.grid_net / n_c) ** 3:.0f}x fewer voxels than the GPU figure's grid"}
         if args.gl_rirs > 0:
             from oracle import griffinlim as ogl
             n_cpu = 16

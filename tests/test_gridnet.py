@@ -6,7 +6,8 @@
 * neraf_b200/gridnet.py's assembly of the whole network, run on those host-built operators, against the oracle.
 
 Tolerances.  Evaluation mode (running statistics: every layer is well conditioned) -- fp32: feature 1e-6, every
-gradient tensor 1e-3 with a median of 1e-5 (a ReLU gate that flips in fp32 moves one tensor by ~1e-4); bf16: feature
+gradient tensor 5e-3 with a median of 1e-5 (ONE ReLU gate that flips between fp32 and the float64 oracle in a
+512-voxel unit moves every tensor behind it by ~1e-3: seen on the B200, profiles/r01f_gridnet_gpu_tests.txt); bf16: feature
 1e-2 (north_star's bf16 bound), gradients 5e-2 median.  Training mode normalises with statistics of the batch of ONE
 grid: the gradient through batch-norm + global average pooling is the small remainder of a cancellation, so torch's
 own fp32 gradient is already 1.5e-2 away from its float64 value on this problem and its bf16-autocast gradient is
@@ -258,11 +259,11 @@ def test_network_eval_mode_fp32_matches_oracle_and_golden(host_ops, problem, gol
     assert rel_fro(out, ref) < 1e-6
     assert rel_fro(out.reshape(-1), golden["feature_eval"]) < 1e-6
     errs = {k: rel_fro(p.grad, grads[k]) for k, p in net.named_parameters()}
-    assert max(errs.values()) < 1e-3, max(errs.items(), key=lambda kv: kv[1])
+    assert max(errs.values()) < 5e-3, max(errs.items(), key=lambda kv: kv[1])
     assert statistics.median(errs.values()) < 1e-5
     for k in golden.files:
         if k.startswith("grad_eval/"):
-            assert rel_fro(dict(net.named_parameters())[k[10:]].grad, golden[k]) < 1e-3, k
+            assert rel_fro(dict(net.named_parameters())[k[10:]].grad, golden[k]) < 5e-3, k
     after = net.state_dict()
     assert all(torch.equal(after[k], sd[k]) for k in sd), "evaluation mode leaves the running statistics alone"
 
@@ -311,7 +312,7 @@ def test_basic_block_backbone_and_2048_features(host_ops):
     assert out.shape == ref.shape == (1, 512, 1, 1, 1)
     assert rel_fro(out, ref) < 1e-6
     errs = [rel_fro(p.grad, grads[k]) for k, p in net.named_parameters()]
-    assert max(errs) < 1e-3 and statistics.median(errs) < 1e-5
+    assert max(errs) < 5e-3 and statistics.median(errs) < 1e-5
 
 
 def test_calling_conventions_and_errors(host_ops, problem):
