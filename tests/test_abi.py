@@ -82,6 +82,36 @@ def test_feed_and_metrics_argument_validation_without_gpu(built):
     assert b"acoustic_metrics" in lib.neraf_last_error()
 
 
+def test_grid_operator_argument_validation_without_gpu(built):
+    """The grid-feature producer's operators reject bad windows, dtypes, strides and null pointers before any launch."""
+    from neraf_b200 import _lib
+    lib = _lib.lib()
+    buf = (C.c_float * 64)()
+    a = C.addressof(buf)
+    w = _lib.Window3d(8, 8, 8, 8, 3, 1, 1)
+    assert lib.neraf_grid_im2col(C.byref(w), None, 0, 8, 1, a, 0, 216, None) == 1 and b"null" in lib.neraf_last_error()
+    assert lib.neraf_grid_im2col(C.byref(w), a, 0, 8, 1, a, 0, 215, None) == 1 and b"ld_col" in lib.neraf_last_error()
+    assert lib.neraf_grid_im2col(C.byref(w), a, 2, 8, 1, a, 0, 216, None) == 1 and b"dtype" in lib.neraf_last_error()
+    assert lib.neraf_grid_im2col(C.byref(w), a, 0, 0, 1, a, 0, 216, None) == 1 and b"strides" in lib.neraf_last_error()
+    for bad in (_lib.Window3d(8, 8, 8, 8, 9, 1, 1), _lib.Window3d(8, 8, 8, 8, 3, 0, 1), _lib.Window3d(8, 8, 8, 8, 3, 1, 3),
+                _lib.Window3d(0, 8, 8, 8, 3, 1, 1), _lib.Window3d(2, 2, 2, 8, 7, 1, 1), _lib.Window3d(2048, 2048, 2048, 8, 3, 1, 1)):
+        assert lib.neraf_grid_col2im(C.byref(bad), a, 0, 216, a, 8, None) == 1
+        assert lib.neraf_grid_maxpool(C.byref(bad), a, 0, 8, a, 8, a, None) == 1
+    assert lib.neraf_grid_col2im(C.byref(w), a, 0, 216, a, 7, None) == 1 and b"row stride" in lib.neraf_last_error()
+    assert lib.neraf_grid_maxpool_backward(C.byref(w), a, None, 1, 8, None, a, 8, None) == 1
+    assert lib.neraf_grid_pack_weight(a, 4, 4, 27, a, 0, 107, None) == 1
+    assert lib.neraf_grid_unpack_wgrad(a, 107, 4, 4, 27, a, None) == 1
+    assert lib.neraf_grid_bn_stats(a, 0, 0, 8, 8, a, None) == 1
+    assert lib.neraf_grid_bn_stats(a, 0, 8, 8, 7, a, None) == 1
+    assert lib.neraf_grid_bn_finalize(None, 8, 8, 1e-5, 0.1, 1, a, a, a, a, None) == 1 and b"statistics" in lib.neraf_last_error()
+    assert lib.neraf_grid_bn_finalize(a, 8, 8, 1e-5, 0.1, 1, None, None, a, a, None) == 1 and b"momentum" in lib.neraf_last_error()
+    assert lib.neraf_grid_bn_finalize(None, 8, 8, 1e-5, 0.0, 0, None, None, a, a, None) == 1
+    assert lib.neraf_grid_bn_apply(a, 0, 8, 8, 8, a, a, a, None, None, 0, 1, a, 8, None) == 1
+    assert lib.neraf_grid_bn_backward_reduce(a, None, None, a, 0, 8, 8, 8, a, a, None, a, None) == 1
+    assert lib.neraf_grid_bn_backward_apply(a, a, 0, 8, 8, 8, a, a, a, None, 1, a, None, None, None) == 1
+    assert lib.neraf_grid_broadcast_rows(a, 1.0, 8, 8, a, 0, 7, None) == 1
+
+
 def test_product_modules_fail_loudly_without_gpu(built):
     from neraf_b200 import _lib
     from neraf_b200.field import NeRAFAudioSoundField
