@@ -284,3 +284,63 @@ def test_full_size_grid_properties():
     f3.backward(dout)
     torch.cuda.synchronize()
     assert torch.isfinite(f3).all() and all(torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@not_yet_run
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_train_step_through_producer_and_field_eager_and_graphed(prec):
+    """NeRAF_model.py:554-566 with the real producer: grid -> ResNet3D -> feature -> field -> loss -> backward.  The
+    producer's parameter gradients must be what its own backward gives for the dg the field returns, and the captured
+    step (GraphedTrainStep picks the autograd capture for a trainable producer) must replay the eager step."""
+    from neraf_b200.model import ConstantGridFeature, GraphedTrainStep, NeRAFAudioModel, NeRAFAudioModelConfig
+    dev = cuda()
+    shape, B = syn.RAF, 256
+    cfg = NeRAFAudioModelConfig(dataset="RAF", precision=prec, grid_step=GRID_STEP, grid_net="resnet50")
+    model = NeRAFAudioModel(cfg, syn.default_aabb(), grid=syn.make_grid(N)[0])
+    model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
+    model.resnet3d.load_state_dict(syn.make_gridnet_state_dict("resnet50"))
+    model = model.to(dev)
+    model.grid = model.grid.to(dev)
+    model.resnet3d.eval()                                   # running statistics: the step is repeatable
+    model.field.always_repack = True
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=1).items()}
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def eager():
+        for p in params:
+            p.grad = None
+        ld = model.get_loss_dict(model.get_outputs(batch), batch)
+        sum(ld.values()).backward()
+        torch.cuda.synchronize()
+        return {k: float(v) for k, v in ld.items()}, {id(p): p.grad.clone() for p in params}
+
+    losses, grads = eager()
+    assert all(torch.isfinite(g).all() for g in grads.values())
+    # the same field fed the producer's feature as a constant: same losses, and its dg drives the producer's backward
+    with torch.no_grad():
+        feat = model.grid_feature().clone()
+    twin = NeRAFAudioModel(NeRAFAudioModelConfig(dataset="RAF", precision=prec), syn.default_aabb(),
+                           resnet3d=ConstantGridFeature(1024, feat)).to(dev)
+    twin.field.load_state_dict(model.field.state_dict())
+    twin.field.always_repack = True
+    ld2 = twin.get_loss_dict(twin.get_outputs(batch), batch)
+    sum(ld2.values()).backward()
+    for k, v in losses.items():
+        assert abs(float(ld2[k]) - v) <= 1e-6 * abs(v), k
+    for p, q in zip(model.field.parameters(), twin.field.parameters()):
+        assert rel_fro(grads[id(p)], q.grad) < 1e-5
+    dg = twin.resnet3d.feature.grad
+    for p in model.resnet3d.parameters():
+        p.grad = None
+    model.resnet3d(model.grid.unsqueeze(0)).backward(dg.view(1, -1, 1, 1, 1))
+    torch.cuda.synchronize()
+    for p in model.resnet3d.parameters():
+        assert rel_fro(p.grad, grads[id(p)]) < 1e-5
+    # captured
+    step = GraphedTrainStep(model, batch)
+    got = step(batch)
+    torch.cuda.synchronize()
+    for k, v in losses.items():
+        assert abs(float(got[k]) - v) <= 1e-5 * abs(v), k
+    for p in params:
+        assert rel_fro(p.grad, grads[id(p)]) < 1e-4
