@@ -8,7 +8,11 @@ are independent given replicated weights, so the path shards by rows of the batc
   inside the loss (neraf_b200/loss.py, ``group=``) so loss and gradients equal the single-GPU values on
   the concatenated batch,
 * parameter gradients are summed across ranks in one coalesced NCCL call.  With the "global" loss the
-  per-rank gradients are already scaled by 1/N_total, so the reduction is a SUM (not a mean).
+  per-rank gradients are already scaled by 1/N_total, so the reduction is a SUM (not a mean),
+* a replicated grid-feature producer (the ResNet3D, gridnet.py) sees the same grid on every rank, and its backward is
+  linear in the feature gradient dg: ``sum_gradient_across_ranks`` all-reduces dg (1024 floats) on its way into the
+  producer, after which every rank's producer gradients ARE the global sums -- the producer's parameters never enter
+  the gradient exchange (collective 3).
 
 Inference (rendering) shards poses with no collective at all.
 """
@@ -40,6 +44,32 @@ def shard_range(n_items: int, rank: int, world_size: int):
     base, rem = divmod(n_items, world_size)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _SumGradient(torch.autograd.Function):
+    """Identity in the forward pass; the backward pass sums the incoming gradient over the group."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def sum_gradient_across_ranks(x: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """x unchanged; d(loss)/dx is all-reduced (SUM) before it flows on.  Put between a REPLICATED sub-network and
+    the sharded computation that consumes its output: the sub-network then receives the global gradient on every
+    rank and its parameter gradients need no exchange.  (Replicas stay in step up to the rounding of their own
+    reductions -- the batch-norm statistics are summed with fp64 atomics; re-broadcast parameters when checkpointing
+    if bit-identical replicas matter.)"""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    return _SumGradient.apply(x, group)
 
 
 class GradientAllReduce:

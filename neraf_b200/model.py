@@ -117,7 +117,13 @@ class NeRAFAudioModel(nn.Module):
         feat = self.resnet3d(g)
         if isinstance(feat, (list, tuple)):
             feat = feat[-1]
-        return feat.flatten()
+        feat = feat.flatten()
+        if self.process_group is not None and feat.requires_grad and not isinstance(self.resnet3d, ConstantGridFeature):
+            # data parallel: the producer is replicated and its backward is linear in dg, so dg (N_features floats) is
+            # summed over the ranks here and the producer's own gradients come out global on every rank
+            from .distributed import sum_gradient_across_ranks
+            feat = sum_gradient_across_ranks(feat, self.process_group)
+        return feat
 
     # ---- training path --------------------------------------------------------------------------
     def get_outputs(self, batch_audio: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -165,6 +171,15 @@ class NeRAFAudioModel(nn.Module):
         if self.use_grid:
             params += list(self.resnet3d.parameters())
         return {"audio_fields": params}
+
+    def data_parallel_parameters(self):
+        """The parameters whose gradients are partial sums over this rank's shard and must be all-reduced
+        (``distributed.GradientAllReduce``): the field's, and a ConstantGridFeature's vector.  A replicated ResNet3D
+        producer is NOT in the list: ``grid_feature`` sums dg over the ranks before it enters the producer."""
+        params = list(self.field.parameters())
+        if self.use_grid and isinstance(self.resnet3d, ConstantGridFeature):
+            params += list(self.resnet3d.parameters())
+        return params
 
     # ---- eval / render path -----------------------------------------------------------------------
     @torch.no_grad()

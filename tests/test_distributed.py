@@ -89,3 +89,49 @@ def test_shard_helpers():
     b = syn.make_batch(syn.RAF, 8, seed=0)
     parts = [shard_batch(b, r, 2) for r in range(2)]
     assert torch.equal(torch.cat([p["mic_pose"] for p in parts]), b["mic_pose"])
+
+
+def _producer_worker(rank: int, world: int, port: int, out_dir: str):
+    """A replicated ResNet3D producer under data parallelism: dg is summed over the ranks on its way into the producer
+    (model.grid_feature), so every rank's producer gradients equal the single-process gradients for the summed dg and
+    the producer's parameters stay out of the gradient exchange."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from neraf_b200.gridnet import ResNet3D_helper
+        from neraf_b200.model import NeRAFAudioModel, NeRAFAudioModelConfig
+        from tests.gridnet_host import HostOps
+        n = 64
+        sd = syn.make_gridnet_state_dict("resnet18", seed=2)
+
+        def make(group):
+            net = ResNet3D_helper(7, "resnet18", False, 1 / n, 1024, precision="fp32")
+            net.load_state_dict(sd)
+            net.backbone_net.ops = HostOps()
+            net.eval()
+            cfg = NeRAFAudioModelConfig(dataset="RAF", grid_step=1 / n)
+            return NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=net, grid=syn.make_grid(n)[0], process_group=group)
+
+        model = make(dist.group.WORLD)
+        probes = [torch.randn(256, generator=torch.Generator().manual_seed(40 + r)) for r in range(world)]
+        feat = model.grid_feature()
+        assert feat.shape == (256,) and feat.requires_grad
+        (feat * probes[rank]).sum().backward()                     # this rank's shard of the loss
+        single = make(None)                                        # one process, the whole batch
+        (single.grid_feature() * sum(probes)).sum().backward()
+        for (k, p), q in zip(model.resnet3d.named_parameters(), single.resnet3d.parameters()):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-6 * float(q.grad.abs().max())), k
+        exchanged = model.data_parallel_parameters()
+        assert not any(p is q for p in model.resnet3d.parameters() for q in exchanged)
+        assert all(any(p is q for q in exchanged) for p in model.field.parameters())
+        with torch.no_grad():                                      # no autograd graph: nothing to wrap, no collective
+            assert not model.grid_feature().requires_grad
+        open(os.path.join(out_dir, f"producer_ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicated_producer_receives_the_summed_feature_gradient(tmp_path, built):
+    world = 2
+    mp.spawn(_producer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"producer_ok{r}")) for r in range(world))
