@@ -159,7 +159,7 @@ static int check_window(const neraf_window3d* w, Window* out) {
   NERAF_REQUIRE(w->in_d + 2 * w->pad >= w->k && w->in_h + 2 * w->pad >= w->k && w->in_w + 2 * w->pad >= w->k,
                 "grid op: window larger than the padded input");
   *out = make_window(w->in_d, w->in_h, w->in_w, w->channels, w->k, w->stride, w->pad);
-  NERAF_REQUIRE(in_voxels(*out) < 0x7fffffffLL, "grid op: more than 2^31 voxels");
+  NERAF_REQUIRE(in_voxels(*out) < 0x7fffffffLL && out_voxels(*out) < 0x7fffffffLL, "grid op: more than 2^31 voxels");
   return NERAF_OK;
 }
 

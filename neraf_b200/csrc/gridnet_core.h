@@ -66,6 +66,29 @@ GN_HD Window make_window(int in_d, int in_h, int in_w, int C, int k, int stride,
   return w;
 }
 
+// idx = q * d + r.  Voxel counts and -- for every tensor of the reference's networks -- element counts fit 32 bits, and a
+// 64-bit division costs the GPU several times a 32-bit one (these kernels are otherwise a handful of instructions per
+// element), so the 32-bit form is taken whenever both operands allow it.
+GN_HD void split_index(long long idx, long long d, long long* q, int* r) {
+  if ((((unsigned long long)idx | (unsigned long long)d) >> 32) == 0) {
+    const unsigned a = (unsigned)idx, b = (unsigned)d, qq = a / b;
+    *q = (long long)qq;
+    *r = (int)(a - qq * b);
+  } else {
+    const long long qq = idx / d;
+    *q = qq;
+    *r = (int)(idx - qq * d);
+  }
+}
+// voxel index (< 2^31, checked by the callers) -> (d, h, w) for an extent (., H, W)
+GN_HD void split_voxel(long long v, int H, int W, int* d, int* h, int* w) {
+  const unsigned u = (unsigned)v, t = u / (unsigned)W;
+  *w = (int)(u - t * (unsigned)W);
+  const unsigned dd = t / (unsigned)H;
+  *h = (int)(t - dd * (unsigned)H);
+  *d = (int)dd;
+}
+
 GN_HD long long in_voxels(const Window& w) { return (long long)w.in_d * w.in_h * w.in_w; }
 GN_HD long long out_voxels(const Window& w) { return (long long)w.out_d * w.out_h * w.out_w; }
 
@@ -75,14 +98,16 @@ GN_HD long long out_voxels(const Window& w) { return (long long)w.out_d * w.out_
 template <class Tin, class Tout>
 GN_HD void im2col_element(const Window& w, const Tin* in, long long voxel_stride, long long channel_stride, Tout* col,
                           long long ld, long long idx) {
-  const long long v = idx / ld;
-  const int j = (int)(idx - v * ld);
+  long long v;
+  int j;
+  split_index(idx, ld, &v, &j);
   float val = 0.f;
   const int K = w.k * w.k * w.k * w.C;
   if (j < K) {
     const int kidx = j / w.C, c = j - kidx * w.C;
     const int kw = kidx % w.k, kh = (kidx / w.k) % w.k, kd = kidx / (w.k * w.k);
-    const int ow = (int)(v % w.out_w), oh = (int)((v / w.out_w) % w.out_h), od = (int)(v / ((long long)w.out_w * w.out_h));
+    int ow, oh, od;
+    split_voxel(v, w.out_h, w.out_w, &od, &oh, &ow);
     const int id = od * w.stride - w.pad + kd, ih = oh * w.stride - w.pad + kh, iw = ow * w.stride - w.pad + kw;
     if (id >= 0 && id < w.in_d && ih >= 0 && ih < w.in_h && iw >= 0 && iw < w.in_w) {
       const long long vin = ((long long)id * w.in_h + ih) * w.in_w + iw;
@@ -96,9 +121,10 @@ GN_HD void im2col_element(const Window& w, const Tin* in, long long voxel_stride
 // read voxel v_in of dcol[v_out, kidx * C + c].  fp32 accumulation, fixed order (kd, kh, kw ascending): deterministic.
 template <class T>
 GN_HD void col2im_element(const Window& w, const T* dcol, long long ld_col, T* dx, long long ld_dx, long long idx) {
-  const long long v = idx / w.C;
-  const int c = (int)(idx - v * w.C);
-  const int iw = (int)(v % w.in_w), ih = (int)((v / w.in_w) % w.in_h), id = (int)(v / ((long long)w.in_w * w.in_h));
+  long long v;
+  int c, iw, ih, id;
+  split_index(idx, w.C, &v, &c);
+  split_voxel(v, w.in_h, w.in_w, &id, &ih, &iw);
   float acc = 0.f;
   for (int kd = 0; kd < w.k; ++kd) {
     const int td = id + w.pad - kd;
@@ -141,15 +167,17 @@ GN_HD bool gather_can_vec8(const Window& w, bool all_bf16, long long in_row_stri
 // unit idx = (v_out, j8): columns [8 j8, 8 j8 + 8) of row v_out
 GN_HD void im2col_vec8_element(const Window& w, const bf16_t* in, long long voxel_stride, bf16_t* col, long long ld,
                                long long idx) {
-  const long long ld8 = ld / 8;
-  const long long v = idx / ld8;
-  const int j = (int)(idx - v * ld8) * 8;
+  long long v;
+  int j;
+  split_index(idx, ld / 8, &v, &j);
+  j *= 8;
   vec8_t val = {{0u, 0u, 0u, 0u}};
   const int K = w.k * w.k * w.k * w.C;
   if (j < K) {
     const int kidx = j / w.C, c = j - kidx * w.C;
     const int kw = kidx % w.k, kh = (kidx / w.k) % w.k, kd = kidx / (w.k * w.k);
-    const int ow = (int)(v % w.out_w), oh = (int)((v / w.out_w) % w.out_h), od = (int)(v / ((long long)w.out_w * w.out_h));
+    int ow, oh, od;
+    split_voxel(v, w.out_h, w.out_w, &od, &oh, &ow);
     const int id = od * w.stride - w.pad + kd, ih = oh * w.stride - w.pad + kh, iw = ow * w.stride - w.pad + kw;
     if (id >= 0 && id < w.in_d && ih >= 0 && ih < w.in_h && iw >= 0 && iw < w.in_w) {
       const long long vin = ((long long)id * w.in_h + ih) * w.in_w + iw;
@@ -162,10 +190,11 @@ GN_HD void im2col_vec8_element(const Window& w, const bf16_t* in, long long voxe
 // unit idx = (v_in, c8): channels [8 c8, 8 c8 + 8) of input voxel v_in; same summation order as col2im_element
 GN_HD void col2im_vec8_element(const Window& w, const bf16_t* dcol, long long ld_col, bf16_t* dx, long long ld_dx,
                                long long idx) {
-  const int C8 = w.C / 8;
-  const long long v = idx / C8;
-  const int c = (int)(idx - v * C8) * 8;
-  const int iw = (int)(v % w.in_w), ih = (int)((v / w.in_w) % w.in_h), id = (int)(v / ((long long)w.in_w * w.in_h));
+  long long v;
+  int c, iw, ih, id;
+  split_index(idx, w.C / 8, &v, &c);
+  c *= 8;
+  split_voxel(v, w.in_h, w.in_w, &id, &ih, &iw);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int kd = 0; kd < w.k; ++kd) {
     const int td = id + w.pad - kd;
@@ -208,9 +237,10 @@ GN_HD void col2im_vec8_element(const Window& w, const bf16_t* dcol, long long ld
 template <class T>
 GN_HD void maxpool_element(const Window& w, const T* x, long long ld_x, T* y, long long ld_y, int32_t* argmax,
                            long long idx) {
-  const long long v = idx / w.C;
-  const int c = (int)(idx - v * w.C);
-  const int ow = (int)(v % w.out_w), oh = (int)((v / w.out_w) % w.out_h), od = (int)(v / ((long long)w.out_w * w.out_h));
+  long long v;
+  int c, ow, oh, od;
+  split_index(idx, w.C, &v, &c);
+  split_voxel(v, w.out_h, w.out_w, &od, &oh, &ow);
   float best = 0.f;
   long long arg = -1;
   for (int kd = 0; kd < w.k; ++kd) {
@@ -237,9 +267,10 @@ GN_HD void maxpool_element(const Window& w, const T* x, long long ld_x, T* y, lo
 template <class T>
 GN_HD void maxpool_backward_element(const Window& w, const T* dy, const T* dy2, long long ld_dy, const int32_t* argmax,
                                     T* dx, long long ld_dx, long long idx) {
-  const long long v = idx / w.C;
-  const int c = (int)(idx - v * w.C);
-  const int iw = (int)(v % w.in_w), ih = (int)((v / w.in_w) % w.in_h), id = (int)(v / ((long long)w.in_w * w.in_h));
+  long long v;
+  int c, iw, ih, id;
+  split_index(idx, w.C, &v, &c);
+  split_voxel(v, w.in_h, w.in_w, &id, &ih, &iw);
   float acc = 0.f;
   for (int kd = 0; kd < w.k; ++kd) {
     const int td = id + w.pad - kd;
@@ -271,7 +302,10 @@ GN_HD void maxpool_backward_element(const Window& w, const T* dy, const T* dy2, 
 // (co, j) with j in [0, ld) (pad columns zero) ---------------------------------------------------------------------
 template <class Tout>
 GN_HD void pack_weight_element(const float* w, long long c_in, long long k3, Tout* out, long long ld, long long idx) {
-  const long long co = idx / ld, j = idx - co * ld;
+  long long co;
+  int jj;
+  split_index(idx, ld, &co, &jj);
+  const long long j = jj;
   float val = 0.f;
   if (j < k3 * c_in) {
     const long long kidx = j / c_in, ci = j - kidx * c_in;
@@ -330,7 +364,9 @@ template <class T>
 GN_HD void bn_apply_element(const T* x, long long ld_x, long long C, const float* mean, const float* invstd,
                             const float* gamma, const float* beta, const T* residual, long long ld_res, int relu, T* y,
                             long long ld_y, long long idx) {
-  const long long r = idx / C, c = idx - r * C;
+  long long r;
+  int c;
+  split_index(idx, C, &r, &c);
   float v = (to_float(x[r * ld_x + c]) - mean[c]) * invstd[c] * gamma[c] + beta[c];
   if (residual) v += to_float(residual[r * ld_res + c]);
   if (relu && !(v > 0.f)) v = 0.f;
@@ -371,11 +407,14 @@ GN_HD void bn_backward_partial(const T* dy, const T* dy2, const T* y, const T* x
 template <class T>
 GN_HD void bn_backward_element(const T* g, const T* x, long long ld, long long C, const float* mean, const float* invstd,
                                const float* gamma, const double* sums, long long V, int training, T* dx, long long idx) {
-  const long long r = idx / C, c = idx - r * C;
+  long long r;
+  int c;
+  split_index(idx, C, &r, &c);
   float v = to_float(g[r * ld + c]);
   if (training) {
     const float xh = (to_float(x[r * ld + c]) - mean[c]) * invstd[c];
-    v -= (float)((sums[c] + (double)xh * sums[C + c]) / (double)V);
+    const double inv_v = 1.0 / (double)V;                       // loop-invariant: one fp64 division per thread, not per element
+    v -= (float)((sums[c] + (double)xh * sums[C + c]) * inv_v);
   }
   from_float(v * gamma[c] * invstd[c], dx + r * ld + c);
 }
@@ -384,7 +423,9 @@ GN_HD void bn_backward_element(const T* g, const T* x, long long ld, long long C
 // NeRAF_resnet3d.py:141-157) spread back over the voxels
 template <class T>
 GN_HD void broadcast_rows_element(const float* v, float scale, long long C, T* out, long long ld, long long idx) {
-  const long long r = idx / C, c = idx - r * C;
+  long long r;
+  int c;
+  split_index(idx, C, &r, &c);
   from_float(v[c] * scale, out + r * ld + c);
 }
 

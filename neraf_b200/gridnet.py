@@ -251,8 +251,7 @@ class _Act:
 
 class _UnitRecord:
     """What the backward pass of one conv + batch-norm unit needs."""
-    __slots__ = ("conv", "bn", "window", "col", "wmat", "xc", "y", "mean", "invstd", "relu", "in_dims", "in_is_grid",
-                 "direct")
+    __slots__ = ("conv", "bn", "window", "col", "wmat", "xc", "y", "mean", "invstd", "relu", "in_dims", "c_in", "direct")
 
 
 class _Runner:
@@ -266,11 +265,27 @@ class _Runner:
     def conv_bn(self, conv: Conv3dWeight, bn: BatchNorm3dParams, x: _Act, relu: bool, residual: Optional[_Act] = None,
                 grid: Optional[torch.Tensor] = None) -> Tuple[_Act, _UnitRecord]:
         ops, dev = self.ops, conv.weight.device
-        if grid is not None:                       # the stem reads the reference's (1, C, D, H, W) fp32 grid in place
+        weight = conv.weight.detach()
+        if grid is not None and self.dtype == torch.bfloat16:
+            # The stem reads the reference's channels-first fp32 grid (1, C, D, H, W).  C = 7 would force the 2-byte
+            # gather on the largest matrix of the network (0.46 GB at 128^3), so the grid is first laid out channels-last
+            # with the channels padded to 8 (a k = 1 gather: 33 MB) and the stem runs on that -- 16-byte gather, K = 8 k^3
+            # with zero weights on the pad channel.
+            if grid.shape[1] != conv.c_in:
+                raise ValueError(f"convolution expects {conv.c_in} input channels, got {grid.shape[1]}")
+            dims = tuple(grid.shape[2:])
+            c_pad = _round_up(grid.shape[1], 8)
+            v_in = dims[0] * dims[1] * dims[2]
+            cl = torch.empty(v_in, c_pad, dtype=self.dtype, device=dev)
+            ops.im2col(Window3d(dims[0], dims[1], dims[2], grid.shape[1], 1, 1, 0), grid, 1, v_in, cl)
+            x, grid = _Act(cl, dims), None
+            if c_pad != conv.c_in:
+                weight = torch.nn.functional.pad(weight, (0, 0, 0, 0, 0, 0, 0, c_pad - conv.c_in))
+        if grid is not None:                       # fp32: the stem gathers straight from the (1, C, D, H, W) grid
             in_dims, c_in = tuple(grid.shape[2:]), grid.shape[1]
         else:
             in_dims, c_in = x.dims, x.t.shape[1]
-        if c_in != conv.c_in:
+        if c_in != weight.shape[1]:
             raise ValueError(f"convolution expects {conv.c_in} input channels, got {c_in}")
         w = Window3d(in_dims[0], in_dims[1], in_dims[2], c_in, conv.k, conv.stride, conv.pad)
         out_dims = w.out_dims
@@ -286,7 +301,7 @@ class _Runner:
             else:
                 ops.im2col(w, x.t, x.t.stride(0), 1, col)
         wmat = torch.empty(conv.c_out, _round_up(kc, 8), dtype=self.dtype, device=dev)
-        ops.pack_weight(conv.weight.detach(), wmat)
+        ops.pack_weight(weight, wmat)
         xc = torch.empty(v_out, conv.c_out, dtype=self.dtype, device=dev)
         ops.gemm_nt(col, wmat, v_out, conv.c_out, kc, xc)
 
@@ -306,8 +321,7 @@ class _Runner:
         if self.keep:
             rec = _UnitRecord()
             rec.conv, rec.bn, rec.window, rec.col, rec.wmat, rec.xc, rec.y = conv, bn, w, col, wmat, xc, y
-            rec.mean, rec.invstd, rec.relu, rec.in_dims, rec.in_is_grid, rec.direct = mean, invstd, relu, in_dims, \
-                grid is not None, direct
+            rec.mean, rec.invstd, rec.relu, rec.in_dims, rec.c_in, rec.direct = mean, invstd, relu, in_dims, c_in, direct
         return _Act(y, out_dims), rec
 
     # ---- backward -----------------------------------------------------------------------------------------------------
@@ -327,26 +341,29 @@ class _Runner:
         self.grads[id(bn.weight)] = dgamma
         self.grads[id(bn.bias)] = dbeta
 
-        kc = conv.k ** 3 * conv.c_in
+        c_in = rec.c_in                                      # the stem's bf16 path runs on channels padded to 8
+        kc = conv.k ** 3 * c_in
         dw_mat = torch.empty(c_out, rec.wmat.stride(0), dtype=torch.float32, device=dev)
         ops.gemm_tn(dxc, rec.col, c_out, kc, v_out, dw_mat)
-        if conv.k == 1 and dw_mat.stride(0) == kc:
+        if conv.k == 1 and dw_mat.stride(0) == kc and c_in == conv.c_in:
             dweight = dw_mat.view(conv.weight.shape)
         else:
-            dweight = torch.empty_like(conv.weight, dtype=torch.float32)
+            dweight = torch.empty(c_out, c_in, conv.k, conv.k, conv.k, dtype=torch.float32, device=dev)
             ops.unpack_wgrad(dw_mat, dweight)
+            if c_in != conv.c_in:
+                dweight = dweight[:, :conv.c_in].contiguous()
         self.grads[id(conv.weight)] = dweight
 
         dx = None
         if need_dx:
             if rec.direct:
-                dx = torch.empty(v_out, conv.c_in, dtype=self.dtype, device=dev)
+                dx = torch.empty(v_out, c_in, dtype=self.dtype, device=dev)
                 ops.gemm_nn(dxc, rec.wmat, v_out, kc, c_out, dx)
             else:
                 dcol = torch.empty(v_out, rec.wmat.stride(0), dtype=self.dtype, device=dev)
                 ops.gemm_nn(dxc, rec.wmat, v_out, kc, c_out, dcol)
                 v_in = rec.in_dims[0] * rec.in_dims[1] * rec.in_dims[2]
-                dx = torch.empty(v_in, conv.c_in, dtype=self.dtype, device=dev)
+                dx = torch.empty(v_in, c_in, dtype=self.dtype, device=dev)
                 ops.col2im(rec.window, dcol, dx)
         return dx, g
 

@@ -6,7 +6,6 @@ the ResNet3D against the reference network without a GPU.  Never imported by the
 import ctypes as C
 import os
 
-import torch
 
 from neraf_b200 import _lib
 from neraf_b200.gridnet import GridOps
