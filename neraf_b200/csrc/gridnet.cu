@@ -81,6 +81,25 @@ __global__ void __launch_bounds__(kThreads) bn_backward_kernel(const T* g, const
       if (dgamma) dgamma[c] = (float)sums[C + c];
     }
 }
+__global__ void __launch_bounds__(kThreads) bn_apply_vec8_kernel(const bf16_t* x, long long ld_x, long long C,
+                                                                 const float* mean, const float* invstd,
+                                                                 const float* gamma, const float* beta, const bf16_t* res,
+                                                                 long long ld_res, int relu, bf16_t* y, long long ld_y,
+                                                                 long long n) {
+  GN_LOOP(n) bn_apply_vec8_element(x, ld_x, C, mean, invstd, gamma, beta, res, ld_res, relu, y, ld_y, idx);
+}
+__global__ void __launch_bounds__(kThreads) bn_backward_vec8_kernel(const bf16_t* g, const bf16_t* x, long long ld,
+                                                                    long long C, const float* mean, const float* invstd,
+                                                                    const float* gamma, const double* sums, long long V,
+                                                                    int training, bf16_t* dx, float* dgamma, float* dbeta,
+                                                                    long long n) {
+  GN_LOOP(n) bn_backward_vec8_element(g, x, ld, C, mean, invstd, gamma, sums, V, training, dx, idx);
+  if (blockIdx.x == 0)
+    for (long long c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)sums[c];
+      if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+}
 template <class T>
 __global__ void __launch_bounds__(kThreads) broadcast_rows_kernel(const float* v, float scale, long long C, T* out,
                                                                   long long ld, long long n) {
@@ -286,6 +305,12 @@ extern "C" int neraf_grid_bn_apply(const void* x, int32_t dtype, int64_t V, int6
                 (!residual || ld_res >= C), "bn_apply: bad arguments");
   const long long n = V * C;
   cudaStream_t s = (cudaStream_t)stream;
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld_x, residual ? ld_res : 0, ld_y, x, residual, y)) {
+    bn_apply_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>((const bf16_t*)x, ld_x, C, mean, invstd, gamma, beta,
+                                                              (const bf16_t*)residual, ld_res, relu, (bf16_t*)y, ld_y, n / 8);
+    NERAF_CHECK_LAUNCH("bn_apply_vec8_kernel");
+    return NERAF_OK;
+  }
   if (dtype == NERAF_DT_F32)
     bn_apply_kernel<<<grid_for(n), kThreads, 0, s>>>((const float*)x, ld_x, C, mean, invstd, gamma, beta,
                                                      (const float*)residual, ld_res, relu, (float*)y, ld_y, n);
@@ -326,6 +351,12 @@ extern "C" int neraf_grid_bn_backward_apply(const void* g, const void* x, int32_
                 "bn_backward_apply: bad arguments");
   const long long n = V * C;
   cudaStream_t s = (cudaStream_t)stream;
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, ld, ld, g, x, dx)) {
+    bn_backward_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>((const bf16_t*)g, (const bf16_t*)x, ld, C, mean, invstd,
+                                                                 gamma, sums, V, training, (bf16_t*)dx, dgamma, dbeta, n / 8);
+    NERAF_CHECK_LAUNCH("bn_backward_vec8_kernel");
+    return NERAF_OK;
+  }
   if (dtype == NERAF_DT_F32)
     bn_backward_kernel<<<grid_for(n), kThreads, 0, s>>>((const float*)g, (const float*)x, ld, C, mean, invstd, gamma, sums,
                                                         V, training, (float*)dx, dgamma, dbeta, n);

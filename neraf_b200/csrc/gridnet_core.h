@@ -360,6 +360,13 @@ GN_HD void bn_finalize_channel(const double* sums, long long V, long long C, flo
 }
 
 // y = [relu]( gamma (x - mean) invstd + beta [+ residual] )  -- the tail of every conv unit (NeRAF_resnet3d.py:98-113)
+GN_HD float bn_apply_value(float x, float mean, float invstd, float gamma, float beta, bool has_res, float res, int relu) {
+  float v = (x - mean) * invstd * gamma + beta;
+  if (has_res) v += res;
+  if (relu && !(v > 0.f)) v = 0.f;
+  return v;
+}
+
 template <class T>
 GN_HD void bn_apply_element(const T* x, long long ld_x, long long C, const float* mean, const float* invstd,
                             const float* gamma, const float* beta, const T* residual, long long ld_res, int relu, T* y,
@@ -367,10 +374,48 @@ GN_HD void bn_apply_element(const T* x, long long ld_x, long long C, const float
   long long r;
   int c;
   split_index(idx, C, &r, &c);
-  float v = (to_float(x[r * ld_x + c]) - mean[c]) * invstd[c] * gamma[c] + beta[c];
-  if (residual) v += to_float(residual[r * ld_res + c]);
-  if (relu && !(v > 0.f)) v = 0.f;
-  from_float(v, y + r * ld_y + c);
+  const float res = residual ? to_float(residual[r * ld_res + c]) : 0.f;
+  from_float(bn_apply_value(to_float(x[r * ld_x + c]), mean[c], invstd[c], gamma[c], beta[c], residual != nullptr, res, relu),
+             y + r * ld_y + c);
+}
+
+// 16-byte forms for bf16 matrices whose rows are whole 16-byte words (all of the network's activations): unit idx =
+// (r, c8), eight channels per thread, the same per-channel arithmetic as the scalar forms (same bits).
+GN_HD bool rows_can_vec8(bool is_bf16, long long C, long long ld_a, long long ld_b, long long ld_c, const void* a,
+                         const void* b, const void* c) {
+  return is_bf16 && C % 8 == 0 && ld_a % 8 == 0 && ld_b % 8 == 0 && ld_c % 8 == 0 && aligned16(a) && aligned16(b) &&
+         aligned16(c);
+}
+GN_HD void unpack8(const vec8_t& q, float* f) {
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = bits_to_float(q.w[i] << 16);
+    f[2 * i + 1] = bits_to_float(q.w[i] & 0xffff0000u);
+  }
+}
+GN_HD vec8_t pack8(const float* f) {
+  vec8_t out;
+  for (int i = 0; i < 4; ++i) {
+    bf16_t lo, hi;
+    from_float(f[2 * i], &lo);
+    from_float(f[2 * i + 1], &hi);
+    out.w[i] = (uint32_t)lo.bits | ((uint32_t)hi.bits << 16);
+  }
+  return out;
+}
+
+GN_HD void bn_apply_vec8_element(const bf16_t* x, long long ld_x, long long C, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, const bf16_t* residual, long long ld_res,
+                                 int relu, bf16_t* y, long long ld_y, long long idx) {
+  long long r;
+  int c;
+  split_index(idx, C / 8, &r, &c);
+  c *= 8;
+  float xv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, out[8];
+  unpack8(*reinterpret_cast<const vec8_t*>(x + r * ld_x + c), xv);
+  if (residual) unpack8(*reinterpret_cast<const vec8_t*>(residual + r * ld_res + c), rv);
+  for (int i = 0; i < 8; ++i)
+    out[i] = bn_apply_value(xv[i], mean[c + i], invstd[c + i], gamma[c + i], beta[c + i], residual != nullptr, rv[i], relu);
+  *reinterpret_cast<vec8_t*>(y + r * ld_y + c) = pack8(out);
 }
 
 // Backward, first pass over rows [r0, r1) of column c: the gradient that reaches the normalisation is
@@ -404,19 +449,43 @@ GN_HD void bn_backward_partial(const T* dy, const T* dy2, const T* y, const T* x
 
 // Second pass: dx = gamma invstd (g - (sum g + xhat sum g xhat) / V) with batch statistics, gamma invstd g with the
 // running ones (they are constants then).
+GN_HD float bn_backward_value(float g, float x, float mean, float invstd, float gamma, double s_g, double s_gx,
+                              double inv_v, int training) {
+  float v = g;
+  if (training) {
+    const float xh = (x - mean) * invstd;
+    v -= (float)((s_g + (double)xh * s_gx) * inv_v);
+  }
+  return v * gamma * invstd;
+}
+
 template <class T>
 GN_HD void bn_backward_element(const T* g, const T* x, long long ld, long long C, const float* mean, const float* invstd,
                                const float* gamma, const double* sums, long long V, int training, T* dx, long long idx) {
   long long r;
   int c;
   split_index(idx, C, &r, &c);
-  float v = to_float(g[r * ld + c]);
-  if (training) {
-    const float xh = (to_float(x[r * ld + c]) - mean[c]) * invstd[c];
-    const double inv_v = 1.0 / (double)V;                       // loop-invariant: one fp64 division per thread, not per element
-    v -= (float)((sums[c] + (double)xh * sums[C + c]) * inv_v);
-  }
-  from_float(v * gamma[c] * invstd[c], dx + r * ld + c);
+  const double inv_v = 1.0 / (double)V;            // loop-invariant: one fp64 division per thread, not per element
+  from_float(bn_backward_value(to_float(g[r * ld + c]), to_float(x[r * ld + c]), mean[c], invstd[c], gamma[c], sums[c],
+                               sums[C + c], inv_v, training),
+             dx + r * ld + c);
+}
+
+GN_HD void bn_backward_vec8_element(const bf16_t* g, const bf16_t* x, long long ld, long long C, const float* mean,
+                                    const float* invstd, const float* gamma, const double* sums, long long V,
+                                    int training, bf16_t* dx, long long idx) {
+  long long r;
+  int c;
+  split_index(idx, C / 8, &r, &c);
+  c *= 8;
+  const double inv_v = 1.0 / (double)V;
+  float gv[8], xv[8], out[8];
+  unpack8(*reinterpret_cast<const vec8_t*>(g + r * ld + c), gv);
+  unpack8(*reinterpret_cast<const vec8_t*>(x + r * ld + c), xv);
+  for (int i = 0; i < 8; ++i)
+    out[i] = bn_backward_value(gv[i], xv[i], mean[c + i], invstd[c + i], gamma[c + i], sums[c + i], sums[C + c + i], inv_v,
+                               training);
+  *reinterpret_cast<vec8_t*>(dx + r * ld + c) = pack8(out);
 }
 
 // out[r, c] = v[c] * scale: the gradient of the global average pooling (nn.AvgPool3d over the whole extent,

@@ -379,3 +379,35 @@ def test_16_byte_gathers_equal_the_scalar_forms(host_ops):
     dx_s = torch.empty(v_in * c + 1, dtype=torch.bfloat16)[1:].view(v_in, c)
     host_ops.col2im(w, dcol, dx_s)
     assert torch.equal(dx_s, dx_v)
+
+
+def test_16_byte_batchnorm_passes_equal_the_scalar_forms(host_ops):
+    """bn_apply / bn_backward_apply on bf16 rows of whole 16-byte words take the 128-bit kernels; an output buffer 2 bytes
+    off a 16-byte boundary forces the scalar kernels.  Same bits."""
+    g = torch.Generator().manual_seed(12)
+    V, c = 77, 24
+    x = (torch.randn(V, c, generator=g) * 2).bfloat16()
+    res = torch.randn(V, c, generator=g).bfloat16()
+    gam, bet = 1 + 0.2 * torch.randn(c, generator=g), 0.2 * torch.randn(c, generator=g)
+    mean, invstd = 0.1 * torch.randn(c, generator=g), 0.5 + torch.rand(c, generator=g)
+    sums = torch.randn(2, c, generator=g, dtype=torch.float64)
+
+    def off(rows):                      # (rows, c) bf16 view that starts 2 bytes past a 16-byte boundary, row stride c + 8
+        t = torch.empty(rows * (c + 8) + 1, dtype=torch.bfloat16)[1:].view(rows, c + 8)[:, :c]
+        assert t.data_ptr() % 16 != 0
+        return t
+
+    for r, relu in ((res, 1), (None, 0)):
+        y_v, y_s = torch.empty(V, c, dtype=torch.bfloat16), off(V)
+        host_ops.bn_apply(x, mean, invstd, gam, bet, r, relu, y_v)
+        host_ops.bn_apply(x, mean, invstd, gam, bet, r, relu, y_s)
+        assert torch.equal(y_s, y_v)
+    gy = torch.randn(V, c, generator=g).bfloat16()
+    for training in (True, False):
+        d_v = torch.empty(V, c, dtype=torch.bfloat16)
+        host_ops.bn_backward_apply(gy, x, mean, invstd, gam, sums, training, d_v, None, None)
+        # scalar form: all three matrices must share the row stride, so give them all the offset layout
+        gy_s, x_s, d_s = off(V), off(V), off(V)
+        gy_s.copy_(gy); x_s.copy_(x)
+        host_ops.bn_backward_apply(gy_s, x_s, mean, invstd, gam, sums, training, d_s, None, None)
+        assert torch.equal(d_s, d_v)
