@@ -305,7 +305,7 @@ extern "C" int neraf_grid_bn_apply(const void* x, int32_t dtype, int64_t V, int6
                 (!residual || ld_res >= C), "bn_apply: bad arguments");
   const long long n = V * C;
   cudaStream_t s = (cudaStream_t)stream;
-  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld_x, residual ? ld_res : 0, ld_y, x, residual, y)) {
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld_x, residual ? ld_res : 0, ld_y, x, residual, y, mean, invstd, gamma, beta)) {
     bn_apply_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>((const bf16_t*)x, ld_x, C, mean, invstd, gamma, beta,
                                                               (const bf16_t*)residual, ld_res, relu, (bf16_t*)y, ld_y, n / 8);
     NERAF_CHECK_LAUNCH("bn_apply_vec8_kernel");
@@ -351,7 +351,7 @@ extern "C" int neraf_grid_bn_backward_apply(const void* g, const void* x, int32_
                 "bn_backward_apply: bad arguments");
   const long long n = V * C;
   cudaStream_t s = (cudaStream_t)stream;
-  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, ld, ld, g, x, dx)) {
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, ld, ld, g, x, dx, mean, invstd, gamma, sums)) {
     bn_backward_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>((const bf16_t*)g, (const bf16_t*)x, ld, C, mean, invstd,
                                                                  gamma, sums, V, training, (bf16_t*)dx, dgamma, dbeta, n / 8);
     NERAF_CHECK_LAUNCH("bn_backward_vec8_kernel");

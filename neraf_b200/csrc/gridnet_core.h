@@ -382,9 +382,29 @@ GN_HD void bn_apply_element(const T* x, long long ld_x, long long C, const float
 // 16-byte forms for bf16 matrices whose rows are whole 16-byte words (all of the network's activations): unit idx =
 // (r, c8), eight channels per thread, the same per-channel arithmetic as the scalar forms (same bits).
 GN_HD bool rows_can_vec8(bool is_bf16, long long C, long long ld_a, long long ld_b, long long ld_c, const void* a,
-                         const void* b, const void* c) {
+                         const void* b, const void* c, const void* p0, const void* p1, const void* p2, const void* p3) {
   return is_bf16 && C % 8 == 0 && ld_a % 8 == 0 && ld_b % 8 == 0 && ld_c % 8 == 0 && aligned16(a) && aligned16(b) &&
-         aligned16(c);
+         aligned16(c) && aligned16(p0) && aligned16(p1) && aligned16(p2) && aligned16(p3);      // p*: per-channel vectors
+}
+struct alignas(16) f4_t { float v[4]; };
+struct alignas(16) d2_t { double v[2]; };
+// eight consecutive per-channel values as two / four 16-byte loads (p is 16-byte aligned: checked by the dispatch)
+GN_HD void load8(const float* p, float* out) {
+  const f4_t a = *reinterpret_cast<const f4_t*>(p), b = *reinterpret_cast<const f4_t*>(p + 4);
+  for (int i = 0; i < 4; ++i) { out[i] = a.v[i]; out[4 + i] = b.v[i]; }
+}
+GN_HD void load8(const double* p, double* out) {
+  for (int i = 0; i < 4; ++i) {
+    const d2_t a = *reinterpret_cast<const d2_t*>(p + 2 * i);
+    out[2 * i] = a.v[0]; out[2 * i + 1] = a.v[1];
+  }
+}
+GN_HD void load8(const bf16_t* p, float* out) {
+  const vec8_t q = *reinterpret_cast<const vec8_t*>(p);          // by value: one 128-bit load
+  for (int i = 0; i < 4; ++i) {
+    out[2 * i] = bits_to_float(q.w[i] << 16);
+    out[2 * i + 1] = bits_to_float(q.w[i] & 0xffff0000u);
+  }
 }
 GN_HD void unpack8(const vec8_t& q, float* f) {
   for (int i = 0; i < 4; ++i) {
@@ -410,11 +430,11 @@ GN_HD void bn_apply_vec8_element(const bf16_t* x, long long ld_x, long long C, c
   int c;
   split_index(idx, C / 8, &r, &c);
   c *= 8;
-  float xv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, out[8];
-  unpack8(*reinterpret_cast<const vec8_t*>(x + r * ld_x + c), xv);
-  if (residual) unpack8(*reinterpret_cast<const vec8_t*>(residual + r * ld_res + c), rv);
-  for (int i = 0; i < 8; ++i)
-    out[i] = bn_apply_value(xv[i], mean[c + i], invstd[c + i], gamma[c + i], beta[c + i], residual != nullptr, rv[i], relu);
+  float xv[8], rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, out[8], m[8], is[8], ga[8], be[8];
+  load8(x + r * ld_x + c, xv);
+  if (residual) load8(residual + r * ld_res + c, rv);
+  load8(mean + c, m); load8(invstd + c, is); load8(gamma + c, ga); load8(beta + c, be);
+  for (int i = 0; i < 8; ++i) out[i] = bn_apply_value(xv[i], m[i], is[i], ga[i], be[i], residual != nullptr, rv[i], relu);
   *reinterpret_cast<vec8_t*>(y + r * ld_y + c) = pack8(out);
 }
 
@@ -479,12 +499,13 @@ GN_HD void bn_backward_vec8_element(const bf16_t* g, const bf16_t* x, long long 
   split_index(idx, C / 8, &r, &c);
   c *= 8;
   const double inv_v = 1.0 / (double)V;
-  float gv[8], xv[8], out[8];
-  unpack8(*reinterpret_cast<const vec8_t*>(g + r * ld + c), gv);
-  unpack8(*reinterpret_cast<const vec8_t*>(x + r * ld + c), xv);
-  for (int i = 0; i < 8; ++i)
-    out[i] = bn_backward_value(gv[i], xv[i], mean[c + i], invstd[c + i], gamma[c + i], sums[c + i], sums[C + c + i], inv_v,
-                               training);
+  float gv[8], xv[8], out[8], m[8], is[8], ga[8];
+  double sg[8], sgx[8];
+  load8(g + r * ld + c, gv);
+  load8(x + r * ld + c, xv);
+  load8(mean + c, m); load8(invstd + c, is); load8(gamma + c, ga);
+  load8(sums + c, sg); load8(sums + C + c, sgx);
+  for (int i = 0; i < 8; ++i) out[i] = bn_backward_value(gv[i], xv[i], m[i], is[i], ga[i], sg[i], sgx[i], inv_v, training);
   *reinterpret_cast<vec8_t*>(dx + r * ld + c) = pack8(out);
 }
 

@@ -92,7 +92,7 @@ HOST_API int gridhost_bn_apply(const void* x, int32_t dtype, int64_t V, int64_t 
                                const float* invstd, const float* gamma, const float* beta, const void* residual,
                                int64_t ld_res, int32_t relu, void* y, int64_t ld_y, void*) {
   const long long n = V * C;
-  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld_x, residual ? ld_res : 0, ld_y, x, residual, y)) {           // as gridnet.cu
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld_x, residual ? ld_res : 0, ld_y, x, residual, y, mean, invstd, gamma, beta)) {           // as gridnet.cu
     for (long long i = 0; i < n / 8; ++i)
       bn_apply_vec8_element((const bf16_t*)x, ld_x, C, mean, invstd, gamma, beta, (const bf16_t*)residual, ld_res, relu,
                             (bf16_t*)y, ld_y, i);
@@ -131,7 +131,7 @@ HOST_API int gridhost_bn_backward_apply(const void* g, const void* x, int32_t dt
                                         const float* mean, const float* invstd, const float* gamma, const double* sums,
                                         int32_t training, void* dx, float* dgamma, float* dbeta, void*) {
   const long long n = V * C;
-  const bool vec8 = rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, ld, ld, g, x, dx);                              // as gridnet.cu
+  const bool vec8 = rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, ld, ld, g, x, dx, mean, invstd, gamma, sums);                              // as gridnet.cu
   for (long long i = 0; vec8 && i < n / 8; ++i)
     bn_backward_vec8_element((const bf16_t*)g, (const bf16_t*)x, ld, C, mean, invstd, gamma, sums, V, training, (bf16_t*)dx, i);
   for (long long i = 0; !vec8 && i < n; ++i) {
