@@ -49,6 +49,8 @@ class GridOps:
 
     prefix = "neraf_grid_"
 
+    _stream = None
+
     def __init__(self):
         self.lib = _lib.lib()
         self._counters: Dict[torch.device, torch.Tensor] = {}
@@ -57,8 +59,15 @@ class GridOps:
     def check_tensor(self, t: torch.Tensor, what: str) -> None:
         _lib.require_device(t, what)
 
+    def begin(self, device: torch.device) -> None:
+        """Start of one pass (a few hundred calls): the current stream is looked up once."""
+        self._stream = _lib.stream_ptr(device) if device.type == "cuda" else None
+
+    def end(self) -> None:
+        self._stream = None
+
     def stream(self, t: torch.Tensor):
-        return _lib.stream_ptr(t.device)
+        return self._stream if self._stream is not None else _lib.stream_ptr(t.device)
 
     def call(self, name: str, *args) -> None:
         _lib.check(getattr(self.lib, self.prefix + name)(*args))
@@ -138,11 +147,11 @@ class GridOps:
             j.epi.out_bf16, j.epi.ld_bf16 = out.data_ptr(), out.stride(0)
         else:
             j.epi.out_f32, j.epi.ld_f32 = out.data_ptr(), out.stride(0)
-        _lib.check(self.lib.neraf_gemm_bf16_jobs(C.byref(j), 1, cnt.data_ptr(), cnt.numel() * 4, _lib.stream_ptr(dev)))
+        _lib.check(self.lib.neraf_gemm_bf16_jobs(C.byref(j), 1, cnt.data_ptr(), cnt.numel() * 4, self.stream(out)))
 
     def _f32(self, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, out) -> None:
         _lib.check(self.lib.neraf_gemm_f32(M, N, K, A.data_ptr(), a_rs, a_cs, B.data_ptr(), b_rs, b_cs, None, 0, None, 0,
-                                           out.data_ptr(), out.stride(0), 0, _lib.stream_ptr(out.device)))
+                                           out.data_ptr(), out.stride(0), 0, self.stream(out)))
 
     def gemm_nt(self, A, B, M, N, K, out) -> None:
         if A.dtype == torch.bfloat16:
@@ -260,6 +269,7 @@ class _Runner:
     def __init__(self, ops: GridOps, dtype: torch.dtype, training: bool, keep: bool):
         self.ops, self.dtype, self.training, self.keep = ops, dtype, training, keep
         self.grads: Dict[int, torch.Tensor] = {}
+        self.tracked: List[torch.Tensor] = []
 
     # ---- forward ------------------------------------------------------------------------------------------------------
     def conv_bn(self, conv: Conv3dWeight, bn: BatchNorm3dParams, x: _Act, relu: bool, residual: Optional[_Act] = None,
@@ -311,7 +321,7 @@ class _Runner:
             sums = torch.empty(2, conv.c_out, dtype=torch.float64, device=dev)
             ops.bn_stats(xc, sums)
             ops.bn_finalize(sums, v_out, conv.c_out, bn.eps, bn.momentum, True, bn.running_mean, bn.running_var, mean, invstd)
-            bn.num_batches_tracked += 1
+            self.tracked.append(bn.num_batches_tracked)          # all counters are bumped by ONE call after the pass
         else:
             ops.bn_finalize(None, v_out, conv.c_out, bn.eps, 0.0, False, bn.running_mean, bn.running_var, mean, invstd)
         y = torch.empty_like(xc)
@@ -375,15 +385,23 @@ class _GridNetFn(torch.autograd.Function):
         ops.check_tensor(x, "grid")
         ops.check_tensor(params[0], "ResNet3D parameters")
         need_grad = any(ctx.needs_input_grad[2:])
-        with torch.no_grad():
-            out, tape = net._run_forward(ops, x, keep=need_grad)
+        ops.begin(params[0].device)
+        try:
+            with torch.no_grad():
+                out, tape = net._run_forward(ops, x, keep=need_grad)
+        finally:
+            ops.end()
         ctx.net, ctx.ops, ctx.tape, ctx.params = net, ops, tape, params
         return out
 
     @staticmethod
     def backward(ctx, dout: torch.Tensor):
-        with torch.no_grad():
-            grads = ctx.net._run_backward(ctx.ops, ctx.tape, dout)
+        ctx.ops.begin(dout.device)
+        try:
+            with torch.no_grad():
+                grads = ctx.net._run_backward(ctx.ops, ctx.tape, dout)
+        finally:
+            ctx.ops.end()
         ctx.tape = None
         return (None, None) + tuple(grads.get(id(p)) for p in ctx.params)
 
@@ -479,6 +497,8 @@ class ResNet3D(nn.Module):
         ops.bn_stats(a.t, sums)                                                                 # global average pooling
         ops.bn_finalize(sums, v, c, 0.0, 0.0, True, None, None, feat, None)
         tape["last_shape"] = (v, c)
+        if run.tracked:
+            torch._foreach_add_(run.tracked, 1)
         return feat.view(1, c, 1, 1, 1), (tape if keep else None)
 
     def _run_backward(self, ops: GridOps, tape: Dict, dout: torch.Tensor) -> Dict[int, torch.Tensor]:
