@@ -533,6 +533,25 @@ def main():
             del net, grid
         except Exception as exc:                                   # noqa: BLE001 -- an extra row must not lose the line
             line["grid_feature"] = {"error": f"{type(exc).__name__}: {exc}"}
+        # the same step captured in ONE CUDA graph (no Python / ctypes between the ~440 launches), timed in a child
+        # process: a capture has never run on this path before, and a failure there must not cost this process its line
+        if world == 1 and "error" not in line["grid_feature"]:
+            try:
+                child = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools",
+                                                                     "gridnet_quick.py"), str(args.grid_net), args.precision,
+                                        "--graph"], capture_output=True, text=True, timeout=180)
+                rows = [ln for ln in child.stdout.splitlines() if ln.startswith("{")]
+                got = json.loads(rows[-1]) if rows else {}
+                if "graph_ms_per_step" in got:
+                    line["grid_feature"]["graphed"] = {
+                        "ms_per_step": got["graph_ms_per_step"], "achieved_tflops": got["graph_achieved_tflops"],
+                        "value": 1.0 / (got["graph_ms_per_step"] * 1e-3), "unit": "step/s",
+                        "grad_max_rel_vs_eager": got.get("graph_vs_eager_grad_max_rel"),
+                        "api": "torch.cuda.CUDAGraph over ResNet3D_helper(grid).backward() (tools/gridnet_quick.py --graph)"}
+                else:
+                    line["grid_feature"]["graphed"] = {"error": got.get("graph_error") or (child.stderr or "no output")[-300:]}
+            except Exception as exc:                               # noqa: BLE001
+                line["grid_feature"]["graphed"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.gl_rirs > 0:

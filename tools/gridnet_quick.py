@@ -14,8 +14,10 @@ sys.path.insert(0, ROOT)
 from neraf_b200 import _lib, synthetic as syn          # noqa: E402
 from neraf_b200.gridnet import ResNet3D_helper, conv_flops   # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(_pos[0]) if _pos else 128
+prec = _pos[1] if len(_pos) > 1 else "bf16"
+with_graph = "--graph" in sys.argv          # also capture the step in a CUDA graph and time its replay
 out_path = os.path.join(ROOT, "gpurun_out", f"gridnet_{n}_{prec}.json")
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
 res = {"grid": [1, 7, n, n, n], "precision": prec, "import_s": time.time() - t_start}
@@ -63,6 +65,42 @@ res["ms_forward_only"] = s.elapsed_time(e) / k
 res["finite"] = bool(torch.isfinite(f).all() and all(torch.isfinite(p.grad).all() for p in net.parameters()))
 dump()
 print(json.dumps(res))
+if with_graph:
+    # the whole training step (forward + backward of every layer, ~440 launches) as ONE graph launch: what removes the
+    # Python / ctypes launch sequence from the step.  Standard whole-network capture: warm up on a side stream, drop the
+    # gradients so that the capture allocates them from the graph's pool, capture, replay.
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                net.zero_grad(set_to_none=True)
+                net(grid).backward(dfeat)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        eager_grads = [p.grad.clone() for p in net.parameters()]
+        net.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            feat_g = net(grid)
+            feat_g.backward(dfeat)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(k):
+            graph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        res["graph_ms_per_step"] = s.elapsed_time(e) / k
+        res["graph_achieved_tflops"] = fl / (res["graph_ms_per_step"] * 1e-3) / 1e12
+        # training-mode statistics are re-formed from the same grid and weights: the replay must reproduce the eager step
+        res["graph_vs_eager_grad_max_rel"] = max(
+            float((p.grad - a).norm() / a.norm().clamp_min(1e-30)) for p, a in zip(net.parameters(), eager_grads))
+        del graph
+    except Exception as exc:                                     # noqa: BLE001
+        res["graph_error"] = f"{type(exc).__name__}: {exc}"
+    dump()
+    print(json.dumps(res))
 net.eval()
 net.zero_grad(set_to_none=True)
 f1 = net(grid)
