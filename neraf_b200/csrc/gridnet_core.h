@@ -315,8 +315,11 @@ GN_HD void pack_weight_element(const float* w, long long c_in, long long k3, Tou
 }
 // the weight gradient back in the parameter's layout: element idx of dw (c_out, c_in, k^3)
 GN_HD void unpack_wgrad_element(const float* dw_mat, long long ld, long long c_in, long long k3, float* dw, long long idx) {
-  const long long kidx = idx % k3, ci = (idx / k3) % c_in, co = idx / (k3 * c_in);
-  dw[idx] = dw_mat[co * ld + kidx * c_in + ci];
+  long long t, co;
+  int kidx, ci;
+  split_index(idx, k3, &t, &kidx);
+  split_index(t, c_in, &co, &ci);
+  dw[idx] = dw_mat[co * ld + (long long)kidx * c_in + ci];
 }
 
 // ---- batch normalisation (nn.BatchNorm3d, NeRAF_resnet3d.py:120 and the blocks) ------------------------------------
