@@ -5,6 +5,8 @@
 // over channels-last (V, C) matrices: consecutive threads walk consecutive channels of one voxel, so reads and writes
 // are coalesced; grids are sized to a few waves of the 148 SMs.  The contractions themselves run on the tcgen05 job-list
 // kernel (gemm_mega.cu) or the fp32 GEMM (gemm_simt.cu) -- see neraf_b200/gridnet.py for the assembly.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gridnet_core.h"
 #include "kernels.h"
@@ -13,6 +15,13 @@ namespace neraf {
 namespace gridnet {
 
 constexpr int kThreads = 256;
+
+// NERAF_GRID_SCALAR=1 (environment, read once) keeps every kernel on its scalar form: for A/B timing of the 128-bit forms
+// and for bisecting a parity failure.
+static bool allow_vec8() {
+  static const bool scalar_only = getenv("NERAF_GRID_SCALAR") != nullptr;
+  return !scalar_only;
+}
 
 static unsigned grid_for(long long n) {
   const long long want = ceil_div(n, kThreads);
@@ -205,8 +214,8 @@ extern "C" int neraf_grid_im2col(const neraf_window3d* wd, const void* in, int32
   NERAF_REQUIRE(voxel_stride >= 1 && channel_stride >= 1, "im2col: bad input strides");
   const long long n = out_voxels(w) * ld_col;
   cudaStream_t s = (cudaStream_t)stream;
-  if (gather_can_vec8(w, in_dtype == NERAF_DT_BF16 && col_dtype == NERAF_DT_BF16, voxel_stride, channel_stride, ld_col, in,
-                      col)) {
+  if (allow_vec8() && gather_can_vec8(w, in_dtype == NERAF_DT_BF16 && col_dtype == NERAF_DT_BF16, voxel_stride,
+                                      channel_stride, ld_col, in, col)) {
     im2col_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>(w, (const bf16_t*)in, voxel_stride, (bf16_t*)col, ld_col, n / 8);
     NERAF_CHECK_LAUNCH("im2col_vec8_kernel");
     return NERAF_OK;
@@ -233,7 +242,7 @@ extern "C" int neraf_grid_col2im(const neraf_window3d* wd, const void* dcol, int
   NERAF_REQUIRE(ld_col >= (int64_t)w.k * w.k * w.k * w.C && ld_dx >= w.C, "col2im: row stride too small");
   const long long n = in_voxels(w) * w.C;
   cudaStream_t s = (cudaStream_t)stream;
-  if (gather_can_vec8(w, dtype == NERAF_DT_BF16, ld_dx, 1, ld_col, dcol, dx)) {
+  if (allow_vec8() && gather_can_vec8(w, dtype == NERAF_DT_BF16, ld_dx, 1, ld_col, dcol, dx)) {
     col2im_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>(w, (const bf16_t*)dcol, ld_col, (bf16_t*)dx, ld_dx, n / 8);
     NERAF_CHECK_LAUNCH("col2im_vec8_kernel");
     return NERAF_OK;
@@ -305,7 +314,8 @@ extern "C" int neraf_grid_bn_apply(const void* x, int32_t dtype, int64_t V, int6
                 (!residual || ld_res >= C), "bn_apply: bad arguments");
   const long long n = V * C;
   cudaStream_t s = (cudaStream_t)stream;
-  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld_x, residual ? ld_res : 0, ld_y, x, residual, y, mean, invstd, gamma, beta)) {
+  if (allow_vec8() &&
+      rows_can_vec8(dtype == NERAF_DT_BF16, C, ld_x, residual ? ld_res : 0, ld_y, x, residual, y, mean, invstd, gamma, beta)) {
     bn_apply_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>((const bf16_t*)x, ld_x, C, mean, invstd, gamma, beta,
                                                               (const bf16_t*)residual, ld_res, relu, (bf16_t*)y, ld_y, n / 8);
     NERAF_CHECK_LAUNCH("bn_apply_vec8_kernel");
@@ -351,7 +361,7 @@ extern "C" int neraf_grid_bn_backward_apply(const void* g, const void* x, int32_
                 "bn_backward_apply: bad arguments");
   const long long n = V * C;
   cudaStream_t s = (cudaStream_t)stream;
-  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, ld, ld, g, x, dx, mean, invstd, gamma, sums)) {
+  if (allow_vec8() && rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, ld, ld, g, x, dx, mean, invstd, gamma, sums)) {
     bn_backward_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>((const bf16_t*)g, (const bf16_t*)x, ld, C, mean, invstd,
                                                                  gamma, sums, V, training, (bf16_t*)dx, dgamma, dbeta, n / 8);
     NERAF_CHECK_LAUNCH("bn_backward_vec8_kernel");

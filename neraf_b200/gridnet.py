@@ -22,6 +22,7 @@ this file's assembly against the reference network on the CPU.)
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -29,6 +30,9 @@ import torch.nn as nn
 
 from . import _lib
 
+# NERAF_GRID_SCALAR=1: the plain forms everywhere (2-byte gathers, one GEMM per launch, the stem straight from the 7-channel
+# grid) -- the library reads the same variable; for A/B timing and for bisecting a parity failure
+PLAIN_FORMS = bool(os.environ.get("NERAF_GRID_SCALAR"))
 DT_F32, DT_BF16 = 0, 1
 _DT = {torch.float32: DT_F32, torch.bfloat16: DT_BF16}
 
@@ -131,13 +135,8 @@ class GridOps:
     # nt: out(M, N) = A(M, K) B(N, K)^T   forward        (gathered input x packed weight)
     # nn: out(M, N) = A(M, K) B(K, N)     data gradient  (dY x packed weight, the weight read MN-major)
     # tn: out(M, N) = A(K, M)^T B(K, N)   weight gradient (contracts over the voxels, both operands MN-major), fp32 out
-    def _jobs(self, M, N, K, A, B, a_mn, b_mn, out) -> None:
-        dev = out.device
-        n_cnt = (M + 255) // 256 + 8
-        cnt = self._counters.get(dev)
-        if cnt is None or cnt.numel() < n_cnt:
-            cnt = torch.zeros(max(n_cnt, 4096), dtype=torch.int32, device=dev)
-            self._counters[dev] = cnt
+    @staticmethod
+    def _job(M, N, K, A, B, a_mn, b_mn, out) -> "_lib.GemmJob":
         j = _lib.GemmJob()
         j.M, j.N, j.K, j.A, j.lda, j.B, j.ldb = M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
         j.a_mn, j.b_mn, j.wait_job = a_mn, b_mn, -1
@@ -147,7 +146,21 @@ class GridOps:
             j.epi.out_bf16, j.epi.ld_bf16 = out.data_ptr(), out.stride(0)
         else:
             j.epi.out_f32, j.epi.ld_f32 = out.data_ptr(), out.stride(0)
-        _lib.check(self.lib.neraf_gemm_bf16_jobs(C.byref(j), 1, cnt.data_ptr(), cnt.numel() * 4, self.stream(out)))
+        return j
+
+    def _launch(self, jobs, like: torch.Tensor) -> None:
+        """Independent GEMMs in ONE launch of the persistent job-list kernel (their tiles share the SMs)."""
+        dev = like.device
+        n_cnt = sum((int(j.M) + 255) // 256 for j in jobs) + 8
+        cnt = self._counters.get(dev)
+        if cnt is None or cnt.numel() < n_cnt:
+            cnt = torch.zeros(max(n_cnt, 4096), dtype=torch.int32, device=dev)
+            self._counters[dev] = cnt
+        arr = (_lib.GemmJob * len(jobs))(*jobs)
+        _lib.check(self.lib.neraf_gemm_bf16_jobs(arr, len(jobs), cnt.data_ptr(), cnt.numel() * 4, self.stream(like)))
+
+    def _jobs(self, M, N, K, A, B, a_mn, b_mn, out) -> None:
+        self._launch([self._job(M, N, K, A, B, a_mn, b_mn, out)], out)
 
     def _f32(self, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, out) -> None:
         _lib.check(self.lib.neraf_gemm_f32(M, N, K, A.data_ptr(), a_rs, a_cs, B.data_ptr(), b_rs, b_cs, None, 0, None, 0,
@@ -170,6 +183,20 @@ class GridOps:
             self._jobs(M, N, K, A, B, 1, 1, out)
         else:
             self._f32(M, N, K, A, 1, A.stride(0), B, 1, B.stride(0), out)
+
+    batched_backward = not PLAIN_FORMS      # False: gemm_backward issues gemm_tn + gemm_nn (the host stand-in of the tests)
+
+    def gemm_backward(self, dy, wmat, col, v_out, kc, c_out, dw_mat, dcol) -> None:
+        """Both gradients of one convolution from dy (v_out, c_out): dw_mat (c_out, kc) = dy^T col and, when dcol is given,
+        dcol (v_out, kc) = dy wmat.  bf16: the two independent GEMMs go out as one job list -- the weight gradient is a
+        handful of long-K tiles, the data gradient many short ones, together they fill the SMs."""
+        if self.batched_backward and dy.dtype == torch.bfloat16 and dcol is not None:
+            self._launch([self._job(c_out, kc, v_out, dy, col, 1, 1, dw_mat),
+                          self._job(v_out, kc, c_out, dy, wmat, 0, 1, dcol)], dy)
+            return
+        self.gemm_tn(dy, col, c_out, kc, v_out, dw_mat)
+        if dcol is not None:
+            self.gemm_nn(dy, wmat, v_out, kc, c_out, dcol)
 
 
 _default_ops: Optional[GridOps] = None
@@ -276,7 +303,7 @@ class _Runner:
                 grid: Optional[torch.Tensor] = None) -> Tuple[_Act, _UnitRecord]:
         ops, dev = self.ops, conv.weight.device
         weight = conv.weight.detach()
-        if grid is not None and self.dtype == torch.bfloat16:
+        if grid is not None and self.dtype == torch.bfloat16 and not PLAIN_FORMS:
             # The stem reads the reference's channels-first fp32 grid (1, C, D, H, W).  C = 7 would force the 2-byte
             # gather on the largest matrix of the network (0.46 GB at 128^3), so the grid is first laid out channels-last
             # with the channels padded to 8 (a k = 1 gather: 33 MB) and the stem runs on that -- 16-byte gather, K = 8 k^3
@@ -354,7 +381,10 @@ class _Runner:
         c_in = rec.c_in                                      # the stem's bf16 path runs on channels padded to 8
         kc = conv.k ** 3 * c_in
         dw_mat = torch.empty(c_out, rec.wmat.stride(0), dtype=torch.float32, device=dev)
-        ops.gemm_tn(dxc, rec.col, c_out, kc, v_out, dw_mat)
+        dcol = None
+        if need_dx:                  # a 1x1x1 stride-1 convolution's "gathered" gradient IS the input gradient
+            dcol = torch.empty(v_out, c_in if rec.direct else rec.wmat.stride(0), dtype=self.dtype, device=dev)
+        ops.gemm_backward(dxc, rec.wmat, rec.col, v_out, kc, c_out, dw_mat, dcol)
         if conv.k == 1 and dw_mat.stride(0) == kc and c_in == conv.c_in:
             dweight = dw_mat.view(conv.weight.shape)
         else:
@@ -367,11 +397,8 @@ class _Runner:
         dx = None
         if need_dx:
             if rec.direct:
-                dx = torch.empty(v_out, c_in, dtype=self.dtype, device=dev)
-                ops.gemm_nn(dxc, rec.wmat, v_out, kc, c_out, dx)
+                dx = dcol
             else:
-                dcol = torch.empty(v_out, rec.wmat.stride(0), dtype=self.dtype, device=dev)
-                ops.gemm_nn(dxc, rec.wmat, v_out, kc, c_out, dcol)
                 v_in = rec.in_dims[0] * rec.in_dims[1] * rec.in_dims[2]
                 dx = torch.empty(v_in, c_in, dtype=self.dtype, device=dev)
                 ops.col2im(rec.window, dcol, dx)

@@ -16,6 +16,7 @@ HOST_LIB = os.path.join(ROOT, "build", "libgridnet_host.so")
 
 class HostOps(GridOps):
     prefix = "gridhost_"
+    batched_backward = False           # gemm_backward -> gemm_tn + gemm_nn below
 
     def __init__(self):
         self.lib = C.CDLL(HOST_LIB)

@@ -58,7 +58,8 @@ def _unact(m, dims):
 
 # ------------------------------------------------------------------------------------------------ operators
 @pytest.mark.parametrize("dims,c,k,stride,pad", [((9, 6, 7), 7, 5, 2, 2), ((6, 5, 7), 8, 3, 1, 1), ((7, 6, 5), 16, 3, 2, 1),
-                                                ((6, 4, 5), 8, 1, 2, 0), ((33, 31, 32), 64, 3, 1, 1)])
+                                                ((6, 4, 5), 8, 1, 2, 0), ((33, 31, 32), 64, 3, 1, 1),
+                                                ((9, 6, 7), 7, 1, 1, 0), ((9, 6, 7), 8, 5, 2, 2)])   # the bf16 stem's two steps
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gather_kernels_equal_the_host_build(host_ops, dims, c, k, stride, pad, dtype):
     dev, ops = cuda(), default_ops()
@@ -191,6 +192,30 @@ def test_convolution_forward_dgrad_wgrad_match_torch(dims, c_in, c_out, k, strid
     dx = torch.empty(dims[0] * dims[1] * dims[2], c_in, dtype=dtype, device=dev)
     ops.col2im(w, dcol, dx)
     assert rel_fro(_unact(dx.float().cpu(), dims), xr.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+def test_batched_backward_gemms_equal_the_separate_launches():
+    """gemm_backward (bf16): weight gradient + data gradient of one convolution as ONE job list == the two launches."""
+    dev, ops = cuda(), default_ops()
+    g = torch.Generator().manual_seed(21)
+    for v_out, kc, c_out in ((1320, 1728, 64), (512, 256, 1024), (64, 3456, 128), (4096, 64, 256)):
+        dy = torch.randn(v_out, c_out, generator=g).bfloat16().to(dev)
+        col = torch.randn(v_out, kc, generator=g).bfloat16().to(dev)
+        wmat = (torch.randn(c_out, kc, generator=g) / np.sqrt(kc)).bfloat16().to(dev)
+        dw_a, dw_b = torch.zeros(c_out, kc, device=dev), torch.zeros(c_out, kc, device=dev)
+        dc_a = torch.zeros(v_out, kc, dtype=torch.bfloat16, device=dev)
+        dc_b = torch.zeros_like(dc_a)
+        assert ops.batched_backward
+        ops.gemm_backward(dy, wmat, col, v_out, kc, c_out, dw_a, dc_a)
+        ops.gemm_tn(dy, col, c_out, kc, v_out, dw_b)
+        ops.gemm_nn(dy, wmat, v_out, kc, c_out, dc_b)
+        torch.cuda.synchronize()
+        assert torch.equal(dw_a, dw_b) and torch.equal(dc_a, dc_b)
+        assert rel_fro(dw_a, dy.double().t() @ col.double()) < 1e-5
+        assert rel_fro(dc_a, dy.double() @ wmat.double()) < 4e-3
+        ops.gemm_backward(dy, wmat, col, v_out, kc, c_out, dw_a.zero_(), None)          # the stem: no data gradient
+        torch.cuda.synchronize()
+        assert torch.equal(dw_a, dw_b)
 
 
 # ------------------------------------------------------------------------------------------------ the whole network

@@ -30,7 +30,7 @@ else:
     Base = GridOps
 
 TIMED = ("im2col", "col2im", "pack_weight", "unpack_wgrad", "bn_stats", "bn_finalize", "bn_apply", "bn_backward_reduce",
-         "bn_backward_apply", "maxpool", "maxpool_backward", "broadcast_rows", "gemm_nt", "gemm_nn", "gemm_tn")
+         "bn_backward_apply", "maxpool", "maxpool_backward", "broadcast_rows", "gemm_nt", "gemm_backward")
 
 
 def _bytes(ts):
@@ -52,7 +52,11 @@ class TimedOps(Base):
             if not self.enabled:
                 return inner(self, *a, **k)
             nbytes = _bytes(a)
-            flops = 2.0 * a[2] * a[3] * a[4] if name.startswith("gemm") else 0.0
+            flops = 0.0
+            if name == "gemm_nt":                      # (A, B, M, N, K, out)
+                flops = 2.0 * a[2] * a[3] * a[4]
+            elif name == "gemm_backward":              # (dy, wmat, col, v_out, kc, c_out, dw_mat, dcol): wgrad (+ dgrad)
+                flops = 2.0 * a[3] * a[4] * a[5] * (2 if a[7] is not None else 1)
             if host:
                 t0 = time.perf_counter()
                 inner(self, *a, **k)
