@@ -430,11 +430,12 @@ NERAF_API int neraf_grid_im2col(const neraf_window3d* w, const void* in, int32_t
 NERAF_API int neraf_grid_col2im(const neraf_window3d* w, const void* dcol, int32_t dtype, int64_t ld_col, void* dx,
                       int64_t ld_dx, neraf_stream_t stream);
 /* nn.Conv3d weight (c_out, c_in, k, k, k) fp32 -> GEMM operand out[co, kidx c_in + ci], row stride ld_out (pad
- * columns zero), and the weight gradient back: dw[co, ci, kidx] = dw_mat[co * ld + kidx c_in + ci]. */
+ * columns zero), and the weight gradient back: dw[co, ci, kidx] = sum_s dw_mat[s * partial_stride + co * ld + kidx c_in + ci]
+ * over n_partials (>= 1) matrices -- the partial results of a weight-gradient GEMM split over the voxels (split-K). */
 NERAF_API int neraf_grid_pack_weight(const float* weight, int64_t c_out, int64_t c_in, int64_t k3, void* out,
                            int32_t out_dtype, int64_t ld_out, neraf_stream_t stream);
 NERAF_API int neraf_grid_unpack_wgrad(const float* dw_mat, int64_t ld, int64_t c_out, int64_t c_in, int64_t k3,
-                            float* dweight, neraf_stream_t stream);
+                            int32_t n_partials, int64_t partial_stride, float* dweight, neraf_stream_t stream);
 
 /* nn.BatchNorm3d.  sums: dev f64 (2, C), cleared by the call: sum x, sum x^2 over the V rows. */
 NERAF_API int neraf_grid_bn_stats(const void* x, int32_t dtype, int64_t V, int64_t C, int64_t ld, double* sums,

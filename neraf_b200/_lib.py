@@ -94,7 +94,7 @@ GRID_SIGNATURES = {
     "neraf_grid_im2col": (C.c_int, [_pw, _vp, _i32, _i64, _i64, _vp, _i32, _i64, _vp]),
     "neraf_grid_col2im": (C.c_int, [_pw, _vp, _i32, _i64, _vp, _i64, _vp]),
     "neraf_grid_pack_weight": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _vp]),
-    "neraf_grid_unpack_wgrad": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "neraf_grid_unpack_wgrad": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i64, _vp, _vp]),
     "neraf_grid_bn_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),
     "neraf_grid_bn_finalize": (C.c_int, [_vp, _i64, _i64, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "neraf_grid_bn_apply": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp]),

@@ -68,8 +68,9 @@ __global__ void __launch_bounds__(kThreads) pack_weight_kernel(const float* wt, 
   GN_LOOP(n) pack_weight_element(wt, c_in, k3, out, ld, idx);
 }
 __global__ void __launch_bounds__(kThreads) unpack_wgrad_kernel(const float* dw_mat, long long ld, long long c_in,
-                                                                long long k3, float* dw, long long n) {
-  GN_LOOP(n) unpack_wgrad_element(dw_mat, ld, c_in, k3, dw, idx);
+                                                                long long k3, int n_partials, long long partial_stride,
+                                                                float* dw, long long n) {
+  GN_LOOP(n) unpack_wgrad_element(dw_mat, ld, c_in, k3, n_partials, partial_stride, dw, idx);
 }
 template <class T>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T* x, long long ld_x, long long C, const float* mean,
@@ -270,10 +271,14 @@ extern "C" int neraf_grid_pack_weight(const float* weight, int64_t c_out, int64_
 }
 
 extern "C" int neraf_grid_unpack_wgrad(const float* dw_mat, int64_t ld, int64_t c_out, int64_t c_in, int64_t k3,
-                                       float* dweight, neraf_stream_t stream) {
+                                       int32_t n_partials, int64_t partial_stride, float* dweight,
+                                       neraf_stream_t stream) {
   NERAF_REQUIRE(dw_mat && dweight && c_out > 0 && c_in > 0 && k3 > 0 && ld >= c_in * k3, "unpack_wgrad: bad arguments");
+  NERAF_REQUIRE(n_partials >= 1 && n_partials <= 64 && (n_partials == 1 || partial_stride >= c_out * ld),
+                "unpack_wgrad: 1..64 partial matrices, at least c_out * ld floats apart");
   const long long n = c_out * c_in * k3;
-  unpack_wgrad_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(dw_mat, ld, c_in, k3, dweight, n);
+  unpack_wgrad_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(dw_mat, ld, c_in, k3, n_partials, partial_stride,
+                                                                          dweight, n);
   NERAF_CHECK_LAUNCH("unpack_wgrad_kernel");
   return NERAF_OK;
 }

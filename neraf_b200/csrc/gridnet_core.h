@@ -313,13 +313,19 @@ GN_HD void pack_weight_element(const float* w, long long c_in, long long k3, Tou
   }
   from_float(val, out + idx);
 }
-// the weight gradient back in the parameter's layout: element idx of dw (c_out, c_in, k^3)
-GN_HD void unpack_wgrad_element(const float* dw_mat, long long ld, long long c_in, long long k3, float* dw, long long idx) {
+// the weight gradient back in the parameter's layout: element idx of dw (c_out, c_in, k^3).  The GEMM that formed it may
+// have been split over the voxels (split-K: the contraction runs over up to 262 144 voxels while c_out x k^3 c_in is a
+// handful of tiles): dw_mat then holds n_partials matrices partial_stride floats apart, summed here in a fixed order.
+GN_HD void unpack_wgrad_element(const float* dw_mat, long long ld, long long c_in, long long k3, int n_partials,
+                                long long partial_stride, float* dw, long long idx) {
   long long t, co;
   int kidx, ci;
   split_index(idx, k3, &t, &kidx);
   split_index(t, c_in, &co, &ci);
-  dw[idx] = dw_mat[co * ld + (long long)kidx * c_in + ci];
+  const float* src = dw_mat + co * ld + (long long)kidx * c_in + ci;
+  float acc = src[0];
+  for (int s = 1; s < n_partials; ++s) acc += src[s * partial_stride];
+  dw[idx] = acc;
 }
 
 // ---- batch normalisation (nn.BatchNorm3d, NeRAF_resnet3d.py:120 and the blocks) ------------------------------------

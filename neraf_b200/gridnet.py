@@ -92,8 +92,10 @@ class GridOps:
                   self.stream(out))
 
     def unpack_wgrad(self, dw_mat: torch.Tensor, dweight: torch.Tensor) -> None:
+        """dw_mat (c_out, ld) or (S, c_out, ld): S split-K partial results, summed on the way."""
         c_out, c_in = dweight.shape[0], dweight.shape[1]
-        self.call("unpack_wgrad", dw_mat.data_ptr(), dw_mat.stride(0), c_out, c_in, dweight[0, 0].numel(),
+        parts, pstride = (1, 0) if dw_mat.dim() == 2 else (dw_mat.shape[0], dw_mat.stride(0))
+        self.call("unpack_wgrad", dw_mat.data_ptr(), dw_mat.stride(-2), c_out, c_in, dweight[0, 0].numel(), parts, pstride,
                   dweight.data_ptr(), self.stream(dweight))
 
     def bn_stats(self, x: torch.Tensor, sums: torch.Tensor) -> None:
@@ -132,9 +134,12 @@ class GridOps:
                   out.stride(0), self.stream(out))
 
     # -- contractions ---------------------------------------------------------------------------------------------------
-    # nt: out(M, N) = A(M, K) B(N, K)^T   forward        (gathered input x packed weight)
-    # nn: out(M, N) = A(M, K) B(K, N)     data gradient  (dY x packed weight, the weight read MN-major)
-    # tn: out(M, N) = A(K, M)^T B(K, N)   weight gradient (contracts over the voxels, both operands MN-major), fp32 out
+    # A GEMM is described as (M, N, K, A, B, a_mn, b_mn, out):
+    #   nt (0, 0): out(M, N) = A(M, K) B(N, K)^T   forward         (gathered input x packed weight)
+    #   nn (0, 1): out(M, N) = A(M, K) B(K, N)     data gradient   (dY x packed weight, the weight read MN-major)
+    #   tn (1, 1): out(M, N) = A(K, M)^T B(K, N)   weight gradient (contracts over the voxels, both operands MN-major)
+    # bf16 operands: every description of a call goes out in ONE launch of the persistent tcgen05 job-list kernel
+    # (independent GEMMs share the SMs); fp32 operands: one CUDA-core GEMM each (parity path).
     @staticmethod
     def _job(M, N, K, A, B, a_mn, b_mn, out) -> "_lib.GemmJob":
         j = _lib.GemmJob()
@@ -148,9 +153,17 @@ class GridOps:
             j.epi.out_f32, j.epi.ld_f32 = out.data_ptr(), out.stride(0)
         return j
 
-    def _launch(self, jobs, like: torch.Tensor) -> None:
-        """Independent GEMMs in ONE launch of the persistent job-list kernel (their tiles share the SMs)."""
+    def run_gemms(self, descs) -> None:
+        like = descs[0][7]
+        if descs[0][3].dtype != torch.bfloat16:
+            for (M, N, K, A, B, a_mn, b_mn, out) in descs:
+                a_rs, a_cs = (1, A.stride(0)) if a_mn else (A.stride(0), 1)
+                b_rs, b_cs = (1, B.stride(0)) if b_mn else (B.stride(0), 1)
+                _lib.check(self.lib.neraf_gemm_f32(M, N, K, A.data_ptr(), a_rs, a_cs, B.data_ptr(), b_rs, b_cs, None, 0, None,
+                                                   0, out.data_ptr(), out.stride(0), 0, self.stream(out)))
+            return
         dev = like.device
+        jobs = [self._job(*d) for d in descs]
         n_cnt = sum((int(j.M) + 255) // 256 for j in jobs) + 8
         cnt = self._counters.get(dev)
         if cnt is None or cnt.numel() < n_cnt:
@@ -159,44 +172,45 @@ class GridOps:
         arr = (_lib.GemmJob * len(jobs))(*jobs)
         _lib.check(self.lib.neraf_gemm_bf16_jobs(arr, len(jobs), cnt.data_ptr(), cnt.numel() * 4, self.stream(like)))
 
-    def _jobs(self, M, N, K, A, B, a_mn, b_mn, out) -> None:
-        self._launch([self._job(M, N, K, A, B, a_mn, b_mn, out)], out)
-
-    def _f32(self, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, out) -> None:
-        _lib.check(self.lib.neraf_gemm_f32(M, N, K, A.data_ptr(), a_rs, a_cs, B.data_ptr(), b_rs, b_cs, None, 0, None, 0,
-                                           out.data_ptr(), out.stride(0), 0, self.stream(out)))
-
     def gemm_nt(self, A, B, M, N, K, out) -> None:
-        if A.dtype == torch.bfloat16:
-            self._jobs(M, N, K, A, B, 0, 0, out)
-        else:
-            self._f32(M, N, K, A, A.stride(0), 1, B, B.stride(0), 1, out)
+        self.run_gemms([(M, N, K, A, B, 0, 0, out)])
 
     def gemm_nn(self, A, B, M, N, K, out) -> None:
-        if A.dtype == torch.bfloat16:
-            self._jobs(M, N, K, A, B, 0, 1, out)
-        else:
-            self._f32(M, N, K, A, A.stride(0), 1, B, 1, B.stride(0), out)
+        self.run_gemms([(M, N, K, A, B, 0, 1, out)])
 
     def gemm_tn(self, A, B, M, N, K, out) -> None:
-        if A.dtype == torch.bfloat16:
-            self._jobs(M, N, K, A, B, 1, 1, out)
-        else:
-            self._f32(M, N, K, A, 1, A.stride(0), B, 1, B.stride(0), out)
+        self.run_gemms([(M, N, K, A, B, 1, 1, out)])
 
-    batched_backward = not PLAIN_FORMS      # False: gemm_backward issues gemm_tn + gemm_nn (the host stand-in of the tests)
+    batched_backward = not PLAIN_FORMS      # False: one GEMM per launch, no split-K
+    MAX_SPLITS = 16                         # the job list holds 24 GEMMs
+    TILE_TARGET = 74                        # CTA pairs of a B200: enough weight-gradient tiles to occupy them
 
-    def gemm_backward(self, dy, wmat, col, v_out, kc, c_out, dw_mat, dcol) -> None:
-        """Both gradients of one convolution from dy (v_out, c_out): dw_mat (c_out, kc) = dy^T col and, when dcol is given,
-        dcol (v_out, kc) = dy wmat.  bf16: the two independent GEMMs go out as one job list -- the weight gradient is a
-        handful of long-K tiles, the data gradient many short ones, together they fill the SMs."""
-        if self.batched_backward and dy.dtype == torch.bfloat16 and dcol is not None:
-            self._launch([self._job(c_out, kc, v_out, dy, col, 1, 1, dw_mat),
-                          self._job(v_out, kc, c_out, dy, wmat, 0, 1, dcol)], dy)
-            return
-        self.gemm_tn(dy, col, c_out, kc, v_out, dw_mat)
+    def wgrad_splits(self, dy: torch.Tensor, v_out: int, kc: int, c_out: int) -> int:
+        """Split-K factor of a weight-gradient GEMM: its output (c_out, kc) is a handful of 256-row tiles while the
+        contraction runs over all voxels (the stem at 128^3: 4 tiles x 262 144), so the voxels are cut into chunks of
+        >= 2048 that run as separate jobs of the same launch and are summed by unpack_wgrad."""
+        if not self.batched_backward or dy.dtype != torch.bfloat16:
+            return 1
+        tiles = ((c_out + 255) // 256) * ((kc + 255) // 256)
+        return max(1, min(self.MAX_SPLITS, self.TILE_TARGET // tiles, v_out // 2048))
+
+    def gemm_backward(self, dy, wmat, col, v_out, kc, c_out, dw_parts, dcol) -> None:
+        """Both gradients of one convolution from dy (v_out, c_out): the weight gradient dy^T col, split over the voxels
+        into dw_parts.shape[0] partial matrices dw_parts (S, c_out, ld), and -- when dcol is given -- the data gradient
+        dcol (v_out, kc) = dy wmat.  bf16: all of them are jobs of ONE launch."""
+        S = dw_parts.shape[0]
+        rows = (-(-v_out // S) + 63) // 64 * 64
+        descs = []
+        for s_ in range(S):
+            r0, r1 = s_ * rows, min(v_out, (s_ + 1) * rows)
+            descs.append((c_out, kc, r1 - r0, dy[r0:r1], col[r0:r1], 1, 1, dw_parts[s_]))
         if dcol is not None:
-            self.gemm_nn(dy, wmat, v_out, kc, c_out, dcol)
+            descs.append((v_out, kc, c_out, dy, wmat, 0, 1, dcol))
+        if self.batched_backward:
+            self.run_gemms(descs)
+        else:
+            for d in descs:
+                self.run_gemms([d])
 
 
 _default_ops: Optional[GridOps] = None
@@ -380,16 +394,17 @@ class _Runner:
 
         c_in = rec.c_in                                      # the stem's bf16 path runs on channels padded to 8
         kc = conv.k ** 3 * c_in
-        dw_mat = torch.empty(c_out, rec.wmat.stride(0), dtype=torch.float32, device=dev)
+        n_split = ops.wgrad_splits(dxc, v_out, kc, c_out)
+        dw_parts = torch.empty(n_split, c_out, rec.wmat.stride(0), dtype=torch.float32, device=dev)
         dcol = None
         if need_dx:                  # a 1x1x1 stride-1 convolution's "gathered" gradient IS the input gradient
             dcol = torch.empty(v_out, c_in if rec.direct else rec.wmat.stride(0), dtype=self.dtype, device=dev)
-        ops.gemm_backward(dxc, rec.wmat, rec.col, v_out, kc, c_out, dw_mat, dcol)
-        if conv.k == 1 and dw_mat.stride(0) == kc and c_in == conv.c_in:
-            dweight = dw_mat.view(conv.weight.shape)
+        ops.gemm_backward(dxc, rec.wmat, rec.col, v_out, kc, c_out, dw_parts, dcol)
+        if n_split == 1 and conv.k == 1 and dw_parts.stride(1) == kc and c_in == conv.c_in:
+            dweight = dw_parts.view(conv.weight.shape)
         else:
             dweight = torch.empty(c_out, c_in, conv.k, conv.k, conv.k, dtype=torch.float32, device=dev)
-            ops.unpack_wgrad(dw_mat, dweight)
+            ops.unpack_wgrad(dw_parts, dweight)
             if c_in != conv.c_in:
                 dweight = dweight[:, :conv.c_in].contiguous()
         self.grads[id(conv.weight)] = dweight

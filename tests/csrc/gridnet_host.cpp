@@ -62,10 +62,10 @@ HOST_API int gridhost_pack_weight(const float* weight, int64_t c_out, int64_t c_
   return 0;
 }
 
-HOST_API int gridhost_unpack_wgrad(const float* dw_mat, int64_t ld, int64_t c_out, int64_t c_in, int64_t k3, float* dw,
-                                   void*) {
+HOST_API int gridhost_unpack_wgrad(const float* dw_mat, int64_t ld, int64_t c_out, int64_t c_in, int64_t k3,
+                                   int32_t n_partials, int64_t partial_stride, float* dw, void*) {
   const long long n = c_out * c_in * k3;
-  for (long long i = 0; i < n; ++i) unpack_wgrad_element(dw_mat, ld, c_in, k3, dw, i);
+  for (long long i = 0; i < n; ++i) unpack_wgrad_element(dw_mat, ld, c_in, k3, n_partials, partial_stride, dw, i);
   return 0;
 }
 

@@ -16,7 +16,7 @@ HOST_LIB = os.path.join(ROOT, "build", "libgridnet_host.so")
 
 class HostOps(GridOps):
     prefix = "gridhost_"
-    batched_backward = False           # gemm_backward -> gemm_tn + gemm_nn below
+    batched_backward = True            # the product's job lists, split-K included, evaluated by run_gemms below
 
     def __init__(self):
         self.lib = C.CDLL(HOST_LIB)
@@ -36,14 +36,10 @@ class HostOps(GridOps):
         self.calls[name] = self.calls.get(name, 0) + 1
         assert getattr(self.lib, self.prefix + name)(*args) == 0
 
-    def gemm_nt(self, A, B, M, N, K, out):
-        self.calls["gemm_nt"] = self.calls.get("gemm_nt", 0) + 1
-        out[:M, :N] = (A[:M, :K].float() @ B[:N, :K].float().t()).to(out.dtype)
-
-    def gemm_nn(self, A, B, M, N, K, out):
-        self.calls["gemm_nn"] = self.calls.get("gemm_nn", 0) + 1
-        out[:M, :N] = (A[:M, :K].float() @ B[:K, :N].float()).to(out.dtype)
-
-    def gemm_tn(self, A, B, M, N, K, out):
-        self.calls["gemm_tn"] = self.calls.get("gemm_tn", 0) + 1
-        out[:M, :N] = (A[:K, :M].float().t() @ B[:K, :N].float()).to(out.dtype)
+    def run_gemms(self, descs):
+        for (M, N, K, A, B, a_mn, b_mn, out) in descs:
+            kind = {(0, 0): "gemm_nt", (0, 1): "gemm_nn", (1, 1): "gemm_tn"}[(a_mn, b_mn)]
+            self.calls[kind] = self.calls.get(kind, 0) + 1
+            a = A[:K, :M].float().t() if a_mn else A[:M, :K].float()
+            b = B[:K, :N].float() if b_mn else B[:N, :K].float().t()
+            out[:M, :N] = (a @ b).to(out.dtype)

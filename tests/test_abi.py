@@ -100,7 +100,9 @@ def test_grid_operator_argument_validation_without_gpu(built):
     assert lib.neraf_grid_col2im(C.byref(w), a, 0, 216, a, 7, None) == 1 and b"row stride" in lib.neraf_last_error()
     assert lib.neraf_grid_maxpool_backward(C.byref(w), a, None, 1, 8, None, a, 8, None) == 1
     assert lib.neraf_grid_pack_weight(a, 4, 4, 27, a, 0, 107, None) == 1
-    assert lib.neraf_grid_unpack_wgrad(a, 107, 4, 4, 27, a, None) == 1
+    assert lib.neraf_grid_unpack_wgrad(a, 107, 4, 4, 27, 1, 0, a, None) == 1
+    assert lib.neraf_grid_unpack_wgrad(a, 108, 4, 4, 27, 2, 100, a, None) == 1 and b"partial" in lib.neraf_last_error()
+    assert lib.neraf_grid_unpack_wgrad(a, 108, 4, 4, 27, 0, 0, a, None) == 1
     assert lib.neraf_grid_bn_stats(a, 0, 0, 8, 8, a, None) == 1
     assert lib.neraf_grid_bn_stats(a, 0, 8, 8, 7, a, None) == 1
     assert lib.neraf_grid_bn_finalize(None, 8, 8, 1e-5, 0.1, 1, a, a, a, a, None) == 1 and b"statistics" in lib.neraf_last_error()

@@ -194,28 +194,35 @@ def test_convolution_forward_dgrad_wgrad_match_torch(dims, c_in, c_out, k, strid
     assert rel_fro(_unact(dx.float().cpu(), dims), xr.grad) < (1e-5 if dtype == torch.float32 else 2e-2)
 
 
-def test_batched_backward_gemms_equal_the_separate_launches():
-    """gemm_backward (bf16): weight gradient + data gradient of one convolution as ONE job list == the two launches."""
+def test_backward_job_list_with_split_k_equals_the_separate_launches():
+    """gemm_backward (bf16): the weight gradient of one convolution, split over the voxels into partial GEMMs, and its data
+    gradient as ONE job list == one launch per GEMM, unsplit."""
     dev, ops = cuda(), default_ops()
     g = torch.Generator().manual_seed(21)
-    for v_out, kc, c_out in ((1320, 1728, 64), (512, 256, 1024), (64, 3456, 128), (4096, 64, 256)):
+    assert ops.batched_backward
+    for v_out, kc, c_out in ((32768, 1000, 64), (32768, 64, 256), (4096, 3456, 128), (1320, 1728, 64), (512, 256, 1024)):
         dy = torch.randn(v_out, c_out, generator=g).bfloat16().to(dev)
         col = torch.randn(v_out, kc, generator=g).bfloat16().to(dev)
         wmat = (torch.randn(c_out, kc, generator=g) / np.sqrt(kc)).bfloat16().to(dev)
-        dw_a, dw_b = torch.zeros(c_out, kc, device=dev), torch.zeros(c_out, kc, device=dev)
+        S = ops.wgrad_splits(dy, v_out, kc, c_out)
+        assert S == max(1, min(16, 74 // (((c_out + 255) // 256) * ((kc + 255) // 256)), v_out // 2048))
+        parts = torch.full((S, c_out, kc), 7.0, device=dev)
         dc_a = torch.zeros(v_out, kc, dtype=torch.bfloat16, device=dev)
-        dc_b = torch.zeros_like(dc_a)
-        assert ops.batched_backward
-        ops.gemm_backward(dy, wmat, col, v_out, kc, c_out, dw_a, dc_a)
+        ops.gemm_backward(dy, wmat, col, v_out, kc, c_out, parts, dc_a)
+        dw_a = torch.empty(c_out, kc, 1, device=dev)
+        ops.unpack_wgrad(parts, dw_a)
+        dw_b, dc_b = torch.zeros(c_out, kc, device=dev), torch.zeros_like(dc_a)
         ops.gemm_tn(dy, col, c_out, kc, v_out, dw_b)
         ops.gemm_nn(dy, wmat, v_out, kc, c_out, dc_b)
         torch.cuda.synchronize()
-        assert torch.equal(dw_a, dw_b) and torch.equal(dc_a, dc_b)
-        assert rel_fro(dw_a, dy.double().t() @ col.double()) < 1e-5
+        assert torch.equal(dc_a, dc_b)
+        ref = dy.double().t() @ col.double()
+        assert rel_fro(dw_b, ref) < 1e-5 and rel_fro(dw_a[:, :, 0], ref) < 1e-5, (v_out, kc, c_out, S)
         assert rel_fro(dc_a, dy.double() @ wmat.double()) < 4e-3
-        ops.gemm_backward(dy, wmat, col, v_out, kc, c_out, dw_a.zero_(), None)          # the stem: no data gradient
+        ops.gemm_backward(dy, wmat, col, v_out, kc, c_out, parts.fill_(7.0), None)      # the stem: no data gradient
+        ops.unpack_wgrad(parts, dw_a)
         torch.cuda.synchronize()
-        assert torch.equal(dw_a, dw_b)
+        assert rel_fro(dw_a[:, :, 0], ref) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ the whole network
