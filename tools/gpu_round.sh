@@ -10,9 +10,9 @@ tail -4 gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; echo "ref rc=$?"
 # launch list of the SAME command the bench line comes from (CUDA graph replays: ncu lists the kernel nodes), then of the eager plugin calls
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --gl-rirs 148 > gpurun_out/bench_ncu.log 2>&1; echo "ncu list rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_eager.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --gl-rirs 0 > gpurun_out/bench_ncu_eager.log 2>&1; echo "ncu eager list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:mega -s 6 -c 2 -f -o gpurun_out/mega python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --gl-rirs 0 > gpurun_out/ncu_mega.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --gl-rirs 148 --grid-net 0 > gpurun_out/bench_ncu.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_eager.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --gl-rirs 0 --grid-net 0 > gpurun_out/bench_ncu_eager.log 2>&1; echo "ncu eager list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:mega -s 6 -c 2 -f -o gpurun_out/mega python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --gl-rirs 0 --grid-net 0 > gpurun_out/ncu_mega.log 2>&1; echo "ncu full rc=$?"
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
