@@ -36,7 +36,10 @@ def host_ops():
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = os.path.join(root, "build", "libgridnet_host.so")
-    if not os.path.exists(lib):                      # the GPU box receives build/ with the snapshot; rebuild if it did not
+    srcs = [os.path.join(root, "tests", "csrc", "gridnet_host.cpp"), os.path.join(root, "neraf_b200", "csrc", "gridnet_core.h"),
+            os.path.join(root, "include", "neraf_b200.h")]
+    # the GPU box receives build/ with the snapshot; rebuild if it did not, or if it is older than its sources
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(f) for f in srcs):
         os.makedirs(os.path.dirname(lib), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", lib,
                         os.path.join(root, "tests", "csrc", "gridnet_host.cpp")], check=True)
