@@ -497,7 +497,10 @@ class ResNet3D(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 5 or x.shape[0] != 1:
             raise ValueError(f"the grid must be (1, C, D, H, W) like the reference's feat_grid, got {tuple(x.shape)}")
-        params = [p for p in self.parameters()]
+        params = self.__dict__.get("_param_list")
+        if params is None:                      # walked once: Module.to / load_state_dict keep the Parameter objects
+            params = [p for p in self.parameters()]
+            self.__dict__["_param_list"] = params
         return _GridNetFn.apply(self, x, *params)
 
     # ---- the network as a sequence of library calls -----------------------------------------------------------------------
