@@ -503,6 +503,8 @@ def main():
 
     # ---- grid-feature producer: one training-mode forward + backward of ResNet3D-50 on a (1, 7, N, N, N) grid
     if args.grid_net > 0:
+        # (no collective inside the try block: a rank that fails must not leave the others waiting in one)
+        gn_local, gn_err, gn_info = -1.0, None, {}
         try:
             from neraf_b200.gridnet import ResNet3D_helper, conv_flops
             n_g = args.grid_net
@@ -514,7 +516,7 @@ def main():
             dfeat = torch.randn(1, 1024, 1, 1, 1, device=dev)
             for _ in range(2):
                 net(grid).backward(dfeat)
-            barrier()
+            torch.cuda.synchronize()
             l0 = lib.neraf_launch_count()
             k_gn = 5
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -522,17 +524,24 @@ def main():
             for _ in range(k_gn):
                 net(grid).backward(dfeat)
             e.record()
-            barrier()
-            gn_ms = max_over_ranks(s.elapsed_time(e)) / k_gn
-            fl = conv_flops(net.backbone_net, n_g)
-            line["grid_feature"] = {"metric": "grid_net_steps_per_sec", "value": world / (gn_ms * 1e-3), "unit": "step/s",
-                                    "grid": [1, 7, n_g, n_g, n_g], "ms_per_step": gn_ms,
-                                    "gflop_per_step": fl / 1e9, "achieved_tflops": fl / (gn_ms * 1e-3) / 1e12,
-                                    "launches_per_step": (lib.neraf_launch_count() - l0) // k_gn,
-                                    "api": "gridnet.ResNet3D_helper(grid).backward(): training-mode batch norm, all parameter gradients"}
+            torch.cuda.synchronize()
+            gn_local = s.elapsed_time(e) / k_gn
+            gn_info = {"gflop": conv_flops(net.backbone_net, n_g) / 1e9,
+                       "launches": (lib.neraf_launch_count() - l0) // k_gn}
             del net, grid
         except Exception as exc:                                   # noqa: BLE001 -- an extra row must not lose the line
-            line["grid_feature"] = {"error": f"{type(exc).__name__}: {exc}"}
+            gn_err = f"{type(exc).__name__}: {exc}"
+        any_failed = max_over_ranks(1.0 if gn_err else 0.0) > 0
+        gn_ms = max_over_ranks(gn_local)
+        if any_failed:
+            line["grid_feature"] = {"error": gn_err or "another rank failed"}
+        else:
+            line["grid_feature"] = {"metric": "grid_net_steps_per_sec", "value": world / (gn_ms * 1e-3), "unit": "step/s",
+                                    "grid": [1, 7, args.grid_net] + [args.grid_net] * 2, "ms_per_step": gn_ms,
+                                    "gflop_per_step": gn_info["gflop"],
+                                    "achieved_tflops": gn_info["gflop"] / 1e3 / (gn_ms * 1e-3),
+                                    "launches_per_step": gn_info["launches"],
+                                    "api": "gridnet.ResNet3D_helper(grid).backward(): training-mode batch norm, all parameter gradients"}
         # the same step captured in ONE CUDA graph (no Python / ctypes between the ~440 launches), timed in a child
         # process: a capture has never run on this path before, and a failure there must not cost this process its line
         if world == 1 and "error" not in line["grid_feature"]:
