@@ -25,7 +25,7 @@ from neraf_b200.gridnet import ResNet3D_helper, Window3d, default_ops
 from oracle import gridnet as og
 from tests.util import cuda, rel_fro
 
-pytestmark = [pytest.mark.gpu]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]     # nothing here takes a minute; a hang must not hold the run
 not_yet_run = pytest.mark.xfail(strict=False, reason="not yet run on a B200 (round-1 GPU budget spent); see the module docstring")
 
 N, GRID_STEP = 64, 1 / 64
