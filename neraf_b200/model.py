@@ -109,10 +109,23 @@ class NeRAFAudioModel(nn.Module):
         return self.field.soundfield[0].weight.device
 
     # ---- grid feature -------------------------------------------------------------------------
+    def reset_grid(self, device=None) -> None:
+        """NeRAF_model.py:269-277: a zero (7, n, n, n) grid over the unit cube with the voxel-centre coordinates in channels
+        4-6 (colour and density, channels 0-3, are written by the pipeline's query_grid_one_batch, which needs the vision
+        field and stays with the reference)."""
+        device = self.device if device is None else device
+        step = self.config.grid_step
+        n = int(1 / step)
+        self.grid = torch.zeros((7, n, n, n), dtype=torch.float32, device=device)
+        axis = torch.arange(step / 2, 1, step)
+        self.grid[4:] = torch.stack(torch.meshgrid(axis, axis, axis, indexing="ij"), dim=0).to(device)
+
     def grid_feature(self) -> Optional[torch.Tensor]:
         """NeRAF_model.py:554-557: resnet3d(grid[None]).flatten()."""
         if not self.use_grid:
             return None
+        if self.grid is None and not isinstance(self.resnet3d, ConstantGridFeature):
+            self.reset_grid()                           # NeRAF_model.py:298-299
         g = self.grid.unsqueeze(0).to(self.device) if self.grid is not None else None
         feat = self.resnet3d(g)
         if isinstance(feat, (list, tuple)):

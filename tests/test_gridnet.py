@@ -411,3 +411,20 @@ def test_16_byte_batchnorm_passes_equal_the_scalar_forms(host_ops):
         gy_s.copy_(gy); x_s.copy_(x)
         host_ops.bn_backward_apply(gy_s, x_s, mean, invstd, gam, sums, training, d_s, None, None)
         assert torch.equal(d_s, d_v)
+
+
+def test_reset_grid_is_the_reference_grid():
+    """NeRAF_model.py:269-277 restated independently: zeros, voxel-centre coordinates in the last three channels."""
+    from neraf_b200.model import NeRAFAudioModel, NeRAFAudioModelConfig
+    for step in (1 / 64, 1 / 128):
+        model = NeRAFAudioModel(NeRAFAudioModelConfig(dataset="RAF", grid_step=step), syn.default_aabb())
+        assert model.grid is None
+        model.reset_grid(device="cpu")
+        n = int(1 / step)
+        assert model.grid.shape == (7, n, n, n) and model.grid.dtype == torch.float32
+        assert torch.count_nonzero(model.grid[:4]) == 0
+        c = (torch.arange(n, dtype=torch.float64) + 0.5) * step
+        assert torch.allclose(model.grid[4, :, 0, 0].double(), c, atol=1e-7)
+        assert torch.allclose(model.grid[5, 3, :, 7].double(), c, atol=1e-7)
+        assert torch.allclose(model.grid[6, 1, 2, :].double(), c, atol=1e-7)
+        assert torch.all(model.grid[4, 5] == model.grid[4, 5, 0, 0]) and torch.all(model.grid[6, :, :, 9] == model.grid[6, 0, 0, 9])
