@@ -120,6 +120,45 @@ class NeRAFAudioModel(nn.Module):
         axis = torch.arange(step / 2, 1, step)
         self.grid[4:] = torch.stack(torch.meshgrid(axis, axis, axis, indexing="ij"), dim=0).to(device)
 
+    def next_grid_batch(self, batch_size: int = 4096) -> torch.Tensor:
+        """The voxel centres the reference's query_grid_one_batch visits next (NeRAF_model.py:198-203, 306-311, 402-404):
+        a cursor over all n^3 centres in (x, y, z) raster order, wrapping at the end.  The caller evaluates its vision
+        field there and hands the result to ``write_grid_cells``."""
+        if self.grid is None:
+            self.reset_grid()
+        if getattr(self, "_grid_centres", None) is None or self._grid_centres.shape[0] != self.grid[0].numel():
+            step = self.config.grid_step
+            axis = torch.arange(step / 2, 1, step)
+            self._grid_centres = torch.stack(torch.meshgrid(axis, axis, axis, indexing="ij"), dim=-1).view(-1, 3)
+            self.grid_batch_i = 0
+        i = self.grid_batch_i
+        batch = self._grid_centres[i:i + batch_size]
+        self.grid_batch_i = 0 if i + batch_size >= self._grid_centres.shape[0] else i + batch_size
+        return batch
+
+    @torch.no_grad()
+    def write_grid_cells(self, batch_coordinates: torch.Tensor, rgb: torch.Tensor, density: torch.Tensor,
+                         rendered_rgb: bool = False, delta: float = 1e-2) -> None:
+        """NeRAF_model.py:372-400: colour (sigmoid of the field's raw rgb unless it was rendered) into channels 0-2 and
+        alpha = clip(1 - exp(-delta density), 0, 1) into channel 3 of the cells the coordinates fall in; points outside
+        the unit cube are dropped.  Invalidates the cached grid feature."""
+        if self.grid is None:
+            self.reset_grid()
+        dev = self.grid.device
+        coords, rgb, density = batch_coordinates.to(dev), rgb.to(dev), density.to(dev)
+        step = self.config.grid_step
+        xs, ys, zs = ((coords[:, i] / step).int() for i in range(3))
+        n = self.grid.shape
+        mask = (xs >= 0) & (xs < n[1]) & (ys >= 0) & (ys < n[2]) & (zs >= 0) & (zs < n[3])
+        xs, ys, zs = xs[mask].long(), ys[mask].long(), zs[mask].long()
+        alpha = torch.clip(1 - torch.exp(-delta * density), 0, 1)[mask]
+        color = (rgb if rendered_rgb else torch.sigmoid(rgb))[mask]
+        self.grid = self.grid.detach()
+        for c in range(3):
+            self.grid[c, xs, ys, zs] = color[:, c].float()
+        self.grid[3, xs, ys, zs] = alpha.float().reshape(-1)
+        self._grid_feature_cache = None
+
     def grid_feature(self) -> Optional[torch.Tensor]:
         """NeRAF_model.py:554-557: resnet3d(grid[None]).flatten()."""
         if not self.use_grid:

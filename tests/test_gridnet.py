@@ -428,3 +428,42 @@ def test_reset_grid_is_the_reference_grid():
         assert torch.allclose(model.grid[5, 3, :, 7].double(), c, atol=1e-7)
         assert torch.allclose(model.grid[6, 1, 2, :].double(), c, atol=1e-7)
         assert torch.all(model.grid[4, 5] == model.grid[4, 5, 0, 0]) and torch.all(model.grid[6, :, :, 9] == model.grid[6, 0, 0, 9])
+
+
+def test_grid_cursor_and_cell_writer_follow_the_reference():
+    """NeRAF_model.py:306-311,372-404 restated with a plain loop: the cursor visits every voxel centre once per sweep, a
+    batch of field outputs lands in the cells its coordinates fall in, points outside the unit cube are dropped."""
+    from neraf_b200.model import NeRAFAudioModel, NeRAFAudioModelConfig
+    step = 1 / 16
+    model = NeRAFAudioModel(NeRAFAudioModelConfig(dataset="RAF", grid_step=step), syn.default_aabb())
+    model.reset_grid(device="cpu")
+    seen = torch.cat([model.next_grid_batch(1000) for _ in range(5)])          # 16^3 = 4096 = 4 * 1000 + 96
+    assert seen.shape == (4096, 3) and model.grid_batch_i == 0
+    assert torch.equal(seen, model.grid[4:].permute(1, 2, 3, 0).reshape(-1, 3))
+    assert torch.equal(model.next_grid_batch(10), seen[:10])                    # wrapped around
+    g = torch.Generator().manual_seed(3)
+    coords = torch.rand(500, 3, generator=g) * 1.2 - 0.1                        # some outside
+    rgb, density = torch.randn(500, 3, generator=g), torch.rand(500, 1, generator=g) * 300
+    before = model.grid.clone()
+    model.write_grid_cells(coords, rgb, density)
+    want = before.clone()
+    for p in range(500):
+        i, j, k = (int(coords[p, a] / step) for a in range(3))                  # .int() truncates toward zero
+        if not all(0 <= v < 16 for v in (i, j, k)):
+            continue
+        want[:3, i, j, k] = torch.sigmoid(rgb[p])
+        want[3, i, j, k] = torch.clip(1 - torch.exp(-1e-2 * density[p, 0]), 0, 1)
+    # cells hit twice keep the last write in both versions only if the order is the same: compare cells hit once
+    idx = torch.stack([(coords[:, a] / step).int() for a in range(3)], 1)
+    ok = ((idx >= 0) & (idx < 16)).all(1)
+    flat = (idx[ok, 0] * 256 + idx[ok, 1] * 16 + idx[ok, 2]).long()
+    once = torch.bincount(flat, minlength=4096) == 1
+    sel = once.view(16, 16, 16)
+    assert torch.allclose(model.grid[:4][:, sel], want[:4][:, sel], atol=1e-7)
+    untouched = torch.bincount(flat, minlength=4096).view(16, 16, 16) == 0
+    assert torch.equal(model.grid[:4][:, untouched], before[:4][:, untouched])
+    assert torch.equal(model.grid[4:], before[4:])
+    model.write_grid_cells(coords[:5], rgb[:5].sigmoid(), density[:5], rendered_rgb=True)
+    i, j, k = (int(coords[0, a] / step) for a in range(3))
+    if all(0 <= v < 16 for v in (i, j, k)):
+        assert torch.allclose(model.grid[:3, i, j, k], rgb[0].sigmoid(), atol=1e-7)
