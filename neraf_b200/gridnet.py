@@ -12,8 +12,11 @@ a 1x1x1 convolution IS a GEMM on the activation matrix and a kxkxk convolution i
 plus a GEMM; with 180 GB of HBM the gathered matrices of a whole 128^3 grid (0.5 GB for the stem) are simply kept for
 the weight-gradient GEMM.  Every contraction -- forward, data gradient, weight gradient (which contracts over the
 voxels, read MN-major from the same row-major matrices) -- runs on the tcgen05 job-list kernel
-(``neraf_gemm_bf16_jobs``); ``precision="fp32"`` uses the CUDA-core GEMM for parity.  Batch normalisation is a strip
-reduction + one elementwise pass fused with the residual add and the ReLU; its backward is the same two passes.
+(``neraf_gemm_bf16_jobs``); the two gradients of a convolution go out as ONE job list, with the weight gradient split
+over the voxels (split-K) so that its few output tiles occupy all SMs; ``precision="fp32"`` uses the CUDA-core GEMM for
+parity.  The bf16 stem runs on a channels-last copy of the grid padded from 7 to 8 channels, so every gather moves
+16-byte words.  Batch normalisation is a strip reduction + one elementwise pass fused with the residual add and the
+ReLU; its backward is the same two passes.
 
 There is no PyTorch/CPU fallback: the module raises without the library or on CPU tensors.  (``GridOps`` is the one
 seam: tests/test_gridnet.py substitutes a host build of the very same per-element code, csrc/gridnet_core.h, to check
