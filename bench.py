@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--gl-rirs", type=int, default=2072, help="RIRs per Griffin-Lim launch (0 disables); 2072 = 14 per SM")
     ap.add_argument("--large-batch", type=int, default=16384, help="extra large-batch point of the sweep (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--loss-columns", type=int, default=65536,
+                    help="columns of the stand-alone spectral-loss timing (K2's HBM roofline: at the training batch the "
+                         "kernels are launch-latency sized); 0 disables")
     ap.add_argument("--grid-net", type=int, default=128,
                     help="also time the grid-feature producer (ResNet3D-50 training-mode fwd+bwd, SURVEY 8f row 1) on an "
                          "N^3 grid (the reference's grid is 128^3); 0 disables")
@@ -500,6 +503,60 @@ def main():
                                     "api": "neraf_b200.metrics.acoustic_metrics(device waveforms) -> T60, EDT, C50 on the host",
                                     "d2h_bytes_per_call": sum(v.numel() * 8 for v in host_m.values())}
         del wd
+
+    # ---- spectral loss alone at a size where it is bandwidth- and not latency-sized ("measure at 64 k too"):
+    # forward = sums + finalize in one launch (8 B / element read), backward = gradient (8 B read + 4 B written);
+    # pred and gt (2 x 134 MB at 65 536 RAF columns) are larger than L2, so every launch streams from HBM
+    if args.loss_columns > 0:
+        sl, sl_err = (-1.0, -1.0), None
+        try:
+            n_el = args.loss_columns * shape.C * shape.F
+            pred_l = torch.randn(n_el, device=dev) * 1.5 - 3.0
+            gt_l = torch.randn(n_el, device=dev) * 1.5 - 3.0
+            scratch_l = torch.zeros(5, dtype=torch.float64, device=dev)
+            losses_l = torch.zeros(2, dtype=torch.float32, device=dev)
+            dpred_l = torch.empty_like(pred_l)
+            crit, st = _lib.CRITERIA["SC+SLMSE"], _lib.stream_ptr(dev)
+
+            def loss_fwd():
+                _lib.check(lib.neraf_spectral_loss_forward(pred_l.data_ptr(), gt_l.data_ptr(), n_el, crit, 1e-4, 1e-3,
+                                                           scratch_l.data_ptr(), losses_l.data_ptr(), st))
+
+            def loss_bwd():
+                _lib.check(lib.neraf_spectral_loss_backward(pred_l.data_ptr(), gt_l.data_ptr(), n_el, n_el, crit,
+                                                            scratch_l.data_ptr(), None, None, 1e-4, 1e-3,
+                                                            dpred_l.data_ptr(), st))
+            out_ms = []
+            for fn in (loss_fwd, loss_bwd):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(20):
+                    fn()
+                e.record()
+                torch.cuda.synchronize()
+                out_ms.append(s.elapsed_time(e) / 20)
+            sl = tuple(out_ms)
+            del pred_l, gt_l, dpred_l
+        except Exception as exc:                                   # noqa: BLE001 -- an extra row must not lose the line
+            sl_err = f"{type(exc).__name__}: {exc}"
+        sl_failed = max_over_ranks(1.0 if sl_err else 0.0) > 0
+        f_ms, b_ms = max_over_ranks(sl[0]), max_over_ranks(sl[1])
+        if sl_failed:
+            line["spectral_loss"] = {"error": sl_err or "another rank failed"}
+        else:
+            n_el = args.loss_columns * shape.C * shape.F
+            f_gbs, b_gbs = 8.0 * n_el / (f_ms * 1e-3) / 1e9, 12.0 * n_el / (b_ms * 1e-3) / 1e9
+            line["spectral_loss"] = {
+                "columns_per_gpu": args.loss_columns, "elements_per_gpu": n_el,
+                "forward": {"ms": f_ms, "bytes_per_element": 8, "gbs": f_gbs, "frac": f_gbs / peaks["hbm_gbs"]},
+                "backward": {"ms": b_ms, "bytes_per_element": 12, "gbs": b_gbs, "frac": b_gbs / peaks["hbm_gbs"]},
+                "roofline": {"bound": "hbm", "achieved": f_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": f_gbs / peaks["hbm_gbs"], "traffic": None,
+                             "note": "neraf_spectral_loss_forward (pred + gt read once, fp64 accumulation), 20 back-to-back "
+                                     "launches on inputs larger than L2; per GPU"}}
 
     # ---- grid-feature producer: one training-mode forward + backward of ResNet3D-50 on a (1, 7, N, N, N) grid
     if args.grid_net > 0:
