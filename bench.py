@@ -224,7 +224,7 @@ def main():
     model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
     model = model.to(dev)
     model.field.always_repack = True          # training semantics: parameters change every step -> bf16 re-pack in every step
-    params = [p for p in model.parameters() if p.requires_grad]
+    params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
     reducer = GradientAllReduce(params, group)
 
     B = args.batch

@@ -836,9 +836,7 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   }
   int units = sm_count() / 2;
   if (max_ctas >= 2 && max_ctas / 2 < units) units = max_ctas / 2;   // leave SMs to a concurrent kernel (collectives)
-  const int grid = (tile < units ? tile : units) * 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(MEGA_THREADS);
   cfg.dynamicSmemBytes = MEGA_SMEM_BYTES;
   cfg.stream = stream;
@@ -846,6 +844,20 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  // The CTA pairs spin on counters other pairs write, with a static tile stride: every pair of the grid must be
+  // co-resident.  Never launch more pairs than the device can hold at once for this kernel's footprint (asked once
+  // per device; an SM held by a concurrent kernel at run time is the caller's business: max_ctas).
+  static int resident_pairs[64] = {0};
+  if (dev >= 0 && dev < 64 && resident_pairs[dev] == 0) {
+    cfg.gridDim = dim3((unsigned)(units * 2));
+    int n = 0;
+    NERAF_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, umma_mega_kernel, &cfg));
+    NERAF_REQUIRE(n > 0, "mega_run: no CTA pair of the job-list kernel fits on this device");
+    resident_pairs[dev] = n;
+  }
+  if (dev >= 0 && dev < 64 && resident_pairs[dev] < units) units = resident_pairs[dev];
+  const int grid = (tile < units ? tile : units) * 2;
+  cfg.gridDim = dim3((unsigned)grid);
   NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_mega_kernel, P));
   NERAF_CHECK_LAUNCH("umma_mega_kernel");
   if (trace_path) {

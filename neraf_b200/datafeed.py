@@ -46,8 +46,8 @@ class EpochSampler:
 
     def __init__(self, n: int, batch_size: int, seed: int = 0, rank: int = 0, world_size: int = 1,
                  drop_last: bool = False):
-        if n <= 0 or batch_size <= 0 or not (0 <= rank < world_size):
-            raise ValueError("EpochSampler: need n > 0, batch_size > 0 and 0 <= rank < world_size")
+        if n < world_size or batch_size <= 0 or not (0 <= rank < world_size):
+            raise ValueError("EpochSampler: need n >= world_size > rank >= 0 and batch_size > 0")
         self.n, self.batch_size, self.seed, self.rank, self.world_size = n, batch_size, seed, rank, world_size
         self.drop_last = drop_last
         self.epoch, self.cursor = 0, 0
@@ -58,15 +58,21 @@ class EpochSampler:
         return torch.randperm(self.n, generator=g)
 
     def next_range(self) -> Tuple[int, int, int]:
-        """(epoch, lo, hi): this rank's rows of the next global batch are permutation(epoch)[lo:hi]."""
+        """(epoch, lo, hi): this rank's rows of the next global batch are permutation(epoch)[lo:hi].
+
+        Every rank always gets the SAME number of rows: the data-parallel loss normalises by ``n_local * world_size``
+        (loss.py) and a rank with an empty shard would never reach its collectives.  A partial last global batch of r
+        rows is therefore cut into ``r // world_size`` rows per rank (the ``r % world_size`` < world_size samples left
+        over are skipped for this epoch), and dropped altogether when that is zero."""
         gb = self.batch_size * self.world_size
-        if self.cursor >= self.n or (self.drop_last and self.cursor + gb > self.n and self.cursor > 0):
+        rem = self.n - self.cursor
+        if rem <= 0 or (rem < gb and self.cursor > 0 and (self.drop_last or rem < self.world_size)):
             self.epoch, self.cursor = self.epoch + 1, 0
-        end = min(self.cursor + gb, self.n)
-        lo = min(self.cursor + self.rank * self.batch_size, end)
-        hi = min(lo + self.batch_size, end)
+            rem = self.n
+        per = self.batch_size if rem >= gb else rem // self.world_size
+        lo = self.cursor + self.rank * per
         self.cursor += gb
-        return self.epoch, lo, hi
+        return self.epoch, lo, lo + per
 
 
 class ResidentAudioFeed:

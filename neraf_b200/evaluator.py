@@ -25,7 +25,15 @@ class _Evaluator:
 
     def __init__(self, fs: int, device=None):
         self.fs = fs
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._device = None if device is None else torch.device(device)
+
+    @property
+    def device(self) -> torch.device:
+        """Where the waveforms are measured: the constructor's device, else the current CUDA device -- resolved on first
+        use, so that the model can build its evaluator on a host without a GPU (NeRAF_model.py:130,134)."""
+        if self._device is None:
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return self._device
 
     # -- N RIRs at once ----------------------------------------------------------------------------
     def get_full_metrics_batch(self, wav_gt_ff, wav_pred_istft, log_gt=None) -> List[Dict[str, float]]:

@@ -80,6 +80,9 @@ class _FieldFn(torch.autograd.Function):
         if need_grad:
             ctx.module, ctx.dims, ctx.prec, ctx.B, ctx.n_enc = module, dims, prec, B, n_enc
             ctx.ws, ctx.pack, ctx.grid_c = ws, pack, grid_c
+            # the bf16 operand copies are shared by every forward of this module: remember which parameter versions
+            # they were derived from, the data gradient must read the same ones
+            ctx.pack_sig = None if pack is None else module._pack_cache[(dims.n_grid, prec, weights[0].device)][0]
             ctx.enc_given = enc is not None
             ctx.save_for_backward(out, *params)
         return out
@@ -87,10 +90,19 @@ class _FieldFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout: torch.Tensor):
         lib = _lib.lib()
+        if ctx.ws is None:
+            raise RuntimeError("the field's saved activations were released by a previous backward (retain_graph is not "
+                               "supported: run the forward again)")
         out, *params = ctx.saved_tensors
         n_layers = len(params) // 2
         weights = list(params[:n_layers])
         dev = out.device
+        if ctx.pack_sig is not None:
+            hit = ctx.module._pack_cache.get((ctx.dims.n_grid, ctx.prec, weights[0].device))
+            if hit is None or hit[0] != ctx.pack_sig or hit[1] is not ctx.pack:
+                raise RuntimeError("the field's bf16 operand copies were re-derived from different parameter values "
+                                   "between this forward and its backward (a parameter changed without its backward "
+                                   "having run): run the forward again")
         dout_c = dout.contiguous().float()
         # one flat gradient buffer: weights first (their sizes keep every view 16-byte aligned), then the bias
         # gradients and dgrid back to back so that the library zeroes them with a single memset

@@ -1,24 +1,32 @@
 """Host-side mirror of the reference audio model for the acoustic-field hot path.
 
-``NeRAFAudioModel`` keeps the method surface the nerfstudio pipeline calls
-(/root/reference/NeRAF/NeRAF_pipeline.py:188,191,248-250,279-280,362-364):
-``get_outputs(batch_audio)``, ``get_loss_dict(outputs, batch, metrics_dict)``,
-``get_outputs_for_camera(camera, obb_box, batch_audio)``, ``get_image_metrics_and_images``,
-``get_param_groups`` and the attributes ``field``, ``grid``, ``resnet3d``, ``istft_transform``,
-``max_len``, ``mic_ch`` -- with every tensor operation of the hot path executed by the CUDA library.
+``NeRAFAudioModel`` is a drop-in for the reference class of the same name (/root/reference/NeRAF/NeRAF_model.py:104-805)
+as the unmodified pipeline drives it (NeRAF_pipeline.py:135-150, 186-191, 244-252, 276-281, 355-364, 438-455, 477-497):
 
-nerfstudio is not a dependency: the class derives from ``nn.Module``; INTEGRATION.md shows the
-three-line subclass that plugs it into a real nerfstudio ``Model``.  The scene-grid feature producer is either the
-reference's ResNet3D-50 on the library (``config.grid_net = "resnet50"`` builds ``gridnet.ResNet3D_helper`` exactly
-as NeRAF_model.py:185 does), a learnable constant vector (``"constant"``, the default until the producer's launch code
-has run on a B200 -- DESIGN.md section 9), or any ``nn.Module`` passed as ``resnet3d``.
+* constructed by ``config.audio_model.setup(scene_box=..., num_train_data=..., device=...)`` -> ``Model.__init__(config,
+  scene_box, num_train_data, **kwargs)`` -> ``populate_modules()`` (NeRAF_model.py:121-219);
+* ``get_outputs(batch_audio)``, ``get_loss_dict(outputs, batch, metrics_dict)``, ``get_metrics_dict(outputs, batch)``,
+  ``set_eval_data(...)``, ``get_outputs_for_camera(camera, obb_box, batch_audio)``,
+  ``get_image_metrics_and_images(outputs, batch) -> (metrics_dict, images_dict)``, ``get_param_groups()``,
+  ``update_to_step(step)``; attributes ``field``, ``grid``, ``resnet3d``, ``istft_transform``, ``evaluator``,
+  ``spatial_distortion``, ``max_len``, ``mic_ch``, ``scene_box``
+
+-- with every tensor operation of the hot path executed by the CUDA library.
+
+Base class: nerfstudio's ``Model`` / ``ModelConfig`` when nerfstudio is importable (the class then IS a nerfstudio
+model and the switch in NeRAF_config.py is one import); otherwise the restatement below of the few lines of
+``nerfstudio/models/base_model.py`` the pipeline relies on [RECALLED: nerfstudio 1.x] -- same constructor, same
+``populate_modules`` hook, same ``device`` property and ``device_indicator_param``.  The scene-grid feature producer is
+the reference's ResNet3D-50 on the library (``config.grid_net = "resnet50"``, the default: NeRAF_model.py:185), a
+learnable constant vector (``"constant"``), or any ``nn.Module`` passed as ``resnet3d=``.
 """
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass
-from typing import Dict, Optional
+from dataclasses import dataclass, field as dc_field
+from typing import Any, Dict, List, Optional, Tuple, Type
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -27,10 +35,67 @@ from .field import N_ENC, NeRAFAudioSoundField
 from .griffinlim import GriffinLim
 from .loss import spectral_loss
 
+try:                                                      # the real base classes whenever nerfstudio is installed
+    from nerfstudio.models.base_model import Model as _ModelBase, ModelConfig as _ModelConfigBase
+    HAVE_NERFSTUDIO = True
+except Exception:                                         # noqa: BLE001 - absent (this image) or broken install
+    HAVE_NERFSTUDIO = False
+
+    @dataclass
+    class _ModelConfigBase:
+        """nerfstudio ``InstantiateConfig``: ``setup(**kwargs)`` builds ``_target(config, **kwargs)``."""
+        _target: Type = dc_field(default_factory=lambda: _ModelBase)
+
+        def setup(self, **kwargs) -> Any:
+            return self._target(self, **kwargs)
+
+    class _ModelBase(nn.Module):
+        """The part of nerfstudio's ``Model`` the pipeline uses: constructor -> ``populate_modules``; ``device`` from an
+        empty parameter (it is in the reference's checkpoints as ``audio_model.device_indicator_param``)."""
+
+        def __init__(self, config, scene_box, num_train_data: int = 0, **kwargs) -> None:
+            super().__init__()
+            self.config = config
+            self.scene_box = scene_box
+            self.render_aabb = None
+            self.num_train_data = num_train_data
+            self.kwargs = kwargs
+            self.collider = None
+            self.populate_modules()
+            self.callbacks = None
+            self.device_indicator_param = nn.Parameter(torch.empty(0))
+
+        @property
+        def device(self):
+            return self.device_indicator_param.device
+
+        def populate_modules(self):
+            pass
+
+        def get_training_callbacks(self, training_callback_attributes=None) -> List:
+            return []
+
+        def forward(self, ray_bundle):
+            return self.get_outputs(ray_bundle)
+
+        def update_to_step(self, step: int) -> None:
+            pass
+
+        def load_model(self, loaded_state: Dict[str, Any]) -> None:
+            state = {k.replace("module.", ""): v for k, v in loaded_state["model"].items()}
+            self.load_state_dict(state)
+
 
 @dataclass
-class NeRAFAudioModelConfig:
-    """Same fields and defaults as the reference config (NeRAF_model.py:82-101) + ``precision``."""
+class SceneBox:
+    """Stand-in for ``nerfstudio.data.scene_box.SceneBox`` where only ``.aabb`` (2, 3) is read (NeRAF_model.py:541)."""
+    aabb: torch.Tensor
+
+
+@dataclass
+class NeRAFAudioModelConfig(_ModelConfigBase):
+    """Same fields and defaults as the reference config (NeRAF_model.py:82-101) + ``precision`` and ``grid_net``."""
+    _target: Type = dc_field(default_factory=lambda: NeRAFAudioModel)
     dataset: str = "SoundSpaces"
     use_grid: bool = True
     grid_step: float = 1 / 128
@@ -45,7 +110,7 @@ class NeRAFAudioModelConfig:
     hop_len: int = 128
     win_len: int = 512
     precision: str = "bf16"          # "bf16": tcgen05 tensor cores; "fp32": CUDA-core parity path
-    grid_net: str = "constant"       # "resnet50": the reference's ResNet3D_helper (gridnet.py); "constant": a vector
+    grid_net: str = "resnet50"       # "resnet50": the reference's ResNet3D_helper (NeRAF_model.py:185); "constant": a vector
 
 
 class ConstantGridFeature(nn.Module):
@@ -59,22 +124,84 @@ class ConstantGridFeature(nn.Module):
         return self.feature
 
 
-class NeRAFAudioModel(nn.Module):
-    def __init__(self, config: NeRAFAudioModelConfig, aabb: torch.Tensor, resnet3d: Optional[nn.Module] = None,
-                 grid: Optional[torch.Tensor] = None, process_group=None):
+class _QueryEncoding(nn.Module):
+    """Place-holder for the reference's encoder modules (``time_encoding`` / ``position_encoding`` / ``rot_encoding``,
+    NeRAF_model.py:158-171): the arithmetic lives in the library's prep kernel; what the plugin reads from these objects
+    is ``get_out_dim()`` (:169-171) and ``parameters()`` (:733-736, none that hold values)."""
+
+    def __init__(self, in_dim: int, out_dim: int, tcnn_params: bool = False):
         super().__init__()
-        self.config = config
+        self.in_dim, self.out_dim = in_dim, out_dim
+        if tcnn_params:
+            # tcnn modules register an (empty, for a parameter-free encoding) ``params`` tensor: the key
+            # ``rot_encoding.tcnn_encoding.params`` of the reference's checkpoints [RECALLED: tinycudann/modules.py]
+            self.tcnn_encoding = nn.Module()
+            self.tcnn_encoding.params = nn.Parameter(torch.zeros(0))
+
+    def get_out_dim(self) -> int:
+        return self.out_dim
+
+    def forward(self, x):
+        raise _lib.NerafError("the encodings are fused into the field's first layer: call NeRAFAudioModel.get_outputs or "
+                              "neraf_b200.field.encode_queries")
+
+
+_VIRIDIS = np.array([[0x44, 0x01, 0x54], [0x48, 0x28, 0x78], [0x3e, 0x49, 0x89], [0x31, 0x68, 0x8e], [0x26, 0x82, 0x8e],
+                     [0x1f, 0x9e, 0x89], [0x35, 0xb7, 0x79], [0x6e, 0xce, 0x58], [0xb5, 0xde, 0x2b], [0xfd, 0xe7, 0x25]],
+                    dtype=np.float64) / 255.0
+
+
+def _viridis(v: np.ndarray) -> np.ndarray:
+    """``matplotlib.cm.viridis(v)[..., :3]`` (NeRAF_model.py:781-790; display only).  matplotlib's table when it is
+    importable, else a linear interpolation of the palette's ten published anchor colours."""
+    try:
+        from matplotlib import cm
+        return cm.viridis(v)[..., :3]
+    except Exception:                                     # noqa: BLE001 - matplotlib is not in the build image
+        x = np.clip(np.nan_to_num(np.asarray(v, dtype=np.float64)), 0.0, 1.0) * (len(_VIRIDIS) - 1)
+        i = np.minimum(x.astype(np.int64), len(_VIRIDIS) - 2)
+        f = (x - i)[..., None]
+        return _VIRIDIS[i] * (1 - f) + _VIRIDIS[i + 1] * f
+
+
+class NeRAFAudioModel(_ModelBase):
+    """NeRAF_model.py:104-805.  ``NeRAFAudioModel(config, scene_box, num_train_data, **kwargs)``; ``scene_box`` is
+    anything with an ``.aabb`` (2, 3) tensor -- or that tensor itself.  Keyword extras (kept in ``self.kwargs`` like
+    nerfstudio does): ``resnet3d=`` (a ready producer module), ``grid=`` (an initial (7, n, n, n) grid),
+    ``process_group=`` (data parallel: global spectral-convergence sums), ``device=`` (ignored here as in nerfstudio:
+    the pipeline calls ``.to(device)``)."""
+
+    config: NeRAFAudioModelConfig
+
+    def __init__(self, config: NeRAFAudioModelConfig, scene_box, num_train_data: int = 0, **kwargs):
+        if torch.is_tensor(scene_box):
+            scene_box = SceneBox(aabb=scene_box.detach().float().reshape(2, 3).clone())
+        super().__init__(config, scene_box, num_train_data, **kwargs)
+
+    def default_RAF_config(self):                           # NeRAF_model.py:109-119
+        self.config.fs = 48000
+        self.config.max_len = 0.32
+        if self.config.fs == 48000:
+            self.config.N_freq_stft, self.config.hop_len, self.config.win_len = 513, 256, 512
+        elif self.config.fs == 16000:
+            self.config.N_freq_stft, self.config.hop_len, self.config.win_len = 257, 128, 256
+
+    def populate_modules(self):
+        """NeRAF_model.py:121-219 (without the viewer widgets, :215-219)."""
+        super().populate_modules()
+        from .evaluator import RAFEvaluator, SoundSpacesEvaluator
+        config = self.config
+        kwargs = getattr(self, "kwargs", {})
         self.dataset = config.dataset
-        if self.dataset == "RAF":                       # default_RAF_config, NeRAF_model.py:109-119
-            config.fs = 48000
-            config.max_len = 0.32
-            if config.fs == 48000:
-                config.N_freq_stft, config.hop_len, config.win_len = 513, 256, 512
+        if self.dataset == "RAF":
+            self.default_RAF_config()
             self.max_len = int(config.max_len * config.fs) // config.hop_len
             self.mic_ch = 1
+            self.evaluator = RAFEvaluator(fs=config.fs)
         else:
             self.max_len = int(config.max_len)
             self.mic_ch = 2
+            self.evaluator = SoundSpacesEvaluator(fs=config.fs)
         self.use_grid = config.use_grid
         self.loss_factor = config.loss_factor
         self.criterion_name = config.criterion
@@ -82,10 +209,22 @@ class NeRAFAudioModel(nn.Module):
             raise ValueError(f"unknown criterion {self.criterion_name}")
         self.istft_transform = GriffinLim(n_fft=(config.N_freq_stft - 1) * 2, win_length=config.win_len,
                                           hop_length=config.hop_len, power=1)
-        self.register_buffer("aabb", aabb.detach().float().reshape(2, 3).clone(), persistent=False)
-        self.process_group = process_group               # DP: global spectral-convergence sums
+        self.spatial_distortion = None                       # injected by the pipeline (NeRAF_pipeline.py:143)
+        self.time_encoding = _QueryEncoding(1, 21)
+        self.position_encoding = _QueryEncoding(3, 63)
+        self.rot_encoding = _QueryEncoding(3, 16, tcnn_params=True)
+        self.input_ch_time = self.time_encoding.get_out_dim()
+        self.input_ch_pose = self.position_encoding.get_out_dim()
+        self.input_ch_rot = self.rot_encoding.get_out_dim()
+        self.register_buffer("aabb", torch.as_tensor(self.scene_box.aabb).detach().float().reshape(2, 3).clone(),
+                             persistent=False)
+        self.process_group = kwargs.get("process_group")     # DP: global spectral-convergence sums
         n_grid = config.N_features if self.use_grid else 0
         if self.use_grid:
+            self.grid_size = np.array([0, 1, 0, 1, 0, 1])
+            self.grid_step = config.grid_step
+            self.N_features = config.N_features
+            resnet3d = kwargs.get("resnet3d")
             if resnet3d is not None:
                 self.resnet3d = resnet3d
             elif config.grid_net == "constant":
@@ -97,16 +236,17 @@ class NeRAFAudioModel(nn.Module):
                                                 precision=config.precision)
             else:
                 raise ValueError(f"unknown grid_net {config.grid_net!r}")
-            self.grid = grid                             # plain attribute like the reference (NeRAF_pipeline.py:451-455)
+            self.grid_size_after_resnet = config.N_features
+            self._delta = 1e-2
+            self.grid_batch_i = 0
+            self.grid = kwargs.get("grid")               # plain attribute like the reference (NeRAF_pipeline.py:451-455);
+                                                         # None forces the reset on first use (NeRAF_model.py:203)
         self.field = NeRAFAudioSoundField(n_grid + N_ENC, config.W_field, sound_rez=self.mic_ch,
                                           N_frequencies=config.N_freq_stft, precision=config.precision)
+        self.eval_source_pose = self.eval_mic_pose = self.eval_rot = self.eval_gt = None      # :209-213
         self._grid_feature_cache = None
         self._prefetch = None          # (host tensor, device copy, ready event) of batch['data'], see get_outputs
         self._copy_stream = None
-
-    @property
-    def device(self) -> torch.device:
-        return self.field.soundfield[0].weight.device
 
     # ---- grid feature -------------------------------------------------------------------------
     def reset_grid(self, device=None) -> None:
@@ -159,8 +299,9 @@ class NeRAFAudioModel(nn.Module):
         self.grid[3, xs, ys, zs] = alpha.float().reshape(-1)
         self._grid_feature_cache = None
 
-    def grid_feature(self) -> Optional[torch.Tensor]:
-        """NeRAF_model.py:554-557: resnet3d(grid[None]).flatten()."""
+    def grid_feature(self, sync_gradient: bool = True) -> Optional[torch.Tensor]:
+        """NeRAF_model.py:554-557: resnet3d(grid[None]).flatten().  ``sync_gradient=False``: the caller hands the producer a
+        feature gradient that is already summed over the ranks (GraphedTrainStep under data parallelism)."""
         if not self.use_grid:
             return None
         if self.grid is None and not isinstance(self.resnet3d, ConstantGridFeature):
@@ -170,7 +311,8 @@ class NeRAFAudioModel(nn.Module):
         if isinstance(feat, (list, tuple)):
             feat = feat[-1]
         feat = feat.flatten()
-        if self.process_group is not None and feat.requires_grad and not isinstance(self.resnet3d, ConstantGridFeature):
+        if (sync_gradient and self.process_group is not None and feat.requires_grad
+                and not isinstance(self.resnet3d, ConstantGridFeature)):
             # data parallel: the producer is replicated and its backward is linear in dg, so dg (N_features floats) is
             # summed over the ranks here and the producer's own gradients come out global on every rank
             from .distributed import sum_gradient_across_ranks
@@ -218,8 +360,28 @@ class NeRAFAudioModel(nn.Module):
                                 self.process_group)
         return {"audio_sc_loss": sc, "audio_mag_loss": mag}
 
-    def get_param_groups(self):
-        params = list(self.field.parameters())
+    def get_metrics_dict(self, outputs: torch.Tensor, batch: Dict[str, torch.Tensor]):
+        """NeRAF_model.py:568-582 (called on eval batches, NeRAF_pipeline.py:249): magnitudes clip(e^x - 1e-3, 0, 1e4) of
+        prediction and target -> ``evaluator.get_stft_metrics``.  Computed where the prediction lives (the reference moves
+        it to the host first)."""
+        with torch.no_grad():
+            predicted = outputs.detach().float()
+            gt = batch["data"].to(device=predicted.device, dtype=torch.float32)
+            mag_prd = torch.clip(torch.exp(predicted) - 1e-3, 0.0, 10000.0)
+            mag_gt = torch.clip(torch.exp(gt) - 1e-3, 0.0, 10000.0)
+            return self.evaluator.get_stft_metrics(mag_prd, mag_gt)
+
+    def set_eval_data(self, eval_source_pose, eval_mic_pose, eval_rot, eval_gt):
+        """NeRAF_model.py:602-608 (NeRAF_pipeline.py:147,461)."""
+        self.eval_source_pose = eval_source_pose
+        self.eval_mic_pose = eval_mic_pose
+        self.eval_rot = eval_rot
+        self.eval_gt = eval_gt
+
+    def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
+        """NeRAF_model.py:730-737: field + (parameter-free) encoders + the grid-feature producer."""
+        params = (list(self.field.parameters()) + list(self.rot_encoding.parameters())
+                  + list(self.position_encoding.parameters()) + list(self.time_encoding.parameters()))
         if self.use_grid:
             params += list(self.resnet3d.parameters())
         return {"audio_fields": params}
@@ -269,35 +431,54 @@ class NeRAFAudioModel(nn.Module):
         """Eval branch of NeRAF_model.py:610-728 (camera=None): one RIR, keys as in the reference."""
         if camera is not None:
             raise NotImplementedError("viewer cameras need nerfstudio; pass batch_audio (the ns-eval path)")
+        self.set_eval_data(batch_audio["mic_pose"], batch_audio["source_pose"], batch_audio["rot"],
+                           batch_audio.get("data"))                                                  # :653 (swapped there too)
         y = self.query_rirs(batch_audio["mic_pose"], batch_audio["source_pose"], batch_audio["rot"])[0]   # (T, C, F)
         stft = {}
         for ch in range(y.shape[1]):
             stft[f"stft_ch_{ch}"] = torch.flip(y[:, ch, :].transpose(0, 1).unsqueeze(-1).cpu(), [0])
-        gt = batch_audio.get("data")
+        gt = self.eval_gt
         if gt is not None:
+            gt = torch.as_tensor(gt)
             for ch in range(gt.shape[0]):
                 stft[f"gt_ch_{ch}"] = torch.flip(gt[ch].unsqueeze(-1).cpu(), [0])
                 stft[f"comparison_ch_{ch}"] = torch.cat([stft[f"stft_ch_{ch}"], stft[f"gt_ch_{ch}"]], dim=1)
+            if self.use_grid and self.grid is not None:                                              # :713-720
+                stft["grid"] = self.grid[0:3].mean(dim=3).permute(1, 2, 0).to(self.device)
+                stft["grid_density"] = self.grid[3].mean(dim=2).unsqueeze(-1).to(self.device)
         stft["raw_output"] = y
         return stft
 
     @torch.no_grad()
-    def get_image_metrics_and_images(self, outputs: Dict, batch: Dict, evaluator=None):
-        """NeRAF_model.py:739-760: Griffin-Lim on prediction AND ground truth (one batched launch), then the
-        CPU acoustic metrics of the supplied evaluator (``evaluator.get_full_metrics`` signature of the reference)."""
+    def get_image_metrics_and_images(self, outputs: Dict, batch: Dict) -> Tuple[Dict[str, float], Dict[str, torch.Tensor]]:
+        """NeRAF_model.py:739-805 -> ``(metrics_dict, images_dict)``: Griffin-Lim on ground truth AND prediction (one
+        batched launch instead of two calls), ``self.evaluator.get_full_metrics`` with the reference's seven arguments
+        (the waveforms stay on the device; the evaluator measures them there), and the display images."""
         dev = self.device
         stft = outputs["raw_output"].permute(1, 2, 0)                       # (C, F, T)
-        data = batch["data"].to(dev)
+        data = torch.as_tensor(batch["data"]).to(dev, torch.float32)
         mag_prd = torch.clip(torch.exp(stft) - 1e-3, 0.0, 10000.0)
         mag_gt = torch.clip(torch.exp(data) - 1e-3, 0.0, 10000.0)
         waves = self.istft_transform(torch.stack([mag_gt, mag_prd]))         # (2, C, L)
-        wav_istft_gt, wav_istft_prd = waves[0].cpu().numpy(), waves[1].cpu().numpy()
-        out = {"wav_istft_gt": wav_istft_gt, "wav_istft_prd": wav_istft_prd}
-        if evaluator is not None:
-            out["metrics"] = evaluator.get_full_metrics(mag_prd.cpu().numpy(), mag_gt.cpu().numpy(),
-                                                        batch["waveform"].cpu().numpy(), wav_istft_prd, wav_istft_gt,
-                                                        stft.cpu().numpy(), data.cpu().numpy())
-        return out
+        wav_gt = torch.as_tensor(batch["waveform"])
+        metrics_dict = self.evaluator.get_full_metrics(mag_prd, mag_gt, wav_gt, waves[1], waves[0], stft, data)
+        images_dict: Dict[str, torch.Tensor] = {}
+        ids = [k.replace("gt_ch_", "") for k in outputs if k.startswith("gt_ch_")]
+        if ids:
+            lo = min(float(outputs["gt_ch_" + i].min()) for i in ids)
+            hi = max(float(outputs["gt_ch_" + i].max()) for i in ids)
+            span = (hi - lo) if hi > lo else 1.0
+            for i in ids:
+                v = _viridis(((outputs["stft_ch_" + i] - lo) / span).cpu().numpy().squeeze(-1))
+                g = _viridis(((outputs["gt_ch_" + i] - lo) / span).cpu().numpy().squeeze(-1))
+                images_dict["comparison_ch_" + i] = torch.from_numpy(np.concatenate([v, g], axis=1))
+        if self.use_grid and "grid" in outputs:
+            images_dict["grid"] = outputs["grid"]
+            d = outputs["grid_density"]
+            rng = float(d.max() - d.min())
+            d = (d - d.min()) / (rng if rng > 0 else 1.0)
+            images_dict["grid_density"] = torch.from_numpy(_viridis(d.cpu().numpy().squeeze(-1)))
+        return metrics_dict, images_dict
 
 
 class GraphedTrainStep:
@@ -369,15 +550,14 @@ class GraphedTrainStep:
         self.static = views(self._static_bytes)
         for k in keys:
             self.static[k].copy_(example_batch[k].to(device=dev, dtype=dtypes[k]))
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]   # not the empty marker parameters
         self.group = model.process_group
-        functional_ok = (not model.use_grid) or isinstance(model.resnet3d, ConstantGridFeature)
         if functional is None:
-            functional = functional_ok
+            functional = True
         if not functional and self.group is not None:
             raise ValueError("the data-parallel step is built from direct library calls (functional=True)")
         if not functional:
-            self._capture_autograd(warmup)      # a trainable ResNet3D producer: gradients flow on through autograd
+            self._capture_autograd(warmup)      # the plugin's autograd calls, captured as they are
         else:
             self._capture_functional(warmup)
 
@@ -421,12 +601,19 @@ class GraphedTrainStep:
         field = model.field
         if field.precision != "bf16" and field.precision != "fp32":
             raise ValueError("unknown precision")
-        if model.use_grid and not isinstance(model.resnet3d, ConstantGridFeature):
-            raise NotImplementedError("the two-graph data-parallel step needs a ConstantGridFeature grid producer "
-                                      "(an arbitrary ResNet3D is trained through autograd: use the eager calls)")
         lib = _lib.lib()
         weights, biases = field._param_lists()
-        grid_p = model.resnet3d.feature if model.use_grid else None
+        # A real grid-feature producer (the ResNet3D) stays an autograd module around the field's direct calls: its
+        # output is copied into a static vector the field reads, and the dg the field returns drives its backward --
+        # inside the same graph (single process), or eagerly around the two graphs (data parallel: dg is formed from
+        # the REDUCED db1 after the gradient exchange, so it is global and the producer's gradients need no exchange).
+        self._producer = model.resnet3d if (model.use_grid and not isinstance(model.resnet3d, ConstantGridFeature)) else None
+        self._feat = None
+        if self._producer is not None:
+            self._g_static = torch.zeros(model.config.N_features, dtype=torch.float32, device=dev)
+            grid_p = self._g_static
+        else:
+            grid_p = model.resnet3d.feature if model.use_grid else None
         n_grid = 0 if grid_p is None else grid_p.numel()
         dims = field._dims(n_grid)
         prec = _lib.PRECISIONS[field.precision]
@@ -481,8 +668,10 @@ class GraphedTrainStep:
             dgrid = parts[first_b + n_b].view_as(grid_p) if tail_grid else torch.zeros_like(grid_p)
         if defer:
             dws = [torch.zeros_like(weights[0])] + dws
-        order = list(weights) + list(biases) + ([grid_p] if grid_p is not None else [])
-        views = dws + dbs + ([dgrid] if grid_p is not None else [])
+        own_grid = grid_p is not None and self._producer is None       # the constant vector is a parameter of the step
+        order = list(weights) + list(biases) + ([grid_p] if own_grid else [])
+        views = dws + dbs + ([dgrid] if own_grid else [])
+        self._dgrid = dgrid
         for t, v in zip(order, views):
             t.grad = v
         qs = _lib.Queries()
@@ -597,25 +786,50 @@ class GraphedTrainStep:
             self.losses = {"audio_mse": losses[1]}
         else:
             self.losses = {"audio_sc_loss": losses[0], "audio_mag_loss": losses[1]}
+
+        def producer_forward():
+            if self._producer is None:
+                return None
+            feat = model.grid_feature(sync_gradient=False)
+            self._g_static.copy_(feat.detach().reshape(-1))
+            return feat
+
+        def producer_backward(feat):
+            if feat is not None:
+                feat.backward(dgrid.view_as(feat))
+        self._producer_forward, self._producer_backward = producer_forward, producer_backward
+        producer_params = [] if self._producer is None else [p for p in self._producer.parameters() if p.requires_grad]
+
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         if self.group is None:
             with torch.cuda.stream(side):
                 for _ in range(warmup):
+                    for p in producer_params:
+                        p.grad = None
                     l0 = lib.neraf_launch_count()
+                    feat = producer_forward()
                     forward_part()
                     backward_part()
+                    producer_backward(feat)
                     self.launches_per_step = lib.neraf_launch_count() - l0
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
+            for p in producer_params:          # first accumulation inside the capture assigns: a replay overwrites
+                p.grad = None
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
+                feat = producer_forward()
                 forward_part()
                 backward_part()
+                producer_backward(feat)
             return
         with torch.cuda.stream(side):
             for _ in range(warmup):
+                for p in producer_params:
+                    p.grad = None
                 l0 = lib.neraf_launch_count()
+                feat = producer_forward()
                 forward_part()
                 dist.all_reduce(self.sums[:4], group=self.group)
                 backward_part()
@@ -624,6 +838,9 @@ class GraphedTrainStep:
                 self.launches_per_step = lib.neraf_launch_count() - l0
                 dist.all_reduce(self._bias_region if self.nvls else self.flat_grad, group=self.group)
                 grid_part()
+                producer_backward(feat)
+        for p in producer_params:
+            p.grad = None
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph_fwd, self.graph_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -681,6 +898,8 @@ class GraphedTrainStep:
         else:
             self._reduce(self.flat_grad, dtype)
         self._grid_part()
+        self._producer_backward(self._feat)        # dg is global now: so are the replicated producer's gradients
+        self._feat = None
 
     def prefetch(self, batch: Dict[str, torch.Tensor]) -> None:
         """Start copying the NEXT step's batch (pinned host tensors) into staging buffers on a copy stream, so that the
@@ -720,6 +939,7 @@ class GraphedTrainStep:
                 t.grad = v
         else:
             import torch.distributed as dist
+            self._feat = self._producer_forward()          # eager autograd; its backward runs in allreduce_grads()
             self.graph_fwd.replay()
             dist.all_reduce(self.sums[:4], group=self.group)
             self.graph_bwd.replay()

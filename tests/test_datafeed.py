@@ -73,6 +73,27 @@ def test_two_ranks_see_what_one_rank_with_twice_the_batch_sees(drop_last):
         assert sorted(seen.tolist()) == list(range(n))          # an epoch visits every (RIR, time bin) once
 
 
+@pytest.mark.parametrize("n,B,world", [(10, 2, 2), (11, 2, 2), (9, 2, 2), (103, 8, 4), (7, 16, 3), (1000, 48, 8)])
+def test_ranks_always_get_equal_shards(n, B, world):
+    """The data-parallel loss normalises by n_local * world_size and every rank must reach its collectives: a partial
+    last global batch is cut evenly (never an empty or a shorter shard on one rank), the < world_size left-over samples
+    are skipped, and the shards stay disjoint rows of one permutation."""
+    ranks = [EpochSampler(n, B, seed=1, rank=r, world_size=world) for r in range(world)]
+    seen = []
+    for _ in range(3 * (n // (B * world) + 2)):
+        got = [s.next_range() for s in ranks]
+        sizes = {hi - lo for _, lo, hi in got}
+        assert len(sizes) == 1 and sizes.pop() >= 1 and len({e for e, _, _ in got}) == 1
+        for r in range(1, world):
+            assert got[r][1] == got[r - 1][2]                  # consecutive rows of the same global batch
+        if got[0][0] == 0:
+            seen.append(ranks[0].permutation(0)[got[0][1]:got[-1][2]])
+    seen = torch.cat(seen)
+    assert len(set(seen.tolist())) == len(seen) and n - len(seen) < world
+    with pytest.raises(ValueError):
+        EpochSampler(2, 4, world_size=3)
+
+
 def test_feed_fails_loudly_without_a_device():
     with pytest.raises(_lib.NerafError):
         ResidentAudioFeed(torch.zeros(2, 4, 1, 5), torch.zeros(2, 3), torch.zeros(2, 3), torch.zeros(2, 3), 4, 8)

@@ -1,15 +1,10 @@
 """Grid-feature producer on the B200: the CUDA operators against the host build of the
 same per-element code and against torch, the whole ResNet3D against the float64 oracle and the reference's golden
-vectors, and a full-size (128^3) pass checked through size-independent properties.
+vectors, a full-size (128^3) pass checked through size-independent properties, and the train step through producer and
+field (eager, and both captured forms).
 
-STATUS (profiles/r01f_gridnet_gpu_tests.txt): the operator tests, the evaluation-mode fp32 network test and both bf16
-network tests ran on a B200 with the round's last GPU seconds -- 44 passed; the evaluation-mode fp32 test tripped its
-max-over-tensors gradient gate at 1.6e-3 (one ReLU gate of a 512-voxel unit flipped against the float64 oracle: every
-tensor behind it moved by ~1e-3, every tensor before it sits at 1e-7), and that gate is 5e-3 now.  The two tests that
-did NOT get to run (training-mode fp32, full size) stay xfail(strict=False) until they have: this file sorts last and
-the driver runs pytest with -x, so an unverified test must not be able to hide the verified suite.  What they cover
-was exercised by tools/gridnet_quick.py on the B200 (profiles/r01f_gridnet_128_bf16.json: 128^3 training step, finite,
-evaluation-mode backward exactly linear, feature repeatable).
+STATUS: every test of this file ran green on a B200 on the round-2 tree (profiles/r02a_pytest_gpu.txt: the whole
+``-m gpu`` suite with ``--runxfail``, 197 passed) -- no xfail marks are left.
 Tolerances are those of tests/test_gridnet.py (stated there).
 """
 import os
@@ -26,7 +21,6 @@ from oracle import gridnet as og
 from tests.util import cuda, rel_fro
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]     # nothing here takes a minute; a hang must not hold the run
-not_yet_run = pytest.mark.xfail(strict=False, reason="not yet run on a B200 (round-1 GPU budget spent); see the module docstring")
 
 N, GRID_STEP = 64, 1 / 64
 
@@ -220,12 +214,20 @@ def test_backward_job_list_with_split_k_equals_the_separate_launches():
         torch.cuda.synchronize()
         assert torch.equal(dc_a, dc_b)
         ref = dy.double().t() @ col.double()
-        assert rel_fro(dw_b, ref) < 1e-5 and rel_fro(dw_a[:, :, 0], ref) < 1e-5, (v_out, kc, c_out, S)
+        # bf16 operands are exact here (the reference uses the same rounded values): what is left is the fp32 accumulation
+        # over the v_out voxels.  The tensor core adds each 16-deep partial product into the running fp32 sum without
+        # round-to-nearest, so the error grows like a biased walk: bound 8 sqrt(K) 2^-24 (K = 32 768: 8.6e-5; the unsplit
+        # form measured 3.75e-5 on the B200), never below 1e-5.  Split-K shortens every chain, so it must meet the same
+        # bound, and the two forms must agree with each other to twice that.
+        bound = max(1e-5, 8.0 * np.sqrt(v_out) * 2.0 ** -24)
+        e_unsplit, e_split = rel_fro(dw_b, ref), rel_fro(dw_a[:, :, 0], ref)
+        assert e_unsplit < bound and e_split < bound, (v_out, kc, c_out, S, e_unsplit, e_split, bound)
+        assert rel_fro(dw_a[:, :, 0], dw_b) < 2 * bound
         assert rel_fro(dc_a, dy.double() @ wmat.double()) < 4e-3
         ops.gemm_backward(dy, wmat, col, v_out, kc, c_out, parts.fill_(7.0), None)      # the stem: no data gradient
         ops.unpack_wgrad(parts, dw_a)
         torch.cuda.synchronize()
-        assert rel_fro(dw_a[:, :, 0], ref) < 1e-5
+        assert rel_fro(dw_a[:, :, 0], ref) < bound
 
 
 # ------------------------------------------------------------------------------------------------ the whole network
@@ -257,11 +259,16 @@ def test_network_eval_mode_fp32(problem, golden_dir):
     assert rel_fro(out, ref) < 1e-5
     assert rel_fro(out.reshape(-1), golden["feature_eval"]) < 1e-5
     errs = {k: rel_fro(p.grad, grads[k]) for k, p in net.named_parameters()}
-    assert max(errs.values()) < 5e-3, max(errs.items(), key=lambda kv: kv[1])     # one flipped ReLU gate: ~1e-3
+    # The backward of a ReLU network is discontinuous in its forward: a pre-activation that the fp32 forward puts on the
+    # other side of zero than the float64 oracle (|z| ~ 1e-7 of its scale) flips one gate and moves every gradient behind
+    # it by that unit's share -- ~1/512 of a late layer's 512-voxel maps, measured 1.6e-3 on the B200.  So: the typical
+    # tensor must sit at fp32 rounding (median 1e-5), at most a tenth of the tensors may feel a flipped gate at all, and
+    # none may be off by more than a few such flips (5e-3).
     assert statistics.median(errs.values()) < 1e-5
+    assert sum(e > 1e-4 for e in errs.values()) <= len(errs) // 10, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    assert max(errs.values()) < 5e-3, max(errs.items(), key=lambda kv: kv[1])
 
 
-@not_yet_run
 def test_network_training_mode_fp32(problem, golden_dir):
     sd, x, dout = problem
     golden = np.load(os.path.join(golden_dir, "gridnet_resnet50.npz"))
@@ -293,7 +300,6 @@ def test_network_bf16_tcgen05(problem, training):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
 
 
-@not_yet_run
 def test_full_size_grid_properties():
     """BASELINE's shape: one (1, 7, 128, 128, 128) grid, ResNet3D-50, 1024 features (NeRAF_model.py:185, grid_step 1/128).
     The float64 oracle needs minutes at this size, so the check is through properties: the evaluation-mode backward is
@@ -321,7 +327,6 @@ def test_full_size_grid_properties():
     assert torch.isfinite(f3).all() and all(torch.isfinite(p.grad).all() for p in net.parameters())
 
 
-@not_yet_run
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_train_step_through_producer_and_field_eager_and_graphed(prec):
     """NeRAF_model.py:554-566 with the real producer: grid -> ResNet3D -> feature -> field -> loss -> backward.  The
@@ -339,7 +344,7 @@ def test_train_step_through_producer_and_field_eager_and_graphed(prec):
     model.resnet3d.eval()                                   # running statistics: the step is repeatable
     model.field.always_repack = True
     batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=1).items()}
-    params = [p for p in model.parameters() if p.requires_grad]
+    params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
 
     def eager():
         for p in params:
@@ -371,11 +376,14 @@ def test_train_step_through_producer_and_field_eager_and_graphed(prec):
     torch.cuda.synchronize()
     for p in model.resnet3d.parameters():
         assert rel_fro(p.grad, grads[id(p)]) < 1e-5
-    # captured
-    step = GraphedTrainStep(model, batch)
-    got = step(batch)
-    torch.cuda.synchronize()
-    for k, v in losses.items():
-        assert abs(float(got[k]) - v) <= 1e-5 * abs(v), k
-    for p in params:
-        assert rel_fro(p.grad, grads[id(p)]) < 1e-4
+    # captured: the field's direct library calls with the producer's autograd around them (default), and the plugin's
+    # autograd calls captured as they are
+    for functional in (True, False):
+        step = GraphedTrainStep(model, batch, functional=functional)
+        for _ in range(2):                                  # a replay overwrites, it does not accumulate
+            got = step(batch)
+        torch.cuda.synchronize()
+        for k, v in losses.items():
+            assert abs(float(got[k]) - v) <= 1e-5 * abs(v), (k, functional)
+        for p in params:
+            assert rel_fro(p.grad, grads[id(p)]) < 1e-4, functional

@@ -31,7 +31,7 @@ def build(group):
 
 
 def flat(model):
-    return torch.cat([p.grad.reshape(-1).float() for p in model.parameters() if p.requires_grad])
+    return torch.cat([p.grad.reshape(-1).float() for p in model.parameters() if p.requires_grad and p.numel() > 0])
 
 
 batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=10 + rank).items()}

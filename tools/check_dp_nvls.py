@@ -36,7 +36,7 @@ for name, fused in (("nccl", False), ("nvls", True)):
         ld = step(batch)
         step.allreduce_grads()
     torch.cuda.synchronize()
-    res[name] = (torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone(), {k: float(v) for k, v in ld.items()}, step.nvls)
+    res[name] = (torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.numel() > 0]).clone(), {k: float(v) for k, v in ld.items()}, step.nvls)
     dist.barrier()
 a, b = res["nccl"][0], res["nvls"][0]
 rel = float((a.double() - b.double()).norm() / a.double().norm())

@@ -42,7 +42,7 @@ for name, kw in variants:
         torch.cuda.synchronize()
         if it >= 5:
             tot += s.elapsed_time(e) * 1e3 / n
-    g = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).double()
+    g = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.numel() > 0]).double()
     if ref is None:
         ref = g
     err = float((g - ref).norm() / ref.norm())
