@@ -112,64 +112,82 @@ int pack_list(PackList& L, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Both gradients of the hoisted grid block of layer 1 in ONE launch (they only share their input db1):
-//   blocks [0, n_outer)   dW1[n, :G] = db1[n] * g        (8 rows per block)
-//   the rest              dg[k]     += sum_n W1[n, k] db1[n]   (32 columns x one slice of n per block; dg pre-zeroed)
-// ---------------------------------------------------------------------------------------------
+// Both gradients of the hoisted grid block of layer 1 in ONE pass over the rows (they share their input db1 = s):
+//   dW1[n, :K] = s[n] * g        (rank 1: 4 K bytes written per row)
+//   dg[k]     += sum_n W1[n, k] s[n]                (4 K bytes read per row; dg pre-zeroed)
+// HBM-bound (20.9 MB written + 20.9 MB read at n1 = 5096, K = 1024).  A block owns GG_ROWS consecutive rows and ALL K
+// columns: thread t holds columns t, t + 256, ... (coalesced 1 KB runs; W1's row stride 1187 rules out 16-byte
+// vectors), every load of the block's rows is issued before the first use (GG_ROWS x K/256 independent 4-byte loads
+// per thread in flight), the column sums stay in registers and leave as one fire-and-forget atomic per column and block.
 // compact (optional): the per-query block of dW1, (N, E) with row stride ld_c, copied into dW[:, K:K+E] by the same
 // rows (data parallel: that block was all-reduced in a compact buffer, see neraf_field_backward_dp).
-// TPB threads per block: TPB / 128 outer rows and TPB / 32 n-lanes per block.
-template <int TPB>
-__global__ void __launch_bounds__(TPB) grid_grads_kernel(const float* __restrict__ s, const float* __restrict__ g,
-                                                         const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
-                                                         float* __restrict__ dW, float* __restrict__ dg, int n_outer,
-                                                         int n_slices, const float* __restrict__ compact, int64_t E,
-                                                         int64_t ld_c) {
-  constexpr int NY = TPB / 32;                     // n-lanes of the dg part
-  constexpr int RPB = TPB / 128;                   // rows per block of the outer part
-  __shared__ float red[NY][33];
-  int blk = blockIdx.x;
-  if (blk < n_outer) {
-    const int64_t n = (int64_t)blk * RPB + threadIdx.x / 128;
-    if (n >= N) return;
-    const float sn = __ldg(s + n);
-    float* row = dW + n * ldw;
-    for (int64_t k = threadIdx.x % 128; k < K; k += 128) row[k] = sn * __ldg(g + k);
-    if (compact)
-      for (int64_t e = threadIdx.x % 128; e < E; e += 128) row[K + e] = __ldg(compact + n * ld_c + e);
-    return;
-  }
-  blk -= n_outer;
-  const int kx = threadIdx.x % 32, ny = threadIdx.x / 32;
-  const int kblk = blk / n_slices, slice = blk % n_slices;
-  const int64_t k = (int64_t)kblk * 32 + kx;
-  const int64_t per = (N + n_slices - 1) / n_slices;
-  const int64_t n_lo = (int64_t)slice * per, n_hi = n_lo + per < N ? n_lo + per : N;
-  float acc = 0.f;
-  if (k < K)
-    for (int64_t n = n_lo + ny; n < n_hi; n += NY) acc = fmaf(__ldg(W + n * ldw + k), __ldg(s + n), acc);
-  red[ny][kx] = acc;
-  __syncthreads();
-  if (ny == 0 && k < K) {
-    float t = 0.f;
+// ---------------------------------------------------------------------------------------------
+constexpr int GG_ROWS = 8;
+constexpr int GG_TPB = 256;
+
+template <int KCH>      // column chunks of 256 per thread: K <= 256 * KCH
+__global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restrict__ s, const float* __restrict__ g,
+                                                            const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
+                                                            float* __restrict__ dW, float* __restrict__ dg,
+                                                            const float* __restrict__ compact, int64_t E, int64_t ld_c) {
+  const int t = threadIdx.x;
+  const int64_t n0 = (int64_t)blockIdx.x * GG_ROWS;
+  const int rows = (int)(N - n0 < GG_ROWS ? N - n0 : GG_ROWS);
+  float gk[KCH], acc[KCH], w[GG_ROWS][KCH], sn[GG_ROWS];
 #pragma unroll
-    for (int i = 0; i < NY; ++i) t += red[i][kx];
-    atomicAdd(dg + k, t);
+  for (int j = 0; j < KCH; ++j) {
+    const int64_t k = t + 256 * j;
+    gk[j] = k < K ? __ldg(g + k) : 0.f;
+    acc[j] = 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < GG_ROWS; ++r) sn[r] = r < rows ? __ldg(s + n0 + r) : 0.f;
+  if (dg) {
+#pragma unroll
+    for (int r = 0; r < GG_ROWS; ++r)
+#pragma unroll
+      for (int j = 0; j < KCH; ++j) {
+        const int64_t k = t + 256 * j;
+        w[r][j] = (r < rows && k < K) ? __ldg(W + (n0 + r) * ldw + k) : 0.f;
+      }
+  }
+  if (dW) {
+#pragma unroll
+    for (int r = 0; r < GG_ROWS; ++r) {
+      if (r < rows) {
+        float* row = dW + (n0 + r) * ldw;
+#pragma unroll
+        for (int j = 0; j < KCH; ++j) {
+          const int64_t k = t + 256 * j;
+          if (k < K) row[k] = sn[r] * gk[j];
+        }
+        if (compact)
+          for (int64_t e = t; e < E; e += GG_TPB) row[K + e] = __ldg(compact + (n0 + r) * ld_c + e);
+      }
+    }
+  }
+  if (dg) {
+#pragma unroll
+    for (int r = 0; r < GG_ROWS; ++r)
+#pragma unroll
+      for (int j = 0; j < KCH; ++j) acc[j] = fmaf(w[r][j], sn[r], acc[j]);
+#pragma unroll
+    for (int j = 0; j < KCH; ++j) {
+      const int64_t k = t + 256 * j;
+      if (k < K) atomicAdd(dg + k, acc[j]);
+    }
   }
 }
 
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
                bool dg_is_zero, cudaStream_t stream, const float* compact, int64_t E, int64_t ld_c) {
-  if (N <= 0 || K <= 0) return NERAF_OK;
-  // 256-thread blocks (2 outer rows / 8 n-lanes each) and 32 slices of n: measured 1.7 us faster per step than
-  // 1024-thread blocks with 16 slices (tools/ab_step.py) -- more, shorter blocks fill the last wave better
-  const int n_outer = dW ? (int)ceil_div(N, 2) : 0;
-  const int n_slices = 32;
-  const int n_bwd = dg ? (int)ceil_div(K, 32) * n_slices : 0;
-  if (n_outer + n_bwd == 0) return NERAF_OK;
+  if (N <= 0 || K <= 0 || (!dW && !dg)) return NERAF_OK;
+  NERAF_REQUIRE(K <= 256 * 8, "grid_grads: at most 2048 grid-feature columns (got %lld)", (long long)K);
   if (dg && !dg_is_zero) NERAF_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)K * 4, stream));
-  grid_grads_kernel<256><<<(unsigned)(n_outer + n_bwd), 256, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, n_outer, n_slices,
-                                                                        dW ? compact : nullptr, E, ld_c);
+  const unsigned grid = (unsigned)ceil_div(N, GG_ROWS);
+  const float* cp = dW ? compact : nullptr;
+  if (K <= 256 * 4) grid_grads_kernel<4><<<grid, GG_TPB, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, cp, E, ld_c);
+  else grid_grads_kernel<8><<<grid, GG_TPB, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, cp, E, ld_c);
   NERAF_CHECK_LAUNCH("grid_grads_kernel");
   return NERAF_OK;
 }

@@ -39,12 +39,29 @@ def _bn(sd, name, x, training, new_stats):
 
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, grid_step: Optional[float] = None, n_features: int = 1024,
             training: bool = True, prefix: str = "backbone_net.",
-            new_stats: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+            new_stats: Optional[Dict[str, torch.Tensor]] = None, gates=None, gate_log=None) -> torch.Tensor:
     """x (1, C, D, H, W) -> (1, N, d, h, w) exactly as ``ResNet3D.forward``; ``sd`` values must already have x's dtype
-    (parameters may require grad).  ``new_stats`` receives the running statistics a training-mode pass leaves."""
+    (parameters may require grad).  ``new_stats`` receives the running statistics a training-mode pass leaves.
+
+    The gradient of a ReLU network is discontinuous in its forward pass: a pre-activation within rounding of zero gives
+    a different gate -- and different gradients everywhere behind it -- in float32 than in float64.  To compare a
+    lower-precision implementation's BACKWARD with this oracle, the gates can be pinned: ``gate_log`` (a list) receives
+    the boolean pattern ``z > 0`` of every ReLU in call order; ``gates`` (such a list) replaces ``relu(z)`` by
+    ``z * gates[i]``."""
     p = prefix
+    n_relu = [0]
+
+    def relu(z):
+        i = n_relu[0]
+        n_relu[0] += 1
+        if gate_log is not None:
+            gate_log.append(z.detach() > 0)
+        if gates is None:
+            return F.relu(z)
+        return z * gates[i].to(z.dtype)
+
     h = F.conv3d(x, sd[p + "conv1.weight"], stride=2, padding=2)
-    h = F.relu(_bn(sd, p + "bn1", h, training, new_stats))
+    h = relu(_bn(sd, p + "bn1", h, training, new_stats))
     h = F.max_pool3d(h, kernel_size=3, stride=2, padding=1)
     n_stages = 4 if n_features == 2048 else 3
     for s in range(n_stages):
@@ -54,23 +71,24 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, grid_step: Optional[fl
             stride = 2 if (s > 0 and b == 0) else 1
             res = h
             if q + "conv3.weight" in sd:                                               # Bottleneck
-                o = F.relu(_bn(sd, q + "bn1", F.conv3d(h, sd[q + "conv1.weight"]), training, new_stats))
-                o = F.relu(_bn(sd, q + "bn2", F.conv3d(o, sd[q + "conv2.weight"], stride=stride, padding=1), training, new_stats))
+                o = relu(_bn(sd, q + "bn1", F.conv3d(h, sd[q + "conv1.weight"]), training, new_stats))
+                o = relu(_bn(sd, q + "bn2", F.conv3d(o, sd[q + "conv2.weight"], stride=stride, padding=1), training, new_stats))
                 o = _bn(sd, q + "bn3", F.conv3d(o, sd[q + "conv3.weight"]), training, new_stats)
             else:                                                                      # BasicBlock
-                o = F.relu(_bn(sd, q + "bn1", F.conv3d(h, sd[q + "conv1.weight"], stride=stride, padding=1), training, new_stats))
+                o = relu(_bn(sd, q + "bn1", F.conv3d(h, sd[q + "conv1.weight"], stride=stride, padding=1), training, new_stats))
                 o = _bn(sd, q + "bn2", F.conv3d(o, sd[q + "conv2.weight"], padding=1), training, new_stats)
             if q + "downsample.0.weight" in sd:
                 res = _bn(sd, q + "downsample.1", F.conv3d(h, sd[q + "downsample.0.weight"], stride=stride), training, new_stats)
-            h = F.relu(o + res)
+            h = relu(o + res)
             b += 1
     return F.avg_pool3d(h, avgpool_window(grid_step, n_features), stride=1)
 
 
 def forward_backward(sd: Dict[str, torch.Tensor], x: torch.Tensor, dout: torch.Tensor, grid_step=None, n_features=1024,
-                     training=True, dtype=torch.float64, prefix="backbone_net."
+                     training=True, dtype=torch.float64, prefix="backbone_net.", gates=None, gate_log=None
                      ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
-    """Feature, gradients of every parameter for the upstream gradient ``dout``, and the updated running statistics."""
+    """Feature, gradients of every parameter for the upstream gradient ``dout``, and the updated running statistics
+    (``gates`` / ``gate_log``: see ``forward``)."""
     work = {}
     for k, v in sd.items():
         if v.dtype.is_floating_point:
@@ -81,7 +99,7 @@ def forward_backward(sd: Dict[str, torch.Tensor], x: torch.Tensor, dout: torch.T
         else:
             work[k] = v
     stats: Dict[str, torch.Tensor] = {}
-    out = forward(work, x.to(dtype), grid_step, n_features, training, prefix, stats)
+    out = forward(work, x.to(dtype), grid_step, n_features, training, prefix, stats, gates, gate_log)
     out.backward(dout.to(dtype).reshape(out.shape))
     grads = {k: v.grad for k, v in work.items() if isinstance(v, torch.Tensor) and v.requires_grad}
     return out.detach(), grads, stats

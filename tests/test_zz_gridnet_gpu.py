@@ -250,23 +250,48 @@ def _run(sd, x, dout, precision, training, n=N, grid_step=GRID_STEP):
     return net, out.detach()
 
 
+def _tape_gates(tape):
+    """The product's ReLU gates (post-activation > 0) in the oracle's call order and layout: stem, then bn1 / bn2 / block
+    output of every block (neraf_b200/gridnet.py keeps the activations on the autograd node's tape until backward)."""
+    recs = [tape["stem"]] + [r for block, _ in tape["blocks"] for r in block]
+    return [_unact((r.y > 0).cpu(), r.window.out_dims) for r in recs]
+
+
 def test_network_eval_mode_fp32(problem, golden_dir):
     sd, x, dout = problem
+    dev = cuda()
     golden = np.load(os.path.join(golden_dir, "gridnet_resnet50.npz"))
-    ref, grads, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=False)
-    net, out = _run(sd, x, dout, "fp32", False)
+    net = ResNet3D_helper(in_channels=7, backbone="resnet50", grid_step=GRID_STEP, N_features=1024, precision="fp32")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    out = net(x.to(dev))
+    gates = _tape_gates(out.grad_fn.tape)
+    out.backward(dout.to(dev))
+    torch.cuda.synchronize()
+    natural = []
+    ref, grads_nat, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=False, gate_log=natural)
     assert out.shape == (1, 1024, 1, 1, 1) and out.dtype == torch.float32
     assert rel_fro(out, ref) < 1e-5
     assert rel_fro(out.reshape(-1), golden["feature_eval"]) < 1e-5
+    # The backward of a ReLU network is discontinuous in its forward: a pre-activation that fp32 puts on the other side of
+    # zero than float64 does flips one gate and moves every gradient behind it (measured: ONE flipped unit of a
+    # 512-voxel map in layer2.0, 1.6e-3 on the 38 tensors in front of it, 1e-7 on the 91 behind).  That is a property of
+    # the precision, not of the backward pass -- so the float64 oracle is evaluated at the PRODUCT's gate pattern, which
+    # may differ from its own in a handful of the ~9 M units, and every gradient tensor is gated at fp32 rounding.
+    assert len(gates) == len(natural) == 40 and all(a.shape == b.shape for a, b in zip(gates, natural))
+    flipped = sum(int((a != b).sum()) for a, b in zip(gates, natural))
+    assert flipped <= 16, flipped
+    _, grads, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=False, gates=gates)
+    # conditioning: torch's own float32 pass at the same gates (the stem's weight gradient is the remainder of a
+    # cancellation over all voxels -- torch fp32 is 5.6e-4 off its float64 value there, 4e-7 everywhere else)
+    _, grads32, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=False, gates=gates, dtype=torch.float32)
     errs = {k: rel_fro(p.grad, grads[k]) for k, p in net.named_parameters()}
-    # The backward of a ReLU network is discontinuous in its forward: a pre-activation that the fp32 forward puts on the
-    # other side of zero than the float64 oracle (|z| ~ 1e-7 of its scale) flips one gate and moves every gradient behind
-    # it by that unit's share -- ~1/512 of a late layer's 512-voxel maps, measured 1.6e-3 on the B200.  So: the typical
-    # tensor must sit at fp32 rounding (median 1e-5), at most a tenth of the tensors may feel a flipped gate at all, and
-    # none may be off by more than a few such flips (5e-3).
+    for k, e in errs.items():
+        assert e < 2e-5 + 3 * rel_fro(grads32[k], grads[k]), (k, e)
     assert statistics.median(errs.values()) < 1e-5
-    assert sum(e > 1e-4 for e in errs.values()) <= len(errs) // 10, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
-    assert max(errs.values()) < 5e-3, max(errs.items(), key=lambda kv: kv[1])
+    # ... and against the oracle's own pattern the difference is what those flips are worth, nothing more
+    errs_nat = {k: rel_fro(p.grad, grads_nat[k]) for k, p in net.named_parameters()}
+    assert max(errs_nat.values()) < 5e-3 * max(flipped, 1)
 
 
 def test_network_training_mode_fp32(problem, golden_dir):
