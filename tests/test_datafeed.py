@@ -37,6 +37,13 @@ def test_oracle_reproduces_the_reference_dataset_batches(golden_dir):
                 assert np.array_equal(got[k], ref[k]), k
 
 
+def _equal_up_to_the_host_logf(a, ref):
+    """Bit-equal where torch's logf of THIS host is the one that made the golden file; torch dispatches log to a
+    different vector routine per ISA (AVX2 / AVX512 builds of SLEEF differ in the last bit on ~5 % of the inputs), so
+    on another host the same arithmetic is allowed one unit in the last place."""
+    return np.array_equal(a, ref) or np.max(np.abs(a - ref)) <= 1.2e-7 * np.max(np.abs(ref))
+
+
 def test_cache_rows_equal_the_reference_samples_bit_for_bit(golden_dir):
     """Host side of the product: the cache is built with torch's own log, like the reference's samples."""
     z, mags, batches = _golden(golden_dir)
@@ -44,7 +51,11 @@ def test_cache_rows_equal_the_reference_samples_bit_for_bit(golden_dir):
     cache = torch.stack([target_columns(torch.from_numpy(m), max_len) for m in mags])       # (n, T, C, F)
     flat = cache.reshape(-1, cache.shape[2], cache.shape[3]).numpy()
     ref = np.concatenate([b["data"] for b in batches])
-    assert np.array_equal(flat[z["indices"]], ref)
+    assert _equal_up_to_the_host_logf(flat[z["indices"]], ref)
+    # ... and bit-equal to the reference's own expression (NeRAF_dataset.py:283-288) evaluated by this host's torch
+    for m, c in zip(mags, cache):
+        t = min(m.shape[2], max_len)
+        assert torch.equal(c[:t], torch.log(torch.from_numpy(m).float()[:, :, :t] + 1e-3).permute(2, 0, 1))
     assert np.max(np.abs(ofeed.full_cache(mags, max_len) - flat.reshape(flat.shape[0], -1))) < 3e-7 * np.abs(flat).max()
 
 
@@ -112,7 +123,11 @@ def test_gather_reproduces_the_reference_batches_bit_for_bit(golden_dir):
         got = feed.batch_from_indices(torch.from_numpy(z["indices"][16 * b:16 * (b + 1)]))
         for k in KEYS:
             assert got[k].dtype == torch.from_numpy(ref[k]).dtype, k
-            assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
+            if k == "data":
+                assert _equal_up_to_the_host_logf(got[k].cpu().numpy(), ref[k]), k
+                assert torch.equal(got[k].cpu(), feed.cache.cpu().reshape(-1, *got[k].shape[1:])[z["indices"][16 * b:16 * (b + 1)]])
+            else:
+                assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
     feed.check()
 
 

@@ -58,17 +58,20 @@ def _projection(t, name):
 
 # ------------------------------------------------------------------------------------------------ oracle vs reference
 def test_oracle_matches_the_reference_golden(problem, golden):
+    # fp32 on the host: torch picks its convolution / reduction kernels per ISA (the golden file was written on an AVX2
+    # host; on an AVX512 host the same 50 layers land 1.1e-6 away), so the gates are fp32 round-off across hosts, not
+    # bit equality -- the float64 comparisons below (and the GPU tests) are the tight ones
     sd, x, dout = problem
     assert np.array_equal(golden["dout"], dout.reshape(-1).numpy())
     stats = {}
     with torch.no_grad():
         f_train = og.forward(sd, x, GRID_STEP, 1024, True, new_stats=stats)
-    assert rel_fro(f_train.reshape(-1), golden["feature_train"]) < 1e-6
+    assert rel_fro(f_train.reshape(-1), golden["feature_train"]) < 5e-6
     for k in golden.files:
         if k.startswith("stats/"):
-            assert rel_fro(stats[k[6:]], golden[k]) < 1e-6, k
+            assert rel_fro(stats[k[6:]], golden[k]) < 5e-6, k
     f_eval, grads, _ = og.forward_backward(sd, x, dout, GRID_STEP, training=False, dtype=torch.float32)
-    assert rel_fro(f_eval.reshape(-1), golden["feature_eval"]) < 1e-6
+    assert rel_fro(f_eval.reshape(-1), golden["feature_eval"]) < 5e-6
     norms = json.loads(str(golden["grad_eval_norms"]))
     projs = json.loads(str(golden["grad_eval_projections"]))
     assert set(norms) == set(grads)
@@ -77,7 +80,7 @@ def test_oracle_matches_the_reference_golden(problem, golden):
         assert abs(_projection(g, k) - projs[k]) <= 1e-4 * norms[k], k
     for k in golden.files:
         if k.startswith("grad_eval/"):
-            assert rel_fro(grads[k[10:]], golden[k]) < 1e-5, k
+            assert rel_fro(grads[k[10:]], golden[k]) < 5e-5, k
 
 
 def test_state_dict_is_the_reference_checkpoint_contract(golden):
