@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 7
+#define NERAF_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))
@@ -57,6 +57,9 @@ enum { NERAF_ORDER_TIME_MIC_SRC_ROT = 0, /* NeRAF_model.py:560 (after the grid b
 
 NERAF_API int neraf_version(void);
 NERAF_API const char* neraf_last_error(void);
+/* sizeof() of a public struct by its type name ("neraf_gemm_job", ...), 0 for an unknown name: lets a binding check
+ * its mirror of the layouts (tests/test_abi.py does, for the ctypes table). */
+NERAF_API size_t neraf_abi_sizeof(const char* name);
 /* Cumulative number of CUDA kernels launched by this library in this process (bench.py: gpu_launches). */
 NERAF_API long long neraf_launch_count(void);
 /* 1 when the current device is compute capability 10.x, else 0 (no error raised). */
@@ -175,6 +178,18 @@ NERAF_API int neraf_field_forward_loss_sums(const neraf_field_dims* dims, int pr
 /* The spectral loss's gradient formed inside the backward instead of being read from `dout` (which may then be NULL):
  * dout[i] = neraf_spectral_loss_backward(out, gt, ..., sums, upstream = 1)[i], evaluated on the fly by the kernel that
  * applies the heads' 10*tanh derivative -- one launch and a 2 x 4 B/element round trip less per step. */
+/* Data parallel: the ranks' copies of one small exchange buffer in symmetric (peer-mapped) memory -- what
+ * torch.distributed._symmetric_memory hands out: peers[r] is rank r's buffer as mapped into THIS process
+ * (peers[rank] the local one), NERAF_EXCHANGE_BYTES each, zero before the first use.  Kernels exchange a few words
+ * per step through it (stores to every peer + a flag, spin on the local flags) instead of a host-issued collective,
+ * so a whole training step stays one CUDA graph. */
+#define NERAF_MAX_RANKS 16
+#define NERAF_EXCHANGE_BYTES 4096
+typedef struct {
+  int32_t world, rank;
+  void* peers[NERAF_MAX_RANKS];
+} neraf_rank_exchange;
+
 typedef struct {
   const float* gt;          /* (B, C, F) target log-magnitudes, same layout as out          */
   int64_t n_total;          /* elements over ALL ranks (the mean's denominator)             */
@@ -184,7 +199,50 @@ typedef struct {
   float* losses;            /* optional dev f32[2]: the two weighted losses (what                */
                             /* neraf_spectral_loss_finalize writes), formed by the same launch  */
   float* total;             /* optional dev f32[1] (with losses): their sum, what a Trainer reads */
+  /* fuse_sums != 0: ONE launch forms the partial sums of (out, gt) itself, meets at a grid barrier (where, under
+   * data parallelism, the last block exchanges the four sums with the other ranks through `exchange`), and then forms
+   * the gradient -- no loss launch and no host collective between forward and backward.  `sums` must hold zeros on
+   * entry (neraf_field_forward_loss_sums with gt == NULL clears it) and receives the GLOBAL sums; `sync` is a device
+   * u32[4] that is zero before its first use and owned by this call sequence (barrier state + step counter). */
+  int32_t fuse_sums;
+  uint32_t* sync;
+  const neraf_rank_exchange* exchange;   /* NULL: single process */
 } neraf_loss_grad;
+
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (SURVEY.md 8e collective 1; the reference has no multi-GPU path at all,
+ * NeRAF_pipeline.py:153-157) as ONE kernel of this library over peer-mapped ("symmetric") memory: a two-shot
+ * all-reduce -- multimem.ld_reduce of this rank's slice (the NVSwitch adds the ranks' copies), multimem.st of the sum
+ * into every rank's copy -- chunk by chunk in the order the backward finishes the gradients.  Enqueued on a stream
+ * BESIDE neraf_field_backward_dp (fork before it, join after both): every chunk waits for the completion counter
+ * (neraf_dp_options.notify) the backward advances, so gradients travel while the remaining GEMMs run, and the whole
+ * training step -- no host-issued collective anywhere -- is one CUDA graph.
+ *   region   : every rank's gradient buffer in symmetric memory (same layout on every rank): peers[r] is rank r's as
+ *              mapped into this process (peers[rank] the local one), multicast its NVLS alias or NULL (then plain peer
+ *              loads / stores are used).  The sums replace the addends in place, on every rank.
+ *   chunks   : byte ranges of the region (16-byte multiples), bf16 (f32 == 0) or fp32 elements, fp32 accumulation;
+ *              notify / notify_increment: dev u32 counter that this rank's producer advances by notify_increment per
+ *              step when the chunk is stored (NULL: ready when the call starts).  EVERY step that advances the
+ *              counters must run this call exactly once (the kernel counts steps in `state`).
+ *   signals  : every rank's NERAF_EXCHANGE_BYTES signal buffer (symmetric memory, zero before first use; may be the
+ *              buffer of neraf_rank_exchange); state: dev u32[4] of this rank, zero before first use.
+ *   max_ctas : 0 = one CTA per SM (256 threads, fits beside a CTA of the job-list kernel). */
+#define NERAF_MAX_EXCHANGE_CHUNKS 16
+typedef struct {
+  int64_t offset, bytes;
+  const uint32_t* notify;
+  uint32_t notify_increment;
+  int32_t f32;
+} neraf_exchange_chunk;
+typedef struct {
+  int32_t world, rank, n_chunks, max_ctas;
+  neraf_exchange_chunk chunks[NERAF_MAX_EXCHANGE_CHUNKS];
+  void* multicast;
+  void* peers[NERAF_MAX_RANKS];
+  void* signals[NERAF_MAX_RANKS];
+  uint32_t* state;
+} neraf_grad_exchange;
+NERAF_API int neraf_dp_exchange_grads(const neraf_grad_exchange* x, neraf_stream_t stream);
 
 typedef struct {
   const neraf_multicast* mc;
@@ -194,6 +252,17 @@ typedef struct {
   int32_t max_ctas;
   const neraf_loss_grad* loss;   /* NULL: read the upstream gradient from dout */
   void* const* dweights_bf16;    /* NULL: fp32 weight gradients in dweights / dw0_compact */
+  uint32_t* notify;              /* optional dev u32[n_trunk + 2], never cleared by the library: completion counters for a
+                                    kernel running BESIDE the backward (neraf_dp_exchange_grads): [i] weight gradient of
+                                    trunk layer i stored, [n_trunk] head weight gradients stored, [n_trunk + 1] every bias
+                                    gradient final.  Each launch advances counter k by notify_increment[k]. */
+  uint32_t* notify_increment;    /* HOST u32[n_trunk + 2], written by the call (with notify) */
+  const neraf_grad_exchange* exchange;   /* optional (with notify): neraf_dp_exchange_grads is enqueued BESIDE the backward's
+                                    GEMM launch on a helper stream of the library (forked after the head-gradient kernel,
+                                    joined before the call returns its stream); chunks whose notify points into `notify`
+                                    get their notify_increment from this call */
+  int32_t zero_tail_slack;       /* the caller owns up to 3 floats behind the last bias gradient (/ dgrid): the fused loss
+                                    kernel may clear the back-to-back gradient vectors in whole 16-byte words */
 } neraf_dp_options;
 
 NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precision, int64_t batch, const float* dout,
@@ -368,6 +437,7 @@ NERAF_API int neraf_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
  *                 block r (256 rows) starts when row block r of wait_job is complete (both jobs have the same M);
  *                 wait_all == 1: when every row block of wait_job is complete.
  *   colsum      : optional dev fp32 (N), must be zeroed by the caller: += column sums of the fp32 results.
+ *   notify      : see below.
  *   bias        : must not be produced by a job of the same launch (it is prefetched before dependencies resolve);
  *                 A, B, gate and gate_mask may be.
  *   out_bf16    : ld_bf16 is a multiple of 8, so a row has round_up(N, 8) - N pad columns: they may be overwritten
@@ -388,6 +458,8 @@ typedef struct {
   int32_t merge_next;   /* 1: interleave this job's tiles with those of the NEXT job (which must not wait for this one) */
   neraf_gemm_epilogue epi;
   float* colsum;
+  uint32_t* notify;     /* optional dev u32, never cleared: advanced (gpu-scope release) as the job's tiles are stored, by a
+                           fixed amount per launch -- lets a CONCURRENT kernel wait for this job's output */
 } neraf_gemm_job;
 
 NERAF_API int neraf_gemm_bf16_jobs(const neraf_gemm_job* jobs, int n_jobs, void* counters, size_t counters_bytes,

@@ -20,6 +20,7 @@ ACT_NONE, ACT_LEAKY, ACT_TANH10 = 0, 1, 2
 CRIT_SC_SLMSE, CRIT_SC_SLL1, CRIT_MSE = 0, 1, 2
 ORDER_TIME_MIC_SRC_ROT, ORDER_MIC_SRC_TIME_ROT = 0, 1
 MAX_TRUNK = 8
+MAX_RANKS, EXCHANGE_BYTES, MAX_EXCHANGE_CHUNKS = 16, 4096, 16
 
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 CRITERIA = {"SC+SLMSE": CRIT_SC_SLMSE, "SC+SLL1": CRIT_SC_SLL1, "MSE": CRIT_MSE}
@@ -53,22 +54,41 @@ class GemmJob(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("A", C.c_void_p), ("lda", C.c_int64),
                 ("B", C.c_void_p), ("ldb", C.c_int64), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("b_static", C.c_int32),
                 ("bn", C.c_int32),
-                ("wait_job", C.c_int32), ("wait_all", C.c_int32), ("merge_next", C.c_int32), ("epi", GemmEpilogue), ("colsum", C.c_void_p)]
+                ("wait_job", C.c_int32), ("wait_all", C.c_int32), ("merge_next", C.c_int32), ("epi", GemmEpilogue), ("colsum", C.c_void_p),
+                ("notify", C.c_void_p)]
 
 
 class Multicast(C.Structure):
     _fields_ = [("local_base", C.c_void_p), ("multicast_base", C.c_void_p), ("bytes", C.c_size_t)]
 
 
+class RankExchange(C.Structure):    # neraf_rank_exchange
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("peers", C.c_void_p * MAX_RANKS)]
+
+
 class LossGrad(C.Structure):        # neraf_loss_grad
     _fields_ = [("gt", C.c_void_p), ("n_total", C.c_int64), ("criterion", C.c_int32), ("sums", C.c_void_p),
-                ("w_sc", C.c_float), ("w_mag", C.c_float), ("losses", C.c_void_p), ("total", C.c_void_p)]
+                ("w_sc", C.c_float), ("w_mag", C.c_float), ("losses", C.c_void_p), ("total", C.c_void_p),
+                ("fuse_sums", C.c_int32), ("sync", C.c_void_p), ("exchange", C.POINTER(RankExchange))]
+
+
+class ExchangeChunk(C.Structure):   # neraf_exchange_chunk
+    _fields_ = [("offset", C.c_int64), ("bytes", C.c_int64), ("notify", C.c_void_p), ("notify_increment", C.c_uint32),
+                ("f32", C.c_int32)]
+
+
+class GradExchange(C.Structure):    # neraf_grad_exchange
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_chunks", C.c_int32), ("max_ctas", C.c_int32),
+                ("chunks", ExchangeChunk * MAX_EXCHANGE_CHUNKS), ("multicast", C.c_void_p),
+                ("peers", C.c_void_p * MAX_RANKS), ("signals", C.c_void_p * MAX_RANKS), ("state", C.c_void_p)]
 
 
 class DpOptions(C.Structure):
     _fields_ = [("mc", C.POINTER(Multicast)), ("dw0_compact", C.c_void_p), ("defer_grid_grads", C.c_int32),
                 ("phase", C.c_int32), ("max_ctas", C.c_int32), ("loss", C.POINTER(LossGrad)),
-                ("dweights_bf16", C.POINTER(C.c_void_p))]
+                ("dweights_bf16", C.POINTER(C.c_void_p)), ("notify", C.c_void_p),
+                ("notify_increment", C.POINTER(C.c_uint32)), ("exchange", C.POINTER(GradExchange)),
+                ("zero_tail_slack", C.c_int32)]
 
 
 class MetricParams(C.Structure):     # neraf_metric_params
@@ -111,6 +131,7 @@ SIGNATURES = {
     "neraf_version": (C.c_int, []),
     "neraf_last_error": (C.c_char_p, []),
     "neraf_launch_count": (C.c_longlong, []),
+    "neraf_abi_sizeof": (C.c_size_t, [C.c_char_p]),
     "neraf_device_supported": (C.c_int, []),
     "neraf_field_sizes": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, C.POINTER(_sz), C.POINTER(_sz)]),
     "neraf_field_pack": (C.c_int, [C.POINTER(FieldDims), _i32, _pp, _pp, _vp, _sz, _vp]),
@@ -122,6 +143,7 @@ SIGNATURES = {
                                         _vp, _vp, _i64, _vp]),
     "neraf_field_backward_dp": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
                                            _vp, _vp, _i64, C.POINTER(DpOptions), _vp]),
+    "neraf_dp_exchange_grads": (C.c_int, [C.POINTER(GradExchange), _vp]),
     "neraf_field_grid_grads": (C.c_int, [C.POINTER(FieldDims), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),
     "neraf_spectral_loss_sums": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
@@ -141,6 +163,13 @@ SIGNATURES = {
     "neraf_convert_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
     **GRID_SIGNATURES,
 }
+
+# ctypes mirror of every public struct, by its C type name (layouts are checked against neraf_abi_sizeof)
+STRUCTS = {"neraf_field_dims": FieldDims, "neraf_queries": Queries, "neraf_multicast": Multicast,
+           "neraf_rank_exchange": RankExchange, "neraf_loss_grad": LossGrad, "neraf_dp_options": DpOptions,
+           "neraf_exchange_chunk": ExchangeChunk, "neraf_grad_exchange": GradExchange, "neraf_gl_params": GlParams,
+           "neraf_metric_params": MetricParams, "neraf_gemm_epilogue": GemmEpilogue, "neraf_gemm_job": GemmJob,
+           "neraf_window3d": Window3d}
 
 _lib = None
 _lock = threading.Lock()

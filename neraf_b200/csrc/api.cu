@@ -40,6 +40,18 @@ int neraf_version(void) { return NERAF_ABI_VERSION; }
 
 const char* neraf_last_error(void) { return neraf::last_error_buffer(); }
 
+size_t neraf_abi_sizeof(const char* name) {
+  if (!name) return 0;
+#define NERAF_SIZEOF(T) if (strcmp(name, #T) == 0) return sizeof(T)
+  NERAF_SIZEOF(neraf_field_dims); NERAF_SIZEOF(neraf_queries); NERAF_SIZEOF(neraf_multicast);
+  NERAF_SIZEOF(neraf_rank_exchange); NERAF_SIZEOF(neraf_loss_grad); NERAF_SIZEOF(neraf_dp_options);
+  NERAF_SIZEOF(neraf_exchange_chunk); NERAF_SIZEOF(neraf_grad_exchange); NERAF_SIZEOF(neraf_gl_params);
+  NERAF_SIZEOF(neraf_metric_params); NERAF_SIZEOF(neraf_gemm_epilogue); NERAF_SIZEOF(neraf_gemm_job);
+  NERAF_SIZEOF(neraf_window3d);
+#undef NERAF_SIZEOF
+  return 0;
+}
+
 long long neraf_launch_count(void) { return neraf::g_launch_count.load(std::memory_order_relaxed); }
 
 int neraf_device_supported(void) {

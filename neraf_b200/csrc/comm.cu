@@ -1,0 +1,257 @@
+// Data-parallel gradient exchange as ONE kernel of this library, running BESIDE the backward's job-list launch.
+//
+// Why: at the reference batch (2048 columns per GPU) the gradient all-reduce is as long as a third of the step, and
+// issued by the host after the backward it is fully exposed (SCALE_r01.json: 0.63 efficiency on 8 GPUs).  The weight
+// gradients finish in backward order, so most of them can travel while the remaining GEMMs run -- if the exchange
+// (a) needs no host call between the kernels (the step stays one CUDA graph) and (b) does not take SMs away from the
+// persistent GEMM kernel.  This kernel does both: it is launched on a parallel branch of the graph with one small CTA
+// per SM (256 threads, <= 40 registers, no shared memory: it fits beside a job-list CTA), and is driven by the
+// completion counters the job-list kernel advances as it stores gradient tiles (neraf_gemm_job.notify).
+//
+// Algorithm (two-shot all-reduce over peer-mapped "symmetric" memory; NVLink 5 / NVSwitch):
+//   per chunk c (one weight-gradient matrix, bf16; last: the bias gradients, fp32), in the order the backward finishes
+//   them:
+//     herald (block 0, one thread)  waits until THIS rank has stored chunk c (notify counter, gpu-scope acquire), then
+//                                   raises ready[c][rank] in every peer's signal buffer (system-scope release);
+//     workers (all other blocks)    wait until ready[c][q] is raised for every rank q, then reduce this rank's 1/world
+//                                   slice of the chunk: multimem.ld_reduce (the switch adds the ranks' copies, fp32
+//                                   accumulation) -> multimem.st of the sum into every rank's copy (NVLS).  Without a
+//                                   multicast mapping the same is done with plain peer loads and stores.
+//   end: workers fence (system scope) and draw a ticket; the herald waits for all tickets, raises done[rank] everywhere
+//   and waits for every rank's done flag: when the kernel ends, every rank holds the sums of every chunk.
+// Flags carry the step number (kept in `state`, advanced by the herald), so nothing is ever reset and a flag that is
+// ahead of a slow reader is still "raised".  Deadlock freedom: the job-list kernel never waits for this kernel; the
+// herald only waits for counters of its own device and for peers that run the same graph.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace neraf {
+
+constexpr int kCommThreads = 256;
+constexpr int kReadyOffset = 2048;             // u32 ready[NERAF_MAX_EXCHANGE_CHUNKS][NERAF_MAX_RANKS]
+constexpr int kDoneOffset = 3072;              // u32 done[NERAF_MAX_RANKS]
+static_assert(kReadyOffset + NERAF_MAX_EXCHANGE_CHUNKS * NERAF_MAX_RANKS * 4 <= kDoneOffset, "signal buffer layout");
+static_assert(kDoneOffset + NERAF_MAX_RANKS * 4 <= NERAF_EXCHANGE_BYTES, "signal buffer layout");
+constexpr long long kCommSpinLimit = 4000000000LL;      // ~2 s: a lost peer traps instead of hanging the GPU
+
+struct CommChunk {
+  unsigned long long offset, bytes;            // of the exchange region; multiples of 16
+  const unsigned int* notify; unsigned int increment;
+  int f32;
+};
+struct CommArgs {
+  int n_chunks, world, rank;
+  CommChunk ch[NERAF_MAX_EXCHANGE_CHUNKS];
+  uint8_t* mc;                                 // multicast alias of the region (nullptr: peer loads / stores)
+  uint8_t* peers[NERAF_MAX_RANKS];
+  uint8_t* sig[NERAF_MAX_RANKS];
+  unsigned int* state;                         // [0] steps completed  [1] worker tickets
+};
+
+__device__ __forceinline__ unsigned int comm_ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int comm_ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void comm_st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool reached(unsigned int value, unsigned int target) { return (int)(value - target) >= 0; }
+
+__device__ __forceinline__ uint4 mm_ld_reduce_bf16(const void* p) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 mm_ld_reduce_f32(const void* p) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st(void* p, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_peer(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer(void* p, const uint4& v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// sum of the ranks' 16-byte granules at byte offset `off` without NVLS: fp32 accumulation in rank order
+__device__ __forceinline__ uint4 peer_sum(const CommArgs& A, unsigned long long off, bool f32) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int q = 0; q < A.world; ++q) {
+    const uint4 v = ld_peer(A.peers[q] + off);
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+    if (f32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+  }
+  uint4 r;
+  if (f32) {
+    r = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+  } else {
+    unsigned int o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+      o[i] = *reinterpret_cast<const unsigned int*>(&h);
+    }
+    r = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  return r;
+}
+
+__global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
+  const unsigned int seq = A.state[0] + 1u;               // this step's number: what a raised flag holds
+  unsigned int* my_sig_ready = reinterpret_cast<unsigned int*>(A.sig[A.rank] + kReadyOffset);
+  unsigned int* my_sig_done = reinterpret_cast<unsigned int*>(A.sig[A.rank] + kDoneOffset);
+
+  if (blockIdx.x == 0) {
+    // ------------------------------------------------------------------ herald
+    if (threadIdx.x == 0) {
+      for (int c = 0; c < A.n_chunks; ++c) {
+        const CommChunk& ch = A.ch[c];
+        if (ch.notify != nullptr) {
+          const unsigned int target = seq * ch.increment;   // counters only ever advance (mod 2^32 arithmetic)
+          const long long t0 = clock64();
+          while (!reached(comm_ld_acquire_gpu(ch.notify), target)) {
+            __nanosleep(200);
+            if (clock64() - t0 > kCommSpinLimit) __trap();
+          }
+        }
+        __threadfence_system();
+        for (int q = 0; q < A.world; ++q)
+          comm_st_release_sys(reinterpret_cast<unsigned int*>(A.sig[q] + kReadyOffset) + c * NERAF_MAX_RANKS + A.rank, seq);
+      }
+      // every worker of this rank has reduced and broadcast its slices
+      {
+        const long long t0 = clock64();
+        while (comm_ld_acquire_gpu(A.state + 1) != gridDim.x - 1) {
+          __nanosleep(200);
+          if (clock64() - t0 > kCommSpinLimit) __trap();
+        }
+      }
+      __threadfence_system();
+      for (int q = 0; q < A.world; ++q)
+        comm_st_release_sys(reinterpret_cast<unsigned int*>(A.sig[q] + kDoneOffset) + A.rank, seq);
+      for (int q = 0; q < A.world; ++q) {
+        const long long t0 = clock64();
+        while (!reached(comm_ld_acquire_sys(my_sig_done + q), seq)) {
+          __nanosleep(200);
+          if (clock64() - t0 > kCommSpinLimit) __trap();
+        }
+      }
+      A.state[1] = 0u;
+      A.state[0] = seq;
+      __threadfence();
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- workers
+  const int workers = (int)gridDim.x - 1;
+  const long long wtid = (long long)(blockIdx.x - 1) * kCommThreads + threadIdx.x;
+  const long long wthreads = (long long)workers * kCommThreads;
+  for (int c = 0; c < A.n_chunks; ++c) {
+    const CommChunk& ch = A.ch[c];
+    if (threadIdx.x < A.world) {
+      const unsigned int* flag = my_sig_ready + c * NERAF_MAX_RANKS + threadIdx.x;
+      const long long t0 = clock64();
+      while (!reached(comm_ld_acquire_sys(flag), seq)) {
+        __nanosleep(200);
+        if (clock64() - t0 > kCommSpinLimit) __trap();
+      }
+    }
+    __syncthreads();
+    // this rank's slice of the chunk, in 16-byte granules
+    const long long granules = (long long)(ch.bytes / 16);
+    const long long g0 = granules * A.rank / A.world, g1 = granules * (A.rank + 1) / A.world;
+    const unsigned long long base = ch.offset + (unsigned long long)g0 * 16;
+    const long long n = g1 - g0;
+    const bool f32 = ch.f32 != 0;
+    if (A.mc != nullptr) {
+      long long i = wtid;
+      for (; i + 3 * wthreads < n; i += 4 * wthreads) {      // four requests in flight per thread
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const void* p = A.mc + base + (unsigned long long)(i + u * wthreads) * 16;
+          v[u] = f32 ? mm_ld_reduce_f32(p) : mm_ld_reduce_bf16(p);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mm_st(A.mc + base + (unsigned long long)(i + u * wthreads) * 16, v[u]);
+      }
+      for (; i < n; i += wthreads) {
+        void* p = A.mc + base + (unsigned long long)i * 16;
+        const uint4 v = f32 ? mm_ld_reduce_f32(p) : mm_ld_reduce_bf16(p);
+        mm_st(p, v);
+      }
+    } else {
+      for (long long i = wtid; i < n; i += wthreads) {
+        const unsigned long long off = base + (unsigned long long)i * 16;
+        const uint4 v = peer_sum(A, off, f32);
+        for (int q = 0; q < A.world; ++q) st_peer(A.peers[q] + off, v);
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(A.state + 1, 1u);
+}
+
+}  // namespace neraf
+
+using namespace neraf;
+
+extern "C" int neraf_dp_exchange_grads(const neraf_grad_exchange* x, neraf_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NERAF_REQUIRE(x, "dp_exchange_grads: null argument");
+  NERAF_REQUIRE(x->world >= 1 && x->world <= NERAF_MAX_RANKS && x->rank >= 0 && x->rank < x->world,
+                "dp_exchange_grads: bad world / rank");
+  NERAF_REQUIRE(x->n_chunks >= 1 && x->n_chunks <= NERAF_MAX_EXCHANGE_CHUNKS, "dp_exchange_grads: 1..%d chunks",
+                NERAF_MAX_EXCHANGE_CHUNKS);
+  NERAF_REQUIRE(x->state, "dp_exchange_grads: state is null");
+  CommArgs A = {};
+  A.n_chunks = x->n_chunks; A.world = x->world; A.rank = x->rank;
+  A.mc = reinterpret_cast<uint8_t*>(x->multicast);
+  A.state = x->state;
+  NERAF_REQUIRE(!A.mc || ((uintptr_t)A.mc & 15) == 0, "dp_exchange_grads: misaligned multicast mapping");
+  for (int r = 0; r < x->world; ++r) {
+    NERAF_REQUIRE(x->peers[r] && x->signals[r], "dp_exchange_grads: region / signal buffer of rank %d is null", r);
+    NERAF_REQUIRE(((uintptr_t)x->peers[r] & 15) == 0, "dp_exchange_grads: misaligned region of rank %d", r);
+    A.peers[r] = reinterpret_cast<uint8_t*>(x->peers[r]);
+    A.sig[r] = reinterpret_cast<uint8_t*>(x->signals[r]);
+  }
+  for (int c = 0; c < x->n_chunks; ++c) {
+    const neraf_exchange_chunk& s = x->chunks[c];
+    NERAF_REQUIRE(s.offset % 16 == 0 && s.bytes % 16 == 0, "dp_exchange_grads: chunk %d is not 16-byte tileable", c);
+    NERAF_REQUIRE(!s.notify || s.notify_increment > 0, "dp_exchange_grads: chunk %d: notify without an increment", c);
+    A.ch[c] = CommChunk{(unsigned long long)s.offset, (unsigned long long)s.bytes, s.notify, s.notify_increment, s.f32 ? 1 : 0};
+  }
+  // one small CTA per SM (it must fit BESIDE a CTA of the job-list kernel), never more than are resident at once
+  int grid = x->max_ctas > 0 ? x->max_ctas : sm_count();
+  if (grid > sm_count()) grid = sm_count();
+  if (grid < 2) grid = 2;
+  grad_exchange_kernel<<<(unsigned)grid, kCommThreads, 0, stream>>>(A);
+  NERAF_CHECK_LAUNCH("grad_exchange_kernel");
+  return NERAF_OK;
+}

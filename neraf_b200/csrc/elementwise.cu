@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restr
                                                             const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
                                                             float* __restrict__ dW, float* __restrict__ dg,
                                                             const float* __restrict__ compact, int64_t E, int64_t ld_c) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // programmatic dependent launch: the backward GEMMs are complete
   const int t = threadIdx.x;
   const int64_t n0 = (int64_t)blockIdx.x * GG_ROWS;
   const int rows = (int)(N - n0 < GG_ROWS ? N - n0 : GG_ROWS);
@@ -186,8 +187,15 @@ int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int6
   if (dg && !dg_is_zero) NERAF_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)K * 4, stream));
   const unsigned grid = (unsigned)ceil_div(N, GG_ROWS);
   const float* cp = dW ? compact : nullptr;
-  if (K <= 256 * 4) grid_grads_kernel<4><<<grid, GG_TPB, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, cp, E, ld_c);
-  else grid_grads_kernel<8><<<grid, GG_TPB, 0, stream>>>(s, g, W, ldw, N, K, dW, dg, cp, E, ld_c);
+  // no memset in front of it: the kernel follows the backward's job-list launch directly and may be set up under its tail
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GG_TPB); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ((!dg || dg_is_zero) && pdl_enabled()) ? 1 : 0;
+  if (K <= 256 * 4) NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<4>, s, g, W, ldw, N, K, dW, dg, cp, E, ld_c));
+  else NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<8>, s, g, W, ldw, N, K, dW, dg, cp, E, ld_c));
   NERAF_CHECK_LAUNCH("grid_grads_kernel");
   return NERAF_OK;
 }
@@ -223,11 +231,6 @@ int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cud
 // ---------------------------------------------------------------------------------------------
 // Gradient through y = 10*tanh(z):  dz = dout * (10 - y*y/10)
 // ---------------------------------------------------------------------------------------------
-struct HeadColsum {
-  float* ptr[8];          // one bias-gradient vector per head (C <= 8)
-  long long width;        // columns per head; 0 = no column sums
-};
-
 constexpr int kHeadRows = 32;        // rows per block of head_backward_kernel (4 per thread, all loads in flight at once)
 
 // Block = 32 columns x 8 row lanes over kHeadRows rows: coalesced 128-byte row segments, the bias gradient
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
 
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
                   int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream,
-                  const neraf_loss_grad* loss) {
+                  const neraf_loss_grad* loss, float* zero, int64_t n_zero) {
   if (M <= 0 || N <= 0) return NERAF_OK;
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, kHeadRows));
   NERAF_REQUIRE(grid.y <= 65535, "head_backward: batch too large for one launch (%lld)", (long long)M);
@@ -308,6 +311,8 @@ int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float
     for (int64_t c = 0; c < heads; ++c) cs.ptr[c] = colsum[c];
     cs.width = head_width;
   }
+  if (loss && loss->fuse_sums) return loss_head_fused(y, M, N, dz_f32, ld_f32, dz_bf16, ld_bf16, cs, loss, zero, n_zero, stream);
+  NERAF_REQUIRE(n_zero == 0, "head_backward: only the fused loss kernel clears a region");
   if (loss) {
     NERAF_REQUIRE(loss->gt && loss->sums && loss->n_total > 0 && loss->criterion >= 0 && loss->criterion <= 2,
                   "head_backward: bad neraf_loss_grad");

@@ -367,7 +367,8 @@ static int field_forward_impl(const neraf_field_dims* dims, int precision, const
   if (side) NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
   // the counters were cleared by field_prep_kernel above, and every job-list launch clears them again before it exits:
   // neither this launch nor the backward's needs a memset node
-  NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream, 0, true));
+  // (programmatic dependent launch only when the launch has ONE predecessor, the prep kernel: not beside the helper stream)
+  NERAF_TRY(mega_run(jobs, l.L + 1, at(ws, l.counters), l.counters_bytes, stream, 0, true, side == nullptr));
   return NERAF_OK;
 }
 
@@ -400,6 +401,8 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   int phase = opt ? opt->phase : 0;
   const int max_ctas = opt ? opt->max_ctas : 0;
   const neraf_loss_grad* loss = opt ? opt->loss : nullptr;
+  const bool zero_tail_slack = opt && opt->zero_tail_slack;
+  uint32_t* notify = opt ? opt->notify : nullptr;
   void* const* dw16 = opt ? opt->dweights_bf16 : nullptr;
   NERAF_REQUIRE(phase >= 0 && phase <= 2, "field_backward_dp: phase must be 0, 1 or 2");
   Layout l;
@@ -481,8 +484,13 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   // buffers (and dgrid, accumulated by grid_grads) are zeroed with as few memsets as their addresses allow -- one
   // when the caller laid them out back to back (neraf_b200/field.py does).
   bool dgrid_zeroed = false;
+  float* zero_start = nullptr;                       // one 16-byte-tileable span: cleared by the fused loss kernel instead
+  int64_t zero_n = 0;
   if (phase != 2) {
     const int nb = l.L + l.C;
+    struct Span { float* a; float* b; };
+    Span spans[NERAF_MAX_TRUNK + 8 + 1];
+    int ns = 0;
     int i = 0;
     while (i < nb) {
       float* start = dbiases[i];
@@ -490,12 +498,22 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       int j = i + 1;
       while (j < nb && dbiases[j] == end) { end += j < l.L ? l.n[j] : l.F; ++j; }
       if (j == nb && dgrid && l.G > 0 && dgrid == end && !defer_grid_grads) { end += l.G; dgrid_zeroed = true; }
-      NERAF_CHECK_CUDA(cudaMemsetAsync(start, 0, (size_t)(end - start) * 4, stream));
+      spans[ns++] = Span{start, end};
       i = j;
+    }
+    const bool fused_clear = loss && loss->fuse_sums && ns == 1 && ((uintptr_t)spans[0].a & 15) == 0 &&
+                             ((spans[0].b - spans[0].a) % 4 == 0 || zero_tail_slack);
+    if (fused_clear) {
+      zero_start = spans[0].a;
+      zero_n = round_up(spans[0].b - spans[0].a, 4);
+    } else {
+      for (int k = 0; k < ns; ++k)
+        NERAF_CHECK_CUDA(cudaMemsetAsync(spans[k].a, 0, (size_t)(spans[k].b - spans[k].a) * 4, stream));
     }
   }
   void* dzh = at(ws, l.dzh);
-  if (phase != 2) NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream, loss));
+  if (phase != 2)
+    NERAF_TRY(head_backward(dout, out, B, l.CF, nullptr, 0, dzh, l.ld_h, dbiases + l.L, l.F, stream, loss, zero_start, zero_n));
   bool heads_contiguous = true;                      // the C head gradients form one (C*F, W) matrix?
   for (int c = 1; c < l.C; ++c) heads_contiguous = heads_contiguous && dweights[l.L + c] == dweights[l.L] + (size_t)c * l.F * l.W;
   // Fused all-reduce (data parallel): weight gradients are not stored but added into every rank's copy of the
@@ -511,6 +529,8 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   };
   NERAF_REQUIRE(!mc || heads_contiguous, "field_backward_dp: head gradients must be contiguous");
   MegaJob jobs[NERAF_MEGA_MAX_JOBS];
+  int notify_slot[NERAF_MEGA_MAX_JOBS];               // which completion counter of neraf_dp_options.notify a job advances
+  for (int i = 0; i < NERAF_MEGA_MAX_JOBS; ++i) notify_slot[i] = -1;
   int nj = 0;
   // phase 1 stops before the last dgrad (dZ of layer 1) and the per-query block of dW1; phase 2 is exactly those:
   // the caller all-reduces what phase 1 finished while phase 2 computes (neraf_dp_options).
@@ -523,6 +543,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     j.colsum = dbiases[last];
   }
   if (phase != 2) {                                    // head weight gradients (all heads in one GEMM)
+    notify_slot[nj] = l.L;
     MegaJob& j = jobs[nj++];
     j = make_wgrad_job(l.CF, l.W, B, dzh, l.ld_h, at(ws, l.x[last]), l.ldx[last], -1);
     j.wait_all = 0;
@@ -551,6 +572,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       if (mc && phase == 0) j.merge_next = 1;
     }
     if (phase == 2 && i == 1) continue;                // dW_1 belongs to phase 1
+    notify_slot[nj] = i;
     MegaJob& w = jobs[nj++];                           // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
     if (i > 0) {
       w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
@@ -573,7 +595,45 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       }
     }
   }
-  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas, true));   // left clean by the forward's launch
+  // Completion counters for a concurrent consumer (the data-parallel gradient exchange, neraf_dp_exchange_grads): one per
+  // weight gradient, one for "every bias gradient is final" = the last job of the dgrad chain (its row blocks need all
+  // row blocks of every earlier link; the heads' bias gradients were complete before this launch).
+  unsigned int increments[NERAF_MEGA_MAX_JOBS] = {0};
+  if (notify) {
+    NERAF_REQUIRE(phase == 0, "field_backward_dp: completion counters need the one-launch backward (phase 0)");
+    notify_slot[producer] = l.L + 1;
+    for (int j = 0; j < nj; ++j)
+      if (notify_slot[j] >= 0) jobs[j].notify = notify + notify_slot[j];
+  }
+  // Data parallel: the gradient exchange kernel runs BESIDE the job-list launch (helper stream forked here, after the
+  // head-gradient kernel, joined after both) and follows the completion counters.
+  const neraf_grad_exchange* xg = opt ? opt->exchange : nullptr;
+  SideStream* side = xg ? side_stream() : nullptr;
+  NERAF_REQUIRE(!xg || notify, "field_backward_dp: exchange needs notify");
+  if (side) {
+    NERAF_CHECK_CUDA(cudaEventRecord(side->fork, stream));
+    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
+  // left clean by the forward's launch; set up under the tail of the head-gradient kernel that precedes it
+  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas, true, phase != 2, increments));
+  unsigned int by_slot[NERAF_MAX_TRUNK + 2] = {0};
+  if (notify)
+    for (int j = 0; j < nj; ++j)
+      if (notify_slot[j] >= 0) by_slot[notify_slot[j]] = increments[j];
+  if (notify && opt->notify_increment)
+    for (int k = 0; k < l.L + 2; ++k) opt->notify_increment[k] = by_slot[k];
+  if (xg) {
+    neraf_grad_exchange x = *xg;                       // chunks that name one of this call's counters get its increment
+    for (int c = 0; c < x.n_chunks && c < NERAF_MAX_EXCHANGE_CHUNKS; ++c) {
+      const uint32_t* nf = x.chunks[c].notify;
+      if (nf >= notify && nf < notify + l.L + 2) x.chunks[c].notify_increment = by_slot[nf - notify];
+    }
+    NERAF_TRY(neraf_dp_exchange_grads(&x, side ? side->stream : stream));
+    if (side) {
+      NERAF_CHECK_CUDA(cudaEventRecord(side->done, side->stream));
+      NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
+    }
+  }
   if (!heads_contiguous && phase != 2 && !dw16)
     for (int c = 0; c < l.C; ++c)
       NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,

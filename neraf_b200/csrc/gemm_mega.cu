@@ -77,6 +77,8 @@ struct alignas(64) DeviceJob {
   const __nv_bfloat16* gate; long long ldg;
   float* out_f32; long long ld_f32;
   float* colsum;
+  unsigned int* notify;            // optional: += 1 (gpu-scope release) per epilogue warp and tile, never cleared -- a concurrent
+                                   // kernel (the data-parallel gradient exchange) learns from it that the job's output is complete
   const float* loss_gt; long long ld_gt; double* loss_sums;   // out_mode 3 only: spectral-loss partial sums (fused)
 };
 
@@ -231,6 +233,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above overlapped the tail of the previous kernel of the stream; nothing
+  // it produced has been touched yet.  This grid's CTAs are all resident by now, so the next kernel may start moving in.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -703,7 +709,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       if (out_mode == 4) used_multicast = true;      // fenced once, at the end of the kernel
       __syncwarp();
       if (tracer) { stamp_clock(P.trace, tile, TR_CK_FENCE); stamp(P.trace, tile, TR_EPI_DONE); }
-      if (lane == 0) red_release_add(P.counters + J.cnt_off + mt, 1u);   // ... before the row block's progress is (16 arrivals per tile)
+      if (lane == 0) {
+        red_release_add(P.counters + J.cnt_off + mt, 1u);   // ... before the row block's progress is (16 arrivals per tile)
+        if (J.notify != nullptr) red_release_add(J.notify, 1u);
+      }
     }
     // multimem.red reductions are fire-and-forget while the kernel runs (the NVLink queue drains behind the remaining
     // tiles); one system-scope fence per warp makes them performed before the kernel can end
@@ -734,7 +743,7 @@ int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t col
                       CUtensorMap* out);
 
 int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas,
-             bool counters_clean) {
+             bool counters_clean, bool pdl, unsigned int* notify_increment) {
   using namespace umma;
   NERAF_REQUIRE(jobs && n_jobs > 0 && n_jobs <= NERAF_MEGA_MAX_JOBS, "mega_run: 1..%d jobs", NERAF_MEGA_MAX_JOBS);
   static MegaParams P;          // large: build in static storage (single-threaded driver, see header conventions)
@@ -808,6 +817,8 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
                   "mega_run: job %d: mask_out needs the LeakyReLU epilogue and a bf16 output", i);
     NERAF_REQUIRE(!(s.epi.gate && s.epi.gate_mask), "mega_run: job %d: gate and gate_mask are exclusive", i);
     d.colsum = s.colsum;
+    d.notify = s.notify;
+    if (notify_increment) notify_increment[i] = (unsigned int)(d.num_m * d.num_n) * MEGA_EPI_WARPS * 2;
     d.loss_gt = s.epi.out_f32 ? s.epi.loss_gt : nullptr; d.ld_gt = s.epi.ld_gt; d.loss_sums = s.epi.loss_sums;
     NERAF_REQUIRE(!s.epi.loss_gt || s.epi.out_f32, "mega_run: job %d: loss_gt needs an fp32 output", i);
   }
@@ -840,10 +851,12 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   cfg.blockDim = dim3(MEGA_THREADS);
   cfg.dynamicSmemBytes = MEGA_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (pdl && pdl_enabled() && !trace_path) ? 2 : 1;
   // The CTA pairs spin on counters other pairs write, with a static tile stride: every pair of the grid must be
   // co-resident.  Never launch more pairs than the device can hold at once for this kernel's footprint (asked once
   // per device; an SM held by a concurrent kernel at run time is the caller's business: max_ctas).

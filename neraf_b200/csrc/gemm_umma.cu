@@ -358,7 +358,8 @@ static int tile_override() {
 }
 
 // NERAF_PDL=0 disables programmatic dependent launch (debugging).
-static bool pdl_enabled() {
+}  // namespace umma
+bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("NERAF_PDL");
@@ -366,6 +367,7 @@ static bool pdl_enabled() {
   }
   return v != 0;
 }
+namespace umma {
 
 template <int BN, int CG>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {

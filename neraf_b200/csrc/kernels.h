@@ -36,8 +36,11 @@ typedef neraf_gemm_job MegaJob;      // public contract: include/neraf_b200.h
 // max_ctas: 0 = one CTA per SM; otherwise an upper bound on the grid (a concurrent kernel gets the other SMs)
 // counters_clean: the caller guarantees the counter buffer is zero (cleared explicitly, or last used by this kernel,
 // which clears what it used before it exits): no memset node is issued
+// pdl: launch with programmatic stream serialization (the previous work of the stream must be a kernel of this library
+// that executes griddepcontrol.launch_dependents, or any kernel: the prologue then simply starts when that one ends)
+// notify_increment (optional, host, n_jobs entries): by how much one launch advances each job's `notify` counter
 int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas = 0,
-             bool counters_clean = false);
+             bool counters_clean = false, bool pdl = false, unsigned int* notify_increment = nullptr);
 
 // elementwise.cu
 int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out, void* out_t,
@@ -61,11 +64,21 @@ int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int6
                bool dg_is_zero, cudaStream_t stream, const float* compact = nullptr, int64_t E = 0, int64_t ld_c = 0);
 // out[n] = sum_m X[m*ld + n]   fp32 row-major (M,N)
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
+struct HeadColsum {
+  float* ptr[8];          // one bias-gradient vector per head (C <= 8)
+  long long width;        // columns per head; 0 = no column sums
+};
+// NERAF_PDL=0 disables programmatic dependent launch everywhere (debugging / A-B timing)
+bool pdl_enabled();
+// loss.cu: the loss's partial sums, (data parallel) their exchange, the loss gradient through 10 tanh and the heads'
+// bias gradients in ONE launch (neraf_loss_grad.fuse_sums); zero[0 .. n_zero) is cleared before the gradient half
+int loss_head_fused(const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16, int64_t ld_bf16,
+                    const HeadColsum& cs, const neraf_loss_grad* loss, float* zero, int64_t n_zero, cudaStream_t stream);
 // dz = dout * (10 - y^2/10): gradient through 10*tanh; outputs fp32 (M,N) and/or bf16 (M,N) row-major.
 // colsum (optional): per-head bias-gradient buffers, column n is added (atomics) to colsum[n / head_width][n % head_width]
 // loss (optional): dout is not read but evaluated from (y, loss->gt, loss->sums) as neraf_spectral_loss_backward does.
 int head_backward(const float* dout, const float* y, int64_t M, int64_t N, float* dz_f32, int64_t ld_f32, void* dz_bf16,
                   int64_t ld_bf16, float* const* colsum, int64_t head_width, cudaStream_t stream,
-                  const neraf_loss_grad* loss = nullptr);
+                  const neraf_loss_grad* loss = nullptr, float* zero = nullptr, int64_t n_zero = 0);
 
 }  // namespace neraf

@@ -502,8 +502,20 @@ class GraphedTrainStep:
     def __init__(self, model: NeRAFAudioModel, example_batch: Dict[str, torch.Tensor], warmup: int = 3,
                  fused_allreduce: bool = False, overlap_allreduce: bool = False,
                  grad_dtype: torch.dtype = torch.float32, functional: Optional[bool] = None,
-                 fuse_loss_sums: bool = False):
+                 fuse_loss_sums: bool = False, exchange: str = "auto"):
         self.model = model
+        # Data parallel: how the gradients (and the loss's four partial sums) cross the ranks.
+        #   "kernel": by the library's own kernels over symmetric memory -- the sums inside the fused loss kernel
+        #             (neraf_rank_exchange), the gradients by neraf_dp_exchange_grads running BESIDE the backward's GEMM
+        #             launch -- so the whole step is ONE CUDA graph with no host-issued collective (bf16 path, bf16
+        #             gradients on the wire, fp32 accumulation in the switch);
+        #   "nccl":   two graphs around an eager 32-byte all-reduce + one NCCL all-reduce of the flat buffer after the
+        #             backward (allreduce_grads()) -- the round-1 form, kept for A/B timing and for the fp32 path;
+        #   "auto":   "kernel" when it applies (bf16 field, symmetric memory available), else "nccl".
+        if exchange not in ("auto", "kernel", "nccl"):
+            raise ValueError("exchange must be 'auto', 'kernel' or 'nccl'")
+        self.exchange = exchange
+        self.kernel_exchange = False
         # True: the loss's partial sums come out of the heads' forward epilogue (neraf_field_forward_loss_sums) -- one
         # launch and a re-read of the prediction less, but the extra exp / target loads sit in the epilogue of the LAST
         # link of the forward's dependency chain: measured 4.5 us per step slower at B=2048 (tools/ab_step.py: 378.0
@@ -640,6 +652,7 @@ class GraphedTrainStep:
         tail_grid = grid_p is not None and not defer
         if tail_grid:
             sizes = sizes + [grid_p.numel()]
+        sizes = sizes + [3]        # slack: the fused loss kernel clears the bias gradients (/ dg) in whole 16-byte words
         # Fused all-reduce (experimental): the flat buffer lives in symmetric memory and the weight-gradient GEMMs add
         # their tiles into every rank's copy through its multicast alias.  Otherwise plain memory + one NCCL all-reduce.
         self.flat_grad, mc_ptr = None, 0
@@ -668,6 +681,29 @@ class GraphedTrainStep:
             dgrid = parts[first_b + n_b].view_as(grid_p) if tail_grid else torch.zeros_like(grid_p)
         if defer:
             dws = [torch.zeros_like(weights[0])] + dws
+        # ---- data parallel, exchange by the library's own kernels (see __init__): the bf16 weight gradients and the fp32
+        # bias gradients live in ONE symmetric-memory region (every rank maps every rank's copy; NVLS multicast alias
+        # when the fabric has one), a second small symmetric buffer carries the flags
+        self._xchg = None
+        want_kernel = (self.group is not None and defer and field.precision == "bf16" and not self.fused_allreduce
+                       and not self.overlap_allreduce and self.exchange in ("auto", "kernel")
+                       and all(t.shape[1] % 8 == 0 for t in weights[1:]))
+        if self.exchange == "kernel" and not want_kernel:
+            raise ValueError("exchange='kernel' needs a process group, the bf16 field with a grid feature and layer "
+                             "widths that are multiples of 8")
+        if want_kernel:
+            try:
+                self._xchg = self._setup_kernel_exchange(dev, world, n_weight_elems, [b.numel() for b in biases])
+            except Exception as e:                 # no symmetric memory on this fabric
+                if self.exchange == "kernel":
+                    raise
+                import warnings
+                warnings.warn(f"neraf_b200: symmetric-memory gradient exchange unavailable ({e}); using NCCL")
+                self._xchg = None
+        self.kernel_exchange = self._xchg is not None
+        if self.kernel_exchange:                   # bias gradients accumulate straight into the exchanged region
+            dbs = list(torch.split(self._xchg["bias"][:sum(b.numel() for b in biases)], [b.numel() for b in biases]))
+            dbs = [v.view_as(t) for v, t in zip(dbs, biases)]
         own_grid = grid_p is not None and self._producer is None       # the constant vector is a parameter of the step
         order = list(weights) + list(biases) + ([grid_p] if own_grid else [])
         views = dws + dbs + ([dgrid] if own_grid else [])
@@ -694,6 +730,21 @@ class GraphedTrainStep:
         lg.losses = losses.data_ptr()          # ... and so are the two loss values and their sum
         self.total_loss = torch.zeros((), dtype=torch.float32, device=dev)
         lg.total = self.total_loss.data_ptr()
+        # ONE loss launch: partial sums -> grid barrier (+ the ranks' exchange of the four sums) -> gradient
+        # (neraf_loss_grad.fuse_sums).  Not with the two-graph NCCL form (the host all-reduces the sums in between) and
+        # not when the heads' epilogue forms the sums.
+        self._sync = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._fused_loss = ((self.group is None or self.kernel_exchange) and not self.fuse_loss_sums
+                            and (self.kernel_exchange or os.environ.get("NERAF_FUSED_LOSS", "1") != "0"))   # =0: A/B timing
+        self._rank_x = None
+        if self._fused_loss:
+            lg.fuse_sums, lg.sync = 1, self._sync.data_ptr()
+            if self.kernel_exchange:
+                self._rank_x = _lib.RankExchange()
+                self._rank_x.world, self._rank_x.rank = world, self._xchg["rank"]
+                for r, pz in enumerate(self._xchg["signal_ptrs"]):
+                    self._rank_x.peers[r] = pz
+                lg.exchange = C.pointer(self._rank_x)
         w_arr, b_arr = _lib.ptr_array(weights), _lib.ptr_array(biases)
         dw_arr, db_arr = _lib.ptr_array(dws), _lib.ptr_array(dbs)
         self._keep = (pack, ws, out, losses, views, qs, w_arr, b_arr, dw_arr, db_arr, dims, lg)
@@ -703,9 +754,17 @@ class GraphedTrainStep:
         # layout as the fp32 flat buffer), so the only conversion passes left are the 40 KB of bias gradients before
         # and the widening of the reduced sums after the collective
         self._flat_low, dw16_arr = None, None
-        if (self.grad_dtype == torch.bfloat16 and defer and field.precision == "bf16" and not self.nvls
+        if self.kernel_exchange or (self.grad_dtype == torch.bfloat16 and defer and field.precision == "bf16" and not self.nvls
                 and not self.overlap_allreduce and all(t.shape[1] % 8 == 0 for t in weights[1:])):
-            self._flat_low = torch.zeros(sum(sizes), dtype=torch.bfloat16, device=dev)
+            self._flat_low = (self._xchg["weights16"] if self.kernel_exchange
+                              else torch.zeros(sum(sizes), dtype=torch.bfloat16, device=dev))
+            if self.kernel_exchange:               # view with the flat buffer's layout (weights | nothing else is read)
+                sizes16 = sizes[:nw + 1]
+                parts16 = list(torch.split(self._flat_low[:sum(sizes16)], sizes16))
+                dw16 = [parts16[nw]] + parts16[:nw]
+                dw16_arr = _lib.ptr_array(dw16)
+                self._n_weight_elems = n_weight_elems
+        if self._flat_low is not None and not self.kernel_exchange:
             parts16 = list(torch.split(self._flat_low, sizes))
             dw16 = [parts16[nw]] + parts16[:nw]                   # entry 0: the compact dW1 block
             dw16_arr = _lib.ptr_array(dw16)
@@ -727,6 +786,39 @@ class GraphedTrainStep:
             o.defer_grid_grads = 1 if defer else 0
             o.loss = C.pointer(lg)
             o.dweights_bf16 = dw16_arr
+            o.zero_tail_slack = 1
+        if self.kernel_exchange:
+            # completion counters the backward advances + the chunk table of the exchange, in the order the backward
+            # finishes the gradients: heads, trunk layers L..2, the compact dW1 block, and last the bias gradients
+            L = len(weights) - field.sound_rez
+            self._notify = torch.zeros(L + 2, dtype=torch.int32, device=dev)
+            self._notify_inc = (C.c_uint32 * (L + 2))()
+            gx = _lib.GradExchange()
+            gx.world, gx.rank, gx.max_ctas = world, self._xchg["rank"], int(os.environ.get("NERAF_COMM_CTAS_KERNEL", "0"))
+            offs16 = [0]
+            for n_el in sizes[:nw + 1]:
+                offs16.append(offs16[-1] + n_el * 2)
+            n_heads_el = sum(t.numel() for t in weights[L:])
+            chunks = [(offs16[L - 1], n_heads_el * 2, L, 0)]                       # heads (contiguous)
+            for i in range(L - 1, 0, -1):                                           # trunk layer i = red_w[i - 1]
+                chunks.append((offs16[i - 1], sizes[i - 1] * 2, i, 0))
+            chunks.append((offs16[nw], sizes[nw] * 2, 0, 0))                        # compact dW1 block
+            chunks.append((self._xchg["bias_offset"], self._xchg["bias_bytes"], L + 1, 1))
+            gx.n_chunks = len(chunks)
+            for c, (off, nbytes, slot, f32) in enumerate(chunks):
+                gx.chunks[c].offset, gx.chunks[c].bytes = off, nbytes
+                gx.chunks[c].notify = self._notify.data_ptr() + 4 * slot
+                gx.chunks[c].f32 = f32
+            gx.multicast = self._xchg["multicast"] or None
+            for r in range(world):
+                gx.peers[r] = self._xchg["region_ptrs"][r]
+                gx.signals[r] = self._xchg["signal_ptrs"][r]
+            self._comm_state = torch.zeros(4, dtype=torch.int32, device=dev)
+            gx.state = self._comm_state.data_ptr()
+            self._gx = gx
+            opt1.notify = self._notify.data_ptr()
+            opt1.notify_increment = C.cast(self._notify_inc, C.POINTER(C.c_uint32))
+            opt1.exchange = C.pointer(gx)
         opt1.phase, opt1.max_ctas = (1 if self.overlap else 0), 0
         opt2.phase, opt2.max_ctas = 2, max(2, (sm_count - self.comm_ctas) // 2 * 2)
         # regions of the flat buffer: what the first backward graph finishes | what the second one does
@@ -758,8 +850,9 @@ class GraphedTrainStep:
                                                              b_arr, pack.data_ptr(), pack.numel(), 1, ws.data_ptr(),
                                                              ws.numel(), out.data_ptr(), 1, None,
                                                              self.sums.data_ptr(), s))
-                _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
-                                                        self.sums.data_ptr(), 1, s))
+                if not self._fused_loss:
+                    _lib.check(lib.neraf_spectral_loss_sums(out.data_ptr(), st["data"].data_ptr(), n_local,
+                                                            self.sums.data_ptr(), 1, s))
             if self.nvls:
                 torch.cuda.current_stream(dev).wait_stream(zero_stream)
 
@@ -776,6 +869,8 @@ class GraphedTrainStep:
                                                    _lib.stream_ptr(dev)))
 
         def grid_part():          # after the exchange: the grid-block gradients from the REDUCED db1, dW1 block copied back
+            if self.kernel_exchange:      # bf16 sums (every rank holds them) -> the fp32 .grad views
+                self.flat_grad[:n_weight_elems].copy_(self._flat_low[:n_weight_elems])
             if defer:
                 _lib.check(lib.neraf_field_grid_grads(C.byref(dims), grid_p.data_ptr(), weights[0].data_ptr(),
                                                       dbs[0].data_ptr(), compact.data_ptr(), dws[0].data_ptr(),
@@ -802,6 +897,30 @@ class GraphedTrainStep:
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        if self.kernel_exchange:
+            # ONE graph per step on every rank: forward | fused loss (the ranks trade the four sums inside it) | backward
+            # with the gradient exchange kernel beside it | widening + grid-block gradients | producer backward
+            def whole_step():
+                feat = producer_forward()
+                forward_part()
+                backward_part()
+                grid_part()
+                producer_backward(feat)
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    for p in producer_params:
+                        p.grad = None
+                    l0 = lib.neraf_launch_count()
+                    whole_step()
+                    self.launches_per_step = lib.neraf_launch_count() - l0
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for p in producer_params:
+                p.grad = None
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                whole_step()
+            return
         if self.group is None:
             with torch.cuda.stream(side):
                 for _ in range(warmup):
@@ -853,6 +972,40 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph_bwd2):
                 backward_part2()
 
+    def _setup_kernel_exchange(self, dev, world: int, n_weight_elems: int, bias_sizes) -> dict:
+        """Symmetric-memory buffers of the kernel exchange: one region (bf16 weight gradients in the flat buffer's order,
+        then the fp32 bias gradients) and a NERAF_EXCHANGE_BYTES flag buffer; every rank's mapping of both."""
+        import torch.distributed as dist
+        n_bias = (sum(bias_sizes) + 3) // 4 * 4
+        bias_offset = (n_weight_elems * 2 + 255) // 256 * 256
+        nbytes = bias_offset + n_bias * 4
+        rank = dist.get_rank(self.group)
+        if world == 1:
+            # a one-rank group (tests): nothing to map, the protocol runs against the local buffers
+            region = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            signals = torch.zeros(_lib.EXCHANGE_BYTES, dtype=torch.uint8, device=dev)
+            region_ptrs, signal_ptrs, multicast = [region.data_ptr()], [signals.data_ptr()], 0
+            handles = None
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            region = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            signals = symm_mem.empty(_lib.EXCHANGE_BYTES, dtype=torch.uint8, device=dev)
+            h_region = symm_mem.rendezvous(region, self.group.group_name)
+            h_signals = symm_mem.rendezvous(signals, self.group.group_name)
+            region.zero_()
+            signals.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)             # every rank's flags are zero before anyone raises one
+            region_ptrs = [int(p) for p in h_region.buffer_ptrs]
+            signal_ptrs = [int(p) for p in h_signals.buffer_ptrs]
+            multicast = 0 if os.environ.get("NERAF_NO_MULTICAST") else int(h_region.multicast_ptr or 0)
+            handles = (h_region, h_signals)
+        return {"region": region, "signals": signals, "handles": handles, "rank": rank,
+                "region_ptrs": region_ptrs, "signal_ptrs": signal_ptrs, "multicast": multicast,
+                "weights16": region[:n_weight_elems * 2].view(torch.bfloat16),
+                "bias": region[bias_offset:bias_offset + n_bias * 4].view(torch.float32),
+                "bias_offset": bias_offset, "bias_bytes": n_bias * 4}
+
     def _reduce(self, region: torch.Tensor, dtype: torch.dtype) -> None:
         """Sum ``region`` of the flat gradient buffer over the ranks (NCCL), optionally through a bf16 copy."""
         import torch.distributed as dist
@@ -883,7 +1036,7 @@ class GraphedTrainStep:
         ``dtype=torch.bfloat16`` halves the bytes on NVLink (30.4 MB instead of 60.8 MB): the buffer is rounded to bf16,
         summed, and widened back; the rounding (2^-9 relative per element) is below the bf16 path's own gradient error.
         """
-        if self.group is None:
+        if self.group is None or self.kernel_exchange:      # kernel path: the graph already holds the global gradients
             return
         import torch.distributed as dist
         dtype = self.grad_dtype if dtype is None else dtype
@@ -933,7 +1086,7 @@ class GraphedTrainStep:
                 src = batch[k]
                 if src is not dst:
                     dst.copy_(src, non_blocking=True)
-        if self.group is None:
+        if self.group is None or self.kernel_exchange:
             self.graph.replay()
             for t, v in getattr(self, "_grad_views", ()):          # eager steps in between may have replaced .grad
                 t.grad = v

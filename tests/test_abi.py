@@ -27,7 +27,20 @@ def test_library_exports_every_declared_symbol(built):
     exported = sorted(set(re.findall(r" T (neraf_\w+)", out)))
     assert exported == names
     lib = _lib.lib()
-    assert lib.neraf_version() == 7
+    assert lib.neraf_version() == 8
+
+
+def test_ctypes_mirrors_have_the_layout_of_the_header(built):
+    """Every struct the header declares has a ctypes mirror of the same size (a field added on one side only would
+    silently shift everything behind it)."""
+    from neraf_b200 import _lib
+    lib = _lib.lib()
+    text = open(os.path.join(ROOT, "include", "neraf_b200.h")).read()
+    declared = sorted(set(re.findall(r"^}\s*(neraf_\w+);", text, flags=re.M)))
+    assert declared == sorted(_lib.STRUCTS), "a public struct has no ctypes mirror"
+    for name, cls in _lib.STRUCTS.items():
+        assert lib.neraf_abi_sizeof(name.encode()) == C.sizeof(cls), name
+    assert lib.neraf_abi_sizeof(b"no_such_struct") == 0
 
 
 def test_library_is_sm100a_with_tcgen05_and_tma(built):

@@ -280,10 +280,15 @@ def test_two_graph_data_parallel_step_equals_autograd_step():
         ref_loss = {k: float(v) for k, v in ld.items()}
         # serial exchange (compact dW1 block, deferred grid-block gradients), two-phase backward with the bulk of the
         # exchange on a communication stream, bf16 exchange: all must reproduce the autograd step
-        for kw, tol in ((dict(), 1e-5), (dict(overlap_allreduce=True), 1e-5),
-                        (dict(grad_dtype=torch.bfloat16), 4e-3), (dict(fused_allreduce=True), 1e-5)):
+        # ... and so must the ONE-graph step whose exchanges are the library's own kernels (exchange="kernel": the four
+        # loss sums traded inside the fused loss kernel, the gradients by neraf_dp_exchange_grads beside the backward;
+        # on one rank the protocol runs against the local buffers -- flags, parities, completion counters and all)
+        for kw, tol in ((dict(exchange="nccl"), 1e-5), (dict(exchange="nccl", overlap_allreduce=True), 1e-5),
+                        (dict(exchange="nccl", grad_dtype=torch.bfloat16), 4e-3), (dict(fused_allreduce=True), 1e-5),
+                        (dict(exchange="kernel"), 4e-3), (dict(), 4e-3)):
             step = GraphedTrainStep(model, batch, **kw)
-            for _ in range(2):
+            assert step.kernel_exchange == (kw.get("exchange", "auto") != "nccl" and not kw.get("fused_allreduce"))
+            for _ in range(3):
                 got = step(batch)
                 step.allreduce_grads()
             torch.cuda.synchronize()
