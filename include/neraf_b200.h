@@ -273,10 +273,12 @@ NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precisio
 
 /* dweight0[n, k] = dbias0[n] * grid_feature[k] (k < n_grid; row stride n_grid + n_enc; may be NULL),
  * dweight0[n, n_grid + e] = dw0_compact[n, e] (when dw0_compact != NULL) and
- * dgrid[k] = sum_n weight0[n, k] * dbias0[n] (may be NULL): the deferred part of neraf_field_backward_dp. */
+ * dgrid[k] = sum_n weight0[n, k] * dbias0[n] (may be NULL; overwritten; bit-reproducible: the row blocks' partial sums
+ * meet in fp64): the deferred part of neraf_field_backward_dp.
+ * scratch (with dgrid): dev, >= 8 * n_grid + 8 bytes, 8-byte aligned, zero before the first use; the call leaves it zero. */
 NERAF_API int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
                            const float* dbias0, const float* dw0_compact, float* dweight0, float* dgrid,
-                           neraf_stream_t stream);
+                           void* scratch, neraf_stream_t stream);
 
 /* Encodings only (NeRFEncoding x3 + SHEncoding + normalisation/zeroing, NeRAF_model.py:533-551):
  * enc_out dev fp32 (B, 163) row stride ld. */

@@ -125,10 +125,16 @@ int pack_list(PackList& L, cudaStream_t stream) {
 constexpr int GG_ROWS = 8;
 constexpr int GG_TPB = 256;
 
+// dg is a sum over all N rows of every column: the row blocks add their partial sums into an fp64 scratch vector
+// (atomics: their order varies from run to run, but at fp64 the variation is ~1e-16 and vanishes in the rounding to
+// fp32 -- with fp32 atomics the last bits of dg changed between runs, and the bf16 producer behind it (whose backward
+// rounds dg to bf16) turned that into 3e-3 jumps of its parameter gradients and, under data parallelism, into replicas
+// that drift apart).  The last block to finish (ticket) rounds the sums into dg and leaves scratch and ticket zero.
 template <int KCH>      // column chunks of 256 per thread: K <= 256 * KCH
 __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restrict__ s, const float* __restrict__ g,
                                                             const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
                                                             float* __restrict__ dW, float* __restrict__ dg,
+                                                            double* __restrict__ dg64, unsigned int* __restrict__ ticket,
                                                             const float* __restrict__ compact, int64_t E, int64_t ld_c) {
   asm volatile("griddepcontrol.wait;" ::: "memory");        // programmatic dependent launch: the backward GEMMs are complete
   const int t = threadIdx.x;
@@ -175,16 +181,32 @@ __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < KCH; ++j) {
       const int64_t k = t + 256 * j;
-      if (k < K) atomicAdd(dg + k, acc[j]);
+      if (k < K) atomicAdd(dg64 + k, (double)acc[j]);
+    }
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      for (int64_t k = t; k < K; k += GG_TPB) {
+        dg[k] = (float)__ldcg(dg64 + k);
+        dg64[k] = 0.0;
+      }
+      if (t == 0) *ticket = 0u;
     }
   }
 }
 
+// scratch: G doubles + one u32 ticket (zero before the first use, left zero)
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
-               bool dg_is_zero, cudaStream_t stream, const float* compact, int64_t E, int64_t ld_c) {
+               void* scratch, cudaStream_t stream, const float* compact, int64_t E, int64_t ld_c) {
   if (N <= 0 || K <= 0 || (!dW && !dg)) return NERAF_OK;
   NERAF_REQUIRE(K <= 256 * 8, "grid_grads: at most 2048 grid-feature columns (got %lld)", (long long)K);
-  if (dg && !dg_is_zero) NERAF_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)K * 4, stream));
+  NERAF_REQUIRE(!dg || (scratch && ((uintptr_t)scratch & 7) == 0), "grid_grads: dg needs an 8-byte aligned scratch buffer");
+  double* dg64 = reinterpret_cast<double*>(scratch);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(dg64 + K);
   const unsigned grid = (unsigned)ceil_div(N, GG_ROWS);
   const float* cp = dW ? compact : nullptr;
   // no memset in front of it: the kernel follows the backward's job-list launch directly and may be set up under its tail
@@ -193,9 +215,9 @@ int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int6
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = ((!dg || dg_is_zero) && pdl_enabled()) ? 1 : 0;
-  if (K <= 256 * 4) NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<4>, s, g, W, ldw, N, K, dW, dg, cp, E, ld_c));
-  else NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<8>, s, g, W, ldw, N, K, dW, dg, cp, E, ld_c));
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (K <= 256 * 4) NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<4>, s, g, W, ldw, N, K, dW, dg, dg64, ticket, cp, E, ld_c));
+  else NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<8>, s, g, W, ldw, N, K, dW, dg, dg64, ticket, cp, E, ld_c));
   NERAF_CHECK_LAUNCH("grid_grads_kernel");
   return NERAF_OK;
 }

@@ -49,6 +49,8 @@ struct Layout {
   size_t dzh;
   int64_t ld_h;
   size_t counters, counters_bytes;   // dependency counters of the job-list kernel
+  size_t gscratch, gscratch_bytes;   // fp64 accumulator of dg + ticket (grid_grads), directly behind the counters: both are
+                                     // cleared by field_prep_kernel in every forward
   size_t dwh;                        // (C*F, W) fp32 joint head weight gradient (only used when C > 1)
   size_t ws_bytes;
 };
@@ -105,6 +107,8 @@ int make_layout(const neraf_field_dims* d, int precision, int64_t batch, Layout*
   l.dzh = take(cur, B * l.ld_h * es);
   l.counters_bytes = (size_t)NERAF_MEGA_MAX_JOBS * (size_t)(ceil_div(batch > 0 ? batch : 1, 256) + 32) * 4;
   l.counters = take(cur, l.counters_bytes);
+  l.gscratch_bytes = (size_t)round_up((int64_t)l.G * 8 + 8, 256);
+  l.gscratch = take(cur, l.gscratch_bytes);
   l.dwh = (bf && l.C > 1) ? take(cur, (size_t)l.CF * l.W * 4) : 0;
   l.ws_bytes = cur;
   return NERAF_OK;
@@ -299,7 +303,8 @@ static int field_forward_impl(const neraf_field_dims* dims, int precision, const
       NERAF_CHECK_CUDA(cudaMemcpy2DAsync(enc, (size_t)l.E * 4, q->enc, (size_t)q->enc_ld * 4, (size_t)l.E * 4, (size_t)B,
                                          cudaMemcpyDeviceToDevice, stream));
     NERAF_TRY(field_prep(q->enc ? nullptr : q, enc, l.E, nullptr, 0, l.E, weights[0], ldw0, biases[0], grid_feature, l.n[0],
-                         l.G, c1w, l.E, nullptr, 0, stream));
+                         l.G, c1w, l.E, nullptr, 0, stream, nullptr, reinterpret_cast<unsigned int*>(at(ws, l.counters)),
+                         (int64_t)((l.gscratch + l.gscratch_bytes - l.counters) / 4)));
     const float* x = enc;
     int64_t ldx = l.E;
     for (int i = 0; i < l.L; ++i) {
@@ -335,7 +340,8 @@ static int field_forward_impl(const neraf_field_dims* dims, int precision, const
   if (q->enc) NERAF_TRY(convert_bf16(q->enc, B, l.E, q->enc_ld, enc, l.ld_enc, nullptr, 0, stream));
   NERAF_TRY(field_prep(q->enc ? nullptr : q, nullptr, 0, enc, l.ld_enc, (int)l.ld_enc, weights[0], ldw0, biases[0],
                        grid_feature, l.n[0], l.G, c1w, l.E, do_pack ? at(pack, l.w[0]) : nullptr, l.ldw[0], stream,
-                       loss_sums, reinterpret_cast<unsigned int*>(at(ws, l.counters)), (int64_t)(l.counters_bytes / 4)));
+                       loss_sums, reinterpret_cast<unsigned int*>(at(ws, l.counters)),
+                       (int64_t)((l.gscratch + l.gscratch_bytes - l.counters) / 4)));
 
   // One persistent launch for the whole MLP (two when the operands are being re-packed on the helper stream:
   // layer 1 starts as soon as its own copy exists, the remaining layers once the helper stream has finished).
@@ -470,7 +476,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
         NERAF_TRY(gemm_f32(l.n[0], l.E, B, dz, 1, l.n[0], enc, 1, l.E, nullptr, NERAF_ACT_NONE, nullptr, 0,
                            dweights[0] + l.G, ldw0, 0, stream));
         if (l.G > 0)
-          NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, false, stream));
+          NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, at(ws, l.gscratch), stream));
         if (denc)
           NERAF_TRY(gemm_f32(B, l.E, l.n[0], dz, l.n[0], 1, weights[0] + l.G, 1, ldw0, nullptr, NERAF_ACT_NONE, nullptr, 0,
                              denc, denc_ld, 0, stream));
@@ -481,9 +487,8 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
 
   // ---- bf16 tensor-core path: the dgrad chain and all weight-gradient GEMMs in ONE launch.
   // Bias gradients are column sums of the fp32 dZ accumulated by the epilogues (atomics on zeroed buffers): the
-  // buffers (and dgrid, accumulated by grid_grads) are zeroed with as few memsets as their addresses allow -- one
-  // when the caller laid them out back to back (neraf_b200/field.py does).
-  bool dgrid_zeroed = false;
+  // buffers are zeroed with as few memsets as their addresses allow -- one when the caller laid them out back to back
+  // (neraf_b200/field.py does); dgrid is overwritten by grid_grads.
   float* zero_start = nullptr;                       // one 16-byte-tileable span: cleared by the fused loss kernel instead
   int64_t zero_n = 0;
   if (phase != 2) {
@@ -497,7 +502,6 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       float* end = start + (i < l.L ? l.n[i] : l.F);
       int j = i + 1;
       while (j < nb && dbiases[j] == end) { end += j < l.L ? l.n[j] : l.F; ++j; }
-      if (j == nb && dgrid && l.G > 0 && dgrid == end && !defer_grid_grads) { end += l.G; dgrid_zeroed = true; }
       spans[ns++] = Span{start, end};
       i = j;
     }
@@ -639,7 +643,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       NERAF_CHECK_CUDA(cudaMemcpyAsync(dweights[l.L + c], at(ws, l.dwh) + (size_t)c * l.F * l.W * 4, (size_t)l.F * l.W * 4,
                                        cudaMemcpyDeviceToDevice, stream));
   if (l.G > 0 && !defer_grid_grads && phase != 1)
-    NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, dgrid_zeroed, stream));
+    NERAF_TRY(grid_grads(dbiases[0], grid_feature, weights[0], ldw0, l.n[0], l.G, dweights[0], dgrid, at(ws, l.gscratch), stream));
   return NERAF_OK;
 }
 
@@ -663,10 +667,11 @@ extern "C" int neraf_field_backward_dp(const neraf_field_dims* dims, int precisi
 
 extern "C" int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
                                       const float* dbias0, const float* dw0_compact, float* dweight0, float* dgrid,
-                                      neraf_stream_t stream) {
+                                      void* scratch, neraf_stream_t stream) {
   NERAF_REQUIRE(dims && dims->n_trunk >= 1, "field_grid_grads: dims is null");
   if (dims->n_grid <= 0) return NERAF_OK;
   NERAF_REQUIRE(grid_feature && weight0 && dbias0 && (dweight0 || dgrid), "field_grid_grads: null pointer");
+  NERAF_REQUIRE(!dgrid || scratch, "field_grid_grads: dgrid needs scratch");
   return grid_grads(dbias0, grid_feature, weight0, (int64_t)dims->n_grid + dims->n_enc, dims->trunk[0], dims->n_grid, dweight0,
-                    dgrid, false, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 8));
+                    dgrid, scratch, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 8));
 }

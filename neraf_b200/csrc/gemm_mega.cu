@@ -92,6 +92,8 @@ struct MegaParams {
                                    // the last CTA to finish clears them all, so the NEXT launch finds them zero
   unsigned int* counters;
   unsigned long long* trace;       // null unless tracing
+  int pdl_late;                    // programmatic dependent launch: release the next kernel when this CTA's tiles are done
+                                   // (1) or as soon as the grid is resident (0)
   DeviceJob jobs[NERAF_MEGA_MAX_JOBS];
 };
 
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel of the stream; nothing
   // it produced has been touched yet.  This grid's CTAs are all resident by now, so the next kernel may start moving in.
   pdl_wait();
-  pdl_launch_dependents();
+  if (!P.pdl_late) pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -719,6 +721,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
     if (used_multicast) __threadfence_system();
   }
 
+  if (P.pdl_late) pdl_launch_dependents();            // this CTA has no tile left: the next kernel's CTAs may be set up
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
@@ -750,6 +753,10 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
   P.num_jobs = n_jobs;
+  {
+    const char* e = getenv("NERAF_PDL_TRIGGER");       // "early" / "late" (tuning; default late)
+    P.pdl_late = (e && e[0] == 'e') ? 0 : 1;
+  }
   int tile = 0, cnt = 0;
   int cnt_off[NERAF_MEGA_MAX_JOBS], nrb[NERAF_MEGA_MAX_JOBS], num_n[NERAF_MEGA_MAX_JOBS];
   for (int i = 0; i < n_jobs; ++i) {

@@ -58,10 +58,11 @@ struct PackList {
   const float* copy_src[8]; float* copy_dst; int64_t copy_width, n_copy;   // copy_dst[j] = copy_src[j / width][j % width]
 };
 int pack_list(PackList& L, cudaStream_t stream);
-// dW[n*ldw + k] = s[n] * g[k] (dW may be null) and dg[k] = sum_n W[n*ldw + k] * s[n] (dg may be null) in one launch
+// dW[n*ldw + k] = s[n] * g[k] (dW may be null) and dg[k] = sum_n W[n*ldw + k] * s[n] (dg may be null; OVERWRITTEN,
+// bit-reproducible) in one launch.  scratch (needed with dg): K doubles + 8 bytes, zero before the first use, left zero.
 // compact (optional): (N, E) block with row stride ld_c copied into dW[:, K:K+E]
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
-               bool dg_is_zero, cudaStream_t stream, const float* compact = nullptr, int64_t E = 0, int64_t ld_c = 0);
+               void* scratch, cudaStream_t stream, const float* compact = nullptr, int64_t E = 0, int64_t ld_c = 0);
 // out[n] = sum_m X[m*ld + n]   fp32 row-major (M,N)
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
 struct HeadColsum {

@@ -11,6 +11,8 @@
 //      reduction forms the losses itself (neraf_spectral_loss_forward),
 //   3. one elementwise kernel for d loss / d pred.
 // HBM-bound: 8 B/element forward, 12 B/element backward.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "loss_math.cuh"
@@ -370,9 +372,12 @@ int loss_head_fused(const float* y, int64_t M, int64_t N, float* dz_f32, int64_t
     int n = 0;
     NERAF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, loss_head_kernel, 256, 0));
     NERAF_REQUIRE(n > 0, "loss_head_fused: the kernel does not fit on this device");
-    per_sm[dev] = n > 4 ? 4 : n;
+    per_sm[dev] = n;
   }
-  const int64_t cap = (int64_t)sm_count() * (dev >= 0 && dev < 64 ? per_sm[dev] : 1);
+  int blocks_per_sm = 4;
+  if (const char* e = getenv("NERAF_LOSS_BLOCKS")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : 4;      // tuning
+  if (dev >= 0 && dev < 64 && blocks_per_sm > per_sm[dev]) blocks_per_sm = per_sm[dev];
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
   const int64_t want = ceil_div(M, 32) * ceil_div(N, 32);
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   cudaLaunchConfig_t cfg = {};

@@ -735,7 +735,11 @@ class GraphedTrainStep:
         # not when the heads' epilogue forms the sums.
         self._sync = torch.zeros(4, dtype=torch.int32, device=dev)
         self._fused_loss = ((self.group is None or self.kernel_exchange) and not self.fuse_loss_sums
-                            and (self.kernel_exchange or os.environ.get("NERAF_FUSED_LOSS", "1") != "0"))   # =0: A/B timing
+                            and (self.kernel_exchange or os.environ.get("NERAF_FUSED_LOSS", "0") == "1"))
+        # single process: the two launches (loss_sums_kernel + head_backward_kernel) measured 8 us per step FASTER than the
+        # one-launch form at B = 2048 (profiles/r02e_ab_tuning.txt: 341 vs 350 us; each phase of the fused kernel runs on
+        # half the resident threads and the barrier's serial section sits between them), so the one-launch form is used
+        # where it replaces a host-issued collective (data parallel) and is opt-in otherwise (NERAF_FUSED_LOSS=1)
         self._rank_x = None
         if self._fused_loss:
             lg.fuse_sums, lg.sync = 1, self._sync.data_ptr()
@@ -874,8 +878,10 @@ class GraphedTrainStep:
             if defer:
                 _lib.check(lib.neraf_field_grid_grads(C.byref(dims), grid_p.data_ptr(), weights[0].data_ptr(),
                                                       dbs[0].data_ptr(), compact.data_ptr(), dws[0].data_ptr(),
-                                                      dgrid.data_ptr(), _lib.stream_ptr(dev)))
+                                                      dgrid.data_ptr(), self._grid_scratch.data_ptr(),
+                                                      _lib.stream_ptr(dev)))
         self._grid_part = grid_part
+        self._grid_scratch = torch.zeros(2 * max(n_grid, 1) + 4, dtype=torch.float32, device=dev)   # fp64 sums of dg + ticket
 
         if model.criterion_name == "MSE":
             self.losses = {"audio_mse": losses[1]}

@@ -399,10 +399,18 @@ def test_train_step_through_producer_and_field_eager_and_graphed(prec):
         p.grad = None
     model.resnet3d(model.grid.unsqueeze(0)).backward(dg.view(1, -1, 1, 1, 1))
     torch.cuda.synchronize()
+    # Two RUNS of the field step give dg up to the last bits of fp32 (the bias gradients behind it are sums of fp32
+    # atomics, whose order varies).  The fp32 producer carries that through (1e-5); the bf16 producer ROUNDS dg to bf16
+    # at its entry, so now and then an element lands on the other side of a rounding boundary and its (linear,
+    # evaluation-mode) backward moves by up to a few 1e-3 -- any comparison of its gradients ACROSS runs is gated at
+    # bf16 resolution, and the bit-tight statement is made for one and the same dg below.
+    cross_run = 1e-5 if prec == "fp32" else 2e-2
     for p in model.resnet3d.parameters():
-        assert rel_fro(p.grad, grads[id(p)]) < 1e-5
+        assert rel_fro(p.grad, grads[id(p)]) < cross_run
     # captured: the field's direct library calls with the producer's autograd around them (default), and the plugin's
     # autograd calls captured as they are
+    producer = list(model.resnet3d.parameters())
+    producer_ids = {id(p) for p in producer}
     for functional in (True, False):
         step = GraphedTrainStep(model, batch, functional=functional)
         for _ in range(2):                                  # a replay overwrites, it does not accumulate
@@ -411,4 +419,16 @@ def test_train_step_through_producer_and_field_eager_and_graphed(prec):
         for k, v in losses.items():
             assert abs(float(got[k]) - v) <= 1e-5 * abs(v), (k, functional)
         for p in params:
-            assert rel_fro(p.grad, grads[id(p)]) < 1e-4, functional
+            assert rel_fro(p.grad, grads[id(p)]) < (max(cross_run, 1e-4) if id(p) in producer_ids else 1e-4), functional
+        if functional:
+            # ... and for the dg this very replay produced, the producer's gradients inside the graph are exactly what
+            # its backward gives eagerly (same kernels, same input: only fp64-atomic noise of the batch-norm sums)
+            assert rel_fro(step._dgrid, dg) < 1e-5
+            in_graph = {id(p): p.grad.clone() for p in producer}
+            dg_step = step._dgrid.clone()
+            for p in producer:
+                p.grad = None
+            model.resnet3d(model.grid.unsqueeze(0)).backward(dg_step.view(1, -1, 1, 1, 1))
+            torch.cuda.synchronize()
+            for p in producer:
+                assert rel_fro(p.grad, in_graph[id(p)]) < 1e-5, "in-graph producer backward"

@@ -20,7 +20,7 @@ def build(name, **env):
             if v is None: os.environ.pop(k, None)
             else: os.environ[k] = v
 # NERAF_PDL is read once per process by the library: run the script twice (NERAF_PDL=0 / unset) for that A/B
-variants = {"one loss launch (sums + barrier + gradient)": build("fused"),
+variants = {"one loss launch (sums + barrier + gradient)": build("fused", NERAF_FUSED_LOSS="1"),
             "loss_sums + head_backward launches": build("split", NERAF_FUSED_LOSS="0"),
             "sums in the heads' epilogue": GraphedTrainStep(model, batch, fuse_loss_sums=True)}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -47,20 +47,28 @@ sum(ld.values()).backward()
 ref_g, ref_l = flat(single), {k: float(v) for k, v in ld.items()}
 
 ok = True
-for name, dtype, tol in (("fp32 exchange", torch.float32, 1e-4), ("bf16 exchange", torch.bfloat16, 4e-3)):
+for name, kw, tol in (("NCCL, fp32 exchange (two graphs)", dict(exchange="nccl", grad_dtype=torch.float32), 1e-4),
+                      ("NCCL, bf16 exchange (two graphs)", dict(exchange="nccl", grad_dtype=torch.bfloat16), 4e-3),
+                      ("kernel exchange (ONE graph: sums traded in the loss kernel, NVLS all-reduce beside the backward)",
+                       dict(exchange="kernel"), 4e-3)):
     model = build(dist.group.WORLD)
-    step = GraphedTrainStep(model, batch, grad_dtype=dtype)
-    for _ in range(2):
+    step = GraphedTrainStep(model, batch, **kw)
+    for _ in range(4):
         got = step(batch)
         step.allreduce_grads()
     torch.cuda.synchronize()
     g = flat(model)
+    # every rank must hold the SAME gradients bit for bit with the kernel exchange (one reduced buffer, deterministic dg)
+    gmax, gmin = g.clone(), g.clone()
+    dist.all_reduce(gmax, op=dist.ReduceOp.MAX); dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+    identical = bool((gmax == gmin).all())
     err = float((g - ref_g).norm() / ref_g.norm())
     lerr = max(abs(float(got[k]) - ref_l[k]) / abs(ref_l[k]) for k in ref_l)
     ok = ok and err < tol and lerr < 1e-5
     if rank == 0:
         print(f"{world} ranks x {B} columns, {name}: summed gradients vs single process on {world * B} columns: "
-              f"rel {err:.2e} (tol {tol:g}); losses rel {lerr:.1e}", flush=True)
+              f"rel {err:.2e} (tol {tol:g}); losses rel {lerr:.1e}; ranks bit-identical: {identical}"
+              f"{' [multicast]' if getattr(step, '_xchg', None) and step._xchg['multicast'] else ''}", flush=True)
     dist.barrier()
 if rank == 0:
     print("DP == single:", "OK" if ok else "MISMATCH", flush=True)

@@ -18,10 +18,12 @@ shape, B = syn.RAF, 2048
 batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, B, seed=10 + rank).items()}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ref = None
-variants = [("serial fp32", dict(overlap_allreduce=False, grad_dtype=torch.float32)),
-            ("serial bf16", dict(overlap_allreduce=False, grad_dtype=torch.bfloat16)),
-            ("overlap fp32", dict(overlap_allreduce=True, grad_dtype=torch.float32)),
-            ("overlap bf16", dict(overlap_allreduce=True, grad_dtype=torch.bfloat16))]
+variants = [("nccl fp32", dict(exchange="nccl", grad_dtype=torch.float32)),
+            ("nccl bf16", dict(exchange="nccl", grad_dtype=torch.bfloat16)),
+            ("kernel", dict(exchange="kernel"))]
+if os.environ.get("WITH_OVERLAP"):
+    variants += [("overlap fp32", dict(exchange="nccl", overlap_allreduce=True, grad_dtype=torch.float32)),
+                 ("overlap bf16", dict(exchange="nccl", overlap_allreduce=True, grad_dtype=torch.bfloat16))]
 if os.environ.get("WITH_NVLS"):
     variants.append(("nvls fused", dict(fused_allreduce=True)))
 for name, kw in variants:
@@ -49,7 +51,8 @@ for name, kw in variants:
     t = torch.tensor([tot], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"{name:14s} {float(t):8.1f} us/step   overlap={getattr(step, 'overlap', False)} nvls={step.nvls}   "
-              f"grads vs serial fp32: {err:.2e}", flush=True)
+        print(f"{name:14s} {float(t):8.1f} us/step   kernel_exchange={step.kernel_exchange} "
+              f"multicast={bool(step._xchg and step._xchg['multicast'])} overlap={getattr(step, 'overlap', False)} "
+              f"nvls={step.nvls}   grads vs nccl fp32: {err:.2e}", flush=True)
     dist.barrier()
 dist.destroy_process_group()
