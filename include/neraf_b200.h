@@ -213,10 +213,11 @@ typedef struct {
  * Data-parallel gradient exchange (SURVEY.md 8e collective 1; the reference has no multi-GPU path at all,
  * NeRAF_pipeline.py:153-157) as ONE kernel of this library over peer-mapped ("symmetric") memory: a two-shot
  * all-reduce -- multimem.ld_reduce of this rank's slice (the NVSwitch adds the ranks' copies), multimem.st of the sum
- * into every rank's copy -- chunk by chunk in the order the backward finishes the gradients.  Enqueued on a stream
- * BESIDE neraf_field_backward_dp (fork before it, join after both): every chunk waits for the completion counter
- * (neraf_dp_options.notify) the backward advances, so gradients travel while the remaining GEMMs run, and the whole
- * training step -- no host-issued collective anywhere -- is one CUDA graph.
+ * into every rank's copy -- chunk by chunk in the order the backward finishes the gradients.  Passed to
+ * neraf_field_backward_dp (neraf_dp_options.exchange) it runs BESIDE the backward's GEMM launch: every chunk waits for
+ * the completion counter (neraf_dp_options.notify) the backward advances, so gradients travel while the remaining GEMMs
+ * run, and the whole training step -- no host-issued collective anywhere -- is one CUDA graph.  Called on its own it is
+ * an ordinary in-stream all-reduce of the chunks.
  *   region   : every rank's gradient buffer in symmetric memory (same layout on every rank): peers[r] is rank r's as
  *              mapped into this process (peers[rank] the local one), multicast its NVLS alias or NULL (then plain peer
  *              loads / stores are used).  The sums replace the addends in place, on every rank.
@@ -257,10 +258,10 @@ typedef struct {
                                     trunk layer i stored, [n_trunk] head weight gradients stored, [n_trunk + 1] every bias
                                     gradient final.  Each launch advances counter k by notify_increment[k]. */
   uint32_t* notify_increment;    /* HOST u32[n_trunk + 2], written by the call (with notify) */
-  const neraf_grad_exchange* exchange;   /* optional (with notify): neraf_dp_exchange_grads is enqueued BESIDE the backward's
-                                    GEMM launch on a helper stream of the library (forked after the head-gradient kernel,
-                                    joined before the call returns its stream); chunks whose notify points into `notify`
-                                    get their notify_increment from this call */
+  const neraf_grad_exchange* exchange;   /* optional (with notify): the exchange kernel is launched right behind the backward's
+                                    GEMM kernel as a programmatic dependent that never waits for it -- it moves in once
+                                    that persistent grid is resident and runs beside it; chunks whose notify points into
+                                    `notify` get their notify_increment from this call */
   int32_t zero_tail_slack;       /* the caller owns up to 3 floats behind the last bias gradient (/ dgrid): the fused loss
                                     kernel may clear the back-to-back gradient vectors in whole 16-byte words */
 } neraf_dp_options;

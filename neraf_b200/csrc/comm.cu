@@ -4,9 +4,10 @@
 // issued by the host after the backward it is fully exposed (SCALE_r01.json: 0.63 efficiency on 8 GPUs).  The weight
 // gradients finish in backward order, so most of them can travel while the remaining GEMMs run -- if the exchange
 // (a) needs no host call between the kernels (the step stays one CUDA graph) and (b) does not take SMs away from the
-// persistent GEMM kernel.  This kernel does both: it is launched on a parallel branch of the graph with one small CTA
-// per SM (256 threads, <= 40 registers, no shared memory: it fits beside a job-list CTA), and is driven by the
-// completion counters the job-list kernel advances as it stores gradient tiles (neraf_gemm_job.notify).
+// persistent GEMM kernel.  This kernel does both: small CTAs (256 threads, <= 40 registers, no shared memory: one fits
+// beside a job-list CTA on every SM), launched behind the job-list kernel as a programmatic dependent that never waits
+// for it (it moves in once that grid is resident: field.cu), driven by the completion counters the job-list kernel
+// advances as it stores gradient tiles (neraf_gemm_job.notify).
 //
 // Algorithm (two-shot all-reduce over peer-mapped "symmetric" memory; NVLink 5 / NVSwitch):
 //   per chunk c (one weight-gradient matrix, bf16; last: the bias gradients, fp32), in the order the backward finishes
@@ -222,8 +223,8 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
 
 using namespace neraf;
 
-extern "C" int neraf_dp_exchange_grads(const neraf_grad_exchange* x, neraf_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+namespace neraf {
+int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool beside_previous) {
   NERAF_REQUIRE(x, "dp_exchange_grads: null argument");
   NERAF_REQUIRE(x->world >= 1 && x->world <= NERAF_MAX_RANKS && x->rank >= 0 && x->rank < x->world,
                 "dp_exchange_grads: bad world / rank");
@@ -251,7 +252,18 @@ extern "C" int neraf_dp_exchange_grads(const neraf_grad_exchange* x, neraf_strea
   int grid = x->max_ctas > 0 ? x->max_ctas : sm_count();
   if (grid > sm_count()) grid = sm_count();
   if (grid < 2) grid = 2;
-  grad_exchange_kernel<<<(unsigned)grid, kCommThreads, 0, stream>>>(A);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCommThreads); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = beside_previous ? 1 : 0;
+  NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grad_exchange_kernel, A));
   NERAF_CHECK_LAUNCH("grad_exchange_kernel");
   return NERAF_OK;
+}
+}  // namespace neraf
+
+extern "C" int neraf_dp_exchange_grads(const neraf_grad_exchange* x, neraf_stream_t stream) {
+  return neraf::dp_exchange_grads(x, (cudaStream_t)stream, false);
 }

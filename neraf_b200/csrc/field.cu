@@ -609,17 +609,17 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
     for (int j = 0; j < nj; ++j)
       if (notify_slot[j] >= 0) jobs[j].notify = notify + notify_slot[j];
   }
-  // Data parallel: the gradient exchange kernel runs BESIDE the job-list launch (helper stream forked here, after the
-  // head-gradient kernel, joined after both) and follows the completion counters.
+  // Data parallel: the gradient exchange kernel runs BESIDE the job-list launch and follows its completion counters.  It
+  // is launched right behind it in the same stream as a programmatic dependent that never waits: it moves in when every
+  // CTA pair of the persistent GEMM grid is resident (they release their dependents at start), so its CTAs -- wherever
+  // the block scheduler puts them -- can never keep a pair from becoming resident.  (Launched on a second stream, two of
+  // its CTAs on one SM could: the pairs spin on each other's progress, the exchange spins on theirs -- a deadlock that
+  // the watchdog turned into a launch failure, intermittently, on graph replays.)
   const neraf_grad_exchange* xg = opt ? opt->exchange : nullptr;
-  SideStream* side = xg ? side_stream() : nullptr;
   NERAF_REQUIRE(!xg || notify, "field_backward_dp: exchange needs notify");
-  if (side) {
-    NERAF_CHECK_CUDA(cudaEventRecord(side->fork, stream));
-    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  }
   // left clean by the forward's launch; set up under the tail of the head-gradient kernel that precedes it
-  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas, true, phase != 2, increments));
+  NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas, true, phase != 2, increments,
+                     xg != nullptr));
   unsigned int by_slot[NERAF_MAX_TRUNK + 2] = {0};
   if (notify)
     for (int j = 0; j < nj; ++j)
@@ -632,11 +632,7 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       const uint32_t* nf = x.chunks[c].notify;
       if (nf >= notify && nf < notify + l.L + 2) x.chunks[c].notify_increment = by_slot[nf - notify];
     }
-    NERAF_TRY(neraf_dp_exchange_grads(&x, side ? side->stream : stream));
-    if (side) {
-      NERAF_CHECK_CUDA(cudaEventRecord(side->done, side->stream));
-      NERAF_CHECK_CUDA(cudaStreamWaitEvent(stream, side->done, 0));
-    }
+    NERAF_TRY(dp_exchange_grads(&x, stream, true));
   }
   if (!heads_contiguous && phase != 2 && !dw16)
     for (int c = 0; c < l.C; ++c)

@@ -746,7 +746,7 @@ int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t col
                       CUtensorMap* out);
 
 int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas,
-             bool counters_clean, bool pdl, unsigned int* notify_increment) {
+             bool counters_clean, bool pdl, unsigned int* notify_increment, bool release_dependents_early) {
   using namespace umma;
   NERAF_REQUIRE(jobs && n_jobs > 0 && n_jobs <= NERAF_MEGA_MAX_JOBS, "mega_run: 1..%d jobs", NERAF_MEGA_MAX_JOBS);
   static MegaParams P;          // large: build in static storage (single-threaded driver, see header conventions)
@@ -756,6 +756,7 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   {
     const char* e = getenv("NERAF_PDL_TRIGGER");       // "early" / "late" (tuning; default late)
     P.pdl_late = (e && e[0] == 'e') ? 0 : 1;
+    if (release_dependents_early) P.pdl_late = 0;      // a kernel that runs BESIDE this one is waiting to move in
   }
   int tile = 0, cnt = 0;
   int cnt_off[NERAF_MEGA_MAX_JOBS], nrb[NERAF_MEGA_MAX_JOBS], num_n[NERAF_MEGA_MAX_JOBS];

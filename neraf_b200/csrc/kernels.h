@@ -39,8 +39,16 @@ typedef neraf_gemm_job MegaJob;      // public contract: include/neraf_b200.h
 // pdl: launch with programmatic stream serialization (the previous work of the stream must be a kernel of this library
 // that executes griddepcontrol.launch_dependents, or any kernel: the prologue then simply starts when that one ends)
 // notify_increment (optional, host, n_jobs entries): by how much one launch advances each job's `notify` counter
+// release_dependents_early: griddepcontrol.launch_dependents as soon as every CTA of the grid is resident -- for a kernel
+// launched behind this one with programmatic stream serialization that never waits for it (griddepcontrol.wait) but
+// runs BESIDE it: it moves in only once this persistent grid holds all its SM slots, so it can never keep a CTA pair
+// of this grid from becoming resident (the pairs spin on each other's progress)
 int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas = 0,
-             bool counters_clean = false, bool pdl = false, unsigned int* notify_increment = nullptr);
+             bool counters_clean = false, bool pdl = false, unsigned int* notify_increment = nullptr,
+             bool release_dependents_early = false);
+// comm.cu: neraf_dp_exchange_grads; beside_previous: launched as a programmatic dependent of the previous kernel of the
+// stream (which must release its dependents early, see above) without ever waiting for it
+int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool beside_previous);
 
 // elementwise.cu
 int convert_bf16(const float* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out, void* out_t,
