@@ -184,7 +184,7 @@ NERAF_API int neraf_field_forward_loss_sums(const neraf_field_dims* dims, int pr
  * per step through it (stores to every peer + a flag, spin on the local flags) instead of a host-issued collective,
  * so a whole training step stays one CUDA graph. */
 #define NERAF_MAX_RANKS 16
-#define NERAF_EXCHANGE_BYTES 4096
+#define NERAF_EXCHANGE_BYTES 8192
 typedef struct {
   int32_t world, rank;
   void* peers[NERAF_MAX_RANKS];
@@ -222,16 +222,17 @@ typedef struct {
  *              mapped into this process (peers[rank] the local one), multicast its NVLS alias or NULL (then plain peer
  *              loads / stores are used).  The sums replace the addends in place, on every rank.
  *   chunks   : byte ranges of the region (16-byte multiples), bf16 (f32 == 0) or fp32 elements, fp32 accumulation;
- *              notify / notify_increment: dev u32 counter that this rank's producer advances by notify_increment per
- *              step when the chunk is stored (NULL: ready when the call starts).  EVERY step that advances the
- *              counters must run this call exactly once (the kernel counts steps in `state`).
+ *              notify / notify_count / notify_increment: dev u32 counters that this rank's producer advances by
+ *              notify_increment each per step as the chunk is stored (NULL: ready when the call starts).  EVERY step
+ *              that advances the counters must run this call exactly once (the kernel counts steps in `state`).
  *   signals  : every rank's NERAF_EXCHANGE_BYTES signal buffer (symmetric memory, zero before first use; may be the
  *              buffer of neraf_rank_exchange); state: dev u32[4] of this rank, zero before first use.
  *   max_ctas : 0 = one CTA per SM (256 threads, fits beside a CTA of the job-list kernel). */
-#define NERAF_MAX_EXCHANGE_CHUNKS 16
+#define NERAF_MAX_EXCHANGE_CHUNKS 32
 typedef struct {
   int64_t offset, bytes;
-  const uint32_t* notify;
+  const uint32_t* notify;      /* notify_count consecutive counters: the chunk is ready when ALL have advanced */
+  uint32_t notify_count;
   uint32_t notify_increment;
   int32_t f32;
 } neraf_exchange_chunk;
@@ -245,6 +246,7 @@ typedef struct {
 } neraf_grad_exchange;
 NERAF_API int neraf_dp_exchange_grads(const neraf_grad_exchange* x, neraf_stream_t stream);
 
+#define NERAF_NOTIFY_COUNTERS 1024
 typedef struct {
   const neraf_multicast* mc;
   float* dw0_compact;
@@ -253,11 +255,17 @@ typedef struct {
   int32_t max_ctas;
   const neraf_loss_grad* loss;   /* NULL: read the upstream gradient from dout */
   void* const* dweights_bf16;    /* NULL: fp32 weight gradients in dweights / dw0_compact */
-  uint32_t* notify;              /* optional dev u32[n_trunk + 2], never cleared by the library: completion counters for a
-                                    kernel running BESIDE the backward (neraf_dp_exchange_grads): [i] weight gradient of
-                                    trunk layer i stored, [n_trunk] head weight gradients stored, [n_trunk + 1] every bias
-                                    gradient final.  Each launch advances counter k by notify_increment[k]. */
-  uint32_t* notify_increment;    /* HOST u32[n_trunk + 2], written by the call (with notify) */
+  uint32_t* notify;              /* optional dev u32[NERAF_NOTIFY_COUNTERS], never cleared by the library: completion
+                                    counters for a kernel running BESIDE the backward (neraf_dp_exchange_grads).  Matrix
+                                    k (k < n_trunk: weight gradient of trunk layer k; k == n_trunk: the head weight
+                                    gradients, all heads as one (C F, W) matrix; k == n_trunk + 1: "every bias gradient
+                                    is final") owns notify_count[k] = ceil(rows_k / 256) consecutive counters from
+                                    notify_offset[k] = sum of the counts before it (rows: trunk[k], C F, batch): counter r
+                                    advances by notify_increment[k] per launch when rows [256 r, 256 r + 256) of the
+                                    gradient matrix are stored (k == n_trunk + 1: all of its counters must advance). */
+  uint32_t* notify_offset;       /* HOST u32[n_trunk + 2] each, written by the call (with notify) */
+  uint32_t* notify_count;
+  uint32_t* notify_increment;
   const neraf_grad_exchange* exchange;   /* optional (with notify): the exchange kernel is launched right behind the backward's
                                     GEMM kernel as a programmatic dependent that never waits for it -- it moves in once
                                     that persistent grid is resident and runs beside it; chunks whose notify points into
@@ -461,8 +469,9 @@ typedef struct {
   int32_t merge_next;   /* 1: interleave this job's tiles with those of the NEXT job (which must not wait for this one) */
   neraf_gemm_epilogue epi;
   float* colsum;
-  uint32_t* notify;     /* optional dev u32, never cleared: advanced (gpu-scope release) as the job's tiles are stored, by a
-                           fixed amount per launch -- lets a CONCURRENT kernel wait for this job's output */
+  uint32_t* notify;     /* optional dev u32[ceil(M / 256)], never cleared: counter r is advanced (gpu-scope release) as the
+                           tiles of rows [256 r, 256 r + 256) are stored, by a fixed amount per launch -- lets a
+                           CONCURRENT kernel wait for (parts of) this job's output */
 } neraf_gemm_job;
 
 NERAF_API int neraf_gemm_bf16_jobs(const neraf_gemm_job* jobs, int n_jobs, void* counters, size_t counters_bytes,

@@ -20,7 +20,7 @@ ACT_NONE, ACT_LEAKY, ACT_TANH10 = 0, 1, 2
 CRIT_SC_SLMSE, CRIT_SC_SLL1, CRIT_MSE = 0, 1, 2
 ORDER_TIME_MIC_SRC_ROT, ORDER_MIC_SRC_TIME_ROT = 0, 1
 MAX_TRUNK = 8
-MAX_RANKS, EXCHANGE_BYTES, MAX_EXCHANGE_CHUNKS = 16, 4096, 16
+MAX_RANKS, EXCHANGE_BYTES, MAX_EXCHANGE_CHUNKS, NOTIFY_COUNTERS = 16, 8192, 32, 1024
 
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 CRITERIA = {"SC+SLMSE": CRIT_SC_SLMSE, "SC+SLL1": CRIT_SC_SLL1, "MSE": CRIT_MSE}
@@ -73,8 +73,8 @@ class LossGrad(C.Structure):        # neraf_loss_grad
 
 
 class ExchangeChunk(C.Structure):   # neraf_exchange_chunk
-    _fields_ = [("offset", C.c_int64), ("bytes", C.c_int64), ("notify", C.c_void_p), ("notify_increment", C.c_uint32),
-                ("f32", C.c_int32)]
+    _fields_ = [("offset", C.c_int64), ("bytes", C.c_int64), ("notify", C.c_void_p), ("notify_count", C.c_uint32),
+                ("notify_increment", C.c_uint32), ("f32", C.c_int32)]
 
 
 class GradExchange(C.Structure):    # neraf_grad_exchange
@@ -87,6 +87,7 @@ class DpOptions(C.Structure):
     _fields_ = [("mc", C.POINTER(Multicast)), ("dw0_compact", C.c_void_p), ("defer_grid_grads", C.c_int32),
                 ("phase", C.c_int32), ("max_ctas", C.c_int32), ("loss", C.POINTER(LossGrad)),
                 ("dweights_bf16", C.POINTER(C.c_void_p)), ("notify", C.c_void_p),
+                ("notify_offset", C.POINTER(C.c_uint32)), ("notify_count", C.POINTER(C.c_uint32)),
                 ("notify_increment", C.POINTER(C.c_uint32)), ("exchange", C.POINTER(GradExchange)),
                 ("zero_tail_slack", C.c_int32)]
 

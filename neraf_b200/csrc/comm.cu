@@ -30,14 +30,14 @@ namespace neraf {
 
 constexpr int kCommThreads = 256;
 constexpr int kReadyOffset = 2048;             // u32 ready[NERAF_MAX_EXCHANGE_CHUNKS][NERAF_MAX_RANKS]
-constexpr int kDoneOffset = 3072;              // u32 done[NERAF_MAX_RANKS]
+constexpr int kDoneOffset = 4096;              // u32 done[NERAF_MAX_RANKS]
 static_assert(kReadyOffset + NERAF_MAX_EXCHANGE_CHUNKS * NERAF_MAX_RANKS * 4 <= kDoneOffset, "signal buffer layout");
 static_assert(kDoneOffset + NERAF_MAX_RANKS * 4 <= NERAF_EXCHANGE_BYTES, "signal buffer layout");
 constexpr long long kCommSpinLimit = 4000000000LL;      // ~2 s: a lost peer traps instead of hanging the GPU
 
 struct CommChunk {
   unsigned long long offset, bytes;            // of the exchange region; multiples of 16
-  const unsigned int* notify; unsigned int increment;
+  const unsigned int* notify; unsigned int count, increment;
   int f32;
 };
 struct CommArgs {
@@ -134,10 +134,11 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
         if (ch.notify != nullptr) {
           const unsigned int target = seq * ch.increment;   // counters only ever advance (mod 2^32 arithmetic)
           const long long t0 = clock64();
-          while (!reached(comm_ld_acquire_gpu(ch.notify), target)) {
-            __nanosleep(200);
-            if (clock64() - t0 > kCommSpinLimit) __trap();
-          }
+          for (unsigned int i = 0; i < ch.count; ++i)
+            while (!reached(comm_ld_acquire_gpu(ch.notify + i), target)) {
+              __nanosleep(200);
+              if (clock64() - t0 > kCommSpinLimit) __trap();
+            }
         }
         __threadfence_system();
         for (int q = 0; q < A.world; ++q)
@@ -245,8 +246,10 @@ int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool be
   for (int c = 0; c < x->n_chunks; ++c) {
     const neraf_exchange_chunk& s = x->chunks[c];
     NERAF_REQUIRE(s.offset % 16 == 0 && s.bytes % 16 == 0, "dp_exchange_grads: chunk %d is not 16-byte tileable", c);
-    NERAF_REQUIRE(!s.notify || s.notify_increment > 0, "dp_exchange_grads: chunk %d: notify without an increment", c);
-    A.ch[c] = CommChunk{(unsigned long long)s.offset, (unsigned long long)s.bytes, s.notify, s.notify_increment, s.f32 ? 1 : 0};
+    NERAF_REQUIRE(!s.notify || (s.notify_increment > 0 && s.notify_count > 0),
+                  "dp_exchange_grads: chunk %d: notify without a counter count / increment", c);
+    A.ch[c] = CommChunk{(unsigned long long)s.offset, (unsigned long long)s.bytes, s.notify, s.notify_count, s.notify_increment,
+                        s.f32 ? 1 : 0};
   }
   // one small CTA per SM (it must fit BESIDE a CTA of the job-list kernel), never more than are resident at once
   int grid = x->max_ctas > 0 ? x->max_ctas : sm_count();

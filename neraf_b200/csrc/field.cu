@@ -603,11 +603,26 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   // weight gradient, one for "every bias gradient is final" = the last job of the dgrad chain (its row blocks need all
   // row blocks of every earlier link; the heads' bias gradients were complete before this launch).
   unsigned int increments[NERAF_MEGA_MAX_JOBS] = {0};
+  unsigned int slot_off[NERAF_MAX_TRUNK + 2] = {0}, slot_cnt[NERAF_MAX_TRUNK + 2] = {0}, slot_inc[NERAF_MAX_TRUNK + 2] = {0};
   if (notify) {
     NERAF_REQUIRE(phase == 0, "field_backward_dp: completion counters need the one-launch backward (phase 0)");
     notify_slot[producer] = l.L + 1;
-    for (int j = 0; j < nj; ++j)
-      if (notify_slot[j] >= 0) jobs[j].notify = notify + notify_slot[j];
+    // canonical layout (a binding can compute it): matrix k owns ceil(rows_k / 256) counters behind those of matrix k - 1
+    unsigned int next = 0;
+    for (int k = 0; k < l.L + 2; ++k) {
+      const int64_t rows = k < l.L ? l.n[k] : (k == l.L ? l.CF : B);
+      slot_off[k] = next;
+      slot_cnt[k] = (unsigned int)ceil_div(rows, 256);
+      next += slot_cnt[k];
+    }
+    for (int j = 0; j < nj; ++j) {
+      if (notify_slot[j] < 0) continue;
+      const int k = notify_slot[j];
+      NERAF_REQUIRE((unsigned int)ceil_div(jobs[j].M, 256) == slot_cnt[k], "field_backward_dp: counter layout mismatch (job %d)", j);
+      jobs[j].notify = notify + slot_off[k];
+    }
+    NERAF_REQUIRE(next <= NERAF_NOTIFY_COUNTERS, "field_backward_dp: %u completion counters needed, %d available", next,
+                  NERAF_NOTIFY_COUNTERS);
   }
   // Data parallel: the gradient exchange kernel runs BESIDE the job-list launch and follows its completion counters.  It
   // is launched right behind it in the same stream as a programmatic dependent that never waits: it moves in when every
@@ -620,17 +635,28 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
   // left clean by the forward's launch; set up under the tail of the head-gradient kernel that precedes it
   NERAF_TRY(mega_run(jobs, nj, at(ws, l.counters), l.counters_bytes, stream, max_ctas, true, phase != 2, increments,
                      xg != nullptr));
-  unsigned int by_slot[NERAF_MAX_TRUNK + 2] = {0};
-  if (notify)
+  if (notify) {
     for (int j = 0; j < nj; ++j)
-      if (notify_slot[j] >= 0) by_slot[notify_slot[j]] = increments[j];
-  if (notify && opt->notify_increment)
-    for (int k = 0; k < l.L + 2; ++k) opt->notify_increment[k] = by_slot[k];
+      if (notify_slot[j] >= 0) slot_inc[notify_slot[j]] = increments[j];
+    for (int k = 0; k < l.L + 2; ++k) {
+      if (opt->notify_offset) opt->notify_offset[k] = slot_off[k];
+      if (opt->notify_count) opt->notify_count[k] = slot_cnt[k];
+      if (opt->notify_increment) opt->notify_increment[k] = slot_inc[k];
+    }
+  }
   if (xg) {
-    neraf_grad_exchange x = *xg;                       // chunks that name one of this call's counters get its increment
+    neraf_grad_exchange x = *xg;                       // chunks that name counters of this call get their increment
     for (int c = 0; c < x.n_chunks && c < NERAF_MAX_EXCHANGE_CHUNKS; ++c) {
       const uint32_t* nf = x.chunks[c].notify;
-      if (nf >= notify && nf < notify + l.L + 2) x.chunks[c].notify_increment = by_slot[nf - notify];
+      if (!nf || nf < notify || nf >= notify + NERAF_NOTIFY_COUNTERS) continue;
+      const unsigned int idx = (unsigned int)(nf - notify);
+      bool found = false;
+      for (int k = 0; k < l.L + 2 && !found; ++k)
+        if (idx >= slot_off[k] && idx + x.chunks[c].notify_count <= slot_off[k] + slot_cnt[k]) {
+          x.chunks[c].notify_increment = slot_inc[k];
+          found = true;
+        }
+      NERAF_REQUIRE(found, "field_backward_dp: chunk %d of the exchange names counters of no single gradient matrix", c);
     }
     NERAF_TRY(dp_exchange_grads(&x, stream, true));
   }

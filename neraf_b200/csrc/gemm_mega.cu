@@ -77,8 +77,9 @@ struct alignas(64) DeviceJob {
   const __nv_bfloat16* gate; long long ldg;
   float* out_f32; long long ld_f32;
   float* colsum;
-  unsigned int* notify;            // optional: += 1 (gpu-scope release) per epilogue warp and tile, never cleared -- a concurrent
-                                   // kernel (the data-parallel gradient exchange) learns from it that the job's output is complete
+  unsigned int* notify;            // optional, one counter per row block: += 1 (gpu-scope release) per epilogue warp and tile,
+                                   // never cleared -- a concurrent kernel (the data-parallel gradient exchange) learns from
+                                   // them which rows of the job's output are complete
   const float* loss_gt; long long ld_gt; double* loss_sums;   // out_mode 3 only: spectral-loss partial sums (fused)
 };
 
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
       if (tracer) { stamp_clock(P.trace, tile, TR_CK_FENCE); stamp(P.trace, tile, TR_EPI_DONE); }
       if (lane == 0) {
         red_release_add(P.counters + J.cnt_off + mt, 1u);   // ... before the row block's progress is (16 arrivals per tile)
-        if (J.notify != nullptr) red_release_add(J.notify, 1u);
+        if (J.notify != nullptr) red_release_add(J.notify + mt, 1u);
       }
     }
     // multimem.red reductions are fire-and-forget while the kernel runs (the NVLink queue drains behind the remaining
@@ -826,7 +827,7 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     NERAF_REQUIRE(!(s.epi.gate && s.epi.gate_mask), "mega_run: job %d: gate and gate_mask are exclusive", i);
     d.colsum = s.colsum;
     d.notify = s.notify;
-    if (notify_increment) notify_increment[i] = (unsigned int)(d.num_m * d.num_n) * MEGA_EPI_WARPS * 2;
+    if (notify_increment) notify_increment[i] = (unsigned int)d.num_n * MEGA_EPI_WARPS * 2;   // per row-block counter
     d.loss_gt = s.epi.out_f32 ? s.epi.loss_gt : nullptr; d.ld_gt = s.epi.ld_gt; d.loss_sums = s.epi.loss_sums;
     NERAF_REQUIRE(!s.epi.loss_gt || s.epi.out_f32, "mega_run: job %d: loss_gt needs an fp32 output", i);
   }

@@ -795,24 +795,43 @@ class GraphedTrainStep:
             # completion counters the backward advances + the chunk table of the exchange, in the order the backward
             # finishes the gradients: heads, trunk layers L..2, the compact dW1 block, and last the bias gradients
             L = len(weights) - field.sound_rez
-            self._notify = torch.zeros(L + 2, dtype=torch.int32, device=dev)
-            self._notify_inc = (C.c_uint32 * (L + 2))()
+            self._notify = torch.zeros(_lib.NOTIFY_COUNTERS, dtype=torch.int32, device=dev)
+            self._notify_meta = [(C.c_uint32 * (L + 2))() for _ in range(3)]           # offset, count, increment (host, out)
             gx = _lib.GradExchange()
             gx.world, gx.rank, gx.max_ctas = world, self._xchg["rank"], int(os.environ.get("NERAF_COMM_CTAS_KERNEL", "0"))
             offs16 = [0]
             for n_el in sizes[:nw + 1]:
                 offs16.append(offs16[-1] + n_el * 2)
-            n_heads_el = sum(t.numel() for t in weights[L:])
-            chunks = [(offs16[L - 1], n_heads_el * 2, L, 0)]                       # heads (contiguous)
-            for i in range(L - 1, 0, -1):                                           # trunk layer i = red_w[i - 1]
-                chunks.append((offs16[i - 1], sizes[i - 1] * 2, i, 0))
-            chunks.append((offs16[nw], sizes[nw] * 2, 0, 0))                        # compact dW1 block
-            chunks.append((self._xchg["bias_offset"], self._xchg["bias_bytes"], L + 1, 1))
+            # the library's counter layout (neraf_dp_options.notify): one counter per 256 rows of every gradient matrix
+            rows = [t.shape[0] for t in weights[:L]] + [sum(t.shape[0] for t in weights[L:]), B]
+            n_cnt = [(r + 255) // 256 for r in rows]
+            cnt_off = [sum(n_cnt[:k]) for k in range(L + 2)]
+            target_bytes = int(os.environ.get("NERAF_EXCHANGE_CHUNK_MB", "3")) << 20
+
+            def matrix_chunks(slot, offset, n_rows, row_bytes):
+                """Row-block groups of one gradient matrix, each ~target_bytes: they travel while the rest is computed."""
+                groups = max(1, min(n_cnt[slot], (n_rows * row_bytes + target_bytes - 1) // target_bytes))
+                out, c0 = [], 0
+                for g in range(groups):
+                    c1 = n_cnt[slot] * (g + 1) // groups
+                    r0, r1 = c0 * 256, min(n_rows, c1 * 256)
+                    out.append((offset + r0 * row_bytes, (r1 - r0) * row_bytes, cnt_off[slot] + c0, c1 - c0, 0))
+                    c0 = c1
+                return out
+            chunks = matrix_chunks(L, offs16[L - 1], rows[L], weights[L].shape[1] * 2)   # heads (contiguous)
+            for i in range(L - 1, 0, -1):                                                # trunk layer i = red_w[i - 1]
+                chunks += matrix_chunks(i, offs16[i - 1], rows[i], weights[i].shape[1] * 2)
+            chunks += matrix_chunks(0, offs16[nw], rows[0], ldc * 2)                     # compact dW1 block
+            chunks.append((self._xchg["bias_offset"], self._xchg["bias_bytes"], cnt_off[L + 1], n_cnt[L + 1], 1))
+            if len(chunks) > _lib.MAX_EXCHANGE_CHUNKS:
+                raise ValueError("too many exchange chunks: raise NERAF_EXCHANGE_CHUNK_MB")
             gx.n_chunks = len(chunks)
-            for c, (off, nbytes, slot, f32) in enumerate(chunks):
+            for c, (off, nbytes, cnt0, cnt_n, f32) in enumerate(chunks):
                 gx.chunks[c].offset, gx.chunks[c].bytes = off, nbytes
-                gx.chunks[c].notify = self._notify.data_ptr() + 4 * slot
+                gx.chunks[c].notify = self._notify.data_ptr() + 4 * cnt0
+                gx.chunks[c].notify_count = cnt_n
                 gx.chunks[c].f32 = f32
+            self._exchange_chunks = chunks
             gx.multicast = self._xchg["multicast"] or None
             for r in range(world):
                 gx.peers[r] = self._xchg["region_ptrs"][r]
@@ -821,7 +840,8 @@ class GraphedTrainStep:
             gx.state = self._comm_state.data_ptr()
             self._gx = gx
             opt1.notify = self._notify.data_ptr()
-            opt1.notify_increment = C.cast(self._notify_inc, C.POINTER(C.c_uint32))
+            opt1.notify_offset, opt1.notify_count, opt1.notify_increment = (
+                C.cast(m, C.POINTER(C.c_uint32)) for m in self._notify_meta)
             opt1.exchange = C.pointer(gx)
         opt1.phase, opt1.max_ctas = (1 if self.overlap else 0), 0
         opt2.phase, opt2.max_ctas = 2, max(2, (sm_count - self.comm_ctas) // 2 * 2)
