@@ -281,13 +281,17 @@ NERAF_API int neraf_field_backward_dp(const neraf_field_dims* dims, int precisio
                             int64_t denc_ld, const neraf_dp_options* opt, neraf_stream_t stream);
 
 /* dweight0[n, k] = dbias0[n] * grid_feature[k] (k < n_grid; row stride n_grid + n_enc; may be NULL),
- * dweight0[n, n_grid + e] = dw0_compact[n, e] (when dw0_compact != NULL) and
+ * dweight0[n, n_grid + e] = dw0_compact[n, e] (when dw0_compact != NULL; fp32, or bf16 with compact_bf16 != 0; row stride
+ * round_up(n_enc, 8)) and
  * dgrid[k] = sum_n weight0[n, k] * dbias0[n] (may be NULL; overwritten; bit-reproducible: the row blocks' partial sums
  * meet in fp64): the deferred part of neraf_field_backward_dp.
- * scratch (with dgrid): dev, >= 8 * n_grid + 8 bytes, 8-byte aligned, zero before the first use; the call leaves it zero. */
+ * scratch (with dgrid): dev, >= 8 * n_grid + 8 bytes, 8-byte aligned, zero before the first use; the call leaves it zero.
+ * widen_*: optional second duty of the same launch after a bf16 gradient exchange: widen_dst[i] = (float)widen_src_bf16[i]
+ * for i < widen_n (both 16-byte aligned): the exchanged sums land in the fp32 .grad buffer without a launch of their own. */
 NERAF_API int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
-                           const float* dbias0, const float* dw0_compact, float* dweight0, float* dgrid,
-                           void* scratch, neraf_stream_t stream);
+                           const float* dbias0, const void* dw0_compact, int32_t compact_bf16, float* dweight0,
+                           float* dgrid, void* scratch, const void* widen_src_bf16, float* widen_dst, int64_t widen_n,
+                           neraf_stream_t stream);
 
 /* Encodings only (NeRFEncoding x3 + SHEncoding + normalisation/zeroing, NeRAF_model.py:533-551):
  * enc_out dev fp32 (B, 163) row stride ld. */

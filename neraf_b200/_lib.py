@@ -145,7 +145,7 @@ SIGNATURES = {
     "neraf_field_backward_dp": (C.c_int, [C.POINTER(FieldDims), _i32, _i64, _vp, _vp, _vp, _pp, _vp, _vp, _sz, _pp, _pp,
                                            _vp, _vp, _i64, C.POINTER(DpOptions), _vp]),
     "neraf_dp_exchange_grads": (C.c_int, [C.POINTER(GradExchange), _vp]),
-    "neraf_field_grid_grads": (C.c_int, [C.POINTER(FieldDims), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "neraf_field_grid_grads": (C.c_int, [C.POINTER(FieldDims), _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "neraf_encode_queries": (C.c_int, [C.POINTER(Queries), _vp, _i64, _vp]),
     "neraf_spectral_loss_sums": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp]),
     "neraf_spectral_loss_finalize": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp]),

@@ -4,6 +4,8 @@
 //    (NeRAF_model.py:557-560 expands the same 1024 values to every row): the rank-1 weight
 //    gradient and the gradient w.r.t. the grid feature (the forward mat-vec lives in encode.cu's prep kernel),
 //  * bias gradients (column sums), and the gradient through the 10*tanh heads (NeRAF_field.py:57-58).
+#include <algorithm>
+
 #include "common.cuh"
 #include <cstdlib>
 
@@ -135,9 +137,31 @@ __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restr
                                                             const float* __restrict__ W, int64_t ldw, int64_t N, int64_t K,
                                                             float* __restrict__ dW, float* __restrict__ dg,
                                                             double* __restrict__ dg64, unsigned int* __restrict__ ticket,
-                                                            const float* __restrict__ compact, int64_t E, int64_t ld_c) {
+                                                            const void* __restrict__ compact, int compact_bf16, int64_t E,
+                                                            int64_t ld_c, int gg_blocks,
+                                                            const __nv_bfloat16* __restrict__ widen_src,
+                                                            float* __restrict__ widen_dst, int64_t widen_n) {
   asm volatile("griddepcontrol.wait;" ::: "memory");        // programmatic dependent launch: the backward GEMMs are complete
   const int t = threadIdx.x;
+  if ((int)blockIdx.x >= gg_blocks) {
+    // extra blocks (data parallel): the exchanged bf16 gradient sums -> the fp32 .grad buffer, 16 bytes in, 32 out
+    const int64_t n8 = widen_n / 8;
+    const int64_t stride = (int64_t)(gridDim.x - gg_blocks) * GG_TPB;
+    for (int64_t i = (int64_t)(blockIdx.x - gg_blocks) * GG_TPB + t; i < n8; i += stride) {
+      const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(widen_src) + i);
+      const unsigned int w[4] = {raw.x, raw.y, raw.z, raw.w};
+      float4 lo, hi;
+      lo.x = __uint_as_float(w[0] << 16); lo.y = __uint_as_float(w[0] & 0xffff0000u);
+      lo.z = __uint_as_float(w[1] << 16); lo.w = __uint_as_float(w[1] & 0xffff0000u);
+      hi.x = __uint_as_float(w[2] << 16); hi.y = __uint_as_float(w[2] & 0xffff0000u);
+      hi.z = __uint_as_float(w[3] << 16); hi.w = __uint_as_float(w[3] & 0xffff0000u);
+      reinterpret_cast<float4*>(widen_dst)[2 * i] = lo;
+      reinterpret_cast<float4*>(widen_dst)[2 * i + 1] = hi;
+    }
+    if (blockIdx.x == gridDim.x - 1)
+      for (int64_t i = n8 * 8 + t; i < widen_n; i += GG_TPB) widen_dst[i] = __bfloat162float(widen_src[i]);
+    return;
+  }
   const int64_t n0 = (int64_t)blockIdx.x * GG_ROWS;
   const int rows = (int)(N - n0 < GG_ROWS ? N - n0 : GG_ROWS);
   float gk[KCH], acc[KCH], w[GG_ROWS][KCH], sn[GG_ROWS];
@@ -168,8 +192,13 @@ __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restr
           const int64_t k = t + 256 * j;
           if (k < K) row[k] = sn[r] * gk[j];
         }
-        if (compact)
-          for (int64_t e = t; e < E; e += GG_TPB) row[K + e] = __ldg(compact + (n0 + r) * ld_c + e);
+        if (compact) {
+          if (compact_bf16)
+            for (int64_t e = t; e < E; e += GG_TPB)
+              row[K + e] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(compact)[(n0 + r) * ld_c + e]);
+          else
+            for (int64_t e = t; e < E; e += GG_TPB) row[K + e] = __ldg(reinterpret_cast<const float*>(compact) + (n0 + r) * ld_c + e);
+        }
       }
     }
   }
@@ -186,7 +215,7 @@ __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restr
     __shared__ bool last;
     __threadfence();
     __syncthreads();
-    if (t == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (t == 0) last = atomicAdd(ticket, 1u) == (unsigned int)gg_blocks - 1;
     __syncthreads();
     if (last) {
       __threadfence();
@@ -201,14 +230,21 @@ __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restr
 
 // scratch: G doubles + one u32 ticket (zero before the first use, left zero)
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
-               void* scratch, cudaStream_t stream, const float* compact, int64_t E, int64_t ld_c) {
+               void* scratch, cudaStream_t stream, const void* compact, int64_t E, int64_t ld_c, bool compact_bf16,
+               const void* widen_src, float* widen_dst, int64_t widen_n) {
   if (N <= 0 || K <= 0 || (!dW && !dg)) return NERAF_OK;
+  NERAF_REQUIRE(widen_n == 0 || (widen_src && widen_dst && ((uintptr_t)widen_src & 15) == 0 && ((uintptr_t)widen_dst & 15) == 0),
+                "grid_grads: the buffers to widen must be 16-byte aligned");
   NERAF_REQUIRE(K <= 256 * 8, "grid_grads: at most 2048 grid-feature columns (got %lld)", (long long)K);
   NERAF_REQUIRE(!dg || (scratch && ((uintptr_t)scratch & 7) == 0), "grid_grads: dg needs an 8-byte aligned scratch buffer");
   double* dg64 = reinterpret_cast<double*>(scratch);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(dg64 + K);
-  const unsigned grid = (unsigned)ceil_div(N, GG_ROWS);
-  const float* cp = dW ? compact : nullptr;
+  const int gg_blocks = (int)ceil_div(N, GG_ROWS);
+  const int widen_blocks = widen_n > 0 ? (int)std::min<int64_t>(ceil_div(widen_n, 8 * GG_TPB * 4), 4 * sm_count()) : 0;
+  const unsigned grid = (unsigned)(gg_blocks + widen_blocks);
+  const void* cp = dW ? compact : nullptr;
+  const int cbf = compact_bf16 ? 1 : 0;
+  const __nv_bfloat16* wsrc = reinterpret_cast<const __nv_bfloat16*>(widen_src);
   // no memset in front of it: the kernel follows the backward's job-list launch directly and may be set up under its tail
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GG_TPB); cfg.stream = stream;
@@ -216,8 +252,12 @@ int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int6
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  if (K <= 256 * 4) NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<4>, s, g, W, ldw, N, K, dW, dg, dg64, ticket, cp, E, ld_c));
-  else NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<8>, s, g, W, ldw, N, K, dW, dg, dg64, ticket, cp, E, ld_c));
+  if (K <= 256 * 4)
+    NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<4>, s, g, W, ldw, N, K, dW, dg, dg64, ticket, cp, cbf, E, ld_c,
+                                        gg_blocks, wsrc, widen_dst, widen_n));
+  else
+    NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grid_grads_kernel<8>, s, g, W, ldw, N, K, dW, dg, dg64, ticket, cp, cbf, E, ld_c,
+                                        gg_blocks, wsrc, widen_dst, widen_n));
   NERAF_CHECK_LAUNCH("grid_grads_kernel");
   return NERAF_OK;
 }

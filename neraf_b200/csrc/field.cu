@@ -559,11 +559,17 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       NERAF_TRY(mc_alias(j.epi.out_f32, &j.epi.out_f32_multicast));
     }
   }
+  // With the gradient exchange running beside this launch, the largest weight gradient (dW of trunk layer 1: two thirds
+  // of the bytes) is scheduled BEFORE the dgrad job of the same step instead of behind it: it is then complete -- and
+  // travelling -- while the last dgrad job and the compact dW1 block are computed, instead of finishing with the launch.
+  const bool exchange_beside = opt && opt->exchange;
+  int status = NERAF_OK;
   for (int i = last; i >= 0; --i) {
     if (phase == 2 && i > 1) continue;
     if (phase == 1 && i == 0) break;
     const int dz_producer = (phase == 2 && i == 1) ? -1 : producer;   // job that writes dZ_i (phase 2: an earlier launch)
-    if (i > 0 && !(phase == 1 && i == 1)) {            // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
+    auto add_dgrad = [&]() {                           // chain: dZ_{i-1} = (dZ_i W_i) * leaky'(x_{i-1})
+      if (!(i > 0 && !(phase == 1 && i == 1))) return;
       producer = nj;
       MegaJob& j = jobs[nj++];
       j = make_dgrad_job(B, l.k[i], l.n[i], at(ws, l.dz[i]), l.ldx[i], at(pack, l.w[i]), l.ldw[i], dz_producer);
@@ -574,31 +580,36 @@ static int field_backward_impl(const neraf_field_dims* dims, int precision, int6
       // both only need dZ_i -- interleaved, the link drains behind the dgrad tiles instead of throttling every CTA
       // pair at once (the largest pair, dgrad 2->1 / dW_2, is 70 % of the bytes and sits at the end of the backward).
       if (mc && phase == 0) j.merge_next = 1;
-    }
-    if (phase == 2 && i == 1) continue;                // dW_1 belongs to phase 1
-    notify_slot[nj] = i;
-    MegaJob& w = jobs[nj++];                           // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
-    if (i > 0) {
-      w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
-      if (dw16) {
-        w.epi.out_bf16 = dw16[i]; w.epi.ld_bf16 = l.k[i];
+    };
+    auto add_wgrad = [&]() {                           // dW_i = dZ_i^T x_{i-1}: needs every row block of dZ_i
+      if (phase == 2 && i == 1) return;                // dW_1 belongs to phase 1
+      notify_slot[nj] = i;
+      MegaJob& w = jobs[nj++];
+      if (i > 0) {
+        w = make_wgrad_job(l.n[i], l.k[i], B, at(ws, l.dz[i]), l.ldx[i], at(ws, l.x[i - 1]), l.ldx[i - 1], dz_producer);
+        if (dw16) {
+          w.epi.out_bf16 = dw16[i]; w.epi.ld_bf16 = l.k[i];
+        } else {
+          w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
+          if (status == NERAF_OK) status = mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast);
+        }
       } else {
-        w.epi.out_f32 = dweights[i]; w.epi.ld_f32 = l.k[i];
-        NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
+        w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
+        w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
+        if (dw0_compact) { w.epi.out_f32 = dw0_compact; w.epi.ld_f32 = round_up(l.E, 8); }   // (n_1, E) with 32-byte rows
+        if (dw16) { w.epi.out_f32 = nullptr; w.epi.out_bf16 = dw16[0]; w.epi.ld_bf16 = round_up(l.E, 8); }
+        if (status == NERAF_OK) status = mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast);
+        if (denc) {
+          MegaJob& e = jobs[nj++];
+          e = make_dgrad_job(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.w[0]), l.ldw[0], dz_producer);
+          e.epi.out_f32 = denc; e.epi.ld_f32 = denc_ld;
+        }
       }
-    } else {
-      w = make_wgrad_job(l.n[0], l.E, B, at(ws, l.dz[0]), l.ldx[0], at(ws, l.enc), l.ld_enc, dz_producer);
-      w.epi.out_f32 = dweights[0] + l.G; w.epi.ld_f32 = ldw0;
-      if (dw0_compact) { w.epi.out_f32 = dw0_compact; w.epi.ld_f32 = round_up(l.E, 8); }   // (n_1, E) with 32-byte rows
-      if (dw16) { w.epi.out_f32 = nullptr; w.epi.out_bf16 = dw16[0]; w.epi.ld_bf16 = round_up(l.E, 8); }
-      NERAF_TRY(mc_alias(w.epi.out_f32, &w.epi.out_f32_multicast));
-      if (denc) {
-        MegaJob& e = jobs[nj++];
-        e = make_dgrad_job(B, l.E, l.n[0], at(ws, l.dz[0]), l.ldx[0], at(pack, l.w[0]), l.ldw[0], dz_producer);
-        e.epi.out_f32 = denc; e.epi.ld_f32 = denc_ld;
-      }
-    }
+    };
+    if (exchange_beside && phase == 0 && i == 1 && !mc) { add_wgrad(); add_dgrad(); }
+    else { add_dgrad(); add_wgrad(); }
   }
+  NERAF_TRY(status);
   // Completion counters for a concurrent consumer (the data-parallel gradient exchange, neraf_dp_exchange_grads): one per
   // weight gradient, one for "every bias gradient is final" = the last job of the dgrad chain (its row blocks need all
   // row blocks of every earlier link; the heads' bias gradients were complete before this launch).
@@ -688,12 +699,14 @@ extern "C" int neraf_field_backward_dp(const neraf_field_dims* dims, int precisi
 }
 
 extern "C" int neraf_field_grid_grads(const neraf_field_dims* dims, const float* grid_feature, const float* weight0,
-                                      const float* dbias0, const float* dw0_compact, float* dweight0, float* dgrid,
-                                      void* scratch, neraf_stream_t stream) {
+                                      const float* dbias0, const void* dw0_compact, int32_t compact_bf16, float* dweight0,
+                                      float* dgrid, void* scratch, const void* widen_src_bf16, float* widen_dst,
+                                      int64_t widen_n, neraf_stream_t stream) {
   NERAF_REQUIRE(dims && dims->n_trunk >= 1, "field_grid_grads: dims is null");
   if (dims->n_grid <= 0) return NERAF_OK;
   NERAF_REQUIRE(grid_feature && weight0 && dbias0 && (dweight0 || dgrid), "field_grid_grads: null pointer");
   NERAF_REQUIRE(!dgrid || scratch, "field_grid_grads: dgrid needs scratch");
   return grid_grads(dbias0, grid_feature, weight0, (int64_t)dims->n_grid + dims->n_enc, dims->trunk[0], dims->n_grid, dweight0,
-                    dgrid, scratch, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 8));
+                    dgrid, scratch, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 8), compact_bf16 != 0,
+                    widen_src_bf16, widen_dst, widen_n);
 }

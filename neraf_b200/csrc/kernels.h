@@ -68,9 +68,12 @@ struct PackList {
 int pack_list(PackList& L, cudaStream_t stream);
 // dW[n*ldw + k] = s[n] * g[k] (dW may be null) and dg[k] = sum_n W[n*ldw + k] * s[n] (dg may be null; OVERWRITTEN,
 // bit-reproducible) in one launch.  scratch (needed with dg): K doubles + 8 bytes, zero before the first use, left zero.
-// compact (optional): (N, E) block with row stride ld_c copied into dW[:, K:K+E]
+// compact (optional): (N, E) block (fp32, or bf16 with compact_bf16) with row stride ld_c copied into dW[:, K:K+E]
+// widen_* (optional, data parallel): widen_dst[i] = float(widen_src[i]) for i < widen_n, bf16 -> fp32, by extra blocks of
+// the same launch
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
-               void* scratch, cudaStream_t stream, const float* compact = nullptr, int64_t E = 0, int64_t ld_c = 0);
+               void* scratch, cudaStream_t stream, const void* compact = nullptr, int64_t E = 0, int64_t ld_c = 0,
+               bool compact_bf16 = false, const void* widen_src = nullptr, float* widen_dst = nullptr, int64_t widen_n = 0);
 // out[n] = sum_m X[m*ld + n]   fp32 row-major (M,N)
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
 struct HeadColsum {

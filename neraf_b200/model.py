@@ -806,7 +806,10 @@ class GraphedTrainStep:
             rows = [t.shape[0] for t in weights[:L]] + [sum(t.shape[0] for t in weights[L:]), B]
             n_cnt = [(r + 255) // 256 for r in rows]
             cnt_off = [sum(n_cnt[:k]) for k in range(L + 2)]
-            target_bytes = int(os.environ.get("NERAF_EXCHANGE_CHUNK_MB", "3")) << 20
+            # One chunk per matrix by default.  Streaming ~3 MB row groups while the rest of a matrix is computed measured
+            # SLOWER (2 GPUs: 552 vs 525 us per step): every chunk costs a flag round trip plus a load-reduce round trip
+            # over NVLink (~10 us) whatever its size, and the workers take the chunks one after the other.
+            target_bytes = int(os.environ.get("NERAF_EXCHANGE_CHUNK_MB", "64")) << 20
 
             def matrix_chunks(slot, offset, n_rows, row_bytes):
                 """Row-block groups of one gradient matrix, each ~target_bytes: they travel while the rest is computed."""
@@ -821,8 +824,9 @@ class GraphedTrainStep:
             chunks = matrix_chunks(L, offs16[L - 1], rows[L], weights[L].shape[1] * 2)   # heads (contiguous)
             for i in range(L - 1, 0, -1):                                                # trunk layer i = red_w[i - 1]
                 chunks += matrix_chunks(i, offs16[i - 1], rows[i], weights[i].shape[1] * 2)
-            chunks += matrix_chunks(0, offs16[nw], rows[0], ldc * 2)                     # compact dW1 block
+            # the bias gradients are final when the dgrad chain ends, the compact dW1 block is the backward's last job
             chunks.append((self._xchg["bias_offset"], self._xchg["bias_bytes"], cnt_off[L + 1], n_cnt[L + 1], 1))
+            chunks += matrix_chunks(0, offs16[nw], rows[0], ldc * 2)                     # compact dW1 block
             if len(chunks) > _lib.MAX_EXCHANGE_CHUNKS:
                 raise ValueError("too many exchange chunks: raise NERAF_EXCHANGE_CHUNK_MB")
             gx.n_chunks = len(chunks)
@@ -893,12 +897,21 @@ class GraphedTrainStep:
                                                    _lib.stream_ptr(dev)))
 
         def grid_part():          # after the exchange: the grid-block gradients from the REDUCED db1, dW1 block copied back
-            if self.kernel_exchange:      # bf16 sums (every rank holds them) -> the fp32 .grad views
-                self.flat_grad[:n_weight_elems].copy_(self._flat_low[:n_weight_elems])
-            if defer:
+            if not defer:
+                return
+            if self.kernel_exchange:
+                # one launch: the bf16 sums every rank now holds -> the fp32 .grad views (all matrices but the compact dW1
+                # block, which goes straight into dW1), and the grid block of dW1 / dg from the reduced db1
+                n_widen = n_weight_elems - n1 * ldc
                 _lib.check(lib.neraf_field_grid_grads(C.byref(dims), grid_p.data_ptr(), weights[0].data_ptr(),
-                                                      dbs[0].data_ptr(), compact.data_ptr(), dws[0].data_ptr(),
-                                                      dgrid.data_ptr(), self._grid_scratch.data_ptr(),
+                                                      dbs[0].data_ptr(), self._flat_low[n_widen:].data_ptr(), 1,
+                                                      dws[0].data_ptr(), dgrid.data_ptr(), self._grid_scratch.data_ptr(),
+                                                      self._flat_low.data_ptr(), self.flat_grad.data_ptr(), n_widen,
+                                                      _lib.stream_ptr(dev)))
+            else:
+                _lib.check(lib.neraf_field_grid_grads(C.byref(dims), grid_p.data_ptr(), weights[0].data_ptr(),
+                                                      dbs[0].data_ptr(), compact.data_ptr(), 0, dws[0].data_ptr(),
+                                                      dgrid.data_ptr(), self._grid_scratch.data_ptr(), None, None, 0,
                                                       _lib.stream_ptr(dev)))
         self._grid_part = grid_part
         self._grid_scratch = torch.zeros(2 * max(n_grid, 1) + 4, dtype=torch.float32, device=dev)   # fp64 sums of dg + ticket
