@@ -243,6 +243,9 @@ typedef struct {
   void* peers[NERAF_MAX_RANKS];
   void* signals[NERAF_MAX_RANKS];
   uint32_t* state;
+  uint64_t* trace;     /* optional dev u64[4 + 4 * n_chunks], %globaltimer stamps of the last call: [0] start, [1] this rank's
+                          workers done, [2] every rank done; per chunk c at [4 + 4 c]: announced by this rank, announced
+                          by every rank (seen by worker block 1), issued by worker block 1 */
 } neraf_grad_exchange;
 NERAF_API int neraf_dp_exchange_grads(const neraf_grad_exchange* x, neraf_stream_t stream);
 

@@ -80,7 +80,8 @@ class ExchangeChunk(C.Structure):   # neraf_exchange_chunk
 class GradExchange(C.Structure):    # neraf_grad_exchange
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_chunks", C.c_int32), ("max_ctas", C.c_int32),
                 ("chunks", ExchangeChunk * MAX_EXCHANGE_CHUNKS), ("multicast", C.c_void_p),
-                ("peers", C.c_void_p * MAX_RANKS), ("signals", C.c_void_p * MAX_RANKS), ("state", C.c_void_p)]
+                ("peers", C.c_void_p * MAX_RANKS), ("signals", C.c_void_p * MAX_RANKS), ("state", C.c_void_p),
+                ("trace", C.c_void_p)]
 
 
 class DpOptions(C.Structure):

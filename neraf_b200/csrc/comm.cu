@@ -47,6 +47,7 @@ struct CommArgs {
   uint8_t* peers[NERAF_MAX_RANKS];
   uint8_t* sig[NERAF_MAX_RANKS];
   unsigned int* state;                         // [0] steps completed  [1] worker tickets
+  unsigned long long* trace;                   // optional: globaltimer stamps (see neraf_grad_exchange.trace)
 };
 
 __device__ __forceinline__ unsigned int comm_ld_acquire_gpu(const unsigned int* p) {
@@ -61,6 +62,15 @@ __device__ __forceinline__ unsigned int comm_ld_acquire_sys(const unsigned int* 
 }
 __device__ __forceinline__ void comm_st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void comm_st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void comm_stamp(unsigned long long* trace, int slot) {
+  if (trace == nullptr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  trace[slot] = t;
 }
 __device__ __forceinline__ bool reached(unsigned int value, unsigned int target) { return (int)(value - target) >= 0; }
 
@@ -129,6 +139,7 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
   if (blockIdx.x == 0) {
     // ------------------------------------------------------------------ herald
     if (threadIdx.x == 0) {
+      comm_stamp(A.trace, 0);
       for (int c = 0; c < A.n_chunks; ++c) {
         const CommChunk& ch = A.ch[c];
         if (ch.notify != nullptr) {
@@ -140,9 +151,12 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
               if (clock64() - t0 > kCommSpinLimit) __trap();
             }
         }
+        // ONE system-scope fence (everything observed through the counters is ordered before the flags), then plain
+        // flag stores: a release store per peer is a fence per peer -- measured ~3 us each, x 8 peers x 8 chunks on 8 GPUs
         __threadfence_system();
         for (int q = 0; q < A.world; ++q)
-          comm_st_release_sys(reinterpret_cast<unsigned int*>(A.sig[q] + kReadyOffset) + c * NERAF_MAX_RANKS + A.rank, seq);
+          comm_st_relaxed_sys(reinterpret_cast<unsigned int*>(A.sig[q] + kReadyOffset) + c * NERAF_MAX_RANKS + A.rank, seq);
+        comm_stamp(A.trace, 4 + 4 * c);                     // this rank's chunk c announced
       }
       // every worker of this rank has reduced and broadcast its slices
       {
@@ -152,9 +166,10 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
           if (clock64() - t0 > kCommSpinLimit) __trap();
         }
       }
+      comm_stamp(A.trace, 1);                               // this rank's workers are done
       __threadfence_system();
       for (int q = 0; q < A.world; ++q)
-        comm_st_release_sys(reinterpret_cast<unsigned int*>(A.sig[q] + kDoneOffset) + A.rank, seq);
+        comm_st_relaxed_sys(reinterpret_cast<unsigned int*>(A.sig[q] + kDoneOffset) + A.rank, seq);
       for (int q = 0; q < A.world; ++q) {
         const long long t0 = clock64();
         while (!reached(comm_ld_acquire_sys(my_sig_done + q), seq)) {
@@ -162,6 +177,7 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
           if (clock64() - t0 > kCommSpinLimit) __trap();
         }
       }
+      comm_stamp(A.trace, 2);                               // every rank is done
       A.state[1] = 0u;
       A.state[0] = seq;
       __threadfence();
@@ -184,6 +200,7 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
       }
     }
     __syncthreads();
+    if (blockIdx.x == 1 && threadIdx.x == 0) comm_stamp(A.trace, 4 + 4 * c + 1);     // every rank announced chunk c
     // this rank's slice of the chunk, in 16-byte granules
     const long long granules = (long long)(ch.bytes / 16);
     const long long g0 = granules * A.rank / A.world, g1 = granules * (A.rank + 1) / A.world;
@@ -214,6 +231,7 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
         for (int q = 0; q < A.world; ++q) st_peer(A.peers[q] + off, v);
       }
     }
+    if (blockIdx.x == 1 && threadIdx.x == 0) comm_stamp(A.trace, 4 + 4 * c + 2);     // block 1 has issued its share of chunk c
   }
   __threadfence_system();
   __syncthreads();
@@ -236,6 +254,7 @@ int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool be
   A.n_chunks = x->n_chunks; A.world = x->world; A.rank = x->rank;
   A.mc = reinterpret_cast<uint8_t*>(x->multicast);
   A.state = x->state;
+  A.trace = reinterpret_cast<unsigned long long*>(x->trace);
   NERAF_REQUIRE(!A.mc || ((uintptr_t)A.mc & 15) == 0, "dp_exchange_grads: misaligned multicast mapping");
   for (int r = 0; r < x->world; ++r) {
     NERAF_REQUIRE(x->peers[r] && x->signals[r], "dp_exchange_grads: region / signal buffer of rank %d is null", r);

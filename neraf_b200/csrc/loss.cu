@@ -245,8 +245,9 @@ __global__ void __maxnreg__(40) loss_head_kernel(const LossHeadArgs A) {
         double* slot = reinterpret_cast<double*>(peer) + (par * NERAF_MAX_RANKS + A.rank) * 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) st_relaxed_sys_f64(slot + k, __ldcg(A.sums + k));
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned int*>(peer + kXchgFlagOffset) + par * NERAF_MAX_RANKS + A.rank, seq);
+        __threadfence_system();                             // the slot is visible before the flag (one fence, plain store)
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned int*>(peer + kXchgFlagOffset) +
+                                                                 par * NERAF_MAX_RANKS + A.rank), "r"(seq) : "memory");
         const unsigned int* flag = reinterpret_cast<const unsigned int*>(reinterpret_cast<uint8_t*>(A.peers[A.rank]) + kXchgFlagOffset) +
                                    par * NERAF_MAX_RANKS + threadIdx.x;
         const long long t0 = clock64();

@@ -842,6 +842,10 @@ class GraphedTrainStep:
                 gx.signals[r] = self._xchg["signal_ptrs"][r]
             self._comm_state = torch.zeros(4, dtype=torch.int32, device=dev)
             gx.state = self._comm_state.data_ptr()
+            self._comm_trace = None
+            if os.environ.get("NERAF_COMM_TRACE"):             # timeline of the exchange kernel (tools/time_dp_segments.py)
+                self._comm_trace = torch.zeros(4 + 4 * len(chunks), dtype=torch.int64, device=dev)
+                gx.trace = self._comm_trace.data_ptr()
             self._gx = gx
             opt1.notify = self._notify.data_ptr()
             opt1.notify_offset, opt1.notify_count, opt1.notify_increment = (

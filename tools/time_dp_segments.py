@@ -21,6 +21,8 @@ ref = None
 variants = [("nccl fp32", dict(exchange="nccl", grad_dtype=torch.float32)),
             ("nccl bf16", dict(exchange="nccl", grad_dtype=torch.bfloat16)),
             ("kernel", dict(exchange="kernel"))]
+if os.environ.get("ONLY"):
+    variants = [v for v in variants if v[0] in os.environ["ONLY"].split(",")]
 if os.environ.get("WITH_OVERLAP"):
     variants += [("overlap fp32", dict(exchange="nccl", overlap_allreduce=True, grad_dtype=torch.float32)),
                  ("overlap bf16", dict(exchange="nccl", overlap_allreduce=True, grad_dtype=torch.bfloat16))]
@@ -54,5 +56,17 @@ for name, kw in variants:
         print(f"{name:14s} {float(t):8.1f} us/step   kernel_exchange={step.kernel_exchange} "
               f"multicast={bool(step._xchg and step._xchg['multicast'])} overlap={getattr(step, 'overlap', False)} "
               f"nvls={step.nvls}   grads vs nccl fp32: {err:.2e}", flush=True)
+    tr = getattr(step, "_comm_trace", None)
+    if tr is not None:                     # timeline of the exchange kernel of the LAST step, this rank, us from its start
+        t = tr.cpu().tolist()
+        t0 = t[0]
+        line = f"rank {rank} exchange kernel: workers done {(t[1] - t0) / 1e3:.1f}, every rank done {(t[2] - t0) / 1e3:.1f} us; chunks"
+        for c, ch in enumerate(step._exchange_chunks):
+            a, b, d = ((t[4 + 4 * c + i] - t0) / 1e3 for i in range(3))
+            line += f" | {ch[1] / 1e6:.1f} MB: announced {a:.1f}, all ranks {b:.1f}, issued {d:.1f}"
+        for r in range(world):
+            if r == rank and r in (0, world - 1):
+                print(line, flush=True)
+            dist.barrier()
     dist.barrier()
 dist.destroy_process_group()
