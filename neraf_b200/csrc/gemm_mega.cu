@@ -50,12 +50,15 @@ namespace umma {
 
 constexpr int MEGA_EPI_WARPS = 8;                              // two per TMEM lane quarter (column halves)
 constexpr int MEGA_THREADS = 64 + 32 * MEGA_EPI_WARPS;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int MEGA_STAGES = 6;
+constexpr int MEGA_STAGES = 6;                                 // ring depth (MegaParams.stages may ask for fewer)
 constexpr int MEGA_A_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB
 constexpr int MEGA_B_BYTES = 128 * BLOCK_K * 2;                // up to bn/2 = 128 rows: 16 KB
 constexpr int MEGA_OUT_BYTES = 32 * 128;                       // per-warp 32x32 fp32 transpose tile (unaligned fp32 outputs only)
 constexpr int MEGA_BIAS_BYTES = 256;                            // per-warp bias slice of the current chunk pair
-constexpr int MEGA_SMEM_BYTES = MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES) + MEGA_EPI_WARPS * (MEGA_OUT_BYTES + MEGA_BIAS_BYTES) + (2 * MEGA_STAGES + 4) * 8 + 16;
+constexpr int mega_smem_bytes(int stages) {
+  return stages * (MEGA_A_BYTES + MEGA_B_BYTES) + MEGA_EPI_WARPS * (MEGA_OUT_BYTES + MEGA_BIAS_BYTES) + (2 * MEGA_STAGES + 4) * 8 + 16;
+}
+constexpr int MEGA_SMEM_BYTES = mega_smem_bytes(MEGA_STAGES);   // 226 KB: with the 1 KB the system reserves per CTA the SM is full
 constexpr int MEGA_TMEM_COLS = 512;
 constexpr int MEGA_ACC_COLS = 256;
 constexpr int MN_BOX_BYTES = 64 * 128;                         // one MN-major box: 64 k-rows x 64 MN elements
@@ -93,6 +96,8 @@ struct MegaParams {
                                    // the last CTA to finish clears them all, so the NEXT launch finds them zero
   unsigned int* counters;
   unsigned long long* trace;       // null unless tracing
+  int stages;                      // depth of the operand ring (<= MEGA_STAGES): 5 leaves 32 KB of the SM's shared memory free,
+                                   // which is what lets a CTA of another kernel (the gradient exchange) sit beside this one
   int pdl_late;                    // programmatic dependent launch: release the next kernel when this CTA's tiles are done
                                    // (1) or as soon as the grid is resident (0)
   DeviceJob jobs[NERAF_MEGA_MAX_JOBS];
@@ -211,9 +216,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
   // 128-byte swizzle of TMA / UMMA needs it, and there is no room for an alignment slack)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int STAGES = P.stages;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + MEGA_STAGES * MEGA_A_BYTES;
-  uint8_t* out_buf = smem + MEGA_STAGES * (MEGA_A_BYTES + MEGA_B_BYTES);       // 1024-byte aligned
+  uint8_t* smem_b = smem + STAGES * MEGA_A_BYTES;
+  uint8_t* out_buf = smem + STAGES * (MEGA_A_BYTES + MEGA_B_BYTES);            // 1024-byte aligned
   float* bias_buf = reinterpret_cast<float*>(out_buf + MEGA_EPI_WARPS * MEGA_OUT_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_buf + MEGA_EPI_WARPS * (MEGA_OUT_BYTES + MEGA_BIAS_BYTES));
   uint64_t* empty_bar = full_bar + MEGA_STAGES;
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < MEGA_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, MEGA_EPI_WARPS * CG); }
     fence_barrier_init();
   }
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           }
           return __all_sync(FULL_MASK, ok);
         };
-        const int pre_max = J.b_static ? (num_kb < MEGA_STAGES ? num_kb : MEGA_STAGES) : 0;
+        const int pre_max = J.b_static ? (num_kb < STAGES ? num_kb : STAGES) : 0;
         int pre = 0;
         int st = stage; uint32_t ph = phase;
         const long long t0 = clock64();
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
             issued = __shfl_sync(FULL_MASK, issued, 0);
             if (issued) {
               ++pre;
-              if (++st == MEGA_STAGES) { st = 0; ph ^= 1; }
+              if (++st == STAGES) { st = 0; ph ^= 1; }
             }
           }
           if (!issued) __nanosleep(32);
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           if (is_leader) stamp(P.trace, tile, TR_DEP);
           for (int kb = 0; kb < pre; ++kb) {
             load_a(stage, kb);
-            if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
           stage = st; phase = ph;
@@ -335,12 +341,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           if (is_leader) mbar_expect_tx(full_bar + stage, stage_bytes);
           load_a(stage, kb);
           load_b(stage, kb);
-          if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (is_leader) stamp(P.trace, tile, TR_LOADED);
       } else {
         for (int kb = kb0; kb < num_kb; ++kb)
-          if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       __syncwarp();
     }
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_bf16<CG>(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
           umma_commit<CG>(empty_bar + stage);
-          if (++stage == MEGA_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit<CG>(tmem_full + as);
         stamp(P.trace, tile, TR_MMA_DONE);
@@ -758,7 +764,11 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     const char* e = getenv("NERAF_PDL_TRIGGER");       // "early" / "late" (tuning; default late)
     P.pdl_late = (e && e[0] == 'e') ? 0 : 1;
     if (release_dependents_early) P.pdl_late = 0;      // a kernel that runs BESIDE this one is waiting to move in
+    const char* st = getenv("NERAF_MEGA_STAGES");
+    P.stages = st ? atoi(st) : (release_dependents_early ? MEGA_STAGES - 1 : MEGA_STAGES);
+    if (P.stages < 2 || P.stages > MEGA_STAGES) P.stages = MEGA_STAGES;
   }
+  const int smem_bytes = mega_smem_bytes(P.stages);
   int tile = 0, cnt = 0;
   int cnt_off[NERAF_MEGA_MAX_JOBS], nrb[NERAF_MEGA_MAX_JOBS], num_n[NERAF_MEGA_MAX_JOBS];
   for (int i = 0; i < n_jobs; ++i) {
@@ -858,7 +868,7 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   if (max_ctas >= 2 && max_ctas / 2 < units) units = max_ctas / 2;   // leave SMs to a concurrent kernel (collectives)
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(MEGA_THREADS);
-  cfg.dynamicSmemBytes = MEGA_SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
