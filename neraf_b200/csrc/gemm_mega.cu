@@ -768,7 +768,11 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     P.stages = st ? atoi(st) : (release_dependents_early ? MEGA_STAGES - 1 : MEGA_STAGES);
     if (P.stages < 2 || P.stages > MEGA_STAGES) P.stages = MEGA_STAGES;
   }
-  const int smem_bytes = mega_smem_bytes(P.stages);
+  // A shorter ring alone does not make room beside this kernel: the SM's shared-memory carve-out comes in steps (..., 196,
+  // 228 KB) and is chosen to fit the resident CTA -- the 5-stage footprint lands 880 bytes under the 196 KB step, and a
+  // second CTA needs 1 KB of its own.  4 KB of padding push the request over that step: the SM is configured with 228 KB
+  // and ~28 KB stay free for the CTA of the kernel that runs beside.
+  const int smem_bytes = mega_smem_bytes(P.stages) + (P.stages < MEGA_STAGES ? 4096 : 0);
   int tile = 0, cnt = 0;
   int cnt_off[NERAF_MEGA_MAX_JOBS], nrb[NERAF_MEGA_MAX_JOBS], num_n[NERAF_MEGA_MAX_JOBS];
   for (int i = 0; i < n_jobs; ++i) {
@@ -862,6 +866,8 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   NERAF_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
+    NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
     configured[dev] = true;
   }
   int units = sm_count() / 2;
