@@ -227,7 +227,7 @@ typedef struct {
  *              that advances the counters must run this call exactly once (the kernel counts steps in `state`).
  *   signals  : every rank's NERAF_EXCHANGE_BYTES signal buffer (symmetric memory, zero before first use; may be the
  *              buffer of neraf_rank_exchange); state: dev u32[4] of this rank, zero before first use.
- *   max_ctas : 0 = one CTA per SM (256 threads, fits beside a CTA of the job-list kernel). */
+ *   max_ctas : 0 = one CTA per SM (128 threads, fits beside a CTA of the job-list kernel). */
 #define NERAF_MAX_EXCHANGE_CHUNKS 32
 typedef struct {
   int64_t offset, bytes;

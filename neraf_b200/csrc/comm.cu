@@ -4,7 +4,7 @@
 // issued by the host after the backward it is fully exposed (SCALE_r01.json: 0.63 efficiency on 8 GPUs).  The weight
 // gradients finish in backward order, so most of them can travel while the remaining GEMMs run -- if the exchange
 // (a) needs no host call between the kernels (the step stays one CUDA graph) and (b) does not take SMs away from the
-// persistent GEMM kernel.  This kernel does both: small CTAs (256 threads, <= 40 registers, no shared memory: one fits
+// persistent GEMM kernel.  This kernel does both: small CTAs (128 threads, <= 48 registers, no shared memory: one fits
 // beside a job-list CTA on every SM), launched behind the job-list kernel as a programmatic dependent that never waits
 // for it (it moves in once that grid is resident: field.cu), driven by the completion counters the job-list kernel
 // advances as it stores gradient tiles (neraf_gemm_job.notify).
@@ -28,7 +28,11 @@
 
 namespace neraf {
 
-constexpr int kCommThreads = 256;
+// 128 threads x <= 48 registers: 4 warps x 1536 registers (warp allocations are rounded up to 512) = 6144, which is what
+// is left beside a job-list CTA (10 warps x 5632 = 56320 of 65536); 256 threads x 40 registers did NOT fit -- the exchange
+// then only moved in as CTA pairs of the GEMM kernel ran out of tiles (profiles/r02j_exchange_timeline.txt)
+constexpr int kCommThreads = 128;
+constexpr int kCommUnroll = 6;                 // 16-byte load-reduce requests in flight per thread
 constexpr int kReadyOffset = 2048;             // u32 ready[NERAF_MAX_EXCHANGE_CHUNKS][NERAF_MAX_RANKS]
 constexpr int kDoneOffset = 4096;              // u32 done[NERAF_MAX_RANKS]
 static_assert(kReadyOffset + NERAF_MAX_EXCHANGE_CHUNKS * NERAF_MAX_RANKS * 4 <= kDoneOffset, "signal buffer layout");
@@ -131,7 +135,7 @@ __device__ __forceinline__ uint4 peer_sum(const CommArgs& A, unsigned long long 
   return r;
 }
 
-__global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
+__global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
   const unsigned int seq = A.state[0] + 1u;               // this step's number: what a raised flag holds
   unsigned int* my_sig_ready = reinterpret_cast<unsigned int*>(A.sig[A.rank] + kReadyOffset);
   unsigned int* my_sig_done = reinterpret_cast<unsigned int*>(A.sig[A.rank] + kDoneOffset);
@@ -209,15 +213,15 @@ __global__ void __maxnreg__(40) grad_exchange_kernel(const CommArgs A) {
     const bool f32 = ch.f32 != 0;
     if (A.mc != nullptr) {
       long long i = wtid;
-      for (; i + 3 * wthreads < n; i += 4 * wthreads) {      // four requests in flight per thread
-        uint4 v[4];
+      for (; i + (kCommUnroll - 1) * wthreads < n; i += kCommUnroll * wthreads) {
+        uint4 v[kCommUnroll];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kCommUnroll; ++u) {
           const void* p = A.mc + base + (unsigned long long)(i + u * wthreads) * 16;
           v[u] = f32 ? mm_ld_reduce_f32(p) : mm_ld_reduce_bf16(p);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mm_st(A.mc + base + (unsigned long long)(i + u * wthreads) * 16, v[u]);
+        for (int u = 0; u < kCommUnroll; ++u) mm_st(A.mc + base + (unsigned long long)(i + u * wthreads) * 16, v[u]);
       }
       for (; i < n; i += wthreads) {
         void* p = A.mc + base + (unsigned long long)i * 16;
