@@ -210,7 +210,7 @@ __device__ __forceinline__ const DeviceJob& locate_tile(const MegaParams& P, int
 
 __device__ __forceinline__ float gate_factor(float x) { return x > 0.f ? 1.f : kLeakySlope; }
 
-__global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) {
+__device__ __forceinline__ void mega_body(const MegaParams& P) {
   constexpr int CG = 2;
   // the kernel has no static shared memory, so the dynamic window starts 1024-byte aligned (checked below: the
   // 128-byte swizzle of TMA / UMMA needs it, and there is no room for an alignment slack)
@@ -747,6 +747,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid
   }
 }
 
+__global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) { mega_body(P); }
+
+// The same kernel held to 152 registers per thread, for launches that another kernel must be able to sit BESIDE (the
+// data-parallel gradient exchange).  Registers are handed out per SM sub-partition: this CTA's 10 warps land 3/3/2/2 on
+// the four partitions, and with 160+ registers per thread the two partitions that hold three warps have no room left
+// for a single warp of any other CTA -- measured (tools/micro/pdl_beside.cu): beside 320 threads x 159 registers NOTHING
+// becomes resident, beside 320 x 151 a 128-thread x 48-register CTA does.
+__global__ void __maxnreg__(152) umma_mega_kernel_slim(const __grid_constant__ MegaParams P) { mega_body(P); }
+
 }  // namespace umma
 
 int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
@@ -865,11 +874,13 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   int dev = 0;
   NERAF_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
-    NERAF_CHECK_CUDA(cudaFuncSetAttribute(umma_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
+    for (auto kern : {umma_mega_kernel, umma_mega_kernel_slim}) {
+      NERAF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
+      NERAF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     configured[dev] = true;
   }
+  auto kernel = release_dependents_early ? umma_mega_kernel_slim : umma_mega_kernel;
   int units = sm_count() / 2;
   if (max_ctas >= 2 && max_ctas / 2 < units) units = max_ctas / 2;   // leave SMs to a concurrent kernel (collectives)
   cudaLaunchConfig_t cfg = {};
@@ -896,7 +907,7 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   if (dev >= 0 && dev < 64 && resident_pairs[dev] < units) units = resident_pairs[dev];
   const int grid = (tile < units ? tile : units) * 2;
   cfg.gridDim = dim3((unsigned)grid);
-  NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_mega_kernel, P));
+  NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, P));
   NERAF_CHECK_LAUNCH("umma_mega_kernel");
   if (trace_path) {
     std::vector<unsigned long long> host((size_t)tile * TR_SLOTS);
