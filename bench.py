@@ -137,10 +137,17 @@ def run_reference(args):
         return
     shape = syn.RAF if args.shape == "RAF" else syn.SOUNDSPACES
     res = time_cpu_baseline(shape, args.batch, max(args.steps, 1), max(args.warmup, 1), budget_s=120.0)
+    cfg_ref = workload_config(shape, args)
+    cfg_ref.update({"precision": "fp32", "launch": "torch CPU eager, all host threads", "l2": "n/a (CPU)",
+                    "grad_allreduce": "none (rank 0 only)",
+                    "reference_kind": "port: /root/reference (and nerfstudio / tiny-cuda-nn, which its classes import) does not "
+                                      "exist on the GPU box, so the arm times oracle/'s restatement of NeRAF_field.py / "
+                                      "NeRAF_evaluator.py / the encodings -- pinned against the reference's own classes in the "
+                                      "build container (oracle/make_golden.py)"})
     line = {"impl": "reference", "metric": "stft_columns_per_sec_train_fwd_bwd", "value": res["value"],
             "unit": "columns/s", "n_gpus": args.gpus, "steps": res["steps"], "warmup": max(args.warmup, 1),
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(shape, args),
+            "dtype": "f32", "data": "synthetic", "config": cfg_ref,
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -150,9 +157,17 @@ def workload_config(shape, args):
     return {"workload": f"{shape.name} FurnishedRoom-shaped audio-field training step (encode + MLP 1187->5096->2048->"
                         f"1024->1024->512->{shape.C}x{shape.F} + SC/log-STFT loss + backward), B={args.batch} columns/GPU, "
                         f"T={shape.T}", "batch_per_gpu": args.batch, "C": shape.C, "F": shape.F, "T": shape.T,
-            "precision": args.precision, "launch": "eager" if getattr(args, "no_graph", False) else ("one CUDA graph per step" if args.gpus == 1 else "two CUDA graphs per step + eager NCCL all-reduces") + " (value, e2e); eager plugin calls (e2e_eager)",
+            "precision": args.precision,
+            "launch": ("eager" if getattr(args, "no_graph", False) else
+                       ("one CUDA graph per step" if (args.gpus == 1 or getattr(args, "kernel_exchange", False))
+                        else "two CUDA graphs per step + eager NCCL all-reduces")) + " (value, e2e); eager plugin calls (e2e_eager)",
             "l2": "flushed between timed steps (256 MiB write, outside the events)",
-            "grad_allreduce": f"{getattr(args, 'grad_dtype', 'fp32')} (one flat NCCL all-reduce, N > 1 only)",
+            "grad_allreduce": ("none (one GPU)" if args.gpus == 1 else
+                               ("bf16, by the library's own kernels over symmetric memory: the loss's four sums inside the loss "
+                                "kernel, the gradients by a two-shot NVLS all-reduce (multimem.ld_reduce / multimem.st) running "
+                                "beside the backward's GEMM launch -- no host-issued collective in the step"
+                                if getattr(args, "kernel_exchange", False) else
+                                f"{getattr(args, 'grad_dtype', 'fp32')} (one flat NCCL all-reduce after the backward)")),
             "optimizer": "not in the timed region (metric is fwd+bwd; nerfstudio's Adam is outside the path)"}
 
 
@@ -188,6 +203,12 @@ def main():
                     help="also time the grid-feature producer (ResNet3D-50 training-mode fwd+bwd, SURVEY 8f row 1) on an "
                          "N^3 grid (the reference's grid is 128^3); 0 disables")
     ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "kernel", "nccl"],
+                    help="N > 1: gradient exchange of the graphed step (GraphedTrainStep: the library's own kernels over "
+                         "symmetric memory, or NCCL)")
+    ap.add_argument("--sweep", default="1024,4096,8192,16384,32768,65536",
+                    help="global batch sizes of the large-batch sweep (BASELINE config 5), split over the GPUs; '' disables")
+    ap.add_argument("--no-soundspaces", action="store_true", help="skip the SoundSpaces-shaped training step (BASELINE config 3)")
     ap.add_argument("--grad-dtype", default=None, choices=["fp32", "bf16"],
                     help="dtype of the gradient all-reduce for N > 1 (default: bf16 with --precision bf16, else fp32)")
     args = ap.parse_args()
@@ -251,7 +272,9 @@ def main():
         # N = 1: one graph around the autograd calls.  N > 1: two graphs (forward + loss sums | backward) with the
         # loss's 32-byte all-reduce between them issued eagerly -- no NCCL call is ever captured
         graphed = GraphedTrainStep(model, dev_batch,
-                                   grad_dtype=torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32)
+                                   grad_dtype=torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32,
+                                   exchange=args.exchange)
+        args.kernel_exchange = graphed.kernel_exchange
 
     def step_value(batch):
         if graphed is None:
@@ -296,7 +319,9 @@ def main():
     launches_per_step = lib.neraf_launch_count() - l_eager0
     if graphed is not None:          # the graph replays the kernels of its last eager warm-up step
         launches_per_step = graphed.launches_per_step
-    ms_dev, launches, wall_dev = timed(dev_batch, args.steps, read_loss=False, fn=step_value)
+    # `value`: inputs resident in HBM when the timed region starts -- the graphed step reads its static buffers in place
+    ms_dev, launches, wall_dev = timed(graphed.static if graphed is not None else dev_batch, args.steps, read_loss=False,
+                                       fn=step_value)
     if graphed is not None:
         launches = launches_per_step * args.steps
     ms_e2e_eager, _, wall_e2e = timed(host_batch, args.steps, read_loss=True)
@@ -418,6 +443,92 @@ def main():
         line["large_batch"] = {"batch_per_gpu": BL, "value": BL / (ms_b * 1e-3), "unit": "columns/s", "ms_per_step": ms_b,
                                "roofline_frac": ach / peaks["bf16_tflops_sustained"], "achieved_tflops": ach, "steps": 20}
         del g_big, big
+
+    def time_graphed(shape_x, model_x, b, steps_x, seed):
+        """ms per step (max over ranks) of the graphed training step at b columns per GPU: inputs resident in the step's
+        static buffers, L2 flushed between steps, CUDA events per step."""
+        bt = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape_x, b, seed=seed + rank).items()}
+        g = GraphedTrainStep(model_x, bt, exchange=args.exchange)
+
+        def fn(_):
+            g(g.static)
+            g.allreduce_grads()
+        for _ in range(3):
+            fn(None)
+        ms_x, _, _ = timed(None, steps_x, read_loss=False, fn=fn)
+        tot = max_over_ranks(sum(ms_x))
+        kx = g.kernel_exchange
+        del g, bt
+        return tot / steps_x, kx
+
+    # ---- BASELINE config 5: the large-batch sweep, GLOBAL batch split over the GPUs (strong scaling per point)
+    if graphed is not None and args.sweep:
+        rows = []
+        for gb in [int(x) for x in args.sweep.split(",") if x]:
+            b = gb // world
+            if b < 128:
+                continue
+            ms_b, kx = time_graphed(shape, model, b, 20, seed=31)
+            ach = FLOP_PER_COLUMN_TRAIN[shape.C] * b / (ms_b * 1e-3) / 1e12
+            rows.append({"global_batch": gb, "batch_per_gpu": b, "ms_per_step": ms_b, "value": b * world / (ms_b * 1e-3),
+                         "unit": "columns/s", "roofline_frac_per_gpu": ach / peaks["bf16_tflops_sustained"]})
+        line["batch_sweep"] = {"scaling": "strong (global batch / n_gpus columns per GPU)", "steps": 20, "points": rows,
+                               "note": "same graphed step as `value`; inputs resident in the static buffers"}
+
+    # ---- BASELINE config 3: SoundSpaces-shaped (binaural, orientation-conditioned) training step, data parallel over N
+    if graphed is not None and not args.no_soundspaces and shape.name != "SoundSpaces":
+        sx = syn.SOUNDSPACES
+        cfg_x = NeRAFAudioModelConfig(dataset=sx.name, max_len=sx.T, fs=sx.fs, N_freq_stft=sx.F, hop_len=sx.hop,
+                                      win_len=sx.win, precision=args.precision)
+        model_x = NeRAFAudioModel(cfg_x, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)),
+                                  process_group=group)
+        model_x.field.load_state_dict(syn.make_state_dict(sx, seed=0))
+        model_x = model_x.to(dev)
+        model_x.field.always_repack = True
+        ms_x, kx = time_graphed(sx, model_x, B, 50, seed=41)
+        ach = FLOP_PER_COLUMN_TRAIN[sx.C] * B / (ms_x * 1e-3) / 1e12
+        line["soundspaces"] = {"metric": "stft_columns_per_sec_train_fwd_bwd", "value": B * world / (ms_x * 1e-3),
+                               "unit": "columns/s", "ms_per_step": ms_x, "batch_per_gpu": B, "C": sx.C, "F": sx.F, "T": sx.T,
+                               "n_gpus": world, "scaling": "weak", "steps": 50,
+                               "roofline_frac_per_gpu": ach / peaks["bf16_tflops_sustained"],
+                               "exchange": "kernel" if kx else ("nccl" if world > 1 else "none")}
+        del model_x
+
+    # ---- N > 1: the data-parallel step must BE single-process training on the concatenated batch (SURVEY 8e: the
+    # reference refuses world_size > 1, so this equality is the specification); a mismatch fails the run
+    if world > 1 and graphed is not None:
+        Bc = 768
+        keys = ("time_query", "mic_pose", "source_pose", "rot", "data")
+        mine = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in syn.make_batch(shape, Bc, seed=910 + rank).items()}
+        whole = {}
+        for k in keys:
+            parts = [torch.empty_like(mine[k]) for _ in range(world)]
+            dist.all_gather(parts, mine[k].contiguous())
+            whole[k] = torch.cat(parts)
+        single = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)))
+        single.field.load_state_dict(syn.make_state_dict(shape, seed=0))
+        single = single.to(dev)
+        ld_s = single.get_loss_dict(single.get_outputs(whole), whole)
+        sum(ld_s.values()).backward()
+        flat = lambda m: torch.cat([p.grad.reshape(-1).float() for p in m.parameters() if p.requires_grad and p.numel() > 0])  # noqa: E731
+        ref_g = flat(single)
+        g_chk = GraphedTrainStep(model, mine, exchange=args.exchange)
+        for _ in range(3):
+            got = g_chk(mine)
+            g_chk.allreduce_grads()
+        torch.cuda.synchronize()
+        err = float((flat(model) - ref_g).norm() / ref_g.norm())
+        lerr = max(abs(float(got[k]) - float(ld_s[k])) / abs(float(ld_s[k])) for k in got)
+        tol = 4e-3 if args.precision == "bf16" else 1e-4          # bf16 exchange: 2^-9 per addend
+        err, lerr = max_over_ranks(err), max_over_ranks(lerr)
+        line["dp_equals_single"] = {"ranks": world, "columns_per_rank": Bc, "summed_gradients_rel_err": err, "losses_rel_err": lerr,
+                                    "tolerance": tol, "exchange": "kernel" if g_chk.kernel_exchange else "nccl",
+                                    "ok": bool(err < tol and lerr < 1e-5)}
+        del g_chk, single
+        if not line["dp_equals_single"]["ok"]:
+            if rank == 0:
+                sys.stderr.write(f"bench.py: data-parallel step != single-process step: {line['dp_equals_single']}\n")
+            raise SystemExit(4)
 
     # ---- Griffin-Lim: RIRs/s (second half of the BASELINE metric), rank-local poses, no collective
     if args.gl_rirs > 0:
@@ -639,7 +750,7 @@ def main():
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if args.grid_net > 0 and "error" not in line.get("grid_feature", {"error": 1}):
             from oracle import gridnet as ogn
-            n_c = min(64, args.grid_net)               # bounded sample: a 64^3 grid is 1/8 of the 128^3 work
+            n_c = args.grid_net                        # the SAME grid as the GPU figure (about half a minute of CPU work at 128^3)
             sd_c, x_c = syn.make_gridnet_state_dict("resnet50"), syn.make_grid(n_c)
             t0 = time.perf_counter()
             ogn.forward_backward(sd_c, x_c, torch.ones(1, 1024, 1, 1, 1), 1.0 / n_c, dtype=torch.float32)
@@ -647,7 +758,7 @@ def main():
             line["grid_feature"]["cpu_baseline"] = {
                 "value": 1.0 / dt, "unit": "step/s", "cores": os.cpu_count() or 1, "kind": "port", "grid": [1, 7, n_c, n_c, n_c],
                 "sample": f"one training-mode fwd+bwd of the oracle (torch {torch.__version__} CPU fp32 conv3d / batch_norm) on a "
-                          f"{n_c}^3 grid -- {(args.grid_net / n_c) ** 3:.0f}x fewer voxels than the GPU figure's grid"}
+                          f"{n_c}^3 grid (the GPU figure's grid)"}
         if args.gl_rirs > 0:
             from oracle import griffinlim as ogl
             n_cpu = 16
