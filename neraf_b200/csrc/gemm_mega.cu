@@ -38,11 +38,14 @@
 // Cross-SM visibility: TMA stores complete (bulk wait_group) -> __threadfence -> red.release(counter); consumer:
 // ld.acquire spin -> fence.proxy.async -> TMA loads.
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "mega_plan.h"
 #include "umma_common.cuh"
 
 namespace neraf {
@@ -100,6 +103,9 @@ struct MegaParams {
                                    // which is what lets a CTA of another kernel (the gradient exchange) sit beside this one
   int pdl_late;                    // programmatic dependent launch: release the next kernel when this CTA's tiles are done
                                    // (1) or as soon as the grid is resident (0)
+  const uint32_t* sched;           // explicit tile plan (mega_plan.h) or null = static stride over the tiles in job order:
+                                   // int32 offsets[sched_units + 1], then per unit its tiles (job << 20 | tile of the job)
+  int sched_units;
   DeviceJob jobs[NERAF_MEGA_MAX_JOBS];
 };
 
@@ -208,6 +214,39 @@ __device__ __forceinline__ const DeviceJob& locate_tile(const MegaParams& P, int
   return J;
 }
 
+// The tiles of one unit, in execution order: the planner's list (the next code is fetched one tile ahead) or the static
+// stride.  Every role of the CTA pair walks it on its own and sees the same sequence; `tile` is the tile's unique
+// index (slot of the plan / position in job order), used by the timeline only.
+struct TileWalk {
+  int pos, end, stride, j;
+  const uint32_t* codes;
+  uint32_t nxt;
+  __device__ __forceinline__ TileWalk(const MegaParams& P, int unit, int num_units) : j(0), nxt(0) {
+    if (P.sched != nullptr) {
+      const int32_t* off = reinterpret_cast<const int32_t*>(P.sched);
+      pos = __ldg(off + unit); end = __ldg(off + unit + 1); stride = 1;
+      codes = P.sched + (P.sched_units + 1);
+      if (pos < end) nxt = __ldg(codes + pos);
+    } else {
+      pos = unit; end = P.num_tiles; stride = num_units; codes = nullptr;
+    }
+  }
+  __device__ __forceinline__ bool next(const MegaParams& P, int& tile, const DeviceJob*& J, int& local) {
+    if (pos >= end) return false;
+    tile = pos;
+    pos += stride;
+    if (codes != nullptr) {
+      const uint32_t c = nxt;
+      if (pos < end) nxt = __ldg(codes + pos);
+      J = &P.jobs[c >> plan::kLocalBits];
+      local = (int)(c & plan::kLocalMask);
+    } else {
+      J = &locate_tile(P, tile, j, local);
+    }
+    return true;
+  }
+};
+
 __device__ __forceinline__ float gate_factor(float x) { return x > 0.f ? 1.f : kLeakySlope; }
 
 __device__ __forceinline__ void mega_body(const MegaParams& P) {
@@ -253,11 +292,12 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
     // dependency checks up to 32 counters per round trip instead of one after the other: 8 sequential L2 round trips
     // cost ~3 us in front of every weight-gradient tile) -- and a job seen complete once is never polled again.
     int stage = 0; uint32_t phase = 0;
-    int j = 0;
     uint32_t done_jobs = 0;                                      // bit i: every row block of job i is known complete
-    for (int tile = unit; tile < P.num_tiles; tile += num_units) {
-      int local;
-      const DeviceJob& J = locate_tile(P, tile, j, local);
+    TileWalk walk(P, unit, num_units);
+    int tile, local;
+    const DeviceJob* Jp;
+    while (walk.next(P, tile, Jp, local)) {
+      const DeviceJob& J = *Jp;
       const int mt = local / J.num_n, nt = local % J.num_n;          // row-block major: a row block completes early
       const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
       const int b_rows = J.bn / CG;
@@ -354,10 +394,11 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
     if (lane == 0 && is_leader) {
       int stage = 0; uint32_t phase = 0;
-      int it = 0, j = 0;
-      for (int tile = unit; tile < P.num_tiles; tile += num_units, ++it) {
-        int local;
-        const DeviceJob& J = locate_tile(P, tile, j, local);
+      TileWalk walk(P, unit, num_units);
+      int tile, local;
+      const DeviceJob* Jp;
+      for (int it = 0; walk.next(P, tile, Jp, local); ++it) {
+        const DeviceJob& J = *Jp;
         const int num_kb = (J.K + BLOCK_K - 1) / BLOCK_K;
         const bool a_mn = J.a_mn != 0, b_mn = J.b_mn != 0;
         const uint32_t idesc = make_idesc(BLOCK_M * CG, J.bn) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
@@ -397,10 +438,11 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
     float* wbuf_f = reinterpret_cast<float*>(wbuf);
     float* bias_s = bias_buf + (warp - 2) * (MEGA_BIAS_BYTES / 4);
     bool used_multicast = false;
-    int it = 0, j = 0;
-    for (int tile = unit; tile < P.num_tiles; tile += num_units, ++it) {
-      int local;
-      const DeviceJob& J = locate_tile(P, tile, j, local);
+    TileWalk walk(P, unit, num_units);
+    int tile, local;
+    const DeviceJob* Jp;
+    for (int it = 0; walk.next(P, tile, Jp, local); ++it) {
+      const DeviceJob& J = *Jp;
       const int mt = local / J.num_n, nt = local % J.num_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -761,6 +803,103 @@ __global__ void __maxnreg__(152) umma_mega_kernel_slim(const __grid_constant__ M
 int get_tensor_map_2d(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
                       CUtensorMap* out);
 
+// ---- tile plans: computed once per (job shapes, units, policy) and kept in device memory for the life of the process
+namespace {
+struct PlanEntry {
+  uint32_t* dev = nullptr;            // null: the static stride is at least as good
+  std::vector<uint32_t> codes;        // host copy (timeline)
+  double static_us = 0.0, plan_us = 0.0;
+  int policy = 0;
+};
+std::map<std::vector<int>, PlanEntry>& plan_cache() {
+  static std::map<std::vector<int>, PlanEntry> cache;
+  return cache;
+}
+}  // namespace
+
+// NERAF_MEGA_PLAN = auto (default) | static | cp | rb : cp / rb force a policy even when the model predicts no gain
+// (tests; A/B timing).  The plan table is uploaded with a synchronous copy the first time a job list is seen; a first
+// sighting inside a stream capture (no warm-up call) falls back to the static stride for that graph.
+static int attach_plan(umma::MegaParams& P, const MegaJob* jobs, int n_jobs, int units, int dev, cudaStream_t stream,
+                       bool beside, std::vector<uint32_t>* trace_codes) {
+  using namespace umma;
+  P.sched = nullptr; P.sched_units = 0;
+  const char* env = getenv("NERAF_MEGA_PLAN");
+  int mode = -1;                                       // -1 auto
+  if (env && env[0] == 's') mode = plan::STATIC_STRIDE;
+  else if (env && env[0] == 'c') mode = plan::CRITICAL_PATH;
+  else if (env && env[0] == 'r') mode = plan::ROW_BLOCK;
+  bool merged = false;
+  for (int i = 0; i < n_jobs; ++i) merged = merged || jobs[i].merge_next;
+  if (trace_codes) {                                   // static order: slot = position in job order
+    trace_codes->clear();
+    if (!merged)
+      for (int i = 0; i < n_jobs; ++i)
+        for (int t = 0; t < P.jobs[i].num_m * P.jobs[i].num_n; ++t)
+          trace_codes->push_back(((uint32_t)i << plan::kLocalBits) | (uint32_t)t);
+  }
+  if (mode == plan::STATIC_STRIDE || merged || units < 2) return NERAF_OK;
+  if (beside && mode < 0 && !getenv("NERAF_MEGA_PLAN_BESIDE")) return NERAF_OK;
+  std::vector<plan::PlanJob> pj(n_jobs);
+  std::vector<int> key;
+  key.reserve(n_jobs * 9 + 3);
+  key.push_back(dev); key.push_back(units); key.push_back(mode);
+  for (int i = 0; i < n_jobs; ++i) {
+    const DeviceJob& d = P.jobs[i];
+    plan::PlanJob& j = pj[i];
+    j.num_m = d.num_m; j.num_n = d.num_n; j.kb = (d.K + BLOCK_K - 1) / BLOCK_K; j.bn = d.bn;
+    j.a_mn = d.a_mn; j.b_mn = d.b_mn; j.wait_job = d.wait_job; j.wait_all = d.wait_all;
+    if (d.out_mode == 3) j.kind = d.act == NERAF_ACT_TANH10 ? plan::EPI_ROWS_TANH : plan::EPI_ROWS;
+    else if (d.gate_mask || d.gate) j.kind = plan::EPI_DGRAD;
+    else if (d.a_mn) j.kind = plan::EPI_WGRAD;
+    else j.kind = plan::EPI_ACT_BF16;
+    NERAF_REQUIRE((unsigned)(d.num_m * d.num_n) <= plan::kLocalMask, "mega_run: job %d has too many tiles for a plan", i);
+    const int rec[9] = {j.num_m, j.num_n, j.kb, j.bn, j.a_mn, j.b_mn, j.wait_job, j.wait_all, j.kind};
+    key.insert(key.end(), rec, rec + 9);
+  }
+  auto& cache = plan_cache();
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NERAF_CHECK_CUDA(cudaStreamIsCapturing(stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return NERAF_OK;      // no allocation / synchronous copy inside a capture
+    PlanEntry e;
+    e.static_us = plan::make_plan(pj.data(), n_jobs, units, plan::STATIC_STRIDE).makespan;
+    plan::Plan best;
+    if (mode >= 0) {
+      best = plan::make_plan(pj.data(), n_jobs, units, (plan::Policy)mode);
+      e.policy = mode;
+    } else {
+      best = plan::make_plan(pj.data(), n_jobs, units, plan::CRITICAL_PATH);
+      e.policy = plan::CRITICAL_PATH;
+      plan::Plan rb = plan::make_plan(pj.data(), n_jobs, units, plan::ROW_BLOCK);
+      if (rb.makespan < best.makespan) { best = std::move(rb); e.policy = plan::ROW_BLOCK; }
+    }
+    e.plan_us = best.makespan;
+    // auto: the model is good to ~10 %; a plan must promise clearly more than that noise
+    const char* thr = getenv("NERAF_MEGA_PLAN_GAIN");
+    const double need = thr ? atof(thr) : 0.05;
+    if (mode >= 0 || best.makespan < e.static_us * (1.0 - need)) {
+      std::vector<uint32_t> table((size_t)units + 1 + best.codes.size());
+      for (int x = 0; x <= units; ++x) table[x] = (uint32_t)best.unit_off[x];
+      std::copy(best.codes.begin(), best.codes.end(), table.begin() + units + 1);
+      NERAF_CHECK_CUDA(cudaMalloc(&e.dev, table.size() * sizeof(uint32_t)));
+      NERAF_CHECK_CUDA(cudaMemcpy(e.dev, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      e.codes = std::move(best.codes);
+    }
+    if (getenv("NERAF_MEGA_PLAN_VERBOSE"))
+      fprintf(stderr, "neraf mega plan: %d jobs on %d units: static %.1f us, %s %.1f us -> %s\n", n_jobs, units, e.static_us,
+              e.policy == plan::ROW_BLOCK ? "row-block" : "critical-path", e.plan_us, e.dev ? "planned" : "static stride");
+    it = cache.emplace(std::move(key), std::move(e)).first;
+  }
+  const PlanEntry& e = it->second;
+  if (e.dev) {
+    P.sched = e.dev; P.sched_units = units;
+    if (trace_codes) *trace_codes = e.codes;
+  }
+  return NERAF_OK;
+}
+
 int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_bytes, cudaStream_t stream, int max_ctas,
              bool counters_clean, bool pdl, unsigned int* notify_increment, bool release_dependents_early) {
   using namespace umma;
@@ -905,7 +1044,13 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     resident_pairs[dev] = n;
   }
   if (dev >= 0 && dev < 64 && resident_pairs[dev] < units) units = resident_pairs[dev];
-  const int grid = (tile < units ? tile : units) * 2;
+  if (tile < units) units = tile;
+  // Which unit runs which tile: the planner's explicit lists when its model predicts a gain over the static stride
+  // (mega_plan.h), else the stride.  Never beside another kernel by default: the data-parallel exchange wants the weight
+  // gradients in the order the caller listed them.
+  std::vector<uint32_t> trace_codes;
+  NERAF_TRY(attach_plan(P, jobs, n_jobs, units, dev, stream, release_dependents_early, trace_path ? &trace_codes : nullptr));
+  const int grid = units * 2;
   cfg.gridDim = dim3((unsigned)grid);
   NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, P));
   NERAF_CHECK_LAUNCH("umma_mega_kernel");
@@ -915,14 +1060,17 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
     NERAF_CHECK_CUDA(cudaMemcpy(host.data(), P.trace, trace_bytes, cudaMemcpyDeviceToHost));
     NERAF_CHECK_CUDA(cudaFree(P.trace));
     if (FILE* f = fopen(trace_path, "ab")) {
-      // record: magic, n_jobs, n_tiles, units, then per job {tile_start, M, N, K, bn, a_mn, b_mn, wait_job}, then the stamps
-      const int hdr[4] = {0x4d454741, n_jobs, tile, units};
+      // record: magic, n_jobs, n_tiles, units, then per job {tile_start, M, N, K, bn, a_mn, b_mn, wait_job}, then per
+      // stamp slot the tile it belongs to (job << 20 | tile of the job; 0xffffffff: use tile_start), then the stamps
+      const int hdr[4] = {0x4d454732, n_jobs, tile, units};
       fwrite(hdr, sizeof(int), 4, f);
       for (int i = 0; i < n_jobs; ++i) {
         const DeviceJob& d = P.jobs[i];
         const int rec[8] = {d.tile_start, d.M, d.N, d.K, d.bn, d.a_mn, d.b_mn, d.wait_job};
         fwrite(rec, sizeof(int), 8, f);
       }
+      trace_codes.resize((size_t)tile, 0xffffffffu);
+      fwrite(trace_codes.data(), sizeof(uint32_t), trace_codes.size(), f);
       fwrite(host.data(), sizeof(unsigned long long), host.size(), f);
       fclose(f);
     }

@@ -918,6 +918,7 @@ class GraphedTrainStep:
                                                       dgrid.data_ptr(), self._grid_scratch.data_ptr(), None, None, 0,
                                                       _lib.stream_ptr(dev)))
         self._grid_part = grid_part
+        self._parts = (forward_part, backward_part, grid_part)      # tools/time_dp_parts.py times them one by one
         self._grid_scratch = torch.zeros(2 * max(n_grid, 1) + 4, dtype=torch.float32, device=dev)   # fp64 sums of dg + ticket
 
         if model.criterion_name == "MSE":

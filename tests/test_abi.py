@@ -152,6 +152,14 @@ def test_product_package_does_not_import_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
 
 
+def test_tile_planner_produces_valid_schedules(built):
+    """csrc/mega_plan.h on the CPU: every plan holds every tile once, can be executed in list order by spinning units
+    whatever the timing (no deadlock), and beats the static stride on the field's large-batch backward."""
+    out = subprocess.run([os.path.join(ROOT, "build", "mega_plan_check")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all plans valid" in out.stdout
+
+
 def test_griffinlim_core_on_host_matches_torchaudio_golden(built, golden_dir):
     """Drives neraf_b200/csrc/gl_core.h (the code the GPU kernel executes) lane by lane on the CPU."""
     exe = os.path.join(ROOT, "build", "gl_host_check")
