@@ -54,6 +54,22 @@ int sm_count();
 
 constexpr float kLeakySlope = 0.1f;
 
+// e^x for the spectral loss (two per element in every K2 kernel).  libdevice's expf spends ~8 instructions per call,
+// three of them on the half-rate integer pipe (scaling by 2^j): with two calls per element the loss kernels were
+// INSTRUCTION-bound at 0.73 of the HBM roofline (profiles/r02k bench: forward 56 us for 268 MB).  MUFU.EX2 scales by
+// itself, so all that is needed is the argument x log2(e) to better than fp32: t = fl(x L), r = the exact rounding
+// error of that product plus x (log2 e - L), and 2^(t + r) = 2^t (1 + r ln 2) to first order (|r| < 2^-20).  Five
+// FMA-pipe instructions + one MUFU; relative error <= 2^-22 (the MUFU's), the same 2 ulp class as expf.
+__device__ __forceinline__ float exp_fma(float x) {
+  constexpr float kL2E = 1.44269502162933349609375f;          // float(log2 e)
+  constexpr float kL2E_lo = 1.92596299112661746e-08f;         // log2 e - float(log2 e)
+  const float t = x * kL2E;
+  const float r = fmaf(x, kL2E_lo, fmaf(x, kL2E, -t));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return fmaf(e, r * 0.693147180559945309f, e);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == NERAF_ACT_LEAKY) return v > 0.f ? v : kLeakySlope * v;
   if (act == NERAF_ACT_TANH10) return 10.f * tanhf(v);

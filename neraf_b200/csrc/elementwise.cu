@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
         const float x = yy[i], t = dd[i], d = x - t;
         float g = l1 ? b * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * b * d;
         if (lg.criterion != NERAF_CRIT_MSE) {
-          const float ex = expf(x), et = expf(t);
+          const float ex = exp_fma(x), et = exp_fma(t);
           g += a * (ex - et) * ex;
         }
         dd[i] = g;

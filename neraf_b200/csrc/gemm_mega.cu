@@ -664,7 +664,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
                     const float x = wbuf_f[r * 32 + (lane ^ r)];
                     out_f32[(long long)(m_base + r) * ld_f32 + n] = x;
                     const float y = __ldg(loss_gt + (long long)(m_base + r) * ld_gt + n);
-                    const float ex = expf(x), ey = expf(y);
+                    const float ex = exp_fma(x), ey = exp_fma(y);
                     const float dm = ey - ex, ym = ey - 1e-3f, d = y - x;
                     s_num += (double)(dm * dm);
                     s_den += (double)(ym * ym);

@@ -33,7 +33,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // rounding of an 8-term fp32 sum of non-negative terms (< 5e-7 relative) is far inside the 1e-5 gate.
 struct Terms { float num, den, sq, ab; };
 __device__ __forceinline__ Terms terms(float x, float y) {
-  const float ex = expf(x), ey = expf(y);
+  const float ex = exp_fma(x), ey = exp_fma(y);
   const float dm = ey - ex;                 // (e^y - 1e-3) - (e^x - 1e-3)
   const float ym = ey - kEpsMag;
   const float d = y - x;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const float* __restr
     const float d = x - y;
     float g = l1 ? b * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * b * d;
     if (criterion != NERAF_CRIT_MSE) {
-      const float ex = expf(x), ey = expf(y);
+      const float ex = exp_fma(x), ey = exp_fma(y);
       g += a * (ex - ey) * ex;
     }
     return g;
@@ -314,7 +314,7 @@ __global__ void __maxnreg__(40) loss_head_kernel(const LossHeadArgs A) {
         const float x = yy[i], t = dd[i], d = x - t;
         float g = l1 ? b * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * b * d;
         if (A.criterion != NERAF_CRIT_MSE) {
-          const float ex = expf(x), et = expf(t);
+          const float ex = exp_fma(x), et = exp_fma(t);
           g += a * (ex - et) * ex;
         }
         const float v = g * (10.f - x * x * 0.1f);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, pass m (1 GPU): per-tile timelines of the job-list kernel at B = 2048 and B = 16384
 mkdir -p gpurun_out; rm -f gpurun_out/trace2k.bin gpurun_out/trace16k.bin
-COMMON="--steps 1 --warmup 3 --no-graph --gl-rirs 0 --no-cpu-baseline --large-batch 0 --loss-columns 0 --grid-net 0 --sweep '' --no-soundspaces"
+COMMON="--steps 1 --warmup 3 --no-graph --gl-rirs 0 --no-cpu-baseline --large-batch 0 --loss-columns 0 --grid-net 0 --sweep= --no-soundspaces"
 NERAF_MEGA_TRACE=gpurun_out/trace2k.bin timeout 300 python bench.py $COMMON > gpurun_out/trace2k.log 2>&1; echo "rc=$?"
 NERAF_MEGA_TRACE=gpurun_out/trace16k.bin timeout 300 python bench.py --batch 16384 $COMMON > gpurun_out/trace16k.log 2>&1; echo "rc=$?"
 tail -2 gpurun_out/trace16k.log | cut -c1-300
