@@ -226,7 +226,7 @@ typedef struct {
  *              notify_increment each per step as the chunk is stored (NULL: ready when the call starts).  EVERY step
  *              that advances the counters must run this call exactly once (the kernel counts steps in `state`).
  *   signals  : every rank's NERAF_EXCHANGE_BYTES signal buffer (symmetric memory, zero before first use; may be the
- *              buffer of neraf_rank_exchange); state: dev u32[4] of this rank, zero before first use.
+ *              buffer of neraf_rank_exchange); state: dev u32[NERAF_EXCHANGE_STATE_WORDS] of this rank, zero before first use.
  *   max_ctas : 0 = one CTA per SM (128 threads, fits beside a CTA of the job-list kernel). */
 #define NERAF_MAX_EXCHANGE_CHUNKS 32
 typedef struct {
@@ -235,7 +235,15 @@ typedef struct {
   uint32_t notify_count;
   uint32_t notify_increment;
   int32_t f32;
+  /* pull form only: where the sums of this chunk go, as fp32, instead of replacing the addends in the region (NULL:
+   * they stay in the region, in the chunk's element type).  row_elems == 0: element i of the chunk -> dst[i] (dst
+   * 16-byte aligned).  row_elems > 0: the chunk is a (rows, src_ld) matrix with row_elems valid columns (src_ld a
+   * multiple of 8 bf16 / 4 fp32 elements): element (r, c) -> dst[r * dst_ld + c]. */
+  float* dst;
+  int64_t dst_ld;
+  int32_t row_elems, src_ld;
 } neraf_exchange_chunk;
+#define NERAF_EXCHANGE_STATE_WORDS 64
 typedef struct {
   int32_t world, rank, n_chunks, max_ctas;
   neraf_exchange_chunk chunks[NERAF_MAX_EXCHANGE_CHUNKS];
@@ -243,6 +251,10 @@ typedef struct {
   void* peers[NERAF_MAX_RANKS];
   void* signals[NERAF_MAX_RANKS];
   uint32_t* state;
+  int32_t pull;        /* 0: push form (multimem.st / peer stores of the sums into every rank's region).  1: pull form:
+                          a rank stores the sums of its slice into its own region only and every rank fetches the other
+                          ranks' slices with peer loads, delivering them to chunk.dst as fp32 when that is set -- the
+                          exchange then ends with the gradients in the optimizer's buffers, no widening pass follows */
   uint64_t* trace;     /* optional dev u64[4 + 4 * n_chunks], %globaltimer stamps of the last call: [0] start, [1] this rank's
                           workers done, [2] every rank done; per chunk c at [4 + 4 c]: announced by this rank, announced
                           by every rank (seen by worker block 1), issued by worker block 1 */

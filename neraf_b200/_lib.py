@@ -21,6 +21,7 @@ CRIT_SC_SLMSE, CRIT_SC_SLL1, CRIT_MSE = 0, 1, 2
 ORDER_TIME_MIC_SRC_ROT, ORDER_MIC_SRC_TIME_ROT = 0, 1
 MAX_TRUNK = 8
 MAX_RANKS, EXCHANGE_BYTES, MAX_EXCHANGE_CHUNKS, NOTIFY_COUNTERS = 16, 8192, 32, 1024
+EXCHANGE_STATE_WORDS = 64
 
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 CRITERIA = {"SC+SLMSE": CRIT_SC_SLMSE, "SC+SLL1": CRIT_SC_SLL1, "MSE": CRIT_MSE}
@@ -74,14 +75,15 @@ class LossGrad(C.Structure):        # neraf_loss_grad
 
 class ExchangeChunk(C.Structure):   # neraf_exchange_chunk
     _fields_ = [("offset", C.c_int64), ("bytes", C.c_int64), ("notify", C.c_void_p), ("notify_count", C.c_uint32),
-                ("notify_increment", C.c_uint32), ("f32", C.c_int32)]
+                ("notify_increment", C.c_uint32), ("f32", C.c_int32), ("dst", C.c_void_p), ("dst_ld", C.c_int64),
+                ("row_elems", C.c_int32), ("src_ld", C.c_int32)]
 
 
 class GradExchange(C.Structure):    # neraf_grad_exchange
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_chunks", C.c_int32), ("max_ctas", C.c_int32),
                 ("chunks", ExchangeChunk * MAX_EXCHANGE_CHUNKS), ("multicast", C.c_void_p),
                 ("peers", C.c_void_p * MAX_RANKS), ("signals", C.c_void_p * MAX_RANKS), ("state", C.c_void_p),
-                ("trace", C.c_void_p)]
+                ("pull", C.c_int32), ("trace", C.c_void_p)]
 
 
 class DpOptions(C.Structure):

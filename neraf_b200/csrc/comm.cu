@@ -18,6 +18,14 @@
 //                                   slice of the chunk: multimem.ld_reduce (the switch adds the ranks' copies, fp32
 //                                   accumulation) -> multimem.st of the sum into every rank's copy (NVLS).  Without a
 //                                   multicast mapping the same is done with plain peer loads and stores.
+//   Pull mode (neraf_grad_exchange.pull; what the graphed data-parallel step uses): the second shot is turned around.
+//   A worker stores the sums of its slice into its OWN copy only; the last worker of the rank to finish the slice
+//   raises reduced[c][rank] everywhere; then every rank PULLS the other ranks' slices with plain peer loads and writes
+//   them where the optimizer wants them: as fp32 into the parameter's .grad (chunk.dst; a compact row-strided block is
+//   scattered into its columns of the layer-1 gradient).  Same bytes on the wire, one more flag hop per chunk (hidden
+//   beside the backward for all but the last chunk) -- and the separate widening pass over all gradients that followed
+//   the push form (28.7 MB read + 57.4 MB written after the exchange: 20 of the 34 us of the kernel behind the
+//   backward, profiles/r02l_dp_parts_1rank.txt) is gone.
 //   end: workers fence (system scope) and draw a ticket; the herald waits for all tickets, raises done[rank] everywhere
 //   and waits for every rank's done flag: when the kernel ends, every rank holds the sums of every chunk.
 // Flags carry the step number (kept in `state`, advanced by the herald), so nothing is ever reset and a flag that is
@@ -33,19 +41,31 @@ namespace neraf {
 // then only moved in as CTA pairs of the GEMM kernel ran out of tiles (profiles/r02j_exchange_timeline.txt)
 constexpr int kCommThreads = 128;
 constexpr int kCommUnroll = 6;                 // 16-byte load-reduce requests in flight per thread
+// Pull form, second shot: peer loads land in SHARED memory (cp.async, 16 bytes each, thread-private slots), which costs
+// no registers -- the 48-register budget caps register-held loads at 6 per thread, i.e. 1.8 MB in flight per GPU, and at
+// NVLink's ~3 us round trip that is what bounded the exchange (20.9 MB in 53 us, profiles/r02j_time_dp8.txt).  Two
+// groups of kPullDepth slots per thread: one group lands while the other is converted and stored.  24 KB per CTA is
+// what is left beside a 5-stage CTA of the job-list kernel (gemm_mega.cu: 228 KB carve-out - 199 KB - 4 KB padding).
+constexpr int kPullDepth = 6;
+constexpr int kPullSmemBytes = 2 * kPullDepth * kCommThreads * 16;
 constexpr int kReadyOffset = 2048;             // u32 ready[NERAF_MAX_EXCHANGE_CHUNKS][NERAF_MAX_RANKS]
 constexpr int kDoneOffset = 4096;              // u32 done[NERAF_MAX_RANKS]
+constexpr int kReducedOffset = 4608;           // u32 reduced[NERAF_MAX_EXCHANGE_CHUNKS][NERAF_MAX_RANKS]  (pull mode)
+constexpr int kChunkTickets = 2;               // state[2 + c]: workers of this rank that have reduced their part of chunk c
 static_assert(kReadyOffset + NERAF_MAX_EXCHANGE_CHUNKS * NERAF_MAX_RANKS * 4 <= kDoneOffset, "signal buffer layout");
-static_assert(kDoneOffset + NERAF_MAX_RANKS * 4 <= NERAF_EXCHANGE_BYTES, "signal buffer layout");
+static_assert(kDoneOffset + NERAF_MAX_RANKS * 4 <= kReducedOffset, "signal buffer layout");
+static_assert(kReducedOffset + NERAF_MAX_EXCHANGE_CHUNKS * NERAF_MAX_RANKS * 4 <= NERAF_EXCHANGE_BYTES, "signal buffer layout");
+static_assert(kChunkTickets + NERAF_MAX_EXCHANGE_CHUNKS <= NERAF_EXCHANGE_STATE_WORDS, "state layout");
 constexpr long long kCommSpinLimit = 4000000000LL;      // ~2 s: a lost peer traps instead of hanging the GPU
 
 struct CommChunk {
   unsigned long long offset, bytes;            // of the exchange region; multiples of 16
   const unsigned int* notify; unsigned int count, increment;
   int f32;
+  float* dst; long long dst_ld; int row_elems, src_ld;      // pull mode: where the sums go as fp32 (null: stay in the region)
 };
 struct CommArgs {
-  int n_chunks, world, rank;
+  int n_chunks, world, rank, pull;
   CommChunk ch[NERAF_MAX_EXCHANGE_CHUNKS];
   uint8_t* mc;                                 // multicast alias of the region (nullptr: peer loads / stores)
   uint8_t* peers[NERAF_MAX_RANKS];
@@ -135,6 +155,44 @@ __device__ __forceinline__ uint4 peer_sum(const CommArgs& A, unsigned long long 
   return r;
 }
 
+__device__ __forceinline__ void st_local(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The 16-byte granule `g` of a chunk (8 bf16 or 4 fp32 sums) -> the chunk's fp32 destination.  Contiguous: element i of
+// the chunk is dst[i].  Row-strided (row_elems > 0): the chunk is a (rows, src_ld) matrix of which row_elems columns are
+// valid; element (r, c) goes to dst[r * dst_ld + c] (rows of the destination need not be 16-byte aligned).
+__device__ __forceinline__ void deliver(const CommChunk& ch, unsigned int g, const uint4& v) {
+  const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+  if (ch.f32) {
+    if (ch.row_elems <= 0) {
+      __stcs(reinterpret_cast<float4*>(ch.dst) + g, make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3])));
+    } else {
+      const unsigned int e0 = g * 4u, r = e0 / (unsigned int)ch.src_ld; const int c0 = (int)(e0 - r * (unsigned int)ch.src_ld);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (c0 + i < ch.row_elems) ch.dst[(long long)r * ch.dst_ld + c0 + i] = __uint_as_float(w[i]);
+    }
+    return;
+  }
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  if (ch.row_elems <= 0) {
+    float4* d = reinterpret_cast<float4*>(ch.dst) + 2 * g;
+    __stcs(d, make_float4(f[0], f[1], f[2], f[3]));
+    __stcs(d + 1, make_float4(f[4], f[5], f[6], f[7]));
+  } else {
+    const unsigned int e0 = g * 8u, r = e0 / (unsigned int)ch.src_ld; const int c0 = (int)(e0 - r * (unsigned int)ch.src_ld);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (c0 + i < ch.row_elems) ch.dst[(long long)r * ch.dst_ld + c0 + i] = f[i];
+  }
+}
+
+template <bool kPull>
 __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
   const unsigned int seq = A.state[0] + 1u;               // this step's number: what a raised flag holds
   unsigned int* my_sig_ready = reinterpret_cast<unsigned int*>(A.sig[A.rank] + kReadyOffset);
@@ -205,34 +263,101 @@ __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
     }
     __syncthreads();
     if (blockIdx.x == 1 && threadIdx.x == 0) comm_stamp(A.trace, 4 + 4 * c + 1);     // every rank announced chunk c
-    // this rank's slice of the chunk, in 16-byte granules
-    const long long granules = (long long)(ch.bytes / 16);
-    const long long g0 = granules * A.rank / A.world, g1 = granules * (A.rank + 1) / A.world;
-    const unsigned long long base = ch.offset + (unsigned long long)g0 * 16;
-    const long long n = g1 - g0;
+    // this rank's slice of the chunk, in 16-byte granules (equal slices: the owner of a granule is g / per); 32-bit
+    // indices throughout (a chunk is < 64 GB) -- the kernel lives on 48 registers
+    const unsigned int granules = (unsigned int)(ch.bytes / 16);
+    const unsigned int per = (granules + A.world - 1) / A.world;
+    const unsigned int g0 = per * A.rank < granules ? per * A.rank : granules;
+    const unsigned int g1 = g0 + per < granules ? g0 + per : granules;
+    const unsigned int n = g1 - g0;
     const bool f32 = ch.f32 != 0;
-    if (A.mc != nullptr) {
-      long long i = wtid;
-      for (; i + (kCommUnroll - 1) * wthreads < n; i += kCommUnroll * wthreads) {
+    constexpr bool pull = kPull;
+    const unsigned int wt = (unsigned int)wtid, wn = (unsigned int)wthreads;
+    uint8_t* mine = A.peers[A.rank] + ch.offset;
+    auto reduce16 = [&](unsigned int g) -> uint4 {
+      const unsigned long long off = ch.offset + (unsigned long long)g * 16;
+      if (A.mc != nullptr) return f32 ? mm_ld_reduce_f32(A.mc + off) : mm_ld_reduce_bf16(A.mc + off);
+      return peer_sum(A, off, f32);
+    };
+    auto publish = [&](unsigned int g, const uint4& v) {              // the sum of granule g of the chunk
+      if (!pull) {
+        const unsigned long long off = ch.offset + (unsigned long long)g * 16;
+        if (A.mc != nullptr) mm_st(A.mc + off, v);
+        else for (int q = 0; q < A.world; ++q) st_peer(A.peers[q] + off, v);
+      } else {
+        st_local(mine + (unsigned long long)g * 16, v);               // the other ranks fetch it from here
+        if (ch.dst != nullptr) deliver(ch, g, v);
+      }
+    };
+    {
+      unsigned int i = wt;
+      for (; i + (kCommUnroll - 1) * wn < n; i += kCommUnroll * wn) {
         uint4 v[kCommUnroll];
 #pragma unroll
-        for (int u = 0; u < kCommUnroll; ++u) {
-          const void* p = A.mc + base + (unsigned long long)(i + u * wthreads) * 16;
-          v[u] = f32 ? mm_ld_reduce_f32(p) : mm_ld_reduce_bf16(p);
-        }
+        for (int u = 0; u < kCommUnroll; ++u) v[u] = reduce16(g0 + i + u * wn);
 #pragma unroll
-        for (int u = 0; u < kCommUnroll; ++u) mm_st(A.mc + base + (unsigned long long)(i + u * wthreads) * 16, v[u]);
+        for (int u = 0; u < kCommUnroll; ++u) publish(g0 + i + u * wn, v[u]);
       }
-      for (; i < n; i += wthreads) {
-        void* p = A.mc + base + (unsigned long long)i * 16;
-        const uint4 v = f32 ? mm_ld_reduce_f32(p) : mm_ld_reduce_bf16(p);
-        mm_st(p, v);
+      for (; i < n; i += wn) publish(g0 + i, reduce16(g0 + i));
+    }
+    if (pull && A.world > 1) {
+      // ---- second shot, turned around: announce this rank's reduced slice, then fetch the other ranks' slices
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(A.state + kChunkTickets + c, 1u);
+        if (t == (unsigned int)workers - 1) {                         // every worker's part of the slice is stored
+          A.state[kChunkTickets + c] = 0u;
+          __threadfence_system();
+          for (int q = 0; q < A.world; ++q)
+            comm_st_relaxed_sys(reinterpret_cast<unsigned int*>(A.sig[q] + kReducedOffset) + c * NERAF_MAX_RANKS + A.rank, seq);
+        }
       }
-    } else {
-      for (long long i = wtid; i < n; i += wthreads) {
-        const unsigned long long off = base + (unsigned long long)i * 16;
-        const uint4 v = peer_sum(A, off, f32);
-        for (int q = 0; q < A.world; ++q) st_peer(A.peers[q] + off, v);
+      if (threadIdx.x < A.world && threadIdx.x != A.rank) {
+        const unsigned int* flag = reinterpret_cast<const unsigned int*>(A.sig[A.rank] + kReducedOffset) + c * NERAF_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while (!reached(comm_ld_acquire_sys(flag), seq)) {
+          __nanosleep(100);
+          if (clock64() - t0 > kCommSpinLimit) __trap();
+        }
+      }
+      __syncthreads();
+      const unsigned int others = granules - n;
+      auto granule_of = [&](unsigned int j) { return j < g0 ? j : j + n; };     // j-th granule that is not this rank's
+      auto keep = [&](unsigned int g, const uint4& v) {
+        if (ch.dst != nullptr) deliver(ch, g, v);
+        else st_local(mine + (unsigned long long)g * 16, v);
+      };
+      // thread-private slots: group h, slot u of thread t at ((h * kPullDepth + u) * kCommThreads + t) * 16
+      extern __shared__ __align__(16) uint8_t pull_smem[];
+      uint4* slots = reinterpret_cast<uint4*>(pull_smem) + threadIdx.x;
+      auto issue = [&](int h, unsigned int j0) {                      // group h <- granules j0, j0 + wn, ... (those that exist)
+#pragma unroll
+        for (int u = 0; u < kPullDepth; ++u) {
+          const unsigned int j = j0 + u * wn;
+          if (j < others) {
+            const unsigned int g = granule_of(j);
+            cp_async16(slots + (h * kPullDepth + u) * kCommThreads, A.peers[g / per] + ch.offset + (unsigned long long)g * 16);
+          }
+        }
+        cp_async_commit();
+      };
+      auto drain = [&](int h, unsigned int j0) {
+#pragma unroll
+        for (int u = 0; u < kPullDepth; ++u) {
+          const unsigned int j = j0 + u * wn;
+          if (j < others) keep(granule_of(j), slots[(h * kPullDepth + u) * kCommThreads]);
+        }
+      };
+      const unsigned int step = kPullDepth * wn;
+      unsigned int j = wt;
+      int h = 0;
+      if (j < others) issue(0, j);
+      for (; j < others; j += step, h ^= 1) {
+        const bool more = j + step < others;
+        if (more) issue(h ^ 1, j + step);                             // the next group is in flight while this one drains
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        drain(h, j);
       }
     }
     if (blockIdx.x == 1 && threadIdx.x == 0) comm_stamp(A.trace, 4 + 4 * c + 2);     // block 1 has issued its share of chunk c
@@ -255,7 +380,7 @@ int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool be
                 NERAF_MAX_EXCHANGE_CHUNKS);
   NERAF_REQUIRE(x->state, "dp_exchange_grads: state is null");
   CommArgs A = {};
-  A.n_chunks = x->n_chunks; A.world = x->world; A.rank = x->rank;
+  A.n_chunks = x->n_chunks; A.world = x->world; A.rank = x->rank; A.pull = x->pull ? 1 : 0;
   A.mc = reinterpret_cast<uint8_t*>(x->multicast);
   A.state = x->state;
   A.trace = reinterpret_cast<unsigned long long*>(x->trace);
@@ -271,8 +396,12 @@ int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool be
     NERAF_REQUIRE(s.offset % 16 == 0 && s.bytes % 16 == 0, "dp_exchange_grads: chunk %d is not 16-byte tileable", c);
     NERAF_REQUIRE(!s.notify || (s.notify_increment > 0 && s.notify_count > 0),
                   "dp_exchange_grads: chunk %d: notify without a counter count / increment", c);
+    NERAF_REQUIRE(!s.dst || x->pull, "dp_exchange_grads: chunk %d: a destination needs the pull form", c);
+    NERAF_REQUIRE(!s.dst || s.row_elems > 0 || ((uintptr_t)s.dst & 15) == 0, "dp_exchange_grads: chunk %d: misaligned destination", c);
+    NERAF_REQUIRE(!s.dst || s.row_elems <= 0 || (s.src_ld >= s.row_elems && s.src_ld % (s.f32 ? 4 : 8) == 0 && s.dst_ld >= s.row_elems),
+                  "dp_exchange_grads: chunk %d: bad row-strided destination", c);
     A.ch[c] = CommChunk{(unsigned long long)s.offset, (unsigned long long)s.bytes, s.notify, s.notify_count, s.notify_increment,
-                        s.f32 ? 1 : 0};
+                        s.f32 ? 1 : 0, s.dst, (long long)s.dst_ld, s.dst ? s.row_elems : 0, s.src_ld};
   }
   // one small CTA per SM (it must fit BESIDE a CTA of the job-list kernel), never more than are resident at once
   int grid = x->max_ctas > 0 ? x->max_ctas : sm_count();
@@ -280,11 +409,13 @@ int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool be
   if (grid < 2) grid = 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kCommThreads); cfg.stream = stream;
+  cfg.dynamicSmemBytes = (A.pull && A.world > 1) ? kPullSmemBytes : 0;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = beside_previous ? 1 : 0;
-  NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grad_exchange_kernel, A));
+  if (A.pull) NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grad_exchange_kernel<true>, A));
+  else NERAF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grad_exchange_kernel<false>, A));
   NERAF_CHECK_LAUNCH("grad_exchange_kernel");
   return NERAF_OK;
 }

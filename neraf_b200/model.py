@@ -811,36 +811,58 @@ class GraphedTrainStep:
             # over NVLink (~10 us) whatever its size, and the workers take the chunks one after the other.
             target_bytes = int(os.environ.get("NERAF_EXCHANGE_CHUNK_MB", "64")) << 20
 
-            def matrix_chunks(slot, offset, n_rows, row_bytes):
-                """Row-block groups of one gradient matrix, each ~target_bytes: they travel while the rest is computed."""
+            # Push form (default): multimem.st of the bf16 sums into every rank's region, then one widening launch.
+            # NERAF_EXCHANGE_PULL=1: the pull form -- a rank reduces its slice in place and every rank fetches the other
+            # slices (peer loads through shared memory) straight into the fp32 .grad buffers, no widening pass.  Correct
+            # (tools/check_dp_equals_single.py) but measured SLOWER at 2 GPUs (499 vs 445 us per step,
+            # profiles/r02s_time_dp2_pull.txt): every chunk pays two more system fences and a flag hop (~20 us per
+            # chunk, 7 chunks), which the 20 us saved behind the exchange do not buy back.
+            self._pull = os.environ.get("NERAF_EXCHANGE_PULL", "0") == "1"
+            flat_ptr = self.flat_grad.data_ptr()
+
+            def matrix_chunks(slot, offset, n_rows, row_bytes, dst=None, dst_ld=0, row_elems=0):
+                """Row-block groups of one gradient matrix, each ~target_bytes: they travel while the rest is computed.
+                dst: fp32 destination of the sums (pull form); default: the same elements of the flat fp32 buffer."""
                 groups = max(1, min(n_cnt[slot], (n_rows * row_bytes + target_bytes - 1) // target_bytes))
                 out, c0 = [], 0
                 for g in range(groups):
                     c1 = n_cnt[slot] * (g + 1) // groups
                     r0, r1 = c0 * 256, min(n_rows, c1 * 256)
-                    out.append((offset + r0 * row_bytes, (r1 - r0) * row_bytes, cnt_off[slot] + c0, c1 - c0, 0))
+                    off = offset + r0 * row_bytes
+                    if not self._pull:
+                        d = (0, 0, 0, 0)
+                    elif dst is None:
+                        d = (flat_ptr + off * 2, 0, 0, 0)                  # bf16 byte offset -> fp32 byte offset
+                    else:
+                        d = (dst + r0 * dst_ld * 4, dst_ld, row_elems, row_bytes // 2)
+                    out.append((off, (r1 - r0) * row_bytes, cnt_off[slot] + c0, c1 - c0, 0) + d)
                     c0 = c1
                 return out
             chunks = matrix_chunks(L, offs16[L - 1], rows[L], weights[L].shape[1] * 2)   # heads (contiguous)
             for i in range(L - 1, 0, -1):                                                # trunk layer i = red_w[i - 1]
                 chunks += matrix_chunks(i, offs16[i - 1], rows[i], weights[i].shape[1] * 2)
             # the bias gradients are final when the dgrad chain ends, the compact dW1 block is the backward's last job
-            chunks.append((self._xchg["bias_offset"], self._xchg["bias_bytes"], cnt_off[L + 1], n_cnt[L + 1], 1))
-            chunks += matrix_chunks(0, offs16[nw], rows[0], ldc * 2)                     # compact dW1 block
+            chunks.append((self._xchg["bias_offset"], self._xchg["bias_bytes"], cnt_off[L + 1], n_cnt[L + 1], 1, 0, 0, 0, 0))
+            # compact dW1 block: its sums go straight into columns [n_grid, n_grid + n_enc) of dW1
+            chunks += matrix_chunks(0, offs16[nw], rows[0], ldc * 2, dst=dws[0].data_ptr() + n_grid * 4,
+                                    dst_ld=weights[0].shape[1], row_elems=field.in_size - n_grid)
             if len(chunks) > _lib.MAX_EXCHANGE_CHUNKS:
                 raise ValueError("too many exchange chunks: raise NERAF_EXCHANGE_CHUNK_MB")
             gx.n_chunks = len(chunks)
-            for c, (off, nbytes, cnt0, cnt_n, f32) in enumerate(chunks):
+            gx.pull = 1 if self._pull else 0
+            for c, (off, nbytes, cnt0, cnt_n, f32, dst, dst_ld, row_elems, src_ld) in enumerate(chunks):
                 gx.chunks[c].offset, gx.chunks[c].bytes = off, nbytes
                 gx.chunks[c].notify = self._notify.data_ptr() + 4 * cnt0
                 gx.chunks[c].notify_count = cnt_n
                 gx.chunks[c].f32 = f32
+                gx.chunks[c].dst, gx.chunks[c].dst_ld = dst or None, dst_ld
+                gx.chunks[c].row_elems, gx.chunks[c].src_ld = row_elems, src_ld
             self._exchange_chunks = chunks
             gx.multicast = self._xchg["multicast"] or None
             for r in range(world):
                 gx.peers[r] = self._xchg["region_ptrs"][r]
                 gx.signals[r] = self._xchg["signal_ptrs"][r]
-            self._comm_state = torch.zeros(4, dtype=torch.int32, device=dev)
+            self._comm_state = torch.zeros(_lib.EXCHANGE_STATE_WORDS, dtype=torch.int32, device=dev)
             gx.state = self._comm_state.data_ptr()
             self._comm_trace = None
             if os.environ.get("NERAF_COMM_TRACE"):             # timeline of the exchange kernel (tools/time_dp_segments.py)
@@ -903,7 +925,13 @@ class GraphedTrainStep:
         def grid_part():          # after the exchange: the grid-block gradients from the REDUCED db1, dW1 block copied back
             if not defer:
                 return
-            if self.kernel_exchange:
+            if self.kernel_exchange and self._pull:
+                # the exchange delivered every weight gradient as fp32 where it belongs: what is left is the grid block of
+                # dW1 and dg, both from the reduced db1
+                _lib.check(lib.neraf_field_grid_grads(C.byref(dims), grid_p.data_ptr(), weights[0].data_ptr(),
+                                                      dbs[0].data_ptr(), None, 0, dws[0].data_ptr(), dgrid.data_ptr(),
+                                                      self._grid_scratch.data_ptr(), None, None, 0, _lib.stream_ptr(dev)))
+            elif self.kernel_exchange:
                 # one launch: the bf16 sums every rank now holds -> the fp32 .grad views (all matrices but the compact dW1
                 # block, which goes straight into dW1), and the grid block of dW1 / dg from the reduced db1
                 n_widen = n_weight_elems - n1 * ldc

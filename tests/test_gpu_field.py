@@ -344,8 +344,13 @@ def test_two_graph_data_parallel_step_equals_autograd_step():
         # on one rank the protocol runs against the local buffers -- flags, parities, completion counters and all)
         for kw, tol in ((dict(exchange="nccl"), 1e-5), (dict(exchange="nccl", overlap_allreduce=True), 1e-5),
                         (dict(exchange="nccl", grad_dtype=torch.bfloat16), 4e-3), (dict(fused_allreduce=True), 1e-5),
-                        (dict(exchange="kernel"), 4e-3), (dict(), 4e-3)):
+                        (dict(exchange="kernel"), 4e-3), (dict(), 4e-3), (dict(exchange="kernel", _pull=True), 4e-3)):
+            # default: the push form + widening launch; NERAF_EXCHANGE_PULL=1: the pull form (sums delivered as fp32 into
+            # the .grad buffers by the exchange itself)
+            kw = dict(kw)
+            os.environ["NERAF_EXCHANGE_PULL"] = "1" if kw.pop("_pull", False) else "0"
             step = GraphedTrainStep(model, batch, **kw)
+            os.environ.pop("NERAF_EXCHANGE_PULL")
             assert step.kernel_exchange == (kw.get("exchange", "auto") != "nccl" and not kw.get("fused_allreduce"))
             for _ in range(3):
                 got = step(batch)
