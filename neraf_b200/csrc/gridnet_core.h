@@ -271,30 +271,27 @@ GN_HD void maxpool_backward_element(const Window& w, const T* dy, const T* dy2, 
   int c, iw, ih, id;
   split_index(idx, w.C, &v, &c);
   split_voxel(v, w.in_h, w.in_w, &id, &ih, &iw);
+  // the windows that contain this voxel: o in [ceil((i + pad - k + 1) / s), floor((i + pad) / s)] per axis (at most
+  // ceil(k / s)^3 of them: 8 for the 3/2 pooling), walked from the highest o down -- the order in which the plain k^3
+  // loop with its stride test meets them, so the sum is bit-identical to that form, at 8 instead of 27 iterations and
+  // without a division per iteration (the kernel was 540 us of a 7 ms producer step)
   float acc = 0.f;
-  for (int kd = 0; kd < w.k; ++kd) {
-    const int td = id + w.pad - kd;
-    if (td < 0 || td % w.stride) continue;
-    const int od = td / w.stride;
-    if (od >= w.out_d) continue;
-    for (int kh = 0; kh < w.k; ++kh) {
-      const int th = ih + w.pad - kh;
-      if (th < 0 || th % w.stride) continue;
-      const int oh = th / w.stride;
-      if (oh >= w.out_h) continue;
-      for (int kw = 0; kw < w.k; ++kw) {
-        const int tw = iw + w.pad - kw;
-        if (tw < 0 || tw % w.stride) continue;
-        const int ow = tw / w.stride;
-        if (ow >= w.out_w) continue;
+  const int s_ = w.stride;
+  const int td = id + w.pad - w.k + 1, th = ih + w.pad - w.k + 1, tw = iw + w.pad - w.k + 1;
+  const int od0 = td <= 0 ? 0 : (td + s_ - 1) / s_, oh0 = th <= 0 ? 0 : (th + s_ - 1) / s_, ow0 = tw <= 0 ? 0 : (tw + s_ - 1) / s_;
+  int od1 = (id + w.pad) / s_, oh1 = (ih + w.pad) / s_, ow1 = (iw + w.pad) / s_;
+  if (od1 > w.out_d - 1) od1 = w.out_d - 1;
+  if (oh1 > w.out_h - 1) oh1 = w.out_h - 1;
+  if (ow1 > w.out_w - 1) ow1 = w.out_w - 1;
+  for (int od = od1; od >= od0; --od)
+    for (int oh = oh1; oh >= oh0; --oh)
+      for (int ow = ow1; ow >= ow0; --ow) {
         const long long vout = ((long long)od * w.out_h + oh) * w.out_w + ow;
         if (argmax[vout * w.C + c] == (int32_t)v) {
           acc += to_float(dy[vout * ld_dy + c]);
           if (dy2) acc += to_float(dy2[vout * ld_dy + c]);
         }
       }
-    }
-  }
   from_float(acc, dx + v * ld_dx + c);
 }
 

@@ -376,3 +376,57 @@ def test_empty_batch(prec):
     assert y.shape == (0, shape.C, shape.F)
     h = field(torch.zeros(0, 1187, device=dev))
     assert h.shape == (0, shape.C, shape.F)
+
+
+def test_autocast_gradscaler_step_and_non_finite_skip():
+    """The reference trains under fp16 autocast with a GradScaler (NeRAF_config.py:79, nerfstudio's Trainer:
+    ``scaler.scale(loss).backward(); scaler.step(opt); scaler.update()``).  The plugin's autograd nodes must (1) carry the
+    scale through -- unscaled gradients equal the gradients of the unscaled loss --, and (2) propagate a non-finite
+    loss to non-finite gradients, so that the scaler SKIPS the optimizer step and backs its scale off."""
+    from neraf_b200.model import ConstantGridFeature, NeRAFAudioModel, NeRAFAudioModelConfig
+    dev = cuda()
+    shape, B = syn.RAF, 256
+    cfg = NeRAFAudioModelConfig(dataset="RAF", precision="bf16")
+    model = NeRAFAudioModel(cfg, syn.default_aabb(), resnet3d=ConstantGridFeature(1024, syn.make_grid_feature(0)))
+    model.field.load_state_dict(syn.make_state_dict(shape, seed=0))
+    model = model.to(dev)
+    params = [p for p in model.parameters() if p.requires_grad and p.numel() > 0]
+    batch = syn.make_batch(shape, B, seed=5)
+
+    def step(b, scaler, opt):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = model.get_outputs(b)
+            loss = sum(model.get_loss_dict(out, b, {}).values())
+        scaler.scale(loss).backward()
+        return loss
+
+    # (1) the scale is carried through both nodes
+    opt = torch.optim.SGD(params, lr=0.0)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    loss = step(batch, scaler, opt)
+    assert loss.dtype == torch.float32 and torch.isfinite(loss)
+    scaled = [p.grad.clone() for p in params]
+    opt.zero_grad(set_to_none=True)
+    out = model.get_outputs(batch)
+    sum(model.get_loss_dict(out, batch, {}).values()).backward()
+    for s, p in zip(scaled, params):
+        assert rel_fro(s / 1024.0, p.grad) < 1e-3          # bias gradients: atomics order; bf16 dz rounding at another scale
+    # (2) a NaN target -> NaN loss -> non-finite gradients -> the step is skipped and the scale halves
+    opt = torch.optim.SGD(params, lr=1.0)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    bad = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    bad["data"][3, 0, 7] = float("nan")
+    before = [p.detach().clone() for p in params]
+    loss = step(bad, scaler, opt)
+    assert not torch.isfinite(loss)
+    assert any(not torch.isfinite(p.grad).all() for p in params)
+    scaler.step(opt)
+    scaler.update()
+    assert all(torch.equal(b, p.detach()) for b, p in zip(before, params)), "the optimizer step must have been skipped"
+    assert scaler.get_scale() == 512.0
+    # ... and the next finite batch trains again
+    loss = step(batch, scaler, opt)
+    scaler.step(opt)
+    scaler.update()
+    assert torch.isfinite(loss) and not torch.equal(before[0], params[0].detach())
