@@ -168,7 +168,12 @@ def workload_config(shape, args):
                                 "beside the backward's GEMM launch -- no host-issued collective in the step"
                                 if getattr(args, "kernel_exchange", False) else
                                 f"{getattr(args, 'grad_dtype', 'fp32')} (one flat NCCL all-reduce after the backward)")),
-            "optimizer": "not in the timed region (metric is fwd+bwd; nerfstudio's Adam is outside the path)"}
+            "optimizer": "not in the timed region (metric is fwd+bwd; nerfstudio's Adam is outside the path)",
+            "grid_feature": "the batch-invariant 1024-vector is a learnable constant in `value` / `e2e` (its gradient dg is "
+                            "computed); the ResNet3D-50 that produces it in the reference is timed in grid_feature.* and, inside "
+                            "the train step, in step_with_producer",
+            "tiles": "job-list kernel: static stride at this batch; explicit tile plans (csrc/mega_plan.h) where the planner's "
+                     "model predicts >= 5 % (large_batch, batch_sweep)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -729,6 +734,17 @@ def main():
                     line["grid_feature"]["graphed"] = {"error": got.get("graph_error") or (child.stderr or "no output")[-300:]}
             except Exception as exc:                               # noqa: BLE001
                 line["grid_feature"]["graphed"] = {"error": f"{type(exc).__name__}: {exc}"}
+            # ... and the audio train step AS THE REFERENCE RUNS IT: producer forward -> field step -> producer backward in
+            # one graph (NeRAF_model.py:554-566: the ResNet3D runs, and trains, in every audio step).  The headline `value`
+            # holds the grid feature constant (BASELINE's metric is the acoustic-field path); this is the step with it.
+            try:
+                child = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools",
+                                                                     "step_with_producer.py"), str(args.grid_net), str(B)],
+                                       capture_output=True, text=True, timeout=240)
+                rows = [ln for ln in child.stdout.splitlines() if ln.startswith("{")]
+                line["step_with_producer"] = json.loads(rows[-1]) if rows else {"error": (child.stderr or "no output")[-300:]}
+            except Exception as exc:                               # noqa: BLE001
+                line["step_with_producer"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.gl_rirs > 0:

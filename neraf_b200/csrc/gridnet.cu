@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(kThreads) maxpool_backward_kernel(Window w, co
                                                                     long long ld_dx, long long n) {
   GN_LOOP(n) maxpool_backward_element(w, dy, dy2, ld_dy, argmax, dx, ld_dx, idx);
 }
+__global__ void __launch_bounds__(kThreads) maxpool_backward_vec8_kernel(Window w, const bf16_t* dy, const bf16_t* dy2,
+                                                                         long long ld_dy, const int32_t* argmax,
+                                                                         bf16_t* dx, long long ld_dx, long long n) {
+  GN_LOOP(n) maxpool_backward_vec8_element(w, dy, dy2, ld_dy, argmax, dx, ld_dx, idx);
+}
 template <class T>
 __global__ void __launch_bounds__(kThreads) pack_weight_kernel(const float* wt, long long c_in, long long k3, T* out,
                                                                long long ld, long long n) {
@@ -407,6 +412,12 @@ extern "C" int neraf_grid_maxpool_backward(const neraf_window3d* wd, const void*
   NERAF_REQUIRE(dy && dx && argmax && ld_dy >= w.C && ld_dx >= w.C, "maxpool_backward: bad arguments");
   const long long n = in_voxels(w) * w.C;
   cudaStream_t s = (cudaStream_t)stream;
+  if (allow_vec8() && rows_can_vec8(dtype == NERAF_DT_BF16, w.C, ld_dy, ld_dx, 8, dy, dx, argmax, dy2, nullptr, nullptr, nullptr)) {
+    maxpool_backward_vec8_kernel<<<grid_for(n / 8), kThreads, 0, s>>>(w, (const bf16_t*)dy, (const bf16_t*)dy2, ld_dy, argmax,
+                                                                      (bf16_t*)dx, ld_dx, n / 8);
+    NERAF_CHECK_LAUNCH("maxpool_backward_vec8_kernel");
+    return NERAF_OK;
+  }
   if (dtype == NERAF_DT_F32)
     maxpool_backward_kernel<<<grid_for(n), kThreads, 0, s>>>(w, (const float*)dy, (const float*)dy2, ld_dy, argmax,
                                                              (float*)dx, ld_dx, n);

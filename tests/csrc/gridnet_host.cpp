@@ -162,6 +162,11 @@ HOST_API int gridhost_maxpool_backward(const neraf_window3d* wd, const void* dy,
                                        const int32_t* argmax, void* dx, int64_t ld_dx, void*) {
   const Window w = window_of(wd);
   const long long n = in_voxels(w) * w.C;
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, w.C, ld_dy, ld_dx, 8, dy, dx, argmax, dy2, nullptr, nullptr, nullptr)) {   // as gridnet.cu
+    for (long long i = 0; i < n / 8; ++i)
+      maxpool_backward_vec8_element(w, (const bf16_t*)dy, (const bf16_t*)dy2, ld_dy, argmax, (bf16_t*)dx, ld_dx, i);
+    return 0;
+  }
   for (long long i = 0; i < n; ++i) {
     if (dtype == NERAF_DT_F32) maxpool_backward_element(w, (const float*)dy, (const float*)dy2, ld_dy, argmax, (float*)dx, ld_dx, i);
     else maxpool_backward_element(w, (const bf16_t*)dy, (const bf16_t*)dy2, ld_dy, argmax, (bf16_t*)dx, ld_dx, i);
