@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NERAF_ABI_VERSION 8
+#define NERAF_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define NERAF_API __attribute__((visibility("default")))

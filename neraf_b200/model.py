@@ -806,10 +806,13 @@ class GraphedTrainStep:
             rows = [t.shape[0] for t in weights[:L]] + [sum(t.shape[0] for t in weights[L:]), B]
             n_cnt = [(r + 255) // 256 for r in rows]
             cnt_off = [sum(n_cnt[:k]) for k in range(L + 2)]
-            # One chunk per matrix by default.  Streaming ~3 MB row groups while the rest of a matrix is computed measured
-            # SLOWER (2 GPUs: 552 vs 525 us per step): every chunk costs a flag round trip plus a load-reduce round trip
-            # over NVLink (~10 us) whatever its size, and the workers take the chunks one after the other.
-            target_bytes = int(os.environ.get("NERAF_EXCHANGE_CHUNK_MB", "64")) << 20
+            # Row groups of ~5 MB: the largest matrix (dW of trunk layer 1, 20.9 MB = two thirds of the bytes) then travels
+            # in five pieces while its remaining row blocks are still being computed -- its exchange, which gated everything
+            # behind it (the workers take the chunks in order), ends ~20 us earlier.  Measured per step
+            # (tools/time_dp_segments.py; profiles/r02ac_time_dp8_chunk*.txt, r02ad): 2 GPUs 442.9 (one chunk per matrix) /
+            # 431.4 (7 MB) / 426.1 (5 MB) / 436.4 us (3 MB: every chunk costs a flag round trip and a load-reduce round trip
+            # over NVLink, ~10 us, whatever its size); 8 GPUs 442.9 / 439.6 (11 MB) / 434.5 us (7 MB).
+            target_bytes = int(os.environ.get("NERAF_EXCHANGE_CHUNK_MB", "5")) << 20
 
             # Push form (default): multimem.st of the bf16 sums into every rank's region, then one widening launch.
             # NERAF_EXCHANGE_PULL=1: the pull form -- a rank reduces its slice in place and every rank fetches the other

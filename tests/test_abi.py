@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     exported = sorted(set(re.findall(r" T (neraf_\w+)", out)))
     assert exported == names
     lib = _lib.lib()
-    assert lib.neraf_version() == 8
+    assert lib.neraf_version() == 9
 
 
 def test_ctypes_mirrors_have_the_layout_of_the_header(built):
