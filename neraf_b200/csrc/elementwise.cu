@@ -248,6 +248,47 @@ __global__ void __launch_bounds__(GG_TPB) grid_grads_kernel(const float* __restr
   }
 }
 
+// bf16 -> fp32 widening of the exchanged gradient sums as a launch of its own (data parallel): 16 bytes in, 32 out, four
+// loads in flight per thread, 32 registers -> full occupancy.  neraf_field_grid_grads runs it on the helper stream BESIDE the
+// grid-gradient kernel: fused into that kernel's grid (extra blocks) the two roles shared its 80-register, 3-blocks-per-SM
+// footprint and the launch was latency-bound at 37 us for 130 MB (ncu: 31 % occupancy, DRAM 26 % busy).
+__global__ void __launch_bounds__(256) widen_bf16_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t n8 = n / 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto widen8 = [&](int64_t i, const uint4& raw) {
+    const unsigned int w[4] = {raw.x, raw.y, raw.z, raw.w};
+    float4 lo, hi;
+    lo.x = __uint_as_float(w[0] << 16); lo.y = __uint_as_float(w[0] & 0xffff0000u);
+    lo.z = __uint_as_float(w[1] << 16); lo.w = __uint_as_float(w[1] & 0xffff0000u);
+    hi.x = __uint_as_float(w[2] << 16); hi.y = __uint_as_float(w[2] & 0xffff0000u);
+    hi.z = __uint_as_float(w[3] << 16); hi.w = __uint_as_float(w[3] & 0xffff0000u);
+    __stcs(reinterpret_cast<float4*>(dst) + 2 * i, lo);
+    __stcs(reinterpret_cast<float4*>(dst) + 2 * i + 1, hi);
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n8; i += 4 * stride) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = __ldcs(reinterpret_cast<const uint4*>(src) + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) widen8(i + u * stride, raw[u]);
+  }
+  for (; i < n8; i += stride) widen8(i, __ldcs(reinterpret_cast<const uint4*>(src) + i));
+  if (blockIdx.x == 0)
+    for (int64_t k = n8 * 8 + threadIdx.x; k < n; k += blockDim.x) dst[k] = __bfloat162float(src[k]);
+}
+
+int widen_bf16(const void* src, float* dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return NERAF_OK;
+  NERAF_REQUIRE(src && dst && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "widen_bf16: buffers must be 16-byte aligned");
+  const int64_t want = ceil_div(n, 8 * 256 * 4);
+  const int64_t cap = 8 * (int64_t)sm_count();
+  widen_bf16_kernel<<<(unsigned)std::max<int64_t>(1, std::min(want, cap)), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  NERAF_CHECK_LAUNCH("widen_bf16_kernel");
+  return NERAF_OK;
+}
+
 // scratch: G doubles + one u32 ticket (zero before the first use, left zero)
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
                void* scratch, cudaStream_t stream, const void* compact, int64_t E, int64_t ld_c, bool compact_bf16,

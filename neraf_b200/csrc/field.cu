@@ -706,7 +706,17 @@ extern "C" int neraf_field_grid_grads(const neraf_field_dims* dims, const float*
   if (dims->n_grid <= 0) return NERAF_OK;
   NERAF_REQUIRE(grid_feature && weight0 && dbias0 && (dweight0 || dgrid), "field_grid_grads: null pointer");
   NERAF_REQUIRE(!dgrid || scratch, "field_grid_grads: dgrid needs scratch");
-  return grid_grads(dbias0, grid_feature, weight0, (int64_t)dims->n_grid + dims->n_enc, dims->trunk[0], dims->n_grid, dweight0,
-                    dgrid, scratch, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 8), compact_bf16 != 0,
-                    widen_src_bf16, widen_dst, widen_n);
+  // the widening (28.7 MB -> 57.4 MB, no dependence on db1) runs on the helper stream beside the grid-gradient kernel
+  SideStream* side = (widen_n > 0 && !getenv("NERAF_WIDEN_FUSED")) ? side_stream() : nullptr;
+  if (side) {
+    NERAF_CHECK_CUDA(cudaEventRecord(side->fork, (cudaStream_t)stream));
+    NERAF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    NERAF_TRY(widen_bf16(widen_src_bf16, widen_dst, widen_n, side->stream));
+    NERAF_CHECK_CUDA(cudaEventRecord(side->done, side->stream));
+  }
+  NERAF_TRY(grid_grads(dbias0, grid_feature, weight0, (int64_t)dims->n_grid + dims->n_enc, dims->trunk[0], dims->n_grid, dweight0,
+                       dgrid, scratch, (cudaStream_t)stream, dw0_compact, dims->n_enc, round_up(dims->n_enc, 8), compact_bf16 != 0,
+                       side ? nullptr : widen_src_bf16, side ? nullptr : widen_dst, side ? 0 : widen_n));
+  if (side) NERAF_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, side->done, 0));
+  return NERAF_OK;
 }

@@ -74,6 +74,8 @@ int pack_list(PackList& L, cudaStream_t stream);
 int grid_grads(const float* s, const float* g, const float* W, int64_t ldw, int64_t N, int64_t K, float* dW, float* dg,
                void* scratch, cudaStream_t stream, const void* compact = nullptr, int64_t E = 0, int64_t ld_c = 0,
                bool compact_bf16 = false, const void* widen_src = nullptr, float* widen_dst = nullptr, int64_t widen_n = 0);
+// dst[i] = float(src[i]), bf16 -> fp32, i < n (both 16-byte aligned)
+int widen_bf16(const void* src, float* dst, int64_t n, cudaStream_t stream);
 // out[n] = sum_m X[m*ld + n]   fp32 row-major (M,N)
 int colsum_f32(const float* X, int64_t M, int64_t N, int64_t ld, float* out, cudaStream_t stream);
 struct HeadColsum {
