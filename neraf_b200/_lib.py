@@ -208,7 +208,15 @@ def require_device(t: torch.Tensor, what: str) -> None:
         raise NerafError(f"{what} must live on a CUDA device (got {t.device}); neraf_b200 has no CPU path")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device: Optional[torch.device] = None) -> int:
+    """cudaStream_t of torch's current stream on ``device``.  The raw getter is one C call; going through
+    ``torch.cuda.current_stream(device).cuda_stream`` costs ~7 us of Python per call, four times per eager step."""
+    if _raw_stream is not None:
+        idx = device.index if (device is not None and device.index is not None) else torch.cuda.current_device()
+        return _raw_stream(idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

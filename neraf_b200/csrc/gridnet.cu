@@ -173,6 +173,80 @@ __global__ void __launch_bounds__(kRedCols * kRedLanes) bn_backward_reduce_kerne
   }
 }
 
+// 128-bit forms: a thread owns 8 consecutive channels (one 16-byte load per row and operand).  Thread t of the 256:
+// column group t % groups, row lane t / groups, where groups = min(C / 8, 32) -- for narrow matrices (C = 64: 8 groups) a
+// warp covers four whole rows per load instead of a quarter of its lanes one row; blockIdx.x walks blocks of 256 channels.
+// (The scalar forms read 2 bytes per thread and 64-byte row segments per warp: 19 % of a producer step.)
+constexpr int kRed8Threads = 256;
+struct Red8Shape { int groups, lanes; };
+__device__ __forceinline__ void red8_finish(double (&s)[8], double (&ss)[8], int group, int lane, int lanes, int groups,
+                                            long long c, long long C, double* sums) {
+  __shared__ double sh[16][kRed8Threads];
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sh[k][t] = s[k]; sh[8 + k][t] = ss[k]; }
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    for (int i = 1; i < lanes; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s[k] += sh[k][i * groups + group]; ss[k] += sh[8 + k][i * groups + group]; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(sums + c + k, s[k]);
+      atomicAdd(sums + C + c + k, ss[k]);
+    }
+  }
+}
+__global__ void __launch_bounds__(kRed8Threads) column_sums_vec8_kernel(const bf16_t* x, long long ld, long long V, long long C,
+                                                                        long long rows_per_block, int groups, double* sums) {
+  const int lanes = kRed8Threads / groups;
+  const int group = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const long long c = ((long long)blockIdx.x * groups + group) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < V ? r0 + rows_per_block : V;
+  double s[8], ss[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = 0.0; ss[k] = 0.0; }
+  if (c < C) column_sums_partial8(x, ld, c, r0 + lane, r1, (long long)lanes, s, ss);
+  red8_finish(s, ss, group, lane, lanes, groups, c, C, sums);
+}
+__global__ void __launch_bounds__(kRed8Threads) bn_backward_reduce_vec8_kernel(const bf16_t* dy, const bf16_t* dy2, const bf16_t* y,
+                                                                               const bf16_t* x, long long ld, long long V,
+                                                                               long long C, const float* mean,
+                                                                               const float* invstd, bf16_t* g_out,
+                                                                               long long rows_per_block, int groups,
+                                                                               double* sums) {
+  const int lanes = kRed8Threads / groups;
+  const int group = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const long long c = ((long long)blockIdx.x * groups + group) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < V ? r0 + rows_per_block : V;
+  double s[8], ss[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = 0.0; ss[k] = 0.0; }
+  if (c < C) bn_backward_partial8(dy, dy2, y, x, ld, mean, invstd, g_out, c, r0 + lane, r1, (long long)lanes, s, ss);
+  red8_finish(s, ss, group, lane, lanes, groups, c, C, sums);
+}
+// column groups per block (a divisor of 256, or 0: use the scalar form) and the grid: about four blocks per SM
+static int red8_shape(long long V, long long C, dim3* grid, long long* rows_per_block) {
+  const long long cg = C / 8;
+  int groups = 32;
+  if (cg < 32) {
+    if (cg <= 0 || (cg & (cg - 1)) != 0) return 0;
+    groups = (int)cg;
+  }
+  const int lanes = kRed8Threads / groups;
+  const long long col_blocks = ceil_div(cg, groups);
+  long long row_blocks = ceil_div((long long)sm_count() * 4, col_blocks);
+  if (row_blocks < 1) row_blocks = 1;
+  long long rows = round_up(ceil_div(V, row_blocks), lanes);
+  if (rows < 4 * lanes) rows = 4 * lanes;
+  row_blocks = ceil_div(V, rows);
+  *grid = dim3((unsigned)col_blocks, (unsigned)row_blocks);
+  *rows_per_block = rows;
+  return groups;
+}
+
 // rows per block so that the grid is about four blocks per SM, in multiples of the 8 row lanes
 static long long strip_rows(long long V, long long C, dim3* grid) {
   const long long col_blocks = ceil_div(C, kRedCols);
@@ -295,6 +369,15 @@ extern "C" int neraf_grid_bn_stats(const void* x, int32_t dtype, int64_t V, int6
   cudaStream_t s = (cudaStream_t)stream;
   NERAF_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)(2 * C) * sizeof(double), s));
   dim3 grid;
+  if (allow_vec8() && rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, 8, 8, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) {
+    long long rows8 = 0;
+    const int groups = red8_shape(V, C, &grid, &rows8);
+    if (groups > 0) {
+      column_sums_vec8_kernel<<<grid, kRed8Threads, 0, s>>>((const bf16_t*)x, ld, V, C, rows8, groups, sums);
+      NERAF_CHECK_LAUNCH("column_sums_vec8_kernel");
+      return NERAF_OK;
+    }
+  }
   const long long rows = strip_rows(V, C, &grid);
   if (dtype == NERAF_DT_F32)
     column_sums_kernel<<<grid, kRedCols * kRedLanes, 0, s>>>((const float*)x, ld, V, C, rows, sums);
@@ -349,6 +432,17 @@ extern "C" int neraf_grid_bn_backward_reduce(const void* dy, const void* dy2, co
   cudaStream_t s = (cudaStream_t)stream;
   NERAF_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)(2 * C) * sizeof(double), s));
   dim3 grid;
+  if (allow_vec8() && rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, 8, 8, dy, x, g_out, dy2, y, mean, invstd)) {
+    long long rows8 = 0;
+    const int groups = red8_shape(V, C, &grid, &rows8);
+    if (groups > 0) {
+      bn_backward_reduce_vec8_kernel<<<grid, kRed8Threads, 0, s>>>((const bf16_t*)dy, (const bf16_t*)dy2, (const bf16_t*)y,
+                                                                   (const bf16_t*)x, ld, V, C, mean, invstd, (bf16_t*)g_out,
+                                                                   rows8, groups, sums);
+      NERAF_CHECK_LAUNCH("bn_backward_reduce_vec8_kernel");
+      return NERAF_OK;
+    }
+  }
   const long long rows = strip_rows(V, C, &grid);
   if (dtype == NERAF_DT_F32)
     bn_backward_reduce_kernel<<<grid, kRedCols * kRedLanes, 0, s>>>((const float*)dy, (const float*)dy2, (const float*)y,

@@ -474,6 +474,66 @@ GN_HD void maxpool_backward_vec8_element(const Window& w, const bf16_t* dy, cons
   *reinterpret_cast<vec8_t*>(dx + v * ld_dx + c) = pack8(acc);
 }
 
+// ---- 128-bit forms of the two batch-norm reductions: eight consecutive channels [c, c + 8) of rows r0, r0 + step, ...
+// per call, PER CHANNEL the arithmetic of column_sums_partial / bn_backward_partial (fp32 strips of 64 rows into fp64
+// sums: the same bits for the same (r0, r1, step)).  One 16-byte load per row and operand instead of eight 2-byte ones.
+GN_HD void column_sums_partial8(const bf16_t* x, long long ld, long long c, long long r0, long long r1, long long step,
+                                double* s, double* ss) {
+  double S[8], SS[8];
+  for (int k = 0; k < 8; ++k) { S[k] = 0.0; SS[k] = 0.0; }
+  long long r = r0;
+  while (r < r1) {
+    float a[8], b[8];
+    for (int k = 0; k < 8; ++k) { a[k] = 0.f; b[k] = 0.f; }
+    for (int i = 0; i < 64 && r < r1; ++i, r += step) {
+      float v[8];
+      load8(x + r * ld + c, v);
+      for (int k = 0; k < 8; ++k) { a[k] += v[k]; b[k] = fmaf(v[k], v[k], b[k]); }
+    }
+    for (int k = 0; k < 8; ++k) { S[k] += (double)a[k]; SS[k] += (double)b[k]; }
+  }
+  for (int k = 0; k < 8; ++k) { s[k] = S[k]; ss[k] = SS[k]; }
+}
+
+GN_HD void bn_backward_partial8(const bf16_t* dy, const bf16_t* dy2, const bf16_t* y, const bf16_t* x, long long ld,
+                                const float* mean, const float* invstd, bf16_t* g_out, long long c, long long r0,
+                                long long r1, long long step, double* s_g, double* s_gx) {
+  float m[8], is[8];
+  load8(mean + c, m);
+  load8(invstd + c, is);
+  double S[8], SX[8];
+  for (int k = 0; k < 8; ++k) { S[k] = 0.0; SX[k] = 0.0; }
+  long long r = r0;
+  while (r < r1) {
+    float a[8], b[8];
+    for (int k = 0; k < 8; ++k) { a[k] = 0.f; b[k] = 0.f; }
+    for (int i = 0; i < 64 && r < r1; ++i, r += step) {
+      float g[8], xv[8];
+      load8(dy + r * ld + c, g);
+      if (dy2) {
+        float g2[8];
+        load8(dy2 + r * ld + c, g2);
+        for (int k = 0; k < 8; ++k) g[k] += g2[k];
+      }
+      if (y) {
+        float yv[8];
+        load8(y + r * ld + c, yv);
+        for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) g[k] = 0.f;
+      }
+      const vec8_t stored = pack8(g);
+      *reinterpret_cast<vec8_t*>(g_out + r * ld + c) = stored;
+      unpack8(stored, g);                         // the sums see what the second pass will read
+      load8(x + r * ld + c, xv);
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xv[k] - m[k]) * is[k];
+        a[k] += g[k]; b[k] = fmaf(g[k], xh, b[k]);
+      }
+    }
+    for (int k = 0; k < 8; ++k) { S[k] += (double)a[k]; SX[k] += (double)b[k]; }
+  }
+  for (int k = 0; k < 8; ++k) { s_g[k] = S[k]; s_gx[k] = SX[k]; }
+}
+
 GN_HD void bn_apply_vec8_element(const bf16_t* x, long long ld_x, long long C, const float* mean, const float* invstd,
                                  const float* gamma, const float* beta, const bf16_t* residual, long long ld_res,
                                  int relu, bf16_t* y, long long ld_y, long long idx) {

@@ -71,6 +71,15 @@ HOST_API int gridhost_unpack_wgrad(const float* dw_mat, int64_t ld, int64_t c_ou
 
 HOST_API int gridhost_bn_stats(const void* x, int32_t dtype, int64_t V, int64_t C, int64_t ld, double* sums, void*) {
   memset(sums, 0, sizeof(double) * 2 * C);
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, 8, 8, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) {      // as gridnet.cu
+    for (long long c = 0; c < C; c += 8)
+      for (long long lane = 0; lane < kLanes; ++lane) {
+        double s[8], ss[8];
+        column_sums_partial8((const bf16_t*)x, ld, c, lane, V, kLanes, s, ss);
+        for (int k = 0; k < 8; ++k) { sums[c + k] += s[k]; sums[C + c + k] += ss[k]; }
+      }
+    return 0;
+  }
   for (long long c = 0; c < C; ++c)
     for (long long lane = 0; lane < kLanes; ++lane) {
       double s = 0.0, ss = 0.0;
@@ -113,6 +122,16 @@ HOST_API int gridhost_bn_backward_reduce(const void* dy, const void* dy2, const 
                                          int64_t V, int64_t C, int64_t ld, const float* mean, const float* invstd,
                                          void* g_out, double* sums, void*) {
   memset(sums, 0, sizeof(double) * 2 * C);
+  if (rows_can_vec8(dtype == NERAF_DT_BF16, C, ld, 8, 8, dy, x, g_out, dy2, y, mean, invstd)) {                              // as gridnet.cu
+    for (long long c = 0; c < C; c += 8)
+      for (long long lane = 0; lane < kLanes; ++lane) {
+        double s[8], ss[8];
+        bn_backward_partial8((const bf16_t*)dy, (const bf16_t*)dy2, (const bf16_t*)y, (const bf16_t*)x, ld, mean, invstd,
+                             (bf16_t*)g_out, c, lane, V, kLanes, s, ss);
+        for (int k = 0; k < 8; ++k) { sums[c + k] += s[k]; sums[C + c + k] += ss[k]; }
+      }
+    return 0;
+  }
   for (long long c = 0; c < C; ++c)
     for (long long lane = 0; lane < kLanes; ++lane) {
       double s = 0.0, ss = 0.0;

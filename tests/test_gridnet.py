@@ -416,6 +416,54 @@ def test_16_byte_batchnorm_passes_equal_the_scalar_forms(host_ops):
         assert torch.equal(d_s, d_v)
 
 
+def test_16_byte_batchnorm_reductions_and_pooling_gradient_equal_the_scalar_forms(host_ops):
+    """bn_stats / bn_backward_reduce / maxpool_backward on bf16 rows of whole 16-byte words take the 128-bit forms (eight
+    channels per thread); a buffer 2 bytes off a 16-byte boundary forces the scalar ones.  Same bits: per channel the
+    arithmetic (fp32 strips of 64 rows into fp64 sums; the windows a voxel won, highest first) is the same."""
+    from neraf_b200.gridnet import Window3d
+    g = torch.Generator().manual_seed(13)
+    V, c = 333, 24
+
+    def off(rows, cols=c):              # bf16 view that starts 2 bytes past a 16-byte boundary, row stride cols + 8
+        t = torch.empty(rows * (cols + 8) + 1, dtype=torch.bfloat16)[1:].view(rows, cols + 8)[:, :cols]
+        assert t.data_ptr() % 16 != 0
+        return t
+
+    x = (torch.randn(V, c, generator=g) * 2).bfloat16()
+    x_s = off(V); x_s.copy_(x)
+    s_v, s_s = torch.empty(2, c, dtype=torch.float64), torch.empty(2, c, dtype=torch.float64)
+    host_ops.bn_stats(x, s_v)
+    host_ops.bn_stats(x_s, s_s)
+    assert torch.equal(s_v, s_s)
+    dy, dy2 = torch.randn(V, c, generator=g).bfloat16(), torch.randn(V, c, generator=g).bfloat16()
+    y = torch.relu(torch.randn(V, c, generator=g)).bfloat16()
+    mean, invstd = 0.1 * torch.randn(c, generator=g), 0.5 + torch.rand(c, generator=g)
+    for second, gate in ((dy2, y), (None, y), (None, None)):
+        g_v, g_s = torch.empty(V, c, dtype=torch.bfloat16), off(V)
+        host_ops.bn_backward_reduce(dy, second, gate, x, mean, invstd, g_v, s_v)
+        dy_s, x_o = off(V), off(V)
+        dy_s.copy_(dy); x_o.copy_(x)
+        sec_s = gate_s = None
+        if second is not None:
+            sec_s = off(V); sec_s.copy_(second)
+        if gate is not None:
+            gate_s = off(V); gate_s.copy_(gate)
+        host_ops.bn_backward_reduce(dy_s, sec_s, gate_s, x_o, mean, invstd, g_s, s_s)
+        assert torch.equal(g_v, g_s) and torch.equal(s_v, s_s)
+    # pooling gradient on a (6, 5, 7) grid, 16 channels, with ties (post-ReLU zeros)
+    w = Window3d(6, 5, 7, 16, 3, 2, 1)
+    n_in, od, oh, ow = 6 * 5 * 7, 3, 3, 4
+    xin = torch.relu(torch.randn(n_in, 16, generator=g)).bfloat16()
+    yout, arg = torch.empty(od * oh * ow, 16, dtype=torch.bfloat16), torch.empty(od * oh * ow, 16, dtype=torch.int32)
+    host_ops.maxpool(w, xin, yout, arg)
+    gy, gy2 = torch.randn(od * oh * ow, 16, generator=g).bfloat16(), torch.randn(od * oh * ow, 16, generator=g).bfloat16()
+    for second in (gy2, None):
+        d_v, d_s = torch.empty(n_in, 16, dtype=torch.bfloat16), off(n_in, 16)
+        host_ops.maxpool_backward(w, gy, second, arg, d_v)
+        host_ops.maxpool_backward(w, gy, second, arg, d_s)
+        assert torch.equal(d_v, d_s)
+
+
 def test_reset_grid_is_the_reference_grid():
     """NeRAF_model.py:269-277 restated independently: zeros, voxel-centre coordinates in the last three channels."""
     from neraf_b200.model import NeRAFAudioModel, NeRAFAudioModelConfig
