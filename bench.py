@@ -425,7 +425,7 @@ def main():
                      "frac": achieved / peaks["bf16_tflops_sustained"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of the step's two job-list launches at B=2048 RAF bf16
                      # (ncu --set full, profiles/r01e_mega_ncu_summary.txt: 49.9 MB forward + 172.5 MB backward)
-                     "traffic": 222.4e6 if (B == 2048 and shape.name == "RAF" and args.precision == "bf16") else None,
+                     "traffic": 215.9e6 if (B == 2048 and shape.name == "RAF" and args.precision == "bf16") else None,   # ncu, profiles/r02z_mega_ncu_summary.txt: 45.8 + 170.1 MB
                      "traffic_unit": "bytes per step (both umma_mega_kernel launches)",
                      "kernel": "umma_mega_kernel (job-list tcgen05 kernel: all GEMMs of the step in 3 launches; achieved = 89.54 "
                                "MFLOP/column x columns / whole-step device time, i.e. the non-GEMM kernels of the step are "
@@ -670,9 +670,14 @@ def main():
                 "forward": {"ms": f_ms, "bytes_per_element": 8, "gbs": f_gbs, "frac": f_gbs / peaks["hbm_gbs"]},
                 "backward": {"ms": b_ms, "bytes_per_element": 12, "gbs": b_gbs, "frac": b_gbs / peaks["hbm_gbs"]},
                 "roofline": {"bound": "hbm", "achieved": f_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": f_gbs / peaks["hbm_gbs"], "traffic": None,
+                             "frac": f_gbs / peaks["hbm_gbs"],
+                             # dram__bytes_read + write of one launch (ncu --set full, profiles/r02z_k2_ncu_summary.txt: 269.0 +
+                             # 4.4 MB at 33.6 M elements = the 8 B/element of the algorithm, nothing is read twice)
+                             "traffic": 273.4e6 if (args.loss_columns == 65536 and shape.name == "RAF") else None,
+                             "traffic_backward": 362.4e6 if (args.loss_columns == 65536 and shape.name == "RAF") else None,
                              "note": "neraf_spectral_loss_forward (pred + gt read once, fp64 accumulation), 20 back-to-back "
-                                     "launches on inputs larger than L2; per GPU"}}
+                                     "launches on inputs larger than L2; per GPU; the backward's ncu capture still held 41 MB of "
+                                     "its 134 MB of writes in L2 when it ended"}}
 
     # ---- grid-feature producer: one training-mode forward + backward of ResNet3D-50 on a (1, 7, N, N, N) grid
     if args.grid_net > 0:

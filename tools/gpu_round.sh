@@ -18,3 +18,9 @@ import json
 d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
 print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'], 'e2e_feed', (d.get('e2e_resident_feed') or {}).get('value'), 'e2e_eager', d['e2e_eager']['value'], 'frac', d['roofline']['frac'], 'GL', d['griffinlim']['value'], d['griffinlim']['roofline']['frac'], 'render', d['render']['value'], 'cpu', d['cpu_baseline']['value'], d['clocks'])
 PY
+# K2 at 65 536 columns alone (tools/k2_only.py): ncu --set full of the two loss kernels
+timeout 300 ncu --set full --clock-control none -k regex:'loss_sums_kernel|loss_backward_kernel' -s 4 -c 2 -f -o gpurun_out/k2 python tools/k2_only.py > gpurun_out/ncu_k2.log 2>&1; echo "ncu k2 rc=$?"
+ncu -i gpurun_out/k2.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_summary.py > gpurun_out/k2_ncu_summary.txt
+ncu -i gpurun_out/mega.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_summary.py mega > gpurun_out/mega_ncu_summary.txt
+rm -f gpurun_out/k2.ncu-rep gpurun_out/mega.ncu-rep
+grep -E "^==|time_duration|dram__bytes_read.sum |dram__bytes_write.sum |dram_throughput" gpurun_out/k2_ncu_summary.txt | cut -c1-150
