@@ -31,6 +31,8 @@
 // Flags carry the step number (kept in `state`, advanced by the herald), so nothing is ever reset and a flag that is
 // ahead of a slow reader is still "raised".  Deadlock freedom: the job-list kernel never waits for this kernel; the
 // herald only waits for counters of its own device and for peers that run the same graph.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -72,6 +74,7 @@ struct CommArgs {
   uint8_t* sig[NERAF_MAX_RANKS];
   unsigned int* state;                         // [0] steps completed  [1] worker tickets
   unsigned long long* trace;                   // optional: globaltimer stamps (see neraf_grad_exchange.trace)
+  unsigned int sleep_ns;                       // back-off between polls of a flag / counter
 };
 
 __device__ __forceinline__ unsigned int comm_ld_acquire_gpu(const unsigned int* p) {
@@ -209,7 +212,7 @@ __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
           const long long t0 = clock64();
           for (unsigned int i = 0; i < ch.count; ++i)
             while (!reached(comm_ld_acquire_gpu(ch.notify + i), target)) {
-              __nanosleep(200);
+              __nanosleep(A.sleep_ns);
               if (clock64() - t0 > kCommSpinLimit) __trap();
             }
         }
@@ -224,7 +227,7 @@ __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
       {
         const long long t0 = clock64();
         while (comm_ld_acquire_gpu(A.state + 1) != gridDim.x - 1) {
-          __nanosleep(200);
+          __nanosleep(A.sleep_ns);
           if (clock64() - t0 > kCommSpinLimit) __trap();
         }
       }
@@ -235,7 +238,7 @@ __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
       for (int q = 0; q < A.world; ++q) {
         const long long t0 = clock64();
         while (!reached(comm_ld_acquire_sys(my_sig_done + q), seq)) {
-          __nanosleep(200);
+          __nanosleep(A.sleep_ns);
           if (clock64() - t0 > kCommSpinLimit) __trap();
         }
       }
@@ -257,7 +260,7 @@ __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
       const unsigned int* flag = my_sig_ready + c * NERAF_MAX_RANKS + threadIdx.x;
       const long long t0 = clock64();
       while (!reached(comm_ld_acquire_sys(flag), seq)) {
-        __nanosleep(200);
+        __nanosleep(A.sleep_ns);
         if (clock64() - t0 > kCommSpinLimit) __trap();
       }
     }
@@ -317,7 +320,7 @@ __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
         const unsigned int* flag = reinterpret_cast<const unsigned int*>(A.sig[A.rank] + kReducedOffset) + c * NERAF_MAX_RANKS + threadIdx.x;
         const long long t0 = clock64();
         while (!reached(comm_ld_acquire_sys(flag), seq)) {
-          __nanosleep(100);
+          __nanosleep(A.sleep_ns);
           if (clock64() - t0 > kCommSpinLimit) __trap();
         }
       }
@@ -384,6 +387,10 @@ int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool be
   A.mc = reinterpret_cast<uint8_t*>(x->multicast);
   A.state = x->state;
   A.trace = reinterpret_cast<unsigned long long*>(x->trace);
+  {
+    const char* e = getenv("NERAF_COMM_SLEEP_NS");        // tuning: back-off between polls (default 200 ns)
+    A.sleep_ns = e ? (unsigned int)atoi(e) : 200u;
+  }
   NERAF_REQUIRE(!A.mc || ((uintptr_t)A.mc & 15) == 0, "dp_exchange_grads: misaligned multicast mapping");
   for (int r = 0; r < x->world; ++r) {
     NERAF_REQUIRE(x->peers[r] && x->signals[r], "dp_exchange_grads: region / signal buffer of rank %d is null", r);
