@@ -75,6 +75,7 @@ struct CommArgs {
   unsigned int* state;                         // [0] steps completed  [1] worker tickets
   unsigned long long* trace;                   // optional: globaltimer stamps (see neraf_grad_exchange.trace)
   unsigned int sleep_ns;                       // back-off between polls of a flag / counter
+  int one_fence;
 };
 
 __device__ __forceinline__ unsigned int comm_ld_acquire_gpu(const unsigned int* p) {
@@ -365,9 +366,16 @@ __global__ void __maxnreg__(48) grad_exchange_kernel(const CommArgs A) {
     }
     if (blockIdx.x == 1 && threadIdx.x == 0) comm_stamp(A.trace, 4 + 4 * c + 2);     // block 1 has issued its share of chunk c
   }
-  __threadfence_system();
+  // every store of this block is ordered before its ticket: the barrier orders the block's stores before thread 0, whose
+  // single system fence is cumulative over them (the pattern of a grid-wide barrier, at system scope) -- 128 fences per
+  // block instead cost ~5 us at the end of the kernel (profiles/r02al_*: 431 -> 428 us per step); NERAF_COMM_ONE_FENCE=0
+  // restores a fence per thread
+  if (!A.one_fence) __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(A.state + 1, 1u);
+  if (threadIdx.x == 0) {
+    if (A.one_fence) __threadfence_system();
+    atomicAdd(A.state + 1, 1u);
+  }
 }
 
 }  // namespace neraf
@@ -390,6 +398,8 @@ int dp_exchange_grads(const neraf_grad_exchange* x, cudaStream_t stream, bool be
   {
     const char* e = getenv("NERAF_COMM_SLEEP_NS");        // tuning: back-off between polls (default 200 ns)
     A.sleep_ns = e ? (unsigned int)atoi(e) : 200u;
+    const char* f = getenv("NERAF_COMM_ONE_FENCE");
+    A.one_fence = (f && f[0] == '0') ? 0 : 1;
   }
   NERAF_REQUIRE(!A.mc || ((uintptr_t)A.mc & 15) == 0, "dp_exchange_grads: misaligned multicast mapping");
   for (int r = 0; r < x->world; ++r) {

@@ -847,6 +847,9 @@ class GraphedTrainStep:
             # the bias gradients are final when the dgrad chain ends, the compact dW1 block is the backward's last job
             chunks.append((self._xchg["bias_offset"], self._xchg["bias_bytes"], cnt_off[L + 1], n_cnt[L + 1], 1, 0, 0, 0, 0))
             # compact dW1 block: its sums go straight into columns [n_grid, n_grid + n_enc) of dW1
+            # (the backward's LAST job: whatever of it travels after the last GEMM tile is exposed, so it goes in two halves)
+            tail_bytes = int(float(os.environ.get("NERAF_EXCHANGE_TAIL_MB", "0.9")) * (1 << 20))
+            target_bytes = min(target_bytes, max(tail_bytes, 1 << 16))
             chunks += matrix_chunks(0, offs16[nw], rows[0], ldc * 2, dst=dws[0].data_ptr() + n_grid * 4,
                                     dst_ld=weights[0].shape[1], row_elems=field.in_size - n_grid)
             if len(chunks) > _lib.MAX_EXCHANGE_CHUNKS:
