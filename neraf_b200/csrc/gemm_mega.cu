@@ -249,6 +249,17 @@ struct TileWalk {
 
 __device__ __forceinline__ float gate_factor(float x) { return x > 0.f ? 1.f : kLeakySlope; }
 
+// Epilogue features a job list may need.  The kernel is compiled in a few feature sets (kF) and a launch takes the
+// smallest one that covers its jobs: with every output form in one body the full kernel spills per-tile state (ptxas: 128
+// bytes of stack at 168 registers, 80 bytes at the 152 registers of the beside-variant); the data-parallel backward's set
+// (mask gate, column sums, bf16 outputs only) needs 142 registers and no stack at all.
+enum : int { F_BIAS = 1, F_TANH = 2, F_MASKGATE = 4, F_GATE = 8, F_MASKOUT = 16, F_OUT_F32 = 32, F_OUT_ROWS = 64, F_OUT_MC = 128,
+             F_LOSS = 256, F_COLSUM = 512, F_TRACE = 1024, F_ALL = 2047 };
+constexpr int CFG_FWD = F_BIAS | F_TANH | F_MASKOUT | F_OUT_ROWS;
+constexpr int CFG_BWD = F_MASKGATE | F_COLSUM | F_OUT_F32 | F_OUT_ROWS;
+constexpr int CFG_LEAN = F_MASKGATE | F_COLSUM;
+
+template <int kF>
 __device__ __forceinline__ void mega_body(const MegaParams& P) {
   constexpr int CG = 2;
   // the kernel has no static shared memory, so the dynamic window starts 1024-byte aligned (checked below: the
@@ -365,7 +376,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
         if (J.wait_all) done_jobs |= 1u << J.wait_job;
         if (lane == 0) {
           fence_proxy_async_all();
-          if (is_leader) stamp(P.trace, tile, TR_DEP);
+          if (is_leader) if (kF & F_TRACE) stamp(P.trace, tile, TR_DEP);
           for (int kb = 0; kb < pre; ++kb) {
             load_a(stage, kb);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -383,7 +394,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
           load_b(stage, kb);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (is_leader) stamp(P.trace, tile, TR_LOADED);
+        if (is_leader) if (kF & F_TRACE) stamp(P.trace, tile, TR_LOADED);
       } else {
         for (int kb = kb0; kb < num_kb; ++kb)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -410,11 +421,11 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
         mbar_wait(tmem_empty + as, aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * MEGA_ACC_COLS);
-        stamp(P.trace, tile, TR_MMA_START);
+        if (kF & F_TRACE) stamp(P.trace, tile, TR_MMA_START);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          if (kb == 0) stamp(P.trace, tile, TR_MMA_FIRST);
+          if (kb == 0) if (kF & F_TRACE) stamp(P.trace, tile, TR_MMA_FIRST);
           const uint32_t sa = smem_u32(smem_a + stage * MEGA_A_BYTES);
           const uint32_t sb = smem_u32(smem_b + stage * MEGA_B_BYTES);
           const uint64_t adesc = a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
@@ -426,7 +437,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit<CG>(tmem_full + as);
-        stamp(P.trace, tile, TR_MMA_DONE);
+        if (kF & F_TRACE) stamp(P.trace, tile, TR_MMA_DONE);
       }
     }
     __syncwarp();
@@ -477,11 +488,11 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
       unsigned int w0 = 0, w1 = 0, w2 = 0, w3 = 0;
       auto pre_bias = [&](int jj, float& bj) {
         const int n0 = n_first + 32 * jj;
-        if (jj < nvalid && bias != nullptr && n0 + lane < N) bj = __ldg(bias + n0 + lane);
+        if ((kF & F_BIAS) && jj < nvalid && bias != nullptr && n0 + lane < N) bj = __ldg(bias + n0 + lane);
       };
       auto pre_gate = [&](int jj, unsigned int& wj) {
         const int n0 = n_first + 32 * jj;
-        if (jj < nvalid && gate_mask != nullptr && row_ok) wj = __ldcg(gate_mask + (long long)(n0 >> 5) * ld_mask + m);
+        if ((kF & F_MASKGATE) && jj < nvalid && gate_mask != nullptr && row_ok) wj = __ldcg(gate_mask + (long long)(n0 >> 5) * ld_mask + m);
       };
       pre_bias(0, b0); pre_bias(1, b1); pre_bias(2, b2); pre_bias(3, b3);
 
@@ -489,7 +500,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
       tc_fence_after();
       pre_gate(0, w0); pre_gate(1, w1); pre_gate(2, w2); pre_gate(3, w3);
       const bool tracer = is_leader && warp == 2 && lane == 0;
-      if (tracer) { stamp(P.trace, tile, TR_EPI_START); stamp_clock(P.trace, tile, TR_CK_START); }
+      if (tracer) { if (kF & F_TRACE) stamp(P.trace, tile, TR_EPI_START); if (kF & F_TRACE) stamp_clock(P.trace, tile, TR_CK_START); }
       if (nvalid == 0) {
         tc_fence_before();
         __syncwarp();
@@ -514,14 +525,14 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
           if (nch == 2) tmem_ld_issue(t_addr0 + (uint32_t)(k * 32 + 32), vb);
         }
         // this pair's bias slice -> shared memory (while the TMEM loads are in flight)
-        if (bias != nullptr) {
+        if ((kF & F_BIAS) && bias != nullptr) {
           bias_s[lane] = k == 0 ? b0 : b2;
           bias_s[32 + lane] = k == 0 ? b1 : b3;
           __syncwarp();
         }
         const unsigned int gm0 = k == 0 ? w0 : w2, gm1 = k == 0 ? w1 : w3;
         tmem_ld_wait();
-        if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_LD);
+        if (tracer && k == 0) if (kF & F_TRACE) stamp_clock(P.trace, tile, TR_CK_LD);
         if (k + 2 >= nvalid) {                                    // accumulator fully read: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
@@ -536,7 +547,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
             float* vh = v + 32 * h;
             const int n0h = n0 + 32 * h;
             const bool full_chunk = n0h + 32 <= N;
-            if (bias != nullptr) {
+            if ((kF & F_BIAS) && bias != nullptr) {
               const float4* bs = reinterpret_cast<const float4*>(bias_s + 32 * h);
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -550,15 +561,15 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
               // needs FSETP: both run on the half-rate ALU pipe, which is what bounds this epilogue.
 #pragma unroll
               for (int q = 0; q < 32; ++q) vh[q] = fmaf(0.55f, vh[q], 0.45f * fabsf(vh[q]));
-            } else if (act == NERAF_ACT_TANH10) {
+            } else if ((kF & F_TANH) && act == NERAF_ACT_TANH10) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) vh[q] = 10.f * tanhf(vh[q]);
             }
-            if (gate_mask != nullptr) {
+            if ((kF & F_MASKGATE) && gate_mask != nullptr) {
               const unsigned int gm = h == 0 ? gm0 : gm1;
 #pragma unroll
               for (int q = 0; q < 32; ++q) vh[q] = (gm >> ((q & 1) * 16 + (q >> 1))) & 1u ? kLeakySlope * vh[q] : vh[q];
-            } else if (gate != nullptr && row_ok) {               // generic bf16 gate (not used by the field)
+            } else if ((kF & F_GATE) && gate != nullptr && row_ok) {   // generic bf16 gate (not used by the field)
               const __nv_bfloat16* g = gate + (long long)m * ldg + n0h;
               if (gate_vec_ok && full_chunk) {
 #pragma unroll
@@ -580,7 +591,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
             }
           }
         }
-        if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_MATH);
+        if (tracer && k == 0) if (kF & F_TRACE) stamp_clock(P.trace, tile, TR_CK_MATH);
         if (out_mode == 1) {
           // bf16 row-major through the 4 KB staging tile: a pair is 32 rows of 128 bytes (128-byte swizzle, one TMA
           // store), a single chunk 32 rows of 64 bytes (64-byte swizzle)
@@ -599,7 +610,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
                 const int off = nch == 2 ? lane * 128 + (((h * 4 + i) ^ (lane & 7)) << 4)
                                          : lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
                 *reinterpret_cast<uint4*>(wbuf + off) = pk;
-                if (mask_out != nullptr) {
+                if ((kF & F_MASKOUT) && mask_out != nullptr) {
                   neg = (neg >> 1) | (pk.x & 0x80008000u);
                   neg = (neg >> 1) | (pk.y & 0x80008000u);
                   neg = (neg >> 1) | (pk.z & 0x80008000u);
@@ -608,7 +619,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
               }
               // LeakyReLU keeps the sign and so does the bf16 rounding: the stored activations' sign bits ARE the
               // backward gate (bit set <=> x < 0), one coalesced word per lane in the transposed mask
-              if (mask_out != nullptr && row_ok) mask_out[(long long)((n0 + 32 * h) >> 5) * ld_mask + m] = neg;
+              if ((kF & F_MASKOUT) && mask_out != nullptr && row_ok) mask_out[(long long)((n0 + 32 * h) >> 5) * ld_mask + m] = neg;
             }
           }
           fence_proxy_async_smem();
@@ -617,7 +628,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
             tma_store_2d(nch == 2 ? &J.tmOut : &J.tmOut1, wbuf, n0, m_base);
             bulk_commit();
           }
-        } else if (out_mode == 2) {
+        } else if ((kF & F_OUT_F32) && out_mode == 2) {
           // fp32 row-major: one 32 x 32 tile (128-byte rows, 128-byte swizzle) per chunk
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -636,7 +647,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
               }
             }
           }
-        } else if (out_mode == 3) {
+        } else if ((kF & F_OUT_ROWS) && out_mode == 3) {
           // rows that TMA cannot tile (e.g. (B, 513) fp32 outputs): transpose through the staging tile
           // (XOR-swizzled 32 x 32 floats, conflict-free both ways) so that lanes write consecutive columns
           float* out_f32 = J.out_f32;
@@ -652,7 +663,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
               __syncwarp();
               const int n = n0 + 32 * h + lane;
               if (n < N) {
-                if (loss_gt == nullptr) {
+                if (!(kF & F_LOSS) || loss_gt == nullptr) {
 #pragma unroll 4
                   for (int r = 0; r < rows; ++r) out_f32[(long long)(m_base + r) * ld_f32 + n] = wbuf_f[r * 32 + (lane ^ r)];
                 } else {
@@ -676,7 +687,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
               __syncwarp();
             }
           }
-          if (loss_gt != nullptr) {
+          if ((kF & F_LOSS) && loss_gt != nullptr) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
               s_num += __shfl_xor_sync(FULL_MASK, s_num, o);
@@ -692,7 +703,7 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
             }
           }
         }
-        else if (out_mode == 4) {
+        else if ((kF & F_OUT_MC) && out_mode == 4) {
           // Fused all-reduce: the tile is ADDED into every rank's copy of the gradient by the NVSwitch
           // (multimem.red on the multicast alias of the output; NVLS).  Same shared-memory transpose as above so
           // that one instruction covers 128 contiguous bytes of a row.
@@ -735,9 +746,9 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
             }
           }
         }
-        if (tracer && k == 0) stamp_clock(P.trace, tile, TR_CK_STORE);
+        if (tracer && k == 0) if (kF & F_TRACE) stamp_clock(P.trace, tile, TR_CK_STORE);
         // ---- bias gradient: column sums of the fp32 values (destroys v)
-        if (colsum != nullptr) {
+        if ((kF & F_COLSUM) && colsum != nullptr) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h < nch) {
@@ -752,14 +763,14 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
           }
         }
       }
-      if (tracer) { stamp_clock(P.trace, tile, TR_CK_LOOP); stamp(P.trace, tile, TR_EPI_STORED); }
+      if (tracer) { if (kF & F_TRACE) stamp_clock(P.trace, tile, TR_CK_LOOP); if (kF & F_TRACE) stamp(P.trace, tile, TR_EPI_STORED); }
       // Publish the tile: lane 0 waits until its TMA stores have been performed, the warp's plain stores (bit mask,
       // unaligned fp32 rows, column-sum atomics) are ordered before lane 0 by the warp barrier, and the counter
       // update itself is a gpu-scope release (one fence instead of a full membar in every lane).
       if (lane == 0 && (out_mode == 1 || out_mode == 2)) { bulk_wait_all0(); fence_proxy_async_all(); }
       if (out_mode == 4) used_multicast = true;      // fenced once, at the end of the kernel
       __syncwarp();
-      if (tracer) { stamp_clock(P.trace, tile, TR_CK_FENCE); stamp(P.trace, tile, TR_EPI_DONE); }
+      if (tracer) { if (kF & F_TRACE) stamp_clock(P.trace, tile, TR_CK_FENCE); if (kF & F_TRACE) stamp(P.trace, tile, TR_EPI_DONE); }
       if (lane == 0) {
         red_release_add(P.counters + J.cnt_off + mt, 1u);   // ... before the row block's progress is (16 arrivals per tile)
         if (J.notify != nullptr) red_release_add(J.notify + mt, 1u);
@@ -789,14 +800,17 @@ __device__ __forceinline__ void mega_body(const MegaParams& P) {
   }
 }
 
-__global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) { mega_body(P); }
+__global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel(const __grid_constant__ MegaParams P) { mega_body<F_ALL>(P); }
+__global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel_fwd(const __grid_constant__ MegaParams P) { mega_body<CFG_FWD>(P); }
+__global__ void __launch_bounds__(MEGA_THREADS, 1) umma_mega_kernel_bwd(const __grid_constant__ MegaParams P) { mega_body<CFG_BWD>(P); }
 
 // The same kernel held to 152 registers per thread, for launches that another kernel must be able to sit BESIDE (the
 // data-parallel gradient exchange).  Registers are handed out per SM sub-partition: this CTA's 10 warps land 3/3/2/2 on
 // the four partitions, and with 160+ registers per thread the two partitions that hold three warps have no room left
 // for a single warp of any other CTA -- measured (tools/micro/pdl_beside.cu): beside 320 threads x 159 registers NOTHING
 // becomes resident, beside 320 x 151 a 128-thread x 48-register CTA does.
-__global__ void __maxnreg__(152) umma_mega_kernel_slim(const __grid_constant__ MegaParams P) { mega_body(P); }
+__global__ void __maxnreg__(152) umma_mega_kernel_slim(const __grid_constant__ MegaParams P) { mega_body<F_ALL>(P); }
+__global__ void __maxnreg__(152) umma_mega_kernel_slim_lean(const __grid_constant__ MegaParams P) { mega_body<CFG_LEAN>(P); }
 
 }  // namespace umma
 
@@ -1013,13 +1027,33 @@ int mega_run(const MegaJob* jobs, int n_jobs, void* counters, size_t counters_by
   int dev = 0;
   NERAF_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    for (auto kern : {umma_mega_kernel, umma_mega_kernel_slim}) {
+    for (auto kern : {umma_mega_kernel, umma_mega_kernel_fwd, umma_mega_kernel_bwd, umma_mega_kernel_slim, umma_mega_kernel_slim_lean}) {
       NERAF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
       NERAF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     configured[dev] = true;
   }
-  auto kernel = release_dependents_early ? umma_mega_kernel_slim : umma_mega_kernel;
+  // feature set of this job list -> kernel variant
+  int need = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const DeviceJob& d = P.jobs[i];
+    if (d.bias) need |= F_BIAS;
+    if (d.act == NERAF_ACT_TANH10) need |= F_TANH;
+    if (d.gate_mask) need |= F_MASKGATE;
+    if (d.gate) need |= F_GATE;
+    if (d.mask_out) need |= F_MASKOUT;
+    if (d.out_mode == 2) need |= F_OUT_F32;
+    if (d.out_mode == 3) need |= F_OUT_ROWS;
+    if (d.out_mode == 4) need |= F_OUT_MC;
+    if (d.loss_gt) need |= F_LOSS;
+    if (d.colsum) need |= F_COLSUM;
+  }
+  if (trace_path) need |= F_TRACE;                   // the per-tile timeline lives in the full kernel only
+  static const bool variants = getenv("NERAF_MEGA_VARIANTS") == nullptr || getenv("NERAF_MEGA_VARIANTS")[0] != '0';
+  auto covers = [&](int cfg) { return variants && (need & ~cfg) == 0; };
+  auto kernel = release_dependents_early ? (covers(CFG_LEAN) ? umma_mega_kernel_slim_lean : umma_mega_kernel_slim)
+                                         : (covers(CFG_FWD) ? umma_mega_kernel_fwd
+                                                            : (covers(CFG_BWD) ? umma_mega_kernel_bwd : umma_mega_kernel));
   int units = sm_count() / 2;
   if (max_ctas >= 2 && max_ctas / 2 < units) units = max_ctas / 2;   // leave SMs to a concurrent kernel (collectives)
   cudaLaunchConfig_t cfg = {};
