@@ -425,7 +425,7 @@ def main():
                      "frac": achieved / peaks["bf16_tflops_sustained"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of the step's two job-list launches at B=2048 RAF bf16
                      # (ncu --set full, profiles/r01e_mega_ncu_summary.txt: 49.9 MB forward + 172.5 MB backward)
-                     "traffic": 215.9e6 if (B == 2048 and shape.name == "RAF" and args.precision == "bf16") else None,   # ncu, profiles/r02z_mega_ncu_summary.txt: 45.8 + 170.1 MB
+                     "traffic": 209.2e6 if (B == 2048 and shape.name == "RAF" and args.precision == "bf16") else None,   # ncu, profiles/r02ap_mega_ncu_summary_variants.txt: 44.7 + 164.5 MB
                      "traffic_unit": "bytes per step (both umma_mega_kernel launches)",
                      "kernel": "umma_mega_kernel (job-list tcgen05 kernel: all GEMMs of the step in 3 launches; achieved = 89.54 "
                                "MFLOP/column x columns / whole-step device time, i.e. the non-GEMM kernels of the step are "
